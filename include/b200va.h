@@ -1,0 +1,237 @@
+/*
+ * b200va.h -- C ABI of the B200-native video-analytics hot path (libb200va.so).
+ *
+ * Drop-in boundary for the per-frame data-parallel path of
+ * skygazer42/realtime-video-analytics-32streams.  Every entry point cites the reference
+ * interface it replaces (paths relative to the reference root).  The reference is pure
+ * Python; a maintainer binds these with ctypes behind the reference's
+ * own classes/functions, so the YAML config keeps working.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no C++/torch types.
+ *   - Pointers marked DEVICE point to CUDA device memory on the handle's device; pointers
+ *     marked HOST are ordinary host memory read synchronously during the call (they are
+ *     small per-frame descriptors, never pixel data).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work
+ *     is enqueued asynchronously on it; nothing synchronises unless stated.
+ *   - Return value: 0 = B200VA_OK, negative = error (b200va_error_string).  Nothing throws.
+ *     b200va_last_error(handle) returns a detailed message for the last failing call.
+ *   - No hidden device allocation after b200va_create(): all scratch and all tracker state
+ *     are carved from arenas sized by b200va_config.
+ *   - There is NO CPU fallback: every compute entry point launches sm_100a kernels.
+ */
+#ifndef B200VA_H_
+#define B200VA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VA_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define B200VA_API __attribute__((visibility("default")))
+#else
+#define B200VA_API
+#endif
+
+enum b200va_status {
+  B200VA_OK = 0,
+  B200VA_ERR_INVALID = -1,  /* bad argument */
+  B200VA_ERR_CUDA = -2,     /* a CUDA runtime call failed; see b200va_last_error */
+  B200VA_ERR_CAPACITY = -3, /* a configured capacity (batch, candidates, tracks...) was exceeded */
+  B200VA_ERR_STATE = -4     /* call order violated (e.g. pending track ids not assigned) */
+};
+
+/* Output tensor formats of b200va_preprocess. */
+enum b200va_out_format {
+  B200VA_OUT_F32_RGB_NCHW = 0, /* detector.py:245-257, half=False: float32, RGB planes, x*(1/255)        */
+  B200VA_OUT_F16_RGB_NCHW = 1, /* detector.py:248-251, half=True : float16(x) * float16(1/255)           */
+  B200VA_OUT_U8_BGR_NCHW = 2,  /* detector.py:777-839 RKNN variant, use_nhwc=False: letterboxed BGR uint8  */
+  B200VA_OUT_U8_BGR_NHWC = 3   /* detector.py:777-839 RKNN variant, use_nhwc=True; also plain resize       */
+};
+
+/* Head tensor layouts accepted by b200va_postprocess (detector.py:278-283 transposes
+ * [C,A] exports to [A,C]; both are read in place here, no transpose pass). */
+enum b200va_head_layout {
+  B200VA_HEAD_CHANNEL_MAJOR = 0, /* [B, C, A]  e.g. YOLOv8 [B,84,8400]   */
+  B200VA_HEAD_ANCHOR_MAJOR = 1   /* [B, A, C]  e.g. YOLOv5 [B,25200,85]  */
+};
+
+/* Scoring rule.  REF_COMPAT is what detector.py:294-307 computes for BOTH model types:
+ * C>5: score_k = head[5+k] * head[4];  C==5: score_0 = head[4]. */
+enum b200va_score_mode { B200VA_SCORE_REF_COMPAT = 0 };
+
+typedef struct b200va_ctx* b200va_handle;
+
+typedef struct b200va_config {
+  int device;         /* CUDA device ordinal                                                     */
+  int max_batch;      /* frames per call (<= 128)                                                */
+  int max_anchors;    /* A upper bound (8400 for 640x640 YOLOv8, 25200 for YOLOv5; <= 262144)    */
+  int max_candidates; /* per-frame candidates surviving the confidence filter (<= 8192)          */
+  int max_dets;       /* per-frame detections kept after NMS (output row capacity)               */
+  int max_streams;    /* tracker stream slots (<= 4096)                                          */
+  int max_tracks;     /* live tracks per stream slot (<= 5600)                                   */
+} b200va_config;
+
+/* Letterbox geometry, the `meta` dict of detector.py:259-263 plus the resized size. */
+typedef struct b200va_letterbox {
+  int src_h, src_w; /* meta["orig_shape"]                            */
+  int new_h, new_w; /* int(h*scale), int(w*scale)  (detector.py:214) */
+  int pad_left, pad_top; /* meta["pad"]                              */
+  double scale;     /* meta["scale"] (float64)                       */
+} b200va_letterbox;
+
+/* Detections, structure-of-arrays, row-major [batch, max_dets].  DEVICE pointers.
+ * Mirrors Detection(class_id, confidence, bbox_xyxy) of detector.py:32-40. */
+typedef struct b200va_dets {
+  float* bbox_xyxy; /* [B, max_dets, 4] float32 (frame pixels)  */
+  float* conf;      /* [B, max_dets]                            */
+  int32_t* cls;     /* [B, max_dets]                            */
+  int32_t* count;   /* [B]                                      */
+} b200va_dets;
+
+/* Float64 detections for callers that hold Python-float Detection objects (tracker.py:50 takes
+ * arbitrary doubles).  Same layout as b200va_dets with double boxes / confidences. */
+typedef struct b200va_dets64 {
+  const double* bbox_xyxy; /* [B, max_dets, 4] */
+  const double* conf;      /* [B, max_dets]    */
+  const int32_t* cls;      /* [B, max_dets]    */
+  const int32_t* count;    /* [B]              */
+} b200va_dets64;
+
+/* Tracker parameters, TrackerConfig of config.py:194-209. */
+typedef struct b200va_tracker_cfg {
+  int max_age;
+  int min_hits;
+  double max_iou_distance;
+} b200va_tracker_cfg;
+
+/* Track rows, structure-of-arrays [batch, max_tracks].  DEVICE pointers.
+ * Mirrors Track(track_id, class_id, confidence, bbox_xyxy, age, hits) of tracker.py:18-33. */
+typedef struct b200va_tracks {
+  int64_t* track_id; /* [B, max_tracks] */
+  int32_t* cls;      /* [B, max_tracks] */
+  double* conf;      /* [B, max_tracks] */
+  double* bbox_xyxy; /* [B, max_tracks, 4] */
+  int32_t* age;      /* [B, max_tracks] */
+  int32_t* hits;     /* [B, max_tracks] */
+  int32_t* count;    /* [B] */
+} b200va_tracks;
+
+/* ---- library ------------------------------------------------------------------------ */
+B200VA_API int b200va_version(void);
+B200VA_API const char* b200va_error_string(int status);
+B200VA_API int b200va_create(const b200va_config* cfg, b200va_handle* out);
+B200VA_API int b200va_destroy(b200va_handle h);
+B200VA_API const char* b200va_last_error(b200va_handle h);
+/* Number of kernels this handle has launched since creation (for launch accounting). */
+B200VA_API int64_t b200va_launch_count(b200va_handle h);
+/* Kernels never block on capacity problems; they raise device-side flags instead.  This call
+ * synchronises `stream`, returns B200VA_ERR_CAPACITY (and clears the flags) if any frame since the
+ * last poll exceeded max_candidates / max_dets / max_tracks (the surplus rows were dropped), else
+ * B200VA_OK.  The reference has no such limits; size the config so that this never fires. */
+B200VA_API int b200va_poll_status(b200va_handle h, void* stream);
+
+/* ---- a1: letterbox preprocess --------------------------------------------------------
+ * Replaces _TensorRTBaseDetector._preprocess (detector.py:198-264) and
+ * RKNNDetector._preprocess (detector.py:777-839) for a batch of frames.
+ * Host-only geometry helper: fills `out` exactly like detector.py:209-230. */
+B200VA_API int b200va_letterbox_meta(int src_h, int src_w, int dst_h, int dst_w, b200va_letterbox* out);
+
+/* frames    HOST array [batch] of DEVICE pointers to BGR uint8 HWC frames
+ * src_h/w   HOST [batch]; src_pitch HOST [batch] row pitch in bytes (>= 3*w)
+ * roi_masks HOST array [batch] of DEVICE pointers to uint8 [src_h, src_w] masks (0 = outside),
+ *           entries may be NULL; the array itself may be NULL.  Fuses apply_roi
+ *           (frame_filter.py:43-50) into the resize taps.
+ * out       DEVICE tensor [batch, 3, dst_h, dst_w] (NCHW formats) or [batch, dst_h, dst_w, 3]
+ * meta_out  HOST [batch], may be NULL */
+B200VA_API int b200va_preprocess(b200va_handle h, const uint8_t* const* frames, const int* src_h, const int* src_w,
+                      const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks, void* out,
+                      int dst_h, int dst_w, int out_format, b200va_letterbox* meta_out, void* stream);
+
+/* ---- a10: downsample -----------------------------------------------------------------
+ * Replaces utils.downsample (frame_filter.py:53-57): cv2.resize INTER_LINEAR, BGR uint8 HWC in,
+ * BGR uint8 HWC out (dst pitch = 3*dst_w).  dst HOST array [batch] of DEVICE pointers.
+ * roi_masks as in b200va_preprocess (may be NULL): the reference applies the ROI to the full
+ * frame BEFORE downsampling (pipeline.py:149-154), so the mask is fused into the taps here too. */
+B200VA_API int b200va_resize_linear_u8(b200va_handle h, const uint8_t* const* frames, const int* src_h, const int* src_w,
+                            const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks,
+                            uint8_t* const* dst, const int* dst_h, const int* dst_w, void* stream);
+
+/* ---- a9: ROI polygons ----------------------------------------------------------------
+ * Replaces the mask construction of utils.apply_roi (frame_filter.py:46-49): one cv2.fillPoly
+ * per polygon (LINE_8, shift 0), union.  pts HOST [sum(poly_sizes), 2] int32 (x, y);
+ * poly_sizes HOST [n_polys]; mask_out DEVICE uint8 [h, w] (255 inside, 0 outside). */
+B200VA_API int b200va_roi_rasterize(b200va_handle h, const int32_t* pts, const int* poly_sizes, int n_polys, int height,
+                         int width, uint8_t* mask_out, void* stream);
+/* Replaces cv2.bitwise_and(frame, frame, mask=mask) (frame_filter.py:50): dst = mask ? src : 0. */
+B200VA_API int b200va_apply_mask(b200va_handle h, const uint8_t* src, int64_t src_pitch, const uint8_t* mask, int height,
+                      int width, uint8_t* dst, int64_t dst_pitch, void* stream);
+
+/* ---- a11: motion filter --------------------------------------------------------------
+ * Replaces MotionFilter.should_process (frame_filter.py:26-40) for a batch:
+ * BGR2GRAY -> GaussianBlur 5x5 -> |new - prev| > 25 -> count; always stores the new blurred gray.
+ * prev_gray    HOST array [batch] of DEVICE uint8 [h, w] state buffers (read, unless has_prev==0)
+ * next_gray    HOST array [batch] of DEVICE uint8 [h, w] buffers receiving the new state
+ *              (must differ from prev_gray[i]: the stencil reads neighbours)
+ * has_prev     HOST [batch]; 0 = first frame of the stream (count is written as -1)
+ * changed_out  DEVICE int32 [batch]: number of pixels with |diff| > 25
+ * The caller decides `count / (h*w) >= threshold` in float64 (frame_filter.py:38-40). */
+B200VA_API int b200va_motion(b200va_handle h, const uint8_t* const* frames, const int* src_h, const int* src_w,
+                  const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks,
+                  const uint8_t* const* prev_gray, uint8_t* const* next_gray, const int* has_prev,
+                  int32_t* changed_out, void* stream);
+
+/* ---- a3-a7: head post-process --------------------------------------------------------
+ * Replaces _TensorRTBaseDetector._postprocess (detector.py:266-338), _xywh2xyxy (:352-359),
+ * _scale_boxes (:340-350), _nms (:361-375) + _iou (:469-481), and folds in
+ * filter_detections (detector.py:99-103, called at pipeline.py:182) when use_filter != 0:
+ * kept boxes whose float64 confidence is below filter_conf_thr_f64 still suppress others but
+ * are not emitted.
+ * head       DEVICE float32, layout per `layout`; B frames, C channels, A anchors
+ * meta       HOST [batch] letterbox geometry of each frame
+ * conf_thr / iou_thr  the Python floats of DetectorConfig; rounded to float32 exactly where
+ *            NumPy does (detector.py:312, :373)
+ * classes    HOST int32 [n_classes] whitelist (detector.py:313-314) or NULL
+ * out        kept detections in keep order (score descending), at most max_dets per frame
+ * Equal scores are ordered higher-candidate-index first (stable argsort reversed). */
+B200VA_API int b200va_postprocess(b200va_handle h, const float* head, int layout, int batch, int channels, int anchors,
+                       const b200va_letterbox* meta, double conf_thr, double iou_thr, const int32_t* classes,
+                       int n_classes, int score_mode, double filter_conf_thr_f64, int use_filter,
+                       const b200va_dets* out, void* stream);
+
+/* ---- a8: IoU tracker -----------------------------------------------------------------
+ * Replaces IouTracker.update (tracker.py:50-95), _match_detection (:97-109), _prune_tracks
+ * (:111-126), _iou (:129-147) for a batch of streams; state lives in the handle per slot.
+ * stream_slots HOST [batch] slot ids in [0, max_streams), distinct within a call
+ * dets         detections per frame ([batch, max_dets] SoA as produced by b200va_postprocess);
+ *              det_scale HOST double [batch] or NULL: pipeline.py:224-240 rescale (1/ratio), applied
+ *              in float64 to the boxes before matching
+ * skip         HOST uint8 [batch] or NULL: 1 = tracker.update(stream, []) (pipeline.py:214-215)
+ * id_base      HOST int64 [batch] or NULL.  New tracks get ids id_base[i], id_base[i]+1, ... in
+ *              creation order; NULL = draw from the handle's shared counter in batch order,
+ *              which reproduces one shared itertools.count(1) updated stream by stream
+ *              (tracker.py:47, pipeline.py:452)
+ * out          all surviving tracks per stream in insertion order (tracker.py:95), may be NULL
+ * new_counts   DEVICE int32 [batch] number of tracks created by this call, may be NULL */
+B200VA_API int b200va_tracker_update(b200va_handle h, const int* stream_slots, int batch, const b200va_dets* dets,
+                          int max_dets, const double* det_scale, const uint8_t* skip,
+                          const b200va_tracker_cfg* cfg, const int64_t* id_base, const b200va_tracks* out,
+                          int32_t* new_counts, void* stream);
+/* Same, for float64 detections (no det_scale: the caller already holds final doubles). */
+B200VA_API int b200va_tracker_update_f64(b200va_handle h, const int* stream_slots, int batch, const b200va_dets64* dets,
+                              int max_dets, const uint8_t* skip, const b200va_tracker_cfg* cfg,
+                              const int64_t* id_base, const b200va_tracks* out, int32_t* new_counts,
+                              void* stream);
+B200VA_API int b200va_tracker_reset(b200va_handle h, int stream_slot, void* stream);
+/* Set the next id of the shared counter (default 1, like itertools.count(1)). */
+B200VA_API int b200va_tracker_set_next_id(b200va_handle h, int64_t next_id, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VA_H_ */

@@ -1,0 +1,355 @@
+"""ctypes binding of ``libb200va.so`` (C ABI declared in ``include/b200va.h``).
+
+The shared library is the product: every compute entry point launches sm_100a kernels and
+there is no Python/NumPy/torch fallback.  If the library is missing or fails to load this module
+raises at import of the first symbol -- it never degrades silently.  PyTorch appears only as the
+owner of device memory and CUDA streams; tensors are passed down as raw pointers.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "lib", "libb200va.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
+OUT_F32_RGB_NCHW, OUT_F16_RGB_NCHW, OUT_U8_BGR_NCHW, OUT_U8_BGR_NHWC = 0, 1, 2, 3
+HEAD_CHANNEL_MAJOR, HEAD_ANCHOR_MAJOR = 0, 1
+SCORE_REF_COMPAT = 0
+
+
+class B200VAError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libb200va: {message} (status {status})")
+        self.status = status
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("max_batch", C.c_int), ("max_anchors", C.c_int), ("max_candidates", C.c_int),
+                ("max_dets", C.c_int), ("max_streams", C.c_int), ("max_tracks", C.c_int)]
+
+
+class Letterbox(C.Structure):
+    _fields_ = [("src_h", C.c_int), ("src_w", C.c_int), ("new_h", C.c_int), ("new_w", C.c_int),
+                ("pad_left", C.c_int), ("pad_top", C.c_int), ("scale", C.c_double)]
+
+    def as_meta(self) -> dict:
+        """The ``meta`` dict of detector.py:259-263."""
+        return {"orig_shape": (self.src_h, self.src_w), "scale": self.scale, "pad": (self.pad_left, self.pad_top)}
+
+
+class Dets(C.Structure):
+    _fields_ = [("bbox_xyxy", C.c_void_p), ("conf", C.c_void_p), ("cls", C.c_void_p), ("count", C.c_void_p)]
+
+
+class Dets64(C.Structure):
+    _fields_ = [("bbox_xyxy", C.c_void_p), ("conf", C.c_void_p), ("cls", C.c_void_p), ("count", C.c_void_p)]
+
+
+class TrackerCfg(C.Structure):
+    _fields_ = [("max_age", C.c_int), ("min_hits", C.c_int), ("max_iou_distance", C.c_double)]
+
+
+class Tracks(C.Structure):
+    _fields_ = [("track_id", C.c_void_p), ("cls", C.c_void_p), ("conf", C.c_void_p), ("bbox_xyxy", C.c_void_p),
+                ("age", C.c_void_p), ("hits", C.c_void_p), ("count", C.c_void_p)]
+
+
+EXPORTS = (
+    "b200va_version", "b200va_error_string", "b200va_create", "b200va_destroy", "b200va_last_error",
+    "b200va_launch_count", "b200va_poll_status", "b200va_letterbox_meta", "b200va_preprocess",
+    "b200va_resize_linear_u8", "b200va_roi_rasterize", "b200va_apply_mask", "b200va_motion",
+    "b200va_postprocess", "b200va_tracker_update", "b200va_tracker_update_f64", "b200va_tracker_reset",
+    "b200va_tracker_set_next_id",
+)
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load ``libb200va.so``; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m realtime_video_analytics_32streams_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, ip, i64p = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int64)
+    lib.b200va_version.restype = C.c_int
+    lib.b200va_error_string.restype = C.c_char_p
+    lib.b200va_error_string.argtypes = [C.c_int]
+    lib.b200va_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    lib.b200va_destroy.argtypes = [vp]
+    lib.b200va_last_error.restype = C.c_char_p
+    lib.b200va_last_error.argtypes = [vp]
+    lib.b200va_launch_count.restype = C.c_int64
+    lib.b200va_launch_count.argtypes = [vp]
+    lib.b200va_poll_status.argtypes = [vp, vp]
+    lib.b200va_letterbox_meta.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Letterbox)]
+    lib.b200va_preprocess.argtypes = [vp, C.POINTER(vp), ip, ip, i64p, C.c_int, C.POINTER(vp), vp, C.c_int, C.c_int,
+                                      C.c_int, C.POINTER(Letterbox), vp]
+    lib.b200va_resize_linear_u8.argtypes = [vp, C.POINTER(vp), ip, ip, i64p, C.c_int, C.POINTER(vp), C.POINTER(vp),
+                                            ip, ip, vp]
+    lib.b200va_roi_rasterize.argtypes = [vp, C.POINTER(C.c_int32), ip, C.c_int, C.c_int, C.c_int, vp, vp]
+    lib.b200va_apply_mask.argtypes = [vp, vp, C.c_int64, vp, C.c_int, C.c_int, vp, C.c_int64, vp]
+    lib.b200va_motion.argtypes = [vp, C.POINTER(vp), ip, ip, i64p, C.c_int, C.POINTER(vp), C.POINTER(vp),
+                                  C.POINTER(vp), ip, vp, vp]
+    lib.b200va_postprocess.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Letterbox), C.c_double,
+                                       C.c_double, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_double, C.c_int,
+                                       C.POINTER(Dets), vp]
+    lib.b200va_tracker_update.argtypes = [vp, ip, C.c_int, C.POINTER(Dets), C.c_int, C.POINTER(C.c_double),
+                                          C.POINTER(C.c_uint8), C.POINTER(TrackerCfg), i64p, C.POINTER(Tracks), vp, vp]
+    lib.b200va_tracker_update_f64.argtypes = [vp, ip, C.c_int, C.POINTER(Dets64), C.c_int, C.POINTER(C.c_uint8),
+                                              C.POINTER(TrackerCfg), i64p, C.POINTER(Tracks), vp, vp]
+    lib.b200va_tracker_reset.argtypes = [vp, C.c_int, vp]
+    lib.b200va_tracker_set_next_id.argtypes = [vp, C.c_int64, vp]
+    for name in EXPORTS:
+        getattr(lib, name)  # AttributeError here = header / library mismatch
+    _lib = lib
+    return lib
+
+
+def letterbox_meta(src_h: int, src_w: int, dst_h: int, dst_w: int) -> Letterbox:
+    """Host-only geometry helper (detector.py:209-230); needs no GPU."""
+    m = Letterbox()
+    rc = load_library().b200va_letterbox_meta(src_h, src_w, dst_h, dst_w, C.byref(m))
+    if rc != OK:
+        raise B200VAError(rc, f"bad letterbox geometry {src_w}x{src_h} -> {dst_w}x{dst_h}")
+    return m
+
+
+def _ptr_array(ptrs: Sequence[Optional[int]]):
+    return (C.c_void_p * len(ptrs))(*[C.c_void_p(p) if p else None for p in ptrs])
+
+
+def _int_array(vals: Sequence[int]):
+    return (C.c_int * len(vals))(*[int(v) for v in vals])
+
+
+class Handle:
+    """One ``b200va_handle``: scratch arenas + tracker state on one GPU."""
+
+    def __init__(self, device: int = 0, max_batch: int = 32, max_anchors: int = 8400, max_candidates: int = 4096,
+                 max_dets: int = 1024, max_streams: int = 64, max_tracks: int = 4096):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("libb200va needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.cfg = Config(device, max_batch, max_anchors, max_candidates, max_dets, max_streams, max_tracks)
+        self._h = C.c_void_p()
+        rc = self.lib.b200va_create(C.byref(self.cfg), C.byref(self._h))
+        if rc != OK:
+            raise B200VAError(rc, (self.lib.b200va_last_error(None) or b"create failed").decode())
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.b200va_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> None:
+        if rc != OK:
+            raise B200VAError(rc, (self.lib.b200va_last_error(self._h) or b"").decode())
+
+    def _stream(self) -> C.c_void_p:
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.b200va_launch_count(self._h))
+
+    def poll_status(self) -> None:
+        """Synchronise and raise if any capacity limit was hit since the last poll."""
+        self._check(self.lib.b200va_poll_status(self._h, self._stream()))
+
+    def _frame_args(self, frames):
+        t = self.torch
+        for f in frames:
+            if not (f.is_cuda and f.dtype == t.uint8 and f.dim() == 3 and f.shape[2] == 3 and f.stride(2) == 1
+                    and f.stride(1) == 3):
+                raise ValueError("frames must be CUDA uint8 tensors [H, W, 3] with packed pixels")
+        ptrs = _ptr_array([f.data_ptr() for f in frames])
+        hs = _int_array([f.shape[0] for f in frames])
+        ws = _int_array([f.shape[1] for f in frames])
+        pitch = (C.c_int64 * len(frames))(*[f.stride(0) for f in frames])
+        return ptrs, hs, ws, pitch
+
+    def _mask_args(self, masks, frames):
+        if masks is None or all(m is None for m in masks):
+            return None
+        t = self.torch
+        for m, f in zip(masks, frames):
+            if m is not None and not (m.is_cuda and m.dtype == t.uint8 and m.is_contiguous()
+                                      and tuple(m.shape) == tuple(f.shape[:2])):
+                raise ValueError("roi masks must be contiguous CUDA uint8 tensors [H, W] matching their frame")
+        return _ptr_array([m.data_ptr() if m is not None else None for m in masks])
+
+    # -- a1 ---------------------------------------------------------------------------------
+    def preprocess(self, frames, dst_hw=(640, 640), fmt: int = OUT_F32_RGB_NCHW, roi_masks=None, out=None):
+        """Batched letterbox.  Returns (tensor [B,3,H,W] or [B,H,W,3], list of Letterbox)."""
+        t = self.torch
+        b = len(frames)
+        dh, dw = int(dst_hw[0]), int(dst_hw[1])
+        dtype = {OUT_F32_RGB_NCHW: t.float32, OUT_F16_RGB_NCHW: t.float16}.get(fmt, t.uint8)
+        shape = (b, dh, dw, 3) if fmt == OUT_U8_BGR_NHWC else (b, 3, dh, dw)
+        if out is None:
+            out = t.empty(shape, dtype=dtype, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
+            raise ValueError("preprocess: `out` has the wrong shape / dtype / layout")
+        metas = (Letterbox * max(b, 1))()
+        if b:
+            ptrs, hs, ws, pitch = self._frame_args(frames)
+            self._check(self.lib.b200va_preprocess(self._h, ptrs, hs, ws, pitch, b, self._mask_args(roi_masks, frames),
+                                                   C.c_void_p(out.data_ptr()), dh, dw, fmt, metas, self._stream()))
+        return out, [metas[i] for i in range(b)]
+
+    # -- a10 --------------------------------------------------------------------------------
+    def resize(self, frames, dst_hw_list, roi_masks=None):
+        """``cv2.resize(frame, (w, h), INTER_LINEAR)`` per frame; returns new uint8 HWC tensors."""
+        t = self.torch
+        outs = [t.empty((int(h), int(w), 3), dtype=t.uint8, device=self.device) for h, w in dst_hw_list]
+        if frames:
+            ptrs, hs, ws, pitch = self._frame_args(frames)
+            self._check(self.lib.b200va_resize_linear_u8(
+                self._h, ptrs, hs, ws, pitch, len(frames), self._mask_args(roi_masks, frames),
+                _ptr_array([o.data_ptr() for o in outs]), _int_array([h for h, _ in dst_hw_list]),
+                _int_array([w for _, w in dst_hw_list]), self._stream()))
+        return outs
+
+    # -- a9 ---------------------------------------------------------------------------------
+    def roi_rasterize(self, polygons, height: int, width: int):
+        """Union of ``cv2.fillPoly`` masks (frame_filter.py:46-49) -> CUDA uint8 [H, W]."""
+        t = self.torch
+        flat: List[int] = []
+        sizes: List[int] = []
+        for poly in polygons:
+            sizes.append(len(poly))
+            for x, y in poly:
+                # np.array(polygon, dtype=np.int32) truncates toward zero
+                flat.extend((int(x), int(y)))
+        mask = t.empty((height, width), dtype=t.uint8, device=self.device)
+        pts = (C.c_int32 * max(len(flat), 1))(*flat)
+        self._check(self.lib.b200va_roi_rasterize(self._h, pts, _int_array(sizes) if sizes else None, len(sizes),
+                                                  height, width, C.c_void_p(mask.data_ptr()), self._stream()))
+        return mask
+
+    def apply_mask(self, frame, mask, out=None):
+        t = self.torch
+        if out is None:
+            out = t.empty((frame.shape[0], frame.shape[1], 3), dtype=t.uint8, device=self.device)
+        self._check(self.lib.b200va_apply_mask(self._h, C.c_void_p(frame.data_ptr()), frame.stride(0),
+                                               C.c_void_p(mask.data_ptr()), frame.shape[0], frame.shape[1],
+                                               C.c_void_p(out.data_ptr()), out.stride(0), self._stream()))
+        return out
+
+    # -- a11 --------------------------------------------------------------------------------
+    def motion(self, frames, prev_gray, next_gray, roi_masks=None, changed_out=None):
+        """Blurred-gray update + changed-pixel counts.  ``prev_gray[i]`` may be None (first frame:
+        count -1).  Returns the int32 device tensor of counts."""
+        t = self.torch
+        b = len(frames)
+        if changed_out is None:
+            changed_out = t.empty((b,), dtype=t.int32, device=self.device)
+        if b:
+            ptrs, hs, ws, pitch = self._frame_args(frames)
+            has_prev = _int_array([0 if p is None else 1 for p in prev_gray])
+            self._check(self.lib.b200va_motion(
+                self._h, ptrs, hs, ws, pitch, b, self._mask_args(roi_masks, frames),
+                _ptr_array([p.data_ptr() if p is not None else None for p in prev_gray]),
+                _ptr_array([n.data_ptr() for n in next_gray]), has_prev, C.c_void_p(changed_out.data_ptr()),
+                self._stream()))
+        return changed_out
+
+    # -- a3-a7 ------------------------------------------------------------------------------
+    def alloc_dets(self, batch: int):
+        t = self.torch
+        md = self.cfg.max_dets
+        return {"bbox_xyxy": t.empty((batch, md, 4), dtype=t.float32, device=self.device),
+                "conf": t.empty((batch, md), dtype=t.float32, device=self.device),
+                "cls": t.empty((batch, md), dtype=t.int32, device=self.device),
+                "count": t.zeros((batch,), dtype=t.int32, device=self.device)}
+
+    @staticmethod
+    def _dets_struct(d) -> Dets:
+        return Dets(d["bbox_xyxy"].data_ptr(), d["conf"].data_ptr(), d["cls"].data_ptr(), d["count"].data_ptr())
+
+    def postprocess(self, head, metas, conf_thr: float, iou_thr: float, classes=None, layout=None,
+                    filter_conf: Optional[float] = None, out=None):
+        """Decode + filter + NMS for ``head`` [B,C,A] (channel major) or [B,A,C] (anchor major)."""
+        t = self.torch
+        if not (head.is_cuda and head.dtype == t.float32 and head.dim() == 3 and head.is_contiguous()):
+            raise ValueError("head must be a contiguous CUDA float32 tensor [B, C, A] or [B, A, C]")
+        b, d1, d2 = head.shape
+        if layout is None:  # detector.py:282-283: transpose when shape[0] < shape[1]
+            layout = HEAD_CHANNEL_MAJOR if (d1 != 0 and d1 < d2) else HEAD_ANCHOR_MAJOR
+        channels, anchors = (d1, d2) if layout == HEAD_CHANNEL_MAJOR else (d2, d1)
+        if out is None:
+            out = self.alloc_dets(b)
+        marr = (Letterbox * max(b, 1))(*metas)
+        cls_arr = (C.c_int32 * len(classes))(*[int(c) for c in classes]) if classes else None
+        ds = self._dets_struct(out)
+        self._check(self.lib.b200va_postprocess(
+            self._h, C.c_void_p(head.data_ptr()), layout, b, channels, anchors, marr, float(conf_thr), float(iou_thr),
+            cls_arr, len(classes) if classes else 0, SCORE_REF_COMPAT,
+            float(filter_conf) if filter_conf is not None else 0.0, 1 if filter_conf is not None else 0,
+            C.byref(ds), self._stream()))
+        return out
+
+    # -- a8 ---------------------------------------------------------------------------------
+    def alloc_tracks(self, batch: int):
+        t = self.torch
+        mt = self.cfg.max_tracks
+        return {"track_id": t.empty((batch, mt), dtype=t.int64, device=self.device),
+                "cls": t.empty((batch, mt), dtype=t.int32, device=self.device),
+                "conf": t.empty((batch, mt), dtype=t.float64, device=self.device),
+                "bbox_xyxy": t.empty((batch, mt, 4), dtype=t.float64, device=self.device),
+                "age": t.empty((batch, mt), dtype=t.int32, device=self.device),
+                "hits": t.empty((batch, mt), dtype=t.int32, device=self.device),
+                "count": t.zeros((batch,), dtype=t.int32, device=self.device),
+                "new_count": t.zeros((batch,), dtype=t.int32, device=self.device)}
+
+    def tracker_update(self, slots, dets, max_age: int, min_hits: int, max_iou_distance: float, det_scale=None,
+                       skip=None, id_base=None, out=None, f64: bool = False):
+        b = len(slots)
+        if out is None:
+            out = self.alloc_tracks(b)
+        cfg = TrackerCfg(int(max_age), int(min_hits), float(max_iou_distance))
+        ts = Tracks(out["track_id"].data_ptr(), out["cls"].data_ptr(), out["conf"].data_ptr(),
+                    out["bbox_xyxy"].data_ptr(), out["age"].data_ptr(), out["hits"].data_ptr(),
+                    out["count"].data_ptr())
+        skip_arr = (C.c_uint8 * b)(*[1 if s else 0 for s in skip]) if skip is not None else None
+        idb = (C.c_int64 * b)(*[int(v) for v in id_base]) if id_base is not None else None
+        max_dets = int(dets["conf"].shape[1])
+        if f64:
+            ds = Dets64(dets["bbox_xyxy"].data_ptr(), dets["conf"].data_ptr(), dets["cls"].data_ptr(),
+                        dets["count"].data_ptr())
+            self._check(self.lib.b200va_tracker_update_f64(self._h, _int_array(slots), b, C.byref(ds), max_dets,
+                                                           skip_arr, C.byref(cfg), idb, C.byref(ts),
+                                                           C.c_void_p(out["new_count"].data_ptr()), self._stream()))
+        else:
+            ds = self._dets_struct(dets)
+            sc = (C.c_double * b)(*[float(v) for v in det_scale]) if det_scale is not None else None
+            self._check(self.lib.b200va_tracker_update(self._h, _int_array(slots), b, C.byref(ds), max_dets, sc,
+                                                       skip_arr, C.byref(cfg), idb, C.byref(ts),
+                                                       C.c_void_p(out["new_count"].data_ptr()), self._stream()))
+        return out
+
+    def tracker_reset(self, slot: int) -> None:
+        self._check(self.lib.b200va_tracker_reset(self._h, int(slot), self._stream()))
+
+    def tracker_set_next_id(self, next_id: int) -> None:
+        self._check(self.lib.b200va_tracker_set_next_id(self._h, int(next_id), self._stream()))

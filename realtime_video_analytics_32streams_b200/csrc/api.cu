@@ -1,0 +1,117 @@
+// Library entry points that are not tied to one kernel family: handle life cycle, error text,
+// launch accounting and the capacity flags the kernels raise.
+#include "common.cuh"
+
+int postprocess_configure(b200va_ctx* h);  // postprocess.cu
+int preprocess_configure(b200va_ctx* h);   // preprocess.cu
+
+extern "C" int b200va_version(void) { return B200VA_VERSION; }
+
+extern "C" const char* b200va_error_string(int status) {
+  switch (status) {
+    case B200VA_OK: return "ok";
+    case B200VA_ERR_INVALID: return "invalid argument";
+    case B200VA_ERR_CUDA: return "CUDA runtime error";
+    case B200VA_ERR_CAPACITY: return "configured capacity exceeded";
+    case B200VA_ERR_STATE: return "invalid call order";
+    default: return "unknown status";
+  }
+}
+
+static int create_impl(b200va_ctx* h) {
+  const b200va_config& c = h->cfg;
+  REQUIRE(h, c.max_batch >= 1 && c.max_batch <= B200VA_MAX_BATCH, "max_batch must be in [1, %d]", B200VA_MAX_BATCH);
+  REQUIRE(h, c.max_anchors >= 1 && c.max_anchors <= 262144, "max_anchors must be in [1, 262144]");
+  REQUIRE(h, c.max_candidates >= 1 && c.max_candidates <= 8192, "max_candidates must be in [1, 8192]");
+  REQUIRE(h, c.max_dets >= 1 && c.max_dets <= c.max_candidates, "max_dets must be in [1, max_candidates]");
+  REQUIRE(h, c.max_streams >= 1 && c.max_streams <= 4096, "max_streams must be in [1, 4096]");
+  REQUIRE(h, c.max_tracks >= 1 && c.max_tracks <= 5600, "max_tracks must be in [1, 5600]");
+  int ndev = 0;
+  CUDA_TRY(h, cudaGetDeviceCount(&ndev));
+  REQUIRE(h, c.device >= 0 && c.device < ndev, "device %d not present (%d visible)", c.device, ndev);
+  CUDA_TRY(h, cudaSetDevice(c.device));
+  cudaDeviceProp prop;
+  CUDA_TRY(h, cudaGetDeviceProperties(&prop, c.device));
+  REQUIRE(h, prop.major >= 10, "device %d is sm_%d%d; this library is built for sm_100a only", c.device, prop.major, prop.minor);
+  h->num_sms = prop.multiProcessorCount;
+  const size_t frames = c.max_batch < B200VA_LAUNCH_FRAMES ? c.max_batch : B200VA_LAUNCH_FRAMES;
+  const size_t n = frames * (size_t)c.max_candidates;
+  CUDA_TRY(h, cudaMalloc(&h->cand_key, n * sizeof(unsigned long long)));
+  CUDA_TRY(h, cudaMalloc(&h->cand_box, n * sizeof(float4)));
+  CUDA_TRY(h, cudaMalloc(&h->cand_cls, n * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc(&h->cand_count, frames * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMemset(h->cand_count, 0, frames * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc(&h->status_flags, FLAG_COUNT * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMemset(h->status_flags, 0, FLAG_COUNT * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc(&h->roi_scratch, ROI_SCRATCH_BYTES));
+  int rc = tap_cache_create(h);
+  if (rc) return rc;
+  rc = preprocess_configure(h);
+  if (rc) return rc;
+  rc = postprocess_configure(h);
+  if (rc) return rc;
+  rc = tracker_state_create(h);
+  if (rc) return rc;
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  return B200VA_OK;
+}
+
+static std::string g_create_error;
+
+extern "C" int b200va_create(const b200va_config* cfg, b200va_handle* out) {
+  if (!cfg || !out) return B200VA_ERR_INVALID;
+  *out = nullptr;
+  b200va_ctx* h = new b200va_ctx();
+  h->cfg = *cfg;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  int rc = create_impl(h);
+  if (prev >= 0) cudaSetDevice(prev);
+  if (rc != B200VA_OK) {
+    g_create_error = h->last_error;
+    b200va_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return B200VA_OK;
+}
+
+extern "C" int b200va_destroy(b200va_handle h) {
+  if (!h) return B200VA_OK;
+  {
+    DeviceGuard guard(h->cfg.device);
+    cudaDeviceSynchronize();
+    tracker_state_destroy(h);
+    tap_cache_destroy(h);
+    if (h->cand_key) cudaFree(h->cand_key);
+    if (h->cand_box) cudaFree(h->cand_box);
+    if (h->cand_cls) cudaFree(h->cand_cls);
+    if (h->cand_count) cudaFree(h->cand_count);
+    if (h->status_flags) cudaFree(h->status_flags);
+    if (h->roi_scratch) cudaFree(h->roi_scratch);
+  }
+  delete h;
+  return B200VA_OK;
+}
+
+extern "C" const char* b200va_last_error(b200va_handle h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+extern "C" int64_t b200va_launch_count(b200va_handle h) { return h ? h->launches.load() : 0; }
+
+extern "C" int b200va_poll_status(b200va_handle h, void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int32_t flags[FLAG_COUNT];
+  CUDA_TRY(h, cudaMemcpyAsync(flags, h->status_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  if (flags[FLAG_CAND_OVERFLOW] || flags[FLAG_DET_OVERFLOW] || flags[FLAG_TRACK_OVERFLOW]) {
+    CUDA_TRY(h, cudaMemsetAsync(h->status_flags, 0, sizeof(flags), st));
+    return set_error(h, B200VA_ERR_CAPACITY, "capacity exceeded since the last poll:%s%s%s",
+                     flags[FLAG_CAND_OVERFLOW] ? " candidates>max_candidates" : "",
+                     flags[FLAG_DET_OVERFLOW] ? " detections>max_dets" : "",
+                     flags[FLAG_TRACK_OVERFLOW] ? " tracks>max_tracks" : "");
+  }
+  return B200VA_OK;
+}

@@ -1,0 +1,160 @@
+// Internal helpers shared by the libb200va translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "b200va.h"
+
+#define B200VA_MAX_BATCH 128
+// Frames per kernel launch: per-frame descriptors travel as kernel parameters (<= 4 KB).
+#define B200VA_LAUNCH_FRAMES 64
+
+struct TrackerState;  // tracker.cu
+struct TapCache;      // preprocess.cu
+
+// status_flags[] slots written by kernels (device int32), mirrored on demand by b200va_check.
+enum {
+  FLAG_CAND_OVERFLOW = 0,   // a frame produced more candidates than max_candidates
+  FLAG_DET_OVERFLOW = 1,    // a frame kept more detections than max_dets
+  FLAG_TRACK_OVERFLOW = 2,  // a stream needed more than max_tracks live tracks
+  FLAG_COUNT = 8
+};
+
+struct b200va_ctx {
+  b200va_config cfg;
+  int num_sms = 0;
+  std::string last_error;
+  std::atomic<int64_t> launches{0};
+  std::mutex mu;
+
+  // ---- post-process scratch (device), all [max_batch, max_candidates] ----
+  unsigned long long* cand_key = nullptr;  // (score bits << 32) | anchor index
+  float4* cand_box = nullptr;              // xyxy, frame pixels
+  int32_t* cand_cls = nullptr;
+  int32_t* cand_count = nullptr;           // [max_batch]
+  int32_t* status_flags = nullptr;         // device int32[FLAG_COUNT]
+  // ---- preprocess ----
+  TapCache* taps = nullptr;
+  // ---- roi rasteriser scratch ----
+  void* roi_scratch = nullptr;  // device, ROI_SCRATCH_BYTES
+  // ---- tracker ----
+  TrackerState* tracker = nullptr;
+};
+
+#define ROI_SCRATCH_BYTES (1 << 20)
+
+inline int set_error(b200va_ctx* h, int code, const char* fmt, ...) {
+  if (h) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    h->last_error = buf;
+  }
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                            \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return set_error((h), B200VA_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                       __FILE__, __LINE__);                                                          \
+  } while (0)
+
+#define LAUNCH_CHECK(h)                                                                      \
+  do {                                                                                       \
+    (h)->launches.fetch_add(1, std::memory_order_relaxed);                                   \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess)                                                                   \
+      return set_error((h), B200VA_ERR_CUDA, "kernel launch failed: %s (%s:%d)",             \
+                       cudaGetErrorString(_e), __FILE__, __LINE__);                          \
+  } while (0)
+
+#define REQUIRE(h, cond, ...)                                             \
+  do {                                                                    \
+    if (!(cond)) return set_error((h), B200VA_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// per-module state owned by the handle
+int tap_cache_create(b200va_ctx* h);
+void tap_cache_destroy(b200va_ctx* h);
+int tracker_state_create(b200va_ctx* h);
+void tracker_state_destroy(b200va_ctx* h);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, UBLKCP in SASS) -----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy; dst, src and bytes must be multiples of 16.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// 16-byte async global->shared copy (LDGSTS), L2-only caching: streamed frame rows.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+#endif

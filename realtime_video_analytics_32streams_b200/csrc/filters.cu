@@ -1,0 +1,575 @@
+// a9 / a11: ROI polygon masks and the motion gate.
+//
+// Replaces utils.apply_roi (frame_filter.py:43-50: cv2.fillPoly per polygon + bitwise_and) and
+// MotionFilter.should_process (frame_filter.py:26-40: BGR2GRAY -> GaussianBlur 5x5 -> absdiff ->
+// threshold 25 -> count).  OpenCV's integer arithmetic is restated (oracle/cv_restate.py holds the
+// CPU statement the tests compare against):
+//   fillPoly   = 8-connected Bresenham boundary  U  even-odd scanline fill on 16.16 edge
+//                crossings.  Both are evaluated in closed form per pixel / per line step, so the
+//                rasteriser is fully parallel.
+//   BGR2GRAY   = (B*3735 + G*19235 + R*9798 + 16384) >> 15
+//   Gaussian   = separable [1 4 6 4 1], BORDER_REFLECT_101, one rounding (sum + 128) >> 8
+//   motion     = count(|new - prev| > 25); the new blurred gray always replaces the state.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// ROI rasteriser
+// ------------------------------------------------------------------------------------------
+struct RoiEdge {  // scanline edge, active for y in [y0, y1)
+  long long x, dx;  // 16.16 fixed point
+  int y0, y1;
+  int poly, pad_;
+};
+struct RoiLine {  // clipped boundary segment, left-to-right Bresenham
+  int x1, y1, major, minor, sy, vert;
+};
+
+// cv::clipLine on a width x height image (OpenCV drawing.cpp, restated): double arithmetic,
+// truncation toward zero.  Returns false when the segment misses the image.
+static bool clip_line(long long width, long long height, long long& x1, long long& y1, long long& x2, long long& y2) {
+  const long long right = width - 1, bottom = height - 1;
+  if (width <= 0 || height <= 0) return false;
+  int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+  int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+  if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+    long long a;
+    if (c1 & 12) {
+      a = c1 < 8 ? 0 : bottom;
+      x1 += (long long)((double)(a - y1) * (double)(x2 - x1) / (double)(y2 - y1));
+      y1 = a;
+      c1 = (x1 < 0) + (x1 > right) * 2;
+    }
+    if (c2 & 12) {
+      a = c2 < 8 ? 0 : bottom;
+      x2 += (long long)((double)(a - y2) * (double)(x2 - x1) / (double)(y2 - y1));
+      y2 = a;
+      c2 = (x2 < 0) + (x2 > right) * 2;
+    }
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+      if (c1) {
+        a = c1 == 1 ? 0 : right;
+        y1 += (long long)((double)(a - x1) * (double)(y2 - y1) / (double)(x2 - x1));
+        x1 = a;
+        c1 = 0;
+      }
+      if (c2) {
+        a = c2 == 1 ? 0 : right;
+        y2 += (long long)((double)(a - x2) * (double)(y2 - y1) / (double)(x2 - x1));
+        x2 = a;
+        c2 = 0;
+      }
+    }
+  }
+  return (c1 | c2) == 0;
+}
+
+static long long trunc_div(long long a, long long b) { return a / b; }  // C++ division truncates toward zero
+
+// Thread = 16 consecutive mask pixels of one row.  A pixel at X = x << 16 is inside a polygon
+// when the number of active-edge crossings strictly left of X is odd, or a crossing sits exactly
+// on X (which is what pairing the sorted crossings and filling [ceil(xa), floor(xb)] yields).
+__global__ void __launch_bounds__(256) k_roi_fill(const RoiEdge* __restrict__ edges, int n_edges, int n_polys,
+                                                  int height, int width, uint8_t* __restrict__ mask, int vec_ok) {
+  const int chunks = (width + 15) >> 4;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= chunks * height) return;
+  const int y = gid / chunks, x0 = (gid % chunks) << 4;
+  uint32_t inside = 0;  // bit j: pixel x0 + j
+  int e = 0;
+  for (int poly = 0; poly < n_polys; ++poly) {
+    uint32_t parity = 0, exact = 0;
+    for (; e < n_edges && edges[e].poly == poly; ++e) {
+      const RoiEdge ed = edges[e];
+      if (y < ed.y0 || y >= ed.y1) continue;
+      const long long xe = ed.x + (long long)(y - ed.y0) * ed.dx;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const long long X = (long long)(x0 + j) << 16;
+        parity ^= (uint32_t)(xe < X) << j;
+        exact |= (uint32_t)(xe == X) << j;
+      }
+    }
+    inside |= parity | exact;
+  }
+  uint8_t* row = mask + (size_t)y * width + x0;
+  if (vec_ok) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v |= ((inside >> (4 * q + j)) & 1u) ? (0xffu << (8 * j)) : 0u;
+      w[q] = v;
+    }
+    *reinterpret_cast<uint4*>(row) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    for (int j = 0; j < 16 && x0 + j < width; ++j) row[j] = ((inside >> j) & 1u) ? 255 : 0;
+  }
+}
+
+// Thread = one step of one boundary line.  Step i of OpenCV's 8-connected line lies at major
+// offset i and minor offset floor((2*minor*i + major - 1) / (2*major)).
+__global__ void __launch_bounds__(256) k_roi_lines(const RoiLine* __restrict__ lines, int width, uint8_t* __restrict__ mask) {
+  const RoiLine ln = lines[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > ln.major) return;
+  const int m = ln.major > 0 ? (int)((2ll * ln.minor * i + ln.major - 1) / (2ll * ln.major)) : 0;
+  const int x = ln.vert ? ln.x1 + m : ln.x1 + i;
+  const int y = ln.vert ? ln.y1 + ln.sy * i : ln.y1 + ln.sy * m;
+  mask[(size_t)y * width + x] = 255;
+}
+
+// dst = mask ? src : 0 (cv2.bitwise_and(frame, frame, mask=mask)); thread = 16 pixels.
+__global__ void __launch_bounds__(256) k_apply_mask(const uint8_t* __restrict__ src, long long src_pitch,
+                                                    const uint8_t* __restrict__ mask, int height, int width,
+                                                    uint8_t* __restrict__ dst, long long dst_pitch, int vec_ok) {
+  const int chunks = (width + 15) >> 4;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= chunks * height) return;
+  const int y = gid / chunks, x0 = (gid % chunks) << 4;
+  const uint8_t* s = src + (long long)y * src_pitch + 3ll * x0;
+  uint8_t* d = dst + (long long)y * dst_pitch + 3ll * x0;
+  const uint8_t* m = mask + (size_t)y * width + x0;
+  if (vec_ok) {
+    const uint4 mv = __ldg(reinterpret_cast<const uint4*>(m));
+    const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+    uint32_t in[12], out[12];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(s) + q);
+      in[4 * q] = v.x, in[4 * q + 1] = v.y, in[4 * q + 2] = v.z, in[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int wd = 0; wd < 12; ++wd) {
+      uint32_t sel = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int px = (4 * wd + b) / 3;
+        const uint32_t on = (mw[px >> 2] >> (8 * (px & 3))) & 0xffu;
+        sel |= on ? (0xffu << (8 * b)) : 0u;
+      }
+      out[wd] = in[wd] & sel;
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      reinterpret_cast<uint4*>(d)[q] = make_uint4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+  } else {
+    for (int j = 0; j < 16 && x0 + j < width; ++j) {
+      const bool on = m[j] != 0;
+      d[3 * j] = on ? s[3 * j] : 0;
+      d[3 * j + 1] = on ? s[3 * j + 1] : 0;
+      d[3 * j + 2] = on ? s[3 * j + 2] : 0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Motion gate
+// ------------------------------------------------------------------------------------------
+constexpr int kMotionWarps = 8;
+constexpr int kStripPx = 256;             // pixels per warp-row (8 per lane)
+constexpr int kRawBytes = 16 + 768 + 16;  // pixels [-2, 258) of a strip, on 16-byte chunk boundaries
+constexpr int kMaskBytes = 16 + 256 + 16;
+constexpr int kStagesM = 4;
+
+struct MotionFrame {
+  const uint8_t* src;
+  const uint8_t* mask;
+  const uint8_t* prev;
+  uint8_t* next;
+  long long pitch;
+  int h, w, has_prev, fast;
+};
+struct MotionParams {
+  MotionFrame f[B200VA_LAUNCH_FRAMES];
+  int32_t* changed;
+  int rows_per_task;
+};
+static_assert(sizeof(MotionParams) <= 4000, "kernel parameter block too large");
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  const int period = 2 * (n - 1);
+  i %= period;
+  if (i < 0) i += period;
+  return i >= n ? period - i : i;
+}
+__device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) {
+  return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
+}
+
+__global__ void __launch_bounds__(kMotionWarps * 32) k_motion(const __grid_constant__ MotionParams p, int frame0) {
+  __shared__ __align__(16) uint8_t s_raw[kMotionWarps][kStagesM][kRawBytes];
+  __shared__ __align__(16) uint8_t s_msk[kMotionWarps][kStagesM][kMaskBytes];
+  __shared__ __align__(16) uint8_t s_gray[kMotionWarps][4 + kStripPx + 12];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int frame = blockIdx.y;
+  const MotionFrame& f = p.f[frame];
+  const int W = f.w, H = f.h;
+  const int strips = (W + kStripPx - 1) / kStripPx;
+  const int row_tasks = (H + p.rows_per_task - 1) / p.rows_per_task;
+  const int task = blockIdx.x * kMotionWarps + warp;
+  if (task >= strips * row_tasks) return;
+  const int x0 = (task % strips) * kStripPx;
+  const int yb = (task / strips) * p.rows_per_task;
+  const int ye = min(H, yb + p.rows_per_task);
+  const bool has_mask = f.mask != nullptr;
+  const bool fast = f.fast != 0;
+  const int row_bytes = 3 * W;
+
+  // raw[16 + 3*(x - x0) + c] holds channel c of pixel x; msk[16 + (x - x0)] its ROI flag
+  auto load_row = [&](int r, int stage) {
+    const int rr = reflect101(r, H);
+    const uint8_t* g = f.src + (long long)rr * f.pitch;
+    uint8_t* raw = s_raw[warp][stage];
+    uint8_t* msk = s_msk[warp][stage];
+    if (fast) {
+      const int b0 = 3 * x0 - 16;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int c = lane + 32 * k;
+        const int off = b0 + 16 * c;
+        if (c < kRawBytes / 16 && off >= 0 && off + 16 <= row_bytes) cp_async16(raw + 16 * c, g + off);
+      }
+      if (has_mask) {
+        const int off = x0 - 16 + 16 * lane;
+        if (lane < kMaskBytes / 16 && off >= 0 && off + 16 <= W) cp_async16(msk + 16 * lane, f.mask + (size_t)rr * W + off);
+      }
+    } else {
+      const int lo = max(0, x0 - 2), hi = min(W, x0 + kStripPx + 2);
+      for (int i = 3 * lo + lane; i < 3 * hi; i += 32) raw[16 + i - 3 * x0] = __ldg(g + i);
+      if (has_mask)
+        for (int i = lo + lane; i < hi; i += 32) msk[16 + i - x0] = __ldg(f.mask + (size_t)rr * W + i);
+    }
+    cp_async_commit();
+  };
+
+  const int r_first = yb - 2, r_last = ye + 1;  // rows whose horizontal pass this task needs
+  const int nrows = r_last - r_first + 1;
+  for (int k = 0; k < kStagesM - 1; ++k) {
+    if (k < nrows) load_row(r_first + k, k);
+    else cp_async_commit();
+  }
+
+  uint32_t ring[5][4];  // horizontal sums, 8 pixels as 4 packed u16 pairs; ring[4] is the newest row
+#pragma unroll
+  for (int a = 0; a < 5; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) ring[a][b] = 0;
+  int changed = 0;
+  uint8_t* gbuf = s_gray[warp];  // gbuf[2 + (x - x0)] = gray of pixel x, for x - x0 in [-2, 258)
+  const int xl = x0 + 8 * lane;
+
+  for (int k = 0; k < nrows; ++k) {
+    const int stage = k % kStagesM;
+    if (k + kStagesM - 1 < nrows) load_row(r_first + k + kStagesM - 1, (k + kStagesM - 1) % kStagesM);
+    else cp_async_commit();
+    cp_async_wait<kStagesM - 1>();
+    __syncwarp();
+    const uint8_t* raw = s_raw[warp][stage];
+    const uint8_t* msk = s_msk[warp][stage];
+
+    // gray of the lane's own 8 pixels
+    uint32_t g8[8];
+    if (xl + 8 <= W) {
+      const uint2* q = reinterpret_cast<const uint2*>(raw + 16 + 24 * lane);
+      const uint2 w0 = q[0], w1 = q[1], w2 = q[2];
+      const uint32_t wd[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
+      uint2 mk = make_uint2(0xffffffffu, 0xffffffffu);
+      if (has_mask) mk = *reinterpret_cast<const uint2*>(msk + 16 + 8 * lane);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint32_t ch[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int bidx = 3 * j + c;
+          ch[c] = (wd[bidx >> 2] >> (8 * (bidx & 3))) & 0xffu;
+        }
+        const uint32_t on = ((j < 4 ? mk.x : mk.y) >> (8 * (j & 3))) & 0xffu;
+        g8[j] = on ? gray_of(ch[0], ch[1], ch[2]) : 0u;  // masked pixels are black: gray 0
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int x = xl + j;
+        g8[j] = 0;
+        if (x < W + 2) {
+          const int xr = reflect101(x, W);
+          const uint8_t* px = raw + 16 + 3 * (xr - x0);
+          const bool on = !has_mask || msk[16 + xr - x0];
+          g8[j] = on ? gray_of(px[0], px[1], px[2]) : 0u;
+        }
+      }
+    }
+    {
+      const uint32_t lo = g8[0] | (g8[1] << 8) | (g8[2] << 16) | (g8[3] << 24);
+      const uint32_t hi = g8[4] | (g8[5] << 8) | (g8[6] << 16) | (g8[7] << 24);
+      // gbuf + 2 + 8*lane is only 2-byte aligned: write as four 16-bit halves
+      uint16_t* gp = reinterpret_cast<uint16_t*>(gbuf + 2 + 8 * lane);
+      gp[0] = (uint16_t)lo;
+      gp[1] = (uint16_t)(lo >> 16);
+      gp[2] = (uint16_t)hi;
+      gp[3] = (uint16_t)(hi >> 16);
+    }
+    if (lane < 4) {  // halo pixels x0-2, x0-1, x0+256, x0+257
+      const int x = lane < 2 ? x0 - 2 + lane : x0 + kStripPx + (lane - 2);
+      if (x < W + 2) {
+        const int xr = reflect101(x, W);
+        const uint8_t* px = raw + 16 + 3 * (xr - x0);
+        const bool on = !has_mask || msk[16 + xr - x0];
+        gbuf[2 + x - x0] = (uint8_t)(on ? gray_of(px[0], px[1], px[2]) : 0u);
+      }
+    }
+    __syncwarp();
+    // horizontal [1 4 6 4 1] over gbuf[8*lane .. 8*lane + 12)
+    {
+      const uint32_t* gw = reinterpret_cast<const uint32_t*>(gbuf + 8 * lane);
+      const uint32_t a = gw[0], b = gw[1], c = gw[2];
+      uint32_t t[12];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        t[j] = (a >> (8 * j)) & 0xffu;
+        t[4 + j] = (b >> (8 * j)) & 0xffu;
+        t[8 + j] = (c >> (8 * j)) & 0xffu;
+      }
+#pragma unroll
+      for (int a5 = 0; a5 < 4; ++a5)
+#pragma unroll
+        for (int b4 = 0; b4 < 4; ++b4) ring[a5][b4] = ring[a5 + 1][b4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const uint32_t h0 = t[j] + 4u * t[j + 1] + 6u * t[j + 2] + 4u * t[j + 3] + t[j + 4];
+        const uint32_t h1 = t[j + 1] + 4u * t[j + 2] + 6u * t[j + 3] + 4u * t[j + 4] + t[j + 5];
+        ring[4][j >> 1] = h0 | (h1 << 16);
+      }
+    }
+    __syncwarp();  // gbuf is rewritten by the next row
+
+    const int y = r_first + k - 2;  // the output row whose five inputs are now in the ring
+    if (k >= 4 && y >= yb && y < ye) {
+      uint32_t out[2];
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        // packed u16 pairs: sums stay below 65536, no carry between halves
+        const uint32_t v0 = ring[0][2 * hlf] + 4u * ring[1][2 * hlf] + 6u * ring[2][2 * hlf] + 4u * ring[3][2 * hlf] +
+                            ring[4][2 * hlf] + 0x00800080u;
+        const uint32_t v1 = ring[0][2 * hlf + 1] + 4u * ring[1][2 * hlf + 1] + 6u * ring[2][2 * hlf + 1] +
+                            4u * ring[3][2 * hlf + 1] + ring[4][2 * hlf + 1] + 0x00800080u;
+        const uint32_t p0 = (v0 >> 8) & 0x00ff00ffu, p1 = (v1 >> 8) & 0x00ff00ffu;
+        out[hlf] = (p0 & 0xffu) | ((p0 >> 16) << 8) | ((p1 & 0xffu) << 16) | ((p1 >> 16) << 24);
+      }
+      const size_t o = (size_t)y * W + xl;
+      if (fast && xl + 8 <= W) {
+        if (f.has_prev) {
+          const uint2 pv = __ldg(reinterpret_cast<const uint2*>(f.prev + o));
+          const uint32_t d0 = __vcmpgtu4(__vabsdiffu4(out[0], pv.x), 0x19191919u);
+          const uint32_t d1 = __vcmpgtu4(__vabsdiffu4(out[1], pv.y), 0x19191919u);
+          changed += (__popc(d0) + __popc(d1)) >> 3;
+        }
+        *reinterpret_cast<uint2*>(f.next + o) = make_uint2(out[0], out[1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (xl + j < W) {
+            const int nv = (out[j >> 2] >> (8 * (j & 3))) & 0xff;
+            if (f.has_prev) {
+              const int pv = f.prev[o + j];
+              changed += (abs(nv - pv) > 25) ? 1 : 0;
+            }
+            f.next[o + j] = (uint8_t)nv;
+          }
+        }
+      }
+    }
+  }
+  changed = warp_sum(changed);
+  if (lane == 0) {
+    if (f.has_prev) {
+      if (changed) atomicAdd(p.changed + frame0 + frame, changed);
+    } else if (task == 0) {
+      p.changed[frame0 + frame] = -1;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int b200va_roi_rasterize(b200va_handle h, const int32_t* pts, const int* poly_sizes, int n_polys, int height,
+                                    int width, uint8_t* mask_out, void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  REQUIRE(h, mask_out && height > 0 && width > 0, "bad mask geometry %dx%d", width, height);
+  REQUIRE(h, n_polys >= 0 && (n_polys == 0 || (pts && poly_sizes)), "NULL polygon arrays");
+  std::vector<RoiEdge> edges;
+  std::vector<RoiLine> lines;
+  int max_major = 0;
+  const int32_t* q = pts;
+  for (int pi = 0; pi < n_polys; ++pi) {
+    const int n = poly_sizes[pi];
+    REQUIRE(h, n >= 0, "polygon %d has negative size", pi);
+    if (n == 0) continue;
+    long long px = q[2 * (n - 1)], py = q[2 * (n - 1) + 1];
+    for (int i = 0; i < n; ++i) {
+      const long long qx = q[2 * i], qy = q[2 * i + 1];
+      // boundary segment (clipped to the image like cv::LineIterator does)
+      {
+        long long x1 = px, y1 = py, x2 = qx, y2 = qy;
+        bool ok = true;
+        if (!(x1 >= 0 && x1 < width && x2 >= 0 && x2 < width && y1 >= 0 && y1 < height && y2 >= 0 && y2 < height))
+          ok = clip_line(width, height, x1, y1, x2, y2);
+        if (ok) {
+          long long dx = x2 - x1, dy = y2 - y1;
+          RoiLine ln;
+          ln.sy = 1;
+          if (dx < 0) {  // left to right: start from the other end
+            dx = -dx;
+            dy = -dy;
+            x1 = x2;
+            y1 = y2;
+          }
+          if (dy < 0) {
+            dy = -dy;
+            ln.sy = -1;
+          }
+          ln.vert = dy > dx;
+          ln.major = (int)(ln.vert ? dy : dx);
+          ln.minor = (int)(ln.vert ? dx : dy);
+          ln.x1 = (int)x1;
+          ln.y1 = (int)y1;
+          lines.push_back(ln);
+          if (ln.major > max_major) max_major = ln.major;
+        }
+      }
+      // scanline edge: slope from the clipped end points, start extrapolated to the unclipped top row
+      if (py != qy) {
+        long long c0x = px, c0y = py, c1x = qx, c1y = qy;
+        if (!(px >= 0 && px < width && qx >= 0 && qx < width && py >= 0 && py < height && qy >= 0 && qy < height)) {
+          long long t0x = px, t0y = py, t1x = qx, t1y = qy;
+          clip_line(width, height, t0x, t0y, t1x, t1y);
+          c0x = t0x;
+          c1x = t1x;
+          if (t0y != t1y) {
+            c0y = t0y;
+            c1y = t1y;
+          }
+        }
+        RoiEdge e;
+        e.dx = trunc_div((c1x - c0x) * 65536ll, c1y - c0y);
+        e.poly = pi;
+        e.pad_ = 0;
+        if (py < qy) {
+          e.y0 = (int)py;
+          e.y1 = (int)qy;
+          e.x = c0x * 65536ll + (py - c0y) * e.dx;
+        } else {
+          e.y0 = (int)qy;
+          e.y1 = (int)py;
+          e.x = c1x * 65536ll + (qy - c1y) * e.dx;
+        }
+        edges.push_back(e);
+      }
+      px = qx;
+      py = qy;
+    }
+    q += 2 * n;
+  }
+  const size_t eb = edges.size() * sizeof(RoiEdge), lb = lines.size() * sizeof(RoiLine);
+  const size_t lo = (eb + 255) & ~(size_t)255;
+  if (lo + lb > ROI_SCRATCH_BYTES) return set_error(h, B200VA_ERR_CAPACITY, "polygons too complex: %zu edges", edges.size());
+  uint8_t* scratch = (uint8_t*)h->roi_scratch;
+  if (eb) CUDA_TRY(h, cudaMemcpyAsync(scratch, edges.data(), eb, cudaMemcpyHostToDevice, st));
+  if (lb) CUDA_TRY(h, cudaMemcpyAsync(scratch + lo, lines.data(), lb, cudaMemcpyHostToDevice, st));
+  const int chunks = (width + 15) / 16;
+  const long long threads = (long long)chunks * height;
+  const int vec_ok = (width % 16 == 0) && ((uintptr_t)mask_out % 16 == 0);
+  k_roi_fill<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((const RoiEdge*)scratch, (int)edges.size(), n_polys, height,
+                                                              width, mask_out, vec_ok);
+  LAUNCH_CHECK(h);
+  if (!lines.empty()) {
+    dim3 grid((max_major + 1 + 255) / 256, (unsigned)lines.size());
+    k_roi_lines<<<grid, 256, 0, st>>>((const RoiLine*)(scratch + lo), width, mask_out);
+    LAUNCH_CHECK(h);
+  }
+  // the scratch buffer is reused by the next call: rasterisation is a once-per-stream setup step
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  return B200VA_OK;
+}
+
+extern "C" int b200va_apply_mask(b200va_handle h, const uint8_t* src, int64_t src_pitch, const uint8_t* mask, int height,
+                                 int width, uint8_t* dst, int64_t dst_pitch, void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  REQUIRE(h, src && mask && dst && height > 0 && width > 0, "bad arguments");
+  REQUIRE(h, src_pitch >= 3ll * width && dst_pitch >= 3ll * width, "pitch smaller than 3*width");
+  const int chunks = (width + 15) / 16;
+  const long long threads = (long long)chunks * height;
+  const int vec_ok = (width % 16 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0) &&
+                     ((uintptr_t)mask % 16 == 0) && (src_pitch % 16 == 0) && (dst_pitch % 16 == 0);
+  k_apply_mask<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, src_pitch, mask, height, width, dst,
+                                                                                  dst_pitch, vec_ok);
+  LAUNCH_CHECK(h);
+  return B200VA_OK;
+}
+
+extern "C" int b200va_motion(b200va_handle h, const uint8_t* const* frames, const int* src_h, const int* src_w,
+                             const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks,
+                             const uint8_t* const* prev_gray, uint8_t* const* next_gray, const int* has_prev,
+                             int32_t* changed_out, void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  REQUIRE(h, frames && src_h && src_w && next_gray && has_prev && changed_out, "NULL argument");
+  REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
+  if (batch == 0) return B200VA_OK;
+  CUDA_TRY(h, cudaMemsetAsync(changed_out, 0, sizeof(int32_t) * batch, st));
+  for (int base = 0; base < batch; base += B200VA_LAUNCH_FRAMES) {
+    const int n = batch - base < B200VA_LAUNCH_FRAMES ? batch - base : B200VA_LAUNCH_FRAMES;
+    MotionParams p;
+    memset(&p, 0, sizeof(p));
+    int max_tasks = 0;
+    // rows per warp task: tall enough that the 4 halo rows stay a small overhead, short enough
+    // that the launch fills the SMs several times over
+    long long total_px = 0;
+    for (int i = 0; i < n; ++i) total_px += (long long)src_h[base + i] * src_w[base + i];
+    int rows = 32;
+    {
+      const long long want_tasks = (long long)h->num_sms * 64 * 4;
+      while (rows > 8 && total_px / ((long long)rows * kStripPx) < want_tasks) rows >>= 1;
+    }
+    p.rows_per_task = rows;
+    for (int i = 0; i < n; ++i) {
+      const int b = base + i;
+      MotionFrame& f = p.f[i];
+      REQUIRE(h, frames[b] && next_gray[b], "frame %d: NULL frame or state buffer", b);
+      REQUIRE(h, src_h[b] > 0 && src_w[b] > 0, "frame %d has bad size", b);
+      REQUIRE(h, !has_prev[b] || (prev_gray && prev_gray[b]), "frame %d: has_prev without a previous buffer", b);
+      REQUIRE(h, !has_prev[b] || prev_gray[b] != next_gray[b], "frame %d: prev_gray and next_gray alias", b);
+      f.src = frames[b];
+      f.mask = roi_masks ? roi_masks[b] : nullptr;
+      f.prev = has_prev[b] ? prev_gray[b] : nullptr;
+      f.next = next_gray[b];
+      f.pitch = src_pitch ? src_pitch[b] : 3ll * src_w[b];
+      REQUIRE(h, f.pitch >= 3ll * src_w[b], "frame %d: pitch smaller than 3*width", b);
+      f.h = src_h[b];
+      f.w = src_w[b];
+      f.has_prev = has_prev[b] ? 1 : 0;
+      f.fast = (f.w % 16 == 0) && ((uintptr_t)f.src % 16 == 0) && (f.pitch % 16 == 0) && ((uintptr_t)f.next % 16 == 0) &&
+               (!f.prev || (uintptr_t)f.prev % 16 == 0) && (!f.mask || (uintptr_t)f.mask % 16 == 0);
+      const int strips = (f.w + kStripPx - 1) / kStripPx;
+      const int row_tasks = (f.h + rows - 1) / rows;
+      if (strips * row_tasks > max_tasks) max_tasks = strips * row_tasks;
+    }
+    p.changed = changed_out;
+    dim3 grid((max_tasks + kMotionWarps - 1) / kMotionWarps, n);
+    k_motion<<<grid, kMotionWarps * 32, 0, st>>>(p, base);
+    LAUNCH_CHECK(h);
+  }
+  return B200VA_OK;
+}

@@ -1,0 +1,451 @@
+// a3-a7: YOLO head post-process for a batch of frames.
+//
+// Replaces _TensorRTBaseDetector._postprocess (detector.py:266-338), _xywh2xyxy (:352-359),
+// _scale_boxes (:340-350), _nms (:361-375), _iou (:469-481) and filter_detections (:99-103).
+// All float32 arithmetic uses explicit round-to-nearest intrinsics in NumPy's operation order
+// (no FMA contraction, true division), so kept indices, scores and boxes are bit-identical.
+//
+//   k_decode_cm / k_decode_am   one pass over the head tensor (the only HBM-heavy step):
+//       objectness x class score, first-max argmax, confidence / class filter, xywh -> xyxy,
+//       un-letterbox, clip; survivors are compacted per frame with warp ballots.
+//   k_sort_nms                  one CTA per frame: bitonic sort of (score, anchor) keys in shared
+//       memory, then exact greedy NMS in 64-box chunks -- an in-chunk 64x64 IoU bit matrix
+//       resolved by one warp, after which the chunk's survivors suppress every later box in
+//       parallel -- and ordered emission with the float64 re-threshold folded in.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace {
+
+struct PostFrame {
+  float left, top, scale, xmax, ymax;
+};
+
+struct PostParams {
+  PostFrame f[B200VA_LAUNCH_FRAMES];
+  uint32_t class_mask[64];  // whitelist bitmap over class ids (np.isin, detector.py:313-314)
+  const float* head;
+  unsigned long long* cand_key;
+  float4* cand_box;
+  int32_t* cand_cls;
+  int32_t* cand_count;
+  int C, A, max_cand, use_mask;
+  float conf_thr;
+};
+static_assert(sizeof(PostParams) <= 4000, "kernel parameter block too large");
+
+__device__ __forceinline__ uint32_t order_bits(float v) {
+  // monotone map float -> uint32 (larger float, larger integer)
+  uint32_t b = __float_as_uint(v);
+  return b ^ ((b & 0x80000000u) ? 0xffffffffu : 0x80000000u);
+}
+__device__ __forceinline__ float unorder_bits(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u ^ 0x80000000u) : ~u;
+  return __uint_as_float(b);
+}
+
+// detector.py:352-359 then :340-350, float32, NumPy operation order.
+__device__ __forceinline__ float4 decode_box(float cx, float cy, float w, float h, const PostFrame& f) {
+  const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);  // w / 2.0 is exact either way
+  float x1 = __fsub_rn(cx, hw), y1 = __fsub_rn(cy, hh), x2 = __fadd_rn(cx, hw), y2 = __fadd_rn(cy, hh);
+  x1 = __fdiv_rn(__fsub_rn(x1, f.left), f.scale);
+  x2 = __fdiv_rn(__fsub_rn(x2, f.left), f.scale);
+  y1 = __fdiv_rn(__fsub_rn(y1, f.top), f.scale);
+  y2 = __fdiv_rn(__fsub_rn(y2, f.top), f.scale);
+  x1 = fminf(fmaxf(x1, 0.f), f.xmax);
+  x2 = fminf(fmaxf(x2, 0.f), f.xmax);
+  y1 = fminf(fmaxf(y1, 0.f), f.ymax);
+  y2 = fminf(fmaxf(y2, 0.f), f.ymax);
+  return make_float4(x1, y1, x2, y2);
+}
+
+__device__ __forceinline__ bool class_allowed(const PostParams& p, int cls) {
+  if (!p.use_mask) return true;
+  if (cls >= 2048) return false;
+  return (p.class_mask[cls >> 5] >> (cls & 31)) & 1u;
+}
+
+__device__ __forceinline__ void emit_candidate(const PostParams& p, int frame, int pos, int anchor, float conf, int cls,
+                                               float4 box) {
+  if (pos >= p.max_cand) return;  // overflow is flagged by k_sort_nms from the raw count
+  const size_t o = (size_t)frame * p.max_cand + pos;
+  p.cand_key[o] = ((unsigned long long)order_bits(conf) << 32) | ((unsigned long long)(uint32_t)anchor << 14) |
+                  (unsigned long long)(uint32_t)pos;
+  p.cand_box[o] = box;
+  p.cand_cls[o] = cls;
+}
+
+// channel-major head [B, C, A]: a thread owns one anchor, a warp reads 128 contiguous bytes per channel
+__global__ void __launch_bounds__(256) k_decode_cm(const __grid_constant__ PostParams p, int frame0) {
+  const int frame = blockIdx.y;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* __restrict__ hd = p.head + (size_t)(frame0 + frame) * p.C * p.A;
+  const int A = p.A, C = p.C;
+  bool pass = false;
+  float best = 0.f;
+  int cls = 0;
+  if (a < A) {
+    const float obj = __ldg(hd + (size_t)4 * A + a);
+    if (C > 5) {
+      // scores = class_probs * objectness for both model types (detector.py:294-305)
+      best = __fmul_rn(__ldg(hd + (size_t)5 * A + a), obj);
+      int c = 6;
+      for (; c + 8 <= C; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldg(hd + (size_t)(c + k) * A + a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float s = __fmul_rn(v[k], obj);
+          if (s > best) {  // np.argmax: first maximum wins
+            best = s;
+            cls = c + k - 5;
+          }
+        }
+      }
+      for (; c < C; ++c) {
+        const float s = __fmul_rn(__ldg(hd + (size_t)c * A + a), obj);
+        if (s > best) {
+          best = s;
+          cls = c - 5;
+        }
+      }
+    } else {
+      best = obj;  // scores = predictions[:, 4:], detector.py:306-307
+    }
+    pass = (best >= p.conf_thr) && class_allowed(p, cls);
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, pass);
+  if (ballot == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(p.cand_count + frame, __popc(ballot));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (pass) {
+    const int pos = base + __popc(ballot & ((1u << lane) - 1u));
+    const float cx = __ldg(hd + a), cy = __ldg(hd + (size_t)A + a), w = __ldg(hd + (size_t)2 * A + a),
+                h = __ldg(hd + (size_t)3 * A + a);
+    emit_candidate(p, frame, pos, a, best, cls, decode_box(cx, cy, w, h, p.f[frame]));
+  }
+}
+
+// anchor-major head [B, A, C]: a warp owns one anchor and strides its lanes over the channels
+__global__ void __launch_bounds__(256) k_decode_am(const __grid_constant__ PostParams p, int frame0) {
+  const int frame = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (a >= p.A) return;
+  const int C = p.C;
+  const float* __restrict__ row = p.head + ((size_t)(frame0 + frame) * p.A + a) * C;
+  const float obj = __ldg(row + 4);
+  float best;
+  int cls;
+  if (C > 5) {
+    best = -INFINITY;
+    cls = 0x7fffffff;
+    bool have = false;
+    for (int c = 5 + lane; c < C; c += 32) {
+      const float s = __fmul_rn(__ldg(row + c), obj);
+      if (!have || s > best) {
+        best = s;
+        cls = c - 5;
+        have = true;
+      }
+    }
+    // NaN scores never pass the >= filter; order them below everything in the reduction
+    if (!(best == best)) best = -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, cls, o);
+      if (ob > best || (ob == best && oc < cls)) {
+        best = ob;
+        cls = oc;
+      }
+    }
+  } else {
+    best = obj;
+    cls = 0;
+  }
+  if (lane == 0) {
+    if ((best >= p.conf_thr) && class_allowed(p, cls)) {
+      const int pos = atomicAdd(p.cand_count + frame, 1);
+      emit_candidate(p, frame, pos, a, best, cls, decode_box(__ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3), p.f[frame]));
+    }
+  }
+}
+
+// ---- sort + NMS + emit ----------------------------------------------------------------------
+
+struct NmsParams {
+  const unsigned long long* cand_key;
+  const float4* cand_box;
+  const int32_t* cand_cls;
+  int32_t* cand_count;  // read, then reset to 0 for the next call
+  int32_t* flags;
+  float* out_box;
+  float* out_conf;
+  int32_t* out_cls;
+  int32_t* out_count;
+  int max_cand, max_dets, cap_pow2;
+  float iou_thr;
+  double filter_thr;
+  int use_filter;
+};
+
+// _iou of detector.py:469-481 in float32; returns true when box j must be suppressed by box i.
+__device__ __forceinline__ bool suppresses(const float4 a, const float4 b, float thr) {
+  const float x1 = fmaxf(a.x, b.x), y1 = fmaxf(a.y, b.y), x2 = fminf(a.z, b.z), y2 = fminf(a.w, b.w);
+  const float iw = fmaxf(0.f, __fsub_rn(x2, x1)), ih = fmaxf(0.f, __fsub_rn(y2, y1));
+  const float inter = __fmul_rn(iw, ih);
+  const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  const float iou = __fdiv_rn(inter, fmaxf(uni, 1e-6f));
+  return !(iou <= thr);
+}
+
+constexpr int kNmsThreads = 1024;
+
+__global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int frame = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int n_raw = p.cand_count[frame];
+  const int n = min(n_raw, p.max_cand);
+  int np2 = 64;
+  while (np2 < n) np2 <<= 1;
+
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);              // [cap_pow2]
+  float4* box = reinterpret_cast<float4*>(smem_raw + (size_t)p.cap_pow2 * 8);               // [cap_pow2]
+  uint32_t* supp = reinterpret_cast<uint32_t*>(smem_raw + (size_t)p.cap_pow2 * 24);         // [cap_pow2/32]
+  unsigned long long* keep_w = reinterpret_cast<unsigned long long*>(supp + p.cap_pow2 / 32);  // [cap_pow2/64]
+  int* keep_off = reinterpret_cast<int*>(keep_w + p.cap_pow2 / 64);                         // [cap_pow2/64 + 1]
+  __shared__ unsigned long long rows[64];
+
+  __syncthreads();
+  if (tid == 0) {
+    p.cand_count[frame] = 0;
+    if (n_raw > p.max_cand) atomicOr(p.flags + FLAG_CAND_OVERFLOW, 1);
+  }
+  if (n == 0) {
+    if (tid == 0) p.out_count[frame] = 0;
+    return;
+  }
+  const size_t cbase = (size_t)frame * p.max_cand;
+  for (int i = tid; i < np2; i += kNmsThreads) keys[i] = i < n ? p.cand_key[cbase + i] : 0ull;
+  for (int i = tid; i < np2 / 32; i += kNmsThreads) supp[i] = 0u;
+  __syncthreads();
+
+  // bitonic sort, descending
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < np2; i += kNmsThreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) {
+            keys[i] = b;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < n; i += kNmsThreads) box[i] = p.cand_box[cbase + (keys[i] & 0x3fffull)];
+  __syncthreads();
+
+  const float thr = p.iou_thr;
+  const int nchunks = (n + 63) >> 6;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int c0 = ch << 6;
+    const int m = min(64, n - c0);
+    if (tid < 64) rows[tid] = 0ull;
+    __syncthreads();
+    // (a) in-chunk IoU bits: thread -> row i = tid / 16, columns 4 * (tid % 16) ..
+    {
+      const int i = tid >> 4, jb = (tid & 15) << 2;
+      if (i < m) {
+        const float4 bi = box[c0 + i];
+        unsigned long long bits = 0ull;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = jb + q;
+          if (j > i && j < m && suppresses(bi, box[c0 + j], thr)) bits |= 1ull << j;
+        }
+        if (bits) atomicOr(&rows[i], bits);
+      }
+    }
+    __syncthreads();
+    // (b) one warp resolves the chunk sequentially; rows live in registers, two per lane
+    if (tid < 32) {
+      const unsigned long long r_lo = rows[tid], r_hi = rows[tid + 32];
+      const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
+      unsigned long long alive = ~(((unsigned long long)supp[(c0 >> 5) + 1] << 32) | supp[c0 >> 5]) & valid;
+      unsigned long long kept = 0ull;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        const unsigned long long r = __shfl_sync(0xffffffffu, i < 32 ? r_lo : r_hi, i & 31);
+        const unsigned long long on = 0ull - ((alive >> i) & 1ull);
+        kept |= on & (1ull << i);
+        alive &= ~(r & on);
+      }
+      if (tid == 0) keep_w[ch] = kept;
+    }
+    __syncthreads();
+    // (c) this chunk's survivors suppress every later box
+    const unsigned long long kept = keep_w[ch];
+    if (kept) {
+      for (int j = c0 + 64 + tid; j < n; j += kNmsThreads) {
+        if ((supp[j >> 5] >> (j & 31)) & 1u) continue;
+        const float4 bj = box[j];
+        unsigned long long kk = kept;
+        while (kk) {
+          const int i = __ffsll((long long)kk) - 1;
+          kk &= kk - 1;
+          if (suppresses(box[c0 + i], bj, thr)) {
+            atomicOr(&supp[j >> 5], 1u << (j & 31));
+            break;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // filter_detections (detector.py:99-103): float64 compare on the kept boxes only
+  if (p.use_filter) {
+    for (int i = tid; i < n; i += kNmsThreads) {
+      if ((keep_w[i >> 6] >> (i & 63)) & 1ull) {
+        const float conf = unorder_bits((uint32_t)(keys[i] >> 32));
+        if (!((double)conf >= p.filter_thr)) atomicAnd(&keep_w[i >> 6], ~(1ull << (i & 63)));
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int acc = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      keep_off[ch] = acc;
+      acc += __popcll(keep_w[ch]);
+    }
+    keep_off[nchunks] = acc;
+    p.out_count[frame] = min(acc, p.max_dets);
+    if (acc > p.max_dets) atomicOr(p.flags + FLAG_DET_OVERFLOW, 1);
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += kNmsThreads) {
+    const unsigned long long w = keep_w[i >> 6];
+    if ((w >> (i & 63)) & 1ull) {
+      const int pos = keep_off[i >> 6] + __popcll(w & ((1ull << (i & 63)) - 1ull));
+      if (pos < p.max_dets) {
+        const size_t o = (size_t)frame * p.max_dets + pos;
+        const float4 b = box[i];
+        reinterpret_cast<float4*>(p.out_box)[o] = b;
+        p.out_conf[o] = unorder_bits((uint32_t)(keys[i] >> 32));
+        p.out_cls[o] = p.cand_cls[cbase + (keys[i] & 0x3fffull)];
+      }
+    }
+  }
+}
+
+static int next_pow2(int v) {
+  int p = 64;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+}  // namespace
+
+size_t nms_smem_bytes(int max_cand) {
+  const size_t cap = (size_t)next_pow2(max_cand);
+  return cap * 24 + cap / 8 + cap / 8 + (cap / 64 + 1) * 4 + 64;
+}
+
+int postprocess_configure(b200va_ctx* h) {
+  const size_t smem = nms_smem_bytes(h->cfg.max_candidates);
+  if (smem > 220 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_candidates %d needs %zu bytes of shared memory", h->cfg.max_candidates, smem);
+  CUDA_TRY(h, cudaFuncSetAttribute(k_sort_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return B200VA_OK;
+}
+
+extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout, int batch, int channels, int anchors,
+                                  const b200va_letterbox* meta, double conf_thr, double iou_thr,
+                                  const int32_t* classes, int n_classes, int score_mode, double filter_conf_thr_f64,
+                                  int use_filter, const b200va_dets* out, void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  REQUIRE(h, head && meta && out && out->bbox_xyxy && out->conf && out->cls && out->count, "NULL argument");
+  REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
+  REQUIRE(h, layout == B200VA_HEAD_CHANNEL_MAJOR || layout == B200VA_HEAD_ANCHOR_MAJOR, "unknown layout %d", layout);
+  REQUIRE(h, score_mode == B200VA_SCORE_REF_COMPAT, "unknown score mode %d", score_mode);
+  REQUIRE(h, anchors >= 0 && anchors <= h->cfg.max_anchors, "anchors %d outside [0, %d]", anchors, h->cfg.max_anchors);
+  // detector.py:285-287: fewer than 5 channels is "unexpected shape" -> no detections
+  if (batch == 0) return B200VA_OK;
+  if (channels < 5 || anchors == 0) {
+    CUDA_TRY(h, cudaMemsetAsync(out->count, 0, sizeof(int32_t) * batch, st));
+    return B200VA_OK;
+  }
+  REQUIRE(h, n_classes >= 0 && (n_classes == 0 || classes), "class whitelist is NULL");
+
+  for (int base = 0; base < batch; base += B200VA_LAUNCH_FRAMES) {
+    const int n = batch - base < B200VA_LAUNCH_FRAMES ? batch - base : B200VA_LAUNCH_FRAMES;
+    PostParams p;
+    memset(&p, 0, sizeof(p));
+    for (int i = 0; i < n; ++i) {
+      const b200va_letterbox& m = meta[base + i];
+      p.f[i].left = (float)m.pad_left;
+      p.f[i].top = (float)m.pad_top;
+      p.f[i].scale = (float)m.scale;  // NumPy rounds the Python float to float32 for `boxes /= scale`
+      p.f[i].xmax = (float)(m.src_w - 1);
+      p.f[i].ymax = (float)(m.src_h - 1);
+    }
+    if (n_classes > 0) {  // an empty list means "no filter" (detector.py:313: `if self.config.classes`)
+      p.use_mask = 1;
+      for (int k = 0; k < n_classes; ++k)
+        if (classes[k] >= 0 && classes[k] < 2048) p.class_mask[classes[k] >> 5] |= 1u << (classes[k] & 31);
+    }
+    p.head = head;
+    p.cand_key = h->cand_key;
+    p.cand_box = h->cand_box;
+    p.cand_cls = h->cand_cls;
+    p.cand_count = h->cand_count;
+    p.C = channels;
+    p.A = anchors;
+    p.max_cand = h->cfg.max_candidates;
+    p.conf_thr = (float)conf_thr;  // NEP-50 weak scalar: compared in float32 (detector.py:312)
+    if (layout == B200VA_HEAD_CHANNEL_MAJOR) {
+      dim3 grid((anchors + 255) / 256, n);
+      k_decode_cm<<<grid, 256, 0, st>>>(p, base);
+    } else {
+      dim3 grid((anchors + 7) / 8, n);
+      k_decode_am<<<grid, 256, 0, st>>>(p, base);
+    }
+    LAUNCH_CHECK(h);
+
+    NmsParams q;
+    q.cand_key = h->cand_key;
+    q.cand_box = h->cand_box;
+    q.cand_cls = h->cand_cls;
+    q.cand_count = h->cand_count;
+    q.flags = h->status_flags;
+    q.out_box = out->bbox_xyxy + (size_t)base * h->cfg.max_dets * 4;
+    q.out_conf = out->conf + (size_t)base * h->cfg.max_dets;
+    q.out_cls = out->cls + (size_t)base * h->cfg.max_dets;
+    q.out_count = out->count + base;
+    q.max_cand = h->cfg.max_candidates;
+    q.max_dets = h->cfg.max_dets;
+    q.cap_pow2 = next_pow2(h->cfg.max_candidates);
+    q.iou_thr = (float)iou_thr;  // detector.py:373 compares float32 IoUs with the weak Python scalar
+    q.filter_thr = filter_conf_thr_f64;
+    q.use_filter = use_filter;
+    k_sort_nms<<<n, kNmsThreads, nms_smem_bytes(h->cfg.max_candidates), st>>>(q);
+    LAUNCH_CHECK(h);
+  }
+  return B200VA_OK;
+}

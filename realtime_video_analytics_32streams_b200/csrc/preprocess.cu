@@ -1,0 +1,546 @@
+// a1 / a2 / a10: batched letterbox preprocess and plain bilinear resize.
+//
+// Replaces _TensorRTBaseDetector._preprocess (detector.py:198-264), RKNNDetector._preprocess
+// (detector.py:777-839) and utils.downsample (frame_filter.py:53-57) of the reference.
+// The interpolation is OpenCV's 8-bit INTER_LINEAR: 11-bit integer tap coefficients per axis,
+// horizontal pass in int32, vertical pass ((b0*(S0>>4))>>16 + (b1*(S1>>4))>>16 + 2) >> 2.
+//
+// Data movement: every CTA owns `rows_per_cta` consecutive output rows of one frame.  Only the
+// source rows that carry a non-zero vertical weight are fetched; each is brought into shared
+// memory whole by ONE 1-D bulk async copy (cp.async.bulk -> UBLKCP, the TMA engine) tracked by an
+// mbarrier, `stages` rows ahead of the row being computed.  Threads then gather their taps from
+// shared memory and write planar output rows with 16-byte stores.  Frames whose base / pitch /
+// row length are not 16-byte multiples take the same code with a cooperative byte loader.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace {
+
+struct __align__(16) TapX {
+  int off0, off1;  // byte offsets of the two taps inside a source row; off0 < 0: pad column
+  short a0, a1;    // 11-bit coefficients
+  int mx0;         // x0 | (x1 << 16): pixel indices for the ROI mask row
+};
+struct __align__(16) TapY {
+  int y0, y1;  // source rows; y0 < 0: pad row
+  short b0, b1;
+  int pad_;
+};
+
+struct PreFrame {
+  const uint8_t* src;
+  const uint8_t* mask;  // optional ROI mask [src_h, src_w], 0 = outside
+  long long pitch;
+  int src_h, src_w;
+  int xtab, ytab;  // offsets (in 16-byte entries) into the tap arena
+  int bulk_ok;     // rows can be fetched with 16-byte bulk copies
+  int mask_bulk_ok;
+};
+
+struct PreParams {
+  PreFrame f[B200VA_LAUNCH_FRAMES];
+  const int4* tabs;
+  void* out;
+  int dst_h, dst_w, fmt, rows_per_cta;
+  int row_stride, mask_stride, stages, vec_ok;
+};
+static_assert(sizeof(PreParams) <= 4000, "kernel parameter block too large");
+
+constexpr int kMaxStages = 4;
+constexpr int kThreads = 160;  // 4 output pixels per thread -> 640 columns
+
+__device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, int bytes) {
+  // generic loader for rows that cannot use 16-byte bulk copies
+  for (int i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+template <int FMT>
+__device__ __forceinline__ void store_px4(const PreParams& p, int frame, int d, int x, const int (&v)[4][3]) {
+  // v[j][c]: pixel x+j, channel c in BGR order, value 0..255
+  const int W = p.dst_w, H = p.dst_h;
+  if (FMT == B200VA_OUT_F32_RGB_NCHW) {
+    float* o = (float*)p.out + (size_t)frame * 3 * H * W;
+    const float k = __int_as_float(0x3B808081);  // float32(1.0/255.0), detector.py:251
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      float* row = o + ((size_t)pl * H + d) * W + x;
+      float r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = __fmul_rn((float)v[j][2 - pl], k);
+      if (p.vec_ok) {
+        *reinterpret_cast<float4*>(row) = make_float4(r[0], r[1], r[2], r[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (x + j < W) row[j] = r[j];
+      }
+    }
+  } else if (FMT == B200VA_OUT_F16_RGB_NCHW) {
+    __half* o = (__half*)p.out + (size_t)frame * 3 * H * W;
+    const float k = 0.0039215087890625f;  // float(float16(1.0/255.0)): NumPy rounds the scalar to half first
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      __half* row = o + ((size_t)pl * H + d) * W + x;
+      __half r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = __float2half_rn(__fmul_rn((float)v[j][2 - pl], k));
+      if (p.vec_ok) {
+        uint2 w;
+        w.x = (uint32_t)__half_as_ushort(r[0]) | ((uint32_t)__half_as_ushort(r[1]) << 16);
+        w.y = (uint32_t)__half_as_ushort(r[2]) | ((uint32_t)__half_as_ushort(r[3]) << 16);
+        *reinterpret_cast<uint2*>(row) = w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (x + j < W) row[j] = r[j];
+      }
+    }
+  } else if (FMT == B200VA_OUT_U8_BGR_NCHW) {
+    uint8_t* o = (uint8_t*)p.out + (size_t)frame * 3 * H * W;
+#pragma unroll
+    for (int pl = 0; pl < 3; ++pl) {
+      uint8_t* row = o + ((size_t)pl * H + d) * W + x;
+      if (p.vec_ok) {
+        *reinterpret_cast<uint32_t*>(row) =
+            (uint32_t)v[0][pl] | ((uint32_t)v[1][pl] << 8) | ((uint32_t)v[2][pl] << 16) | ((uint32_t)v[3][pl] << 24);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (x + j < W) row[j] = (uint8_t)v[j][pl];
+      }
+    }
+  } else {  // B200VA_OUT_U8_BGR_NHWC
+    uint8_t* row = (uint8_t*)p.out + (size_t)frame * 3 * H * W + ((size_t)d * W + x) * 3;
+    if (p.vec_ok) {
+      uint32_t w0 = (uint32_t)v[0][0] | ((uint32_t)v[0][1] << 8) | ((uint32_t)v[0][2] << 16) | ((uint32_t)v[1][0] << 24);
+      uint32_t w1 = (uint32_t)v[1][1] | ((uint32_t)v[1][2] << 8) | ((uint32_t)v[2][0] << 16) | ((uint32_t)v[2][1] << 24);
+      uint32_t w2 = (uint32_t)v[2][2] | ((uint32_t)v[3][0] << 8) | ((uint32_t)v[3][1] << 16) | ((uint32_t)v[3][2] << 24);
+      uint32_t* q = reinterpret_cast<uint32_t*>(row);
+      q[0] = w0;
+      q[1] = w1;
+      q[2] = w2;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (x + j < W) {
+          row[3 * j + 0] = (uint8_t)v[j][0];
+          row[3 * j + 1] = (uint8_t)v[j][1];
+          row[3 * j + 2] = (uint8_t)v[j][2];
+        }
+    }
+  }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreads) k_letterbox(const __grid_constant__ PreParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full[kMaxStages];
+
+  const int frame = blockIdx.y;
+  const PreFrame& f = p.f[frame];
+  const TapX* __restrict__ xt = reinterpret_cast<const TapX*>(p.tabs + f.xtab);
+  const TapY* __restrict__ yt = reinterpret_cast<const TapY*>(p.tabs + f.ytab);
+  const int S = p.stages;
+  const int row_begin = blockIdx.x * p.rows_per_cta;
+  const int nrows = min(p.rows_per_cta, p.dst_h - row_begin);
+  const bool has_mask = f.mask != nullptr;
+  const bool bulk = f.bulk_ok && (!has_mask || f.mask_bulk_ok);
+  uint8_t* const rows_base = smem;
+  uint8_t* const mask_base = smem + (size_t)S * 2 * p.row_stride;
+  const uint32_t row_bytes = 3u * (uint32_t)f.src_w;
+
+  if (bulk && threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // one elected thread feeds the TMA engine
+  auto issue = [&](int i) {
+    const TapY ty = yt[row_begin + i];
+    if (ty.y0 < 0) return;
+    const int s = i % S;
+    uint32_t bytes = 0;
+    if (ty.b0) bytes += row_bytes + (has_mask ? (uint32_t)f.src_w : 0u);
+    if (ty.b1) bytes += row_bytes + (has_mask ? (uint32_t)f.src_w : 0u);
+    mbar_expect_tx(&full[s], bytes);
+    uint8_t* r0 = rows_base + (size_t)(2 * s) * p.row_stride;
+    uint8_t* m0 = mask_base + (size_t)(2 * s) * p.mask_stride;
+    if (ty.b0) {
+      bulk_g2s(r0, f.src + (long long)ty.y0 * f.pitch, row_bytes, &full[s]);
+      if (has_mask) bulk_g2s(m0, f.mask + (size_t)ty.y0 * f.src_w, f.src_w, &full[s]);
+    }
+    if (ty.b1) {
+      bulk_g2s(r0 + p.row_stride, f.src + (long long)ty.y1 * f.pitch, row_bytes, &full[s]);
+      if (has_mask) bulk_g2s(m0 + p.mask_stride, f.mask + (size_t)ty.y1 * f.src_w, f.src_w, &full[s]);
+    }
+  };
+
+  if (bulk && threadIdx.x == 0) {
+    for (int i = 0; i < S - 1 && i < nrows; ++i) issue(i);
+  }
+
+  const int ngroups = (p.dst_w + 3) >> 2;
+  // tap entries of this thread's first pixel group stay in registers across all rows
+  TapX tx[4];
+  {
+    const int g = threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = 4 * g + j;
+      if (g < ngroups && x < p.dst_w) {
+        int4 e = __ldg(reinterpret_cast<const int4*>(xt) + x);
+        tx[j] = *reinterpret_cast<TapX*>(&e);
+      } else {
+        tx[j].off0 = -1;
+        tx[j].off1 = -1;
+        tx[j].a0 = tx[j].a1 = 0;
+        tx[j].mx0 = 0;
+      }
+    }
+  }
+
+  uint32_t phase_bits = 0;
+  for (int i = 0; i < nrows; ++i) {
+    const int d = row_begin + i;
+    const TapY ty = yt[d];
+    const int s = bulk ? (i % S) : 0;
+    const uint8_t* r0 = rows_base + (size_t)(2 * s) * p.row_stride;
+    const uint8_t* r1 = r0 + p.row_stride;
+    const uint8_t* m0 = mask_base + (size_t)(2 * s) * p.mask_stride;
+    const uint8_t* m1 = m0 + p.mask_stride;
+    const bool pad_row = ty.y0 < 0;
+
+    if (bulk) {
+      if (threadIdx.x == 0 && i + S - 1 < nrows) issue(i + S - 1);
+      if (!pad_row) {
+        mbar_wait(&full[s], (phase_bits >> s) & 1u);
+        phase_bits ^= 1u << s;
+      }
+    } else if (!pad_row) {
+      if (ty.b0) {
+        coop_copy(const_cast<uint8_t*>(r0), f.src + (long long)ty.y0 * f.pitch, row_bytes);
+        if (has_mask) coop_copy(const_cast<uint8_t*>(m0), f.mask + (size_t)ty.y0 * f.src_w, f.src_w);
+      }
+      if (ty.b1) {
+        coop_copy(const_cast<uint8_t*>(r1), f.src + (long long)ty.y1 * f.pitch, row_bytes);
+        if (has_mask) coop_copy(const_cast<uint8_t*>(m1), f.mask + (size_t)ty.y1 * f.src_w, f.src_w);
+      }
+      __syncthreads();
+    }
+
+    for (int g = threadIdx.x; g < ngroups; g += blockDim.x) {
+      int v[4][3];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        TapX t;
+        if (g == (int)threadIdx.x) {
+          t = tx[j];
+        } else {
+          const int x = 4 * g + j;
+          if (x < p.dst_w) {
+            int4 e = __ldg(reinterpret_cast<const int4*>(xt) + x);
+            t = *reinterpret_cast<TapX*>(&e);
+          } else {
+            t.off0 = -1;
+          }
+        }
+        if (pad_row || t.off0 < 0) {
+          v[j][0] = v[j][1] = v[j][2] = 114;  // copyMakeBorder value, detector.py:233-241
+          continue;
+        }
+        const int a0 = t.a0, a1 = t.a1, b0 = ty.b0, b1 = ty.b1;
+        int s0[3] = {0, 0, 0}, s1[3] = {0, 0, 0};
+        if (b0) {
+          const bool k0 = a0 && (!has_mask || m0[t.mx0 & 0xffff]);
+          const bool k1 = a1 && (!has_mask || m0[(unsigned)t.mx0 >> 16]);
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            s0[c] = (k0 ? (int)r0[t.off0 + c] * a0 : 0) + (k1 ? (int)r0[t.off1 + c] * a1 : 0);
+        }
+        if (b1) {
+          const bool k0 = a0 && (!has_mask || m1[t.mx0 & 0xffff]);
+          const bool k1 = a1 && (!has_mask || m1[(unsigned)t.mx0 >> 16]);
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            s1[c] = (k0 ? (int)r1[t.off0 + c] * a0 : 0) + (k1 ? (int)r1[t.off1 + c] * a1 : 0);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[j][c] = (((b0 * (s0[c] >> 4)) >> 16) + ((b1 * (s1[c] >> 4)) >> 16) + 2) >> 2;
+      }
+      store_px4<FMT>(p, frame, d, 4 * g, v);
+    }
+    // the stage read in this iteration is refilled by the next iteration's issue()
+    __syncthreads();
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+
+struct TapKey {
+  int axis, src, dst_new, pad, dst_full;
+  bool operator<(const TapKey& o) const {
+    return std::tie(axis, src, dst_new, pad, dst_full) < std::tie(o.axis, o.src, o.dst_new, o.pad, o.dst_full);
+  }
+};
+
+}  // namespace
+
+struct TapCache {
+  int4* arena = nullptr;  // device
+  size_t capacity = 0;    // entries
+  size_t used = 0;
+  std::map<TapKey, int> index;
+};
+
+static const size_t kTapArenaEntries = (size_t)1 << 19;  // 8 MiB of 16-byte entries
+
+int tap_cache_create(b200va_ctx* h) {
+  h->taps = new TapCache();
+  h->taps->capacity = kTapArenaEntries;
+  CUDA_TRY(h, cudaMalloc(&h->taps->arena, kTapArenaEntries * sizeof(int4)));
+  return B200VA_OK;
+}
+
+void tap_cache_destroy(b200va_ctx* h) {
+  if (!h->taps) return;
+  if (h->taps->arena) cudaFree(h->taps->arena);
+  delete h->taps;
+  h->taps = nullptr;
+}
+
+// One axis of cv::resize's 8-bit linear tap table (OpenCV resize.cpp, restated; see
+// oracle/cv_restate.py linear_taps).  clamp_frac = x axis.
+static void linear_tap(int src, int dst, int d, bool clamp_frac, int* i0, int* i1, short* c0, short* c1) {
+  const double inv = (double)dst / (double)src;
+  const double scale = 1.0 / inv;
+  float fx = (float)(((double)d + 0.5) * scale - 0.5);
+  int s = (int)floorf(fx);
+  fx -= (float)s;
+  if (clamp_frac) {
+    if (s < 0) {
+      fx = 0.f;
+      s = 0;
+    }
+    if (s >= src - 1) {
+      fx = 0.f;
+      s = src - 1;
+    }
+  }
+  const float one_minus = 1.f - fx;
+  *c0 = (short)lrintf(one_minus * 2048.f);  // cvRound: round-half-even
+  *c1 = (short)lrintf(fx * 2048.f);
+  int a = s < 0 ? 0 : (s > src - 1 ? src - 1 : s);
+  int b = s + 1 < 0 ? 0 : (s + 1 > src - 1 ? src - 1 : s + 1);
+  *i0 = a;
+  *i1 = b;
+}
+
+// Returns the arena offset of the table, building and uploading it on first use.
+static int get_table(b200va_ctx* h, int axis, int src, int dst_new, int pad, int dst_full, int* off_out) {
+  TapCache* tc = h->taps;
+  TapKey key{axis, src, dst_new, pad, dst_full};
+  auto it = tc->index.find(key);
+  if (it != tc->index.end()) {
+    *off_out = it->second;
+    return B200VA_OK;
+  }
+  if (tc->used + (size_t)dst_full > tc->capacity) {
+    // arena full: drop every cached table (synchronise first, launches may still read them)
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    tc->index.clear();
+    tc->used = 0;
+    if ((size_t)dst_full > tc->capacity) return set_error(h, B200VA_ERR_CAPACITY, "tap table of %d entries does not fit", dst_full);
+  }
+  std::vector<int4> host((size_t)dst_full);
+  for (int d = 0; d < dst_full; ++d) {
+    const int k = d - pad;
+    if (axis == 0) {
+      TapX t;
+      if (k < 0 || k >= dst_new) {
+        t.off0 = t.off1 = -1;
+        t.a0 = t.a1 = 0;
+        t.mx0 = 0;
+      } else {
+        int i0, i1;
+        linear_tap(src, dst_new, k, true, &i0, &i1, &t.a0, &t.a1);
+        t.off0 = 3 * i0;
+        t.off1 = 3 * i1;
+        t.mx0 = i0 | (i1 << 16);
+      }
+      memcpy(&host[d], &t, sizeof(int4));
+    } else {
+      TapY t;
+      t.pad_ = 0;
+      if (k < 0 || k >= dst_new) {
+        t.y0 = t.y1 = -1;
+        t.b0 = t.b1 = 0;
+      } else {
+        linear_tap(src, dst_new, k, false, &t.y0, &t.y1, &t.b0, &t.b1);
+      }
+      memcpy(&host[d], &t, sizeof(int4));
+    }
+  }
+  const int off = (int)tc->used;
+  // synchronous copy: the table is visible to every stream once this returns
+  CUDA_TRY(h, cudaMemcpy(tc->arena + off, host.data(), host.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  tc->used += (size_t)dst_full;
+  tc->index[key] = off;
+  *off_out = off;
+  return B200VA_OK;
+}
+
+extern "C" int b200va_letterbox_meta(int src_h, int src_w, int dst_h, int dst_w, b200va_letterbox* out) {
+  if (!out || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0) return B200VA_ERR_INVALID;
+  const double sw = (double)dst_w / (double)src_w, sh = (double)dst_h / (double)src_h;
+  const double scale = sw < sh ? sw : sh;        // min(target_w / w, target_h / h), detector.py:211
+  out->src_h = src_h;
+  out->src_w = src_w;
+  out->new_w = (int)((double)src_w * scale);     // int() truncation, detector.py:214-215
+  out->new_h = (int)((double)src_h * scale);
+  out->pad_left = (dst_w - out->new_w) / 2;      // pad // 2, detector.py:228-230 (pads are >= 0)
+  out->pad_top = (dst_h - out->new_h) / 2;
+  out->scale = scale;
+  return B200VA_OK;
+}
+
+template <int FMT>
+static cudaError_t launch_letterbox(const PreParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  k_letterbox<FMT><<<grid, kThreads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+static const int kLetterboxSmemMax = 200 * 1024;
+
+int preprocess_configure(b200va_ctx* h) {
+  CUDA_TRY(h, cudaFuncSetAttribute(k_letterbox<B200VA_OUT_F32_RGB_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_letterbox<B200VA_OUT_F16_RGB_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_letterbox<B200VA_OUT_U8_BGR_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_letterbox<B200VA_OUT_U8_BGR_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax));
+  return B200VA_OK;
+}
+
+// Shared by b200va_preprocess (letterbox geometry) and b200va_resize_linear_u8 (no padding).
+static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* src_h, const int* src_w,
+                        const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks, void* out,
+                        uint8_t* const* out_ptrs, const int* new_h, const int* new_w, const int* pad_top,
+                        const int* pad_left, int dst_h, int dst_w, int fmt, cudaStream_t st) {
+  const size_t esize = fmt == B200VA_OUT_F32_RGB_NCHW ? 4 : (fmt == B200VA_OUT_F16_RGB_NCHW ? 2 : 1);
+  for (int base = 0; base < batch;) {
+    // frames written through per-frame output pointers are launched one by one
+    const int n = out_ptrs ? 1 : (batch - base < B200VA_LAUNCH_FRAMES ? batch - base : B200VA_LAUNCH_FRAMES);
+    PreParams p;
+    memset(&p, 0, sizeof(p));
+    int max_row = 0, max_w = 0, any_mask = 0;
+    for (int i = 0; i < n; ++i) {
+      const int b = base + i;
+      PreFrame& f = p.f[i];
+      REQUIRE(h, frames[b] != nullptr, "frame %d is NULL", b);
+      REQUIRE(h, src_h[b] > 0 && src_w[b] > 0 && src_w[b] < 65536, "frame %d has unsupported size %dx%d", b, src_w[b], src_h[b]);
+      const int64_t pitch = src_pitch ? src_pitch[b] : (int64_t)3 * src_w[b];
+      REQUIRE(h, pitch >= (int64_t)3 * src_w[b], "frame %d: pitch %lld < 3*width", b, (long long)pitch);
+      REQUIRE(h, new_h[b] > 0 && new_w[b] > 0, "frame %d: resized size %dx%d is empty (cv2.resize would raise)", b, new_w[b], new_h[b]);
+      f.src = frames[b];
+      f.mask = roi_masks ? roi_masks[b] : nullptr;
+      f.pitch = pitch;
+      f.src_h = src_h[b];
+      f.src_w = src_w[b];
+      int rc = get_table(h, 0, src_w[b], new_w[b], pad_left[b], dst_w, &f.xtab);
+      if (rc) return rc;
+      rc = get_table(h, 1, src_h[b], new_h[b], pad_top[b], dst_h, &f.ytab);
+      if (rc) return rc;
+      const int rb = 3 * src_w[b];
+      f.bulk_ok = ((uintptr_t)f.src % 16 == 0) && (pitch % 16 == 0) && (rb % 16 == 0);
+      f.mask_bulk_ok = f.mask ? (((uintptr_t)f.mask % 16 == 0) && (src_w[b] % 16 == 0)) : 1;
+      if (rb > max_row) max_row = rb;
+      if (src_w[b] > max_w) max_w = src_w[b];
+      any_mask |= f.mask != nullptr;
+    }
+    p.tabs = h->taps->arena;
+    p.out = out_ptrs ? (void*)out_ptrs[base] : (void*)((uint8_t*)out + (size_t)base * 3 * dst_h * dst_w * esize);
+    p.dst_h = dst_h;
+    p.dst_w = dst_w;
+    p.fmt = fmt;
+    p.row_stride = (max_row + 127) & ~127;
+    p.mask_stride = any_mask ? ((max_w + 127) & ~127) : 0;
+    const size_t per_stage = 2 * ((size_t)p.row_stride + p.mask_stride);
+    const size_t budget = 160 * 1024;
+    int stages = (int)(budget / per_stage);
+    if (stages > kMaxStages) stages = kMaxStages;
+    REQUIRE(h, stages >= 1, "source rows of %d bytes do not fit in shared memory", max_row);
+    p.stages = stages;
+    // enough CTAs for several waves over the SMs, few enough that the tap registers amortise
+    long long total_rows = (long long)n * dst_h;
+    int rpc = (int)(total_rows / ((long long)h->num_sms * 16));
+    if (rpc < 2) rpc = 2;
+    if (rpc > 16) rpc = 16;
+    p.rows_per_cta = rpc;
+    const uintptr_t ob = (uintptr_t)p.out;
+    switch (fmt) {
+      case B200VA_OUT_F32_RGB_NCHW: p.vec_ok = (dst_w % 4 == 0) && (ob % 16 == 0); break;
+      case B200VA_OUT_F16_RGB_NCHW: p.vec_ok = (dst_w % 4 == 0) && (ob % 8 == 0); break;
+      case B200VA_OUT_U8_BGR_NCHW: p.vec_ok = (dst_w % 4 == 0) && (ob % 4 == 0); break;
+      default: p.vec_ok = (dst_w % 4 == 0) && (ob % 4 == 0); break;
+    }
+    dim3 grid((dst_h + rpc - 1) / rpc, n);
+    const size_t smem = (size_t)stages * per_stage;
+    cudaError_t e;
+    switch (fmt) {
+      case B200VA_OUT_F32_RGB_NCHW: e = launch_letterbox<B200VA_OUT_F32_RGB_NCHW>(p, grid, smem, st); break;
+      case B200VA_OUT_F16_RGB_NCHW: e = launch_letterbox<B200VA_OUT_F16_RGB_NCHW>(p, grid, smem, st); break;
+      case B200VA_OUT_U8_BGR_NCHW: e = launch_letterbox<B200VA_OUT_U8_BGR_NCHW>(p, grid, smem, st); break;
+      case B200VA_OUT_U8_BGR_NHWC: e = launch_letterbox<B200VA_OUT_U8_BGR_NHWC>(p, grid, smem, st); break;
+      default: return set_error(h, B200VA_ERR_INVALID, "unknown output format %d", fmt);
+    }
+    h->launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return set_error(h, B200VA_ERR_CUDA, "letterbox launch failed: %s", cudaGetErrorString(e));
+    base += n;
+  }
+  return B200VA_OK;
+}
+
+extern "C" int b200va_preprocess(b200va_handle h, const uint8_t* const* frames, const int* src_h, const int* src_w,
+                                 const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks, void* out,
+                                 int dst_h, int dst_w, int out_format, b200va_letterbox* meta_out, void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  REQUIRE(h, frames && src_h && src_w && out, "NULL argument");
+  REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
+  REQUIRE(h, dst_h > 0 && dst_w > 0 && dst_w < 65536, "bad destination size %dx%d", dst_w, dst_h);
+  if (batch == 0) return B200VA_OK;
+  std::vector<int> nh(batch), nw(batch), pt(batch), pl(batch);
+  for (int b = 0; b < batch; ++b) {
+    b200va_letterbox m;
+    REQUIRE(h, b200va_letterbox_meta(src_h[b], src_w[b], dst_h, dst_w, &m) == B200VA_OK, "frame %d: bad size %dx%d", b, src_w[b], src_h[b]);
+    nh[b] = m.new_h;
+    nw[b] = m.new_w;
+    pt[b] = m.pad_top;
+    pl[b] = m.pad_left;
+    if (meta_out) meta_out[b] = m;
+  }
+  return run_resample(h, frames, src_h, src_w, src_pitch, batch, roi_masks, out, nullptr, nh.data(), nw.data(),
+                      pt.data(), pl.data(), dst_h, dst_w, out_format, (cudaStream_t)stream);
+}
+
+extern "C" int b200va_resize_linear_u8(b200va_handle h, const uint8_t* const* frames, const int* src_h,
+                                       const int* src_w, const int64_t* src_pitch, int batch,
+                                       const uint8_t* const* roi_masks, uint8_t* const* dst, const int* dst_h,
+                                       const int* dst_w, void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  REQUIRE(h, frames && src_h && src_w && dst && dst_h && dst_w, "NULL argument");
+  REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
+  const int zero = 0;
+  for (int b = 0; b < batch; ++b) {
+    REQUIRE(h, dst[b] != nullptr, "dst %d is NULL", b);
+    REQUIRE(h, dst_h[b] > 0 && dst_w[b] > 0 && dst_w[b] < 65536, "frame %d: bad destination size %dx%d", b, dst_w[b], dst_h[b]);
+    int rc = run_resample(h, frames + b, src_h + b, src_w + b, src_pitch ? src_pitch + b : nullptr, 1,
+                          roi_masks ? roi_masks + b : nullptr, nullptr, dst + b, dst_h + b, dst_w + b, &zero, &zero,
+                          dst_h[b], dst_w[b], B200VA_OUT_U8_BGR_NHWC, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return B200VA_OK;
+}

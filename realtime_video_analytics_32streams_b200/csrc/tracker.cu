@@ -1,0 +1,476 @@
+// a8: the IoU tracker for a batch of streams, state resident in HBM.
+//
+// Replaces IouTracker.update (tracker.py:50-95), _match_detection (:97-109), _prune_tracks
+// (:111-126) and _iou (:129-147).  The reference is sequential and order dependent: detections
+// are matched one after another, a matched track's box is overwritten at once, a new track is
+// matchable by later detections of the same frame, and ties go to the earliest-inserted track.
+// One CTA owns one stream: detections are visited in order, and for each one all threads score
+// the live tracks in parallel (float64, Python's operation order) followed by a block arg-max
+// with the reference's tie rule.  Pruning is a stable block compaction into the slot's second
+// buffer, which preserves dict insertion order.  Track ids come from one counter shared by all
+// streams (tracker.py:47): CTAs hand out provisional ordinals and the last CTA to finish turns
+// them into ids in batch order -- the order one shared IouTracker would have been called in.
+#include "common.cuh"
+
+struct TrackerState {
+  // ping-pong buffers, each [max_streams, max_tracks]
+  long long* id[2];
+  int32_t* cls[2];
+  double* conf[2];
+  double* box[2];  // [.., 4]
+  int32_t* age[2];
+  int32_t* hits[2];
+  uint8_t* touched;   // [max_streams, max_tracks]
+  int32_t* count;     // [max_streams]
+  int32_t* cur;       // [max_streams] current buffer index
+  long long* next_id; // shared counter
+  uint32_t* ticket;   // last-CTA election
+  int32_t* new_count; // [max_batch] scratch
+  void* base = nullptr;
+};
+
+namespace {
+
+struct TrkParams {
+  TrackerState st;
+  int slots[B200VA_MAX_BATCH];
+  double det_scale[B200VA_MAX_BATCH];
+  long long id_base[B200VA_MAX_BATCH];
+  uint8_t skip[B200VA_MAX_BATCH];
+  // detections (one of the two sources)
+  const float* f_box;
+  const float* f_conf;
+  const double* d_box;
+  const double* d_conf;
+  const int32_t* d_cls;
+  const int32_t* d_count;
+  int max_dets, max_tracks, batch;
+  int max_age, min_hits;
+  double thr;
+  int has_id_base, has_scale;
+  // outputs (optional)
+  long long* o_id;
+  int32_t* o_cls;
+  double* o_conf;
+  double* o_box;
+  int32_t* o_age;
+  int32_t* o_hits;
+  int32_t* o_count;
+  int32_t* o_new;
+  int32_t* flags;
+};
+
+constexpr int kTrkThreads = 256;
+
+// tracker.py:129-147, IEEE double, no contraction.
+__device__ __forceinline__ double iou64(double ax1, double ay1, double ax2, double ay2, double bx1, double by1,
+                                        double bx2, double by2) {
+  const double iw = fmax(0.0, __dsub_rn(fmin(ax2, bx2), fmax(ax1, bx1)));
+  const double ih = fmax(0.0, __dsub_rn(fmin(ay2, by2), fmax(ay1, by1)));
+  const double inter = __dmul_rn(iw, ih);
+  const double area_a = __dmul_rn(fmax(0.0, __dsub_rn(ax2, ax1)), fmax(0.0, __dsub_rn(ay2, ay1)));
+  const double area_b = __dmul_rn(fmax(0.0, __dsub_rn(bx2, bx1)), fmax(0.0, __dsub_rn(by2, by1)));
+  const double uni = __dsub_rn(__dadd_rn(area_a, area_b), inter);
+  if (uni <= 0.0) return 0.0;
+  return __ddiv_rn(inter, uni);
+}
+
+__global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__ TrkParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  double* sbox = reinterpret_cast<double*>(smem_raw);                            // [max_tracks][4]
+  int32_t* scls = reinterpret_cast<int32_t*>(sbox + (size_t)p.max_tracks * 4);   // [max_tracks]
+  __shared__ double red_iou[kTrkThreads / 32];
+  __shared__ int red_t[kTrkThreads / 32];
+  __shared__ int s_T, s_new, s_is_last;
+
+  const int bi = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = p.slots[bi];
+  const TrackerState& S = p.st;
+  const int cur = S.cur[slot];
+  const size_t sb = (size_t)slot * p.max_tracks;
+  long long* id_c = S.id[cur] + sb;
+  int32_t* cls_c = S.cls[cur] + sb;
+  double* conf_c = S.conf[cur] + sb;
+  double* box_c = S.box[cur] + sb * 4;
+  int32_t* age_c = S.age[cur] + sb;
+  int32_t* hits_c = S.hits[cur] + sb;
+  uint8_t* touched = S.touched + sb;
+  const int T0 = S.count[slot];
+
+  for (int t = tid; t < T0; t += kTrkThreads) {
+    const double4 b0 = reinterpret_cast<const double4*>(box_c)[t];
+    reinterpret_cast<double4*>(sbox)[t] = b0;
+    scls[t] = cls_c[t];
+    touched[t] = 0;
+  }
+  if (tid == 0) {
+    s_T = T0;
+    s_new = 0;
+  }
+  __syncthreads();
+
+  const int D = p.skip[bi] ? 0 : min(p.d_count[bi], p.max_dets);
+  const size_t db = (size_t)bi * p.max_dets;
+  const double scale = p.det_scale[bi];
+  for (int d = 0; d < D; ++d) {
+    double bx1, by1, bx2, by2, dconf;
+    if (p.f_box) {
+      const float4 b = reinterpret_cast<const float4*>(p.f_box)[db + d];
+      bx1 = b.x, by1 = b.y, bx2 = b.z, by2 = b.w;
+      dconf = (double)p.f_conf[db + d];
+      if (p.has_scale) {  // StreamWorker._rescale_detections, pipeline.py:224-240: float64 multiply
+        bx1 = __dmul_rn(bx1, scale);
+        by1 = __dmul_rn(by1, scale);
+        bx2 = __dmul_rn(bx2, scale);
+        by2 = __dmul_rn(by2, scale);
+      }
+    } else {
+      const double4 b = reinterpret_cast<const double4*>(p.d_box)[db + d];
+      bx1 = b.x, by1 = b.y, bx2 = b.z, by2 = b.w;
+      dconf = p.d_conf[db + d];
+    }
+    const int dcls = p.d_cls[db + d];
+    const int T = s_T;
+
+    double best = 0.0;  // best_iou starts at 0.0 and must be beaten strictly (tracker.py:100-106)
+    int best_t = 0x7fffffff;
+    for (int t = tid; t < T; t += kTrkThreads) {
+      if (scls[t] != dcls) continue;
+      const double4 tb = reinterpret_cast<const double4*>(sbox)[t];
+      // boxes that do not overlap have IoU 0, which can never beat best_iou
+      if (!(fmin(tb.z, bx2) > fmax(tb.x, bx1)) || !(fmin(tb.w, by2) > fmax(tb.y, by1))) continue;
+      const double v = iou64(tb.x, tb.y, tb.z, tb.w, bx1, by1, bx2, by2);
+      if (v >= p.thr && v > best) {
+        best = v;
+        best_t = t;
+      }
+    }
+    const int any = __syncthreads_or(best_t != 0x7fffffff);
+    int match = -1;
+    if (any) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ot = __shfl_xor_sync(0xffffffffu, best_t, o);
+        if (ob > best || (ob == best && ot < best_t)) {
+          best = ob;
+          best_t = ot;
+        }
+      }
+      if (lane == 0) {
+        red_iou[warp] = best;
+        red_t[warp] = best_t;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double b = red_iou[0];
+        int bt = red_t[0];
+        for (int w = 1; w < kTrkThreads / 32; ++w)
+          if (red_iou[w] > b || (red_iou[w] == b && red_t[w] < bt)) {
+            b = red_iou[w];
+            bt = red_t[w];
+          }
+        match = bt;
+      }
+    }
+    if (tid == 0) {
+      int t = match;
+      if (t < 0 || t == 0x7fffffff) {  // tracker.py:69-80: new track, matchable at once
+        t = T;
+        if (t < p.max_tracks) {
+          const int ord = s_new;
+          id_c[t] = p.has_id_base ? p.id_base[bi] + ord : -(long long)(ord + 1);
+          cls_c[t] = dcls;
+          scls[t] = dcls;
+          hits_c[t] = 1;
+          s_new = ord + 1;
+          s_T = T + 1;
+        } else {
+          atomicOr(p.flags + FLAG_TRACK_OVERFLOW, 1);
+          t = -1;
+        }
+      } else {  // tracker.py:82-86: overwrite immediately
+        hits_c[t] += 1;
+      }
+      if (t >= 0) {
+        reinterpret_cast<double4*>(sbox)[t] = make_double4(bx1, by1, bx2, by2);
+        conf_c[t] = dconf;
+        age_c[t] = 0;
+        touched[t] = 1;
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- prune + stable compaction into the other buffer (tracker.py:111-126) ----
+  const int T = s_T;
+  const int nxt = cur ^ 1;
+  long long* id_n = S.id[nxt] + sb;
+  int32_t* cls_n = S.cls[nxt] + sb;
+  double* conf_n = S.conf[nxt] + sb;
+  double* box_n = S.box[nxt] + sb * 4;
+  int32_t* age_n = S.age[nxt] + sb;
+  int32_t* hits_n = S.hits[nxt] + sb;
+  const size_t ob = (size_t)bi * p.max_tracks;
+  __shared__ int warp_cnt[kTrkThreads / 32];
+  __shared__ int s_base;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < T; t0 += kTrkThreads) {
+    const int t = t0 + tid;
+    bool keep = false;
+    int age = 0, hits = 0;
+    if (t < T) {
+      age = age_c[t];
+      hits = hits_c[t];
+      if (touched[t]) {
+        keep = true;
+      } else {
+        age += 1;
+        keep = !(age > p.max_age || hits < p.min_hits);
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    if (keep) {
+      const int dst = off + __popc(bal & ((1u << lane) - 1u));
+      const long long idv = id_c[t];
+      const double cf = conf_c[t];
+      const double4 b = reinterpret_cast<const double4*>(sbox)[t];
+      id_n[dst] = idv;
+      cls_n[dst] = scls[t];
+      conf_n[dst] = cf;
+      reinterpret_cast<double4*>(box_n)[dst] = b;
+      age_n[dst] = age;
+      hits_n[dst] = hits;
+      if (p.o_id) {
+        p.o_id[ob + dst] = idv;
+        p.o_cls[ob + dst] = scls[t];
+        p.o_conf[ob + dst] = cf;
+        reinterpret_cast<double4*>(p.o_box)[ob + dst] = b;
+        p.o_age[ob + dst] = age;
+        p.o_hits[ob + dst] = hits;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < kTrkThreads / 32; ++w) tot += warp_cnt[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    S.count[slot] = s_base;
+    S.cur[slot] = nxt;
+    S.new_count[bi] = s_new;
+    if (p.o_count) p.o_count[bi] = s_base;
+    if (p.o_new) p.o_new[bi] = s_new;
+  }
+
+  // ---- shared id counter: last CTA converts provisional ordinals to ids in batch order ----
+  if (p.has_id_base) return;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned tk = atomicAdd(S.ticket, 1u);
+    s_is_last = (tk == (unsigned)p.batch - 1u);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+  long long next = *S.next_id;
+  for (int i = 0; i < p.batch; ++i) {
+    const int sl = p.slots[i];
+    const int nnew = ((volatile int32_t*)S.new_count)[i];
+    if (nnew > 0) {
+      const int c = ((volatile int32_t*)S.cur)[sl];
+      const int cnt = ((volatile int32_t*)S.count)[sl];
+      long long* ids = S.id[c] + (size_t)sl * p.max_tracks;
+      for (int t = tid; t < cnt; t += kTrkThreads) {
+        const long long v = ((volatile long long*)ids)[t];
+        if (v < 0) {
+          const long long real = next + (-v - 1);
+          ids[t] = real;
+          if (p.o_id) p.o_id[(size_t)i * p.max_tracks + t] = real;
+        }
+      }
+    }
+    next += nnew;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    *S.next_id = next;
+    *S.ticket = 0u;
+  }
+}
+
+__global__ void k_tracker_reset(TrackerState S, int slot) {
+  S.count[slot] = 0;
+}
+__global__ void k_tracker_set_next(TrackerState S, long long v) { *S.next_id = v; }
+
+}  // namespace
+
+int tracker_state_create(b200va_ctx* h) {
+  TrackerState* S = new TrackerState();
+  h->tracker = S;
+  const size_t n = (size_t)h->cfg.max_streams * h->cfg.max_tracks;
+  // one arena: 2 x (id 8 + cls 4 + conf 8 + box 32 + age 4 + hits 4) + touched 1, plus the small arrays
+  size_t bytes = 0;
+  auto take = [&](size_t b) {
+    size_t o = bytes;
+    bytes += (b + 255) & ~(size_t)255;
+    return o;
+  };
+  size_t o_id[2], o_cls[2], o_conf[2], o_box[2], o_age[2], o_hits[2];
+  for (int k = 0; k < 2; ++k) {
+    o_box[k] = take(n * 32);
+    o_id[k] = take(n * 8);
+    o_conf[k] = take(n * 8);
+    o_cls[k] = take(n * 4);
+    o_age[k] = take(n * 4);
+    o_hits[k] = take(n * 4);
+  }
+  size_t o_touched = take(n);
+  size_t o_count = take((size_t)h->cfg.max_streams * 4);
+  size_t o_cur = take((size_t)h->cfg.max_streams * 4);
+  size_t o_next = take(8);
+  size_t o_ticket = take(4);
+  size_t o_new = take((size_t)B200VA_MAX_BATCH * 4);
+  CUDA_TRY(h, cudaMalloc(&S->base, bytes));
+  CUDA_TRY(h, cudaMemset(S->base, 0, bytes));
+  uint8_t* b = (uint8_t*)S->base;
+  for (int k = 0; k < 2; ++k) {
+    S->box[k] = (double*)(b + o_box[k]);
+    S->id[k] = (long long*)(b + o_id[k]);
+    S->conf[k] = (double*)(b + o_conf[k]);
+    S->cls[k] = (int32_t*)(b + o_cls[k]);
+    S->age[k] = (int32_t*)(b + o_age[k]);
+    S->hits[k] = (int32_t*)(b + o_hits[k]);
+  }
+  S->touched = b + o_touched;
+  S->count = (int32_t*)(b + o_count);
+  S->cur = (int32_t*)(b + o_cur);
+  S->next_id = (long long*)(b + o_next);
+  S->ticket = (uint32_t*)(b + o_ticket);
+  S->new_count = (int32_t*)(b + o_new);
+  const long long one = 1;  // itertools.count(1), tracker.py:47
+  CUDA_TRY(h, cudaMemcpy(S->next_id, &one, 8, cudaMemcpyHostToDevice));
+  const size_t smem = (size_t)h->cfg.max_tracks * 36;
+  if (smem > 200 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_tracks %d too large (<= 5600)", h->cfg.max_tracks);
+  CUDA_TRY(h, cudaFuncSetAttribute(k_tracker, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return B200VA_OK;
+}
+
+void tracker_state_destroy(b200va_ctx* h) {
+  if (!h->tracker) return;
+  if (h->tracker->base) cudaFree(h->tracker->base);
+  delete h->tracker;
+  h->tracker = nullptr;
+}
+
+static int tracker_launch(b200va_ctx* h, TrkParams& p, const int* stream_slots, int batch, const double* det_scale,
+                          const uint8_t* skip, const b200va_tracker_cfg* cfg, const int64_t* id_base,
+                          const b200va_tracks* out, int32_t* new_counts, cudaStream_t st) {
+  REQUIRE(h, stream_slots && cfg, "NULL argument");
+  REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch && batch <= B200VA_MAX_BATCH, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
+  if (batch == 0) return B200VA_OK;
+  uint8_t seen[4096 / 8] = {0};
+  for (int i = 0; i < batch; ++i) {
+    const int s = stream_slots[i];
+    REQUIRE(h, s >= 0 && s < h->cfg.max_streams, "stream slot %d outside [0, %d)", s, h->cfg.max_streams);
+    if (s < 4096) {
+      REQUIRE(h, !(seen[s >> 3] & (1 << (s & 7))), "stream slot %d appears twice in one call", s);
+      seen[s >> 3] |= 1 << (s & 7);
+    }
+    p.slots[i] = s;
+    p.det_scale[i] = det_scale ? det_scale[i] : 1.0;
+    p.id_base[i] = id_base ? id_base[i] : 0;
+    p.skip[i] = skip ? skip[i] : 0;
+  }
+  p.st = *h->tracker;
+  p.max_tracks = h->cfg.max_tracks;
+  p.batch = batch;
+  p.max_age = cfg->max_age;
+  p.min_hits = cfg->min_hits;
+  p.thr = cfg->max_iou_distance;
+  p.has_id_base = id_base != nullptr;
+  p.has_scale = det_scale != nullptr;
+  if (out) {
+    REQUIRE(h, out->track_id && out->cls && out->conf && out->bbox_xyxy && out->age && out->hits && out->count, "NULL output array");
+    p.o_id = (long long*)out->track_id;
+    p.o_cls = out->cls;
+    p.o_conf = out->conf;
+    p.o_box = out->bbox_xyxy;
+    p.o_age = out->age;
+    p.o_hits = out->hits;
+    p.o_count = out->count;
+  }
+  p.o_new = new_counts;
+  p.flags = h->status_flags;
+  k_tracker<<<batch, kTrkThreads, (size_t)h->cfg.max_tracks * 36, st>>>(p);
+  LAUNCH_CHECK(h);
+  return B200VA_OK;
+}
+
+extern "C" int b200va_tracker_update(b200va_handle h, const int* stream_slots, int batch, const b200va_dets* dets,
+                                     int max_dets, const double* det_scale, const uint8_t* skip,
+                                     const b200va_tracker_cfg* cfg, const int64_t* id_base, const b200va_tracks* out,
+                                     int32_t* new_counts, void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  REQUIRE(h, dets && dets->bbox_xyxy && dets->conf && dets->cls && dets->count, "NULL detections");
+  REQUIRE(h, max_dets > 0, "max_dets must be positive");
+  TrkParams p;
+  memset(&p, 0, sizeof(p));
+  p.f_box = dets->bbox_xyxy;
+  p.f_conf = dets->conf;
+  p.d_cls = dets->cls;
+  p.d_count = dets->count;
+  p.max_dets = max_dets;
+  return tracker_launch(h, p, stream_slots, batch, det_scale, skip, cfg, id_base, out, new_counts, (cudaStream_t)stream);
+}
+
+extern "C" int b200va_tracker_update_f64(b200va_handle h, const int* stream_slots, int batch, const b200va_dets64* dets,
+                                         int max_dets, const uint8_t* skip, const b200va_tracker_cfg* cfg,
+                                         const int64_t* id_base, const b200va_tracks* out, int32_t* new_counts,
+                                         void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  REQUIRE(h, dets && dets->bbox_xyxy && dets->conf && dets->cls && dets->count, "NULL detections");
+  REQUIRE(h, max_dets > 0, "max_dets must be positive");
+  TrkParams p;
+  memset(&p, 0, sizeof(p));
+  p.d_box = dets->bbox_xyxy;
+  p.d_conf = dets->conf;
+  p.d_cls = dets->cls;
+  p.d_count = dets->count;
+  p.max_dets = max_dets;
+  return tracker_launch(h, p, stream_slots, batch, nullptr, skip, cfg, id_base, out, new_counts, (cudaStream_t)stream);
+}
+
+extern "C" int b200va_tracker_reset(b200va_handle h, int stream_slot, void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  REQUIRE(h, stream_slot >= 0 && stream_slot < h->cfg.max_streams, "stream slot %d outside [0, %d)", stream_slot, h->cfg.max_streams);
+  k_tracker_reset<<<1, 1, 0, (cudaStream_t)stream>>>(*h->tracker, stream_slot);
+  LAUNCH_CHECK(h);
+  return B200VA_OK;
+}
+
+extern "C" int b200va_tracker_set_next_id(b200va_handle h, int64_t next_id, void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  k_tracker_set_next<<<1, 1, 0, (cudaStream_t)stream>>>(*h->tracker, (long long)next_id);
+  LAUNCH_CHECK(h);
+  return B200VA_OK;
+}

@@ -1,0 +1,147 @@
+"""Detector plug-in: the reference's ``BaseDetector`` contract on top of the sm_100a kernels.
+
+Mirrors ``_TensorRTBaseDetector`` (detector.py:182-379 of the reference): ``predict`` is
+``_preprocess -> _infer -> _postprocess`` with the same argument meaning, the same ``meta`` dict
+and the same error behaviour, but the three steps run on the GPU through ``libb200va`` and every
+intermediate stays in HBM.  ``_infer`` is the detector forward -- outside the kernel scope -- and
+is supplied by the caller as any callable from the network input ``[B,3,H,W]`` (CUDA) to the
+decoded head ``[B,C,A]`` / ``[B,A,C]`` (CUDA), e.g. a ``torch.nn.Module``.
+
+``predict_batch`` is additive API (the reference is strictly batch-1, detector.py:280-281).
+"""
+
+from __future__ import annotations
+
+import logging
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native
+from .runtime import FrameStager, get_handle
+from .types import Detection, FramePacket
+
+LOGGER = logging.getLogger(__name__)
+
+
+def filter_detections(detections, min_confidence: float) -> List[Detection]:
+    """detector.py:99-103 -- kept for callers that hold Python detections; the batched path folds
+    this float64 comparison into the NMS emit step instead."""
+    return [det for det in detections if det.confidence >= min_confidence]
+
+
+class B200Detector:
+    """Drop-in for the reference's numpy-path detectors (``backend: b200``)."""
+
+    def __init__(self, config, input_hw: Optional[Sequence[int]] = None, infer: Optional[Callable] = None,
+                 handle: Optional[_native.Handle] = None, fold_filter: bool = False):
+        self.config = config
+        if input_hw is None:
+            size = getattr(config, "input_size", None)
+            input_hw = (int(size[0]), int(size[1])) if size else (640, 640)
+        self.input_hw = (int(input_hw[0]), int(input_hw[1]))
+        self.h = handle if handle is not None else get_handle()
+        self._infer_fn = infer
+        self._stager = FrameStager(self.h)
+        # fold_filter=True applies filter_detections (pipeline.py:182) inside the kernel
+        self.fold_filter = fold_filter
+
+    # ---- the three reference steps ---------------------------------------------------------
+    @property
+    def _fmt(self) -> int:
+        return _native.OUT_F16_RGB_NCHW if getattr(self.config, "half", False) else _native.OUT_F32_RGB_NCHW
+
+    def _preprocess(self, frame, roi_mask=None):
+        """detector.py:198-264.  Returns (CUDA tensor [1,3,H,W], meta dict)."""
+        dev = self._stager.upload([frame])
+        tensor, metas = self.h.preprocess(dev, self.input_hw, self._fmt, [roi_mask] if roi_mask is not None else None)
+        return tensor, metas[0].as_meta()
+
+    def _preprocess_batch(self, frames, roi_masks=None):
+        dev = self._stager.upload(frames)
+        return self.h.preprocess(dev, self.input_hw, self._fmt, roi_masks)
+
+    def _infer(self, tensor):
+        if self._infer_fn is None:
+            raise RuntimeError("B200Detector has no model: pass infer=<callable [B,3,H,W] -> head>")
+        return self._infer_fn(tensor)
+
+    def _as_head(self, predictions):
+        """Normalise whatever ``_infer`` returned to a contiguous CUDA float32 [B, d1, d2]."""
+        t = self.h.torch
+        if isinstance(predictions, (list, tuple)):
+            predictions = predictions[0]  # detector.py:278-279
+        if isinstance(predictions, np.ndarray):
+            predictions = t.from_numpy(np.ascontiguousarray(predictions, dtype=np.float32))
+        if not predictions.is_cuda:
+            predictions = predictions.to(self.h.device, non_blocking=True)
+        if predictions.dtype != t.float32:
+            predictions = predictions.float()
+        return predictions.contiguous()
+
+    def _postprocess(self, predictions, packet: FramePacket, meta: dict) -> List[Detection]:
+        """detector.py:266-338 for one frame (batch-1 like the reference)."""
+        head = self._as_head(predictions)
+        if head.dim() == 3:
+            if head.shape[0] != 1:  # np.squeeze(axis=0) on a batch > 1
+                raise ValueError("cannot select an axis to squeeze out which has size not equal to one")
+        elif head.dim() == 2:
+            head = head[None]
+        else:
+            LOGGER.warning("Unexpected prediction shape: %s", tuple(head.shape))
+            return []
+        _, d1, d2 = head.shape
+        channels = d2 if not (d1 != 0 and d1 < d2) else d1
+        if channels < 5:
+            LOGGER.warning("Unexpected prediction shape: %s", (d1, d2))
+            return []
+        oh, ow = meta["orig_shape"]
+        lb = _native.letterbox_meta(int(oh), int(ow), self.input_hw[0], self.input_hw[1])
+        # honour a caller-edited meta (scale / pad) exactly like _scale_boxes would
+        lb.scale = float(meta["scale"])
+        lb.pad_left, lb.pad_top = int(meta["pad"][0]), int(meta["pad"][1])
+        dets = self._run_post(head, [lb])
+        return self._to_detections(dets, [packet])[0]
+
+    # ---- public API ------------------------------------------------------------------------
+    def predict(self, packet: FramePacket) -> List[Detection]:
+        tensor, meta = self._preprocess(packet.frame)
+        raw = self._infer(tensor)
+        return self._postprocess(raw, packet, meta)
+
+    def predict_batch(self, packets: Sequence[FramePacket], roi_masks=None) -> List[List[Detection]]:
+        if not packets:
+            return []
+        dets, _ = self.predict_batch_device([p.frame for p in packets], roi_masks)
+        return self._to_detections(dets, packets)
+
+    def predict_batch_device(self, frames, roi_masks=None, dets_out=None):
+        """Frames (host arrays or CUDA tensors) -> detections as device SoA tensors + metas."""
+        tensor, metas = self._preprocess_batch(frames, roi_masks)
+        head = self._as_head(self._infer(tensor))
+        if head.dim() != 3 or head.shape[0] != len(frames):
+            raise ValueError(f"infer returned {tuple(head.shape)} for a batch of {len(frames)}")
+        return self._run_post(head, metas, dets_out), metas
+
+    def _run_post(self, head, metas, dets_out=None):
+        cfg = self.config
+        thr = float(cfg.confidence_threshold)
+        return self.h.postprocess(head, metas, thr, float(cfg.iou_threshold), getattr(cfg, "classes", None) or None,
+                                  filter_conf=thr if self.fold_filter else None, out=dets_out)
+
+    def _to_detections(self, dets, packets) -> List[List[Detection]]:
+        counts = dets["count"].cpu().numpy()  # synchronises the current stream
+        kmax = int(counts.max()) if len(counts) else 0
+        if kmax == 0:
+            return [[] for _ in packets]
+        box = dets["bbox_xyxy"][:, :kmax].cpu().numpy()
+        conf = dets["conf"][:, :kmax].cpu().numpy()
+        cls = dets["cls"][:, :kmax].cpu().numpy()
+        out = []
+        for b, packet in enumerate(packets):
+            n = int(counts[b])
+            name = getattr(packet.stream, "name", str(packet.stream))
+            out.append([Detection(name, packet.frame_id, int(cls[b, i]), float(conf[b, i]),
+                                  (float(box[b, i, 0]), float(box[b, i, 1]), float(box[b, i, 2]), float(box[b, i, 3])))
+                        for i in range(n)])
+        return out

@@ -1,0 +1,64 @@
+"""Registration shim for the reference package.
+
+The reference selects its detector by ``detector.backend`` (whitelist: config.py:155-157, dispatch:
+detector.py:54-96) and hard-codes ``IouTracker`` (pipeline.py:452).  ``register_with_reference``
+patches those three places at import time so that a YAML with ``backend: b200`` and
+``tracker.type: b200_iou`` runs this package's kernels behind the reference's own pipeline, and
+swaps the frame-filter functions the pipeline imported by name (pipeline.py:33).
+INTEGRATION.md shows the equivalent two-line source change for maintainers who prefer a patch.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+
+def register_with_reference(infer_factory: Optional[Callable] = None) -> None:
+    """``infer_factory(config) -> callable`` builds the detector forward for a DetectorConfig
+    (e.g. loads the YOLO weights with PyTorch); it is required for ``backend: b200``."""
+    import realtime_analytics.config as rcfg  # the reference, must be importable
+    import realtime_analytics.detector as rdet
+    import realtime_analytics.pipeline as rpipe
+
+    from .detector import B200Detector
+    from .frame_filter import MotionFilter, apply_roi, downsample
+    from .tracker import B200IouTracker
+
+    # 1. whitelist the backend id (config.py:155-157 builds the set inside validate())
+    orig_validate = rcfg.DetectorConfig.validate
+
+    def validate(self):
+        if self.backend == "b200":
+            backend, self.backend = self.backend, "tensorrt"
+            try:
+                orig_validate(self)
+            finally:
+                self.backend = backend
+        else:
+            orig_validate(self)
+
+    rcfg.DetectorConfig.validate = validate
+
+    # 2. dispatch (detector.py:54-96)
+    orig_create = rdet.create_detector
+
+    def create_detector(config):
+        if config.backend.lower() == "b200":
+            if infer_factory is None:
+                raise RuntimeError("backend 'b200' needs register_with_reference(infer_factory=...)")
+            return B200Detector(config, infer=infer_factory(config))
+        return orig_create(config)
+
+    rdet.create_detector = create_detector
+    rpipe.create_detector = create_detector
+
+    # 3. tracker (pipeline.py:452) keyed on tracker.type, and the frame filters (pipeline.py:33)
+    class _Tracker:
+        def __new__(cls, config):
+            if getattr(config, "type", "") == "b200_iou":
+                return B200IouTracker(config)
+            return rpipe._ReferenceIouTracker(config)
+
+    rpipe._ReferenceIouTracker = rpipe.IouTracker
+    rpipe.IouTracker = _Tracker
+    rpipe.apply_roi, rpipe.downsample, rpipe.MotionFilter = apply_roi, downsample, MotionFilter
