@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Benchmark of the pre + post + track hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload at every N: each GPU serves 32 streams of 1080p BGR frames with a synthetic decoded
+YOLOv8 head [32, 84, 8400] (config 3 of BASELINE.json, the one the metric is quoted on); with
+N > 1 every rank (one process per GPU, torchrun) serves its own 32 streams -- weak scaling, no
+data-path collective.  One "step" is one tick: letterbox preprocess of the 32 frames, head decode +
+NMS of the 32 heads, tracker update of the 32 streams.  The detector forward is outside the
+measured path (north_star) -- the head tensors stand in for its output.
+
+`value`   : frames/s with frames and heads already resident in HBM (CUDA events, max over ranks).
+`e2e`     : the same tick through the public API (HotPathEngine.tick) with HOST buffers: pinned
+            frames and heads are copied to the device and the track tables are read back and
+            turned into Track objects inside the timed region.
+`roofline`: the letterbox kernel's algorithmic bytes / its event-timed duration vs measured HBM peak.
+`cpu_baseline` / `--impl reference`: the reference's own OpenCV/NumPy call sequence (oracle, cv2
+            back end) on the host cores of the same box.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from realtime_video_analytics_32streams_b200 import synth  # noqa: E402
+
+METRIC = "pre+post+track frames/sec (32x1080p)"
+STREAMS = 32
+H, W = 1080, 1920
+IN_HW = (640, 640)
+C, A = 84, 8400
+CONF, IOU = 0.35, 0.5
+TRK = dict(max_age=30, max_iou_distance=0.5, min_hits=1)
+N_SETS = 4  # rotating input sets: every step reads frames / heads that left L2 long ago
+OBJECTS, DUP = 24, 3
+# algorithmic HBM bytes of the letterbox kernel per 1080p frame: the 360 tapped
+# source rows (every third row carries weight 2048, the rest 0) + the fp32 NCHW output
+LETTERBOX_BYTES_PER_FRAME = 360 * 1920 * 3 + 3 * 640 * 640 * 4
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {"workload": "32 streams x 1080p BGR per GPU -> letterbox 640x640 fp32 + YOLOv8 head [32,84,8400] decode/NMS "
+                        "+ IoU tracker (BASELINE.json configs[2] shape, 32 streams on every GPU)",
+            "streams_per_gpu": STREAMS, "streams_total": STREAMS * n_gpus, "frame": [H, W, 3], "head": [C, A],
+            "objects_per_frame": OBJECTS * DUP, "conf_thr": CONF, "iou_thr": IOU, "tracker": TRK,
+            "cache": f"{N_SETS} rotating input sets (199 MB frames + 90 MB heads each) > 126 MB L2",
+            "sharding": "by stream id, no collective"}
+
+
+def make_heads(stream: int, n_sets: int) -> np.ndarray:
+    scene = synth.DenseScene(7000 + stream, n_objects=OBJECTS, dup=DUP, n_obj_classes=10)
+    return np.stack([scene.head(t) for t in range(n_sets)])
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, device_index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES when mapping the torch ordinal to an NVML index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = device_index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[device_index])
+                except (ValueError, IndexError):
+                    idx = device_index
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception:  # pragma: no cover
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._poll, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self) -> dict:
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the reference's OpenCV / NumPy call sequence (oracle, cv2 back end)
+# --------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker_init(stream_ids, n_sets):
+    import cv2
+
+    from oracle import hotpath as O
+
+    cv2.setNumThreads(1)
+    _W["O"] = O
+    _W["frames"] = {s: synth.synth_frame(3000 + s, H, W) for s in stream_ids}
+    _W["heads"] = {s: make_heads(s, n_sets) for s in stream_ids}
+    _W["tracker"] = O.IouTracker(TRK["max_age"], TRK["max_iou_distance"], TRK["min_hits"])
+
+
+def _cpu_tick(args):
+    stream_ids, t = args
+    O = _W["O"]
+    n_tracks = 0
+    for s in stream_ids:
+        tensor, meta = O.preprocess(_W["frames"][s], IN_HW, False, backend="cv2")
+        heads = _W["heads"][s]
+        dets = O.postprocess(heads[t % len(heads)][None], meta, CONF, IOU)
+        dets = O.filter_detections(dets, CONF)
+        n_tracks += len(_W["tracker"].update(f"s{s}", dets))
+    return n_tracks
+
+
+def cpu_single_core_sample(budget_s: float = 12.0, n_streams: int = 4) -> dict:
+    """Bounded single-thread sample of the same workload (rank 0, N=1 only)."""
+    ids = list(range(n_streams))
+    _cpu_worker_init(ids, N_SETS)
+    _cpu_tick((ids, 0))  # warm-up
+    t0 = time.perf_counter()
+    ticks = 0
+    while True:
+        _cpu_tick((ids, ticks + 1))
+        ticks += 1
+        if time.perf_counter() - t0 > budget_s or ticks >= 200:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": round(ticks * n_streams / dt, 2), "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": f"{ticks} ticks x {n_streams} streams of the bench workload (1080p letterbox + [84,8400] decode/NMS + "
+                      f"tracker), oracle with the cv2 back end (the reference's own OpenCV/NumPy call sequence), "
+                      f"1 thread, {dt:.1f} s"}
+
+
+def run_reference(args) -> None:
+    """--impl reference: the CPU path on every host core (rank 0 only under torchrun)."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    procs = max(1, min(cores, STREAMS))
+    # a step = one tick of a bounded number of streams, spread evenly over the worker processes
+    streams_per_proc = 1 if procs >= 8 else 2
+    groups = [[p * streams_per_proc + k for k in range(streams_per_proc)] for p in range(procs)]
+    n_frames = procs * streams_per_proc
+    ctx = mp.get_context("fork")
+    pools = [ctx.Pool(1, initializer=_cpu_worker_init, initargs=(g, N_SETS)) for g in groups]
+
+    def tick(t):
+        res = [pool.apply_async(_cpu_tick, ((g, t),)) for pool, g in zip(pools, groups)]
+        for r in res:
+            r.get()
+
+    for t in range(args.warmup):
+        tick(t)
+    t0 = time.perf_counter()
+    for t in range(args.steps):
+        tick(args.warmup + t)
+    dt = time.perf_counter() - t0
+    for pool in pools:
+        pool.terminate()
+    value = n_frames * args.steps / dt
+    sample = (f"each step = one tick of {n_frames} of the {STREAMS} streams ({streams_per_proc} per process, {procs} processes, "
+              f"1 OpenCV thread each); same frames/heads/thresholds as the GPU arm")
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": round(value, 2), "unit": "frames/s", "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": round(value, 2), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_gpu(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from realtime_video_analytics_32streams_b200 import (DetectorConfig, HotPathEngine, StreamConfig, TrackerConfig,
+                                                         _native)
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    h = _native.Handle(device=local, max_batch=STREAMS, max_anchors=A, max_candidates=2048, max_dets=512,
+                       max_streams=2 * STREAMS, max_tracks=1024)
+    # ---- synthetic inputs, resident in HBM --------------------------------------------------
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    frame_sets = [torch.randint(0, 256, (STREAMS, H, W, 3), dtype=torch.uint8, device=dev, generator=g)
+                  for _ in range(N_SETS)]
+    heads_np = np.stack([make_heads(rank * STREAMS + s, N_SETS) for s in range(STREAMS)], axis=1)  # [sets, 32, C, A]
+    head_sets = [torch.from_numpy(heads_np[k]).to(dev) for k in range(N_SETS)]
+    metas = [_native.letterbox_meta(H, W, *IN_HW) for _ in range(STREAMS)]
+    net_in = torch.empty((STREAMS, 3, *IN_HW), dtype=torch.float32, device=dev)
+    dets = h.alloc_dets(STREAMS)
+    tracks = h.alloc_tracks(STREAMS)
+    slots = list(range(STREAMS))
+
+    def step(k, ev=None):
+        frames = list(frame_sets[k % N_SETS].unbind(0))
+        if ev is not None:
+            ev[0].record()
+        h.preprocess(frames, IN_HW, _native.OUT_F32_RGB_NCHW, out=net_in)
+        if ev is not None:
+            ev[1].record()
+        h.postprocess(head_sets[k % N_SETS], metas, CONF, IOU, filter_conf=CONF, out=dets)
+        h.tracker_update(slots, dets, TRK["max_age"], TRK["min_hits"], TRK["max_iou_distance"], out=tracks)
+
+    for k in range(max(args.warmup, 3)):
+        step(k)
+    barrier()
+    h.poll_status()
+    clocks = ClockSampler(local)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = h.launch_count
+    barrier()
+    clocks.start()
+    start.record()
+    for k in range(args.steps):
+        step(args.warmup + k, kev[k])
+    end.record()
+    barrier()
+    clocks.stop()
+    launches = h.launch_count - launches0
+    ms = start.elapsed_time(end)
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    n_tracks = int(tracks["count"].sum().item())
+    h.poll_status()
+    if world > 1:
+        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = world * STREAMS * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers ---------------------------------
+    streams = [StreamConfig(name=f"r{rank}s{s}") for s in range(STREAMS)]
+    host_frames = [torch.empty((H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(STREAMS)]
+    for s, hf in enumerate(host_frames):
+        hf.copy_(frame_sets[0][s])
+    host_heads = [torch.from_numpy(heads_np[k]).pin_memory() for k in range(N_SETS)]
+    tick_no = [0]
+
+    def infer(tensor):  # the detector forward is out of scope: its output arrives from pinned host memory
+        return host_heads[tick_no[0] % N_SETS].to(dev, non_blocking=True)
+
+    for s in range(STREAMS):
+        h.tracker_reset(STREAMS + s)
+    eng = HotPathEngine(streams, DetectorConfig(confidence_threshold=CONF, iou_threshold=IOU),
+                        TrackerConfig(**TRK), infer=infer, handle=h, input_hw=IN_HW, build_objects=True)
+    eng.tracker._slots = {st.name: STREAMS + s for s, st in enumerate(streams)}
+    e2e_steps = max(3, min(args.steps, 50))
+    d2h = 0
+    for k in range(3):
+        tick_no[0] = k
+        res = eng.tick(host_frames)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        tick_no[0] = 3 + k
+        res = eng.tick(host_frames)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    kt = max(max(len(r.tracks) for r in res), 1)
+    kd = max(max(len(r.detections) for r in res), 1)
+    d2h = STREAMS * (4 + 4 + 4) + STREAMS * kt * (8 + 4 + 8 + 32 + 4 + 4) + STREAMS * kd * (16 + 4 + 4)
+    if world > 1:
+        tmax = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
+    e2e_value = world * STREAMS * e2e_steps / e2e_s
+    h.poll_status()
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            with open(peaks_path) as fh:
+                peak, peak_src = float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy, burst)"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        achieved = LETTERBOX_BYTES_PER_FRAME * STREAMS / (k1_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get("k_letterbox_dram_bytes_per_launch")
+        line = {"metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
+                "config": workload_config(world),
+                "roofline": {"bound": "hbm", "kernel": "k_letterbox<F32_RGB_NCHW> (32 x 1080p per launch)",
+                             "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                             "traffic": traffic, "kernel_ms": round(k1_ms, 4),
+                             "algorithmic_bytes_per_launch": LETTERBOX_BYTES_PER_FRAME * STREAMS, "peak_source": peak_src},
+                "e2e": {"value": round(e2e_value, 1), "unit": "frames/s",
+                        "h2d_bytes_per_step": STREAMS * (H * W * 3 + C * A * 4), "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "ms_per_step": round(1e3 * e2e_s / e2e_steps, 3),
+                        "api": "HotPathEngine.tick(pinned host frames) -> FrameResult(Detection, Track objects); "
+                               "head tensors also copied from pinned host memory every step"},
+                "gpu_launches": int(launches), "launches_per_step": launches / max(args.steps, 1),
+                "clocks": clocks.summary(), "tracks_alive": n_tracks}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_single_core_sample()
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the single-core CPU sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -95,7 +95,7 @@ def test_preprocess_pitched_and_unaligned_views(H):
 
     big = synth.synth_frame(77, 400, 700)
     dbig = cu(big)
-    views = [(slice(3, 303), slice(5, 485)), (slice(0, 400), slice(16, 656)), (slice(10, 11), slice(0, 700))]
+    views = [(slice(3, 303), slice(5, 485)), (slice(0, 400), slice(16, 656)), (slice(10, 60), slice(1, 700))]
     for ys, xs in views:
         out, _ = H.preprocess([dbig[ys, xs]], (128, 160), N.OUT_F32_RGB_NCHW)
         ref, _ = O.preprocess(np.ascontiguousarray(big[ys, xs]), (128, 160), False)
@@ -472,7 +472,7 @@ def test_engine_replays_reference_stream_worker(H):
 
     class W:
         def __init__(self, i, spec, cfg):
-            if "eng" not in box:
+            if "streams" not in box:
                 H.tracker_set_next_id(1)
                 box["streams"] = []
                 box["cfg"] = cfg
