@@ -250,17 +250,18 @@ def run_gpu(args) -> None:
                   for _ in range(N_SETS)]
     heads_np = np.stack([make_heads(rank * STREAMS + s, N_SETS) for s in range(STREAMS)], axis=1)  # [sets, 32, C, A]
     head_sets = [torch.from_numpy(heads_np[k]).to(dev) for k in range(N_SETS)]
-    metas = [_native.letterbox_meta(H, W, *IN_HW) for _ in range(STREAMS)]
+    metas = (_native.Letterbox * STREAMS)(*[_native.letterbox_meta(H, W, *IN_HW) for _ in range(STREAMS)])
     net_in = torch.empty((STREAMS, 3, *IN_HW), dtype=torch.float32, device=dev)
     dets = h.alloc_dets(STREAMS)
     tracks = h.alloc_tracks(STREAMS)
-    slots = list(range(STREAMS))
+    slots = _native._int_array(list(range(STREAMS)))
+    # argument arrays are built once per input set: the per-step host work is three foreign calls
+    batches = [_native.FrameBatch(list(fs.unbind(0))) for fs in frame_sets]
 
     def step(k, ev=None):
-        frames = list(frame_sets[k % N_SETS].unbind(0))
         if ev is not None:
             ev[0].record()
-        h.preprocess(frames, IN_HW, _native.OUT_F32_RGB_NCHW, out=net_in)
+        h.preprocess(batches[k % N_SETS], IN_HW, _native.OUT_F32_RGB_NCHW, out=net_in)
         if ev is not None:
             ev[1].record()
         h.postprocess(head_sets[k % N_SETS], metas, CONF, IOU, filter_conf=CONF, out=dets)

@@ -131,6 +131,39 @@ def _int_array(vals: Sequence[int]):
     return (C.c_int * len(vals))(*[int(v) for v in vals])
 
 
+class FrameBatch:
+    """A validated batch of CUDA frames (and optional ROI masks) with its ctypes argument arrays
+    built once.  Re-use it across calls while the underlying tensors stay alive and in place --
+    the per-call host cost drops to one foreign-function call."""
+
+    def __init__(self, frames, roi_masks=None):
+        import torch as t
+
+        self.frames = list(frames)
+        self.masks = list(roi_masks) if roi_masks is not None else None
+        for f in self.frames:
+            if not (f.is_cuda and f.dtype == t.uint8 and f.dim() == 3 and f.shape[2] == 3 and f.stride(2) == 1
+                    and f.stride(1) == 3):
+                raise ValueError("frames must be CUDA uint8 tensors [H, W, 3] with packed pixels")
+        n = len(self.frames)
+        self.n = n
+        self.ptrs = _ptr_array([f.data_ptr() for f in self.frames])
+        self.hs = _int_array([f.shape[0] for f in self.frames])
+        self.ws = _int_array([f.shape[1] for f in self.frames])
+        self.pitch = (C.c_int64 * n)(*[f.stride(0) for f in self.frames])
+        self.mask_ptrs = None
+        if self.masks is not None and any(m is not None for m in self.masks):
+            for m, f in zip(self.masks, self.frames):
+                if m is not None and not (m.is_cuda and m.dtype == t.uint8 and m.is_contiguous()
+                                          and tuple(m.shape) == tuple(f.shape[:2])):
+                    raise ValueError("roi masks must be contiguous CUDA uint8 tensors [H, W] matching their frame")
+            self.mask_ptrs = _ptr_array([m.data_ptr() if m is not None else None for m in self.masks])
+        self.metas = (Letterbox * max(n, 1))()
+
+    def __len__(self):
+        return self.n
+
+
 class Handle:
     """One ``b200va_handle``: scratch arenas + tracker state on one GPU."""
 
@@ -176,33 +209,17 @@ class Handle:
         """Synchronise and raise if any capacity limit was hit since the last poll."""
         self._check(self.lib.b200va_poll_status(self._h, self._stream()))
 
-    def _frame_args(self, frames):
-        t = self.torch
-        for f in frames:
-            if not (f.is_cuda and f.dtype == t.uint8 and f.dim() == 3 and f.shape[2] == 3 and f.stride(2) == 1
-                    and f.stride(1) == 3):
-                raise ValueError("frames must be CUDA uint8 tensors [H, W, 3] with packed pixels")
-        ptrs = _ptr_array([f.data_ptr() for f in frames])
-        hs = _int_array([f.shape[0] for f in frames])
-        ws = _int_array([f.shape[1] for f in frames])
-        pitch = (C.c_int64 * len(frames))(*[f.stride(0) for f in frames])
-        return ptrs, hs, ws, pitch
-
-    def _mask_args(self, masks, frames):
-        if masks is None or all(m is None for m in masks):
-            return None
-        t = self.torch
-        for m, f in zip(masks, frames):
-            if m is not None and not (m.is_cuda and m.dtype == t.uint8 and m.is_contiguous()
-                                      and tuple(m.shape) == tuple(f.shape[:2])):
-                raise ValueError("roi masks must be contiguous CUDA uint8 tensors [H, W] matching their frame")
-        return _ptr_array([m.data_ptr() if m is not None else None for m in masks])
+    @staticmethod
+    def _batch(frames, roi_masks=None) -> FrameBatch:
+        return frames if isinstance(frames, FrameBatch) else FrameBatch(frames, roi_masks)
 
     # -- a1 ---------------------------------------------------------------------------------
     def preprocess(self, frames, dst_hw=(640, 640), fmt: int = OUT_F32_RGB_NCHW, roi_masks=None, out=None):
-        """Batched letterbox.  Returns (tensor [B,3,H,W] or [B,H,W,3], list of Letterbox)."""
+        """Batched letterbox.  ``frames``: list of CUDA tensors or a ``FrameBatch``.
+        Returns (tensor [B,3,H,W] or [B,H,W,3], list of Letterbox)."""
         t = self.torch
-        b = len(frames)
+        fb = self._batch(frames, roi_masks)
+        b = fb.n
         dh, dw = int(dst_hw[0]), int(dst_hw[1])
         dtype = {OUT_F32_RGB_NCHW: t.float32, OUT_F16_RGB_NCHW: t.float16}.get(fmt, t.uint8)
         shape = (b, dh, dw, 3) if fmt == OUT_U8_BGR_NHWC else (b, 3, dh, dw)
@@ -210,22 +227,20 @@ class Handle:
             out = t.empty(shape, dtype=dtype, device=self.device)
         elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
             raise ValueError("preprocess: `out` has the wrong shape / dtype / layout")
-        metas = (Letterbox * max(b, 1))()
         if b:
-            ptrs, hs, ws, pitch = self._frame_args(frames)
-            self._check(self.lib.b200va_preprocess(self._h, ptrs, hs, ws, pitch, b, self._mask_args(roi_masks, frames),
-                                                   C.c_void_p(out.data_ptr()), dh, dw, fmt, metas, self._stream()))
-        return out, [metas[i] for i in range(b)]
+            self._check(self.lib.b200va_preprocess(self._h, fb.ptrs, fb.hs, fb.ws, fb.pitch, b, fb.mask_ptrs,
+                                                   C.c_void_p(out.data_ptr()), dh, dw, fmt, fb.metas, self._stream()))
+        return out, [fb.metas[i] for i in range(b)]
 
     # -- a10 --------------------------------------------------------------------------------
     def resize(self, frames, dst_hw_list, roi_masks=None):
         """``cv2.resize(frame, (w, h), INTER_LINEAR)`` per frame; returns new uint8 HWC tensors."""
         t = self.torch
         outs = [t.empty((int(h), int(w), 3), dtype=t.uint8, device=self.device) for h, w in dst_hw_list]
-        if frames:
-            ptrs, hs, ws, pitch = self._frame_args(frames)
+        fb = self._batch(frames, roi_masks)
+        if fb.n:
             self._check(self.lib.b200va_resize_linear_u8(
-                self._h, ptrs, hs, ws, pitch, len(frames), self._mask_args(roi_masks, frames),
+                self._h, fb.ptrs, fb.hs, fb.ws, fb.pitch, fb.n, fb.mask_ptrs,
                 _ptr_array([o.data_ptr() for o in outs]), _int_array([h for h, _ in dst_hw_list]),
                 _int_array([w for _, w in dst_hw_list]), self._stream()))
         return outs
@@ -261,14 +276,14 @@ class Handle:
         """Blurred-gray update + changed-pixel counts.  ``prev_gray[i]`` may be None (first frame:
         count -1).  Returns the int32 device tensor of counts."""
         t = self.torch
-        b = len(frames)
+        fb = self._batch(frames, roi_masks)
+        b = fb.n
         if changed_out is None:
             changed_out = t.empty((b,), dtype=t.int32, device=self.device)
         if b:
-            ptrs, hs, ws, pitch = self._frame_args(frames)
             has_prev = _int_array([0 if p is None else 1 for p in prev_gray])
             self._check(self.lib.b200va_motion(
-                self._h, ptrs, hs, ws, pitch, b, self._mask_args(roi_masks, frames),
+                self._h, fb.ptrs, fb.hs, fb.ws, fb.pitch, b, fb.mask_ptrs,
                 _ptr_array([p.data_ptr() if p is not None else None for p in prev_gray]),
                 _ptr_array([n.data_ptr() for n in next_gray]), has_prev, C.c_void_p(changed_out.data_ptr()),
                 self._stream()))
@@ -299,7 +314,7 @@ class Handle:
         channels, anchors = (d1, d2) if layout == HEAD_CHANNEL_MAJOR else (d2, d1)
         if out is None:
             out = self.alloc_dets(b)
-        marr = (Letterbox * max(b, 1))(*metas)
+        marr = metas if isinstance(metas, C.Array) else (Letterbox * max(b, 1))(*metas)
         cls_arr = (C.c_int32 * len(classes))(*[int(c) for c in classes]) if classes else None
         ds = self._dets_struct(out)
         self._check(self.lib.b200va_postprocess(
@@ -328,6 +343,7 @@ class Handle:
         if out is None:
             out = self.alloc_tracks(b)
         cfg = TrackerCfg(int(max_age), int(min_hits), float(max_iou_distance))
+        slot_arr = slots if isinstance(slots, C.Array) else _int_array(slots)
         ts = Tracks(out["track_id"].data_ptr(), out["cls"].data_ptr(), out["conf"].data_ptr(),
                     out["bbox_xyxy"].data_ptr(), out["age"].data_ptr(), out["hits"].data_ptr(),
                     out["count"].data_ptr())
@@ -337,13 +353,13 @@ class Handle:
         if f64:
             ds = Dets64(dets["bbox_xyxy"].data_ptr(), dets["conf"].data_ptr(), dets["cls"].data_ptr(),
                         dets["count"].data_ptr())
-            self._check(self.lib.b200va_tracker_update_f64(self._h, _int_array(slots), b, C.byref(ds), max_dets,
+            self._check(self.lib.b200va_tracker_update_f64(self._h, slot_arr, b, C.byref(ds), max_dets,
                                                            skip_arr, C.byref(cfg), idb, C.byref(ts),
                                                            C.c_void_p(out["new_count"].data_ptr()), self._stream()))
         else:
             ds = self._dets_struct(dets)
             sc = (C.c_double * b)(*[float(v) for v in det_scale]) if det_scale is not None else None
-            self._check(self.lib.b200va_tracker_update(self._h, _int_array(slots), b, C.byref(ds), max_dets, sc,
+            self._check(self.lib.b200va_tracker_update(self._h, slot_arr, b, C.byref(ds), max_dets, sc,
                                                        skip_arr, C.byref(cfg), idb, C.byref(ts),
                                                        C.c_void_p(out["new_count"].data_ptr()), self._stream()))
         return out

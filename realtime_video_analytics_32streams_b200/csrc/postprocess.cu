@@ -76,57 +76,102 @@ __device__ __forceinline__ void emit_candidate(const PostParams& p, int frame, i
   p.cand_cls[o] = cls;
 }
 
-// channel-major head [B, C, A]: a thread owns one anchor, a warp reads 128 contiguous bytes per channel
-__global__ void __launch_bounds__(256) k_decode_cm(const __grid_constant__ PostParams p, int frame0) {
+// channel-major head [B, C, A]: a thread owns VEC consecutive anchors and reads every channel row
+// with one 16-byte (VEC = 4) or 4-byte (VEC = 1) load; eight channel rows are in flight per thread.
+template <int VEC>
+__global__ void __launch_bounds__(128) k_decode_cm(const __grid_constant__ PostParams p, int frame0) {
   const int frame = blockIdx.y;
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int a0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   const float* __restrict__ hd = p.head + (size_t)(frame0 + frame) * p.C * p.A;
   const int A = p.A, C = p.C;
-  bool pass = false;
-  float best = 0.f;
-  int cls = 0;
-  if (a < A) {
-    const float obj = __ldg(hd + (size_t)4 * A + a);
+  float best[VEC];
+  int cls[VEC];
+  unsigned pass = 0;  // bit k: anchor a0 + k is a candidate
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    best[k] = 0.f;
+    cls[k] = 0;
+  }
+  auto load = [&](int c, float (&v)[VEC]) {
+    if (VEC == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(hd + (size_t)c * A + a0));
+      v[0] = q.x, v[1 % VEC] = q.y, v[2 % VEC] = q.z, v[3 % VEC] = q.w;
+    } else {
+      v[0] = __ldg(hd + (size_t)c * A + a0);
+    }
+  };
+  if (a0 < A) {
+    float obj[VEC];
+    load(4, obj);
     if (C > 5) {
       // scores = class_probs * objectness for both model types (detector.py:294-305)
-      best = __fmul_rn(__ldg(hd + (size_t)5 * A + a), obj);
+      float first[VEC];
+      load(5, first);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) best[k] = __fmul_rn(first[k], obj[k]);
       int c = 6;
       for (; c + 8 <= C; c += 8) {
-        float v[8];
+        float v[8][VEC];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = __ldg(hd + (size_t)(c + k) * A + a);
+        for (int u = 0; u < 8; ++u) load(c + u, v[u]);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float s = __fmul_rn(v[k], obj);
-          if (s > best) {  // np.argmax: first maximum wins
-            best = s;
-            cls = c + k - 5;
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const float sc = __fmul_rn(v[u][k], obj[k]);
+            if (sc > best[k]) {  // np.argmax: first maximum wins
+              best[k] = sc;
+              cls[k] = c + u - 5;
+            }
+          }
+      }
+      for (; c < C; ++c) {
+        float v[VEC];
+        load(c, v);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const float sc = __fmul_rn(v[k], obj[k]);
+          if (sc > best[k]) {
+            best[k] = sc;
+            cls[k] = c - 5;
           }
         }
       }
-      for (; c < C; ++c) {
-        const float s = __fmul_rn(__ldg(hd + (size_t)c * A + a), obj);
-        if (s > best) {
-          best = s;
-          cls = c - 5;
-        }
-      }
     } else {
-      best = obj;  // scores = predictions[:, 4:], detector.py:306-307
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) best[k] = obj[k];  // scores = predictions[:, 4:], detector.py:306-307
     }
-    pass = (best >= p.conf_thr) && class_allowed(p, cls);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      if ((best[k] >= p.conf_thr) && class_allowed(p, cls[k])) pass |= 1u << k;
   }
-  const unsigned ballot = __ballot_sync(0xffffffffu, pass);
-  if (ballot == 0) return;
+  // warp-aggregated compaction: one atomic per warp
+  const int mine = __popc(pass);
   const int lane = threadIdx.x & 31;
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
   int base = 0;
-  if (lane == 0) base = atomicAdd(p.cand_count + frame, __popc(ballot));
-  base = __shfl_sync(0xffffffffu, base, 0);
+  if (lane == 31) base = atomicAdd(p.cand_count + frame, total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  int pos = base + incl - mine;
   if (pass) {
-    const int pos = base + __popc(ballot & ((1u << lane) - 1u));
-    const float cx = __ldg(hd + a), cy = __ldg(hd + (size_t)A + a), w = __ldg(hd + (size_t)2 * A + a),
-                h = __ldg(hd + (size_t)3 * A + a);
-    emit_candidate(p, frame, pos, a, best, cls, decode_box(cx, cy, w, h, p.f[frame]));
+    float cx[VEC], cy[VEC], w[VEC], h[VEC];
+    load(0, cx);
+    load(1, cy);
+    load(2, w);
+    load(3, h);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      if (pass & (1u << k)) {
+        emit_candidate(p, frame, pos, a0 + k, best[k], cls[k], decode_box(cx[k], cy[k], w[k], h[k], p.f[frame]));
+        ++pos;
+      }
   }
 }
 
@@ -220,9 +265,9 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);              // [cap_pow2]
   float4* box = reinterpret_cast<float4*>(smem_raw + (size_t)p.cap_pow2 * 8);               // [cap_pow2]
   uint32_t* supp = reinterpret_cast<uint32_t*>(smem_raw + (size_t)p.cap_pow2 * 24);         // [cap_pow2/32]
-  unsigned long long* keep_w = reinterpret_cast<unsigned long long*>(supp + p.cap_pow2 / 32);  // [cap_pow2/64]
-  int* keep_off = reinterpret_cast<int*>(keep_w + p.cap_pow2 / 64);                         // [cap_pow2/64 + 1]
-  __shared__ unsigned long long rows[64];
+  uint32_t* keep_w = supp + p.cap_pow2 / 32;                                                // [cap_pow2/32]
+  int* keep_off = reinterpret_cast<int*>(keep_w + p.cap_pow2 / 32);                         // [cap_pow2/64 + 1]
+  __shared__ uint32_t rows[64][2];
 
   __syncthreads();
   if (tid == 0) {
@@ -263,26 +308,27 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
   for (int ch = 0; ch < nchunks; ++ch) {
     const int c0 = ch << 6;
     const int m = min(64, n - c0);
-    if (tid < 64) rows[tid] = 0ull;
+    if (tid < 128) rows[tid >> 1][tid & 1] = 0u;
     __syncthreads();
     // (a) in-chunk IoU bits: thread -> row i = tid / 16, columns 4 * (tid % 16) ..
     {
       const int i = tid >> 4, jb = (tid & 15) << 2;
       if (i < m) {
         const float4 bi = box[c0 + i];
-        unsigned long long bits = 0ull;
+        uint32_t bits = 0u;  // the four columns of a thread fall into one 32-bit half of the row
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = jb + q;
-          if (j > i && j < m && suppresses(bi, box[c0 + j], thr)) bits |= 1ull << j;
+          if (j > i && j < m && suppresses(bi, box[c0 + j], thr)) bits |= 1u << (j & 31);
         }
-        if (bits) atomicOr(&rows[i], bits);
+        if (bits) atomicOr(&rows[i][jb >> 5], bits);
       }
     }
     __syncthreads();
     // (b) one warp resolves the chunk sequentially; rows live in registers, two per lane
     if (tid < 32) {
-      const unsigned long long r_lo = rows[tid], r_hi = rows[tid + 32];
+      const unsigned long long r_lo = ((unsigned long long)rows[tid][1] << 32) | rows[tid][0];
+      const unsigned long long r_hi = ((unsigned long long)rows[tid + 32][1] << 32) | rows[tid + 32][0];
       const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
       unsigned long long alive = ~(((unsigned long long)supp[(c0 >> 5) + 1] << 32) | supp[c0 >> 5]) & valid;
       unsigned long long kept = 0ull;
@@ -293,11 +339,14 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
         kept |= on & (1ull << i);
         alive &= ~(r & on);
       }
-      if (tid == 0) keep_w[ch] = kept;
+      if (tid == 0) {
+        keep_w[2 * ch] = (uint32_t)kept;
+        keep_w[2 * ch + 1] = (uint32_t)(kept >> 32);
+      }
     }
     __syncthreads();
     // (c) this chunk's survivors suppress every later box
-    const unsigned long long kept = keep_w[ch];
+    const unsigned long long kept = ((unsigned long long)keep_w[2 * ch + 1] << 32) | keep_w[2 * ch];
     if (kept) {
       for (int j = c0 + 64 + tid; j < n; j += kNmsThreads) {
         if ((supp[j >> 5] >> (j & 31)) & 1u) continue;
@@ -319,9 +368,9 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
   // filter_detections (detector.py:99-103): float64 compare on the kept boxes only
   if (p.use_filter) {
     for (int i = tid; i < n; i += kNmsThreads) {
-      if ((keep_w[i >> 6] >> (i & 63)) & 1ull) {
+      if ((keep_w[i >> 5] >> (i & 31)) & 1u) {
         const float conf = unorder_bits((uint32_t)(keys[i] >> 32));
-        if (!((double)conf >= p.filter_thr)) atomicAnd(&keep_w[i >> 6], ~(1ull << (i & 63)));
+        if (!((double)conf >= p.filter_thr)) atomicAnd(&keep_w[i >> 5], ~(1u << (i & 31)));
       }
     }
     __syncthreads();
@@ -330,7 +379,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
     int acc = 0;
     for (int ch = 0; ch < nchunks; ++ch) {
       keep_off[ch] = acc;
-      acc += __popcll(keep_w[ch]);
+      acc += __popc(keep_w[2 * ch]) + __popc(keep_w[2 * ch + 1]);
     }
     keep_off[nchunks] = acc;
     p.out_count[frame] = min(acc, p.max_dets);
@@ -338,7 +387,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
   }
   __syncthreads();
   for (int i = tid; i < n; i += kNmsThreads) {
-    const unsigned long long w = keep_w[i >> 6];
+    const unsigned long long w = ((unsigned long long)keep_w[2 * (i >> 6) + 1] << 32) | keep_w[2 * (i >> 6)];
     if ((w >> (i & 63)) & 1ull) {
       const int pos = keep_off[i >> 6] + __popcll(w & ((1ull << (i & 63)) - 1ull));
       if (pos < p.max_dets) {
@@ -362,7 +411,7 @@ static int next_pow2(int v) {
 
 size_t nms_smem_bytes(int max_cand) {
   const size_t cap = (size_t)next_pow2(max_cand);
-  return cap * 24 + cap / 8 + cap / 8 + (cap / 64 + 1) * 4 + 64;
+  return cap * 24 + cap / 8 + cap / 8 + (cap / 64 + 1) * 4 + 64;  // keys, boxes, supp, keep_w, keep_off
 }
 
 int postprocess_configure(b200va_ctx* h) {
@@ -420,8 +469,14 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
     p.max_cand = h->cfg.max_candidates;
     p.conf_thr = (float)conf_thr;  // NEP-50 weak scalar: compared in float32 (detector.py:312)
     if (layout == B200VA_HEAD_CHANNEL_MAJOR) {
-      dim3 grid((anchors + 255) / 256, n);
-      k_decode_cm<<<grid, 256, 0, st>>>(p, base);
+      // 16-byte loads need every channel row (A floats) and the tensor base 16-byte aligned
+      if (anchors % 4 == 0 && ((uintptr_t)head % 16 == 0)) {
+        dim3 grid((anchors / 4 + 127) / 128, n);
+        k_decode_cm<4><<<grid, 128, 0, st>>>(p, base);
+      } else {
+        dim3 grid((anchors + 127) / 128, n);
+        k_decode_cm<1><<<grid, 128, 0, st>>>(p, base);
+      }
     } else {
       dim3 grid((anchors + 7) / 8, n);
       k_decode_am<<<grid, 256, 0, st>>>(p, base);

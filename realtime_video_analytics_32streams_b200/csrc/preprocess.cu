@@ -13,6 +13,8 @@
 // row length are not 16-byte multiples take the same code with a cooperative byte loader.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -34,8 +36,8 @@ struct PreFrame {
   long long pitch;
   int src_h, src_w;
   int xtab, ytab;  // offsets (in 16-byte entries) into the tap arena
-  int bulk_ok;     // rows can be fetched with 16-byte bulk copies
-  int mask_bulk_ok;
+  int bulk_ok;     // frame (and mask) rows can be fetched with 16-byte bulk copies
+  int out_idx;     // position of this frame in the output batch
 };
 
 struct PreParams {
@@ -44,10 +46,12 @@ struct PreParams {
   void* out;
   int dst_h, dst_w, fmt, rows_per_cta;
   int row_stride, mask_stride, stages, vec_ok;
+  int rows_per_stage;  // 1 when no frame of the launch ever needs the second source row
 };
 static_assert(sizeof(PreParams) <= 4000, "kernel parameter block too large");
 
 constexpr int kMaxStages = 4;
+constexpr int kMaxRowsPerCta = 16;
 constexpr int kThreads = 160;  // 4 output pixels per thread -> 640 columns
 
 __device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, int bytes) {
@@ -55,37 +59,36 @@ __device__ __forceinline__ void coop_copy(uint8_t* dst, const uint8_t* src, int 
   for (int i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = __ldg(src + i);
 }
 
+// Store 4 pixels (v[j][c]: pixel j, channel c in BGR order, 0..255).  `o` points at the element
+// of plane 0 (NCHW) / at the pixel (NHWC); `plane` is the plane stride in elements; `nvalid` is
+// how many of the 4 pixels lie inside the row.
 template <int FMT>
-__device__ __forceinline__ void store_px4(const PreParams& p, int frame, int d, int x, const int (&v)[4][3]) {
-  // v[j][c]: pixel x+j, channel c in BGR order, value 0..255
-  const int W = p.dst_w, H = p.dst_h;
+__device__ __forceinline__ void store_px4(void* o, size_t plane, bool vec_ok, int nvalid, const int (&v)[4][3]) {
   if (FMT == B200VA_OUT_F32_RGB_NCHW) {
-    float* o = (float*)p.out + (size_t)frame * 3 * H * W;
     const float k = __int_as_float(0x3B808081);  // float32(1.0/255.0), detector.py:251
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
-      float* row = o + ((size_t)pl * H + d) * W + x;
+      float* row = (float*)o + pl * plane;
       float r[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) r[j] = __fmul_rn((float)v[j][2 - pl], k);
-      if (p.vec_ok) {
+      if (vec_ok) {
         *reinterpret_cast<float4*>(row) = make_float4(r[0], r[1], r[2], r[3]);
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (x + j < W) row[j] = r[j];
+          if (j < nvalid) row[j] = r[j];
       }
     }
   } else if (FMT == B200VA_OUT_F16_RGB_NCHW) {
-    __half* o = (__half*)p.out + (size_t)frame * 3 * H * W;
     const float k = 0.0039215087890625f;  // float(float16(1.0/255.0)): NumPy rounds the scalar to half first
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
-      __half* row = o + ((size_t)pl * H + d) * W + x;
+      __half* row = (__half*)o + pl * plane;
       __half r[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) r[j] = __float2half_rn(__fmul_rn((float)v[j][2 - pl], k));
-      if (p.vec_ok) {
+      if (vec_ok) {
         uint2 w;
         w.x = (uint32_t)__half_as_ushort(r[0]) | ((uint32_t)__half_as_ushort(r[1]) << 16);
         w.y = (uint32_t)__half_as_ushort(r[2]) | ((uint32_t)__half_as_ushort(r[3]) << 16);
@@ -93,26 +96,25 @@ __device__ __forceinline__ void store_px4(const PreParams& p, int frame, int d, 
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (x + j < W) row[j] = r[j];
+          if (j < nvalid) row[j] = r[j];
       }
     }
   } else if (FMT == B200VA_OUT_U8_BGR_NCHW) {
-    uint8_t* o = (uint8_t*)p.out + (size_t)frame * 3 * H * W;
 #pragma unroll
     for (int pl = 0; pl < 3; ++pl) {
-      uint8_t* row = o + ((size_t)pl * H + d) * W + x;
-      if (p.vec_ok) {
+      uint8_t* row = (uint8_t*)o + pl * plane;
+      if (vec_ok) {
         *reinterpret_cast<uint32_t*>(row) =
             (uint32_t)v[0][pl] | ((uint32_t)v[1][pl] << 8) | ((uint32_t)v[2][pl] << 16) | ((uint32_t)v[3][pl] << 24);
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (x + j < W) row[j] = (uint8_t)v[j][pl];
+          if (j < nvalid) row[j] = (uint8_t)v[j][pl];
       }
     }
   } else {  // B200VA_OUT_U8_BGR_NHWC
-    uint8_t* row = (uint8_t*)p.out + (size_t)frame * 3 * H * W + ((size_t)d * W + x) * 3;
-    if (p.vec_ok) {
+    uint8_t* row = (uint8_t*)o;
+    if (vec_ok) {
       uint32_t w0 = (uint32_t)v[0][0] | ((uint32_t)v[0][1] << 8) | ((uint32_t)v[0][2] << 16) | ((uint32_t)v[1][0] << 24);
       uint32_t w1 = (uint32_t)v[1][1] | ((uint32_t)v[1][2] << 8) | ((uint32_t)v[2][0] << 16) | ((uint32_t)v[2][1] << 24);
       uint32_t w2 = (uint32_t)v[2][2] | ((uint32_t)v[3][0] << 8) | ((uint32_t)v[3][1] << 16) | ((uint32_t)v[3][2] << 24);
@@ -123,7 +125,7 @@ __device__ __forceinline__ void store_px4(const PreParams& p, int frame, int d, 
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (x + j < W) {
+        if (j < nvalid) {
           row[3 * j + 0] = (uint8_t)v[j][0];
           row[3 * j + 1] = (uint8_t)v[j][1];
           row[3 * j + 2] = (uint8_t)v[j][2];
@@ -132,10 +134,63 @@ __device__ __forceinline__ void store_px4(const PreParams& p, int frame, int d, 
   }
 }
 
-template <int FMT>
+// Four output pixels of one row from the staged source rows (general two-tap, two-row case).
+template <bool MASK>
+__device__ __forceinline__ void px4_general(const TapX (&t)[4], const uint8_t* __restrict__ r0,
+                                            const uint8_t* __restrict__ r1, const uint8_t* __restrict__ m0,
+                                            const uint8_t* __restrict__ m1, int b0, int b1, int (&v)[4][3]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (t[j].off0 < 0) {
+      v[j][0] = v[j][1] = v[j][2] = 114;  // copyMakeBorder value, detector.py:233-241
+      continue;
+    }
+    int s0[3] = {0, 0, 0}, s1[3] = {0, 0, 0};
+    if (b0) {
+      int c0 = t[j].a0, c1 = t[j].a1;
+      if (MASK) {  // apply_roi zeroes masked source pixels before the resize (pipeline.py:149-154)
+        c0 = m0[t[j].mx0 & 0xffff] ? c0 : 0;
+        c1 = m0[(unsigned)t[j].mx0 >> 16] ? c1 : 0;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s0[c] = (int)r0[t[j].off0 + c] * c0 + (int)r0[t[j].off1 + c] * c1;
+    }
+    if (b1) {
+      int c0 = t[j].a0, c1 = t[j].a1;
+      if (MASK) {
+        c0 = m1[t[j].mx0 & 0xffff] ? c0 : 0;
+        c1 = m1[(unsigned)t[j].mx0 >> 16] ? c1 : 0;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s1[c] = (int)r1[t[j].off0 + c] * c0 + (int)r1[t[j].off1 + c] * c1;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[j][c] = (((b0 * (s0[c] >> 4)) >> 16) + ((b1 * (s1[c] >> 4)) >> 16) + 2) >> 2;
+  }
+}
+
+// Integer-ratio subsampling (e.g. 1080p -> 640x360): every tap is (2048, 0) on both axes, for which
+// the fixed-point formula returns the source byte itself.
+template <bool MASK>
+__device__ __forceinline__ void px4_identity(const TapX (&t)[4], const uint8_t* __restrict__ r0,
+                                             const uint8_t* __restrict__ m0, int (&v)[4][3]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (t[j].off0 < 0) {
+      v[j][0] = v[j][1] = v[j][2] = 114;
+      continue;
+    }
+    const bool on = !MASK || m0[t[j].mx0 & 0xffff];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[j][c] = on ? (int)r0[t[j].off0 + c] : 0;
+  }
+}
+
+template <int FMT, bool MASK>
 __global__ void __launch_bounds__(kThreads) k_letterbox(const __grid_constant__ PreParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full[kMaxStages];
+  __shared__ TapY s_ty[kMaxRowsPerCta];
 
   const int frame = blockIdx.y;
   const PreFrame& f = p.f[frame];
@@ -144,46 +199,51 @@ __global__ void __launch_bounds__(kThreads) k_letterbox(const __grid_constant__ 
   const int S = p.stages;
   const int row_begin = blockIdx.x * p.rows_per_cta;
   const int nrows = min(p.rows_per_cta, p.dst_h - row_begin);
-  const bool has_mask = f.mask != nullptr;
-  const bool bulk = f.bulk_ok && (!has_mask || f.mask_bulk_ok);
+  const bool bulk = f.bulk_ok != 0;
+  const uint32_t stage_bytes = (uint32_t)p.rows_per_stage * (uint32_t)p.row_stride;
+  const uint32_t mstage_bytes = (uint32_t)p.rows_per_stage * (uint32_t)p.mask_stride;
   uint8_t* const rows_base = smem;
-  uint8_t* const mask_base = smem + (size_t)S * 2 * p.row_stride;
+  uint8_t* const mask_base = smem + (size_t)S * stage_bytes;
   const uint32_t row_bytes = 3u * (uint32_t)f.src_w;
 
+  if (threadIdx.x < nrows) s_ty[threadIdx.x] = yt[row_begin + threadIdx.x];
   if (bulk && threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
     mbar_fence_init();
   }
   __syncthreads();
 
-  // one elected thread feeds the TMA engine
-  auto issue = [&](int i) {
-    const TapY ty = yt[row_begin + i];
+  // one elected thread feeds the TMA engine: whole source rows, one bulk copy each
+  auto issue = [&](int i, int s) {
+    const TapY ty = s_ty[i];
     if (ty.y0 < 0) return;
-    const int s = i % S;
-    uint32_t bytes = 0;
-    if (ty.b0) bytes += row_bytes + (has_mask ? (uint32_t)f.src_w : 0u);
-    if (ty.b1) bytes += row_bytes + (has_mask ? (uint32_t)f.src_w : 0u);
-    mbar_expect_tx(&full[s], bytes);
-    uint8_t* r0 = rows_base + (size_t)(2 * s) * p.row_stride;
-    uint8_t* m0 = mask_base + (size_t)(2 * s) * p.mask_stride;
+    const uint32_t per_row = row_bytes + (MASK ? (uint32_t)f.src_w : 0u);
+    mbar_expect_tx(&full[s], (ty.b0 ? per_row : 0u) + (ty.b1 ? per_row : 0u));
+    uint8_t* r0 = rows_base + (size_t)s * stage_bytes;
+    uint8_t* m0 = mask_base + (size_t)s * mstage_bytes;
     if (ty.b0) {
       bulk_g2s(r0, f.src + (long long)ty.y0 * f.pitch, row_bytes, &full[s]);
-      if (has_mask) bulk_g2s(m0, f.mask + (size_t)ty.y0 * f.src_w, f.src_w, &full[s]);
+      if (MASK) bulk_g2s(m0, f.mask + (size_t)ty.y0 * f.src_w, f.src_w, &full[s]);
     }
     if (ty.b1) {
       bulk_g2s(r0 + p.row_stride, f.src + (long long)ty.y1 * f.pitch, row_bytes, &full[s]);
-      if (has_mask) bulk_g2s(m0 + p.mask_stride, f.mask + (size_t)ty.y1 * f.src_w, f.src_w, &full[s]);
+      if (MASK) bulk_g2s(m0 + p.mask_stride, f.mask + (size_t)ty.y1 * f.src_w, f.src_w, &full[s]);
     }
   };
 
+  int s_issue = 0;  // stage the next issued row goes to (thread 0 only)
   if (bulk && threadIdx.x == 0) {
-    for (int i = 0; i < S - 1 && i < nrows; ++i) issue(i);
+    for (int i = 0; i < S - 1 && i < nrows; ++i) {
+      issue(i, s_issue);
+      s_issue = s_issue + 1 == S ? 0 : s_issue + 1;
+    }
   }
 
   const int ngroups = (p.dst_w + 3) >> 2;
+  const int nthreads = blockDim.x;
   // tap entries of this thread's first pixel group stay in registers across all rows
   TapX tx[4];
+  bool ident = true;
   {
     const int g = threadIdx.x;
 #pragma unroll
@@ -198,22 +258,36 @@ __global__ void __launch_bounds__(kThreads) k_letterbox(const __grid_constant__ 
         tx[j].a0 = tx[j].a1 = 0;
         tx[j].mx0 = 0;
       }
+      ident = ident && (tx[j].off0 < 0 || (tx[j].a0 == 2048 && tx[j].a1 == 0));
     }
   }
+  const size_t plane = (size_t)p.dst_h * p.dst_w;
+  const size_t esize = FMT == B200VA_OUT_F32_RGB_NCHW ? 4 : (FMT == B200VA_OUT_F16_RGB_NCHW ? 2 : 1);
+  const bool nhwc = FMT == B200VA_OUT_U8_BGR_NHWC;
+  // element (frame, plane 0, row_begin, 4*tid) / pixel (frame, row_begin, 4*tid)
+  uint8_t* optr = (uint8_t*)p.out + ((size_t)f.out_idx * 3 * plane) * esize +
+                  (nhwc ? ((size_t)row_begin * p.dst_w + 4 * threadIdx.x) * 3
+                        : ((size_t)row_begin * p.dst_w + 4 * threadIdx.x) * esize);
+  const size_t row_step = nhwc ? (size_t)p.dst_w * 3 : (size_t)p.dst_w * esize;
+  const bool vec_ok = p.vec_ok != 0;
+  const int nvalid0 = min(4, p.dst_w - 4 * (int)threadIdx.x);
 
   uint32_t phase_bits = 0;
-  for (int i = 0; i < nrows; ++i) {
-    const int d = row_begin + i;
-    const TapY ty = yt[d];
-    const int s = bulk ? (i % S) : 0;
-    const uint8_t* r0 = rows_base + (size_t)(2 * s) * p.row_stride;
-    const uint8_t* r1 = r0 + p.row_stride;
-    const uint8_t* m0 = mask_base + (size_t)(2 * s) * p.mask_stride;
-    const uint8_t* m1 = m0 + p.mask_stride;
+  int s = 0;
+  for (int i = 0; i < nrows; ++i, optr += row_step) {
+    const TapY ty = s_ty[i];
     const bool pad_row = ty.y0 < 0;
+    const int sc = bulk ? s : 0;
+    const uint8_t* r0 = rows_base + (size_t)sc * stage_bytes;
+    const uint8_t* r1 = r0 + p.row_stride;
+    const uint8_t* m0 = mask_base + (size_t)sc * mstage_bytes;
+    const uint8_t* m1 = m0 + p.mask_stride;
 
     if (bulk) {
-      if (threadIdx.x == 0 && i + S - 1 < nrows) issue(i + S - 1);
+      if (threadIdx.x == 0 && i + S - 1 < nrows) {
+        issue(i + S - 1, s_issue);
+        s_issue = s_issue + 1 == S ? 0 : s_issue + 1;
+      }
       if (!pad_row) {
         mbar_wait(&full[s], (phase_bits >> s) & 1u);
         phase_bits ^= 1u << s;
@@ -221,58 +295,53 @@ __global__ void __launch_bounds__(kThreads) k_letterbox(const __grid_constant__ 
     } else if (!pad_row) {
       if (ty.b0) {
         coop_copy(const_cast<uint8_t*>(r0), f.src + (long long)ty.y0 * f.pitch, row_bytes);
-        if (has_mask) coop_copy(const_cast<uint8_t*>(m0), f.mask + (size_t)ty.y0 * f.src_w, f.src_w);
+        if (MASK) coop_copy(const_cast<uint8_t*>(m0), f.mask + (size_t)ty.y0 * f.src_w, f.src_w);
       }
       if (ty.b1) {
         coop_copy(const_cast<uint8_t*>(r1), f.src + (long long)ty.y1 * f.pitch, row_bytes);
-        if (has_mask) coop_copy(const_cast<uint8_t*>(m1), f.mask + (size_t)ty.y1 * f.src_w, f.src_w);
+        if (MASK) coop_copy(const_cast<uint8_t*>(m1), f.mask + (size_t)ty.y1 * f.src_w, f.src_w);
       }
       __syncthreads();
     }
 
-    for (int g = threadIdx.x; g < ngroups; g += blockDim.x) {
+    if ((int)threadIdx.x < ngroups) {
       int v[4][3];
+      if (pad_row) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j][0] = v[j][1] = v[j][2] = 114;
+      } else if (ident && ty.b0 == 2048 && ty.b1 == 0) {
+        px4_identity<MASK>(tx, r0, m0, v);
+      } else {
+        px4_general<MASK>(tx, r0, r1, m0, m1, ty.b0, ty.b1, v);
+      }
+      store_px4<FMT>(optr, plane, vec_ok, nvalid0, v);
+    }
+    // destination rows wider than 4 * blockDim pixels: remaining groups read their taps from global
+    for (int g = threadIdx.x + nthreads; g < ngroups; g += nthreads) {
+      TapX t[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        TapX t;
-        if (g == (int)threadIdx.x) {
-          t = tx[j];
+        const int x = 4 * g + j;
+        if (x < p.dst_w) {
+          int4 e = __ldg(reinterpret_cast<const int4*>(xt) + x);
+          t[j] = *reinterpret_cast<TapX*>(&e);
         } else {
-          const int x = 4 * g + j;
-          if (x < p.dst_w) {
-            int4 e = __ldg(reinterpret_cast<const int4*>(xt) + x);
-            t = *reinterpret_cast<TapX*>(&e);
-          } else {
-            t.off0 = -1;
-          }
+          t[j].off0 = -1;
         }
-        if (pad_row || t.off0 < 0) {
-          v[j][0] = v[j][1] = v[j][2] = 114;  // copyMakeBorder value, detector.py:233-241
-          continue;
-        }
-        const int a0 = t.a0, a1 = t.a1, b0 = ty.b0, b1 = ty.b1;
-        int s0[3] = {0, 0, 0}, s1[3] = {0, 0, 0};
-        if (b0) {
-          const bool k0 = a0 && (!has_mask || m0[t.mx0 & 0xffff]);
-          const bool k1 = a1 && (!has_mask || m0[(unsigned)t.mx0 >> 16]);
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-            s0[c] = (k0 ? (int)r0[t.off0 + c] * a0 : 0) + (k1 ? (int)r0[t.off1 + c] * a1 : 0);
-        }
-        if (b1) {
-          const bool k0 = a0 && (!has_mask || m1[t.mx0 & 0xffff]);
-          const bool k1 = a1 && (!has_mask || m1[(unsigned)t.mx0 >> 16]);
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-            s1[c] = (k0 ? (int)r1[t.off0 + c] * a0 : 0) + (k1 ? (int)r1[t.off1 + c] * a1 : 0);
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[j][c] = (((b0 * (s0[c] >> 4)) >> 16) + ((b1 * (s1[c] >> 4)) >> 16) + 2) >> 2;
       }
-      store_px4<FMT>(p, frame, d, 4 * g, v);
+      int v[4][3];
+      if (pad_row) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j][0] = v[j][1] = v[j][2] = 114;
+      } else {
+        px4_general<MASK>(t, r0, r1, m0, m1, ty.b0, ty.b1, v);
+      }
+      store_px4<FMT>(optr + (size_t)(g - (int)threadIdx.x) * 4 * (nhwc ? 3 : esize), plane, vec_ok,
+                     min(4, p.dst_w - 4 * g), v);
     }
     // the stage read in this iteration is refilled by the next iteration's issue()
-    __syncthreads();
+    if (!pad_row) __syncthreads();
+    s = s + 1 == S ? 0 : s + 1;
   }
 }
 
@@ -291,7 +360,11 @@ struct TapCache {
   int4* arena = nullptr;  // device
   size_t capacity = 0;    // entries
   size_t used = 0;
-  std::map<TapKey, int> index;
+  struct Entry {
+    int off;
+    bool single;  // y tables: no row ever needs the second source row (all b1 == 0)
+  };
+  std::map<TapKey, Entry> index;
 };
 
 static const size_t kTapArenaEntries = (size_t)1 << 19;  // 8 MiB of 16-byte entries
@@ -338,12 +411,14 @@ static void linear_tap(int src, int dst, int d, bool clamp_frac, int* i0, int* i
 }
 
 // Returns the arena offset of the table, building and uploading it on first use.
-static int get_table(b200va_ctx* h, int axis, int src, int dst_new, int pad, int dst_full, int* off_out) {
+static int get_table(b200va_ctx* h, int axis, int src, int dst_new, int pad, int dst_full, int* off_out,
+                     bool* single_out) {
   TapCache* tc = h->taps;
   TapKey key{axis, src, dst_new, pad, dst_full};
   auto it = tc->index.find(key);
   if (it != tc->index.end()) {
-    *off_out = it->second;
+    *off_out = it->second.off;
+    if (single_out) *single_out = it->second.single;
     return B200VA_OK;
   }
   if (tc->used + (size_t)dst_full > tc->capacity) {
@@ -354,6 +429,7 @@ static int get_table(b200va_ctx* h, int axis, int src, int dst_new, int pad, int
     if ((size_t)dst_full > tc->capacity) return set_error(h, B200VA_ERR_CAPACITY, "tap table of %d entries does not fit", dst_full);
   }
   std::vector<int4> host((size_t)dst_full);
+  bool single = true;
   for (int d = 0; d < dst_full; ++d) {
     const int k = d - pad;
     if (axis == 0) {
@@ -378,6 +454,7 @@ static int get_table(b200va_ctx* h, int axis, int src, int dst_new, int pad, int
         t.b0 = t.b1 = 0;
       } else {
         linear_tap(src, dst_new, k, false, &t.y0, &t.y1, &t.b0, &t.b1);
+        if (t.b1 != 0) single = false;
       }
       memcpy(&host[d], &t, sizeof(int4));
     }
@@ -386,8 +463,9 @@ static int get_table(b200va_ctx* h, int axis, int src, int dst_new, int pad, int
   // synchronous copy: the table is visible to every stream once this returns
   CUDA_TRY(h, cudaMemcpy(tc->arena + off, host.data(), host.size() * sizeof(int4), cudaMemcpyHostToDevice));
   tc->used += (size_t)dst_full;
-  tc->index[key] = off;
+  tc->index[key] = TapCache::Entry{off, single};
   *off_out = off;
+  if (single_out) *single_out = single;
   return B200VA_OK;
 }
 
@@ -405,97 +483,115 @@ extern "C" int b200va_letterbox_meta(int src_h, int src_w, int dst_h, int dst_w,
   return B200VA_OK;
 }
 
-template <int FMT>
-static cudaError_t launch_letterbox(const PreParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  k_letterbox<FMT><<<grid, kThreads, smem, st>>>(p);
+template <int FMT, bool MASK>
+static cudaError_t launch_one(const PreParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  k_letterbox<FMT, MASK><<<grid, kThreads, smem, st>>>(p);
   return cudaGetLastError();
+}
+
+template <int FMT>
+static cudaError_t launch_letterbox(const PreParams& p, bool mask, dim3 grid, size_t smem, cudaStream_t st) {
+  return mask ? launch_one<FMT, true>(p, grid, smem, st) : launch_one<FMT, false>(p, grid, smem, st);
 }
 
 static const int kLetterboxSmemMax = 200 * 1024;
 
+template <int FMT>
+static cudaError_t configure_fmt() {
+  cudaError_t e = cudaFuncSetAttribute(k_letterbox<FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_letterbox<FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax);
+}
+
 int preprocess_configure(b200va_ctx* h) {
-  CUDA_TRY(h, cudaFuncSetAttribute(k_letterbox<B200VA_OUT_F32_RGB_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax));
-  CUDA_TRY(h, cudaFuncSetAttribute(k_letterbox<B200VA_OUT_F16_RGB_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax));
-  CUDA_TRY(h, cudaFuncSetAttribute(k_letterbox<B200VA_OUT_U8_BGR_NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax));
-  CUDA_TRY(h, cudaFuncSetAttribute(k_letterbox<B200VA_OUT_U8_BGR_NHWC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax));
+  CUDA_TRY(h, configure_fmt<B200VA_OUT_F32_RGB_NCHW>());
+  CUDA_TRY(h, configure_fmt<B200VA_OUT_F16_RGB_NCHW>());
+  CUDA_TRY(h, configure_fmt<B200VA_OUT_U8_BGR_NCHW>());
+  CUDA_TRY(h, configure_fmt<B200VA_OUT_U8_BGR_NHWC>());
   return B200VA_OK;
 }
 
 // Shared by b200va_preprocess (letterbox geometry) and b200va_resize_linear_u8 (no padding).
+// Frames with and without an ROI mask go to separate launches (the mask is a template switch).
 static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* src_h, const int* src_w,
                         const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks, void* out,
-                        uint8_t* const* out_ptrs, const int* new_h, const int* new_w, const int* pad_top,
-                        const int* pad_left, int dst_h, int dst_w, int fmt, cudaStream_t st) {
-  const size_t esize = fmt == B200VA_OUT_F32_RGB_NCHW ? 4 : (fmt == B200VA_OUT_F16_RGB_NCHW ? 2 : 1);
-  for (int base = 0; base < batch;) {
-    // frames written through per-frame output pointers are launched one by one
-    const int n = out_ptrs ? 1 : (batch - base < B200VA_LAUNCH_FRAMES ? batch - base : B200VA_LAUNCH_FRAMES);
-    PreParams p;
-    memset(&p, 0, sizeof(p));
-    int max_row = 0, max_w = 0, any_mask = 0;
-    for (int i = 0; i < n; ++i) {
-      const int b = base + i;
-      PreFrame& f = p.f[i];
-      REQUIRE(h, frames[b] != nullptr, "frame %d is NULL", b);
-      REQUIRE(h, src_h[b] > 0 && src_w[b] > 0 && src_w[b] < 65536, "frame %d has unsupported size %dx%d", b, src_w[b], src_h[b]);
-      const int64_t pitch = src_pitch ? src_pitch[b] : (int64_t)3 * src_w[b];
-      REQUIRE(h, pitch >= (int64_t)3 * src_w[b], "frame %d: pitch %lld < 3*width", b, (long long)pitch);
-      REQUIRE(h, new_h[b] > 0 && new_w[b] > 0, "frame %d: resized size %dx%d is empty (cv2.resize would raise)", b, new_w[b], new_h[b]);
-      f.src = frames[b];
-      f.mask = roi_masks ? roi_masks[b] : nullptr;
-      f.pitch = pitch;
-      f.src_h = src_h[b];
-      f.src_w = src_w[b];
-      int rc = get_table(h, 0, src_w[b], new_w[b], pad_left[b], dst_w, &f.xtab);
-      if (rc) return rc;
-      rc = get_table(h, 1, src_h[b], new_h[b], pad_top[b], dst_h, &f.ytab);
-      if (rc) return rc;
-      const int rb = 3 * src_w[b];
-      f.bulk_ok = ((uintptr_t)f.src % 16 == 0) && (pitch % 16 == 0) && (rb % 16 == 0);
-      f.mask_bulk_ok = f.mask ? (((uintptr_t)f.mask % 16 == 0) && (src_w[b] % 16 == 0)) : 1;
-      if (rb > max_row) max_row = rb;
-      if (src_w[b] > max_w) max_w = src_w[b];
-      any_mask |= f.mask != nullptr;
+                        const int* new_h, const int* new_w, const int* pad_top, const int* pad_left, int dst_h,
+                        int dst_w, int fmt, cudaStream_t st) {
+  REQUIRE(h, fmt >= 0 && fmt <= 3, "unknown output format %d", fmt);
+  std::vector<int> order[2];
+  for (int b = 0; b < batch; ++b) order[(roi_masks && roi_masks[b]) ? 1 : 0].push_back(b);
+  for (int with_mask = 0; with_mask < 2; ++with_mask) {
+    const std::vector<int>& idx = order[with_mask];
+    for (size_t base = 0; base < idx.size(); base += B200VA_LAUNCH_FRAMES) {
+      const int n = (int)std::min<size_t>(B200VA_LAUNCH_FRAMES, idx.size() - base);
+      PreParams p;
+      memset(&p, 0, sizeof(p));
+      int max_row = 0, max_w = 0;
+      bool all_single = true;
+      for (int i = 0; i < n; ++i) {
+        const int b = idx[base + i];
+        PreFrame& f = p.f[i];
+        REQUIRE(h, frames[b] != nullptr, "frame %d is NULL", b);
+        REQUIRE(h, src_h[b] > 0 && src_w[b] > 0 && src_w[b] < 65536, "frame %d has unsupported size %dx%d", b, src_w[b], src_h[b]);
+        const int64_t pitch = src_pitch ? src_pitch[b] : (int64_t)3 * src_w[b];
+        REQUIRE(h, pitch >= (int64_t)3 * src_w[b], "frame %d: pitch %lld < 3*width", b, (long long)pitch);
+        REQUIRE(h, new_h[b] > 0 && new_w[b] > 0, "frame %d: resized size %dx%d is empty (cv2.resize would raise)", b, new_w[b], new_h[b]);
+        f.src = frames[b];
+        f.mask = with_mask ? roi_masks[b] : nullptr;
+        f.pitch = pitch;
+        f.src_h = src_h[b];
+        f.src_w = src_w[b];
+        f.out_idx = b;
+        bool single = true;
+        int rc = get_table(h, 0, src_w[b], new_w[b], pad_left[b], dst_w, &f.xtab, nullptr);
+        if (rc) return rc;
+        rc = get_table(h, 1, src_h[b], new_h[b], pad_top[b], dst_h, &f.ytab, &single);
+        if (rc) return rc;
+        all_single = all_single && single;
+        const int rb = 3 * src_w[b];
+        f.bulk_ok = ((uintptr_t)f.src % 16 == 0) && (pitch % 16 == 0) && (rb % 16 == 0) &&
+                    (!f.mask || (((uintptr_t)f.mask % 16 == 0) && (src_w[b] % 16 == 0)));
+        if (rb > max_row) max_row = rb;
+        if (src_w[b] > max_w) max_w = src_w[b];
+      }
+      p.tabs = h->taps->arena;
+      p.out = out;
+      p.dst_h = dst_h;
+      p.dst_w = dst_w;
+      p.fmt = fmt;
+      p.row_stride = (max_row + 127) & ~127;
+      p.mask_stride = with_mask ? ((max_w + 127) & ~127) : 0;
+      p.rows_per_stage = all_single ? 1 : 2;
+      const size_t per_stage = (size_t)p.rows_per_stage * ((size_t)p.row_stride + p.mask_stride);
+      int stages = (int)((size_t)kLetterboxSmemMax / per_stage);
+      if (stages > kMaxStages) stages = kMaxStages;
+      REQUIRE(h, stages >= 1, "source rows of %d bytes do not fit in shared memory", max_row);
+      p.stages = stages;
+      // enough CTAs for several waves over the SMs, few enough that the tap registers amortise
+      const long long total_rows = (long long)n * dst_h;
+      int rpc = (int)(total_rows / ((long long)h->num_sms * 16));
+      if (rpc < 2) rpc = 2;
+      if (rpc > kMaxRowsPerCta) rpc = kMaxRowsPerCta;
+      p.rows_per_cta = rpc;
+      const uintptr_t ob = (uintptr_t)out;
+      const size_t frame_elems = (size_t)3 * dst_h * dst_w;
+      switch (fmt) {
+        case B200VA_OUT_F32_RGB_NCHW: p.vec_ok = (dst_w % 4 == 0) && (ob % 16 == 0); break;
+        case B200VA_OUT_F16_RGB_NCHW: p.vec_ok = (dst_w % 4 == 0) && (ob % 8 == 0); break;
+        default: p.vec_ok = (dst_w % 4 == 0) && (ob % 4 == 0) && (frame_elems % 4 == 0); break;
+      }
+      dim3 grid((dst_h + rpc - 1) / rpc, n);
+      const size_t smem = (size_t)stages * per_stage;
+      cudaError_t e;
+      switch (fmt) {
+        case B200VA_OUT_F32_RGB_NCHW: e = launch_letterbox<B200VA_OUT_F32_RGB_NCHW>(p, with_mask, grid, smem, st); break;
+        case B200VA_OUT_F16_RGB_NCHW: e = launch_letterbox<B200VA_OUT_F16_RGB_NCHW>(p, with_mask, grid, smem, st); break;
+        case B200VA_OUT_U8_BGR_NCHW: e = launch_letterbox<B200VA_OUT_U8_BGR_NCHW>(p, with_mask, grid, smem, st); break;
+        default: e = launch_letterbox<B200VA_OUT_U8_BGR_NHWC>(p, with_mask, grid, smem, st); break;
+      }
+      h->launches.fetch_add(1, std::memory_order_relaxed);
+      if (e != cudaSuccess) return set_error(h, B200VA_ERR_CUDA, "letterbox launch failed: %s", cudaGetErrorString(e));
     }
-    p.tabs = h->taps->arena;
-    p.out = out_ptrs ? (void*)out_ptrs[base] : (void*)((uint8_t*)out + (size_t)base * 3 * dst_h * dst_w * esize);
-    p.dst_h = dst_h;
-    p.dst_w = dst_w;
-    p.fmt = fmt;
-    p.row_stride = (max_row + 127) & ~127;
-    p.mask_stride = any_mask ? ((max_w + 127) & ~127) : 0;
-    const size_t per_stage = 2 * ((size_t)p.row_stride + p.mask_stride);
-    const size_t budget = 160 * 1024;
-    int stages = (int)(budget / per_stage);
-    if (stages > kMaxStages) stages = kMaxStages;
-    REQUIRE(h, stages >= 1, "source rows of %d bytes do not fit in shared memory", max_row);
-    p.stages = stages;
-    // enough CTAs for several waves over the SMs, few enough that the tap registers amortise
-    long long total_rows = (long long)n * dst_h;
-    int rpc = (int)(total_rows / ((long long)h->num_sms * 16));
-    if (rpc < 2) rpc = 2;
-    if (rpc > 16) rpc = 16;
-    p.rows_per_cta = rpc;
-    const uintptr_t ob = (uintptr_t)p.out;
-    switch (fmt) {
-      case B200VA_OUT_F32_RGB_NCHW: p.vec_ok = (dst_w % 4 == 0) && (ob % 16 == 0); break;
-      case B200VA_OUT_F16_RGB_NCHW: p.vec_ok = (dst_w % 4 == 0) && (ob % 8 == 0); break;
-      case B200VA_OUT_U8_BGR_NCHW: p.vec_ok = (dst_w % 4 == 0) && (ob % 4 == 0); break;
-      default: p.vec_ok = (dst_w % 4 == 0) && (ob % 4 == 0); break;
-    }
-    dim3 grid((dst_h + rpc - 1) / rpc, n);
-    const size_t smem = (size_t)stages * per_stage;
-    cudaError_t e;
-    switch (fmt) {
-      case B200VA_OUT_F32_RGB_NCHW: e = launch_letterbox<B200VA_OUT_F32_RGB_NCHW>(p, grid, smem, st); break;
-      case B200VA_OUT_F16_RGB_NCHW: e = launch_letterbox<B200VA_OUT_F16_RGB_NCHW>(p, grid, smem, st); break;
-      case B200VA_OUT_U8_BGR_NCHW: e = launch_letterbox<B200VA_OUT_U8_BGR_NCHW>(p, grid, smem, st); break;
-      case B200VA_OUT_U8_BGR_NHWC: e = launch_letterbox<B200VA_OUT_U8_BGR_NHWC>(p, grid, smem, st); break;
-      default: return set_error(h, B200VA_ERR_INVALID, "unknown output format %d", fmt);
-    }
-    h->launches.fetch_add(1, std::memory_order_relaxed);
-    if (e != cudaSuccess) return set_error(h, B200VA_ERR_CUDA, "letterbox launch failed: %s", cudaGetErrorString(e));
-    base += n;
   }
   return B200VA_OK;
 }
@@ -520,8 +616,8 @@ extern "C" int b200va_preprocess(b200va_handle h, const uint8_t* const* frames, 
     pl[b] = m.pad_left;
     if (meta_out) meta_out[b] = m;
   }
-  return run_resample(h, frames, src_h, src_w, src_pitch, batch, roi_masks, out, nullptr, nh.data(), nw.data(),
-                      pt.data(), pl.data(), dst_h, dst_w, out_format, (cudaStream_t)stream);
+  return run_resample(h, frames, src_h, src_w, src_pitch, batch, roi_masks, out, nh.data(), nw.data(), pt.data(),
+                      pl.data(), dst_h, dst_w, out_format, (cudaStream_t)stream);
 }
 
 extern "C" int b200va_resize_linear_u8(b200va_handle h, const uint8_t* const* frames, const int* src_h,
@@ -538,8 +634,8 @@ extern "C" int b200va_resize_linear_u8(b200va_handle h, const uint8_t* const* fr
     REQUIRE(h, dst[b] != nullptr, "dst %d is NULL", b);
     REQUIRE(h, dst_h[b] > 0 && dst_w[b] > 0 && dst_w[b] < 65536, "frame %d: bad destination size %dx%d", b, dst_w[b], dst_h[b]);
     int rc = run_resample(h, frames + b, src_h + b, src_w + b, src_pitch ? src_pitch + b : nullptr, 1,
-                          roi_masks ? roi_masks + b : nullptr, nullptr, dst + b, dst_h + b, dst_w + b, &zero, &zero,
-                          dst_h[b], dst_w[b], B200VA_OUT_U8_BGR_NHWC, (cudaStream_t)stream);
+                          roi_masks ? roi_masks + b : nullptr, dst[b], dst_h + b, dst_w + b, &zero, &zero, dst_h[b],
+                          dst_w[b], B200VA_OUT_U8_BGR_NHWC, (cudaStream_t)stream);
     if (rc) return rc;
   }
   return B200VA_OK;

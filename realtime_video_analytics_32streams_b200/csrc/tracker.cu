@@ -75,13 +75,54 @@ __device__ __forceinline__ double iou64(double ax1, double ay1, double ax2, doub
   return __ddiv_rn(inter, uni);
 }
 
+constexpr int kDetChunk = 256;   // detections staged in shared memory at a time
+constexpr int kWarpPathMax = 96;  // frames with at most this many tracks + detections run on one warp
+
+struct DetStage {
+  double4 box[kDetChunk];
+  double conf[kDetChunk];
+  int cls[kDetChunk];
+};
+
+// Best track for one detection among tracks t = first, first + stride, ... (tracker.py:97-109).
+__device__ __forceinline__ void scan_tracks(const double* __restrict__ sbox, const int32_t* __restrict__ scls, int T,
+                                            int first, int stride, const double4 db, int dcls, double thr,
+                                            double& best, int& best_t) {
+  best = 0.0;  // best_iou starts at 0.0 and must be beaten strictly
+  best_t = 0x7fffffff;
+  for (int t = first; t < T; t += stride) {
+    if (scls[t] != dcls) continue;
+    const double4 tb = reinterpret_cast<const double4*>(sbox)[t];
+    // boxes that do not overlap have IoU 0, which can never beat best_iou
+    if (!(fmin(tb.z, db.z) > fmax(tb.x, db.x)) || !(fmin(tb.w, db.w) > fmax(tb.y, db.y))) continue;
+    const double v = iou64(tb.x, tb.y, tb.z, tb.w, db.x, db.y, db.z, db.w);
+    if (v >= thr && v > best) {
+      best = v;
+      best_t = t;
+    }
+  }
+}
+
+__device__ __forceinline__ void warp_argmax(double& best, int& best_t) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int ot = __shfl_xor_sync(0xffffffffu, best_t, o);
+    if (ob > best || (ob == best && ot < best_t)) {  // ties: earliest-inserted track
+      best = ob;
+      best_t = ot;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__ TrkParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   double* sbox = reinterpret_cast<double*>(smem_raw);                            // [max_tracks][4]
   int32_t* scls = reinterpret_cast<int32_t*>(sbox + (size_t)p.max_tracks * 4);   // [max_tracks]
+  __shared__ DetStage sd;
   __shared__ double red_iou[kTrkThreads / 32];
   __shared__ int red_t[kTrkThreads / 32];
-  __shared__ int s_T, s_new, s_is_last;
+  __shared__ int s_T, s_new, s_is_last, s_match;
 
   const int bi = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -108,100 +149,127 @@ __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__
     s_T = T0;
     s_new = 0;
   }
-  __syncthreads();
 
   const int D = p.skip[bi] ? 0 : min(p.d_count[bi], p.max_dets);
   const size_t db = (size_t)bi * p.max_dets;
   const double scale = p.det_scale[bi];
-  for (int d = 0; d < D; ++d) {
-    double bx1, by1, bx2, by2, dconf;
-    if (p.f_box) {
-      const float4 b = reinterpret_cast<const float4*>(p.f_box)[db + d];
-      bx1 = b.x, by1 = b.y, bx2 = b.z, by2 = b.w;
-      dconf = (double)p.f_conf[db + d];
-      if (p.has_scale) {  // StreamWorker._rescale_detections, pipeline.py:224-240: float64 multiply
-        bx1 = __dmul_rn(bx1, scale);
-        by1 = __dmul_rn(by1, scale);
-        bx2 = __dmul_rn(bx2, scale);
-        by2 = __dmul_rn(by2, scale);
-      }
-    } else {
-      const double4 b = reinterpret_cast<const double4*>(p.d_box)[db + d];
-      bx1 = b.x, by1 = b.y, bx2 = b.z, by2 = b.w;
-      dconf = p.d_conf[db + d];
-    }
-    const int dcls = p.d_cls[db + d];
-    const int T = s_T;
+  const bool warp_path = T0 + D <= kWarpPathMax;
 
-    double best = 0.0;  // best_iou starts at 0.0 and must be beaten strictly (tracker.py:100-106)
-    int best_t = 0x7fffffff;
-    for (int t = tid; t < T; t += kTrkThreads) {
-      if (scls[t] != dcls) continue;
-      const double4 tb = reinterpret_cast<const double4*>(sbox)[t];
-      // boxes that do not overlap have IoU 0, which can never beat best_iou
-      if (!(fmin(tb.z, bx2) > fmax(tb.x, bx1)) || !(fmin(tb.w, by2) > fmax(tb.y, by1))) continue;
-      const double v = iou64(tb.x, tb.y, tb.z, tb.w, bx1, by1, bx2, by2);
-      if (v >= p.thr && v > best) {
-        best = v;
-        best_t = t;
+  // thread 0 / lane 0 applies the outcome of one detection (tracker.py:69-92)
+  auto apply = [&](int match, int T, const double4 bx, double dconf, int dcls) {
+    int t = match;
+    if (t == 0x7fffffff) {  // no match: new track, matchable at once
+      t = T;
+      if (t < p.max_tracks) {
+        const int ord = s_new;
+        id_c[t] = p.has_id_base ? p.id_base[bi] + ord : -(long long)(ord + 1);
+        cls_c[t] = dcls;
+        scls[t] = dcls;
+        hits_c[t] = 1;
+        s_new = ord + 1;
+        s_T = T + 1;
+      } else {
+        atomicOr(p.flags + FLAG_TRACK_OVERFLOW, 1);
+        t = -1;
       }
+    } else {  // match: overwrite immediately
+      hits_c[t] += 1;
     }
-    const int any = __syncthreads_or(best_t != 0x7fffffff);
-    int match = -1;
-    if (any) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int ot = __shfl_xor_sync(0xffffffffu, best_t, o);
-        if (ob > best || (ob == best && ot < best_t)) {
-          best = ob;
-          best_t = ot;
-        }
-      }
-      if (lane == 0) {
-        red_iou[warp] = best;
-        red_t[warp] = best_t;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        double b = red_iou[0];
-        int bt = red_t[0];
-        for (int w = 1; w < kTrkThreads / 32; ++w)
-          if (red_iou[w] > b || (red_iou[w] == b && red_t[w] < bt)) {
-            b = red_iou[w];
-            bt = red_t[w];
-          }
-        match = bt;
-      }
+    if (t >= 0) {
+      reinterpret_cast<double4*>(sbox)[t] = bx;
+      conf_c[t] = dconf;
+      age_c[t] = 0;
+      touched[t] = 1;
     }
-    if (tid == 0) {
-      int t = match;
-      if (t < 0 || t == 0x7fffffff) {  // tracker.py:69-80: new track, matchable at once
-        t = T;
-        if (t < p.max_tracks) {
-          const int ord = s_new;
-          id_c[t] = p.has_id_base ? p.id_base[bi] + ord : -(long long)(ord + 1);
-          cls_c[t] = dcls;
-          scls[t] = dcls;
-          hits_c[t] = 1;
-          s_new = ord + 1;
-          s_T = T + 1;
-        } else {
-          atomicOr(p.flags + FLAG_TRACK_OVERFLOW, 1);
-          t = -1;
+  };
+
+  for (int d0 = 0; d0 < D; d0 += kDetChunk) {
+    const int nd = min(kDetChunk, D - d0);
+    __syncthreads();  // previous chunk fully consumed (and the track table staged, first time round)
+    for (int i = tid; i < nd; i += kTrkThreads) {
+      const int d = d0 + i;
+      double4 b;
+      double cf;
+      if (p.f_box) {
+        const float4 f4 = reinterpret_cast<const float4*>(p.f_box)[db + d];
+        b = make_double4(f4.x, f4.y, f4.z, f4.w);
+        cf = (double)p.f_conf[db + d];
+        if (p.has_scale) {  // StreamWorker._rescale_detections, pipeline.py:224-240: float64 multiply
+          b.x = __dmul_rn(b.x, scale);
+          b.y = __dmul_rn(b.y, scale);
+          b.z = __dmul_rn(b.z, scale);
+          b.w = __dmul_rn(b.w, scale);
         }
-      } else {  // tracker.py:82-86: overwrite immediately
-        hits_c[t] += 1;
+      } else {
+        b = reinterpret_cast<const double4*>(p.d_box)[db + d];
+        cf = p.d_conf[db + d];
       }
-      if (t >= 0) {
-        reinterpret_cast<double4*>(sbox)[t] = make_double4(bx1, by1, bx2, by2);
-        conf_c[t] = dconf;
-        age_c[t] = 0;
-        touched[t] = 1;
-      }
+      sd.box[i] = b;
+      sd.conf[i] = cf;
+      sd.cls[i] = p.d_cls[db + d];
     }
     __syncthreads();
+
+    if (warp_path) {
+      // few tracks: one warp walks the detections with warp-level synchronisation only
+      if (warp == 0) {
+        for (int i = 0; i < nd; ++i) {
+          const double4 bx = sd.box[i];
+          const int dcls = sd.cls[i];
+          const int T = s_T;
+          double best;
+          int best_t;
+          scan_tracks(sbox, scls, T, lane, 32, bx, dcls, p.thr, best, best_t);
+          const unsigned cand = __ballot_sync(0xffffffffu, best_t != 0x7fffffff);
+          int match = 0x7fffffff;
+          if (cand) {
+            if (cand & (cand - 1)) {
+              warp_argmax(best, best_t);
+              match = best_t;
+            } else {
+              match = __shfl_sync(0xffffffffu, best_t, __ffs(cand) - 1);
+            }
+          }
+          if (lane == 0) apply(match, T, bx, sd.conf[i], dcls);
+          __syncwarp();
+        }
+      }
+    } else {
+      for (int i = 0; i < nd; ++i) {
+        const double4 bx = sd.box[i];
+        const int dcls = sd.cls[i];
+        const int T = s_T;
+        double best;
+        int best_t;
+        scan_tracks(sbox, scls, T, tid, kTrkThreads, bx, dcls, p.thr, best, best_t);
+        const int ncand = __syncthreads_count(best_t != 0x7fffffff);
+        if (ncand == 1) {
+          if (best_t != 0x7fffffff) s_match = best_t;
+          __syncthreads();
+        } else if (ncand > 1) {
+          warp_argmax(best, best_t);
+          if (lane == 0) {
+            red_iou[warp] = best;
+            red_t[warp] = best_t;
+          }
+          __syncthreads();
+          if (tid == 0) {
+            double b = red_iou[0];
+            int bt = red_t[0];
+            for (int w = 1; w < kTrkThreads / 32; ++w)
+              if (red_iou[w] > b || (red_iou[w] == b && red_t[w] < bt)) {
+                b = red_iou[w];
+                bt = red_t[w];
+              }
+            s_match = bt;
+          }
+        }
+        if (tid == 0) apply(ncand == 0 ? 0x7fffffff : s_match, T, bx, sd.conf[i], dcls);
+        __syncthreads();
+      }
+    }
   }
+  __syncthreads();
 
   // ---- prune + stable compaction into the other buffer (tracker.py:111-126) ----
   const int T = s_T;
