@@ -153,6 +153,20 @@ B200VA_API int b200va_preprocess(b200va_handle h, const uint8_t* const* frames, 
                       const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks, void* out,
                       int dst_h, int dst_w, int out_format, b200va_letterbox* meta_out, void* stream);
 
+/* ---- host -> device staging of decoded frames -------------------------------------------
+ * The reference hands host ndarrays to predict() (detector.py:193, pipeline.py:172-179); this is
+ * the upload half of that call.  host_frames HOST array [batch] of HOST pointers (pinned memory
+ * for asynchronous copies), dev_frames HOST array [batch] of DEVICE pointers to full-size frame
+ * buffers, pitches in bytes (NULL = 3*w).  rows_mode 0 copies every row; rows_mode 1 copies only
+ * the rows that b200va_preprocess to dst_h x dst_w reads (non-zero vertical tap weight), into
+ * their original positions -- e.g. one row in three for 1080p -> 640x360 -- so the device frame
+ * is valid for b200va_preprocess but NOT for b200va_motion / b200va_resize_linear_u8.
+ * bytes_copied (HOST, may be NULL) receives the number of bytes put on the bus. */
+B200VA_API int b200va_upload_frames(b200va_handle h, const uint8_t* const* host_frames, uint8_t* const* dev_frames,
+                                    const int* src_h, const int* src_w, const int64_t* host_pitch,
+                                    const int64_t* dev_pitch, int batch, int dst_h, int dst_w, int rows_mode,
+                                    int64_t* bytes_copied, void* stream);
+
 /* ---- a10: downsample -----------------------------------------------------------------
  * Replaces utils.downsample (frame_filter.py:53-57): cv2.resize INTER_LINEAR, BGR uint8 HWC in,
  * BGR uint8 HWC out (dst pitch = 3*dst_w).  dst HOST array [batch] of DEVICE pointers.

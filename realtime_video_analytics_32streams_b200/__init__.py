@@ -13,8 +13,7 @@ All compute lives in ``lib/libb200va.so`` (C ABI: ``include/b200va.h``); importi
 fails loudly when the library is missing.  Nothing in here imports ``oracle/``.
 """
 
-from .types import (Detection, DetectorConfig, FramePacket, FrameResult, MotionFilterConfig, StreamConfig, Track,
-                    TrackerConfig)
+from .types import Detection, DetectorConfig, FramePacket, MotionFilterConfig, StreamConfig, Track, TrackerConfig
 
 __all__ = ["Detection", "DetectorConfig", "FramePacket", "FrameResult", "MotionFilterConfig", "StreamConfig", "Track",
            "TrackerConfig", "B200Detector", "B200IouTracker", "HotPathEngine", "MotionFilter", "apply_roi",
@@ -22,7 +21,7 @@ __all__ = ["Detection", "DetectorConfig", "FramePacket", "FrameResult", "MotionF
 
 _LAZY = {
     "B200Detector": "detector", "filter_detections": "detector", "B200IouTracker": "tracker",
-    "HotPathEngine": "engine", "MotionFilter": "frame_filter", "apply_roi": "frame_filter",
+    "HotPathEngine": "engine", "FrameResult": "engine", "MotionFilter": "frame_filter", "apply_roi": "frame_filter",
     "downsample": "frame_filter", "roi_mask": "frame_filter", "get_handle": "runtime",
     "register_with_reference": "integration",
 }

@@ -63,7 +63,7 @@ EXPORTS = (
     "b200va_launch_count", "b200va_poll_status", "b200va_letterbox_meta", "b200va_preprocess",
     "b200va_resize_linear_u8", "b200va_roi_rasterize", "b200va_apply_mask", "b200va_motion",
     "b200va_postprocess", "b200va_tracker_update", "b200va_tracker_update_f64", "b200va_tracker_reset",
-    "b200va_tracker_set_next_id",
+    "b200va_tracker_set_next_id", "b200va_upload_frames",
 )
 
 _lib = None
@@ -106,6 +106,8 @@ def load_library() -> C.CDLL:
                                           C.POINTER(C.c_uint8), C.POINTER(TrackerCfg), i64p, C.POINTER(Tracks), vp, vp]
     lib.b200va_tracker_update_f64.argtypes = [vp, ip, C.c_int, C.POINTER(Dets64), C.c_int, C.POINTER(C.c_uint8),
                                               C.POINTER(TrackerCfg), i64p, C.POINTER(Tracks), vp, vp]
+    lib.b200va_upload_frames.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip, ip, i64p, i64p, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, i64p, vp]
     lib.b200va_tracker_reset.argtypes = [vp, C.c_int, vp]
     lib.b200va_tracker_set_next_id.argtypes = [vp, C.c_int64, vp]
     for name in EXPORTS:
@@ -213,6 +215,24 @@ class Handle:
     def _batch(frames, roi_masks=None) -> FrameBatch:
         return frames if isinstance(frames, FrameBatch) else FrameBatch(frames, roi_masks)
 
+    # -- staging ----------------------------------------------------------------------------
+    def upload_frames(self, host_ptrs, dev_frames, sparse_for=None) -> int:
+        """Asynchronous host -> device copy of decoded frames.  ``host_ptrs[i]`` = (address, pitch) of
+        frame i in host memory (pinned for a truly asynchronous copy); ``dev_frames`` the CUDA
+        uint8 [H,W,3] destination buffers.  ``sparse_for=(dst_h, dst_w)`` copies only the rows the
+        letterbox to that size reads.  Returns the bytes put on the bus."""
+        n = len(dev_frames)
+        if n == 0:
+            return 0
+        moved = C.c_int64(0)
+        self._check(self.lib.b200va_upload_frames(
+            self._h, _ptr_array([p for p, _ in host_ptrs]), _ptr_array([d.data_ptr() for d in dev_frames]),
+            _int_array([d.shape[0] for d in dev_frames]), _int_array([d.shape[1] for d in dev_frames]),
+            (C.c_int64 * n)(*[int(pt) for _, pt in host_ptrs]), (C.c_int64 * n)(*[d.stride(0) for d in dev_frames]),
+            n, int(sparse_for[0]) if sparse_for else 0, int(sparse_for[1]) if sparse_for else 0,
+            1 if sparse_for else 0, C.byref(moved), self._stream()))
+        return int(moved.value)
+
     # -- a1 ---------------------------------------------------------------------------------
     def preprocess(self, frames, dst_hw=(640, 640), fmt: int = OUT_F32_RGB_NCHW, roi_masks=None, out=None):
         """Batched letterbox.  ``frames``: list of CUDA tensors or a ``FrameBatch``.
@@ -290,13 +310,32 @@ class Handle:
         return changed_out
 
     # -- a3-a7 ------------------------------------------------------------------------------
-    def alloc_dets(self, batch: int):
+    _DET_FIELDS = (("bbox_xyxy", "float32", 4), ("conf", "float32", 1), ("cls", "int32", 1))
+    _TRK_FIELDS = (("bbox_xyxy", "float64", 4), ("track_id", "int64", 1), ("conf", "float64", 1), ("cls", "int32", 1),
+                   ("age", "int32", 1), ("hits", "int32", 1))
+
+    def _alloc_soa(self, fields, batch: int, rows: int, extra_counts, pinned_host: bool = False):
+        """Structure-of-arrays carved from ONE flat byte buffer (field-major), so a whole result set
+        moves device -> host in a single copy.  Returns {name: typed view, "_flat": bytes}."""
         t = self.torch
-        md = self.cfg.max_dets
-        return {"bbox_xyxy": t.empty((batch, md, 4), dtype=t.float32, device=self.device),
-                "conf": t.empty((batch, md), dtype=t.float32, device=self.device),
-                "cls": t.empty((batch, md), dtype=t.int32, device=self.device),
-                "count": t.zeros((batch,), dtype=t.int32, device=self.device)}
+        sizes, off = [], 0
+        for name, dtype, width in fields:
+            nbytes = batch * rows * width * getattr(t, dtype).itemsize
+            sizes.append((name, dtype, width, off, nbytes))
+            off += (nbytes + 255) & ~255
+        for name in extra_counts:
+            sizes.append((name, "int32", 0, off, batch * 4))
+            off += (batch * 4 + 255) & ~255
+        flat = (t.zeros(off, dtype=t.uint8).pin_memory() if pinned_host
+                else t.zeros(off, dtype=t.uint8, device=self.device))
+        out = {"_flat": flat}
+        for name, dtype, width, o, nbytes in sizes:
+            v = flat[o:o + nbytes].view(getattr(t, dtype))
+            out[name] = v.view(batch) if width == 0 else (v.view(batch, rows) if width == 1 else v.view(batch, rows, width))
+        return out
+
+    def alloc_dets(self, batch: int, pinned_host: bool = False):
+        return self._alloc_soa(self._DET_FIELDS, batch, self.cfg.max_dets, ("count",), pinned_host)
 
     @staticmethod
     def _dets_struct(d) -> Dets:
@@ -325,17 +364,8 @@ class Handle:
         return out
 
     # -- a8 ---------------------------------------------------------------------------------
-    def alloc_tracks(self, batch: int):
-        t = self.torch
-        mt = self.cfg.max_tracks
-        return {"track_id": t.empty((batch, mt), dtype=t.int64, device=self.device),
-                "cls": t.empty((batch, mt), dtype=t.int32, device=self.device),
-                "conf": t.empty((batch, mt), dtype=t.float64, device=self.device),
-                "bbox_xyxy": t.empty((batch, mt, 4), dtype=t.float64, device=self.device),
-                "age": t.empty((batch, mt), dtype=t.int32, device=self.device),
-                "hits": t.empty((batch, mt), dtype=t.int32, device=self.device),
-                "count": t.zeros((batch,), dtype=t.int32, device=self.device),
-                "new_count": t.zeros((batch,), dtype=t.int32, device=self.device)}
+    def alloc_tracks(self, batch: int, pinned_host: bool = False):
+        return self._alloc_soa(self._TRK_FIELDS, batch, self.cfg.max_tracks, ("count", "new_count"), pinned_host)
 
     def tracker_update(self, slots, dets, max_age: int, min_hits: int, max_iou_distance: float, det_scale=None,
                        skip=None, id_base=None, out=None, f64: bool = False):

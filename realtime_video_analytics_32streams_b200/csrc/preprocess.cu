@@ -640,3 +640,104 @@ extern "C" int b200va_resize_linear_u8(b200va_handle h, const uint8_t* const* fr
   }
   return B200VA_OK;
 }
+
+// ---- host -> device staging of decoded frames ---------------------------------------------------
+// The letterbox reads only the source rows that carry a non-zero vertical weight (every third row
+// for 1080p -> 640x360, two rows in six for 4K).  With rows_mode = 1 only those rows cross PCIe, into
+// their original positions of the device frame, as one strided 2-D DMA per frame; the kernels then
+// run unchanged.  Frames that feed the motion gate or a downsample need every row (rows_mode = 0).
+namespace {
+struct RowPattern {
+  bool regular = false;  // needed rows = runs of `run` rows every `period` rows starting at `first`
+  int first = 0, run = 0, period = 0, count = 0;
+};
+std::map<std::pair<int, int>, RowPattern> g_row_patterns;
+std::mutex g_row_mu;
+
+RowPattern needed_rows(int src_h, int new_h) {
+  std::lock_guard<std::mutex> lock(g_row_mu);
+  auto key = std::make_pair(src_h, new_h);
+  auto it = g_row_patterns.find(key);
+  if (it != g_row_patterns.end()) return it->second;
+  std::vector<char> need((size_t)src_h, 0);
+  for (int d = 0; d < new_h; ++d) {
+    int y0, y1;
+    short b0, b1;
+    linear_tap(src_h, new_h, d, false, &y0, &y1, &b0, &b1);
+    if (b0) need[y0] = 1;
+    if (b1) need[y1] = 1;
+  }
+  std::vector<std::pair<int, int>> runs;  // (start, length)
+  for (int y = 0; y < src_h;) {
+    if (!need[y]) {
+      ++y;
+      continue;
+    }
+    int e = y;
+    while (e < src_h && need[e]) ++e;
+    runs.push_back({y, e - y});
+    y = e;
+  }
+  RowPattern rp;
+  if (!runs.empty()) {
+    rp.regular = true;
+    rp.first = runs[0].first;
+    rp.run = runs[0].second;
+    rp.count = (int)runs.size();
+    rp.period = runs.size() > 1 ? runs[1].first - runs[0].first : rp.run;
+    for (size_t i = 0; i < runs.size(); ++i)
+      if (runs[i].second != rp.run || runs[i].first != rp.first + (int)i * rp.period) rp.regular = false;
+    // nothing to gain when (nearly) every row is needed
+    if ((long long)rp.run * rp.count * 10 > (long long)src_h * 8) rp.regular = false;
+  }
+  g_row_patterns[key] = rp;
+  return rp;
+}
+}  // namespace
+
+extern "C" int b200va_upload_frames(b200va_handle h, const uint8_t* const* host_frames, uint8_t* const* dev_frames,
+                                    const int* src_h, const int* src_w, const int64_t* host_pitch,
+                                    const int64_t* dev_pitch, int batch, int dst_h, int dst_w, int rows_mode,
+                                    int64_t* bytes_copied, void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  REQUIRE(h, host_frames && dev_frames && src_h && src_w, "NULL argument");
+  REQUIRE(h, batch >= 0, "negative batch");
+  int64_t total = 0;
+  for (int b = 0; b < batch; ++b) {
+    REQUIRE(h, host_frames[b] && dev_frames[b] && src_h[b] > 0 && src_w[b] > 0, "frame %d: bad arguments", b);
+    const size_t rb = (size_t)3 * src_w[b];
+    const size_t hp = host_pitch ? (size_t)host_pitch[b] : rb, dp = dev_pitch ? (size_t)dev_pitch[b] : rb;
+    REQUIRE(h, hp >= rb && dp >= rb, "frame %d: pitch smaller than 3*width", b);
+    RowPattern rp;
+    if (rows_mode == 1) {
+      b200va_letterbox m;
+      REQUIRE(h, b200va_letterbox_meta(src_h[b], src_w[b], dst_h, dst_w, &m) == B200VA_OK && m.new_h > 0, "frame %d: bad letterbox geometry", b);
+      rp = needed_rows(src_h[b], m.new_h);
+    }
+    if (rp.regular) {
+      if (hp == rb && dp == rb) {
+        // a run of consecutive rows is one contiguous span
+        CUDA_TRY(h, cudaMemcpy2DAsync(dev_frames[b] + (size_t)rp.first * dp, (size_t)rp.period * dp,
+                                      host_frames[b] + (size_t)rp.first * hp, (size_t)rp.period * hp,
+                                      (size_t)rp.run * rb, rp.count, cudaMemcpyHostToDevice, st));
+      } else {
+        for (int r = 0; r < rp.run; ++r)
+          CUDA_TRY(h, cudaMemcpy2DAsync(dev_frames[b] + (size_t)(rp.first + r) * dp, (size_t)rp.period * dp,
+                                        host_frames[b] + (size_t)(rp.first + r) * hp, (size_t)rp.period * hp, rb,
+                                        rp.count, cudaMemcpyHostToDevice, st));
+      }
+      total += (int64_t)rp.run * rp.count * (int64_t)rb;
+    } else {
+      if (hp == rb && dp == rb)
+        CUDA_TRY(h, cudaMemcpyAsync(dev_frames[b], host_frames[b], rb * (size_t)src_h[b], cudaMemcpyHostToDevice, st));
+      else
+        CUDA_TRY(h, cudaMemcpy2DAsync(dev_frames[b], dp, host_frames[b], hp, rb, src_h[b], cudaMemcpyHostToDevice, st));
+      total += (int64_t)rb * src_h[b];
+    }
+  }
+  if (bytes_copied) *bytes_copied = total;
+  return B200VA_OK;
+}

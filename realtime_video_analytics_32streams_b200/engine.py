@@ -7,11 +7,18 @@ ROI -> downsample -> motion gate -> adaptive-FPS gate -> predict -> rescale -> f
 host exactly as the reference computes them; everything that touches pixels, head tensors or
 track tables is one batched kernel launch per step.  Skipped streams still age their tracks
 (``_skip_frame``: ``tracker.update(stream, [])``).
+
+``tick`` = ``submit`` + ``collect``.  ``submit`` only enqueues work (uploads, kernels, one
+device->host copy of the result tables into pinned memory); ``collect`` waits for it and hands out
+``FrameResult`` objects whose ``Detection`` / ``Track`` lists are materialised lazily from the host
+arrays.  When no stream uses the motion gate or adaptive FPS (whose decisions depend on the
+previous tick's results) a caller may submit tick k+1 before collecting tick k, which overlaps the
+PCIe upload of the next frames with the host-side handling of the current results.
 """
 
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence
 
 import numpy as np
@@ -21,7 +28,7 @@ from .detector import B200Detector
 from .frame_filter import MotionFilter, roi_mask
 from .runtime import FrameStager, get_handle
 from .tracker import B200IouTracker
-from .types import Detection, FrameResult, MotionFilterConfig, Track
+from .types import Detection, MotionFilterConfig, Track
 
 
 @dataclass
@@ -59,42 +66,154 @@ class _StreamState:
                 self.process_every = max(self.max_process_every, 1)
 
 
+class FrameResult:
+    """What one stream produced in one tick.  ``n_detections`` / ``n_tracks`` and the ``*_arrays``
+    are plain host data; ``detections`` / ``tracks`` build the reference's ``Detection`` / ``Track``
+    objects on first access (the sinks that want objects pay for them, nobody else does)."""
+
+    __slots__ = ("stream_name", "frame_id", "processed", "skip_reason", "n_detections", "n_tracks", "_ctx", "_pos",
+                 "_dets", "_tracks")
+
+    def __init__(self, stream_name, frame_id, processed, skip_reason, n_det, n_trk, ctx, pos):
+        self.stream_name, self.frame_id, self.processed, self.skip_reason = stream_name, frame_id, processed, skip_reason
+        self.n_detections, self.n_tracks = n_det, n_trk
+        self._ctx, self._pos = ctx, pos
+        self._dets = self._tracks = None
+
+    @property
+    def track_arrays(self) -> Dict[str, np.ndarray]:
+        """Host views: track_id, cls, conf, bbox_xyxy, age, hits -- rows [0, n_tracks)."""
+        h, n, p = self._ctx.host_tracks, self.n_tracks, self._pos
+        return {k: h[k][p, :n] for k in ("track_id", "cls", "conf", "bbox_xyxy", "age", "hits")}
+
+    @property
+    def detection_arrays(self) -> Dict[str, np.ndarray]:
+        """Host views: cls, conf (float64), bbox_xyxy (float64, rescaled like pipeline.py:224-240)."""
+        h, n, p = self._ctx.host_dets, self.n_detections, self._pos
+        box = h["bbox_xyxy"][p, :n].astype(np.float64)
+        sc = self._ctx.scale[p]
+        if sc != 1.0:
+            box = box * sc
+        return {"cls": h["cls"][p, :n], "conf": h["conf"][p, :n].astype(np.float64), "bbox_xyxy": box}
+
+    @property
+    def tracks(self) -> List[Track]:
+        if self._tracks is None:
+            a = self.track_arrays
+            self._tracks = [Track(i, c, f, tuple(b), g, k) for i, c, f, b, g, k in
+                            zip(a["track_id"].tolist(), a["cls"].tolist(), a["conf"].tolist(), a["bbox_xyxy"].tolist(),
+                                a["age"].tolist(), a["hits"].tolist())]
+        return self._tracks
+
+    @property
+    def detections(self) -> List[Detection]:
+        if self._dets is None:
+            if not self.processed or self.n_detections == 0:
+                self._dets = []
+            else:
+                a = self.detection_arrays
+                nm, fid = self.stream_name, self.frame_id
+                self._dets = [Detection(nm, fid, c, f, tuple(b)) for c, f, b in
+                              zip(a["cls"].tolist(), a["conf"].tolist(), a["bbox_xyxy"].tolist())]
+        return self._dets
+
+
+class _TickCtx:
+    """Buffers of one in-flight tick."""
+
+    def __init__(self, h: _native.Handle, n: int):
+        t = h.torch
+        self.dets = h.alloc_dets(n)
+        self.tracks = h.alloc_tracks(n)
+        self.host_dets_t = h.alloc_dets(n, pinned_host=True)
+        self.host_tracks_t = h.alloc_tracks(n, pinned_host=True)
+        self.host_dets = {k: v.numpy() for k, v in self.host_dets_t.items() if not k.startswith("_")}
+        self.host_tracks = {k: v.numpy() for k, v in self.host_tracks_t.items() if not k.startswith("_")}
+        self.done = t.cuda.Event()
+        self.busy = False
+        # filled by submit()
+        self.order: List[int] = []
+        self.n_act = 0
+        self.names: List[str] = []
+        self.ids: List[int] = []
+        self.states: List[_StreamState] = []
+        self.skip_reason: List[Optional[str]] = []
+        self.scale: List[float] = []
+        self.live: List[int] = []
+
+
 class HotPathEngine:
     """pre + post + track for a set of streams, one tick at a time."""
 
     def __init__(self, streams: Sequence, detector_config, tracker_config, infer: Callable,
-                 handle: Optional[_native.Handle] = None, input_hw=None, build_objects: bool = True):
+                 handle: Optional[_native.Handle] = None, input_hw=None, depth: int = 2):
         self.h = handle if handle is not None else get_handle()
         self.streams = list(streams)
         self.detector = B200Detector(detector_config, input_hw=input_hw, infer=infer, handle=self.h, fold_filter=True)
         self.tracker = B200IouTracker(tracker_config, handle=self.h)
         self.state: Dict[str, _StreamState] = {s.name: _StreamState(s) for s in self.streams}
         self.stager = FrameStager(self.h)
-        self.build_objects = build_objects
         n = max(len(self.streams), 1)
-        self._dets = self.h.alloc_dets(n)
-        self._tracks = self.h.alloc_tracks(n)
+        self._ctxs = [_TickCtx(self.h, n) for _ in range(max(depth, 1))]
+        self._turn = 0
         self._changed = self.h.torch.empty((n,), dtype=self.h.torch.int32, device=self.h.device)
-        self.last_soa = None  # device SoA of the last tick (tracks), for callers that skip objects
+        self._batches: Dict[tuple, _native.FrameBatch] = {}
+        self._net = None
+        # a tick's gates depend on the previous tick's results for these features
+        self.sequential = any(getattr(s, "motion_filter", False) or getattr(s, "adaptive_fps", False)
+                              for s in self.streams)
 
     # --------------------------------------------------------------------------------------
-    def tick(self, frames: Sequence, frame_ids: Optional[Sequence[int]] = None,
-             infer_ctx=None) -> List[FrameResult]:
-        """``frames[i]`` is the new frame of ``streams[i]`` (host array or CUDA tensor) or None
-        when that stream delivered nothing this tick."""
+    def _frame_batch(self, frames, masks):
+        """Argument arrays are cached per set of device pointers (staging buffers are persistent)."""
+        key = tuple((f.data_ptr(), f.shape[0], f.shape[1], f.stride(0), m.data_ptr() if m is not None else 0)
+                    for f, m in zip(frames, masks))
+        fb = self._batches.get(key)
+        if fb is None:
+            if len(self._batches) > 64:
+                self._batches.clear()
+            fb = self._batches[key] = _native.FrameBatch(frames, masks)
+        return fb
+
+    def _net_in(self, n: int):
         t = self.h.torch
+        dtype = t.float16 if self.detector._fmt == _native.OUT_F16_RGB_NCHW else t.float32
+        if self._net is None or self._net.shape[0] < n or self._net.dtype != dtype:
+            self._net = t.empty((max(n, len(self.streams)), 3, *self.detector.input_hw), dtype=dtype, device=self.h.device)
+        return self._net[:n]
+
+    # --------------------------------------------------------------------------------------
+    def tick(self, frames: Sequence, frame_ids: Optional[Sequence[int]] = None, infer_ctx=None) -> List[FrameResult]:
+        """``frames[i]`` is the new frame of ``streams[i]`` (host array, pinned CPU tensor or CUDA
+        tensor) or None when that stream delivered nothing this tick."""
+        ctx = self.submit(frames, frame_ids, infer_ctx)
+        return self.collect(ctx) if ctx is not None else []
+
+    def submit(self, frames: Sequence, frame_ids: Optional[Sequence[int]] = None, infer_ctx=None) -> Optional[_TickCtx]:
         live = [i for i, f in enumerate(frames) if f is not None]
         if not live:
-            return []
-        dev_frames = self.stager.upload([frames[i] for i in live])
+            return None
+        ctx = self._ctxs[self._turn]
+        self._turn = (self._turn + 1) % len(self._ctxs)
+        if ctx.busy:
+            raise RuntimeError("HotPathEngine: collect() the oldest tick before submitting another one")
+        if self.sequential and any(c.busy for c in self._ctxs):
+            raise RuntimeError("HotPathEngine: streams with motion_filter / adaptive_fps need collect() before the next submit()")
         names = [self.streams[i].name for i in live]
         states = [self.state[n] for n in names]
+        # frames that only feed the letterbox need just its tapped rows on the device
+        sparse_ok = [False] * len(frames)
+        for i, st in zip(live, states):
+            sparse_ok[i] = (not getattr(st.cfg, "motion_filter", False)
+                            and float(getattr(st.cfg, "downsample_ratio", 1.0)) >= 0.999)
+        staged = self.stager.upload(list(frames), sparse_for=self.detector.input_hw, sparse_ok=sparse_ok)
+        dev_frames = [staged[i] for i in live]
         for st in states:
             st.frame_index += 1
-        ids = [frame_ids[i] if frame_ids is not None else self.state[self.streams[i].name].frame_index for i in live]
+        ids = [frame_ids[i] if frame_ids is not None else st.frame_index for i, st in zip(live, states)]
 
         # 1-2. ROI (fused into the consumers) and downsample
-        masks, work, ratios = [], [], []
+        masks, ratios = [], []
         for st, f in zip(states, dev_frames):
             polys = getattr(st.cfg, "roi_polygons", None) or []
             masks.append(roi_mask(polys, f.shape[0], f.shape[1], self.h) if polys else None)
@@ -139,49 +258,42 @@ class HotPathEngine:
         skipped = [k for k in range(len(live)) if skip_reason[k] is not None]
         order = active + skipped  # skipped streams create no tracks, so id order is unaffected
         n_act = len(active)
-        dets = {k_: v[:len(order)] for k_, v in self._dets.items()}
+        nb = len(order)
+        dets = {k_: v[:nb] for k_, v in ctx.dets.items() if not k_.startswith("_")}
         if n_act:
-            tensor, metas = self.h.preprocess([work[k] for k in active], self.detector.input_hw, self.detector._fmt,
-                                              [work_masks[k] for k in active])
+            tensor, metas = self.h.preprocess(self._frame_batch([work[k] for k in active], [work_masks[k] for k in active]),
+                                              self.detector.input_hw, self.detector._fmt, out=self._net_in(n_act))
             head = self.detector._infer(tensor) if infer_ctx is None else self.detector._infer_fn(tensor, infer_ctx)
             head = self.detector._as_head(head)
             if head.dim() != 3 or head.shape[0] != n_act:
                 raise ValueError(f"infer returned {tuple(head.shape)} for a batch of {n_act}")
-            self.detector._run_post(head, metas, {k_: v[:n_act] for k_, v in self._dets.items()})
+            self.detector._run_post(head, metas, {k_: v[:n_act] for k_, v in dets.items()})
         scale = [1.0 / max(ratios[k], 1e-6) if ratios[k] < 0.999 else 1.0 for k in order]
-        out = {k_: v[:len(order)] for k_, v in self._tracks.items()}
+        out = {k_: v[:nb] for k_, v in ctx.tracks.items() if not k_.startswith("_")}
         self.tracker.update_batch([names[k] for k in order], dets,
-                                  det_scale=scale if any(ratios[k] < 0.999 for k in order) else None,
+                                  det_scale=scale if any(s != 1.0 for s in scale) else None,
                                   skip=[0] * n_act + [1] * len(skipped), out=out)
-        self.last_soa = (order, dets, out)
+        # 9. one device -> host copy per result table, into pinned memory
+        ctx.host_dets_t["_flat"].copy_(ctx.dets["_flat"], non_blocking=True)
+        ctx.host_tracks_t["_flat"].copy_(ctx.tracks["_flat"], non_blocking=True)
+        ctx.done.record()
+        ctx.busy = True
+        ctx.order, ctx.n_act, ctx.names, ctx.ids, ctx.states = order, n_act, names, ids, states
+        ctx.skip_reason, ctx.scale, ctx.live = skip_reason, scale, live
+        return ctx
 
-        # 9-13. read back the counts the adaptive state machine needs; build objects on request
-        host_tr = B200IouTracker.soa_to_host(out) if self.build_objects else \
-            {"count": out["count"].cpu().numpy()}
-        det_counts = dets["count"][:n_act].cpu().numpy() if n_act else np.zeros(0, np.int32)
-        host_det = None
-        if self.build_objects and n_act and int(det_counts.max()) > 0:
-            kmax = int(det_counts.max())
-            host_det = (dets["bbox_xyxy"][:n_act, :kmax].cpu().numpy(), dets["conf"][:n_act, :kmax].cpu().numpy(),
-                        dets["cls"][:n_act, :kmax].cpu().numpy())
-        results: List[Optional[FrameResult]] = [None] * len(live)
-        for pos, k in enumerate(order):
-            st = states[k]
-            processed = pos < n_act
+    def collect(self, ctx: _TickCtx) -> List[FrameResult]:
+        """Wait for a submitted tick; update the adaptive-FPS state (pipeline.py:197) and return
+        one FrameResult per live stream, in stream order."""
+        ctx.done.synchronize()
+        ctx.busy = False
+        det_counts = ctx.host_dets["count"]
+        trk_counts = ctx.host_tracks["count"]
+        results: List[Optional[FrameResult]] = [None] * len(ctx.order)
+        for pos, k in enumerate(ctx.order):
+            processed = pos < ctx.n_act
             n_det = int(det_counts[pos]) if processed else 0
-            n_trk = int(host_tr["count"][pos])
-            st.adjust(n_det, n_trk)
-            res = FrameResult(names[k], ids[k], processed, skip_reason[k])
-            if self.build_objects:
-                if processed and host_det is not None:
-                    sc = scale[pos]
-                    box, conf, cls = host_det
-                    res.detections = [Detection(names[k], ids[k], int(cls[pos, i]), float(conf[pos, i]),
-                                                tuple(float(v) * sc if sc != 1.0 else float(v) for v in box[pos, i]))
-                                      for i in range(n_det)]
-                res.tracks = B200IouTracker.tracks_from_soa(host_tr, pos)
-            else:
-                res.detections = n_det  # type: ignore[assignment]
-                res.tracks = n_trk  # type: ignore[assignment]
-            results[k] = res
-        return [r for r in results if r is not None]
+            n_trk = int(trk_counts[pos])
+            ctx.states[k].adjust(n_det, n_trk)
+            results[k] = FrameResult(ctx.names[k], ctx.ids[k], processed, ctx.skip_reason[k], n_det, n_trk, ctx, pos)
+        return results  # type: ignore[return-value]

@@ -49,41 +49,59 @@ def reset_handles() -> None:
 
 
 class FrameStager:
-    """Pinned host ring + device buffers for decoded frames (numpy HWC uint8 -> CUDA)."""
+    """Host -> device staging of decoded frames into persistent per-position device buffers.
+
+    Frame k of a call always lands in the same device tensor (per shape), so pointer-based argument
+    batches can be cached by the caller.  Host frames may be numpy arrays (pageable: the driver
+    stages them) or CPU torch tensors (pinned: truly asynchronous).  ``sparse_for=(h, w)`` uploads
+    only the rows a letterbox to that size reads -- valid when nothing else consumes the frame."""
 
     def __init__(self, handle: "_native.Handle"):
         self.h = handle
-        self._pinned: Dict[tuple, list] = {}
-        self._turn: Dict[tuple, int] = {}
+        self._dev: Dict[tuple, object] = {}
+        self._keep: List = []
+        self.bytes_moved = 0
 
-    def upload(self, frames: Sequence) -> List:
+    def device_buffer(self, k: int, shape):
+        t = self.h.torch
+        key = (k, tuple(shape))
+        buf = self._dev.get(key)
+        if buf is None:
+            buf = self._dev[key] = t.zeros(tuple(shape), dtype=t.uint8, device=self.h.device)
+        return buf
+
+    def upload(self, frames: Sequence, sparse_for=None, sparse_ok: Optional[Sequence[bool]] = None) -> List:
         """Return CUDA uint8 [H,W,3] tensors for ``frames``; CUDA tensors pass through untouched."""
         t = self.h.torch
-        out = []
-        slot_of: Dict[tuple, int] = {}
-        for f in frames:
-            if t.is_tensor(f):
-                if not f.is_cuda:
-                    f = f.to(self.h.device, non_blocking=True)
-                out.append(f)
+        out: List = [None] * len(frames)
+        groups = {False: ([], []), True: ([], [])}
+        keep = []
+        for k, f in enumerate(frames):
+            if f is None:
                 continue
-            a = np.asarray(f)
-            if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
-                raise ValueError("frames must be uint8 arrays of shape [H, W, 3]")
-            if not a.flags["C_CONTIGUOUS"]:
-                a = np.ascontiguousarray(a)
-            key = a.shape
-            k = slot_of.get(key, 0)
-            slot_of[key] = k + 1
-            ring = self._pinned.setdefault(key, [])
-            # two generations per slot so a frame still in flight is never overwritten
-            gen = self._turn.get(key, 0)
-            idx = 2 * k + gen
-            while len(ring) <= idx:
-                ring.append(t.empty(key, dtype=t.uint8, pin_memory=True))
-            pinned = ring[idx]
-            pinned.numpy()[...] = a
-            out.append(pinned.to(self.h.device, non_blocking=True))
-        for key in slot_of:
-            self._turn[key] = 1 - self._turn.get(key, 0)
+            if t.is_tensor(f) and f.is_cuda:
+                out[k] = f
+                continue
+            if t.is_tensor(f):
+                if f.dtype != t.uint8 or f.dim() != 3 or f.shape[2] != 3 or f.stride(2) != 1 or f.stride(1) != 3:
+                    raise ValueError("frames must be uint8 [H, W, 3] with packed pixels")
+                ptr, pitch, shape = f.data_ptr(), f.stride(0), tuple(f.shape)
+            else:
+                a = np.asarray(f)
+                if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+                    raise ValueError("frames must be uint8 arrays of shape [H, W, 3]")
+                if a.strides[2] != 1 or a.strides[1] != 3:
+                    a = np.ascontiguousarray(a)
+                ptr, pitch, shape = a.ctypes.data, a.strides[0], a.shape
+                f = a
+            keep.append(f)
+            dev = self.device_buffer(k, shape)
+            out[k] = dev
+            sparse = bool(sparse_for) and (sparse_ok is None or bool(sparse_ok[k]))
+            groups[sparse][0].append((ptr, pitch))
+            groups[sparse][1].append(dev)
+        for sparse, (ptrs, devs) in groups.items():
+            if devs:
+                self.bytes_moved += self.h.upload_frames(ptrs, devs, sparse_for if sparse else None)
+        self._keep = keep  # sources stay alive until the caller synchronises (end of the tick)
         return out

@@ -51,6 +51,15 @@ class B200IouTracker:
                       int(out["hits"][index, i])) for i in range(n)]
 
     @staticmethod
+    def tracks_from_soa_all(host) -> List[List[Track]]:
+        """All rows of a host SoA -> lists of Track objects (vectorised conversions)."""
+        counts = host["count"].tolist()
+        ids, cls, conf = host["track_id"].tolist(), host["cls"].tolist(), host["conf"].tolist()
+        box, age, hits = host["bbox_xyxy"].tolist(), host["age"].tolist(), host["hits"].tolist()
+        return [[Track(ids[b][i], cls[b][i], conf[b][i], tuple(box[b][i]), age[b][i], hits[b][i]) for i in range(n)]
+                for b, n in enumerate(counts)]
+
+    @staticmethod
     def soa_to_host(out, kmax: Optional[int] = None):
         """Device SoA -> dict of numpy arrays (one synchronising copy per field)."""
         counts = out["count"].cpu().numpy()

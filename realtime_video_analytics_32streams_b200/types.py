@@ -91,15 +91,3 @@ class MotionFilterConfig:
     history: int = 5
     threshold: float = 0.02
     blur_kernel: Tuple[int, int] = (5, 5)
-
-
-@dataclass
-class FrameResult:
-    """What one stream produced in one tick of the batched driver."""
-
-    stream_name: str
-    frame_id: int
-    processed: bool
-    skip_reason: Optional[str] = None  # "motion" | "adaptive" | None
-    detections: List[Detection] = field(default_factory=list)
-    tracks: List[Track] = field(default_factory=list)

@@ -114,6 +114,34 @@ def test_preprocess_with_roi_mask_matches_apply_roi_then_preprocess(H):
         assert np.array_equal(out.cpu().numpy().view(np.uint8), ref.view(np.uint8))
 
 
+def test_sparse_row_upload_feeds_the_letterbox_exactly(H):
+    """Only the rows with a non-zero vertical weight cross PCIe; everything else in the device
+    frame is garbage and must never influence the output."""
+    import torch
+    from realtime_video_analytics_32streams_b200 import _native as N
+    from realtime_video_analytics_32streams_b200.runtime import FrameStager
+
+    shapes = [(1080, 1920), (2160, 3840), (720, 1280), (1083, 1921), (360, 640), (1920, 1080), (540, 960)]
+    frames = [synth.synth_frame(900 + i, h, w) for i, (h, w) in enumerate(shapes)]
+    st = FrameStager(H)
+    for k, f in enumerate(frames):  # poison the persistent buffers
+        st.device_buffer(k, f.shape).copy_(torch.randint(0, 256, f.shape, dtype=torch.uint8, device="cuda"))
+    before = st.bytes_moved
+    pinned = [torch.from_numpy(f).pin_memory() if k % 2 else f for k, f in enumerate(frames)]
+    dev = st.upload(pinned, sparse_for=(640, 640))
+    moved = st.bytes_moved - before
+    assert moved < sum(f.nbytes for f in frames) * 0.6  # 1080p: 1/3 of the rows, 4K: 1/3, 720p: all, ...
+    out, _ = H.preprocess(dev, (640, 640), N.OUT_F32_RGB_NCHW)
+    got = out.cpu().numpy()
+    for i, f in enumerate(frames):
+        ref, _ = O.preprocess(f, (640, 640), False)
+        assert np.array_equal(got[i].view(np.uint8), ref[0].view(np.uint8)), shapes[i]
+    # full upload is byte-identical to the source
+    dev = st.upload(frames)
+    for d, f in zip(dev, frames):
+        assert np.array_equal(d.cpu().numpy(), f)
+
+
 def test_downsample_matches_golden_and_oracle(H):
     from realtime_video_analytics_32streams_b200 import frame_filter as F
 
