@@ -285,6 +285,19 @@ def run_gpu(args) -> None:
     clocks.stop()
     launches = h.launch_count - launches0
     ms = start.elapsed_time(end)
+    # per-call device time (separate untimed loop, events around each C-ABI call)
+    bev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(20)]
+    for k, e in enumerate(bev):
+        e[0].record()
+        h.preprocess(batches[k % N_SETS], IN_HW, _native.OUT_F32_RGB_NCHW, out=net_in)
+        e[1].record()
+        h.postprocess(head_sets[k % N_SETS], metas, CONF, IOU, filter_conf=CONF, out=dets)
+        e[2].record()
+        h.tracker_update(slots, dets, TRK["max_age"], TRK["min_hits"], TRK["max_iou_distance"], out=tracks)
+        e[3].record()
+    torch.cuda.synchronize()
+    breakdown = {name: round(float(np.median([e[i].elapsed_time(e[i + 1]) for e in bev])), 4)
+                 for i, name in enumerate(("preprocess", "postprocess(decode+sort_nms)", "tracker_update"))}
     k1_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     n_tracks = int(tracks["count"].sum().item())
     h.poll_status()
@@ -385,6 +398,7 @@ def run_gpu(args) -> None:
                                "them on the device, see value_heads_resident_on_device); value_with_python_objects "
                                "additionally builds every Detection / Track object"},
                 "gpu_launches": int(launches), "launches_per_step": launches / max(args.steps, 1),
+                "breakdown_ms": breakdown,
                 "clocks": clocks.summary(), "tracks_alive": n_tracks}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_single_core_sample()

@@ -74,7 +74,7 @@ typedef struct b200va_config {
   int max_candidates; /* per-frame candidates surviving the confidence filter (<= 8192)          */
   int max_dets;       /* per-frame detections kept after NMS (output row capacity)               */
   int max_streams;    /* tracker stream slots (<= 4096)                                          */
-  int max_tracks;     /* live tracks per stream slot (<= 5600)                                   */
+  int max_tracks;     /* live tracks per stream slot (<= 4096)                                   */
 } b200va_config;
 
 /* Letterbox geometry, the `meta` dict of detector.py:259-263 plus the resized size. */

@@ -25,7 +25,7 @@ static int create_impl(b200va_ctx* h) {
   REQUIRE(h, c.max_candidates >= 1 && c.max_candidates <= 8192, "max_candidates must be in [1, 8192]");
   REQUIRE(h, c.max_dets >= 1 && c.max_dets <= c.max_candidates, "max_dets must be in [1, max_candidates]");
   REQUIRE(h, c.max_streams >= 1 && c.max_streams <= 4096, "max_streams must be in [1, 4096]");
-  REQUIRE(h, c.max_tracks >= 1 && c.max_tracks <= 5600, "max_tracks must be in [1, 5600]");
+  REQUIRE(h, c.max_tracks >= 1 && c.max_tracks <= 4096, "max_tracks must be in [1, 4096]");
   int ndev = 0;
   CUDA_TRY(h, cudaGetDeviceCount(&ndev));
   REQUIRE(h, c.device >= 0 && c.device < ndev, "device %d not present (%d visible)", c.device, ndev);
@@ -44,6 +44,8 @@ static int create_impl(b200va_ctx* h) {
   CUDA_TRY(h, cudaMalloc(&h->status_flags, FLAG_COUNT * sizeof(int32_t)));
   CUDA_TRY(h, cudaMemset(h->status_flags, 0, FLAG_COUNT * sizeof(int32_t)));
   CUDA_TRY(h, cudaMalloc(&h->roi_scratch, ROI_SCRATCH_BYTES));
+  CUDA_TRY(h, cudaMalloc(&h->dbg, DBG_SLOTS * sizeof(long long)));
+  CUDA_TRY(h, cudaMemset(h->dbg, 0, DBG_SLOTS * sizeof(long long)));
   int rc = tap_cache_create(h);
   if (rc) return rc;
   rc = preprocess_configure(h);
@@ -89,6 +91,7 @@ extern "C" int b200va_destroy(b200va_handle h) {
     if (h->cand_count) cudaFree(h->cand_count);
     if (h->status_flags) cudaFree(h->status_flags);
     if (h->roi_scratch) cudaFree(h->roi_scratch);
+    if (h->dbg) cudaFree(h->dbg);
   }
   delete h;
   return B200VA_OK;
@@ -113,5 +116,14 @@ extern "C" int b200va_poll_status(b200va_handle h, void* stream) {
                      flags[FLAG_DET_OVERFLOW] ? " detections>max_dets" : "",
                      flags[FLAG_TRACK_OVERFLOW] ? " tracks>max_tracks" : "");
   }
+  return B200VA_OK;
+}
+
+// Developer aid: SM-clock stamps written by builds compiled with -DB200VA_PHASE_TIMING (zeros otherwise).
+extern "C" B200VA_API int b200va_debug_read(b200va_handle h, int64_t* out, int n) {
+  if (!h || !out || n < 0 || n > DBG_SLOTS) return B200VA_ERR_INVALID;
+  DeviceGuard guard(h->cfg.device);
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  CUDA_TRY(h, cudaMemcpy(out, h->dbg, sizeof(long long) * n, cudaMemcpyDeviceToHost));
   return B200VA_OK;
 }

@@ -50,7 +50,21 @@ struct b200va_ctx {
   void* roi_scratch = nullptr;  // device, ROI_SCRATCH_BYTES
   // ---- tracker ----
   TrackerState* tracker = nullptr;
+  // ---- developer phase timing (only written by builds with -DB200VA_PHASE_TIMING) ----
+  long long* dbg = nullptr;  // device int64[DBG_SLOTS]
 };
+
+#define DBG_SLOTS 64
+#ifdef B200VA_PHASE_TIMING
+#define PHASE_STAMP(buf, slot)                                              \
+  do {                                                                      \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) (buf)[slot] = clock64(); \
+  } while (0)
+#else
+#define PHASE_STAMP(buf, slot) \
+  do {                         \
+  } while (0)
+#endif
 
 #define ROI_SCRATCH_BYTES (1 << 20)
 

@@ -76,17 +76,22 @@ __device__ __forceinline__ void emit_candidate(const PostParams& p, int frame, i
   p.cand_cls[o] = cls;
 }
 
-// channel-major head [B, C, A]: a thread owns VEC consecutive anchors and reads every channel row
-// with one 16-byte (VEC = 4) or 4-byte (VEC = 1) load; eight channel rows are in flight per thread.
+// channel-major head [B, C, A].  A thread owns VEC consecutive anchors (one 16-byte load per channel
+// row when VEC = 4) and walks the class rows in order; the next eight rows are already in flight
+// while the current eight are scored (software double buffering), so ~16 independent 16-byte loads
+// per thread keep HBM busy.
 template <int VEC>
-__global__ void __launch_bounds__(128) k_decode_cm(const __grid_constant__ PostParams p, int frame0) {
+__global__ void __launch_bounds__(64) k_decode_cm(const __grid_constant__ PostParams p, int frame0) {
   const int frame = blockIdx.y;
+  const int lane = threadIdx.x & 31;
   const int a0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   const float* __restrict__ hd = p.head + (size_t)(frame0 + frame) * p.C * p.A;
   const int A = p.A, C = p.C;
   float best[VEC];
   int cls[VEC];
-  unsigned pass = 0;  // bit k: anchor a0 + k is a candidate
+  unsigned pass = 0;      // bit k: anchor a0 + k is a candidate
+  unsigned nan_seen = 0;  // bit k: some score of anchor a0 + k is NaN (np.argmax then lands on a NaN,
+                          // whose confidence fails the >= filter: the anchor is never a candidate)
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
     best[k] = 0.f;
@@ -107,23 +112,42 @@ __global__ void __launch_bounds__(128) k_decode_cm(const __grid_constant__ PostP
       // scores = class_probs * objectness for both model types (detector.py:294-305)
       float first[VEC];
       load(5, first);
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) best[k] = __fmul_rn(first[k], obj[k]);
+      float cur[8][VEC], nxt[8][VEC];
       int c = 6;
-      for (; c + 8 <= C; c += 8) {
-        float v[8][VEC];
+      const bool have0 = c + 8 <= C;
+      if (have0) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) load(c + u, v[u]);
+        for (int u = 0; u < 8; ++u) load(c + u, cur[u]);
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        best[k] = __fmul_rn(first[k], obj[k]);
+        nan_seen |= (unsigned)(best[k] != best[k]) << k;
+      }
+      while (c + 8 <= C) {
+        const bool more = c + 16 <= C;
+        if (more) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) load(c + 8 + u, nxt[u]);
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
 #pragma unroll
           for (int k = 0; k < VEC; ++k) {
-            const float sc = __fmul_rn(v[u][k], obj[k]);
+            const float sc = __fmul_rn(cur[u][k], obj[k]);
+            nan_seen |= (unsigned)(sc != sc) << k;
             if (sc > best[k]) {  // np.argmax: first maximum wins
               best[k] = sc;
               cls[k] = c + u - 5;
             }
           }
+        c += 8;
+        if (more) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) cur[u][k] = nxt[u][k];
+        }
       }
       for (; c < C; ++c) {
         float v[VEC];
@@ -131,6 +155,7 @@ __global__ void __launch_bounds__(128) k_decode_cm(const __grid_constant__ PostP
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
           const float sc = __fmul_rn(v[k], obj[k]);
+          nan_seen |= (unsigned)(sc != sc) << k;
           if (sc > best[k]) {
             best[k] = sc;
             cls[k] = c - 5;
@@ -143,11 +168,10 @@ __global__ void __launch_bounds__(128) k_decode_cm(const __grid_constant__ PostP
     }
 #pragma unroll
     for (int k = 0; k < VEC; ++k)
-      if ((best[k] >= p.conf_thr) && class_allowed(p, cls[k])) pass |= 1u << k;
+      if (!((nan_seen >> k) & 1u) && (best[k] >= p.conf_thr) && class_allowed(p, cls[k])) pass |= 1u << k;
   }
   // warp-aggregated compaction: one atomic per warp
   const int mine = __popc(pass);
-  const int lane = threadIdx.x & 31;
   int incl = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -237,6 +261,7 @@ struct NmsParams {
   float iou_thr;
   double filter_thr;
   int use_filter;
+  long long* dbg;
 };
 
 // _iou of detector.py:469-481 in float32; returns true when box j must be suppressed by box i.
@@ -247,6 +272,8 @@ __device__ __forceinline__ bool suppresses(const float4 a, const float4 b, float
   const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
   const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
   const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  // disjoint boxes (the common case): 0 / max(union, 1e-6) is exactly +-0 for any finite union
+  if (inter == 0.f && fabsf(uni) <= 3.0e38f) return !(0.f <= thr);
   const float iou = __fdiv_rn(inter, fmaxf(uni, 1e-6f));
   return !(iou <= thr);
 }
@@ -257,6 +284,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int frame = blockIdx.x;
   const int tid = threadIdx.x;
+  PHASE_STAMP(p.dbg, 16);
   const int n_raw = p.cand_count[frame];
   const int n = min(n_raw, p.max_cand);
   int np2 = 64;
@@ -283,26 +311,69 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
   for (int i = tid; i < np2 / 32; i += kNmsThreads) supp[i] = 0u;
   __syncthreads();
 
-  // bitonic sort, descending
-  for (int k = 2; k <= np2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = tid; i < np2; i += kNmsThreads) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const unsigned long long a = keys[i], b = keys[ixj];
-          const bool desc = (i & k) == 0;
-          if (desc ? (a < b) : (a > b)) {
-            keys[i] = b;
-            keys[ixj] = a;
+  PHASE_STAMP(p.dbg, 17);
+  if (n <= 2048) {
+    // rank sort: keys are unique, so rank_i = #{j : key_j > key_i} is a permutation.  Every thread
+    // streams the whole key array from shared memory (broadcast reads) -- two barriers in total
+    // where a bitonic network needs one per round.
+    unsigned long long* sorted = reinterpret_cast<unsigned long long*>(box);  // box[] is not live yet
+    for (int i = tid; i < n; i += kNmsThreads) {
+      const unsigned long long ki = keys[i];
+      int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+      int j = 0;
+      for (; j + 4 <= n; j += 4) {
+        r0 += keys[j] > ki;
+        r1 += keys[j + 1] > ki;
+        r2 += keys[j + 2] > ki;
+        r3 += keys[j + 3] > ki;
+      }
+      for (; j < n; ++j) r0 += keys[j] > ki;
+      sorted[r0 + r1 + r2 + r3] = ki;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += kNmsThreads) keys[i] = sorted[i];
+    __syncthreads();
+  } else {
+    // bitonic sort, descending.  Only the warps that own a compare-exchange take part (named barrier 1).
+    const int sort_threads = min(kNmsThreads, max(32, np2 >> 1));
+    if (tid < sort_threads) {
+      for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int q = tid; q < (np2 >> 1); q += sort_threads) {
+            // q-th pair of this round: i has bit j clear
+            const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+            const int ixj = i | j;
+            const unsigned long long a = keys[i], b = keys[ixj];
+            const bool desc = (i & k) == 0;
+            if (desc ? (a < b) : (a > b)) {
+              keys[i] = b;
+              keys[ixj] = a;
+            }
           }
+          if (sort_threads == 32) __syncwarp();
+          else asm volatile("bar.sync 1, %0;" ::"r"(sort_threads) : "memory");
         }
       }
-      __syncthreads();
+    }
+    __syncthreads();
+  }
+  PHASE_STAMP(p.dbg, 18);
+  // gather boxes (to shared memory) and class ids (to registers) of the sorted candidates in one
+  // round of global loads; element i = tid + 1024 * k lives in slot k of the thread
+  int my_cls[8];  // max_candidates <= 8192
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = tid + k * kNmsThreads;
+    my_cls[k] = 0;
+    if (i < n) {
+      const size_t o = cbase + (keys[i] & 0x3fffull);
+      box[i] = p.cand_box[o];
+      my_cls[k] = p.cand_cls[o];
     }
   }
-  for (int i = tid; i < n; i += kNmsThreads) box[i] = p.cand_box[cbase + (keys[i] & 0x3fffull)];
   __syncthreads();
 
+  PHASE_STAMP(p.dbg, 19);
   const float thr = p.iou_thr;
   const int nchunks = (n + 63) >> 6;
   for (int ch = 0; ch < nchunks; ++ch) {
@@ -310,7 +381,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
     const int m = min(64, n - c0);
     if (tid < 128) rows[tid >> 1][tid & 1] = 0u;
     __syncthreads();
-    // (a) in-chunk IoU bits: thread -> row i = tid / 16, columns 4 * (tid % 16) ..
+    // (a) in-chunk IoU bits (the predicate is symmetric): thread -> row i = tid / 16, columns 4 * (tid % 16) ..
     {
       const int i = tid >> 4, jb = (tid & 15) << 2;
       if (i < m) {
@@ -319,25 +390,32 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = jb + q;
-          if (j > i && j < m && suppresses(bi, box[c0 + j], thr)) bits |= 1u << (j & 31);
+          if (j != i && j < m && suppresses(bi, box[c0 + j], thr)) bits |= 1u << (j & 31);
         }
         if (bits) atomicOr(&rows[i][jb >> 5], bits);
       }
     }
     __syncthreads();
-    // (b) one warp resolves the chunk sequentially; rows live in registers, two per lane
+    // (b) greedy resolution inside the chunk: kept_i = alive_i and no kept j < i suppresses i.  That
+    // recursion has a unique solution; iterating it from kept = alive fixes box i after at most i
+    // rounds, so one warp (two boxes per lane) repeats it until nothing changes -- a handful of
+    // ballots for typical clusters instead of 64 dependent steps.
     if (tid < 32) {
-      const unsigned long long r_lo = ((unsigned long long)rows[tid][1] << 32) | rows[tid][0];
-      const unsigned long long r_hi = ((unsigned long long)rows[tid + 32][1] << 32) | rows[tid + 32][0];
+      const unsigned long long lo_mask = (1ull << tid) - 1ull, hi_mask = (1ull << (tid + 32)) - 1ull;
+      const unsigned long long e0 = (((unsigned long long)rows[tid][1] << 32) | rows[tid][0]) & lo_mask;
+      const unsigned long long e1 = (((unsigned long long)rows[tid + 32][1] << 32) | rows[tid + 32][0]) & hi_mask;
       const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
-      unsigned long long alive = ~(((unsigned long long)supp[(c0 >> 5) + 1] << 32) | supp[c0 >> 5]) & valid;
-      unsigned long long kept = 0ull;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        const unsigned long long r = __shfl_sync(0xffffffffu, i < 32 ? r_lo : r_hi, i & 31);
-        const unsigned long long on = 0ull - ((alive >> i) & 1ull);
-        kept |= on & (1ull << i);
-        alive &= ~(r & on);
+      const unsigned long long alive = ~(((unsigned long long)supp[(c0 >> 5) + 1] << 32) | supp[c0 >> 5]) & valid;
+      const bool a0 = (alive >> tid) & 1ull, a1 = (alive >> (tid + 32)) & 1ull;
+      bool k0 = a0, k1 = a1;
+      unsigned long long kept;
+      while (true) {
+        kept = ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32) | __ballot_sync(0xffffffffu, k0);
+        const bool n0 = a0 && !(e0 & kept), n1 = a1 && !(e1 & kept);
+        const unsigned changed = __ballot_sync(0xffffffffu, n0 != k0 || n1 != k1);
+        k0 = n0;
+        k1 = n1;
+        if (!changed) break;
       }
       if (tid == 0) {
         keep_w[2 * ch] = (uint32_t)kept;
@@ -345,19 +423,28 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
       }
     }
     __syncthreads();
-    // (c) this chunk's survivors suppress every later box
+    // (c) this chunk's survivors suppress every later box.  g threads share one later box (each takes
+    // 64 / g of the chunk's columns); g shrinks as the tail grows so that all 1024 threads stay busy.
     const unsigned long long kept = ((unsigned long long)keep_w[2 * ch + 1] << 32) | keep_w[2 * ch];
-    if (kept) {
-      for (int j = c0 + 64 + tid; j < n; j += kNmsThreads) {
-        if ((supp[j >> 5] >> (j & 31)) & 1u) continue;
-        const float4 bj = box[j];
-        unsigned long long kk = kept;
-        while (kk) {
-          const int i = __ffsll((long long)kk) - 1;
-          kk &= kk - 1;
-          if (suppresses(box[c0 + i], bj, thr)) {
-            atomicOr(&supp[j >> 5], 1u << (j & 31));
-            break;
+    const int tail = n - (c0 + 64);
+    if (kept && tail > 0) {
+      int g = 16;
+      while (g > 1 && tail * g > kNmsThreads) g >>= 1;
+      const int cols = 64 / g;
+      const int part = tid & (g - 1);
+      const unsigned long long mine = (cols == 64 ? kept : (kept >> (part * cols)) & ((1ull << cols) - 1ull));
+      if (mine) {
+        for (int j = c0 + 64 + tid / g; j < n; j += kNmsThreads / g) {
+          if ((supp[j >> 5] >> (j & 31)) & 1u) continue;
+          const float4 bj = box[j];
+          unsigned long long kk = mine;
+          while (kk) {
+            const int i = __ffsll((long long)kk) - 1 + part * cols;
+            kk &= kk - 1;
+            if (suppresses(box[c0 + i], bj, thr)) {
+              atomicOr(&supp[j >> 5], 1u << (j & 31));
+              break;
+            }
           }
         }
       }
@@ -365,6 +452,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
     __syncthreads();
   }
 
+  PHASE_STAMP(p.dbg, 20);
   // filter_detections (detector.py:99-103): float64 compare on the kept boxes only
   if (p.use_filter) {
     for (int i = tid; i < n; i += kNmsThreads) {
@@ -386,7 +474,10 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
     if (acc > p.max_dets) atomicOr(p.flags + FLAG_DET_OVERFLOW, 1);
   }
   __syncthreads();
-  for (int i = tid; i < n; i += kNmsThreads) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = tid + k * kNmsThreads;
+    if (i >= n) break;
     const unsigned long long w = ((unsigned long long)keep_w[2 * (i >> 6) + 1] << 32) | keep_w[2 * (i >> 6)];
     if ((w >> (i & 63)) & 1ull) {
       const int pos = keep_off[i >> 6] + __popcll(w & ((1ull << (i & 63)) - 1ull));
@@ -395,10 +486,11 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
         const float4 b = box[i];
         reinterpret_cast<float4*>(p.out_box)[o] = b;
         p.out_conf[o] = unorder_bits((uint32_t)(keys[i] >> 32));
-        p.out_cls[o] = p.cand_cls[cbase + (keys[i] & 0x3fffull)];
+        p.out_cls[o] = my_cls[k];
       }
     }
   }
+  PHASE_STAMP(p.dbg, 21);
 }
 
 static int next_pow2(int v) {
@@ -471,11 +563,11 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
     if (layout == B200VA_HEAD_CHANNEL_MAJOR) {
       // 16-byte loads need every channel row (A floats) and the tensor base 16-byte aligned
       if (anchors % 4 == 0 && ((uintptr_t)head % 16 == 0)) {
-        dim3 grid((anchors / 4 + 127) / 128, n);
-        k_decode_cm<4><<<grid, 128, 0, st>>>(p, base);
+        dim3 grid((anchors / 4 + 63) / 64, n);
+        k_decode_cm<4><<<grid, 64, 0, st>>>(p, base);
       } else {
-        dim3 grid((anchors + 127) / 128, n);
-        k_decode_cm<1><<<grid, 128, 0, st>>>(p, base);
+        dim3 grid((anchors + 63) / 64, n);
+        k_decode_cm<1><<<grid, 64, 0, st>>>(p, base);
       }
     } else {
       dim3 grid((anchors + 7) / 8, n);
@@ -499,6 +591,7 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
     q.iou_thr = (float)iou_thr;  // detector.py:373 compares float32 IoUs with the weak Python scalar
     q.filter_thr = filter_conf_thr_f64;
     q.use_filter = use_filter;
+    q.dbg = h->dbg;
     k_sort_nms<<<n, kNmsThreads, nms_smem_bytes(h->cfg.max_candidates), st>>>(q);
     LAUNCH_CHECK(h);
   }

@@ -58,6 +58,7 @@ struct TrkParams {
   int32_t* o_count;
   int32_t* o_new;
   int32_t* flags;
+  long long* dbg;
 };
 
 constexpr int kTrkThreads = 256;
@@ -75,14 +76,24 @@ __device__ __forceinline__ double iou64(double ax1, double ay1, double ax2, doub
   return __ddiv_rn(inter, uni);
 }
 
-constexpr int kDetChunk = 256;   // detections staged in shared memory at a time
-constexpr int kWarpPathMax = 96;  // frames with at most this many tracks + detections run on one warp
+constexpr int kDetChunk = 128;  // detections staged in shared memory at a time
+constexpr int kCand = 6;        // candidate slots per detection and kind; more -> exact brute-force scan
 
 struct DetStage {
   double4 box[kDetChunk];
   double conf[kDetChunk];
   int cls[kDetChunk];
 };
+struct Cand {
+  double iou;
+  int idx;  // track index (c_trk) or chunk-local detection index (c_det)
+  int pad_;
+};
+
+// Boxes whose intersection is empty have IoU 0, which can never beat best_iou = 0.0 (tracker.py:100-106).
+__device__ __forceinline__ bool overlaps(const double4 a, const double4 b) {
+  return (a.z > b.x) & (b.z > a.x) & (a.z > a.x) & (b.z > b.x) & (a.w > b.y) & (b.w > a.y) & (a.w > a.y) & (b.w > b.y);
+}
 
 // Best track for one detection among tracks t = first, first + stride, ... (tracker.py:97-109).
 __device__ __forceinline__ void scan_tracks(const double* __restrict__ sbox, const int32_t* __restrict__ scls, int T,
@@ -93,8 +104,7 @@ __device__ __forceinline__ void scan_tracks(const double* __restrict__ sbox, con
   for (int t = first; t < T; t += stride) {
     if (scls[t] != dcls) continue;
     const double4 tb = reinterpret_cast<const double4*>(sbox)[t];
-    // boxes that do not overlap have IoU 0, which can never beat best_iou
-    if (!(fmin(tb.z, db.z) > fmax(tb.x, db.x)) || !(fmin(tb.w, db.w) > fmax(tb.y, db.y))) continue;
+    if (!overlaps(tb, db)) continue;
     const double v = iou64(tb.x, tb.y, tb.z, tb.w, db.x, db.y, db.z, db.w);
     if (v >= thr && v > best) {
       best = v;
@@ -115,17 +125,29 @@ __device__ __forceinline__ void warp_argmax(double& best, int& best_t) {
   }
 }
 
+// The matching is sequential in the reference, but every IoU it can ever ask for within one chunk of
+// detections is known up front: detection i against a track as it stood at the start of the chunk,
+// or against an earlier detection of the chunk (a matched or new track carries exactly that box).
+// Phase A computes those float64 IoUs with all threads and keeps, per detection, the few that pass
+// the threshold; phase B lets one warp walk the detections in order doing only look-ups:
+//   last_det[t] = detection (index in the frame) whose box track t holds now (-1: untouched this frame)
+//   holder[d]   = track currently holding chunk-local detection d's box (-1: none / overwritten since)
+// Nothing in the sequential part touches global memory: confidence, age and id of a touched track
+// are derived from last_det[] when the table is written back.
 __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__ TrkParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   double* sbox = reinterpret_cast<double*>(smem_raw);                            // [max_tracks][4]
   int32_t* scls = reinterpret_cast<int32_t*>(sbox + (size_t)p.max_tracks * 4);   // [max_tracks]
+  int32_t* shits = scls + p.max_tracks;                                          // [max_tracks]
+  int16_t* last_det = reinterpret_cast<int16_t*>(shits + p.max_tracks);          // [max_tracks]
   __shared__ DetStage sd;
-  __shared__ double red_iou[kTrkThreads / 32];
-  __shared__ int red_t[kTrkThreads / 32];
-  __shared__ int s_T, s_new, s_is_last, s_match;
+  __shared__ Cand c_trk[kDetChunk][kCand], c_det[kDetChunk][kCand];
+  __shared__ int n_trk[kDetChunk], n_det[kDetChunk], holder[kDetChunk];
+  __shared__ int s_T, s_new, s_is_last;
 
   const int bi = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  PHASE_STAMP(p.dbg, 0);
   const int slot = p.slots[bi];
   const TrackerState& S = p.st;
   const int cur = S.cur[slot];
@@ -136,14 +158,14 @@ __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__
   double* box_c = S.box[cur] + sb * 4;
   int32_t* age_c = S.age[cur] + sb;
   int32_t* hits_c = S.hits[cur] + sb;
-  uint8_t* touched = S.touched + sb;
   const int T0 = S.count[slot];
 
   for (int t = tid; t < T0; t += kTrkThreads) {
     const double4 b0 = reinterpret_cast<const double4*>(box_c)[t];
     reinterpret_cast<double4*>(sbox)[t] = b0;
     scls[t] = cls_c[t];
-    touched[t] = 0;
+    shits[t] = hits_c[t];
+    last_det[t] = -1;
   }
   if (tid == 0) {
     s_T = T0;
@@ -153,39 +175,11 @@ __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__
   const int D = p.skip[bi] ? 0 : min(p.d_count[bi], p.max_dets);
   const size_t db = (size_t)bi * p.max_dets;
   const double scale = p.det_scale[bi];
-  const bool warp_path = T0 + D <= kWarpPathMax;
 
-  // thread 0 / lane 0 applies the outcome of one detection (tracker.py:69-92)
-  auto apply = [&](int match, int T, const double4 bx, double dconf, int dcls) {
-    int t = match;
-    if (t == 0x7fffffff) {  // no match: new track, matchable at once
-      t = T;
-      if (t < p.max_tracks) {
-        const int ord = s_new;
-        id_c[t] = p.has_id_base ? p.id_base[bi] + ord : -(long long)(ord + 1);
-        cls_c[t] = dcls;
-        scls[t] = dcls;
-        hits_c[t] = 1;
-        s_new = ord + 1;
-        s_T = T + 1;
-      } else {
-        atomicOr(p.flags + FLAG_TRACK_OVERFLOW, 1);
-        t = -1;
-      }
-    } else {  // match: overwrite immediately
-      hits_c[t] += 1;
-    }
-    if (t >= 0) {
-      reinterpret_cast<double4*>(sbox)[t] = bx;
-      conf_c[t] = dconf;
-      age_c[t] = 0;
-      touched[t] = 1;
-    }
-  };
-
+  PHASE_STAMP(p.dbg, 1);
   for (int d0 = 0; d0 < D; d0 += kDetChunk) {
     const int nd = min(kDetChunk, D - d0);
-    __syncthreads();  // previous chunk fully consumed (and the track table staged, first time round)
+    if (d0) __syncthreads();  // previous chunk fully consumed
     for (int i = tid; i < nd; i += kTrkThreads) {
       const int d = d0 + i;
       double4 b;
@@ -207,69 +201,121 @@ __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__
       sd.box[i] = b;
       sd.conf[i] = cf;
       sd.cls[i] = p.d_cls[db + d];
+      n_trk[i] = 0;
+      n_det[i] = 0;
+      holder[i] = -1;
     }
     __syncthreads();
+    PHASE_STAMP(p.dbg, 2);
 
-    if (warp_path) {
-      // few tracks: one warp walks the detections with warp-level synchronisation only
-      if (warp == 0) {
-        for (int i = 0; i < nd; ++i) {
-          const double4 bx = sd.box[i];
-          const int dcls = sd.cls[i];
-          const int T = s_T;
-          double best;
-          int best_t;
-          scan_tracks(sbox, scls, T, lane, 32, bx, dcls, p.thr, best, best_t);
-          const unsigned cand = __ballot_sync(0xffffffffu, best_t != 0x7fffffff);
-          int match = 0x7fffffff;
-          if (cand) {
-            if (cand & (cand - 1)) {
-              warp_argmax(best, best_t);
-              match = best_t;
-            } else {
-              match = __shfl_sync(0xffffffffu, best_t, __ffs(cand) - 1);
-            }
-          }
-          if (lane == 0) apply(match, T, bx, sd.conf[i], dcls);
-          __syncwarp();
-        }
-      }
-    } else {
-      for (int i = 0; i < nd; ++i) {
+    // ---- phase A: every IoU the chunk can need, all threads ----
+    const int Tc = s_T;
+    {
+      const int i = tid & (kDetChunk - 1), half = tid >> 7;  // 256 threads: two per detection
+      if (i < nd) {
         const double4 bx = sd.box[i];
         const int dcls = sd.cls[i];
-        const int T = s_T;
-        double best;
-        int best_t;
-        scan_tracks(sbox, scls, T, tid, kTrkThreads, bx, dcls, p.thr, best, best_t);
-        const int ncand = __syncthreads_count(best_t != 0x7fffffff);
-        if (ncand == 1) {
-          if (best_t != 0x7fffffff) s_match = best_t;
-          __syncthreads();
-        } else if (ncand > 1) {
-          warp_argmax(best, best_t);
-          if (lane == 0) {
-            red_iou[warp] = best;
-            red_t[warp] = best_t;
-          }
-          __syncthreads();
-          if (tid == 0) {
-            double b = red_iou[0];
-            int bt = red_t[0];
-            for (int w = 1; w < kTrkThreads / 32; ++w)
-              if (red_iou[w] > b || (red_iou[w] == b && red_t[w] < bt)) {
-                b = red_iou[w];
-                bt = red_t[w];
-              }
-            s_match = bt;
+        for (int t = half; t < Tc; t += kTrkThreads / kDetChunk) {
+          if (scls[t] != dcls) continue;
+          const double4 tb = reinterpret_cast<const double4*>(sbox)[t];
+          if (!overlaps(tb, bx)) continue;
+          const double v = iou64(tb.x, tb.y, tb.z, tb.w, bx.x, bx.y, bx.z, bx.w);
+          if (v >= p.thr && v > 0.0) {
+            const int k = atomicAdd(&n_trk[i], 1);
+            if (k < kCand) {
+              c_trk[i][k].iou = v;
+              c_trk[i][k].idx = t;
+            }
           }
         }
-        if (tid == 0) apply(ncand == 0 ? 0x7fffffff : s_match, T, bx, sd.conf[i], dcls);
-        __syncthreads();
+        for (int e = half; e < i; e += kTrkThreads / kDetChunk) {
+          if (sd.cls[e] != dcls) continue;
+          const double4 eb = sd.box[e];
+          if (!overlaps(eb, bx)) continue;
+          const double v = iou64(eb.x, eb.y, eb.z, eb.w, bx.x, bx.y, bx.z, bx.w);
+          if (v >= p.thr && v > 0.0) {
+            const int k = atomicAdd(&n_det[i], 1);
+            if (k < kCand) {
+              c_det[i][k].iou = v;
+              c_det[i][k].idx = e;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    PHASE_STAMP(p.dbg, 7);
+
+    // ---- phase B: one warp, detections in order, look-ups only ----
+    if (warp == 0) {
+      for (int i = 0; i < nd; ++i) {
+#ifdef B200VA_PHASE_TIMING
+        if (i < 8) PHASE_STAMP(p.dbg, 8 + i);
+#endif
+        const int T = s_T;
+        const int nt = n_trk[i], ne = n_det[i];
+        const int dcls = sd.cls[i];
+        double best = 0.0;
+        int best_t = 0x7fffffff;
+        if (nt > kCand || ne > kCand) {
+          // crowded detection: exact scan of the live table (boxes in sbox are current)
+          scan_tracks(sbox, scls, T, lane, 32, sd.box[i], dcls, p.thr, best, best_t);
+        } else if (lane < nt) {
+          const Cand c = c_trk[i][lane];
+          if (last_det[c.idx] < d0) {  // not re-boxed by a detection of this chunk
+            best = c.iou;
+            best_t = c.idx;
+          }
+        } else if (lane >= kCand && lane - kCand < ne) {
+          const Cand c = c_det[i][lane - kCand];
+          const int t = holder[c.idx];
+          if (t >= 0) {
+            best = c.iou;
+            best_t = t;
+          }
+        }
+        const unsigned cand = __ballot_sync(0xffffffffu, best_t != 0x7fffffff);
+        int match = 0x7fffffff;
+        if (cand) {
+          if (cand & (cand - 1)) {
+            warp_argmax(best, best_t);
+            match = best_t;
+          } else {
+            match = __shfl_sync(0xffffffffu, best_t, __ffs(cand) - 1);
+          }
+        }
+        if (lane == 0) {
+          // tracker.py:69-92
+          int t = match;
+          if (t == 0x7fffffff) {  // no match: new track, matchable at once
+            t = T;
+            if (t < p.max_tracks) {
+              scls[t] = dcls;
+              shits[t] = 1;
+              last_det[t] = -1;
+              s_new = s_new + 1;
+              s_T = T + 1;
+            } else {
+              atomicOr(p.flags + FLAG_TRACK_OVERFLOW, 1);
+              t = -1;
+            }
+          } else {  // match: overwrite immediately
+            shits[t] += 1;
+          }
+          if (t >= 0) {
+            const int prev = last_det[t];
+            if (prev >= d0) holder[prev - d0] = -1;
+            last_det[t] = (int16_t)(d0 + i);
+            holder[i] = t;
+            reinterpret_cast<double4*>(sbox)[t] = sd.box[i];
+          }
+        }
+        __syncwarp();
       }
     }
   }
   __syncthreads();
+  PHASE_STAMP(p.dbg, 3);
 
   // ---- prune + stable compaction into the other buffer (tracker.py:111-126) ----
   const int T = s_T;
@@ -289,13 +335,14 @@ __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__
     const int t = t0 + tid;
     bool keep = false;
     int age = 0, hits = 0;
+    int ld = -1;
     if (t < T) {
-      age = age_c[t];
-      hits = hits_c[t];
-      if (touched[t]) {
+      ld = last_det[t];
+      hits = shits[t];
+      if (ld >= 0) {  // matched or created this frame: age = 0 (tracker.py:85)
         keep = true;
       } else {
-        age += 1;
+        age = age_c[t] + 1;
         keep = !(age > p.max_age || hits < p.min_hits);
       }
     }
@@ -306,8 +353,13 @@ __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__
     for (int w = 0; w < warp; ++w) off += warp_cnt[w];
     if (keep) {
       const int dst = off + __popc(bal & ((1u << lane) - 1u));
-      const long long idv = id_c[t];
-      const double cf = conf_c[t];
+      // tracks appended this frame sit at t >= T0 in creation order: provisional id = -(ordinal + 1)
+      const long long idv = t < T0 ? id_c[t]
+                                   : (p.has_id_base ? p.id_base[bi] + (t - T0) : -(long long)(t - T0 + 1));
+      double cf;
+      if (ld < 0) cf = conf_c[t];
+      else if (p.f_box) cf = (double)p.f_conf[db + ld];
+      else cf = p.d_conf[db + ld];
       const double4 b = reinterpret_cast<const double4*>(sbox)[t];
       id_n[dst] = idv;
       cls_n[dst] = scls[t];
@@ -341,39 +393,57 @@ __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__
   }
 
   // ---- shared id counter: last CTA converts provisional ordinals to ids in batch order ----
+  PHASE_STAMP(p.dbg, 4);
   if (p.has_id_base) return;
   __threadfence();
   __syncthreads();
+  PHASE_STAMP(p.dbg, 5);
   if (tid == 0) {
     const unsigned tk = atomicAdd(S.ticket, 1u);
     s_is_last = (tk == (unsigned)p.batch - 1u);
   }
   __syncthreads();
+  PHASE_STAMP(p.dbg, 6);
   if (!s_is_last) return;
   __threadfence();
-  long long next = *S.next_id;
-  for (int i = 0; i < p.batch; ++i) {
-    const int sl = p.slots[i];
-    const int nnew = ((volatile int32_t*)S.new_count)[i];
-    if (nnew > 0) {
-      const int c = ((volatile int32_t*)S.cur)[sl];
-      const int cnt = ((volatile int32_t*)S.count)[sl];
-      long long* ids = S.id[c] + (size_t)sl * p.max_tracks;
-      for (int t = tid; t < cnt; t += kTrkThreads) {
-        const long long v = ((volatile long long*)ids)[t];
-        if (v < 0) {
-          const long long real = next + (-v - 1);
-          ids[t] = real;
-          if (p.o_id) p.o_id[(size_t)i * p.max_tracks + t] = real;
-        }
-      }
-    }
-    next += nnew;
+  // every stream's new-track count, buffer index and length are fetched in parallel (one thread
+  // per stream), prefix-summed in batch order, then only streams that created tracks are patched
+  __shared__ int f_new[B200VA_MAX_BATCH], f_cur[B200VA_MAX_BATCH], f_cnt[B200VA_MAX_BATCH], f_pre[B200VA_MAX_BATCH];
+  __shared__ long long f_next;
+  if (tid < p.batch) {
+    const int sl = p.slots[tid];
+    f_new[tid] = ((volatile int32_t*)S.new_count)[tid];
+    f_cur[tid] = ((volatile int32_t*)S.cur)[sl];
+    f_cnt[tid] = ((volatile int32_t*)S.count)[sl];
   }
+  if (tid == kTrkThreads - 1) f_next = *((volatile long long*)S.next_id);
   __syncthreads();
   if (tid == 0) {
-    *S.next_id = next;
+    int acc = 0;
+    for (int i = 0; i < p.batch; ++i) {
+      f_pre[i] = acc;
+      acc += f_new[i];
+    }
+    *S.next_id = f_next + acc;
     *S.ticket = 0u;
+  }
+  __syncthreads();
+  const long long next = f_next;
+  // a warp per stream: new tracks sit at the tail of the table (creation order)
+  for (int i = warp; i < p.batch; i += kTrkThreads / 32) {
+    const int nnew = f_new[i];
+    if (nnew == 0) continue;
+    const int sl = p.slots[i];
+    long long* ids = S.id[f_cur[i]] + (size_t)sl * p.max_tracks;
+    const int cnt = f_cnt[i];
+    for (int t = lane; t < cnt; t += 32) {
+      const long long v = ((volatile long long*)ids)[t];
+      if (v < 0) {
+        const long long real = next + f_pre[i] + (-v - 1);
+        ids[t] = real;
+        if (p.o_id) p.o_id[(size_t)i * p.max_tracks + t] = real;
+      }
+    }
   }
 }
 
@@ -429,8 +499,8 @@ int tracker_state_create(b200va_ctx* h) {
   S->new_count = (int32_t*)(b + o_new);
   const long long one = 1;  // itertools.count(1), tracker.py:47
   CUDA_TRY(h, cudaMemcpy(S->next_id, &one, 8, cudaMemcpyHostToDevice));
-  const size_t smem = (size_t)h->cfg.max_tracks * 36;
-  if (smem > 200 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_tracks %d too large (<= 5600)", h->cfg.max_tracks);
+  const size_t smem = (size_t)h->cfg.max_tracks * 42 + 16;
+  if (smem > 176 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_tracks %d too large (<= 4096)", h->cfg.max_tracks);
   CUDA_TRY(h, cudaFuncSetAttribute(k_tracker, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return B200VA_OK;
 }
@@ -481,7 +551,8 @@ static int tracker_launch(b200va_ctx* h, TrkParams& p, const int* stream_slots, 
   }
   p.o_new = new_counts;
   p.flags = h->status_flags;
-  k_tracker<<<batch, kTrkThreads, (size_t)h->cfg.max_tracks * 36, st>>>(p);
+  p.dbg = h->dbg;
+  k_tracker<<<batch, kTrkThreads, (size_t)h->cfg.max_tracks * 42 + 16, st>>>(p);
   LAUNCH_CHECK(h);
   return B200VA_OK;
 }

@@ -1,0 +1,41 @@
+"""Phase timing of the latency-bound kernels (needs lib/libb200va_timing.so: make -C csrc TIMING=1)."""
+import ctypes as C, os, sys
+os.environ["B200VA_LIB"] = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                        "realtime_video_analytics_32streams_b200", "lib", "libb200va_timing.so")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench as B
+from realtime_video_analytics_32streams_b200 import _native
+h = _native.Handle(device=0, max_batch=32, max_anchors=B.A, max_candidates=2048, max_dets=512, max_streams=64, max_tracks=1024)
+heads = torch.from_numpy(np.stack([B.make_heads(s, 2) for s in range(32)], axis=1)).cuda()
+metas = (_native.Letterbox * 32)(*[_native.letterbox_meta(B.H, B.W, 640, 640) for _ in range(32)])
+dets, tracks = h.alloc_dets(32), h.alloc_tracks(32)
+for k in range(6):
+    h.postprocess(heads[k % 2], metas, B.CONF, B.IOU, filter_conf=B.CONF, out=dets)
+    h.tracker_update(list(range(32)), dets, 30, 1, 0.5, out=tracks)
+buf = (C.c_int64 * 64)()
+h.lib.b200va_debug_read.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
+h.lib.b200va_debug_read(h._h, buf, 64)
+v = list(buf)
+print("tracker phases (SM cycles, block 0): start->staged-issue %d, ->dets staged %d, ->match loop done %d, ->prune done %d, ->fence+sync %d, ->ticket %d" %
+      tuple(v[i + 1] - v[i] for i in range(6)))
+print("tracker: phase A %d, phase B %d; first iterations of B: %s" % (v[7] - v[2], v[3] - v[7], [v[9 + i] - v[8 + i] for i in range(7)]))
+print("nms phases: count+keys %d, sort %d, gather %d, chunks %d, filter+emit %d" % tuple(v[16 + i + 1] - v[16 + i] for i in range(5)))
+print("dets per frame", dets["count"].cpu().tolist()[:8], "tracks", tracks["count"].cpu().tolist()[:8])
+
+# hypothesis check: does a low-occupancy grid (32 CTAs) run slower per instruction than when the rest of the chip is busy?
+side = torch.cuda.Stream()
+a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+for busy in (False, True):
+    torch.cuda.synchronize()
+    if busy:
+        with torch.cuda.stream(side):
+            for _ in range(40):
+                a @ a
+    for k in range(4):
+        h.postprocess(heads[k % 2], metas, B.CONF, B.IOU, filter_conf=B.CONF, out=dets)
+        h.tracker_update(list(range(32)), dets, 30, 1, 0.5, out=tracks)
+    h.lib.b200va_debug_read(h._h, buf, 64)
+    v = list(buf)
+    print("busy" if busy else "idle", "tracker A %d B %d  per-iter %s | nms sort %d chunks %d" %
+          (v[7] - v[2], v[3] - v[7], [v[9 + i] - v[8 + i] for i in range(3)], v[18] - v[17], v[20] - v[19]))
