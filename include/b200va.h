@@ -63,7 +63,14 @@ enum b200va_head_layout {
 
 /* Scoring rule.  REF_COMPAT is what detector.py:294-307 computes for BOTH model types:
  * C>5: score_k = head[5+k] * head[4];  C==5: score_0 = head[4]. */
-enum b200va_score_mode { B200VA_SCORE_REF_COMPAT = 0 };
+enum b200va_score_mode {
+  B200VA_SCORE_REF_COMPAT = 0, /* the reference's rule, bit-exact with detector.py:294-310                    */
+  B200VA_SCORE_V8_NATIVE = 1   /* score_k = head[4+k]: what a YOLOv8 [84, A] export holds (additive mode)     */
+};
+
+/* NMS flavour.  The reference's _nms (detector.py:361-375) is class-agnostic; CLASS_AWARE is the
+ * additive mode named by the north star: a kept box suppresses only boxes of its own class. */
+enum b200va_nms_mode { B200VA_NMS_AGNOSTIC = 0, B200VA_NMS_CLASS_AWARE = 1 };
 
 typedef struct b200va_ctx* b200va_handle;
 
@@ -215,8 +222,19 @@ B200VA_API int b200va_motion(b200va_handle h, const uint8_t* const* frames, cons
  * Equal scores are ordered higher-candidate-index first (stable argsort reversed). */
 B200VA_API int b200va_postprocess(b200va_handle h, const float* head, int layout, int batch, int channels, int anchors,
                        const b200va_letterbox* meta, double conf_thr, double iou_thr, const int32_t* classes,
-                       int n_classes, int score_mode, double filter_conf_thr_f64, int use_filter,
+                       int n_classes, int score_mode, int nms_mode, double filter_conf_thr_f64, int use_filter,
                        const b200va_dets* out, void* stream);
+
+/* ---- a14: DFL decode of a raw YOLOv8 Detect head --------------------------------------
+ * Not part of /root/reference (its _postprocess consumes decoded tensors); restates the published
+ * Ultralytics Detect decode so that a raw export can feed b200va_postprocess.  raw DEVICE float32
+ * [batch, 4*reg_max + num_classes, A]; level_hw HOST [n_levels][2] grid sizes (80x80, 40x40, 20x20 at
+ * 640x640), level_stride HOST [n_levels] (8, 16, 32); out DEVICE float32 [batch, 4 + num_classes, A]
+ * with A = sum(h*w): rows 0-3 = (cx, cy, w, h) in input pixels, rows 4.. = sigmoid(class logits).
+ * Floating point (exp): matches a float32 reference within 1e-5 relative; not bit-exact. */
+B200VA_API int b200va_dfl_decode(b200va_handle h, const float* raw, int batch, int num_classes, int reg_max,
+                                 const int* level_hw, const float* level_stride, int n_levels, float* out,
+                                 void* stream);
 
 /* ---- a8: IoU tracker -----------------------------------------------------------------
  * Replaces IouTracker.update (tracker.py:50-95), _match_detection (:97-109), _prune_tracks

@@ -140,9 +140,12 @@ def nms_order(scores: np.ndarray) -> np.ndarray:
     return np.argsort(scores, kind="stable")[::-1]
 
 
-def nms(boxes: np.ndarray, scores: np.ndarray, iou_threshold: float) -> List[int]:
+def nms(boxes: np.ndarray, scores: np.ndarray, iou_threshold: float, cls: Optional[np.ndarray] = None) -> List[int]:
     """Greedy class-agnostic NMS, detector.py:361-375: keep the best, drop every remaining
-    box whose IoU with it is ``> float32(iou_threshold)``."""
+    box whose IoU with it is ``> float32(iou_threshold)``.
+
+    ``cls`` (not a reference feature; the additive CLASS_AWARE mode of the C ABI): a kept box only
+    suppresses boxes of its own class."""
     n = len(boxes)
     if n == 0:
         return []
@@ -150,17 +153,21 @@ def nms(boxes: np.ndarray, scores: np.ndarray, iou_threshold: float) -> List[int
     sb = boxes[order]
     iou = pairwise_iou_f32(sb)
     thr = F32(iou_threshold)
+    hit = ~(iou <= thr)
+    if cls is not None:
+        sc = np.asarray(cls)[order]
+        hit &= sc[:, None] == sc[None, :]
     suppressed = np.zeros(n, dtype=bool)
     keep: List[int] = []
     for i in range(n):
         if suppressed[i]:
             continue
         keep.append(int(order[i]))
-        suppressed[i + 1:] |= ~(iou[i, i + 1:] <= thr)
+        suppressed[i + 1:] |= hit[i, i + 1:]
     return keep
 
 
-def decode_candidates(pred: np.ndarray, conf_thr: float, classes: Optional[Sequence[int]]):
+def decode_candidates(pred: np.ndarray, conf_thr: float, classes: Optional[Sequence[int]], v8_native: bool = False):
     """detector.py:278-317: layout fix-up, objectness x class score, argmax, filters.
 
     Returns (xywh[N,4] f32, conf[N] f32, cls[N] int64, anchor_index[N]) or None for the
@@ -178,7 +185,9 @@ def decode_candidates(pred: np.ndarray, conf_thr: float, classes: Optional[Seque
         return None
     pred = pred.astype(F32, copy=False)
     boxes = pred[:, :4]
-    if pred.shape[1] > 5:
+    if v8_native:  # additive V8_NATIVE mode of the C ABI (not the reference's rule)
+        scores = pred[:, 4:]
+    elif pred.shape[1] > 5:
         scores = pred[:, 5:] * pred[:, 4:5]  # both model types, :294-305
     else:
         scores = pred[:, 4:]
@@ -212,16 +221,17 @@ def scale_boxes(b: np.ndarray, meta: dict) -> np.ndarray:
 
 
 def postprocess(pred: np.ndarray, meta: dict, conf_thr: float, iou_thr: float,
-                classes: Optional[Sequence[int]] = None) -> List[Det]:
-    """``_TensorRTBaseDetector._postprocess`` (detector.py:266-338); output in keep order."""
-    cand = decode_candidates(pred, conf_thr, classes)
+                classes: Optional[Sequence[int]] = None, v8_native: bool = False, class_aware: bool = False) -> List[Det]:
+    """``_TensorRTBaseDetector._postprocess`` (detector.py:266-338); output in keep order.
+    ``v8_native`` / ``class_aware`` select the additive modes (both False = the reference)."""
+    cand = decode_candidates(pred, conf_thr, classes, v8_native)
     if cand is None:
         return []
     xywh, conf, cls, _ = cand
     if xywh.size == 0:
         return []
     boxes = scale_boxes(xywh2xyxy(xywh), meta)
-    keep = nms(boxes, conf, iou_thr)
+    keep = nms(boxes, conf, iou_thr, cls if class_aware else None)
     return [
         Det(int(cls[i]), float(conf[i]), (float(boxes[i, 0]), float(boxes[i, 1]), float(boxes[i, 2]), float(boxes[i, 3])))
         for i in keep

@@ -18,7 +18,8 @@ LIB_PATH = os.environ.get("B200VA_LIB") or os.path.join(PKG_DIR, "lib", "libb200
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
 OUT_F32_RGB_NCHW, OUT_F16_RGB_NCHW, OUT_U8_BGR_NCHW, OUT_U8_BGR_NHWC = 0, 1, 2, 3
 HEAD_CHANNEL_MAJOR, HEAD_ANCHOR_MAJOR = 0, 1
-SCORE_REF_COMPAT = 0
+SCORE_REF_COMPAT, SCORE_V8_NATIVE = 0, 1
+NMS_AGNOSTIC, NMS_CLASS_AWARE = 0, 1
 
 
 class B200VAError(RuntimeError):
@@ -63,7 +64,7 @@ EXPORTS = (
     "b200va_launch_count", "b200va_poll_status", "b200va_letterbox_meta", "b200va_preprocess",
     "b200va_resize_linear_u8", "b200va_roi_rasterize", "b200va_apply_mask", "b200va_motion",
     "b200va_postprocess", "b200va_tracker_update", "b200va_tracker_update_f64", "b200va_tracker_reset",
-    "b200va_tracker_set_next_id", "b200va_upload_frames",
+    "b200va_tracker_set_next_id", "b200va_upload_frames", "b200va_dfl_decode",
 )
 
 _lib = None
@@ -100,7 +101,7 @@ def load_library() -> C.CDLL:
     lib.b200va_motion.argtypes = [vp, C.POINTER(vp), ip, ip, i64p, C.c_int, C.POINTER(vp), C.POINTER(vp),
                                   C.POINTER(vp), ip, vp, vp]
     lib.b200va_postprocess.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Letterbox), C.c_double,
-                                       C.c_double, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_double, C.c_int,
+                                       C.c_double, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                        C.POINTER(Dets), vp]
     lib.b200va_tracker_update.argtypes = [vp, ip, C.c_int, C.POINTER(Dets), C.c_int, C.POINTER(C.c_double),
                                           C.POINTER(C.c_uint8), C.POINTER(TrackerCfg), i64p, C.POINTER(Tracks), vp, vp]
@@ -108,6 +109,7 @@ def load_library() -> C.CDLL:
                                               C.POINTER(TrackerCfg), i64p, C.POINTER(Tracks), vp, vp]
     lib.b200va_upload_frames.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip, ip, i64p, i64p, C.c_int, C.c_int,
                                          C.c_int, C.c_int, i64p, vp]
+    lib.b200va_dfl_decode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, ip, C.POINTER(C.c_float), C.c_int, vp, vp]
     lib.b200va_tracker_reset.argtypes = [vp, C.c_int, vp]
     lib.b200va_tracker_set_next_id.argtypes = [vp, C.c_int64, vp]
     for name in EXPORTS:
@@ -342,7 +344,8 @@ class Handle:
         return Dets(d["bbox_xyxy"].data_ptr(), d["conf"].data_ptr(), d["cls"].data_ptr(), d["count"].data_ptr())
 
     def postprocess(self, head, metas, conf_thr: float, iou_thr: float, classes=None, layout=None,
-                    filter_conf: Optional[float] = None, out=None):
+                    filter_conf: Optional[float] = None, out=None, score_mode: int = SCORE_REF_COMPAT,
+                    nms_mode: int = NMS_AGNOSTIC):
         """Decode + filter + NMS for ``head`` [B,C,A] (channel major) or [B,A,C] (anchor major)."""
         t = self.torch
         if not (head.is_cuda and head.dtype == t.float32 and head.dim() == 3 and head.is_contiguous()):
@@ -358,9 +361,27 @@ class Handle:
         ds = self._dets_struct(out)
         self._check(self.lib.b200va_postprocess(
             self._h, C.c_void_p(head.data_ptr()), layout, b, channels, anchors, marr, float(conf_thr), float(iou_thr),
-            cls_arr, len(classes) if classes else 0, SCORE_REF_COMPAT,
+            cls_arr, len(classes) if classes else 0, int(score_mode), int(nms_mode),
             float(filter_conf) if filter_conf is not None else 0.0, 1 if filter_conf is not None else 0,
             C.byref(ds), self._stream()))
+        return out
+
+    # -- a14 --------------------------------------------------------------------------------
+    def dfl_decode(self, raw, num_classes: int, reg_max: int = 16, levels=((80, 80), (40, 40), (20, 20)),
+                   strides=(8.0, 16.0, 32.0), out=None):
+        """Raw Detect head [B, 4*reg_max + nc, A] -> decoded [B, 4 + nc, A] (tolerance-level parity)."""
+        t = self.torch
+        b = raw.shape[0]
+        a = sum(h * w for h, w in levels)
+        if not (raw.is_cuda and raw.dtype == t.float32 and raw.is_contiguous()
+                and tuple(raw.shape) == (b, 4 * reg_max + num_classes, a)):
+            raise ValueError("raw must be a contiguous CUDA float32 tensor [B, 4*reg_max + nc, sum(h*w)]")
+        if out is None:
+            out = t.empty((b, 4 + num_classes, a), dtype=t.float32, device=self.device)
+        hw = _int_array([v for lv in levels for v in lv])
+        st = (C.c_float * len(strides))(*[float(s) for s in strides])
+        self._check(self.lib.b200va_dfl_decode(self._h, C.c_void_p(raw.data_ptr()), b, int(num_classes), int(reg_max),
+                                               hw, st, len(levels), C.c_void_p(out.data_ptr()), self._stream()))
         return out
 
     # -- a8 ---------------------------------------------------------------------------------

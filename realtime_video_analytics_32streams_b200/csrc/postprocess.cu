@@ -31,6 +31,8 @@ struct PostParams {
   int32_t* cand_cls;
   int32_t* cand_count;
   int C, A, max_cand, use_mask;
+  int cls0;     // first class channel: 5 (column 4 is objectness) or 4 (scores = pred[:, 4:])
+  int use_obj;  // multiply class scores by column 4
   float conf_thr;
 };
 static_assert(sizeof(PostParams) <= 4000, "kernel parameter block too large");
@@ -107,13 +109,19 @@ __global__ void __launch_bounds__(64) k_decode_cm(const __grid_constant__ PostPa
   };
   if (a0 < A) {
     float obj[VEC];
-    load(4, obj);
-    if (C > 5) {
-      // scores = class_probs * objectness for both model types (detector.py:294-305)
+    if (p.use_obj) {
+      load(4, obj);
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) obj[k] = 1.0f;  // x * 1.0f is exact: scores = pred[:, 4:]
+    }
+    const int cls0 = p.cls0;
+    {
+      // REF_COMPAT: scores = class_probs * objectness for both model types (detector.py:294-305)
       float first[VEC];
-      load(5, first);
+      load(cls0, first);
       float cur[8][VEC], nxt[8][VEC];
-      int c = 6;
+      int c = cls0 + 1;
       const bool have0 = c + 8 <= C;
       if (have0) {
 #pragma unroll
@@ -138,7 +146,7 @@ __global__ void __launch_bounds__(64) k_decode_cm(const __grid_constant__ PostPa
             nan_seen |= (unsigned)(sc != sc) << k;
             if (sc > best[k]) {  // np.argmax: first maximum wins
               best[k] = sc;
-              cls[k] = c + u - 5;
+              cls[k] = c + u - cls0;
             }
           }
         c += 8;
@@ -158,13 +166,10 @@ __global__ void __launch_bounds__(64) k_decode_cm(const __grid_constant__ PostPa
           nan_seen |= (unsigned)(sc != sc) << k;
           if (sc > best[k]) {
             best[k] = sc;
-            cls[k] = c - 5;
+            cls[k] = c - cls0;
           }
         }
       }
-    } else {
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) best[k] = obj[k];  // scores = predictions[:, 4:], detector.py:306-307
     }
 #pragma unroll
     for (int k = 0; k < VEC; ++k)
@@ -207,36 +212,33 @@ __global__ void __launch_bounds__(256) k_decode_am(const __grid_constant__ PostP
   if (a >= p.A) return;
   const int C = p.C;
   const float* __restrict__ row = p.head + ((size_t)(frame0 + frame) * p.A + a) * C;
-  const float obj = __ldg(row + 4);
-  float best;
-  int cls;
-  if (C > 5) {
-    best = -INFINITY;
-    cls = 0x7fffffff;
-    bool have = false;
-    for (int c = 5 + lane; c < C; c += 32) {
-      const float s = __fmul_rn(__ldg(row + c), obj);
-      if (!have || s > best) {
-        best = s;
-        cls = c - 5;
-        have = true;
-      }
+  const float obj = p.use_obj ? __ldg(row + 4) : 1.0f;
+  const int cls0 = p.cls0;
+  float best = -INFINITY;
+  int cls = 0x7fffffff;
+  bool have = false, bad = false;
+  for (int c = cls0 + lane; c < C; c += 32) {
+    const float s = __fmul_rn(__ldg(row + c), obj);
+    bad |= (s != s);
+    if (!have || s > best) {
+      best = s;
+      cls = c - cls0;
+      have = true;
     }
-    // NaN scores never pass the >= filter; order them below everything in the reduction
-    if (!(best == best)) best = -INFINITY;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oc = __shfl_xor_sync(0xffffffffu, cls, o);
-      if (ob > best || (ob == best && oc < cls)) {
-        best = ob;
-        cls = oc;
-      }
-    }
-  } else {
-    best = obj;
-    cls = 0;
   }
+  // a NaN score makes np.argmax land on it and the >= filter drop the anchor
+  bad = __any_sync(0xffffffffu, bad);
+  if (!(best == best)) best = -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, cls, o);
+    if (oc != 0x7fffffff && (cls == 0x7fffffff || ob > best || (ob == best && oc < cls))) {
+      best = ob;
+      cls = oc;
+    }
+  }
+  if (bad) return;
   if (lane == 0) {
     if ((best >= p.conf_thr) && class_allowed(p, cls)) {
       const int pos = atomicAdd(p.cand_count + frame, 1);
@@ -261,6 +263,7 @@ struct NmsParams {
   float iou_thr;
   double filter_thr;
   int use_filter;
+  int class_aware;  // 0: the reference's class-agnostic NMS (detector.py:361-375); 1: suppress same class only
   long long* dbg;
 };
 
@@ -295,6 +298,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
   uint32_t* supp = reinterpret_cast<uint32_t*>(smem_raw + (size_t)p.cap_pow2 * 24);         // [cap_pow2/32]
   uint32_t* keep_w = supp + p.cap_pow2 / 32;                                                // [cap_pow2/32]
   int* keep_off = reinterpret_cast<int*>(keep_w + p.cap_pow2 / 32);                         // [cap_pow2/64 + 1]
+  uint16_t* scl = reinterpret_cast<uint16_t*>(keep_off + p.cap_pow2 / 64 + 1);              // [cap_pow2] class ids (class-aware mode)
   __shared__ uint32_t rows[64][2];
 
   __syncthreads();
@@ -369,11 +373,13 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
       const size_t o = cbase + (keys[i] & 0x3fffull);
       box[i] = p.cand_box[o];
       my_cls[k] = p.cand_cls[o];
+      scl[i] = (uint16_t)my_cls[k];
     }
   }
   __syncthreads();
 
   PHASE_STAMP(p.dbg, 19);
+  const bool aware = p.class_aware != 0;
   const float thr = p.iou_thr;
   const int nchunks = (n + 63) >> 6;
   for (int ch = 0; ch < nchunks; ++ch) {
@@ -390,7 +396,8 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = jb + q;
-          if (j != i && j < m && suppresses(bi, box[c0 + j], thr)) bits |= 1u << (j & 31);
+          if (j != i && j < m && (!aware || scl[c0 + i] == scl[c0 + j]) && suppresses(bi, box[c0 + j], thr))
+            bits |= 1u << (j & 31);
         }
         if (bits) atomicOr(&rows[i][jb >> 5], bits);
       }
@@ -441,7 +448,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
           while (kk) {
             const int i = __ffsll((long long)kk) - 1 + part * cols;
             kk &= kk - 1;
-            if (suppresses(box[c0 + i], bj, thr)) {
+            if ((!aware || scl[c0 + i] == scl[j]) && suppresses(box[c0 + i], bj, thr)) {
               atomicOr(&supp[j >> 5], 1u << (j & 31));
               break;
             }
@@ -503,7 +510,7 @@ static int next_pow2(int v) {
 
 size_t nms_smem_bytes(int max_cand) {
   const size_t cap = (size_t)next_pow2(max_cand);
-  return cap * 24 + cap / 8 + cap / 8 + (cap / 64 + 1) * 4 + 64;  // keys, boxes, supp, keep_w, keep_off
+  return cap * 24 + cap / 8 + cap / 8 + (cap / 64 + 1) * 4 + cap * 2 + 64;  // keys, boxes, supp, keep_w, keep_off, classes
 }
 
 int postprocess_configure(b200va_ctx* h) {
@@ -515,8 +522,8 @@ int postprocess_configure(b200va_ctx* h) {
 
 extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout, int batch, int channels, int anchors,
                                   const b200va_letterbox* meta, double conf_thr, double iou_thr,
-                                  const int32_t* classes, int n_classes, int score_mode, double filter_conf_thr_f64,
-                                  int use_filter, const b200va_dets* out, void* stream) {
+                                  const int32_t* classes, int n_classes, int score_mode, int nms_mode,
+                                  double filter_conf_thr_f64, int use_filter, const b200va_dets* out, void* stream) {
   if (!h) return B200VA_ERR_INVALID;
   std::lock_guard<std::mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
@@ -524,7 +531,9 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
   REQUIRE(h, head && meta && out && out->bbox_xyxy && out->conf && out->cls && out->count, "NULL argument");
   REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
   REQUIRE(h, layout == B200VA_HEAD_CHANNEL_MAJOR || layout == B200VA_HEAD_ANCHOR_MAJOR, "unknown layout %d", layout);
-  REQUIRE(h, score_mode == B200VA_SCORE_REF_COMPAT, "unknown score mode %d", score_mode);
+  REQUIRE(h, score_mode == B200VA_SCORE_REF_COMPAT || score_mode == B200VA_SCORE_V8_NATIVE, "unknown score mode %d", score_mode);
+  REQUIRE(h, nms_mode == B200VA_NMS_AGNOSTIC || nms_mode == B200VA_NMS_CLASS_AWARE, "unknown nms mode %d", nms_mode);
+  REQUIRE(h, nms_mode == B200VA_NMS_AGNOSTIC || channels - 4 <= 65535, "class-aware NMS supports at most 65535 classes");
   REQUIRE(h, anchors >= 0 && anchors <= h->cfg.max_anchors, "anchors %d outside [0, %d]", anchors, h->cfg.max_anchors);
   // detector.py:285-287: fewer than 5 channels is "unexpected shape" -> no detections
   if (batch == 0) return B200VA_OK;
@@ -559,6 +568,10 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
     p.C = channels;
     p.A = anchors;
     p.max_cand = h->cfg.max_candidates;
+    // REF_COMPAT (detector.py:294-307): C > 5 -> class columns 5.. times column 4; C == 5 -> pred[:, 4:].
+    // V8_NATIVE: class columns 4.. as they are (what a YOLOv8 export actually contains).
+    p.use_obj = (score_mode == B200VA_SCORE_REF_COMPAT && channels > 5) ? 1 : 0;
+    p.cls0 = p.use_obj ? 5 : 4;
     p.conf_thr = (float)conf_thr;  // NEP-50 weak scalar: compared in float32 (detector.py:312)
     if (layout == B200VA_HEAD_CHANNEL_MAJOR) {
       // 16-byte loads need every channel row (A floats) and the tensor base 16-byte aligned
@@ -591,6 +604,7 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
     q.iou_thr = (float)iou_thr;  // detector.py:373 compares float32 IoUs with the weak Python scalar
     q.filter_thr = filter_conf_thr_f64;
     q.use_filter = use_filter;
+    q.class_aware = nms_mode == B200VA_NMS_CLASS_AWARE;
     q.dbg = h->dbg;
     k_sort_nms<<<n, kNmsThreads, nms_smem_bytes(h->cfg.max_candidates), st>>>(q);
     LAUNCH_CHECK(h);

@@ -366,6 +366,62 @@ def test_postprocess_filter_fold_and_edge_shapes(H):
     assert out["count"].cpu().tolist() == [0]
 
 
+def test_postprocess_additive_modes_class_aware_and_v8_native(H):
+    """Not reference behaviour (its NMS is class-agnostic, its scoring uses column 4 as objectness):
+    the two additive modes of the ABI against the oracle's statement of them."""
+    from realtime_video_analytics_32streams_b200 import _native as N
+
+    lb = N.letterbox_meta(1080, 1920, 640, 640)
+    meta = O.letterbox_meta(1080, 1920, 640, 640)
+    for seed, n_obj, dup, ncls in ((61, 40, 4, 3), (62, 300, 6, 10), (63, 25, 2, None)):
+        head = synth.synth_head(seed, 84, 8400, n_obj, dup=dup, n_obj_classes=ncls, jitter=3.0)
+        for v8, aware in ((False, True), (True, False), (True, True)):
+            thr = 0.35 if not v8 else 0.5
+            ref = O.postprocess(head[None], meta, thr, 0.5, v8_native=v8, class_aware=aware)
+            out = H.postprocess(cu(head[None]), [lb], thr, 0.5, score_mode=N.SCORE_V8_NATIVE if v8 else N.SCORE_REF_COMPAT,
+                                nms_mode=N.NMS_CLASS_AWARE if aware else N.NMS_AGNOSTIC)
+            n = int(out["count"].cpu()[0])
+            rc, rf, rb = G.dets_arrays(ref)
+            assert n == len(ref) and n > 0, (seed, v8, aware)
+            assert np.array_equal(out["cls"][0, :n].cpu().numpy(), rc)
+            assert np.array_equal(out["conf"][0, :n].cpu().numpy().astype(np.float64), rf)
+            assert np.array_equal(out["bbox_xyxy"][0, :n].cpu().numpy().astype(np.float64), rb)
+    # class-aware keeps more boxes than agnostic on overlapping objects of different classes
+    head = synth.synth_head(62, 84, 8400, 300, dup=6, n_obj_classes=10, jitter=3.0)
+    assert len(O.postprocess(head[None], meta, 0.35, 0.5, class_aware=True)) >= len(O.postprocess(head[None], meta, 0.35, 0.5))
+
+
+def test_dfl_decode_matches_float32_reference_within_tolerance(H):
+    """a14: tolerance-level parity (exp / softmax), oracle = published Ultralytics decode restated."""
+    import torch
+    from oracle import dfl as D
+
+    rng = np.random.default_rng(71)
+    for nc, levels, strides in ((80, ((80, 80), (40, 40), (20, 20)), (8.0, 16.0, 32.0)),
+                                (3, ((12, 20), (6, 10)), (8.0, 16.0))):
+        a = sum(h * w for h, w in levels)
+        raw = rng.normal(0, 2.5, size=(3, 64 + nc, a)).astype(np.float32)
+        got = H.dfl_decode(cu(raw), nc, 16, levels, strides).cpu().numpy()
+        ref = D.dfl_decode(raw, nc, 16, levels, strides)
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got[:, :4], ref[:, :4], rtol=1e-5, atol=2e-4)   # pixels, up to 640
+        np.testing.assert_allclose(got[:, 4:], ref[:, 4:], rtol=1e-5, atol=1e-6)   # probabilities
+        # second opinion: torch float32 softmax on the CPU
+        t = torch.from_numpy(raw[:, :64]).view(3, 4, 16, a).softmax(2)
+        dist = (t * torch.arange(16, dtype=torch.float32).view(1, 1, 16, 1)).sum(2).numpy()
+        anchors, st = D.make_anchors(levels, strides)
+        w = (anchors[0][None] + dist[:, 2]) - (anchors[0][None] - dist[:, 0])
+        np.testing.assert_allclose(got[:, 2], w * st[None], rtol=1e-5, atol=2e-4)
+    # decoded output feeds the post-processor unchanged
+    from realtime_video_analytics_32streams_b200 import _native as N
+
+    dec = H.dfl_decode(cu(raw), nc, 16, levels, strides)
+    out = H.postprocess(dec, [N.letterbox_meta(96, 160, 96, 160)] * 3, 0.25, 0.5, score_mode=N.SCORE_V8_NATIVE)
+    ref = [O.postprocess(D.dfl_decode(raw, nc, 16, levels, strides)[i][None], O.letterbox_meta(96, 160, 96, 160), 0.25, 0.5,
+                         v8_native=True) for i in range(3)]
+    assert out["count"].cpu().tolist() == [len(r) for r in ref]
+
+
 def test_postprocess_capacity_flag(H):
     from realtime_video_analytics_32streams_b200 import _native as N
 
