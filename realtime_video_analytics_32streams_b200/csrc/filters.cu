@@ -10,6 +10,8 @@
 //   BGR2GRAY   = (B*3735 + G*19235 + R*9798 + 16384) >> 15
 //   Gaussian   = separable [1 4 6 4 1], BORDER_REFLECT_101, one rounding (sum + 128) >> 8
 //   motion     = count(|new - prev| > 25); the new blurred gray always replaces the state.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -180,7 +182,9 @@ struct MotionFrame {
   const uint8_t* prev;
   uint8_t* next;
   long long pitch;
-  int h, w, has_prev, fast;
+  int h, w;
+  short has_prev, fast;
+  int out_idx;
 };
 struct MotionParams {
   MotionFrame f[B200VA_LAUNCH_FRAMES];
@@ -200,10 +204,31 @@ __device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) 
   return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
 }
 
-__global__ void __launch_bounds__(kMotionWarps * 32) k_motion(const __grid_constant__ MotionParams p, int frame0) {
+// gray of the pixel whose B, G, R bytes sit in the low three bytes of `px` (the 4th byte is ignored):
+// two 4-way byte dot products with the 15-bit coefficients split into high and low bytes.
+__device__ __forceinline__ uint32_t gray_dp4a(uint32_t px) {
+  const uint32_t lo = 151u | (35u << 8) | (70u << 16);  // 3735 = 14*256 + 151, 19235 = 75*256 + 35, 9798 = 38*256 + 70
+  const uint32_t hi = 14u | (75u << 8) | (38u << 16);
+  return (__dp4a(px, lo, 16384u) + (__dp4a(px, hi, 0u) << 8)) >> 15;
+}
+
+// One warp owns a 256-pixel strip (8 pixels per lane) and streams down its rows.  Per row: the BGR
+// bytes arrive through a 4-stage cp.async ring; gray values are packed two per register (u16 pairs);
+// the two halo pixels on either side come from the neighbouring lanes by shuffle; the horizontal and
+// vertical [1 4 6 4 1] passes run on the packed pairs (sums stay below 65536, no carry between
+// halves); five rows of horizontal sums live in registers (the row loop is unrolled by five so the
+// ring index is static).
+// BORDER_REFLECT_101 for indices at most n-1 outside [0, n): no division on the hot path
+__device__ __forceinline__ int reflect_near(int i, int n) {
+  if (n < 4) return reflect101(i, n);
+  i = i < 0 ? -i : i;
+  return i >= n ? 2 * n - 2 - i : i;
+}
+
+template <bool MASK>
+__global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_constant__ MotionParams p, int frame0) {
   __shared__ __align__(16) uint8_t s_raw[kMotionWarps][kStagesM][kRawBytes];
-  __shared__ __align__(16) uint8_t s_msk[kMotionWarps][kStagesM][kMaskBytes];
-  __shared__ __align__(16) uint8_t s_gray[kMotionWarps][4 + kStripPx + 12];
+  __shared__ __align__(16) uint8_t s_msk[MASK ? kMotionWarps : 1][kStagesM][kMaskBytes];
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int frame = blockIdx.y;
@@ -216,33 +241,37 @@ __global__ void __launch_bounds__(kMotionWarps * 32) k_motion(const __grid_const
   const int x0 = (task % strips) * kStripPx;
   const int yb = (task / strips) * p.rows_per_task;
   const int ye = min(H, yb + p.rows_per_task);
-  const bool has_mask = f.mask != nullptr;
   const bool fast = f.fast != 0;
   const int row_bytes = 3 * W;
+  const int mw = MASK ? warp : 0;
+  const uint8_t* const src = f.src;
+  const uint8_t* const mask = f.mask;
+  const long long pitch = f.pitch;
+  uint8_t* const raw_base = &s_raw[warp][0][0];
+  uint8_t* const msk_base = &s_msk[mw][0][0];
 
-  // raw[16 + 3*(x - x0) + c] holds channel c of pixel x; msk[16 + (x - x0)] its ROI flag
+  // per-lane copy plan of a row, fixed for the whole task: raw[16 + 3*(x - x0) + c] holds channel c
+  // of pixel x, msk[16 + (x - x0)] its ROI flag; chunks that fall outside the row are skipped
+  const int c0_off = 3 * x0 - 16 + 16 * lane, c1_off = c0_off + 512;
+  const bool c0_ok = fast && c0_off >= 0 && c0_off + 16 <= row_bytes;
+  const bool c1_ok = fast && lane + 32 < kRawBytes / 16 && c1_off >= 0 && c1_off + 16 <= row_bytes;
+  const int m_off = x0 - 16 + 16 * lane;
+  const bool m_ok = MASK && fast && lane < kMaskBytes / 16 && m_off >= 0 && m_off + 16 <= W;
+
   auto load_row = [&](int r, int stage) {
-    const int rr = reflect101(r, H);
-    const uint8_t* g = f.src + (long long)rr * f.pitch;
-    uint8_t* raw = s_raw[warp][stage];
-    uint8_t* msk = s_msk[warp][stage];
+    const int rr = reflect_near(r, H);
+    const uint8_t* g = src + (long long)rr * pitch;
+    uint8_t* raw = raw_base + stage * kRawBytes;
+    uint8_t* msk = msk_base + stage * kMaskBytes;
     if (fast) {
-      const int b0 = 3 * x0 - 16;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int c = lane + 32 * k;
-        const int off = b0 + 16 * c;
-        if (c < kRawBytes / 16 && off >= 0 && off + 16 <= row_bytes) cp_async16(raw + 16 * c, g + off);
-      }
-      if (has_mask) {
-        const int off = x0 - 16 + 16 * lane;
-        if (lane < kMaskBytes / 16 && off >= 0 && off + 16 <= W) cp_async16(msk + 16 * lane, f.mask + (size_t)rr * W + off);
-      }
+      if (c0_ok) cp_async16(raw + 16 * lane, g + c0_off);
+      if (c1_ok) cp_async16(raw + 16 * lane + 512, g + c1_off);
+      if (m_ok) cp_async16(msk + 16 * lane, mask + (size_t)rr * W + m_off);
     } else {
       const int lo = max(0, x0 - 2), hi = min(W, x0 + kStripPx + 2);
       for (int i = 3 * lo + lane; i < 3 * hi; i += 32) raw[16 + i - 3 * x0] = __ldg(g + i);
-      if (has_mask)
-        for (int i = lo + lane; i < hi; i += 32) msk[16 + i - x0] = __ldg(f.mask + (size_t)rr * W + i);
+      if (MASK)
+        for (int i = lo + lane; i < hi; i += 32) msk[16 + i - x0] = __ldg(mask + (size_t)rr * W + i);
     }
     cp_async_commit();
   };
@@ -254,132 +283,158 @@ __global__ void __launch_bounds__(kMotionWarps * 32) k_motion(const __grid_const
     else cp_async_commit();
   }
 
-  uint32_t ring[5][4];  // horizontal sums, 8 pixels as 4 packed u16 pairs; ring[4] is the newest row
+  uint32_t ring[5][4];  // horizontal sums of 5 consecutive rows, 8 pixels as 4 packed u16 pairs
 #pragma unroll
   for (int a = 0; a < 5; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) ring[a][b] = 0;
   int changed = 0;
-  uint8_t* gbuf = s_gray[warp];  // gbuf[2 + (x - x0)] = gray of pixel x, for x - x0 in [-2, 258)
   const int xl = x0 + 8 * lane;
+  const bool interior = xl + 8 <= W;  // all 8 pixels of the lane are real pixels
+  // how the strip's outer halo pixels are obtained: 0 = they are staged pixels, 1 = mirror of the
+  // lane's own pixels (image edge on a strip boundary), 2 = generic (reflect through the staged row)
+  const int left_kind = x0 == 0 ? (W >= 4 ? 1 : 2) : 0;
+  const int right_kind = x0 + kStripPx + 2 <= W ? 0 : ((x0 + kStripPx == W && W >= 4) ? 1 : 2);
+  const int lane_raw = 16 + 24 * lane, lane_msk = 16 + 8 * lane;
+  const size_t out_col = (size_t)xl;
+  const bool has_prev = f.has_prev != 0;
+  const uint8_t* const prev = f.prev;
+  uint8_t* const next = f.next;
 
-  for (int k = 0; k < nrows; ++k) {
-    const int stage = k % kStagesM;
-    if (k + kStagesM - 1 < nrows) load_row(r_first + k + kStagesM - 1, (k + kStagesM - 1) % kStagesM);
-    else cp_async_commit();
-    cp_async_wait<kStagesM - 1>();
-    __syncwarp();
-    const uint8_t* raw = s_raw[warp][stage];
-    const uint8_t* msk = s_msk[warp][stage];
+  // gray of an arbitrary pixel of the staged row (slow path: partial strips, tiny images)
+  auto gray_at = [&](const uint8_t* raw, const uint8_t* msk, int x) -> uint32_t {
+    const int xr = reflect101(x, W);
+    const uint8_t* px = raw + 16 + 3 * (xr - x0);
+    if (MASK && !msk[16 + xr - x0]) return 0u;
+    return gray_of(px[0], px[1], px[2]);
+  };
 
-    // gray of the lane's own 8 pixels
-    uint32_t g8[8];
-    if (xl + 8 <= W) {
-      const uint2* q = reinterpret_cast<const uint2*>(raw + 16 + 24 * lane);
-      const uint2 w0 = q[0], w1 = q[1], w2 = q[2];
-      const uint32_t wd[6] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y};
-      uint2 mk = make_uint2(0xffffffffu, 0xffffffffu);
-      if (has_mask) mk = *reinterpret_cast<const uint2*>(msk + 16 + 8 * lane);
+  for (int k0 = 0; k0 < nrows; k0 += 5) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint32_t ch[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int bidx = 3 * j + c;
-          ch[c] = (wd[bidx >> 2] >> (8 * (bidx & 3))) & 0xffu;
-        }
-        const uint32_t on = ((j < 4 ? mk.x : mk.y) >> (8 * (j & 3))) & 0xffu;
-        g8[j] = on ? gray_of(ch[0], ch[1], ch[2]) : 0u;  // masked pixels are black: gray 0
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int x = xl + j;
-        g8[j] = 0;
-        if (x < W + 2) {
-          const int xr = reflect101(x, W);
-          const uint8_t* px = raw + 16 + 3 * (xr - x0);
-          const bool on = !has_mask || msk[16 + xr - x0];
-          g8[j] = on ? gray_of(px[0], px[1], px[2]) : 0u;
-        }
-      }
-    }
-    {
-      const uint32_t lo = g8[0] | (g8[1] << 8) | (g8[2] << 16) | (g8[3] << 24);
-      const uint32_t hi = g8[4] | (g8[5] << 8) | (g8[6] << 16) | (g8[7] << 24);
-      // gbuf + 2 + 8*lane is only 2-byte aligned: write as four 16-bit halves
-      uint16_t* gp = reinterpret_cast<uint16_t*>(gbuf + 2 + 8 * lane);
-      gp[0] = (uint16_t)lo;
-      gp[1] = (uint16_t)(lo >> 16);
-      gp[2] = (uint16_t)hi;
-      gp[3] = (uint16_t)(hi >> 16);
-    }
-    if (lane < 4) {  // halo pixels x0-2, x0-1, x0+256, x0+257
-      const int x = lane < 2 ? x0 - 2 + lane : x0 + kStripPx + (lane - 2);
-      if (x < W + 2) {
-        const int xr = reflect101(x, W);
-        const uint8_t* px = raw + 16 + 3 * (xr - x0);
-        const bool on = !has_mask || msk[16 + xr - x0];
-        gbuf[2 + x - x0] = (uint8_t)(on ? gray_of(px[0], px[1], px[2]) : 0u);
-      }
-    }
-    __syncwarp();
-    // horizontal [1 4 6 4 1] over gbuf[8*lane .. 8*lane + 12)
-    {
-      const uint32_t* gw = reinterpret_cast<const uint32_t*>(gbuf + 8 * lane);
-      const uint32_t a = gw[0], b = gw[1], c = gw[2];
-      uint32_t t[12];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        t[j] = (a >> (8 * j)) & 0xffu;
-        t[4 + j] = (b >> (8 * j)) & 0xffu;
-        t[8 + j] = (c >> (8 * j)) & 0xffu;
-      }
-#pragma unroll
-      for (int a5 = 0; a5 < 4; ++a5)
-#pragma unroll
-        for (int b4 = 0; b4 < 4; ++b4) ring[a5][b4] = ring[a5 + 1][b4];
-#pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        const uint32_t h0 = t[j] + 4u * t[j + 1] + 6u * t[j + 2] + 4u * t[j + 3] + t[j + 4];
-        const uint32_t h1 = t[j + 1] + 4u * t[j + 2] + 6u * t[j + 3] + 4u * t[j + 4] + t[j + 5];
-        ring[4][j >> 1] = h0 | (h1 << 16);
-      }
-    }
-    __syncwarp();  // gbuf is rewritten by the next row
+    for (int u = 0; u < 5; ++u) {
+      const int k = k0 + u;
+      if (k >= nrows) break;
+      const int stage = k & (kStagesM - 1);
+      if (k + kStagesM - 1 < nrows) load_row(r_first + k + kStagesM - 1, (k + kStagesM - 1) & (kStagesM - 1));
+      else cp_async_commit();
+      cp_async_wait<kStagesM - 1>();
+      __syncwarp();
+      const uint8_t* raw = raw_base + stage * kRawBytes;
+      const uint8_t* msk = msk_base + stage * kMaskBytes;
 
-    const int y = r_first + k - 2;  // the output row whose five inputs are now in the ring
-    if (k >= 4 && y >= yb && y < ye) {
-      uint32_t out[2];
+      // ---- gray of the lane's 8 pixels, packed as pairs P[q] = g[2q] | g[2q+1] << 16 ----
+      uint32_t P[4];
+      if (interior) {
+        const uint2* q = reinterpret_cast<const uint2*>(raw + lane_raw);
+        const uint2 w0 = q[0], w1 = q[1], w2 = q[2];
+        uint32_t g8[8];
+        g8[0] = gray_dp4a(w0.x);
+        g8[1] = gray_dp4a(__funnelshift_r(w0.x, w0.y, 24));
+        g8[2] = gray_dp4a(__funnelshift_r(w0.y, w1.x, 16));
+        g8[3] = gray_dp4a(__funnelshift_r(w1.x, w1.y, 8));
+        g8[4] = gray_dp4a(w1.y);
+        g8[5] = gray_dp4a(__funnelshift_r(w1.y, w2.x, 24));
+        g8[6] = gray_dp4a(__funnelshift_r(w2.x, w2.y, 16));
+        g8[7] = gray_dp4a(w2.y >> 8);
+        if (MASK) {  // masked pixels are black (bitwise_and with the mask): gray 0
+          const uint2 mk = *reinterpret_cast<const uint2*>(msk + lane_msk);
 #pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        // packed u16 pairs: sums stay below 65536, no carry between halves
-        const uint32_t v0 = ring[0][2 * hlf] + 4u * ring[1][2 * hlf] + 6u * ring[2][2 * hlf] + 4u * ring[3][2 * hlf] +
-                            ring[4][2 * hlf] + 0x00800080u;
-        const uint32_t v1 = ring[0][2 * hlf + 1] + 4u * ring[1][2 * hlf + 1] + 6u * ring[2][2 * hlf + 1] +
-                            4u * ring[3][2 * hlf + 1] + ring[4][2 * hlf + 1] + 0x00800080u;
-        const uint32_t p0 = (v0 >> 8) & 0x00ff00ffu, p1 = (v1 >> 8) & 0x00ff00ffu;
-        out[hlf] = (p0 & 0xffu) | ((p0 >> 16) << 8) | ((p1 & 0xffu) << 16) | ((p1 >> 16) << 24);
-      }
-      const size_t o = (size_t)y * W + xl;
-      if (fast && xl + 8 <= W) {
-        if (f.has_prev) {
-          const uint2 pv = __ldg(reinterpret_cast<const uint2*>(f.prev + o));
-          const uint32_t d0 = __vcmpgtu4(__vabsdiffu4(out[0], pv.x), 0x19191919u);
-          const uint32_t d1 = __vcmpgtu4(__vabsdiffu4(out[1], pv.y), 0x19191919u);
-          changed += (__popc(d0) + __popc(d1)) >> 3;
+          for (int j = 0; j < 8; ++j)
+            if ((((j < 4 ? mk.x : mk.y) >> (8 * (j & 3))) & 0xffu) == 0u) g8[j] = 0u;
         }
-        *reinterpret_cast<uint2*>(f.next + o) = make_uint2(out[0], out[1]);
+#pragma unroll
+        for (int q2 = 0; q2 < 4; ++q2) P[q2] = g8[2 * q2] | (g8[2 * q2 + 1] << 16);
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (xl + j < W) {
-            const int nv = (out[j >> 2] >> (8 * (j & 3))) & 0xff;
-            if (f.has_prev) {
-              const int pv = f.prev[o + j];
-              changed += (abs(nv - pv) > 25) ? 1 : 0;
+        for (int q2 = 0; q2 < 4; ++q2) {
+          const int x = xl + 2 * q2;
+          const uint32_t a = x < W + 2 ? gray_at(raw, msk, x) : 0u;
+          const uint32_t b = x + 1 < W + 2 ? gray_at(raw, msk, x + 1) : 0u;
+          P[q2] = a | (b << 16);
+        }
+      }
+      // ---- halo pairs from the neighbouring lanes; the strip's outer halo from the staged row ----
+      uint32_t L = __shfl_up_sync(0xffffffffu, P[3], 1);    // pixels xl-2, xl-1
+      uint32_t R = __shfl_down_sync(0xffffffffu, P[0], 1);  // pixels xl+8, xl+9
+      if (lane == 0) {
+        if (left_kind == 0) {  // bytes 10..15 of the staged row: pixels x0-2 and x0-1
+          const uint32_t a = *reinterpret_cast<const uint32_t*>(raw + 8), b = *reinterpret_cast<const uint32_t*>(raw + 12);
+          uint32_t ga = gray_dp4a(__funnelshift_r(a, b, 16)), gb = gray_dp4a(b >> 8);
+          if (MASK) {
+            ga = msk[14] ? ga : 0u;
+            gb = msk[15] ? gb : 0u;
+          }
+          L = ga | (gb << 16);
+        } else if (left_kind == 1) {  // reflect: g[-2] = g[2], g[-1] = g[1]
+          L = (P[1] & 0xffffu) | (P[0] & 0xffff0000u);
+        } else {
+          L = gray_at(raw, msk, x0 - 2) | (gray_at(raw, msk, x0 - 1) << 16);
+        }
+      }
+      if (lane == 31) {
+        if (right_kind == 0) {  // bytes 784..789: pixels x0+256 and x0+257
+          const uint32_t a = *reinterpret_cast<const uint32_t*>(raw + 784), b = *reinterpret_cast<const uint32_t*>(raw + 788);
+          uint32_t ga = gray_dp4a(a), gb = gray_dp4a(__funnelshift_r(a, b, 24));
+          if (MASK) {
+            ga = msk[16 + kStripPx] ? ga : 0u;
+            gb = msk[17 + kStripPx] ? gb : 0u;
+          }
+          R = ga | (gb << 16);
+        } else if (right_kind == 1) {  // reflect: g[W] = g[W-2], g[W+1] = g[W-3]
+          R = (P[3] & 0xffffu) | (P[2] & 0xffff0000u);
+        } else {
+          const int x = x0 + kStripPx;
+          R = (x < W + 2 ? gray_at(raw, msk, x) : 0u) | ((x + 1 < W + 2 ? gray_at(raw, msk, x + 1) : 0u) << 16);
+        }
+      }
+      // ---- horizontal [1 4 6 4 1] on pairs: h_k = P[k-1] + P[k+1] + 4 (Q[k-1] + Q[k]) + 6 P[k], Q[k] = (g[2k+1], g[2k+2]) ----
+      {
+        const uint32_t Qm = __funnelshift_r(L, P[0], 16), Q0 = __funnelshift_r(P[0], P[1], 16),
+                       Q1 = __funnelshift_r(P[1], P[2], 16), Q2 = __funnelshift_r(P[2], P[3], 16),
+                       Q3 = __funnelshift_r(P[3], R, 16);
+        ring[u][0] = L + P[1] + 4u * (Qm + Q0) + 6u * P[0];
+        ring[u][1] = P[0] + P[2] + 4u * (Q0 + Q1) + 6u * P[1];
+        ring[u][2] = P[1] + P[3] + 4u * (Q1 + Q2) + 6u * P[2];
+        ring[u][3] = P[2] + R + 4u * (Q2 + Q3) + 6u * P[3];
+      }
+      __syncwarp();  // every lane is done with this stage before a later iteration refills it
+
+      const int y = r_first + k - 2;  // the output row whose five inputs are now in the ring
+      if (k >= 4 && y < ye) {
+        uint32_t out[2];
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t pq[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int c = 2 * hlf + e;
+            // rows r-4 .. r sit in slots (u+1)%5 .. u; the kernel is symmetric so only the distance matters
+            const uint32_t v = ring[(u + 1) % 5][c] + ring[u][c] + 4u * (ring[(u + 2) % 5][c] + ring[(u + 4) % 5][c]) +
+                               6u * ring[(u + 3) % 5][c] + 0x00800080u;
+            pq[e] = (v >> 8) & 0x00ff00ffu;
+          }
+          out[hlf] = __byte_perm(pq[0], pq[1], 0x6420);
+        }
+        const size_t o = (size_t)y * W + out_col;
+        if (fast && interior) {
+          if (has_prev) {
+            const uint2 pv = __ldg(reinterpret_cast<const uint2*>(prev + o));
+            const uint32_t d0 = __vcmpgtu4(__vabsdiffu4(out[0], pv.x), 0x19191919u);
+            const uint32_t d1 = __vcmpgtu4(__vabsdiffu4(out[1], pv.y), 0x19191919u);
+            changed += (__popc(d0) + __popc(d1)) >> 3;
+          }
+          *reinterpret_cast<uint2*>(next + o) = make_uint2(out[0], out[1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (xl + j < W) {
+              const int nv = (out[j >> 2] >> (8 * (j & 3))) & 0xff;
+              if (has_prev) {
+                const int pv = prev[o + j];
+                changed += (abs(nv - pv) > 25) ? 1 : 0;
+              }
+              next[o + j] = (uint8_t)nv;
             }
-            f.next[o + j] = (uint8_t)nv;
           }
         }
       }
@@ -387,10 +442,10 @@ __global__ void __launch_bounds__(kMotionWarps * 32) k_motion(const __grid_const
   }
   changed = warp_sum(changed);
   if (lane == 0) {
-    if (f.has_prev) {
-      if (changed) atomicAdd(p.changed + frame0 + frame, changed);
+    if (has_prev) {
+      if (changed) atomicAdd(p.changed + frame0 + f.out_idx, changed);
     } else if (task == 0) {
-      p.changed[frame0 + frame] = -1;
+      p.changed[frame0 + f.out_idx] = -1;
     }
   }
 }
@@ -529,47 +584,56 @@ extern "C" int b200va_motion(b200va_handle h, const uint8_t* const* frames, cons
   REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
   if (batch == 0) return B200VA_OK;
   CUDA_TRY(h, cudaMemsetAsync(changed_out, 0, sizeof(int32_t) * batch, st));
-  for (int base = 0; base < batch; base += B200VA_LAUNCH_FRAMES) {
-    const int n = batch - base < B200VA_LAUNCH_FRAMES ? batch - base : B200VA_LAUNCH_FRAMES;
-    MotionParams p;
-    memset(&p, 0, sizeof(p));
-    int max_tasks = 0;
-    // rows per warp task: tall enough that the 4 halo rows stay a small overhead, short enough
-    // that the launch fills the SMs several times over
-    long long total_px = 0;
-    for (int i = 0; i < n; ++i) total_px += (long long)src_h[base + i] * src_w[base + i];
-    int rows = 32;
-    {
-      const long long want_tasks = (long long)h->num_sms * 64 * 4;
-      while (rows > 8 && total_px / ((long long)rows * kStripPx) < want_tasks) rows >>= 1;
+  // frames with and without an ROI mask go to separate launches (the mask is a template switch);
+  // `changed` is indexed by the original batch position
+  std::vector<int> order[2];
+  for (int b = 0; b < batch; ++b) order[(roi_masks && roi_masks[b]) ? 1 : 0].push_back(b);
+  for (int with_mask = 0; with_mask < 2; ++with_mask) {
+    const std::vector<int>& idx = order[with_mask];
+    for (size_t base = 0; base < idx.size(); base += B200VA_LAUNCH_FRAMES) {
+      const int n = (int)std::min<size_t>(B200VA_LAUNCH_FRAMES, idx.size() - base);
+      MotionParams p;
+      memset(&p, 0, sizeof(p));
+      int max_tasks = 0;
+      // rows per warp task: tall enough that the 4 halo rows stay a small overhead, short enough
+      // that the launch fills the SMs several times over
+      long long total_px = 0;
+      for (int i = 0; i < n; ++i) total_px += (long long)src_h[idx[base + i]] * src_w[idx[base + i]];
+      int rows = 64;
+      {
+        const long long want_tasks = (long long)h->num_sms * 48 * 3;
+        while (rows > 8 && total_px / ((long long)rows * kStripPx) < want_tasks) rows >>= 1;
+      }
+      p.rows_per_task = rows;
+      for (int i = 0; i < n; ++i) {
+        const int b = idx[base + i];
+        MotionFrame& f = p.f[i];
+        REQUIRE(h, frames[b] && next_gray[b], "frame %d: NULL frame or state buffer", b);
+        REQUIRE(h, src_h[b] > 0 && src_w[b] > 0, "frame %d has bad size", b);
+        REQUIRE(h, !has_prev[b] || (prev_gray && prev_gray[b]), "frame %d: has_prev without a previous buffer", b);
+        REQUIRE(h, !has_prev[b] || prev_gray[b] != next_gray[b], "frame %d: prev_gray and next_gray alias", b);
+        f.src = frames[b];
+        f.mask = with_mask ? roi_masks[b] : nullptr;
+        f.prev = has_prev[b] ? prev_gray[b] : nullptr;
+        f.next = next_gray[b];
+        f.pitch = src_pitch ? src_pitch[b] : 3ll * src_w[b];
+        REQUIRE(h, f.pitch >= 3ll * src_w[b], "frame %d: pitch smaller than 3*width", b);
+        f.h = src_h[b];
+        f.w = src_w[b];
+        f.has_prev = has_prev[b] ? 1 : 0;
+        f.out_idx = b;
+        f.fast = (f.w % 16 == 0) && ((uintptr_t)f.src % 16 == 0) && (f.pitch % 16 == 0) && ((uintptr_t)f.next % 16 == 0) &&
+                 (!f.prev || (uintptr_t)f.prev % 16 == 0) && (!f.mask || (uintptr_t)f.mask % 16 == 0);
+        const int strips = (f.w + kStripPx - 1) / kStripPx;
+        const int row_tasks = (f.h + rows - 1) / rows;
+        if (strips * row_tasks > max_tasks) max_tasks = strips * row_tasks;
+      }
+      p.changed = changed_out;
+      dim3 grid((max_tasks + kMotionWarps - 1) / kMotionWarps, n);
+      if (with_mask) k_motion<true><<<grid, kMotionWarps * 32, 0, st>>>(p, 0);
+      else k_motion<false><<<grid, kMotionWarps * 32, 0, st>>>(p, 0);
+      LAUNCH_CHECK(h);
     }
-    p.rows_per_task = rows;
-    for (int i = 0; i < n; ++i) {
-      const int b = base + i;
-      MotionFrame& f = p.f[i];
-      REQUIRE(h, frames[b] && next_gray[b], "frame %d: NULL frame or state buffer", b);
-      REQUIRE(h, src_h[b] > 0 && src_w[b] > 0, "frame %d has bad size", b);
-      REQUIRE(h, !has_prev[b] || (prev_gray && prev_gray[b]), "frame %d: has_prev without a previous buffer", b);
-      REQUIRE(h, !has_prev[b] || prev_gray[b] != next_gray[b], "frame %d: prev_gray and next_gray alias", b);
-      f.src = frames[b];
-      f.mask = roi_masks ? roi_masks[b] : nullptr;
-      f.prev = has_prev[b] ? prev_gray[b] : nullptr;
-      f.next = next_gray[b];
-      f.pitch = src_pitch ? src_pitch[b] : 3ll * src_w[b];
-      REQUIRE(h, f.pitch >= 3ll * src_w[b], "frame %d: pitch smaller than 3*width", b);
-      f.h = src_h[b];
-      f.w = src_w[b];
-      f.has_prev = has_prev[b] ? 1 : 0;
-      f.fast = (f.w % 16 == 0) && ((uintptr_t)f.src % 16 == 0) && (f.pitch % 16 == 0) && ((uintptr_t)f.next % 16 == 0) &&
-               (!f.prev || (uintptr_t)f.prev % 16 == 0) && (!f.mask || (uintptr_t)f.mask % 16 == 0);
-      const int strips = (f.w + kStripPx - 1) / kStripPx;
-      const int row_tasks = (f.h + rows - 1) / rows;
-      if (strips * row_tasks > max_tasks) max_tasks = strips * row_tasks;
-    }
-    p.changed = changed_out;
-    dim3 grid((max_tasks + kMotionWarps - 1) / kMotionWarps, n);
-    k_motion<<<grid, kMotionWarps * 32, 0, st>>>(p, base);
-    LAUNCH_CHECK(h);
   }
   return B200VA_OK;
 }

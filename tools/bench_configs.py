@@ -1,0 +1,99 @@
+"""Device-time per tick for the BASELINE.json configurations that are not the bench.py line
+(configs 1, 2, 4, 5 of SURVEY.md §8d).  Inputs resident in HBM, CUDA events around every C-ABI call,
+medians over `--steps` ticks.  Writes profiles/r1_configs.json when --out is given."""
+import argparse, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from realtime_video_analytics_32streams_b200 import _native, synth
+
+ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=30); ap.add_argument("--out", default="")
+ap.add_argument("--only", default="")
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
+    if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6650.0
+
+
+def timed(fns, steps, warm=5):
+    """fns: list of (name, callable). Returns {name: median ms} and total."""
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(fns) + 1)] for _ in range(steps)]
+    for k in range(warm):
+        for _, f in fns: f(k)
+    torch.cuda.synchronize()
+    for k in range(steps):
+        ev[k][0].record()
+        for i, (_, f) in enumerate(fns):
+            f(warm + k); ev[k][i + 1].record()
+    torch.cuda.synchronize()
+    res = {n: float(np.median([e[i].elapsed_time(e[i + 1]) for e in ev])) for i, (n, _) in enumerate(fns)}
+    res["tick_total"] = float(np.median([e[0].elapsed_time(e[-1]) for e in ev]))
+    return res
+
+
+def simple(name, B, hw, n_obj, dup, conf=0.35, iou=0.5, trk=(30, 1, 0.5)):
+    H, W = hw
+    h = _native.Handle(device=0, max_batch=max(B, 1), max_anchors=8400, max_candidates=4096, max_dets=1024, max_streams=B, max_tracks=2048)
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    sets = 4
+    frames = [torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev, generator=g) for _ in range(sets)]
+    batches = [_native.FrameBatch(list(f.unbind(0))) for f in frames]
+    scenes = [synth.DenseScene(9000 + s, n_objects=n_obj, dup=dup, n_obj_classes=10) for s in range(B)]
+    heads = [torch.from_numpy(np.stack([sc.head(t) for sc in scenes])).to(dev) for t in range(sets)]
+    metas = (_native.Letterbox * B)(*[_native.letterbox_meta(H, W, 640, 640) for _ in range(B)])
+    net = torch.empty((B, 3, 640, 640), dtype=torch.float32, device=dev)
+    dets, tracks = h.alloc_dets(B), h.alloc_tracks(B)
+    slots = _native._int_array(list(range(B)))
+    r = timed([("preprocess", lambda k: h.preprocess(batches[k % sets], (640, 640), 0, out=net)),
+               ("postprocess", lambda k: h.postprocess(heads[k % sets], metas, conf, iou, filter_conf=conf, out=dets)),
+               ("tracker", lambda k: h.tracker_update(slots, dets, trk[0], trk[1], trk[2], out=tracks))], args.steps)
+    h.poll_status()
+    r.update(config=name, streams=B, frame=[H, W], frames_per_s=B / (r["tick_total"] * 1e-3),
+             dets_per_frame=float(dets["count"].float().mean()), tracks_per_stream=float(tracks["count"].float().mean()))
+    h.close()
+    return r
+
+
+def config4(B=32):
+    """32 x 4K with per-stream ROI polygons and the motion gate (every pixel is read)."""
+    H, W = 2160, 3840
+    h = _native.Handle(device=0, max_batch=B, max_anchors=8400, max_candidates=4096, max_dets=1024, max_streams=B, max_tracks=2048)
+    g = torch.Generator(device=dev); g.manual_seed(7)
+    sets = 2
+    frames = [torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev, generator=g) for _ in range(sets)]
+    masks = [h.roi_rasterize(synth.synth_polygons(4000 + s, H, W), H, W) for s in range(B)]
+    batches = [_native.FrameBatch(list(f.unbind(0)), masks) for f in frames]
+    gray = [[torch.empty((H, W), dtype=torch.uint8, device=dev) for _ in range(B)] for _ in range(2)]
+    changed = torch.empty((B,), dtype=torch.int32, device=dev)
+    h.motion(batches[0], [None] * B, gray[1], changed_out=changed)
+    scenes = [synth.DenseScene(9100 + s, n_objects=24, dup=3, n_obj_classes=10) for s in range(B)]
+    heads = [torch.from_numpy(np.stack([sc.head(t) for sc in scenes])).to(dev) for t in range(sets)]
+    metas = (_native.Letterbox * B)(*[_native.letterbox_meta(H, W, 640, 640) for _ in range(B)])
+    net = torch.empty((B, 3, 640, 640), dtype=torch.float32, device=dev)
+    dets, tracks = h.alloc_dets(B), h.alloc_tracks(B)
+    slots = _native._int_array(list(range(B)))
+    r = timed([("motion(+roi)", lambda k: h.motion(batches[k % sets], gray[(k + 1) % 2], gray[k % 2], changed_out=changed)),
+               ("preprocess(+roi)", lambda k: h.preprocess(batches[k % sets], (640, 640), 0, out=net)),
+               ("postprocess", lambda k: h.postprocess(heads[k % sets], metas, 0.35, 0.5, filter_conf=0.35, out=dets)),
+               ("tracker", lambda k: h.tracker_update(slots, dets, 30, 1, 0.5, out=tracks))], args.steps)
+    h.poll_status()
+    motion_bytes = B * (H * W * 3 + 3 * H * W)  # frame + mask + prev gray + new gray
+    pre_bytes = B * (720 * W * 3 + 720 * W + 3 * 640 * 640 * 4)  # tapped rows (+ their mask rows) + output
+    r.update(config="4: 32x4K + ROI + motion", streams=B, frame=[H, W], frames_per_s=B / (r["tick_total"] * 1e-3),
+             motion_GBps=motion_bytes / (r["motion(+roi)"] * 1e-3) / 1e9, motion_frac_of_peak=motion_bytes / (r["motion(+roi)"] * 1e-3) / 1e9 / PEAK,
+             preprocess_GBps=pre_bytes / (r["preprocess(+roi)"] * 1e-3) / 1e9,
+             preprocess_frac_of_peak=pre_bytes / (r["preprocess(+roi)"] * 1e-3) / 1e9 / PEAK,
+             motion_algorithmic_bytes=motion_bytes, preprocess_algorithmic_bytes=pre_bytes)
+    h.close()
+    return r
+
+
+out = []
+todo = args.only.split(",") if args.only else ["1", "2", "5", "4"]
+if "1" in todo: out.append(simple("1: 1 stream 1080p (pipeline-sim shape)", 1, (1080, 1920), 10, 1))
+if "2" in todo: out.append(simple("2: 4 streams 1080p (pipeline-rtsp shape)", 4, (1080, 1920), 10, 1))
+if "5" in todo: out.append(simple("5: dense stress, 32 streams, ~1800 candidates -> ~300 kept", 32, (1080, 1920), 300, 6))
+if "4" in todo: out.append(config4())
+for r in out:
+    print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()}))
+if args.out:
+    json.dump({"peak_GBps": PEAK, "results": out}, open(args.out, "w"), indent=1)
