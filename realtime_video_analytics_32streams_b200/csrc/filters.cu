@@ -174,7 +174,7 @@ constexpr int kMotionWarps = 8;
 constexpr int kStripPx = 256;             // pixels per warp-row (8 per lane)
 constexpr int kRawBytes = 16 + 768 + 16;  // pixels [-2, 258) of a strip, on 16-byte chunk boundaries
 constexpr int kMaskBytes = 16 + 256 + 16;
-constexpr int kStagesM = 4;
+constexpr int kStagesM = 5;  // = the row-loop unroll factor, so stage indices are compile-time constants
 
 struct MotionFrame {
   const uint8_t* src;
@@ -225,30 +225,20 @@ __device__ __forceinline__ int reflect_near(int i, int n) {
   return i >= n ? 2 * n - 2 - i : i;
 }
 
-template <bool MASK>
-__global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_constant__ MotionParams p, int frame0) {
-  __shared__ __align__(16) uint8_t s_raw[kMotionWarps][kStagesM][kRawBytes];
-  __shared__ __align__(16) uint8_t s_msk[MASK ? kMotionWarps : 1][kStagesM][kMaskBytes];
-
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int frame = blockIdx.y;
-  const MotionFrame& f = p.f[frame];
+// SIMPLE = the common case (16-byte aligned frame, strip entirely inside the image, image at least 4
+// pixels wide / high): no per-pixel reflection, no byte loaders, vector stores only.  Everything else
+// (partial strips, tiny or unaligned images) runs the same arithmetic through the generic instance;
+// keeping the two apart keeps the hot loop small enough for the instruction cache.
+template <bool MASK, bool SIMPLE>
+__device__ __noinline__ void motion_task(const MotionParams& p, const MotionFrame& f, int frame0, int task, int x0,
+                                         int yb, int ye, uint8_t* raw_base, uint8_t* msk_base) {
+  const int lane = threadIdx.x & 31;
   const int W = f.w, H = f.h;
-  const int strips = (W + kStripPx - 1) / kStripPx;
-  const int row_tasks = (H + p.rows_per_task - 1) / p.rows_per_task;
-  const int task = blockIdx.x * kMotionWarps + warp;
-  if (task >= strips * row_tasks) return;
-  const int x0 = (task % strips) * kStripPx;
-  const int yb = (task / strips) * p.rows_per_task;
-  const int ye = min(H, yb + p.rows_per_task);
-  const bool fast = f.fast != 0;
+  const bool fast = SIMPLE || f.fast != 0;
   const int row_bytes = 3 * W;
-  const int mw = MASK ? warp : 0;
   const uint8_t* const src = f.src;
   const uint8_t* const mask = f.mask;
   const long long pitch = f.pitch;
-  uint8_t* const raw_base = &s_raw[warp][0][0];
-  uint8_t* const msk_base = &s_msk[mw][0][0];
 
   // per-lane copy plan of a row, fixed for the whole task: raw[16 + 3*(x - x0) + c] holds channel c
   // of pixel x, msk[16 + (x - x0)] its ROI flag; chunks that fall outside the row are skipped
@@ -259,11 +249,11 @@ __global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_co
   const bool m_ok = MASK && fast && lane < kMaskBytes / 16 && m_off >= 0 && m_off + 16 <= W;
 
   auto load_row = [&](int r, int stage) {
-    const int rr = reflect_near(r, H);
+    const int rr = SIMPLE ? (r < 0 ? -r : (r >= H ? 2 * H - 2 - r : r)) : reflect_near(r, H);
     const uint8_t* g = src + (long long)rr * pitch;
     uint8_t* raw = raw_base + stage * kRawBytes;
     uint8_t* msk = msk_base + stage * kMaskBytes;
-    if (fast) {
+    if (SIMPLE || fast) {
       if (c0_ok) cp_async16(raw + 16 * lane, g + c0_off);
       if (c1_ok) cp_async16(raw + 16 * lane + 512, g + c1_off);
       if (m_ok) cp_async16(msk + 16 * lane, mask + (size_t)rr * W + m_off);
@@ -278,6 +268,7 @@ __global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_co
 
   const int r_first = yb - 2, r_last = ye + 1;  // rows whose horizontal pass this task needs
   const int nrows = r_last - r_first + 1;
+#pragma unroll
   for (int k = 0; k < kStagesM - 1; ++k) {
     if (k < nrows) load_row(r_first + k, k);
     else cp_async_commit();
@@ -290,11 +281,11 @@ __global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_co
     for (int b = 0; b < 4; ++b) ring[a][b] = 0;
   int changed = 0;
   const int xl = x0 + 8 * lane;
-  const bool interior = xl + 8 <= W;  // all 8 pixels of the lane are real pixels
+  const bool interior = SIMPLE || xl + 8 <= W;  // all 8 pixels of the lane are real pixels
   // how the strip's outer halo pixels are obtained: 0 = they are staged pixels, 1 = mirror of the
   // lane's own pixels (image edge on a strip boundary), 2 = generic (reflect through the staged row)
-  const int left_kind = x0 == 0 ? (W >= 4 ? 1 : 2) : 0;
-  const int right_kind = x0 + kStripPx + 2 <= W ? 0 : ((x0 + kStripPx == W && W >= 4) ? 1 : 2);
+  const int left_kind = x0 == 0 ? ((SIMPLE || W >= 4) ? 1 : 2) : 0;
+  const int right_kind = x0 + kStripPx + 2 <= W ? 0 : ((SIMPLE || (x0 + kStripPx == W && W >= 4)) ? 1 : 2);
   const int lane_raw = 16 + 24 * lane, lane_msk = 16 + 8 * lane;
   const size_t out_col = (size_t)xl;
   const bool has_prev = f.has_prev != 0;
@@ -314,8 +305,8 @@ __global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_co
     for (int u = 0; u < 5; ++u) {
       const int k = k0 + u;
       if (k >= nrows) break;
-      const int stage = k & (kStagesM - 1);
-      if (k + kStagesM - 1 < nrows) load_row(r_first + k + kStagesM - 1, (k + kStagesM - 1) & (kStagesM - 1));
+      const int stage = u;  // k0 is a multiple of 5 = kStagesM: a constant after unrolling
+      if (k + kStagesM - 1 < nrows) load_row(r_first + k + kStagesM - 1, (u + kStagesM - 1) % kStagesM);
       else cp_async_commit();
       cp_async_wait<kStagesM - 1>();
       __syncwarp();
@@ -324,7 +315,7 @@ __global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_co
 
       // ---- gray of the lane's 8 pixels, packed as pairs P[q] = g[2q] | g[2q+1] << 16 ----
       uint32_t P[4];
-      if (interior) {
+      if (SIMPLE || interior) {
         const uint2* q = reinterpret_cast<const uint2*>(raw + lane_raw);
         const uint2 w0 = q[0], w1 = q[1], w2 = q[2];
         uint32_t g8[8];
@@ -336,14 +327,17 @@ __global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_co
         g8[5] = gray_dp4a(__funnelshift_r(w1.y, w2.x, 24));
         g8[6] = gray_dp4a(__funnelshift_r(w2.x, w2.y, 16));
         g8[7] = gray_dp4a(w2.y >> 8);
-        if (MASK) {  // masked pixels are black (bitwise_and with the mask): gray 0
-          const uint2 mk = *reinterpret_cast<const uint2*>(msk + lane_msk);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if ((((j < 4 ? mk.x : mk.y) >> (8 * (j & 3))) & 0xffu) == 0u) g8[j] = 0u;
-        }
 #pragma unroll
         for (int q2 = 0; q2 < 4; ++q2) P[q2] = g8[2 * q2] | (g8[2 * q2 + 1] << 16);
+        if (MASK) {  // masked pixels are black (bitwise_and with the mask): gray 0
+          const uint2 mk = *reinterpret_cast<const uint2*>(msk + lane_msk);
+          // any non-zero mask byte -> 0xff
+          const uint32_t m0 = __vcmpne4(mk.x, 0u), m1 = __vcmpne4(mk.y, 0u);
+          P[0] &= __byte_perm(m0, 0u, 0x1100);
+          P[1] &= __byte_perm(m0, 0u, 0x3322);
+          P[2] &= __byte_perm(m1, 0u, 0x1100);
+          P[3] &= __byte_perm(m1, 0u, 0x3322);
+        }
       } else {
 #pragma unroll
         for (int q2 = 0; q2 < 4; ++q2) {
@@ -365,7 +359,7 @@ __global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_co
             gb = msk[15] ? gb : 0u;
           }
           L = ga | (gb << 16);
-        } else if (left_kind == 1) {  // reflect: g[-2] = g[2], g[-1] = g[1]
+        } else if (SIMPLE || left_kind == 1) {  // reflect: g[-2] = g[2], g[-1] = g[1]
           L = (P[1] & 0xffffu) | (P[0] & 0xffff0000u);
         } else {
           L = gray_at(raw, msk, x0 - 2) | (gray_at(raw, msk, x0 - 1) << 16);
@@ -380,7 +374,7 @@ __global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_co
             gb = msk[17 + kStripPx] ? gb : 0u;
           }
           R = ga | (gb << 16);
-        } else if (right_kind == 1) {  // reflect: g[W] = g[W-2], g[W+1] = g[W-3]
+        } else if (SIMPLE || right_kind == 1) {  // reflect: g[W] = g[W-2], g[W+1] = g[W-3]
           R = (P[3] & 0xffffu) | (P[2] & 0xffff0000u);
         } else {
           const int x = x0 + kStripPx;
@@ -415,8 +409,8 @@ __global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_co
           }
           out[hlf] = __byte_perm(pq[0], pq[1], 0x6420);
         }
-        const size_t o = (size_t)y * W + out_col;
-        if (fast && interior) {
+        const size_t o = (size_t)y * (size_t)W + out_col;
+        if (SIMPLE || (fast && interior)) {
           if (has_prev) {
             const uint2 pv = __ldg(reinterpret_cast<const uint2*>(prev + o));
             const uint32_t d0 = __vcmpgtu4(__vabsdiffu4(out[0], pv.x), 0x19191919u);
@@ -448,6 +442,27 @@ __global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_co
       p.changed[frame0 + f.out_idx] = -1;
     }
   }
+}
+
+template <bool MASK>
+__global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_constant__ MotionParams p, int frame0) {
+  __shared__ __align__(16) uint8_t s_raw[kMotionWarps][kStagesM][kRawBytes];
+  __shared__ __align__(16) uint8_t s_msk[MASK ? kMotionWarps : 1][kStagesM][kMaskBytes];
+  const int warp = threadIdx.x >> 5;
+  const MotionFrame& f = p.f[blockIdx.y];
+  const int W = f.w, H = f.h;
+  const int strips = (W + kStripPx - 1) / kStripPx;
+  const int row_tasks = (H + p.rows_per_task - 1) / p.rows_per_task;
+  const int task = blockIdx.x * kMotionWarps + warp;
+  if (task >= strips * row_tasks) return;
+  const int x0 = (task % strips) * kStripPx;
+  const int yb = (task / strips) * p.rows_per_task;
+  const int ye = min(H, yb + p.rows_per_task);
+  uint8_t* const raw_base = &s_raw[warp][0][0];
+  uint8_t* const msk_base = &s_msk[MASK ? warp : 0][0][0];
+  const bool simple = f.fast && x0 + kStripPx <= W && W >= 4 && H >= 4;
+  if (simple) motion_task<MASK, true>(p, f, frame0, task, x0, yb, ye, raw_base, msk_base);
+  else motion_task<MASK, false>(p, f, frame0, task, x0, yb, ye, raw_base, msk_base);
 }
 
 }  // namespace
