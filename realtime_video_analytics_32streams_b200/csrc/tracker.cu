@@ -76,7 +76,7 @@ __device__ __forceinline__ double iou64(double ax1, double ay1, double ax2, doub
   return __ddiv_rn(inter, uni);
 }
 
-constexpr int kDetChunk = 128;  // detections staged in shared memory at a time
+constexpr int kDetChunk = 64;  // detections staged in shared memory at a time (two warps cover a chunk)
 constexpr int kCand = 6;        // candidate slots per detection and kind; more -> exact brute-force scan
 
 struct DetStage {
@@ -128,22 +128,33 @@ __device__ __forceinline__ void warp_argmax(double& best, int& best_t) {
 // The matching is sequential in the reference, but every IoU it can ever ask for within one chunk of
 // detections is known up front: detection i against a track as it stood at the start of the chunk,
 // or against an earlier detection of the chunk (a matched or new track carries exactly that box).
-// Phase A computes those float64 IoUs with all threads and keeps, per detection, the few that pass
-// the threshold; phase B lets one warp walk the detections in order doing only look-ups:
-//   last_det[t] = detection (index in the frame) whose box track t holds now (-1: untouched this frame)
-//   holder[d]   = track currently holding chunk-local detection d's box (-1: none / overwritten since)
-// Nothing in the sequential part touches global memory: confidence, age and id of a touched track
-// are derived from last_det[] when the table is written back.
+//
+//   phase A   all threads: those float64 IoUs; per detection keep the few that pass the threshold
+//             (c_trk: vs tracks, c_det: vs earlier detections) and count how many detections claim
+//             each track.
+//   phase A2  a thread per detection: a detection is SIMPLE when it has no detection-detection edge
+//             and every track it could match is claimed by it alone -- nothing another detection does
+//             can change its outcome, so it is resolved right away (arg-max over its own list).
+//   phase B   one warp walks the remaining CONFLICTED detections in order, look-ups only:
+//             aux[key] = last conflicted detection that took the track `key`; a track created by
+//             detection j of the chunk has the virtual key Tc + j until phase C numbers it.
+//   phase C   all threads: number the new tracks in detection order (prefix sum), add the hits, and
+//             let the last detection matched to each track write its box.
+//   A chunk in which some detection has more than kCand candidates falls back to the plain
+//   sequential scan (exact, slower).  Nothing in the sequential parts touches global memory:
+//   confidence, age and id of a touched track are derived from last_det[] at write-back.
 __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__ TrkParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   double* sbox = reinterpret_cast<double*>(smem_raw);                            // [max_tracks][4]
   int32_t* scls = reinterpret_cast<int32_t*>(sbox + (size_t)p.max_tracks * 4);   // [max_tracks]
   int32_t* shits = scls + p.max_tracks;                                          // [max_tracks]
-  int16_t* last_det = reinterpret_cast<int16_t*>(shits + p.max_tracks);          // [max_tracks]
+  int32_t* aux = shits + p.max_tracks;                                           // [max_tracks + kDetChunk] claims, then phase-B state
+  int16_t* last_det = reinterpret_cast<int16_t*>(aux + p.max_tracks + kDetChunk);  // [max_tracks] detection holding the track's box now, -1 untouched
   __shared__ DetStage sd;
   __shared__ Cand c_trk[kDetChunk][kCand], c_det[kDetChunk][kCand];
-  __shared__ int n_trk[kDetChunk], n_det[kDetChunk], holder[kDetChunk];
-  __shared__ int s_T, s_new, s_is_last;
+  __shared__ int n_trk[kDetChunk], n_det[kDetChunk], key[kDetChunk], conflicted[kDetChunk], clist[kDetChunk];
+  __shared__ int s_T, s_new, s_is_last, s_fallback, s_nconf;
+  __shared__ int wsum[kTrkThreads / 32];
 
   const int bi = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -203,114 +214,205 @@ __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__
       sd.cls[i] = p.d_cls[db + d];
       n_trk[i] = 0;
       n_det[i] = 0;
-      holder[i] = -1;
+    }
+    if (tid == 0) {
+      s_fallback = 0;
+      s_nconf = 0;
     }
     __syncthreads();
     PHASE_STAMP(p.dbg, 2);
 
-    // ---- phase A: every IoU the chunk can need, all threads ----
+    // ---- phase A: every IoU the chunk can need.  Warp w takes detections w, w+8, ..; lanes take tracks ----
     const int Tc = s_T;
-    {
-      const int i = tid & (kDetChunk - 1), half = tid >> 7;  // 256 threads: two per detection
-      if (i < nd) {
-        const double4 bx = sd.box[i];
-        const int dcls = sd.cls[i];
-        for (int t = half; t < Tc; t += kTrkThreads / kDetChunk) {
-          if (scls[t] != dcls) continue;
-          const double4 tb = reinterpret_cast<const double4*>(sbox)[t];
-          if (!overlaps(tb, bx)) continue;
-          const double v = iou64(tb.x, tb.y, tb.z, tb.w, bx.x, bx.y, bx.z, bx.w);
-          if (v >= p.thr && v > 0.0) {
-            const int k = atomicAdd(&n_trk[i], 1);
-            if (k < kCand) {
-              c_trk[i][k].iou = v;
-              c_trk[i][k].idx = t;
-            }
+    for (int t = tid; t < Tc + kDetChunk; t += kTrkThreads) aux[t] = 0;  // claims per track
+    __syncthreads();
+    for (int i = warp; i < nd; i += kTrkThreads / 32) {
+      const double4 bx = sd.box[i];
+      const int dcls = sd.cls[i];
+      for (int t = lane; t < Tc; t += 32) {
+        if (scls[t] != dcls) continue;
+        const double4 tb = reinterpret_cast<const double4*>(sbox)[t];
+        if (!overlaps(tb, bx)) continue;
+        const double v = iou64(tb.x, tb.y, tb.z, tb.w, bx.x, bx.y, bx.z, bx.w);
+        if (v >= p.thr && v > 0.0) {
+          const int k = atomicAdd(&n_trk[i], 1);
+          if (k < kCand) {
+            c_trk[i][k].iou = v;
+            c_trk[i][k].idx = t;
           }
+          atomicAdd(&aux[t], 1);
         }
-        for (int e = half; e < i; e += kTrkThreads / kDetChunk) {
-          if (sd.cls[e] != dcls) continue;
-          const double4 eb = sd.box[e];
-          if (!overlaps(eb, bx)) continue;
-          const double v = iou64(eb.x, eb.y, eb.z, eb.w, bx.x, bx.y, bx.z, bx.w);
-          if (v >= p.thr && v > 0.0) {
-            const int k = atomicAdd(&n_det[i], 1);
-            if (k < kCand) {
-              c_det[i][k].iou = v;
-              c_det[i][k].idx = e;
-            }
+      }
+      for (int e = lane; e < i; e += 32) {
+        if (sd.cls[e] != dcls) continue;
+        const double4 eb = sd.box[e];
+        if (!overlaps(eb, bx)) continue;
+        const double v = iou64(eb.x, eb.y, eb.z, eb.w, bx.x, bx.y, bx.z, bx.w);
+        if (v >= p.thr && v > 0.0) {
+          const int k = atomicAdd(&n_det[i], 1);
+          if (k < kCand) {
+            c_det[i][k].iou = v;
+            c_det[i][k].idx = e;
           }
         }
       }
     }
     __syncthreads();
-    PHASE_STAMP(p.dbg, 7);
 
-    // ---- phase B: one warp, detections in order, look-ups only ----
-    if (warp == 0) {
-      for (int i = 0; i < nd; ++i) {
-#ifdef B200VA_PHASE_TIMING
-        if (i < 8) PHASE_STAMP(p.dbg, 8 + i);
-#endif
-        const int T = s_T;
+    // ---- phase A2: classify; simple detections are resolved here ----
+    {
+      bool conf = false;
+      if (tid < nd) {
+        const int i = tid;
         const int nt = n_trk[i], ne = n_det[i];
-        const int dcls = sd.cls[i];
+        if (nt > kCand || ne > kCand) atomicOr(&s_fallback, 1);
+        conf = ne > 0;
         double best = 0.0;
         int best_t = 0x7fffffff;
-        if (nt > kCand || ne > kCand) {
-          // crowded detection: exact scan of the live table (boxes in sbox are current)
-          scan_tracks(sbox, scls, T, lane, 32, sd.box[i], dcls, p.thr, best, best_t);
-        } else if (lane < nt) {
-          const Cand c = c_trk[i][lane];
-          if (last_det[c.idx] < d0) {  // not re-boxed by a detection of this chunk
+        for (int k = 0; k < min(nt, kCand); ++k) {
+          const Cand c = c_trk[i][k];
+          conf |= aux[c.idx] > 1;
+          if (c.iou > best || (c.iou == best && c.idx < best_t)) {
             best = c.iou;
             best_t = c.idx;
           }
-        } else if (lane >= kCand && lane - kCand < ne) {
-          const Cand c = c_det[i][lane - kCand];
-          const int t = holder[c.idx];
-          if (t >= 0) {
-            best = c.iou;
-            best_t = t;
-          }
         }
-        const unsigned cand = __ballot_sync(0xffffffffu, best_t != 0x7fffffff);
-        int match = 0x7fffffff;
-        if (cand) {
-          if (cand & (cand - 1)) {
+        conflicted[i] = conf;
+        key[i] = conf ? -1 : (best_t == 0x7fffffff ? Tc + i : best_t);
+      }
+      // ordered list of the conflicted detections (kDetChunk <= 64: two warps cover the chunk)
+      const unsigned bal = __ballot_sync(0xffffffffu, conf);
+      if (warp < 2 && lane == 0) wsum[warp] = __popc(bal);
+      __syncthreads();
+      if (tid < nd && conf) clist[(warp ? wsum[0] : 0) + __popc(bal & ((1u << lane) - 1u))] = tid;
+      if (tid == 0) s_nconf = wsum[0] + (nd > 32 ? wsum[1] : 0);
+      // phase-B state: aux[key] = last conflicted detection that took `key` (-1: none)
+      __syncthreads();
+      for (int t = tid; t < Tc + kDetChunk; t += kTrkThreads) aux[t] = -1;
+      __syncthreads();
+    }
+    PHASE_STAMP(p.dbg, 7);
+
+    if (s_fallback) {
+      // ---- crowded chunk: plain sequential scan of the live table, exact (tracker.py:50-109) ----
+      if (warp == 0) {
+        for (int i = 0; i < nd; ++i) {
+          const int T = s_T;
+          const int dcls = sd.cls[i];
+          double best;
+          int best_t;
+          scan_tracks(sbox, scls, T, lane, 32, sd.box[i], dcls, p.thr, best, best_t);
+          const unsigned cand = __ballot_sync(0xffffffffu, best_t != 0x7fffffff);
+          int match = 0x7fffffff;
+          if (cand) {
             warp_argmax(best, best_t);
             match = best_t;
-          } else {
-            match = __shfl_sync(0xffffffffu, best_t, __ffs(cand) - 1);
           }
-        }
-        if (lane == 0) {
-          // tracker.py:69-92
-          int t = match;
-          if (t == 0x7fffffff) {  // no match: new track, matchable at once
-            t = T;
-            if (t < p.max_tracks) {
-              scls[t] = dcls;
-              shits[t] = 1;
-              last_det[t] = -1;
-              s_new = s_new + 1;
-              s_T = T + 1;
+          if (lane == 0) {
+            int t = match;
+            if (t == 0x7fffffff) {
+              t = T;
+              if (t < p.max_tracks) {
+                scls[t] = dcls;
+                shits[t] = 1;
+                s_new = s_new + 1;
+                s_T = T + 1;
+              } else {
+                atomicOr(p.flags + FLAG_TRACK_OVERFLOW, 1);
+                t = -1;
+              }
             } else {
-              atomicOr(p.flags + FLAG_TRACK_OVERFLOW, 1);
-              t = -1;
+              shits[t] += 1;
             }
-          } else {  // match: overwrite immediately
-            shits[t] += 1;
+            if (t >= 0) {
+              last_det[t] = (int16_t)(d0 + i);
+              reinterpret_cast<double4*>(sbox)[t] = sd.box[i];
+            }
           }
-          if (t >= 0) {
-            const int prev = last_det[t];
-            if (prev >= d0) holder[prev - d0] = -1;
-            last_det[t] = (int16_t)(d0 + i);
-            holder[i] = t;
-            reinterpret_cast<double4*>(sbox)[t] = sd.box[i];
+          __syncwarp();
+        }
+      }
+    } else {
+      // ---- phase B: conflicted detections, in order, look-ups only ----
+      if (warp == 0) {
+        const int nconf = s_nconf;
+        for (int q = 0; q < nconf; ++q) {
+          const int i = clist[q];
+          const int nt = n_trk[i], ne = n_det[i];
+          double best = 0.0;
+          int best_t = 0x7fffffff;
+          if (lane < nt) {
+            const Cand c = c_trk[i][lane];
+            if (aux[c.idx] < 0) {  // nobody re-boxed this track yet in the chunk
+              best = c.iou;
+              best_t = c.idx;
+            }
+          } else if (lane >= kCand && lane - kCand < ne) {
+            const Cand c = c_det[i][lane - kCand];
+            const int e = c.idx, k = key[e];  // the track detection e was given (k >= 0: e precedes i)
+            // still carrying e's box: e was the last to take it (conflicted e), or nobody took it after a simple e
+            if (k >= 0 && (conflicted[e] ? aux[k] == e : aux[k] < 0)) {
+              best = c.iou;
+              best_t = k;
+            }
+          }
+          const unsigned cand = __ballot_sync(0xffffffffu, best_t != 0x7fffffff);
+          int match = Tc + i;  // no match: new track (virtual key)
+          if (cand) {
+            if (cand & (cand - 1)) {
+              warp_argmax(best, best_t);
+              match = best_t;
+            } else {
+              match = __shfl_sync(0xffffffffu, best_t, __ffs(cand) - 1);
+            }
+          }
+          if (lane == 0) {
+            key[i] = match;
+            aux[match] = i;
+          }
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+
+      // ---- phase C: number the new tracks in detection order, count hits, write the final boxes ----
+      {
+        const int i = tid;
+        const int k = i < nd ? key[i] : -1;
+        const bool is_new = i < nd && k == Tc + i;
+        const unsigned bal = __ballot_sync(0xffffffffu, is_new);
+        if (warp < 2 && lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        const int total_new = wsum[0] + (nd > 32 ? wsum[1] : 0);
+        const int room = p.max_tracks - Tc;
+        if (is_new) {
+          const int rank = (warp ? wsum[0] : 0) + __popc(bal & ((1u << lane) - 1u));
+          clist[i] = rank;  // clist is free again: rank of the track created by detection i
+          if (rank < room) {
+            scls[Tc + rank] = sd.cls[i];
+            shits[Tc + rank] = 0;
+            last_det[Tc + rank] = -1;
           }
         }
-        __syncwarp();
+        __syncthreads();
+        if (i < nd) {
+          const int r = k < Tc ? k : Tc + clist[k - Tc];
+          if (r < p.max_tracks) {
+            atomicAdd(&shits[r], 1);
+            // the last detection matched to a track leaves its box there
+            const bool last = conflicted[i] ? aux[k] == i : aux[k] < 0;
+            if (last) {
+              last_det[r] = (int16_t)(d0 + i);
+              reinterpret_cast<double4*>(sbox)[r] = sd.box[i];
+            }
+          }
+        }
+        if (tid == 0) {
+          const int made = min(total_new, room);
+          if (total_new > room) atomicOr(p.flags + FLAG_TRACK_OVERFLOW, 1);
+          s_new += made;
+          s_T = Tc + made;
+        }
       }
     }
   }
@@ -499,8 +601,8 @@ int tracker_state_create(b200va_ctx* h) {
   S->new_count = (int32_t*)(b + o_new);
   const long long one = 1;  // itertools.count(1), tracker.py:47
   CUDA_TRY(h, cudaMemcpy(S->next_id, &one, 8, cudaMemcpyHostToDevice));
-  const size_t smem = (size_t)h->cfg.max_tracks * 42 + 16;
-  if (smem > 176 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_tracks %d too large (<= 4096)", h->cfg.max_tracks);
+  const size_t smem = (size_t)h->cfg.max_tracks * 46 + kDetChunk * 4 + 16;
+  if (smem > 190 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_tracks %d too large (<= 4096)", h->cfg.max_tracks);
   CUDA_TRY(h, cudaFuncSetAttribute(k_tracker, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return B200VA_OK;
 }
@@ -552,7 +654,7 @@ static int tracker_launch(b200va_ctx* h, TrkParams& p, const int* stream_slots, 
   p.o_new = new_counts;
   p.flags = h->status_flags;
   p.dbg = h->dbg;
-  k_tracker<<<batch, kTrkThreads, (size_t)h->cfg.max_tracks * 42 + 16, st>>>(p);
+  k_tracker<<<batch, kTrkThreads, (size_t)h->cfg.max_tracks * 46 + kDetChunk * 4 + 16, st>>>(p);
   LAUNCH_CHECK(h);
   return B200VA_OK;
 }
