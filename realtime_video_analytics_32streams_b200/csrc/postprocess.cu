@@ -300,6 +300,8 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
   int* keep_off = reinterpret_cast<int*>(keep_w + p.cap_pow2 / 32);                         // [cap_pow2/64 + 1]
   uint16_t* scl = reinterpret_cast<uint16_t*>(keep_off + p.cap_pow2 / 64 + 1);              // [cap_pow2] class ids (class-aware mode)
   __shared__ uint32_t rows[64][2];
+  __shared__ float4 kbox[64];
+  __shared__ int kcl[64];
 
   __syncthreads();
   if (tid == 0) {
@@ -316,10 +318,10 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
   __syncthreads();
 
   PHASE_STAMP(p.dbg, 17);
-  if (n <= 2048) {
-    // rank sort: keys are unique, so rank_i = #{j : key_j > key_i} is a permutation.  Every thread
+  if (n <= 256) {
+    // rank sort (small n): keys are unique, so rank_i = #{j : key_j > key_i} is a permutation.  Every thread
     // streams the whole key array from shared memory (broadcast reads) -- two barriers in total
-    // where a bitonic network needs one per round.
+    // where a bitonic network needs one per round.  O(n^2) compares: only worth it for small n.
     unsigned long long* sorted = reinterpret_cast<unsigned long long*>(box);  // box[] is not live yet
     for (int i = tid; i < n; i += kNmsThreads) {
       const unsigned long long ki = keys[i];
@@ -381,28 +383,40 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
   PHASE_STAMP(p.dbg, 19);
   const bool aware = p.class_aware != 0;
   const float thr = p.iou_thr;
+  const bool thr_nonneg = thr >= 0.f;
   const int nchunks = (n + 63) >> 6;
+#ifdef B200VA_PHASE_TIMING
+  long long acc_a = 0, acc_b = 0, acc_c = 0, t_mark = clock64();
+#define NMS_MARK(acc) do { const long long _t = clock64(); acc += _t - t_mark; t_mark = _t; } while (0)
+#else
+#define NMS_MARK(acc) do { } while (0)
+#endif
   for (int ch = 0; ch < nchunks; ++ch) {
     const int c0 = ch << 6;
     const int m = min(64, n - c0);
     if (tid < 128) rows[tid >> 1][tid & 1] = 0u;
     __syncthreads();
-    // (a) in-chunk IoU bits (the predicate is symmetric): thread -> row i = tid / 16, columns 4 * (tid % 16) ..
+    // (a) in-chunk IoU bits: thread -> row i = tid / 16, columns 4 * (tid % 16) ..; the predicate is
+    // symmetric, so only pairs j > i are evaluated and a hit sets both (i, j) and (j, i)
     {
       const int i = tid >> 4, jb = (tid & 15) << 2;
-      if (i < m) {
+      if (i < m && jb + 3 > i) {
         const float4 bi = box[c0 + i];
-        uint32_t bits = 0u;  // the four columns of a thread fall into one 32-bit half of the row
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int j = jb + q;
-          if (j != i && j < m && (!aware || scl[c0 + i] == scl[c0 + j]) && suppresses(bi, box[c0 + j], thr))
-            bits |= 1u << (j & 31);
+          if (j <= i || j >= m) continue;
+          const float4 bj = box[c0 + j];
+          if (thr_nonneg && (bj.z <= bi.x || bi.z <= bj.x || bj.w <= bi.y || bi.w <= bj.y)) continue;  // disjoint: IoU 0
+          if ((!aware || scl[c0 + i] == scl[c0 + j]) && suppresses(bi, bj, thr)) {
+            atomicOr(&rows[i][j >> 5], 1u << (j & 31));
+            atomicOr(&rows[j][i >> 5], 1u << (i & 31));
+          }
         }
-        if (bits) atomicOr(&rows[i][jb >> 5], bits);
       }
     }
     __syncthreads();
+    NMS_MARK(acc_a);
     // (b) greedy resolution inside the chunk: kept_i = alive_i and no kept j < i suppresses i.  That
     // recursion has a unique solution; iterating it from kept = alive fixes box i after at most i
     // rounds, so one warp (two boxes per lane) repeats it until nothing changes -- a handful of
@@ -430,25 +444,36 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
       }
     }
     __syncthreads();
-    // (c) this chunk's survivors suppress every later box.  g threads share one later box (each takes
-    // 64 / g of the chunk's columns); g shrinks as the tail grows so that all 1024 threads stay busy.
+    NMS_MARK(acc_b);
+    // (c) this chunk's survivors suppress every later box.  The survivors are first packed into a
+    // dense list; g threads share one later box (each takes a slice of the list), g shrinking as the
+    // tail grows so that all 1024 threads stay busy.
     const unsigned long long kept = ((unsigned long long)keep_w[2 * ch + 1] << 32) | keep_w[2 * ch];
     const int tail = n - (c0 + 64);
     if (kept && tail > 0) {
+      const int nk = __popcll(kept);
+      if (tid < 64 && ((kept >> tid) & 1ull)) {
+        const int q = __popcll(kept & ((1ull << tid) - 1ull));
+        kbox[q] = box[c0 + tid];
+        kcl[q] = scl[c0 + tid];
+      }
+      __syncthreads();
       int g = 16;
       while (g > 1 && tail * g > kNmsThreads) g >>= 1;
-      const int cols = 64 / g;
       const int part = tid & (g - 1);
-      const unsigned long long mine = (cols == 64 ? kept : (kept >> (part * cols)) & ((1ull << cols) - 1ull));
-      if (mine) {
+      const int per = (nk + g - 1) / g;
+      const int qb = part * per, qe = min(nk, qb + per);
+      if (qb < qe) {
         for (int j = c0 + 64 + tid / g; j < n; j += kNmsThreads / g) {
           if ((supp[j >> 5] >> (j & 31)) & 1u) continue;
           const float4 bj = box[j];
-          unsigned long long kk = mine;
-          while (kk) {
-            const int i = __ffsll((long long)kk) - 1 + part * cols;
-            kk &= kk - 1;
-            if ((!aware || scl[c0 + i] == scl[j]) && suppresses(box[c0 + i], bj, thr)) {
+          const int cj = scl[j];
+          for (int q = qb; q < qe; ++q) {
+            const float4 bi = kbox[q];
+            // disjoint boxes have intersection exactly 0 -> IoU 0 -> kept whenever thr >= 0 (four compares
+            // instead of the full formula; NaN coordinates fail every compare and take the full path)
+            if (thr_nonneg && (bj.z <= bi.x || bi.z <= bj.x || bj.w <= bi.y || bi.w <= bj.y)) continue;
+            if ((!aware || kcl[q] == cj) && suppresses(bi, bj, thr)) {
               atomicOr(&supp[j >> 5], 1u << (j & 31));
               break;
             }
@@ -457,7 +482,15 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
       }
     }
     __syncthreads();
+    NMS_MARK(acc_c);
   }
+#ifdef B200VA_PHASE_TIMING
+  if (blockIdx.x == 0 && tid == 0) {
+    p.dbg[24] = acc_a;
+    p.dbg[25] = acc_b;
+    p.dbg[26] = acc_c;
+  }
+#endif
 
   PHASE_STAMP(p.dbg, 20);
   // filter_detections (detector.py:99-103): float64 compare on the kept boxes only

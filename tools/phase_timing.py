@@ -6,8 +6,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench as B
 from realtime_video_analytics_32streams_b200 import _native
-h = _native.Handle(device=0, max_batch=32, max_anchors=B.A, max_candidates=2048, max_dets=512, max_streams=64, max_tracks=1024)
-heads = torch.from_numpy(np.stack([B.make_heads(s, 2) for s in range(32)], axis=1)).cuda()
+h = _native.Handle(device=0, max_batch=32, max_anchors=B.A, max_candidates=4096, max_dets=1024, max_streams=64, max_tracks=2048)
+if os.environ.get("DENSE"):
+    from realtime_video_analytics_32streams_b200 import synth
+    sc = [synth.DenseScene(9000 + s, n_objects=300, dup=6, n_obj_classes=10) for s in range(32)]
+    heads = torch.from_numpy(np.stack([np.stack([c.head(t) for c in sc]) for t in range(2)])).cuda()
+else:
+    heads = torch.from_numpy(np.stack([B.make_heads(s, 2) for s in range(32)], axis=1)).cuda()
 metas = (_native.Letterbox * 32)(*[_native.letterbox_meta(B.H, B.W, 640, 640) for _ in range(32)])
 dets, tracks = h.alloc_dets(32), h.alloc_tracks(32)
 for k in range(6):
@@ -21,6 +26,7 @@ print("tracker phases (SM cycles, block 0): start->staged-issue %d, ->dets stage
       tuple(v[i + 1] - v[i] for i in range(6)))
 print("tracker: phase A %d, phase B %d; first iterations of B: %s" % (v[7] - v[2], v[3] - v[7], [v[9 + i] - v[8 + i] for i in range(7)]))
 print("nms phases: count+keys %d, sort %d, gather %d, chunks %d, filter+emit %d" % tuple(v[16 + i + 1] - v[16 + i] for i in range(5)))
+print("nms chunk loop split: (a) pair matrix %d, (b) resolve %d, (c) tail %d" % (v[24], v[25], v[26]))
 print("dets per frame", dets["count"].cpu().tolist()[:8], "tracks", tracks["count"].cpu().tolist()[:8])
 
 # hypothesis check: does a low-occupancy grid (32 CTAs) run slower per instruction than when the rest of the chip is busy?
