@@ -164,3 +164,41 @@ def test_sharded_id_aggregation_two_ranks_gloo(tmp_path):
     got = {(s, o): g for r in res for s, o, g in r["ids"]}
     assert got == want
     assert all(r["next"] == counter for r in res)
+
+
+def test_registration_shim_wires_the_reference_factory():
+    """with the reference importable (build container only), `backend: b200`
+    validates, create_detector dispatches to B200Detector and `tracker.type: b200_iou` selects
+    B200IouTracker.  Without a GPU construction must fail loudly (no silent CPU path)."""
+    ref = "/root/" + "reference/src"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present")
+    sys.path.insert(0, ref)
+    try:
+        import realtime_analytics.config as rcfg
+        import realtime_analytics.detector as rdet
+        import realtime_analytics.pipeline as rpipe
+    except Exception as exc:  # pragma: no cover
+        pytest.skip(f"reference not importable: {exc}")
+    import torch
+
+    from realtime_video_analytics_32streams_b200 import register_with_reference
+
+    with pytest.raises(rcfg.ConfigError):
+        rcfg.DetectorConfig(backend="b200").validate()
+    register_with_reference(infer_factory=lambda cfg: (lambda x: x))
+    cfg = rcfg.DetectorConfig(backend="b200", confidence_threshold=0.35, iou_threshold=0.5)
+    cfg.validate()  # whitelisted now
+    assert cfg.backend == "b200"
+    with pytest.raises(rcfg.ConfigError):
+        rcfg.DetectorConfig(backend="nope").validate()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            rdet.create_detector(cfg)
+        with pytest.raises(RuntimeError):
+            rpipe.IouTracker(rcfg.TrackerConfig(type="b200_iou"))
+    # other tracker types still get the reference's own class
+    assert type(rpipe.IouTracker(rcfg.TrackerConfig())).__name__ == "IouTracker"
+    # the YAML authored for config 4 loads with the reference's own loader
+    full = rcfg.load_config(os.path.join(REPO, "config", "pipeline-4k-roi.yaml"))
+    assert full.detector.backend == "b200" and full.streams[0].motion_filter and len(full.streams[0].roi_polygons) == 2

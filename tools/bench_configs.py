@@ -87,8 +87,38 @@ def config4(B=32):
     return r
 
 
+def letterbox_only(name, B, hw, fmt=0, mask=False):
+    H, W = hw
+    h = _native.Handle(device=0, max_batch=B, max_anchors=8400, max_candidates=1024, max_dets=256, max_streams=B, max_tracks=256)
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    frames = [torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev, generator=g) for _ in range(2)]
+    masks = [h.roi_rasterize(synth.synth_polygons(4000 + s, H, W), H, W) for s in range(B)] if mask else None
+    batches = [_native.FrameBatch(list(f.unbind(0)), masks) for f in frames]
+    dt = {0: torch.float32, 1: torch.float16}.get(fmt, torch.uint8)
+    net = torch.empty((B, 3, 640, 640), dtype=dt, device=dev)
+    r = timed([("preprocess", lambda k: h.preprocess(batches[k % 2], (640, 640), fmt, out=net))], args.steps)
+    m = _native.letterbox_meta(H, W, 640, 640)
+    ys = set()
+    from oracle import cv_restate as cvr
+    y0, y1, b0, b1 = cvr.linear_taps(H, m.new_h, False)
+    rows = len(set(y0[b0 != 0].tolist()) | set(y1[b1 != 0].tolist()))
+    esz = {0: 4, 1: 2}.get(fmt, 1)
+    alg = B * (rows * W * 3 + (rows * W if mask else 0) + 3 * 640 * 640 * esz)
+    r.update(config=name, streams=B, frame=[H, W], algorithmic_bytes=alg, GBps=alg / (r["preprocess"] * 1e-3) / 1e9,
+             frac_of_peak=alg / (r["preprocess"] * 1e-3) / 1e9 / PEAK, tapped_rows=rows)
+    h.close()
+    return r
+
+
 out = []
 todo = args.only.split(",") if args.only else ["1", "2", "5", "4"]
+if "L" in todo:
+    out.append(letterbox_only("letterbox 32x1080p fp32", 32, (1080, 1920)))
+    out.append(letterbox_only("letterbox 32x1080p fp16", 32, (1080, 1920), fmt=1))
+    out.append(letterbox_only("letterbox 32x4K fp32", 32, (2160, 3840)))
+    out.append(letterbox_only("letterbox 32x4K fp32 + ROI mask", 32, (2160, 3840), mask=True))
+    out.append(letterbox_only("letterbox 32x720p fp32", 32, (720, 1280)))
+    out.append(letterbox_only("letterbox 32x1440p fp32 (non-integer ratio)", 32, (1440, 2560)))
 if "1" in todo: out.append(simple("1: 1 stream 1080p (pipeline-sim shape)", 1, (1080, 1920), 10, 1))
 if "2" in todo: out.append(simple("2: 4 streams 1080p (pipeline-rtsp shape)", 4, (1080, 1920), 10, 1))
 if "5" in todo: out.append(simple("5: dense stress, 32 streams, ~1800 candidates -> ~300 kept", 32, (1080, 1920), 300, 6))
