@@ -608,6 +608,9 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
     p.conf_thr = (float)conf_thr;  // NEP-50 weak scalar: compared in float32 (detector.py:312)
     if (layout == B200VA_HEAD_CHANNEL_MAJOR) {
       // 16-byte loads need every channel row (A floats) and the tensor base 16-byte aligned
+      // (a TMA-staged variant -- all C rows of a 128-anchor tile bulk-copied to shared memory -- measured
+      // 24.6 us against 21.5 us for this register version on [32,84,8400]: the 512-byte row pieces at a
+      // 33.6 KB stride bound both; block sizes 64..256 are equivalent, 512 is slower)
       if (anchors % 4 == 0 && ((uintptr_t)head % 16 == 0)) {
         dim3 grid((anchors / 4 + 63) / 64, n);
         k_decode_cm<4><<<grid, 64, 0, st>>>(p, base);
