@@ -301,6 +301,37 @@ def run_gpu(args) -> None:
     k1_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     n_tracks = int(tracks["count"].sum().item())
     h.poll_status()
+    # the same tick replayed from CUDA graphs (one per input set): host launch cost out of the picture
+    graph_value = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graphs = []
+        with torch.cuda.stream(side):
+            for k in range(N_SETS):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side):
+                    step(k)
+                graphs.append(gr)
+        torch.cuda.current_stream().wait_stream(side)
+        for k in range(8):
+            graphs[k % N_SETS].replay()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for k in range(args.steps):
+            graphs[k % N_SETS].replay()
+        g1.record()
+        barrier()
+        gms = g0.elapsed_time(g1)
+        if world > 1:
+            tmax = torch.tensor([gms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            gms = float(tmax.item())
+        graph_value = world * STREAMS * args.steps / (gms * 1e-3)
+        h.poll_status()
+    except Exception as exc:  # pragma: no cover - informational only
+        graph_value = f"unavailable: {type(exc).__name__}"
     if world > 1:
         tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -399,6 +430,7 @@ def run_gpu(args) -> None:
                                "additionally builds every Detection / Track object"},
                 "gpu_launches": int(launches), "launches_per_step": launches / max(args.steps, 1),
                 "breakdown_ms": breakdown,
+                "value_cuda_graph_replay": round(graph_value, 1) if isinstance(graph_value, float) else graph_value,
                 "clocks": clocks.summary(), "tracks_alive": n_tracks}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_single_core_sample()

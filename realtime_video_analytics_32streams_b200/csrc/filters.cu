@@ -616,7 +616,7 @@ extern "C" int b200va_motion(b200va_handle h, const uint8_t* const* frames, cons
       for (int i = 0; i < n; ++i) total_px += (long long)src_h[idx[base + i]] * src_w[idx[base + i]];
       int rows = 64;
       {
-        const long long want_tasks = (long long)h->num_sms * 48 * 3;
+        const long long want_tasks = (long long)h->num_sms * 24 * 3;
         while (rows > 8 && total_px / ((long long)rows * kStripPx) < want_tasks) rows >>= 1;
       }
       p.rows_per_task = rows;
