@@ -258,12 +258,21 @@ def run_gpu(args) -> None:
     # argument arrays are built once per input set: the per-step host work is three foreign calls
     batches = [_native.FrameBatch(list(fs.unbind(0))) for fs in frame_sets]
 
+    # one prepared b200va_tick per input set: letterbox on the caller's stream, decode -> NMS -> tracker on the
+    # library's second stream (schedule 1: the letterbox starts when the decode kernel is done and overlaps
+    # NMS + tracker, so the two HBM-bound kernels never share the bus); fork and join are inside every step
+    plans = [h.plan_tick(frames=batches[k], net_out=net_in, dst_hw=IN_HW, fmt=_native.OUT_F32_RGB_NCHW,
+                         head=head_sets[k], metas=metas, conf_thr=CONF, iou_thr=IOU, filter_conf=CONF, dets=dets,
+                         slots=slots, tracker_cfg=(TRK["max_age"], TRK["min_hits"], TRK["max_iou_distance"]),
+                         tracks=tracks, schedule=args.schedule) for k in range(N_SETS)]
+
     def step(k, ev=None):
-        if ev is not None:
-            ev[0].record()
+        plan = plans[k % N_SETS]
+        plan.set_events(*(ev if ev is not None else (None, None)))
+        h.tick(plan)
+
+    def serial_step(k):
         h.preprocess(batches[k % N_SETS], IN_HW, _native.OUT_F32_RGB_NCHW, out=net_in)
-        if ev is not None:
-            ev[1].record()
         h.postprocess(head_sets[k % N_SETS], metas, CONF, IOU, filter_conf=CONF, out=dets)
         h.tracker_update(slots, dets, TRK["max_age"], TRK["min_hits"], TRK["max_iou_distance"], out=tracks)
 
@@ -273,6 +282,9 @@ def run_gpu(args) -> None:
     h.poll_status()
     clocks = ClockSampler(local)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in kev:  # torch creates the CUDA event on its first record; the library records it afterwards
+        a.record()
+        b.record()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = h.launch_count
     barrier()
@@ -301,6 +313,22 @@ def run_gpu(args) -> None:
     k1_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     n_tracks = int(tracks["count"].sum().item())
     h.poll_status()
+    # the same three calls one after the other on one stream (what three separate C-ABI calls cost)
+    for k in range(8):
+        serial_step(k)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for k in range(args.steps):
+        serial_step(k)
+    s1.record()
+    barrier()
+    serial_ms = s0.elapsed_time(s1)
+    if world > 1:
+        tmax = torch.tensor([serial_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        serial_ms = float(tmax.item())
+    serial_value = world * STREAMS * args.steps / (serial_ms * 1e-3)
     # the same tick replayed from CUDA graphs (one per input set): host launch cost out of the picture
     graph_value = None
     try:
@@ -311,7 +339,8 @@ def run_gpu(args) -> None:
             for k in range(N_SETS):
                 gr = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gr, stream=side):
-                    step(k)
+                    plans[k].set_events(None, None)
+                    h.tick(plans[k])
                 graphs.append(gr)
         torch.cuda.current_stream().wait_stream(side)
         for k in range(8):
@@ -430,6 +459,9 @@ def run_gpu(args) -> None:
                                "additionally builds every Detection / Track object"},
                 "gpu_launches": int(launches), "launches_per_step": launches / max(args.steps, 1),
                 "breakdown_ms": breakdown,
+                "schedule": {0: "serial", 1: "letterbox after decode, overlapping NMS + tracker (b200va_tick)",
+                             2: "letterbox overlapping decode + NMS + tracker (b200va_tick)"}[args.schedule],
+                "value_three_serial_calls": round(serial_value, 1),
                 "value_cuda_graph_replay": round(graph_value, 1) if isinstance(graph_value, float) else graph_value,
                 "clocks": clocks.summary(), "tracks_alive": n_tracks}
         if world == 1 and not args.no_cpu:
@@ -448,6 +480,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--schedule", type=int, default=1, choices=[0, 1, 2],
+                    help="b200va_tick schedule: 0 serial, 1 letterbox after decode (default), 2 fully parallel")
     ap.add_argument("--no-cpu", action="store_true", help="skip the single-core CPU sample")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -263,6 +263,55 @@ B200VA_API int b200va_tracker_reset(b200va_handle h, int stream_slot, void* stre
 /* Set the next id of the shared counter (default 1, like itertools.count(1)). */
 B200VA_API int b200va_tracker_set_next_id(b200va_handle h, int64_t next_id, void* stream);
 
+/* ---- one tick: pre ‖ post + track ------------------------------------------------------
+ * The batched form of StreamWorker._process_packet's GPU work (pipeline.py:172-188) for callers that
+ * pipeline around the detector: the letterbox of the frames that go to the detector NEXT and the
+ * head post-process + tracker update of the head the detector produced LAST are independent, so
+ * one call runs them as two branches -- the letterbox on `stream`, decode -> NMS -> tracker on an
+ * internal high-priority stream forked from and joined back into `stream` (capturable in a CUDA
+ * graph).  Every pointer has the meaning it has in b200va_preprocess / b200va_postprocess /
+ * b200va_tracker_update; results are identical to calling those three in sequence.
+ * schedule: 0 = serial on `stream`; 1 = the letterbox starts when the decode kernel has finished and
+ *           overlaps NMS + tracker (the two HBM-bound kernels never share the bus); 2 = the letterbox
+ *           overlaps the whole post-process branch.
+ * ev_pre_begin / ev_pre_end: optional cudaEvent_t recorded on `stream` around the letterbox launch. */
+typedef struct b200va_tick_args {
+  /* b200va_preprocess */
+  const uint8_t* const* frames;
+  const int* src_h;
+  const int* src_w;
+  const int64_t* src_pitch;
+  int batch;
+  const uint8_t* const* roi_masks;
+  void* net_out;
+  int dst_h, dst_w, out_format;
+  b200va_letterbox* meta_out;
+  /* b200va_postprocess */
+  const float* head;
+  int layout, head_batch, channels, anchors;
+  const b200va_letterbox* meta;
+  double conf_thr, iou_thr;
+  const int32_t* classes;
+  int n_classes, score_mode, nms_mode;
+  double filter_conf_thr_f64;
+  int use_filter;
+  const b200va_dets* dets;
+  /* b200va_tracker_update */
+  const int* stream_slots;
+  int trk_batch, max_dets;
+  const double* det_scale;
+  const uint8_t* skip;
+  const b200va_tracker_cfg* trk_cfg;
+  const int64_t* id_base;
+  const b200va_tracks* tracks;
+  int32_t* new_counts;
+  /* scheduling */
+  int schedule;
+  void* ev_pre_begin;
+  void* ev_pre_end;
+} b200va_tick_args;
+B200VA_API int b200va_tick(b200va_handle h, const b200va_tick_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

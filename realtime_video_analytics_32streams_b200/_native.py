@@ -59,12 +59,48 @@ class Tracks(C.Structure):
                 ("age", C.c_void_p), ("hits", C.c_void_p), ("count", C.c_void_p)]
 
 
+class TickArgs(C.Structure):
+    """``b200va_tick_args`` (include/b200va.h)."""
+
+    _fields_ = [
+        ("frames", C.POINTER(C.c_void_p)), ("src_h", C.POINTER(C.c_int)), ("src_w", C.POINTER(C.c_int)),
+        ("src_pitch", C.POINTER(C.c_int64)), ("batch", C.c_int), ("roi_masks", C.POINTER(C.c_void_p)),
+        ("net_out", C.c_void_p), ("dst_h", C.c_int), ("dst_w", C.c_int), ("out_format", C.c_int),
+        ("meta_out", C.POINTER(Letterbox)),
+        ("head", C.c_void_p), ("layout", C.c_int), ("head_batch", C.c_int), ("channels", C.c_int), ("anchors", C.c_int),
+        ("meta", C.POINTER(Letterbox)), ("conf_thr", C.c_double), ("iou_thr", C.c_double),
+        ("classes", C.POINTER(C.c_int32)), ("n_classes", C.c_int), ("score_mode", C.c_int), ("nms_mode", C.c_int),
+        ("filter_conf_thr_f64", C.c_double), ("use_filter", C.c_int), ("dets", C.POINTER(Dets)),
+        ("stream_slots", C.POINTER(C.c_int)), ("trk_batch", C.c_int), ("max_dets", C.c_int),
+        ("det_scale", C.POINTER(C.c_double)), ("skip", C.POINTER(C.c_uint8)), ("trk_cfg", C.POINTER(TrackerCfg)),
+        ("id_base", C.POINTER(C.c_int64)), ("tracks", C.POINTER(Tracks)), ("new_counts", C.c_void_p),
+        ("schedule", C.c_int), ("ev_pre_begin", C.c_void_p), ("ev_pre_end", C.c_void_p),
+    ]
+
+
+SCHEDULE_SERIAL, SCHEDULE_PRE_AFTER_DECODE, SCHEDULE_PRE_PARALLEL = 0, 1, 2
+
+
+class TickPlan:
+    """A fully prepared ``b200va_tick`` call: the argument block and everything it points to are
+    built once, so a tick costs the host one foreign-function call."""
+
+    def __init__(self, args: "TickArgs", keep: tuple):
+        self.args = args
+        self._keep = keep  # owners of every pointer inside `args`
+
+    def set_events(self, begin=None, end=None) -> None:
+        """Optional (already recorded once) ``torch.cuda.Event`` pair around the letterbox launch."""
+        self.args.ev_pre_begin = C.c_void_p(begin.cuda_event) if begin is not None else None
+        self.args.ev_pre_end = C.c_void_p(end.cuda_event) if end is not None else None
+
+
 EXPORTS = (
     "b200va_version", "b200va_error_string", "b200va_create", "b200va_destroy", "b200va_last_error",
     "b200va_launch_count", "b200va_poll_status", "b200va_letterbox_meta", "b200va_preprocess",
     "b200va_resize_linear_u8", "b200va_roi_rasterize", "b200va_apply_mask", "b200va_motion",
     "b200va_postprocess", "b200va_tracker_update", "b200va_tracker_update_f64", "b200va_tracker_reset",
-    "b200va_tracker_set_next_id", "b200va_upload_frames", "b200va_dfl_decode",
+    "b200va_tracker_set_next_id", "b200va_upload_frames", "b200va_dfl_decode", "b200va_tick",
 )
 
 _lib = None
@@ -110,6 +146,7 @@ def load_library() -> C.CDLL:
     lib.b200va_upload_frames.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip, ip, i64p, i64p, C.c_int, C.c_int,
                                          C.c_int, C.c_int, i64p, vp]
     lib.b200va_dfl_decode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, ip, C.POINTER(C.c_float), C.c_int, vp, vp]
+    lib.b200va_tick.argtypes = [vp, C.POINTER(TickArgs), vp]
     lib.b200va_tracker_reset.argtypes = [vp, C.c_int, vp]
     lib.b200va_tracker_set_next_id.argtypes = [vp, C.c_int64, vp]
     for name in EXPORTS:
@@ -414,6 +451,79 @@ class Handle:
                                                        skip_arr, C.byref(cfg), idb, C.byref(ts),
                                                        C.c_void_p(out["new_count"].data_ptr()), self._stream()))
         return out
+
+    # -- one tick: letterbox || decode + NMS + tracker -----------------------------------------
+    def plan_tick(self, frames=None, net_out=None, dst_hw=(640, 640), fmt: int = OUT_F32_RGB_NCHW, roi_masks=None,
+                  head=None, metas=None, conf_thr: float = 0.25, iou_thr: float = 0.45, classes=None, layout=None,
+                  filter_conf: Optional[float] = None, dets=None, score_mode: int = SCORE_REF_COMPAT,
+                  nms_mode: int = NMS_AGNOSTIC, slots=None, tracker_cfg=None, det_scale=None, skip=None,
+                  tracks=None, schedule: int = SCHEDULE_PRE_AFTER_DECODE) -> TickPlan:
+        """Prepare a ``b200va_tick``: the letterbox of ``frames`` into ``net_out`` and the post-process
+        of ``head`` into ``dets`` followed by the tracker update of ``slots`` into ``tracks``.  Either
+        half may be omitted.  ``tracker_cfg`` = (max_age, min_hits, max_iou_distance)."""
+        t = self.torch
+        a = TickArgs()
+        keep = []
+        if frames is not None:
+            fb = self._batch(frames, roi_masks)
+            dh, dw = int(dst_hw[0]), int(dst_hw[1])
+            dtype = {OUT_F32_RGB_NCHW: t.float32, OUT_F16_RGB_NCHW: t.float16}.get(fmt, t.uint8)
+            shape = (fb.n, dh, dw, 3) if fmt == OUT_U8_BGR_NHWC else (fb.n, 3, dh, dw)
+            if net_out is None or tuple(net_out.shape) != shape or net_out.dtype != dtype or not net_out.is_contiguous():
+                raise ValueError("plan_tick: `net_out` must be a contiguous tensor of the letterbox output shape / dtype")
+            a.frames, a.src_h, a.src_w, a.src_pitch, a.batch = fb.ptrs, fb.hs, fb.ws, fb.pitch, fb.n
+            a.roi_masks = fb.mask_ptrs
+            a.net_out, a.dst_h, a.dst_w, a.out_format, a.meta_out = net_out.data_ptr(), dh, dw, fmt, fb.metas
+            keep += [fb, net_out]
+        if head is not None:
+            if not (head.is_cuda and head.dtype == t.float32 and head.dim() == 3 and head.is_contiguous()):
+                raise ValueError("head must be a contiguous CUDA float32 tensor [B, C, A] or [B, A, C]")
+            b, d1, d2 = head.shape
+            if layout is None:
+                layout = HEAD_CHANNEL_MAJOR if (d1 != 0 and d1 < d2) else HEAD_ANCHOR_MAJOR
+            channels, anchors = (d1, d2) if layout == HEAD_CHANNEL_MAJOR else (d2, d1)
+            marr = metas if isinstance(metas, C.Array) else (Letterbox * max(b, 1))(*metas)
+            cls_arr = (C.c_int32 * len(classes))(*[int(c) for c in classes]) if classes else None
+            if dets is None:
+                dets = self.alloc_dets(b)
+            ds = self._dets_struct(dets)
+            a.head, a.layout, a.head_batch, a.channels, a.anchors = head.data_ptr(), layout, b, channels, anchors
+            a.meta, a.conf_thr, a.iou_thr = marr, float(conf_thr), float(iou_thr)
+            a.classes, a.n_classes = cls_arr, len(classes) if classes else 0
+            a.score_mode, a.nms_mode = int(score_mode), int(nms_mode)
+            a.filter_conf_thr_f64 = float(filter_conf) if filter_conf is not None else 0.0
+            a.use_filter = 1 if filter_conf is not None else 0
+            a.dets = C.pointer(ds)
+            keep += [head, marr, cls_arr, dets, ds]
+        if slots is not None:
+            if dets is None or tracker_cfg is None:
+                raise ValueError("plan_tick: the tracker half needs `dets` and `tracker_cfg`")
+            b = len(slots)
+            if tracks is None:
+                tracks = self.alloc_tracks(b)
+            if not a.dets:
+                ds = self._dets_struct(dets)
+                a.dets = C.pointer(ds)
+                keep.append(ds)
+            cfg = TrackerCfg(int(tracker_cfg[0]), int(tracker_cfg[1]), float(tracker_cfg[2]))
+            slot_arr = slots if isinstance(slots, C.Array) else _int_array(slots)
+            ts = Tracks(tracks["track_id"].data_ptr(), tracks["cls"].data_ptr(), tracks["conf"].data_ptr(),
+                        tracks["bbox_xyxy"].data_ptr(), tracks["age"].data_ptr(), tracks["hits"].data_ptr(),
+                        tracks["count"].data_ptr())
+            sc = (C.c_double * b)(*[float(v) for v in det_scale]) if det_scale is not None else None
+            skip_arr = (C.c_uint8 * b)(*[1 if s else 0 for s in skip]) if skip is not None else None
+            a.stream_slots, a.trk_batch, a.max_dets = slot_arr, b, int(dets["conf"].shape[1])
+            a.det_scale, a.skip, a.trk_cfg, a.id_base = sc, skip_arr, C.pointer(cfg), None
+            a.tracks, a.new_counts = C.pointer(ts), tracks["new_count"].data_ptr()
+            keep += [slot_arr, ts, sc, skip_arr, cfg, tracks, dets]
+        a.schedule = int(schedule)
+        plan = TickPlan(a, tuple(keep))
+        plan.dets, plan.tracks = dets, tracks
+        return plan
+
+    def tick(self, plan: TickPlan) -> None:
+        """Run a prepared tick on the current stream (results land in the plan's buffers)."""
+        self._check(self.lib.b200va_tick(self._h, C.byref(plan.args), self._stream()))
 
     def tracker_reset(self, slot: int) -> None:
         self._check(self.lib.b200va_tracker_reset(self._h, int(slot), self._stream()))

@@ -4,6 +4,7 @@
 
 int postprocess_configure(b200va_ctx* h);  // postprocess.cu
 int preprocess_configure(b200va_ctx* h);   // preprocess.cu
+int filters_configure(b200va_ctx* h);      // filters.cu
 
 extern "C" int b200va_version(void) { return B200VA_VERSION; }
 
@@ -52,8 +53,16 @@ static int create_impl(b200va_ctx* h) {
   if (rc) return rc;
   rc = postprocess_configure(h);
   if (rc) return rc;
+  rc = filters_configure(h);
+  if (rc) return rc;
   rc = tracker_state_create(h);
   if (rc) return rc;
+  int prio_lo = 0, prio_hi = 0;
+  CUDA_TRY(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CUDA_TRY(h, cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_decoded, cudaEventDisableTiming));
   CUDA_TRY(h, cudaDeviceSynchronize());
   return B200VA_OK;
 }
@@ -85,6 +94,10 @@ extern "C" int b200va_destroy(b200va_handle h) {
     cudaDeviceSynchronize();
     tracker_state_destroy(h);
     tap_cache_destroy(h);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_decoded) cudaEventDestroy(h->ev_decoded);
     if (h->cand_key) cudaFree(h->cand_key);
     if (h->cand_box) cudaFree(h->cand_box);
     if (h->cand_cls) cudaFree(h->cand_cls);
@@ -103,7 +116,7 @@ extern "C" int64_t b200va_launch_count(b200va_handle h) { return h ? h->launches
 
 extern "C" int b200va_poll_status(b200va_handle h, void* stream) {
   if (!h) return B200VA_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = (cudaStream_t)stream;
   int32_t flags[FLAG_COUNT];

@@ -36,7 +36,7 @@ struct b200va_ctx {
   int num_sms = 0;
   std::string last_error;
   std::atomic<int64_t> launches{0};
-  std::mutex mu;
+  std::recursive_mutex mu;  // recursive: b200va_tick holds it while calling the per-step entry points
 
   // ---- post-process scratch (device), all [max_batch, max_candidates] ----
   unsigned long long* cand_key = nullptr;  // (score bits << 32) | anchor index
@@ -50,6 +50,10 @@ struct b200va_ctx {
   void* roi_scratch = nullptr;  // device, ROI_SCRATCH_BYTES
   // ---- tracker ----
   TrackerState* tracker = nullptr;
+  // ---- b200va_tick: second stream for the post-process + tracker branch ----
+  cudaStream_t side_stream = nullptr;    // non-blocking, highest priority (its 32-CTA kernels slot in first)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_decoded = nullptr;
+  cudaEvent_t hook_after_decode = nullptr;  // when set, b200va_postprocess records it right after the decode launch
   // ---- developer phase timing (only written by builds with -DB200VA_PHASE_TIMING) ----
   long long* dbg = nullptr;  // device int64[DBG_SLOTS]
 };
@@ -139,6 +143,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(

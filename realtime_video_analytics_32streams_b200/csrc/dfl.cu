@@ -95,7 +95,7 @@ extern "C" int b200va_dfl_decode(b200va_handle h, const float* raw, int batch, i
                                  const int* level_hw, const float* level_stride, int n_levels, float* out,
                                  void* stream) {
   if (!h) return B200VA_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   REQUIRE(h, raw && out && level_hw && level_stride, "NULL argument");
   REQUIRE(h, batch >= 0 && num_classes >= 0 && reg_max >= 1 && reg_max <= 64, "bad head geometry");

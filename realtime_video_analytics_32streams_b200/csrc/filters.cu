@@ -458,19 +458,218 @@ __global__ void __launch_bounds__(kMotionWarps * 32, 3) k_motion(const __grid_co
   const int x0 = (task % strips) * kStripPx;
   const int yb = (task / strips) * p.rows_per_task;
   const int ye = min(H, yb + p.rows_per_task);
-  uint8_t* const raw_base = &s_raw[warp][0][0];
-  uint8_t* const msk_base = &s_msk[MASK ? warp : 0][0][0];
-  const bool simple = f.fast && x0 + kStripPx <= W && W >= 4 && H >= 4;
-  if (simple) motion_task<MASK, true>(p, f, frame0, task, x0, yb, ye, raw_base, msk_base);
-  else motion_task<MASK, false>(p, f, frame0, task, x0, yb, ye, raw_base, msk_base);
+  motion_task<MASK, false>(p, f, frame0, task, x0, yb, ye, &s_raw[warp][0][0], &s_msk[MASK ? warp : 0][0][0]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Tile kernel: the motion gate for 16-byte aligned frames (width a multiple of 16, at least 4 x 4)
+// -- every real video format.  Same arithmetic as motion_task at about half the instructions:
+//   * a CTA owns up to 8 adjacent 256-pixel strips x rows_per_task rows.  A ninth warp feeds the TMA
+//     engine: per image row ONE cp.async.bulk each for the tile's BGR bytes, its ROI flags and the
+//     previous blurred gray of the row that becomes final, into a 5-stage ring guarded by full /
+//     empty mbarriers.  The eight compute warps never issue a global load and never wait for the
+//     previous-gray read (36 % of all stall samples in the per-warp cp.async version).
+//   * gray = two 16x8-bit dot products per pixel (IDP.2A) straight from the packed BGR words, no
+//     funnel shifts to isolate a pixel; the coefficients are doubled so the gray byte lands in
+//     bits 16..23 and one PRMT packs two pixels.
+//   * the two halo pixels on either side of a lane's 8 pixels are read from the staged row (the
+//     strips of a tile are contiguous in shared memory): no shuffles, no edge lanes.
+//   * rounding + packing of the vertical pass is one PRMT; |diff| > 25 is three logic ops per four
+//     pixels.
+// ------------------------------------------------------------------------------------------
+constexpr int kTileStrips = 8;
+constexpr int kTileRaw = 16 + kTileStrips * 3 * kStripPx + 16;  // bytes [-16, 6160) of the tile's row piece
+constexpr int kTileMsk = 16 + kTileStrips * kStripPx + 16;
+constexpr int kTilePrev = kTileStrips * kStripPx;
+constexpr int kTileStage = kTileRaw + kTileMsk + kTilePrev;  // 10304, a multiple of 16
+constexpr int kTileStages = 5;                               // = the row-loop unroll factor
+constexpr int kTileThreads = (kTileStrips + 1) * 32;
+constexpr int kTileSmem = kTileStages * kTileStage + 2 * kTileStages * 8;
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// per byte: bit 7 set where the byte is non-zero
+__device__ __forceinline__ uint32_t nonzero_msb4(uint32_t m) { return ((m & 0x7f7f7f7fu) + 0x7f7f7f7fu) | m; }
+
+// doubled BGR2GRAY coefficients as 16-bit pairs for dp2a: 2*3735, 2*19235, 2*9798
+constexpr uint32_t kBG = 7470u | (38470u << 16), kR0 = 19596u, k0B = 7470u << 16, kGR = 38470u | (19596u << 16);
+constexpr uint32_t kRnd = 32768u;  // gray = (2*sum + 2*16384) >> 16 = (sum + 16384) >> 15
+
+// grays (in bits 16..23) of the pixels packed at byte phase 0 / 3 / 6 / 9 of consecutive words
+__device__ __forceinline__ uint32_t gray_ph0(uint32_t w0) { return __dp2a_hi(kR0, w0, __dp2a_lo(kBG, w0, kRnd)); }
+__device__ __forceinline__ uint32_t gray_ph3(uint32_t w0, uint32_t w1) { return __dp2a_lo(kGR, w1, __dp2a_hi(k0B, w0, kRnd)); }
+__device__ __forceinline__ uint32_t gray_ph6(uint32_t w1, uint32_t w2) { return __dp2a_lo(kR0, w2, __dp2a_hi(kBG, w1, kRnd)); }
+__device__ __forceinline__ uint32_t gray_ph9(uint32_t w2) { return __dp2a_hi(kGR, w2, __dp2a_lo(k0B, w2, kRnd)); }
+
+template <bool MASK>
+__global__ void __launch_bounds__(kTileThreads, 3) k_motion_tile(const __grid_constant__ MotionParams p) {
+  extern __shared__ __align__(16) uint8_t s_tile[];
+  uint64_t* const full = reinterpret_cast<uint64_t*>(s_tile + kTileStages * kTileStage);
+  uint64_t* const empty = full + kTileStages;
+  const MotionFrame& f = p.f[blockIdx.y];
+  const int W = f.w, H = f.h;
+  const int tiles_x = (W + kTileStrips * kStripPx - 1) / (kTileStrips * kStripPx);
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int yb = ty * p.rows_per_task;
+  if (yb >= H) return;
+  const int ye = min(H, yb + p.rows_per_task);
+  const int tile_x0 = tx * kTileStrips * kStripPx;
+  const int tile_w = min(W - tile_x0, kTileStrips * kStripPx);
+  const int n_warps = (tile_w + kStripPx - 1) / kStripPx;  // compute warps with at least one pixel
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool has_prev = f.has_prev != 0;
+  const int r_first = yb - 2;
+  const int nrows = ye - yb + 4;  // rows yb-2 .. ye+1 (reflected at the image border)
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kTileStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], (uint32_t)n_warps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kTileStrips) {
+    // ---- producer: one lane drives the TMA engine ----
+    if (lane != 0) return;
+    const int raw_lo = max(0, 3 * tile_x0 - 16), raw_hi = min(3 * W, 3 * (tile_x0 + tile_w) + 16);
+    const int msk_lo = max(0, tile_x0 - 16), msk_hi = min(W, tile_x0 + tile_w + 16);
+    const uint32_t raw_dst = (uint32_t)(raw_lo - (3 * tile_x0 - 16)), raw_n = (uint32_t)(raw_hi - raw_lo);
+    const uint32_t msk_dst = (uint32_t)(kTileRaw + msk_lo - (tile_x0 - 16)), msk_n = (uint32_t)(msk_hi - msk_lo);
+    const uint8_t* const src0 = f.src + raw_lo;
+    const uint8_t* const mask0 = MASK ? f.mask + msk_lo : nullptr;
+    const uint8_t* const prev0 = has_prev ? f.prev + tile_x0 : nullptr;
+    const long long pitch = f.pitch;
+    for (int k = 0; k < nrows; ++k) {
+      const int stage = k % kTileStages, use = k / kTileStages;
+      if (use > 0) mbar_wait(&empty[stage], (uint32_t)(use - 1) & 1u);
+      const int r = r_first + k;
+      const int rr = r < 0 ? -r : (r >= H ? 2 * H - 2 - r : r);
+      uint8_t* st = s_tile + stage * kTileStage;
+      const bool want_prev = has_prev && k >= 4;  // row r - 2 becomes final when row r has been consumed
+      mbar_expect_tx(&full[stage], raw_n + (MASK ? msk_n : 0u) + (want_prev ? (uint32_t)tile_w : 0u));
+      bulk_g2s(st + raw_dst, src0 + (long long)rr * pitch, raw_n, &full[stage]);
+      if (MASK) bulk_g2s(st + msk_dst, mask0 + (size_t)rr * W, msk_n, &full[stage]);
+      if (want_prev) bulk_g2s(st + kTileRaw + kTileMsk, prev0 + (size_t)(r - 2) * W, (uint32_t)tile_w, &full[stage]);
+    }
+    return;
+  }
+  if (warp >= n_warps) return;
+
+  // ---- compute warps: 8 pixels per lane ----
+  const int x0 = tile_x0 + warp * kStripPx;
+  const int xl = x0 + 8 * lane;
+  const bool live = xl < W;                       // W is a multiple of 8: a lane is all inside or all outside
+  const bool left_reflect = xl == 0, right_reflect = xl + 8 == W;
+  const int raw_off = 16 + 3 * (warp * kStripPx + 8 * lane);          // byte of the lane's first pixel
+  const int msk_off = kTileRaw + 16 + warp * kStripPx + 8 * lane;
+  const int prv_off = kTileRaw + kTileMsk + warp * kStripPx + 8 * lane;
+  uint8_t* out_ptr = f.next + (size_t)yb * W + xl;
+
+  uint32_t ring[5][4];
+#pragma unroll
+  for (int a = 0; a < 5; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) ring[a][b] = 0;
+  int changed = 0;
+  uint32_t parity = 0;
+
+  for (int k0 = 0; k0 < nrows; k0 += 5) {
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      const int k = k0 + u;
+      if (k >= nrows) break;
+      mbar_wait(&full[u], parity);
+      const uint8_t* st = s_tile + u * kTileStage;
+
+      // ---- gray of pixels xl-2 .. xl+9 as pairs: L | P[0..3] | R ----
+      uint32_t P[4], L, R;
+      {
+        const uint2* q = reinterpret_cast<const uint2*>(st + raw_off - 8);
+        const uint2 h0 = q[0], a = q[1], b = q[2], c = q[3], h1 = q[4];
+        L = prmt(gray_ph6(h0.x, h0.y), gray_ph9(h0.y), 0x7632u);       // bytes -6 -5 -4 | -3 -2 -1
+        P[0] = prmt(gray_ph0(a.x), gray_ph3(a.x, a.y), 0x7632u);
+        P[1] = prmt(gray_ph6(a.y, b.x), gray_ph9(b.x), 0x7632u);
+        P[2] = prmt(gray_ph0(b.y), gray_ph3(b.y, c.x), 0x7632u);
+        P[3] = prmt(gray_ph6(c.x, c.y), gray_ph9(c.y), 0x7632u);
+        R = prmt(gray_ph0(h1.x), gray_ph3(h1.x, h1.y), 0x7632u);       // bytes 24 25 26 | 27 28 29
+      }
+      if (MASK) {  // pixels outside the ROI are black (bitwise_and with the mask): gray 0
+        const uint2 mk = *reinterpret_cast<const uint2*>(st + msk_off);
+        const uint32_t m0 = nonzero_msb4(mk.x), m1 = nonzero_msb4(mk.y);
+        P[0] &= prmt(m0, 0u, 0x9988u);  // selector bit 3: replicate the selected byte's msb
+        P[1] &= prmt(m0, 0u, 0xbbaau);
+        P[2] &= prmt(m1, 0u, 0x9988u);
+        P[3] &= prmt(m1, 0u, 0xbbaau);
+        const uint32_t ml = nonzero_msb4((uint32_t) * reinterpret_cast<const uint16_t*>(st + msk_off - 2));
+        const uint32_t mr = nonzero_msb4((uint32_t) * reinterpret_cast<const uint16_t*>(st + msk_off + 8));
+        L &= prmt(ml, 0u, 0x9988u);
+        R &= prmt(mr, 0u, 0x9988u);
+      }
+      // BORDER_REFLECT_101: g[-2] = g[2], g[-1] = g[1];  g[W] = g[W-2], g[W+1] = g[W-3]
+      if (left_reflect) L = prmt(P[1], P[0], 0x7610u);
+      if (right_reflect) R = prmt(P[3], P[2], 0x7610u);
+      // ---- horizontal [1 4 6 4 1] on pairs: h_k = P[k-1] + P[k+1] + 4 (Q[k-1] + Q[k]) + 6 P[k], Q[k] = (g[2k+1], g[2k+2]) ----
+      {
+        const uint32_t Qm = __funnelshift_r(L, P[0], 16), Q0 = __funnelshift_r(P[0], P[1], 16),
+                       Q1 = __funnelshift_r(P[1], P[2], 16), Q2 = __funnelshift_r(P[2], P[3], 16),
+                       Q3 = __funnelshift_r(P[3], R, 16);
+        ring[u][0] = L + P[1] + 4u * (Qm + Q0) + 6u * P[0];
+        ring[u][1] = P[0] + P[2] + 4u * (Q0 + Q1) + 6u * P[1];
+        ring[u][2] = P[1] + P[3] + 4u * (Q1 + Q2) + 6u * P[2];
+        ring[u][3] = P[2] + R + 4u * (Q2 + Q3) + 6u * P[3];
+      }
+      if (k >= 4) {  // output row yb + k - 4: its five inputs are in the ring
+        uint32_t v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          v[c] = ring[(u + 1) % 5][c] + ring[u][c] + 4u * (ring[(u + 2) % 5][c] + ring[(u + 4) % 5][c]) +
+                 6u * ring[(u + 3) % 5][c] + 0x00800080u;
+        // (v + 128) >> 8 of both halves of two pairs = bytes 1 and 3 of each word
+        const uint32_t o0 = prmt(v[0], v[1], 0x7531u), o1 = prmt(v[2], v[3], 0x7531u);
+        if (has_prev) {
+          const uint2 pv = *reinterpret_cast<const uint2*>(st + prv_off);
+          const uint32_t d0 = __vabsdiffu4(o0, pv.x), d1 = __vabsdiffu4(o1, pv.y);
+          // per byte d > 25  <=>  bit 7 of ((d & 0x7f) + 102) | d
+          const uint32_t t0 = (((d0 & 0x7f7f7f7fu) + 0x66666666u) | d0) & 0x80808080u;
+          const uint32_t t1 = (((d1 & 0x7f7f7f7fu) + 0x66666666u) | d1) & 0x80808080u;
+          if (live) changed += __popc(t0) + __popc(t1);
+        }
+        if (live) *reinterpret_cast<uint2*>(out_ptr) = make_uint2(o0, o1);
+        out_ptr += W;
+      }
+      __syncwarp();  // every lane has read this stage
+      if (lane == 0) mbar_arrive(&empty[u]);
+    }
+    parity ^= 1u;
+  }
+  changed = warp_sum(changed);
+  if (lane == 0) {
+    if (has_prev) {
+      if (changed) atomicAdd(p.changed + f.out_idx, changed);
+    } else if (blockIdx.x == 0 && warp == 0) {
+      p.changed[f.out_idx] = -1;
+    }
+  }
 }
 
 }  // namespace
 
+int filters_configure(b200va_ctx* h) {  // called by b200va_create on the handle's device
+  CUDA_TRY(h, cudaFuncSetAttribute(k_motion_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_motion_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+  return B200VA_OK;
+}
+
 extern "C" int b200va_roi_rasterize(b200va_handle h, const int32_t* pts, const int* poly_sizes, int n_polys, int height,
                                     int width, uint8_t* mask_out, void* stream) {
   if (!h) return B200VA_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = (cudaStream_t)stream;
   REQUIRE(h, mask_out && height > 0 && width > 0, "bad mask geometry %dx%d", width, height);
@@ -573,7 +772,7 @@ extern "C" int b200va_roi_rasterize(b200va_handle h, const int32_t* pts, const i
 extern "C" int b200va_apply_mask(b200va_handle h, const uint8_t* src, int64_t src_pitch, const uint8_t* mask, int height,
                                  int width, uint8_t* dst, int64_t dst_pitch, void* stream) {
   if (!h) return B200VA_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   REQUIRE(h, src && mask && dst && height > 0 && width > 0, "bad arguments");
   REQUIRE(h, src_pitch >= 3ll * width && dst_pitch >= 3ll * width, "pitch smaller than 3*width");
@@ -592,61 +791,79 @@ extern "C" int b200va_motion(b200va_handle h, const uint8_t* const* frames, cons
                              const uint8_t* const* prev_gray, uint8_t* const* next_gray, const int* has_prev,
                              int32_t* changed_out, void* stream) {
   if (!h) return B200VA_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = (cudaStream_t)stream;
   REQUIRE(h, frames && src_h && src_w && next_gray && has_prev && changed_out, "NULL argument");
   REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
   if (batch == 0) return B200VA_OK;
   CUDA_TRY(h, cudaMemsetAsync(changed_out, 0, sizeof(int32_t) * batch, st));
-  // frames with and without an ROI mask go to separate launches (the mask is a template switch);
-  // `changed` is indexed by the original batch position
-  std::vector<int> order[2];
-  for (int b = 0; b < batch; ++b) order[(roi_masks && roi_masks[b]) ? 1 : 0].push_back(b);
-  for (int with_mask = 0; with_mask < 2; ++with_mask) {
-    const std::vector<int>& idx = order[with_mask];
+  // frames with and without an ROI mask go to separate launches (the mask is a template switch), and so do
+  // 16-byte aligned frames (tile kernel, TMA-fed) and everything else (generic kernel); `changed` is indexed
+  // by the original batch position
+  std::vector<int> order[4];
+  std::vector<long long> pitches(batch);
+  for (int b = 0; b < batch; ++b) {
+    REQUIRE(h, frames[b] && next_gray[b], "frame %d: NULL frame or state buffer", b);
+    REQUIRE(h, src_h[b] > 0 && src_w[b] > 0, "frame %d has bad size", b);
+    REQUIRE(h, !has_prev[b] || (prev_gray && prev_gray[b]), "frame %d: has_prev without a previous buffer", b);
+    REQUIRE(h, !has_prev[b] || prev_gray[b] != next_gray[b], "frame %d: prev_gray and next_gray alias", b);
+    pitches[b] = src_pitch ? src_pitch[b] : 3ll * src_w[b];
+    REQUIRE(h, pitches[b] >= 3ll * src_w[b], "frame %d: pitch smaller than 3*width", b);
+    const bool with_mask = roi_masks && roi_masks[b];
+    const bool aligned = (src_w[b] % 16 == 0) && ((uintptr_t)frames[b] % 16 == 0) && (pitches[b] % 16 == 0) &&
+                         ((uintptr_t)next_gray[b] % 16 == 0) && (!has_prev[b] || (uintptr_t)prev_gray[b] % 16 == 0) &&
+                         (!with_mask || (uintptr_t)roi_masks[b] % 16 == 0);
+    const bool tile = aligned && src_w[b] >= 4 && src_h[b] >= 4;
+    order[(with_mask ? 1 : 0) + (tile ? 2 : 0)].push_back(b);
+  }
+  for (int kind = 0; kind < 4; ++kind) {
+    const int with_mask = kind & 1;
+    const bool tile = (kind & 2) != 0;
+    const std::vector<int>& idx = order[kind];
     for (size_t base = 0; base < idx.size(); base += B200VA_LAUNCH_FRAMES) {
       const int n = (int)std::min<size_t>(B200VA_LAUNCH_FRAMES, idx.size() - base);
       MotionParams p;
       memset(&p, 0, sizeof(p));
-      int max_tasks = 0;
-      // rows per warp task: tall enough that the 4 halo rows stay a small overhead, short enough
-      // that the launch fills the SMs several times over
+      // rows per task: tall enough that the 4 halo rows stay a small overhead, short enough that the
+      // launch fills the SMs several times over
       long long total_px = 0;
       for (int i = 0; i < n; ++i) total_px += (long long)src_h[idx[base + i]] * src_w[idx[base + i]];
       int rows = 64;
       {
-        const long long want_tasks = (long long)h->num_sms * 24 * 3;
-        while (rows > 8 && total_px / ((long long)rows * kStripPx) < want_tasks) rows >>= 1;
+        const long long px_per_task = tile ? (long long)kTileStrips * kStripPx : kStripPx;
+        const long long want_tasks = tile ? (long long)h->num_sms * 3 * 5 : (long long)h->num_sms * 24 * 3;
+        while (rows > 8 && total_px / ((long long)rows * px_per_task) < want_tasks) rows >>= 1;
       }
       p.rows_per_task = rows;
+      int max_tasks = 0;
       for (int i = 0; i < n; ++i) {
         const int b = idx[base + i];
         MotionFrame& f = p.f[i];
-        REQUIRE(h, frames[b] && next_gray[b], "frame %d: NULL frame or state buffer", b);
-        REQUIRE(h, src_h[b] > 0 && src_w[b] > 0, "frame %d has bad size", b);
-        REQUIRE(h, !has_prev[b] || (prev_gray && prev_gray[b]), "frame %d: has_prev without a previous buffer", b);
-        REQUIRE(h, !has_prev[b] || prev_gray[b] != next_gray[b], "frame %d: prev_gray and next_gray alias", b);
         f.src = frames[b];
         f.mask = with_mask ? roi_masks[b] : nullptr;
         f.prev = has_prev[b] ? prev_gray[b] : nullptr;
         f.next = next_gray[b];
-        f.pitch = src_pitch ? src_pitch[b] : 3ll * src_w[b];
-        REQUIRE(h, f.pitch >= 3ll * src_w[b], "frame %d: pitch smaller than 3*width", b);
+        f.pitch = pitches[b];
         f.h = src_h[b];
         f.w = src_w[b];
         f.has_prev = has_prev[b] ? 1 : 0;
         f.out_idx = b;
-        f.fast = (f.w % 16 == 0) && ((uintptr_t)f.src % 16 == 0) && (f.pitch % 16 == 0) && ((uintptr_t)f.next % 16 == 0) &&
-                 (!f.prev || (uintptr_t)f.prev % 16 == 0) && (!f.mask || (uintptr_t)f.mask % 16 == 0);
-        const int strips = (f.w + kStripPx - 1) / kStripPx;
+        f.fast = tile ? 1 : 0;  // generic kernel: 0 selects its byte loaders
+        const int per_row = tile ? (f.w + kTileStrips * kStripPx - 1) / (kTileStrips * kStripPx) : (f.w + kStripPx - 1) / kStripPx;
         const int row_tasks = (f.h + rows - 1) / rows;
-        if (strips * row_tasks > max_tasks) max_tasks = strips * row_tasks;
+        if (per_row * row_tasks > max_tasks) max_tasks = per_row * row_tasks;
       }
       p.changed = changed_out;
-      dim3 grid((max_tasks + kMotionWarps - 1) / kMotionWarps, n);
-      if (with_mask) k_motion<true><<<grid, kMotionWarps * 32, 0, st>>>(p, 0);
-      else k_motion<false><<<grid, kMotionWarps * 32, 0, st>>>(p, 0);
+      if (tile) {
+        dim3 grid(max_tasks, n);
+        if (with_mask) k_motion_tile<true><<<grid, kTileThreads, kTileSmem, st>>>(p);
+        else k_motion_tile<false><<<grid, kTileThreads, kTileSmem, st>>>(p);
+      } else {
+        dim3 grid((max_tasks + kMotionWarps - 1) / kMotionWarps, n);
+        if (with_mask) k_motion<true><<<grid, kMotionWarps * 32, 0, st>>>(p, 0);
+        else k_motion<false><<<grid, kMotionWarps * 32, 0, st>>>(p, 0);
+      }
       LAUNCH_CHECK(h);
     }
   }

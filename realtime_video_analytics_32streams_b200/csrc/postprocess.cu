@@ -558,7 +558,7 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
                                   const int32_t* classes, int n_classes, int score_mode, int nms_mode,
                                   double filter_conf_thr_f64, int use_filter, const b200va_dets* out, void* stream) {
   if (!h) return B200VA_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = (cudaStream_t)stream;
   REQUIRE(h, head && meta && out && out->bbox_xyxy && out->conf && out->cls && out->count, "NULL argument");
@@ -623,6 +623,8 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
       k_decode_am<<<grid, 256, 0, st>>>(p, base);
     }
     LAUNCH_CHECK(h);
+    // b200va_tick, schedule 1: the letterbox on the caller's stream starts when the (HBM-bound) decode is done
+    if (h->hook_after_decode && base + n >= batch) CUDA_TRY(h, cudaEventRecord(h->hook_after_decode, st));
 
     NmsParams q;
     q.cand_key = h->cand_key;

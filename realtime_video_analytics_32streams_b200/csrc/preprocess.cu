@@ -600,7 +600,7 @@ extern "C" int b200va_preprocess(b200va_handle h, const uint8_t* const* frames, 
                                  const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks, void* out,
                                  int dst_h, int dst_w, int out_format, b200va_letterbox* meta_out, void* stream) {
   if (!h) return B200VA_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   REQUIRE(h, frames && src_h && src_w && out, "NULL argument");
   REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
@@ -625,7 +625,7 @@ extern "C" int b200va_resize_linear_u8(b200va_handle h, const uint8_t* const* fr
                                        const uint8_t* const* roi_masks, uint8_t* const* dst, const int* dst_h,
                                        const int* dst_w, void* stream) {
   if (!h) return B200VA_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   REQUIRE(h, frames && src_h && src_w && dst && dst_h && dst_w, "NULL argument");
   REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
@@ -700,7 +700,7 @@ extern "C" int b200va_upload_frames(b200va_handle h, const uint8_t* const* host_
                                     const int64_t* dev_pitch, int batch, int dst_h, int dst_w, int rows_mode,
                                     int64_t* bytes_copied, void* stream) {
   if (!h) return B200VA_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = (cudaStream_t)stream;
   REQUIRE(h, host_frames && dev_frames && src_h && src_w, "NULL argument");

@@ -664,7 +664,7 @@ extern "C" int b200va_tracker_update(b200va_handle h, const int* stream_slots, i
                                      const b200va_tracker_cfg* cfg, const int64_t* id_base, const b200va_tracks* out,
                                      int32_t* new_counts, void* stream) {
   if (!h) return B200VA_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   REQUIRE(h, dets && dets->bbox_xyxy && dets->conf && dets->cls && dets->count, "NULL detections");
   REQUIRE(h, max_dets > 0, "max_dets must be positive");
@@ -683,7 +683,7 @@ extern "C" int b200va_tracker_update_f64(b200va_handle h, const int* stream_slot
                                          const int64_t* id_base, const b200va_tracks* out, int32_t* new_counts,
                                          void* stream) {
   if (!h) return B200VA_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   REQUIRE(h, dets && dets->bbox_xyxy && dets->conf && dets->cls && dets->count, "NULL detections");
   REQUIRE(h, max_dets > 0, "max_dets must be positive");
@@ -699,7 +699,7 @@ extern "C" int b200va_tracker_update_f64(b200va_handle h, const int* stream_slot
 
 extern "C" int b200va_tracker_reset(b200va_handle h, int stream_slot, void* stream) {
   if (!h) return B200VA_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   REQUIRE(h, stream_slot >= 0 && stream_slot < h->cfg.max_streams, "stream slot %d outside [0, %d)", stream_slot, h->cfg.max_streams);
   k_tracker_reset<<<1, 1, 0, (cudaStream_t)stream>>>(*h->tracker, stream_slot);
@@ -709,7 +709,7 @@ extern "C" int b200va_tracker_reset(b200va_handle h, int stream_slot, void* stre
 
 extern "C" int b200va_tracker_set_next_id(b200va_handle h, int64_t next_id, void* stream) {
   if (!h) return B200VA_ERR_INVALID;
-  std::lock_guard<std::mutex> lock(h->mu);
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   k_tracker_set_next<<<1, 1, 0, (cudaStream_t)stream>>>(*h->tracker, (long long)next_id);
   LAUNCH_CHECK(h);
