@@ -276,27 +276,61 @@ def run_gpu(args) -> None:
         h.postprocess(head_sets[k % N_SETS], metas, CONF, IOU, filter_conf=CONF, out=dets)
         h.tracker_update(slots, dets, TRK["max_age"], TRK["min_hits"], TRK["max_iou_distance"], out=tracks)
 
+    # the tick is captured once per input set in a CUDA graph (fork / join included): the timed loop replays
+    # graphs, except that every SAMPLE_EVERY-th step runs the same tick eagerly with an event pair around the
+    # letterbox launch -- the live kernel timing the roofline is computed from
+    SAMPLE_EVERY = 10
     for k in range(max(args.warmup, 3)):
         step(k)
     barrier()
     h.poll_status()
+    graphs, kernels_per_graph = None, 0
+    if not args.no_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graphs = []
+        l0 = h.launch_count
+        with torch.cuda.stream(side):
+            for k in range(N_SETS):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side):
+                    plans[k].set_events(None, None)
+                    h.tick(plans[k])
+                graphs.append(gr)
+        torch.cuda.current_stream().wait_stream(side)
+        kernels_per_graph = (h.launch_count - l0) // N_SETS
+        for k in range(max(args.warmup, 3)):
+            graphs[k % N_SETS].replay()
+        barrier()
+
+    def timed_step(k, ev):
+        if graphs is None or ev is not None:
+            step(k, ev)
+            return 0
+        graphs[k % N_SETS].replay()
+        return kernels_per_graph
+
     clocks = ClockSampler(local)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    n_samples = (args.steps + SAMPLE_EVERY - 1) // SAMPLE_EVERY if graphs is not None else args.steps
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_samples)]
     for a, b in kev:  # torch creates the CUDA event on its first record; the library records it afterwards
         a.record()
         b.record()
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = h.launch_count
+    replayed = 0
     barrier()
     clocks.start()
     start.record()
     for k in range(args.steps):
-        step(args.warmup + k, kev[k])
+        sample = graphs is None or k % SAMPLE_EVERY == 0
+        replayed += timed_step(args.warmup + k, kev[k // SAMPLE_EVERY if graphs is not None else k] if sample else None)
     end.record()
     barrier()
     clocks.stop()
-    launches = h.launch_count - launches0
+    launches = h.launch_count - launches0 + replayed
     ms = start.elapsed_time(end)
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     # per-call device time (separate untimed loop, events around each C-ABI call)
     bev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(20)]
     for k, e in enumerate(bev):
@@ -310,57 +344,29 @@ def run_gpu(args) -> None:
     torch.cuda.synchronize()
     breakdown = {name: round(float(np.median([e[i].elapsed_time(e[i + 1]) for e in bev])), 4)
                  for i, name in enumerate(("preprocess", "postprocess(decode+sort_nms)", "tracker_update"))}
-    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     n_tracks = int(tracks["count"].sum().item())
     h.poll_status()
-    # the same three calls one after the other on one stream (what three separate C-ABI calls cost)
-    for k in range(8):
-        serial_step(k)
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for k in range(args.steps):
-        serial_step(k)
-    s1.record()
-    barrier()
-    serial_ms = s0.elapsed_time(s1)
-    if world > 1:
-        tmax = torch.tensor([serial_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        serial_ms = float(tmax.item())
-    serial_value = world * STREAMS * args.steps / (serial_ms * 1e-3)
-    # the same tick replayed from CUDA graphs (one per input set): host launch cost out of the picture
-    graph_value = None
-    try:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        graphs = []
-        with torch.cuda.stream(side):
-            for k in range(N_SETS):
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=side):
-                    plans[k].set_events(None, None)
-                    h.tick(plans[k])
-                graphs.append(gr)
-        torch.cuda.current_stream().wait_stream(side)
+
+    def timed_variant(fn):
         for k in range(8):
-            graphs[k % N_SETS].replay()
+            fn(k)
         barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
         for k in range(args.steps):
-            graphs[k % N_SETS].replay()
-        g1.record()
+            fn(k)
+        s1.record()
         barrier()
-        gms = g0.elapsed_time(g1)
+        v_ms = s0.elapsed_time(s1)
         if world > 1:
-            tmax = torch.tensor([gms], dtype=torch.float64, device=dev)
+            tmax = torch.tensor([v_ms], dtype=torch.float64, device=dev)
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            gms = float(tmax.item())
-        graph_value = world * STREAMS * args.steps / (gms * 1e-3)
-        h.poll_status()
-    except Exception as exc:  # pragma: no cover - informational only
-        graph_value = f"unavailable: {type(exc).__name__}"
+            v_ms = float(tmax.item())
+        return world * STREAMS * args.steps / (v_ms * 1e-3)
+
+    # informational: the same tick launched eagerly every step, and as three separate C-ABI calls on one stream
+    eager_value = timed_variant(lambda k: step(k))
+    serial_value = timed_variant(serial_step)
     if world > 1:
         tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -461,8 +467,11 @@ def run_gpu(args) -> None:
                 "breakdown_ms": breakdown,
                 "schedule": {0: "serial", 1: "letterbox after decode, overlapping NMS + tracker (b200va_tick)",
                              2: "letterbox overlapping decode + NMS + tracker (b200va_tick)"}[args.schedule],
-                "value_three_serial_calls": round(serial_value, 1),
-                "value_cuda_graph_replay": round(graph_value, 1) if isinstance(graph_value, float) else graph_value,
+                "launch": ("CUDA graph replay of the prepared b200va_tick (one graph per input set); every "
+                           f"{SAMPLE_EVERY}th step is launched eagerly with an event pair around the letterbox kernel"
+                           if graphs is not None else "eager b200va_tick every step, event pair around the letterbox kernel"),
+                "letterbox_samples": len(kev),
+                "value_eager_tick": round(eager_value, 1), "value_three_serial_calls": round(serial_value, 1),
                 "clocks": clocks.summary(), "tracks_alive": n_tracks}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_single_core_sample()
@@ -482,6 +491,7 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--schedule", type=int, default=1, choices=[0, 1, 2],
                     help="b200va_tick schedule: 0 serial, 1 letterbox after decode (default), 2 fully parallel")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the single-core CPU sample")
     args = ap.parse_args()
     if args.impl == "reference":

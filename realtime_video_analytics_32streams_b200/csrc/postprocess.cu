@@ -608,6 +608,9 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
     p.conf_thr = (float)conf_thr;  // NEP-50 weak scalar: compared in float32 (detector.py:312)
     if (layout == B200VA_HEAD_CHANNEL_MAJOR) {
       // 16-byte loads need every channel row (A floats) and the tensor base 16-byte aligned
+      // (splitting the class rows over 4 or 8 warps per anchor group -- every load of a thread in flight at once, merge in
+      // shared memory -- measured 22 us / 36 us against 20 us: the kernel is bound by its fixed launch + ramp + tail
+      // cost of ~5 us on top of the 14 us the bytes need, not by the depth of the per-thread load chain)
       // (a TMA-staged variant -- all C rows of a 128-anchor tile bulk-copied to shared memory -- measured
       // 24.6 us against 21.5 us for this register version on [32,84,8400]: the 512-byte row pieces at a
       // 33.6 KB stride bound both; block sizes 64..256 are equivalent, 512 is slower)

@@ -563,7 +563,13 @@ static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* 
       p.mask_stride = with_mask ? ((max_w + 127) & ~127) : 0;
       p.rows_per_stage = all_single ? 1 : 2;
       const size_t per_stage = (size_t)p.rows_per_stage * ((size_t)p.row_stride + p.mask_stride);
-      int stages = (int)((size_t)kLetterboxSmemMax / per_stage);
+      // ring depth: up to kMaxStages, but shallow enough that several CTAs share an SM -- with whole 4K rows a
+      // 4-deep ring is 90-120 KB and leaves ONE 160-thread CTA per SM (7.6 % warps active, 0.59 of HBM peak)
+      // (measured, 32 x 4K + ROI: 133 us with the deepest ring, 84 us = 0.94 of peak with a 32-56 KB budget)
+      const size_t budget = (size_t)48 * 1024;
+      int stages = (int)(budget / per_stage);
+      if (stages < 2) stages = 2;
+      if ((size_t)stages * per_stage > (size_t)kLetterboxSmemMax) stages = (int)((size_t)kLetterboxSmemMax / per_stage);
       if (stages > kMaxStages) stages = kMaxStages;
       REQUIRE(h, stages >= 1, "source rows of %d bytes do not fit in shared memory", max_row);
       p.stages = stages;
