@@ -263,6 +263,40 @@ B200VA_API int b200va_tracker_reset(b200va_handle h, int stream_slot, void* stre
 /* Set the next id of the shared counter (default 1, like itertools.count(1)). */
 B200VA_API int b200va_tracker_set_next_id(b200va_handle h, int64_t next_id, void* stream);
 
+/* ---- Ultralytics semantics (additive) ---------------------------------
+ * What `YOLO(...).predict(frame, conf, iou, classes, half)` -- the call UltralyticsDetector.predict makes
+ * (detector.py:147-155) -- does around the model forward.  ultralytics==8.3.209 (pylock.toml:1432-1433) is not
+ * part of /root/reference and not installed: these entry points restate its published algorithm (LetterBox,
+ * ops.non_max_suppression, ops.scale_boxes); the NMS step is pinned against torchvision.ops.nms, the rest
+ * against torch CPU arithmetic -- PARITY UNPINNED against ultralytics itself.
+ *
+ * Geometry: new size = round(size * r), r = min(dst_h/h, dst_w/w); padding split round(d/2 -+ 0.1);
+ * auto_pad != 0 pads only the remainder modulo `stride` (the rect shape predict() uses for one image), so the
+ * network input is out_h x out_w <= dst_h x dst_w.  out->scale = r. */
+B200VA_API int b200va_letterbox_meta_ultralytics(int src_h, int src_w, int dst_h, int dst_w, int auto_pad, int stride,
+                                                 b200va_letterbox* out, int* out_h, int* out_w);
+/* b200va_preprocess with caller-supplied geometry (geom[i].new_h/new_w/pad_top/pad_left; e.g. from
+ * b200va_letterbox_meta_ultralytics); every frame is written into a dst_h x dst_w canvas.  Same kernels, same
+ * interpolation, pad value and output formats.  (torch CUDA computes `im /= 255` as im * float32(1/255), which
+ * is exactly B200VA_OUT_F32_RGB_NCHW.) */
+B200VA_API int b200va_preprocess_geom(b200va_handle h, const uint8_t* const* frames, const int* src_h, const int* src_w,
+                                      const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks,
+                                      const b200va_letterbox* geom, void* out, int dst_h, int dst_w, int out_format,
+                                      void* stream);
+/* ops.non_max_suppression + ops.scale_boxes for a decoded head [B, 4 + nc, A] / [B, A, 4 + nc]:
+ * score_k = head[4 + k], candidate iff max_k > conf_thr (strict, float32); xywh -> xyxy in network-input pixels;
+ * NMS on boxes shifted by class * 7680 in float32 (agnostic != 0: no shift) with torchvision's test
+ * inter / (area_i + area_j - inter) > iou_thr (float32 IoU against the double threshold, CPU kernel), equal
+ * scores keep the lower anchor first (stable descending sort); the first max_det survivors are un-letterboxed
+ * with gain = min(in_h/h, in_w/w), pad = round((in - size * gain) / 2 - 0.1), true division by float32(gain),
+ * clamp to [0, w] x [0, h].  max_nms (30000) is never reached: candidates are bounded by max_candidates.
+ * in_h / in_w: shape of the network input the head was computed from.  filter_*: as in b200va_postprocess. */
+B200VA_API int b200va_postprocess_ultralytics(b200va_handle h, const float* head, int layout, int batch, int channels,
+                                              int anchors, const int* src_h, const int* src_w, int in_h, int in_w,
+                                              double conf_thr, double iou_thr, const int32_t* classes, int n_classes,
+                                              int agnostic, int max_det, double filter_conf_thr_f64, int use_filter,
+                                              const b200va_dets* out, void* stream);
+
 /* ---- one tick: pre ‖ post + track ------------------------------------------------------
  * The batched form of StreamWorker._process_packet's GPU work (pipeline.py:172-188) for callers that
  * pipeline around the detector: the letterbox of the frames that go to the detector NEXT and the

@@ -101,6 +101,7 @@ EXPORTS = (
     "b200va_resize_linear_u8", "b200va_roi_rasterize", "b200va_apply_mask", "b200va_motion",
     "b200va_postprocess", "b200va_tracker_update", "b200va_tracker_update_f64", "b200va_tracker_reset",
     "b200va_tracker_set_next_id", "b200va_upload_frames", "b200va_dfl_decode", "b200va_tick",
+    "b200va_letterbox_meta_ultralytics", "b200va_preprocess_geom", "b200va_postprocess_ultralytics",
 )
 
 _lib = None
@@ -147,6 +148,13 @@ def load_library() -> C.CDLL:
                                          C.c_int, C.c_int, i64p, vp]
     lib.b200va_dfl_decode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, ip, C.POINTER(C.c_float), C.c_int, vp, vp]
     lib.b200va_tick.argtypes = [vp, C.POINTER(TickArgs), vp]
+    lib.b200va_letterbox_meta_ultralytics.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                      C.POINTER(Letterbox), ip, ip]
+    lib.b200va_preprocess_geom.argtypes = [vp, C.POINTER(vp), ip, ip, i64p, C.c_int, C.POINTER(vp), C.POINTER(Letterbox),
+                                           vp, C.c_int, C.c_int, C.c_int, vp]
+    lib.b200va_postprocess_ultralytics.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, C.c_int,
+                                                   C.c_double, C.c_double, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int,
+                                                   C.c_double, C.c_int, C.POINTER(Dets), vp]
     lib.b200va_tracker_reset.argtypes = [vp, C.c_int, vp]
     lib.b200va_tracker_set_next_id.argtypes = [vp, C.c_int64, vp]
     for name in EXPORTS:
@@ -162,6 +170,16 @@ def letterbox_meta(src_h: int, src_w: int, dst_h: int, dst_w: int) -> Letterbox:
     if rc != OK:
         raise B200VAError(rc, f"bad letterbox geometry {src_w}x{src_h} -> {dst_w}x{dst_h}")
     return m
+
+
+def letterbox_meta_ultralytics(src_h: int, src_w: int, dst_h: int, dst_w: int, auto: bool = False, stride: int = 32):
+    """Host-only: ultralytics ``LetterBox`` geometry -> (Letterbox, out_h, out_w); needs no GPU."""
+    m, oh, ow = Letterbox(), C.c_int(0), C.c_int(0)
+    rc = load_library().b200va_letterbox_meta_ultralytics(src_h, src_w, dst_h, dst_w, 1 if auto else 0, int(stride),
+                                                          C.byref(m), C.byref(oh), C.byref(ow))
+    if rc != OK:
+        raise B200VAError(rc, f"bad letterbox geometry {src_w}x{src_h} -> {dst_w}x{dst_h}")
+    return m, oh.value, ow.value
 
 
 def _ptr_array(ptrs: Sequence[Optional[int]]):
@@ -401,6 +419,50 @@ class Handle:
             cls_arr, len(classes) if classes else 0, int(score_mode), int(nms_mode),
             float(filter_conf) if filter_conf is not None else 0.0, 1 if filter_conf is not None else 0,
             C.byref(ds), self._stream()))
+        return out
+
+    # -- Ultralytics semantics ---------------------------------------------
+    def preprocess_geom(self, frames, geoms, dst_hw, fmt: int = OUT_F32_RGB_NCHW, roi_masks=None, out=None):
+        """Letterbox with caller-supplied geometry (``geoms``: one ``Letterbox`` per frame, e.g. from
+        ``letterbox_meta_ultralytics``) into a ``dst_hw`` canvas."""
+        t = self.torch
+        fb = self._batch(frames, roi_masks)
+        b = fb.n
+        dh, dw = int(dst_hw[0]), int(dst_hw[1])
+        dtype = {OUT_F32_RGB_NCHW: t.float32, OUT_F16_RGB_NCHW: t.float16}.get(fmt, t.uint8)
+        shape = (b, dh, dw, 3) if fmt == OUT_U8_BGR_NHWC else (b, 3, dh, dw)
+        if out is None:
+            out = t.empty(shape, dtype=dtype, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
+            raise ValueError("preprocess_geom: `out` has the wrong shape / dtype / layout")
+        garr = geoms if isinstance(geoms, C.Array) else (Letterbox * max(b, 1))(*geoms)
+        if b:
+            self._check(self.lib.b200va_preprocess_geom(self._h, fb.ptrs, fb.hs, fb.ws, fb.pitch, b, fb.mask_ptrs, garr,
+                                                        C.c_void_p(out.data_ptr()), dh, dw, fmt, self._stream()))
+        return out
+
+    def postprocess_ultralytics(self, head, frame_hw, in_hw, conf_thr: float = 0.25, iou_thr: float = 0.45, classes=None,
+                                agnostic: bool = False, max_det: int = 300, layout=None,
+                                filter_conf: Optional[float] = None, out=None):
+        """``ops.non_max_suppression`` + ``ops.scale_boxes`` for ``head`` [B, 4 + nc, A] (or [B, A, 4 + nc]).
+        ``frame_hw``: (h, w) of every original frame; ``in_hw``: the network-input shape the head came from."""
+        t = self.torch
+        if not (head.is_cuda and head.dtype == t.float32 and head.dim() == 3 and head.is_contiguous()):
+            raise ValueError("head must be a contiguous CUDA float32 tensor [B, C, A] or [B, A, C]")
+        b, d1, d2 = head.shape
+        if layout is None:
+            layout = HEAD_CHANNEL_MAJOR if (d1 != 0 and d1 < d2) else HEAD_ANCHOR_MAJOR
+        channels, anchors = (d1, d2) if layout == HEAD_CHANNEL_MAJOR else (d2, d1)
+        if out is None:
+            out = self.alloc_dets(b)
+        cls_arr = (C.c_int32 * len(classes))(*[int(c) for c in classes]) if classes else None
+        ds = self._dets_struct(out)
+        self._check(self.lib.b200va_postprocess_ultralytics(
+            self._h, C.c_void_p(head.data_ptr()), layout, b, channels, anchors, _int_array([hw[0] for hw in frame_hw]),
+            _int_array([hw[1] for hw in frame_hw]), int(in_hw[0]), int(in_hw[1]), float(conf_thr), float(iou_thr), cls_arr,
+            len(classes) if classes else 0, 1 if agnostic else 0, int(max_det),
+            float(filter_conf) if filter_conf is not None else 0.0, 1 if filter_conf is not None else 0, C.byref(ds),
+            self._stream()))
         return out
 
     # -- a14 --------------------------------------------------------------------------------

@@ -14,6 +14,8 @@
 //       parallel -- and ordered emission with the float64 re-threshold folded in.
 #include <cuda_fp16.h>
 
+#include <cmath>
+
 #include "common.cuh"
 
 namespace {
@@ -34,6 +36,8 @@ struct PostParams {
   int cls0;     // first class channel: 5 (column 4 is objectness) or 4 (scores = pred[:, 4:])
   int use_obj;  // multiply class scores by column 4
   float conf_thr;
+  int ultra;    // Ultralytics semantics: strict `>` threshold, boxes stay in network-input pixels, equal scores keep
+                // the lower anchor first (torchvision's stable descending sort)
 };
 static_assert(sizeof(PostParams) <= 4000, "kernel parameter block too large");
 
@@ -47,10 +51,22 @@ __device__ __forceinline__ float unorder_bits(uint32_t u) {
   return __uint_as_float(b);
 }
 
-// detector.py:352-359 then :340-350, float32, NumPy operation order.
-__device__ __forceinline__ float4 decode_box(float cx, float cy, float w, float h, const PostFrame& f) {
+// ultralytics scale_boxes + clip_boxes (utils/ops.py): un-pad, true division by float32(gain), clamp to [0, w] x [0, h]
+// (torch CPU semantics; torch CUDA multiplies by the float32 reciprocal instead).
+__device__ __forceinline__ float4 ultra_scale_box(float4 b, const PostFrame& f) {
+  b.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.x, f.left), f.scale), 0.f), f.xmax);
+  b.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.y, f.top), f.scale), 0.f), f.ymax);
+  b.z = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.z, f.left), f.scale), 0.f), f.xmax);
+  b.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.w, f.top), f.scale), 0.f), f.ymax);
+  return b;
+}
+
+// detector.py:352-359 then :340-350, float32, NumPy operation order.  raw = true stops after xywh -> xyxy
+// (ultralytics xywh2xyxy does the same two operations; its NMS runs on network-input pixels).
+__device__ __forceinline__ float4 decode_box(float cx, float cy, float w, float h, const PostFrame& f, bool raw = false) {
   const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);  // w / 2.0 is exact either way
   float x1 = __fsub_rn(cx, hw), y1 = __fsub_rn(cy, hh), x2 = __fadd_rn(cx, hw), y2 = __fadd_rn(cy, hh);
+  if (raw) return make_float4(x1, y1, x2, y2);
   x1 = __fdiv_rn(__fsub_rn(x1, f.left), f.scale);
   x2 = __fdiv_rn(__fsub_rn(x2, f.left), f.scale);
   y1 = __fdiv_rn(__fsub_rn(y1, f.top), f.scale);
@@ -72,7 +88,8 @@ __device__ __forceinline__ void emit_candidate(const PostParams& p, int frame, i
                                                float4 box) {
   if (pos >= p.max_cand) return;  // overflow is flagged by k_sort_nms from the raw count
   const size_t o = (size_t)frame * p.max_cand + pos;
-  p.cand_key[o] = ((unsigned long long)order_bits(conf) << 32) | ((unsigned long long)(uint32_t)anchor << 14) |
+  const uint32_t tie = p.ultra ? (0x3ffffu - (uint32_t)anchor) : (uint32_t)anchor;  // descending sort: which anchor first on equal scores
+  p.cand_key[o] = ((unsigned long long)order_bits(conf) << 32) | ((unsigned long long)tie << 14) |
                   (unsigned long long)(uint32_t)pos;
   p.cand_box[o] = box;
   p.cand_cls[o] = cls;
@@ -173,7 +190,8 @@ __global__ void __launch_bounds__(64) k_decode_cm(const __grid_constant__ PostPa
     }
 #pragma unroll
     for (int k = 0; k < VEC; ++k)
-      if (!((nan_seen >> k) & 1u) && (best[k] >= p.conf_thr) && class_allowed(p, cls[k])) pass |= 1u << k;
+      if (!((nan_seen >> k) & 1u) && (p.ultra ? best[k] > p.conf_thr : best[k] >= p.conf_thr) && class_allowed(p, cls[k]))
+        pass |= 1u << k;
   }
   // warp-aggregated compaction: one atomic per warp
   const int mine = __popc(pass);
@@ -198,7 +216,7 @@ __global__ void __launch_bounds__(64) k_decode_cm(const __grid_constant__ PostPa
 #pragma unroll
     for (int k = 0; k < VEC; ++k)
       if (pass & (1u << k)) {
-        emit_candidate(p, frame, pos, a0 + k, best[k], cls[k], decode_box(cx[k], cy[k], w[k], h[k], p.f[frame]));
+        emit_candidate(p, frame, pos, a0 + k, best[k], cls[k], decode_box(cx[k], cy[k], w[k], h[k], p.f[frame], p.ultra != 0));
         ++pos;
       }
   }
@@ -240,9 +258,10 @@ __global__ void __launch_bounds__(256) k_decode_am(const __grid_constant__ PostP
   }
   if (bad) return;
   if (lane == 0) {
-    if ((best >= p.conf_thr) && class_allowed(p, cls)) {
+    if ((p.ultra ? best > p.conf_thr : best >= p.conf_thr) && class_allowed(p, cls)) {
       const int pos = atomicAdd(p.cand_count + frame, 1);
-      emit_candidate(p, frame, pos, a, best, cls, decode_box(__ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3), p.f[frame]));
+      emit_candidate(p, frame, pos, a, best, cls,
+                     decode_box(__ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3), p.f[frame], p.ultra != 0));
     }
   }
 }
@@ -265,7 +284,14 @@ struct NmsParams {
   int use_filter;
   int class_aware;  // 0: the reference's class-agnostic NMS (detector.py:361-375); 1: suppress same class only
   long long* dbg;
+  // Ultralytics semantics (ops.non_max_suppression + scale_boxes): NMS on network-input boxes shifted by
+  // class * 7680 in float32 (0 when agnostic), torchvision's IoU test, at most max_det_cap boxes kept, then
+  // un-letterbox with f[frame]
+  int ultra, ultra_agnostic, max_det_cap;
+  double iou_thr64;
+  PostFrame f[B200VA_LAUNCH_FRAMES];
 };
+static_assert(sizeof(NmsParams) <= 4000, "kernel parameter block too large");
 
 // _iou of detector.py:469-481 in float32; returns true when box j must be suppressed by box i.
 __device__ __forceinline__ bool suppresses(const float4 a, const float4 b, float thr) {
@@ -281,9 +307,20 @@ __device__ __forceinline__ bool suppresses(const float4 a, const float4 b, float
   return !(iou <= thr);
 }
 
+// torchvision.ops.nms (csrc/ops/cpu/nms_kernel.cpp): inter / (area_i + area_j - inter) > thr, no epsilon.
+__device__ __forceinline__ bool suppresses_tv(const float4 a, const float4 b, double thr) {
+  const float x1 = fmaxf(a.x, b.x), y1 = fmaxf(a.y, b.y), x2 = fminf(a.z, b.z), y2 = fminf(a.w, b.w);
+  const float iw = fmaxf(0.f, __fsub_rn(x2, x1)), ih = fmaxf(0.f, __fsub_rn(y2, y1));
+  const float inter = __fmul_rn(iw, ih);
+  const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
+  const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return (double)iou > thr;  // NaN (0 / 0) never suppresses
+}
+
 constexpr int kNmsThreads = 1024;
 
-__global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
+__global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant__ NmsParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int frame = blockIdx.x;
   const int tid = threadIdx.x;
@@ -373,8 +410,13 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
     my_cls[k] = 0;
     if (i < n) {
       const size_t o = cbase + (keys[i] & 0x3fffull);
-      box[i] = p.cand_box[o];
+      float4 b = p.cand_box[o];
       my_cls[k] = p.cand_cls[o];
+      if (p.ultra && !p.ultra_agnostic) {  // boxes = x[:, :4] + x[:, 5:6] * max_wh, float32 (the rounding is part of the semantics)
+        const float c = __fmul_rn((float)my_cls[k], 7680.f);
+        b = make_float4(__fadd_rn(b.x, c), __fadd_rn(b.y, c), __fadd_rn(b.z, c), __fadd_rn(b.w, c));
+      }
+      box[i] = b;
       scl[i] = (uint16_t)my_cls[k];
     }
   }
@@ -382,8 +424,9 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
 
   PHASE_STAMP(p.dbg, 19);
   const bool aware = p.class_aware != 0;
+  const bool ultra = p.ultra != 0;
   const float thr = p.iou_thr;
-  const bool thr_nonneg = thr >= 0.f;
+  const bool thr_nonneg = ultra ? p.iou_thr64 >= 0.0 : thr >= 0.f;
   const int nchunks = (n + 63) >> 6;
 #ifdef B200VA_PHASE_TIMING
   long long acc_a = 0, acc_b = 0, acc_c = 0, t_mark = clock64();
@@ -408,7 +451,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
           if (j <= i || j >= m) continue;
           const float4 bj = box[c0 + j];
           if (thr_nonneg && (bj.z <= bi.x || bi.z <= bj.x || bj.w <= bi.y || bi.w <= bj.y)) continue;  // disjoint: IoU 0
-          if ((!aware || scl[c0 + i] == scl[c0 + j]) && suppresses(bi, bj, thr)) {
+          if ((!aware || scl[c0 + i] == scl[c0 + j]) && (ultra ? suppresses_tv(bi, bj, p.iou_thr64) : suppresses(bi, bj, thr))) {
             atomicOr(&rows[i][j >> 5], 1u << (j & 31));
             atomicOr(&rows[j][i >> 5], 1u << (i & 31));
           }
@@ -473,7 +516,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
             // disjoint boxes have intersection exactly 0 -> IoU 0 -> kept whenever thr >= 0 (four compares
             // instead of the full formula; NaN coordinates fail every compare and take the full path)
             if (thr_nonneg && (bj.z <= bi.x || bi.z <= bj.x || bj.w <= bi.y || bi.w <= bj.y)) continue;
-            if ((!aware || kcl[q] == cj) && suppresses(bi, bj, thr)) {
+            if ((!aware || kcl[q] == cj) && (ultra ? suppresses_tv(bi, bj, p.iou_thr64) : suppresses(bi, bj, thr))) {
               atomicOr(&supp[j >> 5], 1u << (j & 31));
               break;
             }
@@ -493,6 +536,32 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
 #endif
 
   PHASE_STAMP(p.dbg, 20);
+  // ultralytics: `i = i[:max_det]` on the NMS survivors, before anything else looks at them
+  if (ultra) {
+    if (tid == 0) {
+      int acc = 0;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        for (int w = 0; w < 2; ++w) {
+          uint32_t bits = keep_w[2 * ch + w];
+          const int room = p.max_det_cap - acc;
+          if (room <= 0) {
+            bits = 0u;
+          } else if (__popc(bits) > room) {
+            uint32_t kept_bits = 0u;
+            for (int r = 0; r < room; ++r) {  // keep the `room` lowest set bits
+              const uint32_t low = bits & (0u - bits);
+              kept_bits |= low;
+              bits ^= low;
+            }
+            bits = kept_bits;
+          }
+          keep_w[2 * ch + w] = bits;
+          acc += __popc(bits);
+        }
+      }
+    }
+    __syncthreads();
+  }
   // filter_detections (detector.py:99-103): float64 compare on the kept boxes only
   if (p.use_filter) {
     for (int i = tid; i < n; i += kNmsThreads) {
@@ -523,7 +592,8 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const NmsParams p) {
       const int pos = keep_off[i >> 6] + __popcll(w & ((1ull << (i & 63)) - 1ull));
       if (pos < p.max_dets) {
         const size_t o = (size_t)frame * p.max_dets + pos;
-        const float4 b = box[i];
+        float4 b = box[i];
+        if (ultra) b = ultra_scale_box(p.cand_box[cbase + (keys[i] & 0x3fffull)], p.f[frame]);  // the un-shifted box
         reinterpret_cast<float4*>(p.out_box)[o] = b;
         p.out_conf[o] = unorder_bits((uint32_t)(keys[i] >> 32));
         p.out_cls[o] = my_cls[k];
@@ -553,15 +623,28 @@ int postprocess_configure(b200va_ctx* h) {
   return B200VA_OK;
 }
 
-extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout, int batch, int channels, int anchors,
+namespace {
+struct UltraOpts {  // b200va_postprocess_ultralytics
+  const int* src_h;
+  const int* src_w;
+  int in_h, in_w, agnostic, max_det;
+};
+}  // namespace
+
+static int postprocess_impl(b200va_handle h, const float* head, int layout, int batch, int channels, int anchors,
                                   const b200va_letterbox* meta, double conf_thr, double iou_thr,
                                   const int32_t* classes, int n_classes, int score_mode, int nms_mode,
-                                  double filter_conf_thr_f64, int use_filter, const b200va_dets* out, void* stream) {
+                                  double filter_conf_thr_f64, int use_filter, const b200va_dets* out, void* stream,
+                                  const UltraOpts* ultra) {
   if (!h) return B200VA_ERR_INVALID;
   std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   cudaStream_t st = (cudaStream_t)stream;
-  REQUIRE(h, head && meta && out && out->bbox_xyxy && out->conf && out->cls && out->count, "NULL argument");
+  REQUIRE(h, head && (meta || ultra) && out && out->bbox_xyxy && out->conf && out->cls && out->count, "NULL argument");
+  if (ultra) {
+    REQUIRE(h, ultra->src_h && ultra->src_w && ultra->in_h > 0 && ultra->in_w > 0, "bad frame / input shapes");
+    REQUIRE(h, ultra->max_det >= 1, "max_det must be positive");
+  }
   REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
   REQUIRE(h, layout == B200VA_HEAD_CHANNEL_MAJOR || layout == B200VA_HEAD_ANCHOR_MAJOR, "unknown layout %d", layout);
   REQUIRE(h, score_mode == B200VA_SCORE_REF_COMPAT || score_mode == B200VA_SCORE_V8_NATIVE, "unknown score mode %d", score_mode);
@@ -581,6 +664,20 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
     PostParams p;
     memset(&p, 0, sizeof(p));
     for (int i = 0; i < n; ++i) {
+      if (ultra) {
+        // ultralytics scale_boxes (utils/ops.py): gain = min(h1/h0, w1/w0); pad = round((s1 - s0*gain)/2 - 0.1)
+        // (Python round = round-half-even = nearbyint); boxes /= gain; clamp to [0, w0] x [0, h0]
+        const int h0 = ultra->src_h[base + i], w0 = ultra->src_w[base + i];
+        REQUIRE(h, h0 > 0 && w0 > 0, "frame %d has bad size", base + i);
+        const double g0 = (double)ultra->in_h / h0, g1 = (double)ultra->in_w / w0;
+        const double gain = g0 < g1 ? g0 : g1;
+        p.f[i].left = (float)nearbyint(((double)ultra->in_w - (double)w0 * gain) / 2 - 0.1);
+        p.f[i].top = (float)nearbyint(((double)ultra->in_h - (double)h0 * gain) / 2 - 0.1);
+        p.f[i].scale = (float)gain;
+        p.f[i].xmax = (float)w0;
+        p.f[i].ymax = (float)h0;
+        continue;
+      }
       const b200va_letterbox& m = meta[base + i];
       p.f[i].left = (float)m.pad_left;
       p.f[i].top = (float)m.pad_top;
@@ -606,6 +703,7 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
     p.use_obj = (score_mode == B200VA_SCORE_REF_COMPAT && channels > 5) ? 1 : 0;
     p.cls0 = p.use_obj ? 5 : 4;
     p.conf_thr = (float)conf_thr;  // NEP-50 weak scalar: compared in float32 (detector.py:312)
+    p.ultra = ultra ? 1 : 0;
     if (layout == B200VA_HEAD_CHANNEL_MAJOR) {
       // 16-byte loads need every channel row (A floats) and the tensor base 16-byte aligned
       // (splitting the class rows over 4 or 8 warps per anchor group -- every load of a thread in flight at once, merge in
@@ -630,6 +728,7 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
     if (h->hook_after_decode && base + n >= batch) CUDA_TRY(h, cudaEventRecord(h->hook_after_decode, st));
 
     NmsParams q;
+    memset(&q, 0, sizeof(q));
     q.cand_key = h->cand_key;
     q.cand_box = h->cand_box;
     q.cand_cls = h->cand_cls;
@@ -647,8 +746,31 @@ extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout
     q.use_filter = use_filter;
     q.class_aware = nms_mode == B200VA_NMS_CLASS_AWARE;
     q.dbg = h->dbg;
+    q.ultra = ultra ? 1 : 0;
+    q.ultra_agnostic = ultra ? ultra->agnostic : 0;
+    q.max_det_cap = ultra ? ultra->max_det : 0;
+    q.iou_thr64 = iou_thr;  // torchvision's CPU kernel compares the float32 IoU with the double threshold
+    memcpy(q.f, p.f, sizeof(q.f));
     k_sort_nms<<<n, kNmsThreads, nms_smem_bytes(h->cfg.max_candidates), st>>>(q);
     LAUNCH_CHECK(h);
   }
   return B200VA_OK;
+}
+
+extern "C" int b200va_postprocess(b200va_handle h, const float* head, int layout, int batch, int channels, int anchors,
+                                  const b200va_letterbox* meta, double conf_thr, double iou_thr,
+                                  const int32_t* classes, int n_classes, int score_mode, int nms_mode,
+                                  double filter_conf_thr_f64, int use_filter, const b200va_dets* out, void* stream) {
+  return postprocess_impl(h, head, layout, batch, channels, anchors, meta, conf_thr, iou_thr, classes, n_classes, score_mode,
+                          nms_mode, filter_conf_thr_f64, use_filter, out, stream, nullptr);
+}
+
+extern "C" int b200va_postprocess_ultralytics(b200va_handle h, const float* head, int layout, int batch, int channels,
+                                              int anchors, const int* src_h, const int* src_w, int in_h, int in_w,
+                                              double conf_thr, double iou_thr, const int32_t* classes, int n_classes,
+                                              int agnostic, int max_det, double filter_conf_thr_f64, int use_filter,
+                                              const b200va_dets* out, void* stream) {
+  const UltraOpts u{src_h, src_w, in_h, in_w, agnostic ? 1 : 0, max_det};
+  return postprocess_impl(h, head, layout, batch, channels, anchors, nullptr, conf_thr, iou_thr, classes, n_classes,
+                          B200VA_SCORE_V8_NATIVE, B200VA_NMS_AGNOSTIC, filter_conf_thr_f64, use_filter, out, stream, &u);
 }

@@ -14,6 +14,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "common.cuh"
 
@@ -624,6 +625,64 @@ extern "C" int b200va_preprocess(b200va_handle h, const uint8_t* const* frames, 
   }
   return run_resample(h, frames, src_h, src_w, src_pitch, batch, roi_masks, out, nh.data(), nw.data(), pt.data(),
                       pl.data(), dst_h, dst_w, out_format, (cudaStream_t)stream);
+}
+
+// ultralytics LetterBox.__call__ (data/augment.py; scaleup = True, center = True): sizes are ROUNDED
+// (Python round = round-half-even = nearbyint), the padding is split with round(d / 2 -+ 0.1), and with
+// auto = True only the remainder modulo `stride` is padded (the "rect" shape predict() uses for a single image).
+extern "C" int b200va_letterbox_meta_ultralytics(int src_h, int src_w, int dst_h, int dst_w, int auto_pad, int stride,
+                                                 b200va_letterbox* out, int* out_h, int* out_w) {
+  if (!out || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || (auto_pad && stride <= 0)) return B200VA_ERR_INVALID;
+  const double r0 = (double)dst_h / (double)src_h, r1 = (double)dst_w / (double)src_w;
+  const double r = r0 < r1 ? r0 : r1;
+  const int new_w = (int)nearbyint((double)src_w * r), new_h = (int)nearbyint((double)src_h * r);
+  if (new_w <= 0 || new_h <= 0) return B200VA_ERR_INVALID;
+  int dwi = dst_w - new_w, dhi = dst_h - new_h;
+  if (auto_pad) {
+    dwi %= stride;  // np.mod of non-negative integers
+    dhi %= stride;
+  }
+  const double dw = dwi / 2.0, dh = dhi / 2.0;
+  const int top = (int)nearbyint(dh - 0.1), bottom = (int)nearbyint(dh + 0.1);
+  const int left = (int)nearbyint(dw - 0.1), right = (int)nearbyint(dw + 0.1);
+  out->src_h = src_h;
+  out->src_w = src_w;
+  out->new_h = new_h;
+  out->new_w = new_w;
+  out->pad_left = left;
+  out->pad_top = top;
+  out->scale = r;
+  if (out_h) *out_h = new_h + top + bottom;
+  if (out_w) *out_w = new_w + left + right;
+  return B200VA_OK;
+}
+
+extern "C" int b200va_preprocess_geom(b200va_handle h, const uint8_t* const* frames, const int* src_h, const int* src_w,
+                                      const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks,
+                                      const b200va_letterbox* geom, void* out, int dst_h, int dst_w, int out_format,
+                                      void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  REQUIRE(h, frames && src_h && src_w && out && geom, "NULL argument");
+  REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
+  REQUIRE(h, dst_h > 0 && dst_w > 0 && dst_w < 65536, "bad destination size %dx%d", dst_w, dst_h);
+  if (batch == 0) return B200VA_OK;
+  std::vector<int> nh(batch), nw(batch), pt(batch), pl(batch);
+  for (int b = 0; b < batch; ++b) {
+    const b200va_letterbox& m = geom[b];
+    REQUIRE(h, m.src_h == src_h[b] && m.src_w == src_w[b], "frame %d: geometry is for %dx%d, frame is %dx%d", b, m.src_w,
+            m.src_h, src_w[b], src_h[b]);
+    REQUIRE(h, m.new_h > 0 && m.new_w > 0 && m.pad_top >= 0 && m.pad_left >= 0 && m.pad_top + m.new_h <= dst_h &&
+                   m.pad_left + m.new_w <= dst_w,
+            "frame %d: resized %dx%d at (%d, %d) does not fit %dx%d", b, m.new_w, m.new_h, m.pad_left, m.pad_top, dst_w, dst_h);
+    nh[b] = m.new_h;
+    nw[b] = m.new_w;
+    pt[b] = m.pad_top;
+    pl[b] = m.pad_left;
+  }
+  return run_resample(h, frames, src_h, src_w, src_pitch, batch, roi_masks, out, nh.data(), nw.data(), pt.data(), pl.data(),
+                      dst_h, dst_w, out_format, (cudaStream_t)stream);
 }
 
 extern "C" int b200va_resize_linear_u8(b200va_handle h, const uint8_t* const* frames, const int* src_h,
