@@ -3,6 +3,7 @@
 Public surface (names follow the reference so call sites read the same):
 
 * ``B200Detector``   -- ``BaseDetector`` contract: ``predict(packet)``, plus ``predict_batch``.
+* ``B200UltralyticsDetector`` -- the same contract with the pre / post semantics of ``UltralyticsDetector``.
 * ``B200IouTracker`` -- ``IouTracker`` contract: ``update(stream_name, detections)``, plus ``update_batch``.
 * ``apply_roi``, ``downsample``, ``MotionFilter``, ``MotionFilterConfig`` -- ``utils/frame_filter.py``.
 * ``HotPathEngine``  -- the batched per-tick driver (``StreamWorker._process_packet`` for N streams).
@@ -16,11 +17,11 @@ fails loudly when the library is missing.  Nothing in here imports ``oracle/``.
 from .types import Detection, DetectorConfig, FramePacket, MotionFilterConfig, StreamConfig, Track, TrackerConfig
 
 __all__ = ["Detection", "DetectorConfig", "FramePacket", "FrameResult", "MotionFilterConfig", "StreamConfig", "Track",
-           "TrackerConfig", "B200Detector", "B200IouTracker", "HotPathEngine", "MotionFilter", "apply_roi",
+           "TrackerConfig", "B200Detector", "B200UltralyticsDetector", "B200IouTracker", "HotPathEngine", "MotionFilter", "apply_roi",
            "downsample", "filter_detections", "get_handle", "register_with_reference"]
 
 _LAZY = {
-    "B200Detector": "detector", "filter_detections": "detector", "B200IouTracker": "tracker",
+    "B200Detector": "detector", "B200UltralyticsDetector": "detector", "filter_detections": "detector", "B200IouTracker": "tracker",
     "HotPathEngine": "engine", "FrameResult": "engine", "MotionFilter": "frame_filter", "apply_roi": "frame_filter",
     "downsample": "frame_filter", "roi_mask": "frame_filter", "get_handle": "runtime",
     "register_with_reference": "integration",

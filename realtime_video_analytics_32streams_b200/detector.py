@@ -145,3 +145,62 @@ class B200Detector:
                                   (float(box[b, i, 0]), float(box[b, i, 1]), float(box[b, i, 2]), float(box[b, i, 3])))
                         for i in range(n)])
         return out
+
+
+class B200UltralyticsDetector(B200Detector):
+    """Drop-in for ``UltralyticsDetector`` (detector.py:106-179): what ``YOLO(...).predict(frame, conf, iou,
+    classes, half)`` does around the model forward -- ``LetterBox`` (rounded sizes; ``auto=True`` rect padding
+    for a single image, like ``predict`` on an ndarray with a PyTorch model), ``ops.non_max_suppression``
+    (strict ``>``, class-shifted boxes, ``max_det``) and ``ops.scale_boxes`` -- on the sm_100a kernels.
+    ``infer`` maps the network input ``[B, 3, h, w]`` to the decoded Detect head ``[B, 4 + nc, A]``
+    (what ``model.model(im)[0]`` returns).  Parity against ultralytics itself is unpinned (package absent);
+    see ``oracle/ultralytics_restate.py`` for what the tests pin."""
+
+    def __init__(self, config, input_hw=None, infer=None, handle=None, auto: bool = True, stride: int = 32,
+                 max_det: int = 300, agnostic: bool = False, fold_filter: bool = False):
+        super().__init__(config, input_hw=input_hw, infer=infer, handle=handle, fold_filter=fold_filter)
+        self.auto, self.stride, self.max_det, self.agnostic = bool(auto), int(stride), int(max_det), bool(agnostic)
+
+    def _geometry(self, shapes):
+        geoms, outs = [], set()
+        for h, w in shapes:
+            m, oh, ow = _native.letterbox_meta_ultralytics(int(h), int(w), self.input_hw[0], self.input_hw[1], self.auto,
+                                                           self.stride)
+            geoms.append(m)
+            outs.add((oh, ow))
+        if len(outs) != 1:
+            # LetterBox(auto=...) is only rect when every image of the batch has the same shape (same_shapes)
+            geoms = [_native.letterbox_meta_ultralytics(int(h), int(w), self.input_hw[0], self.input_hw[1], False,
+                                                        self.stride)[0] for h, w in shapes]
+            outs = {self.input_hw}
+        return geoms, next(iter(outs))
+
+    def _preprocess(self, frame, roi_mask=None):
+        dev = self._stager.upload([frame])
+        geoms, in_hw = self._geometry([dev[0].shape[:2]])
+        tensor = self.h.preprocess_geom(dev, geoms, in_hw, self._fmt, [roi_mask] if roi_mask is not None else None)
+        return tensor, {"orig_shape": tuple(int(v) for v in dev[0].shape[:2]), "in_shape": in_hw}
+
+    def _postprocess(self, predictions, packet: FramePacket, meta: dict) -> List[Detection]:
+        head = self._as_head(predictions)
+        if head.dim() == 2:
+            head = head[None]
+        dets = self._run_post_ultra(head, [meta["orig_shape"]], meta["in_shape"])
+        return self._to_detections(dets, [packet])[0]
+
+    def predict_batch_device(self, frames, roi_masks=None, dets_out=None):
+        dev = self._stager.upload(frames)
+        shapes = [tuple(int(v) for v in d.shape[:2]) for d in dev]
+        geoms, in_hw = self._geometry(shapes)
+        tensor = self.h.preprocess_geom(dev, geoms, in_hw, self._fmt, roi_masks)
+        head = self._as_head(self._infer(tensor))
+        if head.dim() != 3 or head.shape[0] != len(frames):
+            raise ValueError(f"infer returned {tuple(head.shape)} for a batch of {len(frames)}")
+        return self._run_post_ultra(head, shapes, in_hw, dets_out), geoms
+
+    def _run_post_ultra(self, head, shapes, in_hw, dets_out=None):
+        cfg = self.config
+        thr = float(cfg.confidence_threshold)
+        return self.h.postprocess_ultralytics(head, shapes, in_hw, thr, float(cfg.iou_threshold),
+                                              getattr(cfg, "classes", None) or None, self.agnostic, self.max_det,
+                                              filter_conf=thr if self.fold_filter else None, out=dets_out)

@@ -2,7 +2,8 @@
 
 The reference selects its detector by ``detector.backend`` (whitelist: config.py:155-157, dispatch:
 detector.py:54-96) and hard-codes ``IouTracker`` (pipeline.py:452).  ``register_with_reference``
-patches those three places at import time so that a YAML with ``backend: b200`` and
+patches those three places at import time so that a YAML with ``backend: b200`` (or
+``b200_ultralytics``: the Ultralytics pre / post semantics of detector.py:106-179) and
 ``tracker.type: b200_iou`` runs this package's kernels behind the reference's own pipeline, and
 swaps the frame-filter functions the pipeline imported by name (pipeline.py:33).
 INTEGRATION.md shows the equivalent two-line source change for maintainers who prefer a patch.
@@ -20,7 +21,7 @@ def register_with_reference(infer_factory: Optional[Callable] = None) -> None:
     import realtime_analytics.detector as rdet
     import realtime_analytics.pipeline as rpipe
 
-    from .detector import B200Detector
+    from .detector import B200Detector, B200UltralyticsDetector
     from .frame_filter import MotionFilter, apply_roi, downsample
     from .tracker import B200IouTracker
 
@@ -28,7 +29,7 @@ def register_with_reference(infer_factory: Optional[Callable] = None) -> None:
     orig_validate = rcfg.DetectorConfig.validate
 
     def validate(self):
-        if self.backend == "b200":
+        if self.backend in ("b200", "b200_ultralytics"):
             backend, self.backend = self.backend, "tensorrt"
             try:
                 orig_validate(self)
@@ -43,10 +44,11 @@ def register_with_reference(infer_factory: Optional[Callable] = None) -> None:
     orig_create = rdet.create_detector
 
     def create_detector(config):
-        if config.backend.lower() == "b200":
+        if config.backend.lower() in ("b200", "b200_ultralytics"):
             if infer_factory is None:
-                raise RuntimeError("backend 'b200' needs register_with_reference(infer_factory=...)")
-            return B200Detector(config, infer=infer_factory(config))
+                raise RuntimeError(f"backend '{config.backend}' needs register_with_reference(infer_factory=...)")
+            cls = B200UltralyticsDetector if config.backend.lower() == "b200_ultralytics" else B200Detector
+            return cls(config, infer=infer_factory(config))
         return orig_create(config)
 
     rdet.create_detector = create_detector

@@ -126,3 +126,35 @@ def test_postprocess_ultralytics_edge_cases(H):
     degenerate = v8_head(10, 80, A, in_hw, 10, 3)
     degenerate[2:4, :] = 0.0  # zero-area boxes: 0 / 0 IoU is NaN and never suppresses
     _compare(H, [empty, nan, degenerate], [(1080, 1920)] * 3, in_hw, conf_thr=0.25, iou_thr=0.45)
+
+
+def test_ultralytics_detector_predict_and_batch(H):
+    """B200UltralyticsDetector.predict / predict_batch = LetterBox(auto) -> infer -> NMS -> scale_boxes."""
+    import torch
+    from realtime_video_analytics_32streams_b200 import (B200UltralyticsDetector, DetectorConfig, FramePacket,
+                                                         StreamConfig)
+
+    frames = [synth.synth_frame(60 + i, 1080, 1920) for i in range(3)]
+    heads = [v8_head(700 + i, 80, 5040, (384, 640), 30, 4) for i in range(3)]
+    seen = []
+
+    def infer(tensor):
+        seen.append(tuple(tensor.shape))
+        return torch.from_numpy(np.stack(heads[:tensor.shape[0]])).cuda()
+
+    cfg = DetectorConfig(confidence_threshold=0.3, iou_threshold=0.5, classes=None)
+    det = B200UltralyticsDetector(cfg, input_hw=(640, 640), infer=infer, handle=H)
+    pkt = [FramePacket(StreamConfig(name=f"s{i}"), frames[i], 7 + i, 0.0) for i in range(3)]
+    one = det.predict(pkt[0])
+    assert seen[-1] == (1, 3, 384, 640)  # rect padding: 1080p -> 384 x 640
+    want = U.postprocess(heads[0], (384, 640), (1080, 1920), 0.3, 0.5)
+    assert [(d.class_id, d.confidence, d.bbox_xyxy) for d in one] == want
+    assert one[0].stream_name == "s0" and one[0].frame_id == 7
+    ref, _ = U.preprocess(frames[0], (640, 640), auto=True)
+    tensor, meta = det._preprocess(frames[0])
+    assert np.array_equal(tensor.cpu().numpy().view(np.uint8), ref.view(np.uint8)) and meta["in_shape"] == (384, 640)
+    many = det.predict_batch(pkt)
+    assert seen[-1] == (3, 3, 384, 640)
+    for i in range(3):
+        want = U.postprocess(heads[i], (384, 640), (1080, 1920), 0.3, 0.5)
+        assert [(d.class_id, d.confidence, d.bbox_xyxy) for d in many[i]] == want
