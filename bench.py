@@ -156,7 +156,7 @@ def _cpu_tick(args):
     return n_tracks
 
 
-def cpu_single_core_sample(budget_s: float = 12.0, n_streams: int = 4) -> dict:
+def cpu_single_core_sample(budget_s: float = 10.0, n_streams: int = 4) -> dict:
     """Bounded single-thread sample of the same workload (rank 0, N=1 only)."""
     ids = list(range(n_streams))
     _cpu_worker_init(ids, N_SETS)
@@ -166,7 +166,7 @@ def cpu_single_core_sample(budget_s: float = 12.0, n_streams: int = 4) -> dict:
     while True:
         _cpu_tick((ids, ticks + 1))
         ticks += 1
-        if time.perf_counter() - t0 > budget_s or ticks >= 200:
+        if time.perf_counter() - t0 > budget_s or ticks >= 2000:
             break
     dt = time.perf_counter() - t0
     return {"value": round(ticks * n_streams / dt, 2), "unit": "frames/s", "cores": 1, "kind": "port",

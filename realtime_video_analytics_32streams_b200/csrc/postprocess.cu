@@ -222,6 +222,113 @@ __global__ void __launch_bounds__(64) k_decode_cm(const __grid_constant__ PostPa
   }
 }
 
+// channel-major head, class rows split over the warps of a CTA -- the SMALL-BATCH variant.  k_decode_cm walks its
+// 80-odd rows in ~10 dependent rounds of loads; with a few frames per launch (4 streams per GPU when 32 streams are
+// sharded over 8 GPUs) nothing overlaps those round trips and one frame costs 12.7 us.  Here lane l of EVERY warp owns
+// the same four anchors; warp j scores rows [cls0 + j*per, cls0 + (j+1)*per) with all of its loads in flight at once
+// (a warp still reads 512 contiguous bytes per row), the partial (best, class) pairs meet in shared memory and warp 0
+// merges them in class order -- `>` keeps the first maximum, exactly np.argmax -- then compacts and emits as before.
+// At 32 frames per launch the kernel is HBM-bound and this variant is slower (22 us against 20 us): the host picks.
+template <int kSplitParts, int kSplitRows>  // kSplitRows: rows one warp holds in flight (<= kSplitParts * kSplitRows class rows)
+__global__ void __launch_bounds__(32 * kSplitParts) k_decode_cm_split(const __grid_constant__ PostParams p, int frame0) {
+  __shared__ float s_best[kSplitParts - 1][4][32];
+  __shared__ int s_cls[kSplitParts - 1][4][32];
+  __shared__ unsigned s_nan[kSplitParts - 1][32];
+  const int frame = blockIdx.y;
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int a0 = (blockIdx.x * 32 + lane) * 4;
+  const int A = p.A, C = p.C, cls0 = p.cls0;
+  const float* __restrict__ hd = p.head + (size_t)(frame0 + frame) * C * A;
+  const int per = (C - cls0 + kSplitParts - 1) / kSplitParts;
+  const int c_lo = cls0 + part * per, c_hi = min(C, c_lo + per);
+  const bool in_range = a0 < A;
+  float best[4] = {0.f, 0.f, 0.f, 0.f};
+  int cls[4] = {0, 0, 0, 0};
+  unsigned nan_seen = 0;
+  bool any = false;
+  if (in_range && c_lo < c_hi) {
+    any = true;
+    float4 obj = make_float4(1.f, 1.f, 1.f, 1.f);  // x * 1.0f is exact: scores = pred[:, 4:]
+    if (p.use_obj) obj = __ldg(reinterpret_cast<const float4*>(hd + (size_t)4 * A + a0));
+    float4 v[kSplitRows];
+#pragma unroll
+    for (int u = 0; u < kSplitRows; ++u)
+      if (c_lo + u < c_hi) v[u] = __ldg(reinterpret_cast<const float4*>(hd + (size_t)(c_lo + u) * A + a0));
+#pragma unroll
+    for (int u = 0; u < kSplitRows; ++u)
+      if (c_lo + u < c_hi) {
+        const float sc[4] = {__fmul_rn(v[u].x, obj.x), __fmul_rn(v[u].y, obj.y), __fmul_rn(v[u].z, obj.z),
+                             __fmul_rn(v[u].w, obj.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          nan_seen |= (unsigned)(sc[k] != sc[k]) << k;
+          if (u == 0 || sc[k] > best[k]) {  // np.argmax: first maximum wins
+            best[k] = sc[k];
+            cls[k] = c_lo + u - cls0;
+          }
+        }
+      }
+  }
+  if (part > 0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s_best[part - 1][k][lane] = any ? best[k] : __int_as_float(0xff800000);  // -inf never wins a `>`
+      s_cls[part - 1][k][lane] = cls[k];
+    }
+    s_nan[part - 1][lane] = nan_seen;
+  }
+  __syncthreads();
+  if (part > 0) return;
+  unsigned pass = 0;
+  if (in_range) {
+#pragma unroll
+    for (int j = 0; j < kSplitParts - 1; ++j) {
+      nan_seen |= s_nan[j][lane];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float b = s_best[j][k][lane];
+        if (b > best[k]) {
+          best[k] = b;
+          cls[k] = s_cls[j][k][lane];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (!((nan_seen >> k) & 1u) && (p.ultra ? best[k] > p.conf_thr : best[k] >= p.conf_thr) && class_allowed(p, cls[k]))
+        pass |= 1u << k;
+  }
+  // warp-aggregated compaction: one atomic per warp
+  const int mine = __popc(pass);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  int base = 0;
+  if (lane == 31) base = atomicAdd(p.cand_count + frame, total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  int pos = base + incl - mine;
+  if (pass) {
+    const float4 cx = __ldg(reinterpret_cast<const float4*>(hd + a0));
+    const float4 cy = __ldg(reinterpret_cast<const float4*>(hd + (size_t)A + a0));
+    const float4 w = __ldg(reinterpret_cast<const float4*>(hd + (size_t)2 * A + a0));
+    const float4 hh = __ldg(reinterpret_cast<const float4*>(hd + (size_t)3 * A + a0));
+    const float cxa[4] = {cx.x, cx.y, cx.z, cx.w}, cya[4] = {cy.x, cy.y, cy.z, cy.w};
+    const float wa[4] = {w.x, w.y, w.z, w.w}, ha[4] = {hh.x, hh.y, hh.z, hh.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (pass & (1u << k)) {
+        emit_candidate(p, frame, pos, a0 + k, best[k], cls[k],
+                       decode_box(cxa[k], cya[k], wa[k], ha[k], p.f[frame], p.ultra != 0));
+        ++pos;
+      }
+  }
+}
+
 // anchor-major head [B, A, C]: a warp owns one anchor and strides its lanes over the channels
 __global__ void __launch_bounds__(256) k_decode_am(const __grid_constant__ PostParams p, int frame0) {
   const int frame = blockIdx.y;
@@ -706,13 +813,16 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
     p.ultra = ultra ? 1 : 0;
     if (layout == B200VA_HEAD_CHANNEL_MAJOR) {
       // 16-byte loads need every channel row (A floats) and the tensor base 16-byte aligned
-      // (splitting the class rows over 4 or 8 warps per anchor group -- every load of a thread in flight at once, merge in
-      // shared memory -- measured 22 us / 36 us against 20 us: the kernel is bound by its fixed launch + ramp + tail
-      // cost of ~5 us on top of the 14 us the bytes need, not by the depth of the per-thread load chain)
       // (a TMA-staged variant -- all C rows of a 128-anchor tile bulk-copied to shared memory -- measured
       // 24.6 us against 21.5 us for this register version on [32,84,8400]: the 512-byte row pieces at a
       // 33.6 KB stride bound both; block sizes 64..256 are equivalent, 512 is slower)
-      if (anchors % 4 == 0 && ((uintptr_t)head % 16 == 0)) {
+      const int n_cls_rows = channels - p.cls0;
+      const bool vec4 = anchors % 4 == 0 && ((uintptr_t)head % 16 == 0);
+      // few frames: latency-bound, split the class rows over 8 warps; many frames: HBM-bound, one thread per anchor quad
+      if (vec4 && n <= 8 && n_cls_rows >= 16 && n_cls_rows <= 96) {
+        dim3 grid((anchors / 4 + 31) / 32, n);
+        k_decode_cm_split<8, 12><<<grid, 256, 0, st>>>(p, base);
+      } else if (vec4) {
         dim3 grid((anchors / 4 + 63) / 64, n);
         k_decode_cm<4><<<grid, 64, 0, st>>>(p, base);
       } else {

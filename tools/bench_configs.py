@@ -47,7 +47,29 @@ def simple(name, B, hw, n_obj, dup, conf=0.35, iou=0.5, trk=(30, 1, 0.5)):
                ("postprocess", lambda k: h.postprocess(heads[k % sets], metas, conf, iou, filter_conf=conf, out=dets)),
                ("tracker", lambda k: h.tracker_update(slots, dets, trk[0], trk[1], trk[2], out=tracks))], args.steps)
     h.poll_status()
-    r.update(config=name, streams=B, frame=[H, W], frames_per_s=B / (r["tick_total"] * 1e-3),
+    # the same tick as one prepared b200va_tick replayed from a CUDA graph (what a deployed loop runs: no host
+    # launch gaps -- with 1-4 streams three Python calls cost more than the kernels -- and NMS + tracker under the letterbox)
+    plans = [h.plan_tick(frames=batches[k], net_out=net, dst_hw=(640, 640), head=heads[k], metas=metas, conf_thr=conf,
+                         iou_thr=iou, filter_conf=conf, dets=dets, slots=slots, tracker_cfg=trk, tracks=tracks)
+             for k in range(sets)]
+    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream()); graphs = []
+    with torch.cuda.stream(side):
+        for k in range(sets):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=side):
+                h.tick(plans[k])
+            graphs.append(gr)
+    torch.cuda.current_stream().wait_stream(side)
+    for k in range(5): graphs[k % sets].replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    n_rep = max(args.steps, 50)
+    for k in range(n_rep): graphs[k % sets].replay()
+    e1.record(); torch.cuda.synchronize()
+    r["tick_graph"] = e0.elapsed_time(e1) / n_rep
+    h.poll_status()
+    r.update(config=name, streams=B, frame=[H, W], frames_per_s=B / (r["tick_graph"] * 1e-3),
+             frames_per_s_serial_calls=B / (r["tick_total"] * 1e-3),
              dets_per_frame=float(dets["count"].float().mean()), tracks_per_stream=float(tracks["count"].float().mean()))
     h.close()
     return r
