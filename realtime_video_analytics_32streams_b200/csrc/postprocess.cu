@@ -618,12 +618,22 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
           if ((supp[j >> 5] >> (j & 31)) & 1u) continue;
           const float4 bj = box[j];
           const int cj = scl[j];
+          // pass 1 (uniform across the warp): which survivors can touch box j at all.  Disjoint boxes have
+          // intersection exactly 0 -> IoU 0 -> kept whenever thr >= 0 (four compares instead of the full formula;
+          // NaN coordinates fail every compare and stay candidates).  Pass 2 runs the full formula only on those
+          // -- a handful per box -- so a warp no longer drags all 32 lanes through the division each time ONE lane
+          // meets its overlapping survivor (dense config: this phase 172 k -> 129 k SM cycles, post-process 183 -> 161 us).
+          unsigned long long cand = 0ull;
           for (int q = qb; q < qe; ++q) {
             const float4 bi = kbox[q];
-            // disjoint boxes have intersection exactly 0 -> IoU 0 -> kept whenever thr >= 0 (four compares
-            // instead of the full formula; NaN coordinates fail every compare and take the full path)
-            if (thr_nonneg && (bj.z <= bi.x || bi.z <= bj.x || bj.w <= bi.y || bi.w <= bj.y)) continue;
-            if ((!aware || kcl[q] == cj) && (ultra ? suppresses_tv(bi, bj, p.iou_thr64) : suppresses(bi, bj, thr))) {
+            const bool apart = thr_nonneg && (bj.z <= bi.x || bi.z <= bj.x || bj.w <= bi.y || bi.w <= bj.y);
+            const bool same = !aware || kcl[q] == cj;
+            cand |= (unsigned long long)(!apart && same) << (q - qb);
+          }
+          while (cand) {
+            const int q = qb + __ffsll((long long)cand) - 1;
+            cand &= cand - 1ull;
+            if (ultra ? suppresses_tv(kbox[q], bj, p.iou_thr64) : suppresses(kbox[q], bj, thr)) {
               atomicOr(&supp[j >> 5], 1u << (j & 31));
               break;
             }
