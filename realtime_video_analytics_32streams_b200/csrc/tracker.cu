@@ -75,7 +75,8 @@ __device__ __forceinline__ double iou64(double ax1, double ay1, double ax2, doub
   return __ddiv_rn(inter, uni);
 }
 
-constexpr int kTrkThreadsDefault = 512;
+constexpr int kTrkThreadsMax = 1024;  // launched; a stream with few detections and tracks keeps only kTrkThreadsMin of them
+constexpr int kTrkThreadsMin = 256;
 constexpr int kDetChunk = 64;  // detections staged in shared memory at a time (two warps cover a chunk)
 constexpr int kCand = 6;        // candidate slots per detection and kind; more -> exact brute-force scan
 
@@ -143,8 +144,7 @@ __device__ __forceinline__ void warp_argmax(double& best, int& best_t) {
 //   A chunk in which some detection has more than kCand candidates falls back to the plain
 //   sequential scan (exact, slower).  Nothing in the sequential parts touches global memory:
 //   confidence, age and id of a touched track are derived from last_det[] at write-back.
-template <int kTrkThreads>
-__global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__ TrkParams p) {
+__global__ void __launch_bounds__(kTrkThreadsMax) k_tracker(const __grid_constant__ TrkParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   double* sbox = reinterpret_cast<double*>(smem_raw);                            // [max_tracks][4]
   int32_t* scls = reinterpret_cast<int32_t*>(sbox + (size_t)p.max_tracks * 4);   // [max_tracks]
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__
   __shared__ Cand c_trk[kDetChunk][kCand], c_det[kDetChunk][kCand];
   __shared__ int n_trk[kDetChunk], n_det[kDetChunk], key[kDetChunk], conflicted[kDetChunk], clist[kDetChunk];
   __shared__ int s_T, s_new, s_is_last, s_fallback, s_nconf;
-  __shared__ int wsum[kTrkThreads / 32];
+  __shared__ int wsum[kTrkThreadsMax / 32];
 
   const int bi = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -171,6 +171,13 @@ __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__
   int32_t* age_c = S.age[cur] + sb;
   int32_t* hits_c = S.hits[cur] + sb;
   const int T0 = S.count[slot];
+  const int D = p.skip[bi] ? 0 : min(p.d_count[bi], p.max_dets);
+  // phase A is bound by dependent shared-memory latency on one SM and scales with the warp count (dense config,
+  // 313 detections x 365 tracks: 131 us with 256 threads, 84 us with 512, 63 us with 1024), while a small stream
+  // (25 x 25) only pays for the wider barriers (19 us with 256, 22 us with 1024): the surplus warps of a small
+  // stream leave at once (a barrier counts the warps that are still alive)
+  const int kTrkThreads = (T0 > 96 || D > 64) ? kTrkThreadsMax : kTrkThreadsMin;
+  if (tid >= kTrkThreads) return;
 
   for (int t = tid; t < T0; t += kTrkThreads) {
     const double4 b0 = reinterpret_cast<const double4*>(box_c)[t];
@@ -184,7 +191,6 @@ __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__
     s_new = 0;
   }
 
-  const int D = p.skip[bi] ? 0 : min(p.d_count[bi], p.max_dets);
   const size_t db = (size_t)bi * p.max_dets;
   const double scale = p.det_scale[bi];
 
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(kTrkThreads) k_tracker(const __grid_constant__
   int32_t* age_n = S.age[nxt] + sb;
   int32_t* hits_n = S.hits[nxt] + sb;
   const size_t ob = (size_t)bi * p.max_tracks;
-  __shared__ int warp_cnt[kTrkThreads / 32];
+  __shared__ int warp_cnt[kTrkThreadsMax / 32];
   __shared__ int s_base;
   if (tid == 0) s_base = 0;
   __syncthreads();
@@ -604,7 +610,7 @@ int tracker_state_create(b200va_ctx* h) {
   CUDA_TRY(h, cudaMemcpy(S->next_id, &one, 8, cudaMemcpyHostToDevice));
   const size_t smem = (size_t)h->cfg.max_tracks * 46 + kDetChunk * 4 + 16;
   if (smem > 190 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_tracks %d too large (<= 4096)", h->cfg.max_tracks);
-  CUDA_TRY(h, cudaFuncSetAttribute(k_tracker<kTrkThreadsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_tracker, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return B200VA_OK;
 }
 
@@ -655,10 +661,7 @@ static int tracker_launch(b200va_ctx* h, TrkParams& p, const int* stream_slots, 
   p.o_new = new_counts;
   p.flags = h->status_flags;
   p.dbg = h->dbg;
-  // 512 threads: phase A (every IoU a chunk can need) is bound by dependent shared-memory latency on one SM, so
-  // it scales with the warp count -- dense config (313 detections x 365 tracks) 131 us with 256 threads, 84 us
-  // with 512, 63 us with 1024; the small configs (25 x 25) take 19 / 19 / 22 us
-  k_tracker<kTrkThreadsDefault><<<batch, kTrkThreadsDefault, (size_t)h->cfg.max_tracks * 46 + kDetChunk * 4 + 16, st>>>(p);
+  k_tracker<<<batch, kTrkThreadsMax, (size_t)h->cfg.max_tracks * 46 + kDetChunk * 4 + 16, st>>>(p);
   LAUNCH_CHECK(h);
   return B200VA_OK;
 }
