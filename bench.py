@@ -286,21 +286,26 @@ def run_gpu(args) -> None:
     h.poll_status()
     graphs, kernels_per_graph = None, 0
     if not args.no_graph:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        graphs = []
-        l0 = h.launch_count
-        with torch.cuda.stream(side):
-            for k in range(N_SETS):
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=side):
-                    plans[k].set_events(None, None)
-                    h.tick(plans[k])
-                graphs.append(gr)
-        torch.cuda.current_stream().wait_stream(side)
-        kernels_per_graph = (h.launch_count - l0) // N_SETS
-        for k in range(max(args.warmup, 3)):
-            graphs[k % N_SETS].replay()
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            graphs = []
+            l0 = h.launch_count
+            with torch.cuda.stream(side):
+                for k in range(N_SETS):
+                    gr = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(gr, stream=side):
+                        plans[k].set_events(None, None)
+                        h.tick(plans[k])
+                    graphs.append(gr)
+            torch.cuda.current_stream().wait_stream(side)
+            kernels_per_graph = (h.launch_count - l0) // N_SETS
+            for k in range(max(args.warmup, 3)):
+                graphs[k % N_SETS].replay()
+        except Exception as exc:  # pragma: no cover - capture refused: every step is launched eagerly instead
+            print(f"bench: CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
+            graphs, kernels_per_graph = None, 0
+            torch.cuda.synchronize()
         barrier()
 
     def timed_step(k, ev):
