@@ -372,6 +372,31 @@ def run_gpu(args) -> None:
     # informational: the same tick launched eagerly every step, and as three separate C-ABI calls on one stream
     eager_value = timed_variant(lambda k: step(k))
     serial_value = timed_variant(serial_step)
+    # informational, N > 1: BASELINE.json's deployment shape -- 32 streams IN TOTAL, 32 / N per GPU (strong scaling).
+    # The kernels are latency-bound at 4 streams per launch, so this is far from N x the single-GPU number.
+    strong_value = None
+    if world > 1 and STREAMS % world == 0 and graphs is not None:
+        m = STREAMS // world
+        s_dets, s_tracks = h.alloc_dets(m), h.alloc_tracks(m)
+        s_slots = _native._int_array([STREAMS + i for i in range(m)])
+        s_metas = (_native.Letterbox * m)(*[metas[i] for i in range(m)])
+        s_plans = [h.plan_tick(frames=_native.FrameBatch(list(frame_sets[k][:m].unbind(0))), net_out=net_in[:m], dst_hw=IN_HW,
+                               fmt=_native.OUT_F32_RGB_NCHW, head=head_sets[k][:m], metas=s_metas, conf_thr=CONF,
+                               iou_thr=IOU, filter_conf=CONF, dets=s_dets, slots=s_slots,
+                               tracker_cfg=(TRK["max_age"], TRK["min_hits"], TRK["max_iou_distance"]), tracks=s_tracks,
+                               schedule=args.schedule) for k in range(N_SETS)]
+        side2 = torch.cuda.Stream()
+        side2.wait_stream(torch.cuda.current_stream())
+        s_graphs = []
+        with torch.cuda.stream(side2):
+            for k in range(N_SETS):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side2):
+                    h.tick(s_plans[k])
+                s_graphs.append(gr)
+        torch.cuda.current_stream().wait_stream(side2)
+        strong_value = timed_variant(lambda k: s_graphs[k % N_SETS].replay()) / world  # m * world = 32 frames per step
+        h.poll_status()
     if world > 1:
         tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -477,6 +502,7 @@ def run_gpu(args) -> None:
                            if graphs is not None else "eager b200va_tick every step, event pair around the letterbox kernel"),
                 "letterbox_samples": len(kev),
                 "value_eager_tick": round(eager_value, 1), "value_three_serial_calls": round(serial_value, 1),
+                "value_32_streams_total_strong_scaling": round(strong_value, 1) if strong_value is not None else None,
                 "clocks": clocks.summary(), "tracks_alive": n_tracks}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_single_core_sample()
