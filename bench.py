@@ -372,6 +372,28 @@ def run_gpu(args) -> None:
     # informational: the same tick launched eagerly every step, and as three separate C-ABI calls on one stream
     eager_value = timed_variant(lambda k: step(k))
     serial_value = timed_variant(serial_step)
+    # informational: the same tick with B200VA_OUT_FLAG_PADS_VALID -- the 280 pad rows of every 640 x 640 input (44 % of
+    # the letterbox output) were written by the earlier steps into the same persistent buffer and are not written
+    # again.  Not the headline: `value` rewrites the whole tensor every step, like the reference does.
+    pads_value = None
+    if graphs is not None:
+        p_plans = [h.plan_tick(frames=batches[k], net_out=net_in, dst_hw=IN_HW,
+                               fmt=_native.OUT_F32_RGB_NCHW | _native.OUT_FLAG_PADS_VALID, head=head_sets[k], metas=metas,
+                               conf_thr=CONF, iou_thr=IOU, filter_conf=CONF, dets=dets, slots=slots,
+                               tracker_cfg=(TRK["max_age"], TRK["min_hits"], TRK["max_iou_distance"]), tracks=tracks,
+                               schedule=args.schedule) for k in range(N_SETS)]
+        side3 = torch.cuda.Stream()
+        side3.wait_stream(torch.cuda.current_stream())
+        p_graphs = []
+        with torch.cuda.stream(side3):
+            for k in range(N_SETS):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=side3):
+                    h.tick(p_plans[k])
+                p_graphs.append(gr)
+        torch.cuda.current_stream().wait_stream(side3)
+        pads_value = timed_variant(lambda k: p_graphs[k % N_SETS].replay())
+        h.poll_status()
     # informational, N > 1: BASELINE.json's deployment shape -- 32 streams IN TOTAL, 32 / N per GPU (strong scaling).
     # The kernels are latency-bound at 4 streams per launch, so this is far from N x the single-GPU number.
     strong_value = None
@@ -502,6 +524,7 @@ def run_gpu(args) -> None:
                            if graphs is not None else "eager b200va_tick every step, event pair around the letterbox kernel"),
                 "letterbox_samples": len(kev),
                 "value_eager_tick": round(eager_value, 1), "value_three_serial_calls": round(serial_value, 1),
+                "value_pad_rows_written_once": round(pads_value, 1) if pads_value is not None else None,
                 "value_32_streams_total_strong_scaling": round(strong_value, 1) if strong_value is not None else None,
                 "clocks": clocks.summary(), "tracks_alive": n_tracks}
         if world == 1 and not args.no_cpu:

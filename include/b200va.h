@@ -54,6 +54,13 @@ enum b200va_out_format {
   B200VA_OUT_U8_BGR_NHWC = 3   /* detector.py:777-839 RKNN variant, use_nhwc=True; also plain resize       */
 };
 
+/* OR-ed into out_format: the caller guarantees that the full-width pad rows of `out` (the 114-valued bands above
+ * and below the resized image) still hold what an earlier call with the same geometry and format wrote there, so
+ * the kernel does not write them again.  A letterboxed 16:9 frame in a 640 x 640 input is 44 % padding: with a
+ * persistent network-input buffer (what a batched tick driver uses anyway) those 69 MB per 32 frames are written
+ * once instead of every tick.  The tensor contents are identical either way. */
+#define B200VA_OUT_FLAG_PADS_VALID 0x100
+
 /* Head tensor layouts accepted by b200va_postprocess (detector.py:278-283 transposes
  * [C,A] exports to [A,C]; both are read in place here, no transpose pass). */
 enum b200va_head_layout {

@@ -17,6 +17,7 @@ LIB_PATH = os.environ.get("B200VA_LIB") or os.path.join(PKG_DIR, "lib", "libb200
 
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
 OUT_F32_RGB_NCHW, OUT_F16_RGB_NCHW, OUT_U8_BGR_NCHW, OUT_U8_BGR_NHWC = 0, 1, 2, 3
+OUT_FLAG_PADS_VALID = 0x100  # OR into the format: the pad rows of `out` are still valid from an earlier call
 HEAD_CHANNEL_MAJOR, HEAD_ANCHOR_MAJOR = 0, 1
 SCORE_REF_COMPAT, SCORE_V8_NATIVE = 0, 1
 NMS_AGNOSTIC, NMS_CLASS_AWARE = 0, 1
@@ -298,8 +299,8 @@ class Handle:
         fb = self._batch(frames, roi_masks)
         b = fb.n
         dh, dw = int(dst_hw[0]), int(dst_hw[1])
-        dtype = {OUT_F32_RGB_NCHW: t.float32, OUT_F16_RGB_NCHW: t.float16}.get(fmt, t.uint8)
-        shape = (b, dh, dw, 3) if fmt == OUT_U8_BGR_NHWC else (b, 3, dh, dw)
+        dtype = {OUT_F32_RGB_NCHW: t.float32, OUT_F16_RGB_NCHW: t.float16}.get(fmt & 0xff, t.uint8)
+        shape = (b, dh, dw, 3) if (fmt & 0xff) == OUT_U8_BGR_NHWC else (b, 3, dh, dw)
         if out is None:
             out = t.empty(shape, dtype=dtype, device=self.device)
         elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
@@ -429,8 +430,8 @@ class Handle:
         fb = self._batch(frames, roi_masks)
         b = fb.n
         dh, dw = int(dst_hw[0]), int(dst_hw[1])
-        dtype = {OUT_F32_RGB_NCHW: t.float32, OUT_F16_RGB_NCHW: t.float16}.get(fmt, t.uint8)
-        shape = (b, dh, dw, 3) if fmt == OUT_U8_BGR_NHWC else (b, 3, dh, dw)
+        dtype = {OUT_F32_RGB_NCHW: t.float32, OUT_F16_RGB_NCHW: t.float16}.get(fmt & 0xff, t.uint8)
+        shape = (b, dh, dw, 3) if (fmt & 0xff) == OUT_U8_BGR_NHWC else (b, 3, dh, dw)
         if out is None:
             out = t.empty(shape, dtype=dtype, device=self.device)
         elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
@@ -529,8 +530,8 @@ class Handle:
         if frames is not None:
             fb = self._batch(frames, roi_masks)
             dh, dw = int(dst_hw[0]), int(dst_hw[1])
-            dtype = {OUT_F32_RGB_NCHW: t.float32, OUT_F16_RGB_NCHW: t.float16}.get(fmt, t.uint8)
-            shape = (fb.n, dh, dw, 3) if fmt == OUT_U8_BGR_NHWC else (fb.n, 3, dh, dw)
+            dtype = {OUT_F32_RGB_NCHW: t.float32, OUT_F16_RGB_NCHW: t.float16}.get(fmt & 0xff, t.uint8)
+            shape = (fb.n, dh, dw, 3) if (fmt & 0xff) == OUT_U8_BGR_NHWC else (fb.n, 3, dh, dw)
             if net_out is None or tuple(net_out.shape) != shape or net_out.dtype != dtype or not net_out.is_contiguous():
                 raise ValueError("plan_tick: `net_out` must be a contiguous tensor of the letterbox output shape / dtype")
             a.frames, a.src_h, a.src_w, a.src_pitch, a.batch = fb.ptrs, fb.hs, fb.ws, fb.pitch, fb.n

@@ -50,6 +50,7 @@ struct PreParams {
   int dst_h, dst_w, fmt, rows_per_cta;
   int row_stride, mask_stride, stages, vec_ok;
   int rows_per_stage;  // 1 when no frame of the launch ever needs the second source row
+  int keep_pad_rows;   // B200VA_OUT_FLAG_PADS_VALID: full-width pad rows of `out` already hold the pad value
 };
 static_assert(sizeof(PreParams) <= 4000, "kernel parameter block too large");
 
@@ -307,7 +308,8 @@ __global__ void __launch_bounds__(kThreads) k_letterbox(const __grid_constant__ 
       __syncthreads();
     }
 
-    if ((int)threadIdx.x < ngroups) {
+    const bool skip_row = pad_row && p.keep_pad_rows;  // written by an earlier call into the same buffer
+    if ((int)threadIdx.x < ngroups && !skip_row) {
       int v[4][3];
       if (pad_row) {
 #pragma unroll
@@ -320,7 +322,7 @@ __global__ void __launch_bounds__(kThreads) k_letterbox(const __grid_constant__ 
       store_px4<FMT>(optr, plane, vec_ok, nvalid0, v);
     }
     // destination rows wider than 4 * blockDim pixels: remaining groups read their taps from global
-    for (int g = threadIdx.x + nthreads; g < ngroups; g += nthreads) {
+    for (int g = threadIdx.x + nthreads; g < ngroups && !skip_row; g += nthreads) {
       TapX t[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -519,8 +521,10 @@ int preprocess_configure(b200va_ctx* h) {
 static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* src_h, const int* src_w,
                         const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks, void* out,
                         const int* new_h, const int* new_w, const int* pad_top, const int* pad_left, int dst_h,
-                        int dst_w, int fmt, cudaStream_t st) {
-  REQUIRE(h, fmt >= 0 && fmt <= 3, "unknown output format %d", fmt);
+                        int dst_w, int fmt_and_flags, cudaStream_t st) {
+  const int fmt = fmt_and_flags & 0xff;
+  REQUIRE(h, fmt >= 0 && fmt <= 3 && (fmt_and_flags & ~(0xff | B200VA_OUT_FLAG_PADS_VALID)) == 0, "unknown output format %d",
+          fmt_and_flags);
   std::vector<int> order[2];
   for (int b = 0; b < batch; ++b) order[(roi_masks && roi_masks[b]) ? 1 : 0].push_back(b);
   for (int with_mask = 0; with_mask < 2; ++with_mask) {
@@ -562,6 +566,7 @@ static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* 
       p.dst_h = dst_h;
       p.dst_w = dst_w;
       p.fmt = fmt;
+      p.keep_pad_rows = (fmt_and_flags & B200VA_OUT_FLAG_PADS_VALID) ? 1 : 0;
       p.row_stride = (max_row + 127) & ~127;
       p.mask_stride = with_mask ? ((max_w + 127) & ~127) : 0;
       p.rows_per_stage = all_single ? 1 : 2;

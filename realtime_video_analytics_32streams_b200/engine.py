@@ -146,7 +146,7 @@ class HotPathEngine:
     """pre + post + track for a set of streams, one tick at a time."""
 
     def __init__(self, streams: Sequence, detector_config, tracker_config, infer: Callable,
-                 handle: Optional[_native.Handle] = None, input_hw=None, depth: int = 2):
+                 handle: Optional[_native.Handle] = None, input_hw=None, depth: int = 2, static_pads: bool = True):
         self.h = handle if handle is not None else get_handle()
         self.streams = list(streams)
         self.detector = B200Detector(detector_config, input_hw=input_hw, infer=infer, handle=self.h, fold_filter=True)
@@ -159,6 +159,10 @@ class HotPathEngine:
         self._changed = self.h.torch.empty((n,), dtype=self.h.torch.int32, device=self.h.device)
         self._batches: Dict[tuple, _native.FrameBatch] = {}
         self._net = None
+        self._net_shapes = []
+        # the network-input buffer is persistent: pad rows are written once per geometry (B200VA_OUT_FLAG_PADS_VALID).
+        # Needs an `infer` that does not write into its input; pass static_pads=False otherwise.
+        self.static_pads = bool(static_pads)
         # a tick's gates depend on the previous tick's results for these features
         self.sequential = any(getattr(s, "motion_filter", False) or getattr(s, "adaptive_fps", False)
                               for s in self.streams)
@@ -180,7 +184,17 @@ class HotPathEngine:
         dtype = t.float16 if self.detector._fmt == _native.OUT_F16_RGB_NCHW else t.float32
         if self._net is None or self._net.shape[0] < n or self._net.dtype != dtype:
             self._net = t.empty((max(n, len(self.streams)), 3, *self.detector.input_hw), dtype=dtype, device=self.h.device)
+            self._net_shapes = [None] * self._net.shape[0]  # source (h, w) whose pad rows each position holds
         return self._net[:n]
+
+    def _pads_flag(self, frames) -> int:
+        """B200VA_OUT_FLAG_PADS_VALID when every batch position was last written from a frame of the same size
+        (same letterbox geometry, same format): its pad rows are already in the persistent buffer."""
+        shapes = [(int(f.shape[0]), int(f.shape[1])) for f in frames]
+        valid = all(self._net_shapes[k] == sh for k, sh in enumerate(shapes))
+        for k, sh in enumerate(shapes):
+            self._net_shapes[k] = sh
+        return _native.OUT_FLAG_PADS_VALID if (valid and self.static_pads) else 0
 
     # --------------------------------------------------------------------------------------
     def tick(self, frames: Sequence, frame_ids: Optional[Sequence[int]] = None, infer_ctx=None) -> List[FrameResult]:
@@ -261,8 +275,11 @@ class HotPathEngine:
         nb = len(order)
         dets = {k_: v[:nb] for k_, v in ctx.dets.items() if not k_.startswith("_")}
         if n_act:
-            tensor, metas = self.h.preprocess(self._frame_batch([work[k] for k in active], [work_masks[k] for k in active]),
-                                              self.detector.input_hw, self.detector._fmt, out=self._net_in(n_act))
+            net = self._net_in(n_act)
+            act_frames = [work[k] for k in active]
+            tensor, metas = self.h.preprocess(self._frame_batch(act_frames, [work_masks[k] for k in active]),
+                                              self.detector.input_hw, self.detector._fmt | self._pads_flag(act_frames),
+                                              out=net)
             head = self.detector._infer(tensor) if infer_ctx is None else self.detector._infer_fn(tensor, infer_ctx)
             head = self.detector._as_head(head)
             if head.dim() != 3 or head.shape[0] != n_act:

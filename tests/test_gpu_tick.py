@@ -137,3 +137,35 @@ def test_tick_halves_are_optional():
     torch.cuda.synchronize()
     _check(h, want, net, post.tracks, 0)
     h.close()
+
+
+def test_pads_valid_flag_skips_only_the_pad_rows():
+    """B200VA_OUT_FLAG_PADS_VALID: same tensor as a full call once the pad rows are in place, and the kernel
+    really leaves them alone (a sentinel written there survives)."""
+    import torch
+    from realtime_video_analytics_32streams_b200 import _native as N
+
+    h = _handle()
+    frames = [synth.synth_frame(40 + i, *hw) for i, hw in enumerate([(1080, 1920), (720, 1280), (1920, 1080), (360, 640)])]
+    dev = [torch.from_numpy(f).cuda() for f in frames]
+    for fmt in (N.OUT_F32_RGB_NCHW, N.OUT_F16_RGB_NCHW, N.OUT_U8_BGR_NHWC):
+        full, metas = h.preprocess(dev, IN_HW, fmt)
+        again = full.clone()
+        h.preprocess(dev, IN_HW, fmt | N.OUT_FLAG_PADS_VALID, out=again)
+        assert torch.equal(again, full)
+        marked = full.clone()
+        top = metas[0].pad_top  # frame 0 is 16:9: rows [0, top) and [top + new_h, 640) are padding
+        sentinel = 7 if fmt == N.OUT_U8_BGR_NHWC else 0.5
+        if fmt == N.OUT_U8_BGR_NHWC:
+            marked[0, :top] = sentinel
+        else:
+            marked[0, :, :top] = sentinel
+        h.preprocess(dev, IN_HW, fmt | N.OUT_FLAG_PADS_VALID, out=marked)
+        band = marked[0, :top] if fmt == N.OUT_U8_BGR_NHWC else marked[0, :, :top]
+        assert bool((band == sentinel).all()) and top == 140
+        inner = (marked[0, top:top + metas[0].new_h] if fmt == N.OUT_U8_BGR_NHWC else marked[0, :, top:top + metas[0].new_h])
+        ref = (full[0, top:top + metas[0].new_h] if fmt == N.OUT_U8_BGR_NHWC else full[0, :, top:top + metas[0].new_h])
+        assert torch.equal(inner, ref)
+        assert torch.equal(marked[1:], full[1:])  # portrait frame: its pad columns are still written
+    h.poll_status()
+    h.close()
