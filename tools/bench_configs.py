@@ -8,6 +8,7 @@ from realtime_video_analytics_32streams_b200 import _native, synth
 
 ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=30); ap.add_argument("--out", default="")
 ap.add_argument("--only", default="")
+ap.add_argument("--lshape", type=int, default=-1, help="with --only L: run just this letterbox shape (0-5)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
@@ -135,12 +136,13 @@ def letterbox_only(name, B, hw, fmt=0, mask=False):
 out = []
 todo = args.only.split(",") if args.only else ["1", "2", "5", "4"]
 if "L" in todo:
-    out.append(letterbox_only("letterbox 32x1080p fp32", 32, (1080, 1920)))
-    out.append(letterbox_only("letterbox 32x1080p fp16", 32, (1080, 1920), fmt=1))
-    out.append(letterbox_only("letterbox 32x4K fp32", 32, (2160, 3840)))
-    out.append(letterbox_only("letterbox 32x4K fp32 + ROI mask", 32, (2160, 3840), mask=True))
-    out.append(letterbox_only("letterbox 32x720p fp32", 32, (720, 1280)))
-    out.append(letterbox_only("letterbox 32x1440p fp32 (non-integer ratio)", 32, (1440, 2560)))
+    shapes = [("letterbox 32x1080p fp32", 32, (1080, 1920), 0, False), ("letterbox 32x1080p fp16", 32, (1080, 1920), 1, False),
+              ("letterbox 32x4K fp32", 32, (2160, 3840), 0, False), ("letterbox 32x4K fp32 + ROI mask", 32, (2160, 3840), 0, True),
+              ("letterbox 32x720p fp32", 32, (720, 1280), 0, False),
+              ("letterbox 32x1440p fp32 (non-integer ratio)", 32, (1440, 2560), 0, False)]
+    for i, (nm, b, hw, fmt, mask) in enumerate(shapes):
+        if args.lshape < 0 or args.lshape == i:
+            out.append(letterbox_only(nm, b, hw, fmt=fmt, mask=mask))
 if "1" in todo: out.append(simple("1: 1 stream 1080p (pipeline-sim shape)", 1, (1080, 1920), 10, 1))
 if "2" in todo: out.append(simple("2: 4 streams 1080p (pipeline-rtsp shape)", 4, (1080, 1920), 10, 1))
 if "5" in todo: out.append(simple("5: dense stress, 32 streams, ~1800 candidates -> ~300 kept", 32, (1080, 1920), 300, 6))
