@@ -395,6 +395,7 @@ struct NmsParams {
   // class * 7680 in float32 (0 when agnostic), torchvision's IoU test, at most max_det_cap boxes kept, then
   // un-letterbox with f[frame]
   int ultra, ultra_agnostic, max_det_cap;
+  int grid_off;  // byte offset of the NmsGrid in dynamic shared memory; 0 = no grid (survivors-vs-tail scan instead)
   double iou_thr64;
   PostFrame f[B200VA_LAUNCH_FRAMES];
 };
@@ -425,6 +426,29 @@ __device__ __forceinline__ bool suppresses_tv(const float4 a, const float4 b, do
   return (double)iou > thr;  // NaN (0 / 0) never suppresses
 }
 
+// Uniform grid over the frame for the kept boxes (reference mode: boxes are clipped to the frame, so every
+// coordinate is finite and inside [0, xmax] x [0, ymax]).  A candidate can only be suppressed by a kept box it
+// overlaps, and two overlapping boxes share at least one cell, so a candidate is tested against the kept boxes
+// registered in the cells it touches (plus the overflow list: boxes that span too many cells or hit a full cell)
+// instead of against every survivor of every earlier chunk: O(candidates x local density) instead of
+// O(candidates x kept).
+constexpr int kGX = 16, kGY = 12, kCells = kGX * kGY, kCellCap = 32, kMaxCellsPerBox = 24;
+struct NmsGrid {
+  int cnt[kCells];
+  int n_over;
+  int pad_[3];
+  uint16_t list[kCells][kCellCap];
+  // followed by: uint32_t over_mark[cap_pow2 / 32]; uint16_t over[cap_pow2];
+};
+__device__ __forceinline__ void cell_range(const float4 b, float inv_w, float inv_h, int& cx0, int& cx1, int& cy0, int& cy1) {
+  cx0 = min(kGX - 1, max(0, (int)(b.x * inv_w)));
+  cx1 = min(kGX - 1, max(0, (int)(b.z * inv_w)));
+  cy0 = min(kGY - 1, max(0, (int)(b.y * inv_h)));
+  cy1 = min(kGY - 1, max(0, (int)(b.w * inv_h)));
+  if (cx1 < cx0) cx1 = cx0;  // inverted boxes (negative width) never overlap anything; keep the range well formed
+  if (cy1 < cy0) cy1 = cy0;
+}
+
 constexpr int kNmsThreads = 1024;
 
 __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant__ NmsParams p) {
@@ -443,6 +467,9 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
   uint32_t* keep_w = supp + p.cap_pow2 / 32;                                                // [cap_pow2/32]
   int* keep_off = reinterpret_cast<int*>(keep_w + p.cap_pow2 / 32);                         // [cap_pow2/64 + 1]
   uint16_t* scl = reinterpret_cast<uint16_t*>(keep_off + p.cap_pow2 / 64 + 1);              // [cap_pow2] class ids (class-aware mode)
+  NmsGrid* const grid = p.grid_off ? reinterpret_cast<NmsGrid*>(smem_raw + p.grid_off) : nullptr;
+  uint32_t* const over_mark = grid ? reinterpret_cast<uint32_t*>(grid + 1) : nullptr;       // [cap_pow2/32]
+  uint16_t* const over = grid ? reinterpret_cast<uint16_t*>(over_mark + p.cap_pow2 / 32) : nullptr;  // [cap_pow2]
   __shared__ uint32_t rows[64][2];
   __shared__ float4 kbox[64];
   __shared__ int kcl[64];
@@ -535,8 +562,17 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
   const float thr = p.iou_thr;
   const bool thr_nonneg = ultra ? p.iou_thr64 >= 0.0 : thr >= 0.f;
   const int nchunks = (n + 63) >> 6;
+  // few candidates: the survivors-vs-tail scan is cheaper than keeping the grid
+  const bool use_grid = grid != nullptr && !ultra && thr_nonneg && n > 256;
+  const float inv_cw = (float)kGX / (p.f[frame].xmax + 1.0f), inv_ch = (float)kGY / (p.f[frame].ymax + 1.0f);
+  if (use_grid) {
+    for (int c = tid; c < kCells; c += kNmsThreads) grid->cnt[c] = 0;
+    for (int w = tid; w < (n + 31) / 32; w += kNmsThreads) over_mark[w] = 0u;
+    if (tid == 0) grid->n_over = 0;
+    __syncthreads();
+  }
 #ifdef B200VA_PHASE_TIMING
-  long long acc_a = 0, acc_b = 0, acc_c = 0, t_mark = clock64();
+  long long acc_a = 0, acc_b = 0, acc_c = 0, acc_q = 0, t_mark = clock64();
 #define NMS_MARK(acc) do { const long long _t = clock64(); acc += _t - t_mark; t_mark = _t; } while (0)
 #else
 #define NMS_MARK(acc) do { } while (0)
@@ -546,6 +582,56 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
     const int m = min(64, n - c0);
     if (tid < 128) rows[tid >> 1][tid & 1] = 0u;
     __syncthreads();
+    // (q) grid mode: is box i of this chunk suppressed by a box kept in an EARLIER chunk?  Four threads per box
+    // (the first eight warps) take the cells it touches.  Pass 1 only collects the kept boxes that overlap box i
+    // (four compares each); pass 2 runs the IoU formula on them with the warp converged.  The CTA is issue-bound
+    // in this loop (all 32 warps busy on one SM), so what counts is warp-instructions: ~1.3 k per query warp and
+    // chunk, against ~4 k per chunk for the survivors-vs-tail scan it replaces in dense scenes.
+    // (Writes supp[], which (a) does not read: no barrier before (a).)
+    if (use_grid && ch > 0 && tid < 256) {
+      const int i = tid >> 2, part = tid & 3;
+      const bool active = i < m;
+      const int self = c0 + (active ? i : 0);
+      const float4 bi = box[self];
+      const int ci = scl[self];
+      int cx0, cx1, cy0, cy1;
+      cell_range(bi, inv_cw, inv_ch, cx0, cx1, cy0, cy1);
+      const int cw = cx1 - cx0 + 1, ncell = active ? cw * (cy1 - cy0 + 1) : 0;
+      const float rcw = 1.0f / (float)cw;
+      constexpr int kQ = 4;  // overlapping kept boxes a lane can defer; more are evaluated on the spot
+      int cand[kQ], nc = 0;
+      bool hit = false;
+      auto consider = [&](int k) {
+        const float4 bk = box[k];
+        if (bk.z <= bi.x || bi.z <= bk.x || bk.w <= bi.y || bi.w <= bk.y) return;  // disjoint: IoU 0 <= thr
+        if (aware && scl[k] != ci) return;
+        if (nc < kQ) cand[nc++] = k;
+        else if (suppresses(bk, bi, thr)) hit = true;
+      };
+      for (int c = part; c < ncell; c += 4) {
+        const int row = (int)(((float)c + 0.5f) * rcw);  // c / cw for these small integers
+        const int cell = (cy0 + row) * kGX + cx0 + (c - row * cw);
+        const int cnt = min(grid->cnt[cell], kCellCap);
+        for (int e = 0; e < cnt; e += 4) {  // one 8-byte load brings four indices
+          const uint2 kk = *reinterpret_cast<const uint2*>(&grid->list[cell][e]);
+          const int k4[4] = {(int)(kk.x & 0xffffu), (int)(kk.x >> 16), (int)(kk.y & 0xffffu), (int)(kk.y >> 16)};
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (e + u < cnt) consider(k4[u]);
+        }
+      }
+      if (active) {
+        const int nover = grid->n_over;
+        for (int e = part; e < nover; e += 4) consider(over[e]);
+      }
+#pragma unroll
+      for (int u = 0; u < kQ; ++u) {
+        if (!__any_sync(0xffffffffu, u < nc && !hit)) break;
+        if (u < nc && !hit && suppresses(box[cand[u]], bi, thr)) hit = true;
+      }
+      if (hit) atomicOr(&supp[self >> 5], 1u << (self & 31));
+    }
+    NMS_MARK(acc_q);
     // (a) in-chunk IoU bits: thread -> row i = tid / 16, columns 4 * (tid % 16) ..; the predicate is
     // symmetric, so only pairs j > i are evaluated and a hit sets both (i, j) and (j, i)
     {
@@ -600,7 +686,30 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
     // tail grows so that all 1024 threads stay busy.
     const unsigned long long kept = ((unsigned long long)keep_w[2 * ch + 1] << 32) | keep_w[2 * ch];
     const int tail = n - (c0 + 64);
-    if (kept && tail > 0) {
+    if (use_grid) {
+      // (c') register this chunk's survivors in the cells they touch (16 threads per survivor)
+      const int b = tid >> 4, part = tid & 15;
+      if (tail > 0 && ((kept >> b) & 1ull)) {
+        const int idx = c0 + b;
+        int cx0, cx1, cy0, cy1;
+        cell_range(box[idx], inv_cw, inv_ch, cx0, cx1, cy0, cy1);
+        const int cw = cx1 - cx0 + 1, ncell = cw * (cy1 - cy0 + 1);
+        bool spill = ncell > kMaxCellsPerBox && part == 0;
+        if (ncell <= kMaxCellsPerBox) {
+          const float rcw = 1.0f / (float)cw;
+          for (int c = part; c < ncell; c += 16) {
+            const int row = (int)(((float)c + 0.5f) * rcw);
+            const int cell = (cy0 + row) * kGX + cx0 + (c - row * cw);
+            const int pos = atomicAdd(&grid->cnt[cell], 1);
+            if (pos < kCellCap) grid->list[cell][pos] = (uint16_t)idx;
+            else spill = true;
+          }
+        }
+        // a box that does not fit its cells goes to the overflow list, once
+        if (spill && !(atomicOr(&over_mark[idx >> 5], 1u << (idx & 31)) & (1u << (idx & 31))))
+          over[atomicAdd(&grid->n_over, 1)] = (uint16_t)idx;
+      }
+    } else if (kept && tail > 0) {
       const int nk = __popcll(kept);
       if (tid < 64 && ((kept >> tid) & 1ull)) {
         const int q = __popcll(kept & ((1ull << tid) - 1ull));
@@ -649,6 +758,17 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
     p.dbg[24] = acc_a;
     p.dbg[25] = acc_b;
     p.dbg[26] = acc_c;
+    p.dbg[27] = acc_q;
+    if (use_grid) {
+      int mx = 0, tot = 0;
+      for (int c = 0; c < kCells; ++c) {
+        mx = max(mx, grid->cnt[c]);
+        tot += grid->cnt[c];
+      }
+      p.dbg[28] = mx;
+      p.dbg[29] = grid->n_over;
+      p.dbg[30] = tot;
+    }
   }
 #endif
 
@@ -728,9 +848,15 @@ static int next_pow2(int v) {
 
 }  // namespace
 
+static size_t nms_base_bytes(int max_cand) {
+  const size_t cap = (size_t)next_pow2(max_cand);
+  return (cap * 24 + cap / 8 + cap / 8 + (cap / 64 + 1) * 4 + cap * 2 + 64 + 15) & ~(size_t)15;  // keys, boxes, supp, keep_w, keep_off, classes
+}
+// the kept-box grid is carried when the candidate capacity leaves room for it (cap <= 4096: 106 KB + 21 KB)
+static size_t nms_grid_offset(int max_cand) { return next_pow2(max_cand) <= 4096 ? nms_base_bytes(max_cand) : 0; }
 size_t nms_smem_bytes(int max_cand) {
   const size_t cap = (size_t)next_pow2(max_cand);
-  return cap * 24 + cap / 8 + cap / 8 + (cap / 64 + 1) * 4 + cap * 2 + 64;  // keys, boxes, supp, keep_w, keep_off, classes
+  return nms_base_bytes(max_cand) + (nms_grid_offset(max_cand) ? sizeof(NmsGrid) + cap / 8 + cap * 2 : 0);
 }
 
 int postprocess_configure(b200va_ctx* h) {
@@ -869,6 +995,7 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
     q.ultra = ultra ? 1 : 0;
     q.ultra_agnostic = ultra ? ultra->agnostic : 0;
     q.max_det_cap = ultra ? ultra->max_det : 0;
+    q.grid_off = (int)nms_grid_offset(h->cfg.max_candidates);
     q.iou_thr64 = iou_thr;  // torchvision's CPU kernel compares the float32 IoU with the double threshold
     memcpy(q.f, p.f, sizeof(q.f));
     k_sort_nms<<<n, kNmsThreads, nms_smem_bytes(h->cfg.max_candidates), st>>>(q);

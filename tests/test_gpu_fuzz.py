@@ -169,6 +169,55 @@ def test_nms_clusters_near_threshold(H):
             assert np.array_equal(out["bbox_xyxy"][0, :m].cpu().numpy().astype(np.float64), rb)
 
 
+def test_nms_grid_paths(H):
+    """More than 256 candidates take the kept-box grid: mixes of tiny boxes crowding one cell (cell lists overflow),
+    frame-sized boxes (too many cells: overflow list), ordinary clusters, zero-area boxes and boxes on the frame
+    border, class-agnostic and class-aware, several thresholds and frame shapes."""
+    from realtime_video_analytics_32streams_b200 import _native as N
+
+    H = N.Handle(device=0, max_batch=2, max_anchors=4096, max_candidates=2048, max_dets=2048, max_streams=2, max_tracks=64)
+    rng = np.random.default_rng(29)
+    for it, (fh, fw) in enumerate([(1080, 1920), (1000, 1000), (2160, 3840), (360, 640), (1920, 1080), (90, 4000)]):
+        lb = N.Letterbox(fh, fw, fh, fw, 0, 0, 1.0)
+        meta = {"orig_shape": (fh, fw), "scale": 1.0, "pad": (0, 0)}
+        n = int(rng.integers(300, 1900))
+        C = 4 + 1 + 6
+        head = np.zeros((C, 2048), np.float32)
+        kinds = rng.choice(5, n, p=[0.45, 0.25, 0.1, 0.1, 0.1])
+        cx = rng.uniform(0, fw, n)
+        cy = rng.uniform(0, fh, n)
+        w = rng.uniform(8, 0.08 * fw, n)
+        h = rng.uniform(8, 0.12 * fh, n)
+        crowd = kinds == 1  # a lattice of tiny boxes inside one grid cell
+        cx[crowd] = 0.3 * fw + rng.integers(0, 12, crowd.sum()) * 7.0
+        cy[crowd] = 0.3 * fh + rng.integers(0, 10, crowd.sum()) * 6.0
+        w[crowd], h[crowd] = rng.uniform(3, 9, crowd.sum()), rng.uniform(3, 8, crowd.sum())
+        huge = kinds == 2
+        w[huge], h[huge] = rng.uniform(0.5 * fw, 1.5 * fw, huge.sum()), rng.uniform(0.5 * fh, 1.5 * fh, huge.sum())
+        flat = kinds == 3
+        w[flat] = 0.0  # zero area: IoU 0 with everything
+        edge = kinds == 4
+        cx[edge] = rng.choice([0.0, fw - 1.0, fw + 50.0], edge.sum())
+        head[0, :n], head[1, :n], head[2, :n], head[3, :n] = cx, cy, w, h
+        scores = np.unique(rng.uniform(0.36, 0.999, 4 * n).astype(np.float32))
+        rng.shuffle(scores)
+        head[4, :n] = 1.0  # objectness; class scores below are the confidences
+        cls = rng.integers(0, 6, n)
+        head[5 + cls, np.arange(n)] = scores[:n]
+        for thr in (0.5, 0.2, 0.0):
+            for aware in (False, True):
+                ref = O.postprocess(head[None], meta, 0.35, thr, class_aware=aware)
+                out = H.postprocess(cu(head[None]), [lb], 0.35, thr, nms_mode=N.NMS_CLASS_AWARE if aware else N.NMS_AGNOSTIC)
+                m = int(out["count"].cpu()[0])
+                rc, rf, rb = G.dets_arrays(ref)
+                assert m == len(ref), (it, thr, aware, m, len(ref))
+                assert np.array_equal(out["cls"][0, :m].cpu().numpy(), rc)
+                assert np.array_equal(out["conf"][0, :m].cpu().numpy().astype(np.float64), rf)
+                assert np.array_equal(out["bbox_xyxy"][0, :m].cpu().numpy().astype(np.float64), rb)
+    H.poll_status()
+    H.close()
+
+
 def test_letterbox_random_geometries(H):
     from realtime_video_analytics_32streams_b200 import _native as N
 

@@ -1,7 +1,7 @@
 """Phase timing of the latency-bound kernels (needs lib/libb200va_timing.so: make -C csrc TIMING=1)."""
 import ctypes as C, os, sys
 os.environ["B200VA_LIB"] = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-                                        "realtime_video_analytics_32streams_b200", "lib", "libb200va_timing.so")
+                                        "realtime_video_analytics_32streams_b200", "lib", os.environ.get("TIMING_LIB", "libb200va_timing.so"))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench as B
@@ -26,7 +26,8 @@ print("tracker phases (SM cycles, block 0): start->staged-issue %d, ->dets stage
       tuple(v[i + 1] - v[i] for i in range(6)))
 print("tracker: phase A %d, phase B %d; first iterations of B: %s" % (v[7] - v[2], v[3] - v[7], [v[9 + i] - v[8 + i] for i in range(7)]))
 print("nms phases: count+keys %d, sort %d, gather %d, chunks %d, filter+emit %d" % tuple(v[16 + i + 1] - v[16 + i] for i in range(5)))
-print("nms chunk loop split: (a) pair matrix %d, (b) resolve %d, (c) tail %d" % (v[24], v[25], v[26]))
+print("nms chunk loop split: (q) grid query (warp 0) %d, (a) pair matrix %d, (b) resolve %d, (c) tail / insert %d" % (v[27], v[24], v[25], v[26]))
+print("grid: max entries per cell %d, overflow list %d, total entries %d" % (v[28], v[29], v[30]))
 print("dets per frame", dets["count"].cpu().tolist()[:8], "tracks", tracks["count"].cpu().tolist()[:8])
 
 # hypothesis check: does a low-occupancy grid (32 CTAs) run slower per instruction than when the rest of the chip is busy?
