@@ -41,6 +41,7 @@ struct PreFrame {
   int xtab, ytab;  // offsets (in 16-byte entries) into the tap arena
   int bulk_ok;     // frame (and mask) rows can be fetched with 16-byte bulk copies
   int out_idx;     // position of this frame in the output batch
+  void* out;       // b200va_resize_linear_u8: this frame's own destination buffer (NULL: PreParams::out + out_idx)
 };
 
 struct PreParams {
@@ -269,7 +270,7 @@ __global__ void __launch_bounds__(kThreads) k_letterbox(const __grid_constant__ 
   const size_t esize = FMT == B200VA_OUT_F32_RGB_NCHW ? 4 : (FMT == B200VA_OUT_F16_RGB_NCHW ? 2 : 1);
   const bool nhwc = FMT == B200VA_OUT_U8_BGR_NHWC;
   // element (frame, plane 0, row_begin, 4*tid) / pixel (frame, row_begin, 4*tid)
-  uint8_t* optr = (uint8_t*)p.out + ((size_t)f.out_idx * 3 * plane) * esize +
+  uint8_t* optr = (f.out ? (uint8_t*)f.out : (uint8_t*)p.out + ((size_t)f.out_idx * 3 * plane) * esize) +
                   (nhwc ? ((size_t)row_begin * p.dst_w + 4 * threadIdx.x) * 3
                         : ((size_t)row_begin * p.dst_w + 4 * threadIdx.x) * esize);
   const size_t row_step = nhwc ? (size_t)p.dst_w * 3 : (size_t)p.dst_w * esize;
@@ -521,7 +522,7 @@ int preprocess_configure(b200va_ctx* h) {
 static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* src_h, const int* src_w,
                         const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks, void* out,
                         const int* new_h, const int* new_w, const int* pad_top, const int* pad_left, int dst_h,
-                        int dst_w, int fmt_and_flags, cudaStream_t st) {
+                        int dst_w, int fmt_and_flags, cudaStream_t st, uint8_t* const* outs = nullptr) {
   const int fmt = fmt_and_flags & 0xff;
   REQUIRE(h, fmt >= 0 && fmt <= 3 && (fmt_and_flags & ~(0xff | B200VA_OUT_FLAG_PADS_VALID)) == 0, "unknown output format %d",
           fmt_and_flags);
@@ -549,6 +550,7 @@ static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* 
         f.src_h = src_h[b];
         f.src_w = src_w[b];
         f.out_idx = b;
+        f.out = outs ? outs[b] : nullptr;
         bool single = true;
         int rc = get_table(h, 0, src_w[b], new_w[b], pad_left[b], dst_w, &f.xtab, nullptr);
         if (rc) return rc;
@@ -594,6 +596,9 @@ static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* 
         case B200VA_OUT_F16_RGB_NCHW: p.vec_ok = (dst_w % 4 == 0) && (ob % 8 == 0); break;
         default: p.vec_ok = (dst_w % 4 == 0) && (ob % 4 == 0) && (frame_elems % 4 == 0); break;
       }
+      if (outs)  // per-frame destinations: every one of them has to allow the vector stores
+        for (int i = 0; i < n; ++i)
+          if ((uintptr_t)outs[idx[base + i]] % 16 != 0) p.vec_ok = 0;
       dim3 grid((dst_h + rpc - 1) / rpc, n);
       const size_t smem = (size_t)stages * per_stage;
       cudaError_t e;
@@ -701,13 +706,35 @@ extern "C" int b200va_resize_linear_u8(b200va_handle h, const uint8_t* const* fr
   DeviceGuard guard(h->cfg.device);
   REQUIRE(h, frames && src_h && src_w && dst && dst_h && dst_w, "NULL argument");
   REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
-  const int zero = 0;
+  // frames that share a destination size go out in ONE launch (per-frame destination pointers); a batch of
+  // streams with the same downsample ratio is one launch, not one per stream
+  std::map<std::pair<int, int>, std::vector<int>> groups;
   for (int b = 0; b < batch; ++b) {
     REQUIRE(h, dst[b] != nullptr, "dst %d is NULL", b);
     REQUIRE(h, dst_h[b] > 0 && dst_w[b] > 0 && dst_w[b] < 65536, "frame %d: bad destination size %dx%d", b, dst_w[b], dst_h[b]);
-    int rc = run_resample(h, frames + b, src_h + b, src_w + b, src_pitch ? src_pitch + b : nullptr, 1,
-                          roi_masks ? roi_masks + b : nullptr, dst[b], dst_h + b, dst_w + b, &zero, &zero, dst_h[b],
-                          dst_w[b], B200VA_OUT_U8_BGR_NHWC, (cudaStream_t)stream);
+    groups[{dst_h[b], dst_w[b]}].push_back(b);
+  }
+  for (const auto& kv : groups) {
+    const std::vector<int>& idx = kv.second;
+    const int n = (int)idx.size();
+    std::vector<const uint8_t*> g_frames(n), g_masks(n);
+    std::vector<uint8_t*> g_out(n);
+    std::vector<int> g_h(n), g_w(n), g_nh(n, kv.first.first), g_nw(n, kv.first.second), g_zero(n, 0);
+    std::vector<int64_t> g_pitch(n);
+    bool any_mask = false;
+    for (int i = 0; i < n; ++i) {
+      const int b = idx[i];
+      g_frames[i] = frames[b];
+      g_masks[i] = roi_masks ? roi_masks[b] : nullptr;
+      any_mask = any_mask || g_masks[i] != nullptr;
+      g_out[i] = dst[b];
+      g_h[i] = src_h[b];
+      g_w[i] = src_w[b];
+      g_pitch[i] = src_pitch ? src_pitch[b] : (int64_t)3 * src_w[b];
+    }
+    int rc = run_resample(h, g_frames.data(), g_h.data(), g_w.data(), g_pitch.data(), n, any_mask ? g_masks.data() : nullptr,
+                          g_out[0], g_nh.data(), g_nw.data(), g_zero.data(), g_zero.data(), kv.first.first, kv.first.second,
+                          B200VA_OUT_U8_BGR_NHWC, (cudaStream_t)stream, g_out.data());
     if (rc) return rc;
   }
   return B200VA_OK;

@@ -161,6 +161,25 @@ def test_downsample_matches_golden_and_oracle(H):
     assert np.array_equal(up, cvr.resize_linear_u8(f, 333, 200))
 
 
+def test_resize_batch_groups_by_destination_size(H):
+    """b200va_resize_linear_u8 for a batch: frames sharing a destination size go out in one launch with per-frame
+    destination pointers; mixed sizes, one ROI mask in the batch, results per frame = cv2.resize restated."""
+    from oracle import cv_restate as cvr
+
+    specs = [(1080, 1920, 540, 960), (1080, 1920, 540, 960), (720, 1280, 540, 960), (1080, 1920, 270, 480),
+             (1083, 1921, 540, 960), (360, 640, 270, 480), (1080, 1920, 540, 960)]
+    frames = [synth.synth_frame(70 + i, h, w) for i, (h, w, _, _) in enumerate(specs)]
+    polys = synth.synth_polygons(77, 1080, 1920)
+    masks = [None] * len(specs)
+    masks[1] = H.roi_rasterize(polys, 1080, 1920)
+    launches0 = H.launch_count
+    outs = H.resize([cu(f) for f in frames], [(dh, dw) for _, _, dh, dw in specs], masks)
+    assert H.launch_count - launches0 == 3  # {540x960 unmasked, 540x960 masked, 270x480}
+    for i, (f, (_, _, dh, dw)) in enumerate(zip(frames, specs)):
+        src = O.apply_roi(f, polys) if i == 1 else f
+        assert np.array_equal(outs[i].cpu().numpy(), cvr.resize_linear_u8(src, dw, dh)), i
+
+
 # ------------------------------------------------------------------------------------------------
 # a9: ROI
 # ------------------------------------------------------------------------------------------------
