@@ -214,6 +214,21 @@ B200VA_API int b200va_motion(b200va_handle h, const uint8_t* const* frames, cons
                   const uint8_t* const* prev_gray, uint8_t* const* next_gray, const int* has_prev,
                   int32_t* changed_out, void* stream);
 
+/* ---- a11 + a1 in one pass: motion gate and letterbox from the same staged rows ------------------
+ * b200va_motion and b200va_preprocess (reference letterbox geometry) on the same frames in ONE pass over each
+ * frame: the motion gate reads every pixel anyway, so the network input is interpolated from the rows it has
+ * staged in shared memory instead of reading the tapped rows and their ROI-mask rows from HBM a second time.
+ * Arguments as in b200va_motion followed by those of b200va_preprocess; out_format is
+ * B200VA_OUT_F32_RGB_NCHW or B200VA_OUT_F16_RGB_NCHW (optionally | B200VA_OUT_FLAG_PADS_VALID).  Results are
+ * identical to the two separate calls.  Frames the fused kernel cannot take (unaligned base / pitch, width
+ * not a multiple of 16, up-scaling geometry) run through the two separate kernels inside this call.
+ * The letterbox of a frame the motion gate then rejects is wasted work (4.9 MB of writes per frame). */
+B200VA_API int b200va_motion_preprocess(b200va_handle h, const uint8_t* const* frames, const int* src_h, const int* src_w,
+                                        const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks,
+                                        const uint8_t* const* prev_gray, uint8_t* const* next_gray, const int* has_prev,
+                                        int32_t* changed_out, void* out, int dst_h, int dst_w, int out_format,
+                                        b200va_letterbox* meta_out, void* stream);
+
 /* ---- a3-a7: head post-process --------------------------------------------------------
  * Replaces _TensorRTBaseDetector._postprocess (detector.py:266-338), _xywh2xyxy (:352-359),
  * _scale_boxes (:340-350), _nms (:361-375) + _iou (:469-481), and folds in

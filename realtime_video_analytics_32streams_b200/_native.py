@@ -103,6 +103,7 @@ EXPORTS = (
     "b200va_postprocess", "b200va_tracker_update", "b200va_tracker_update_f64", "b200va_tracker_reset",
     "b200va_tracker_set_next_id", "b200va_upload_frames", "b200va_dfl_decode", "b200va_tick",
     "b200va_letterbox_meta_ultralytics", "b200va_preprocess_geom", "b200va_postprocess_ultralytics",
+    "b200va_motion_preprocess",
 )
 
 _lib = None
@@ -148,6 +149,8 @@ def load_library() -> C.CDLL:
     lib.b200va_upload_frames.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), ip, ip, i64p, i64p, C.c_int, C.c_int,
                                          C.c_int, C.c_int, i64p, vp]
     lib.b200va_dfl_decode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, ip, C.POINTER(C.c_float), C.c_int, vp, vp]
+    lib.b200va_motion_preprocess.argtypes = [vp, C.POINTER(vp), ip, ip, i64p, C.c_int, C.POINTER(vp), C.POINTER(vp),
+                                             C.POINTER(vp), ip, vp, vp, C.c_int, C.c_int, C.c_int, C.POINTER(Letterbox), vp]
     lib.b200va_tick.argtypes = [vp, C.POINTER(TickArgs), vp]
     lib.b200va_letterbox_meta_ultralytics.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                                       C.POINTER(Letterbox), ip, ip]
@@ -366,6 +369,31 @@ class Handle:
                 _ptr_array([n.data_ptr() for n in next_gray]), has_prev, C.c_void_p(changed_out.data_ptr()),
                 self._stream()))
         return changed_out
+
+    # -- a11 + a1 fused -----------------------------------------------------------------------
+    def motion_preprocess(self, frames, prev_gray, next_gray, dst_hw=(640, 640), fmt: int = OUT_F32_RGB_NCHW,
+                          roi_masks=None, changed_out=None, out=None):
+        """``motion`` and ``preprocess`` of the same frames in one pass over each frame.
+        Returns (changed counts int32 [B], network input [B,3,H,W], list of Letterbox)."""
+        t = self.torch
+        fb = self._batch(frames, roi_masks)
+        b = fb.n
+        dh, dw = int(dst_hw[0]), int(dst_hw[1])
+        dtype = {OUT_F32_RGB_NCHW: t.float32, OUT_F16_RGB_NCHW: t.float16}[fmt & 0xff]
+        if out is None:
+            out = t.empty((b, 3, dh, dw), dtype=dtype, device=self.device)
+        elif tuple(out.shape) != (b, 3, dh, dw) or out.dtype != dtype or not out.is_contiguous():
+            raise ValueError("motion_preprocess: `out` has the wrong shape / dtype / layout")
+        if changed_out is None:
+            changed_out = t.empty((b,), dtype=t.int32, device=self.device)
+        if b:
+            has_prev = _int_array([0 if p is None else 1 for p in prev_gray])
+            self._check(self.lib.b200va_motion_preprocess(
+                self._h, fb.ptrs, fb.hs, fb.ws, fb.pitch, b, fb.mask_ptrs,
+                _ptr_array([p.data_ptr() if p is not None else None for p in prev_gray]),
+                _ptr_array([n.data_ptr() for n in next_gray]), has_prev, C.c_void_p(changed_out.data_ptr()),
+                C.c_void_p(out.data_ptr()), dh, dw, fmt, fb.metas, self._stream()))
+        return changed_out, out, [fb.metas[i] for i in range(b)]
 
     # -- a3-a7 ------------------------------------------------------------------------------
     _DET_FIELDS = (("bbox_xyxy", "float32", 4), ("conf", "float32", 1), ("cls", "int32", 1))

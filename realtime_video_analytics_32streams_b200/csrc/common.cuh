@@ -118,6 +118,29 @@ struct DeviceGuard {
   }
 };
 
+// ---- letterbox tap tables (preprocess.cu builds them; filters.cu's fused pass reads them too) ----
+struct __align__(16) TapX {
+  int off0, off1;  // byte offsets of the two taps inside a source row; off0 < 0: pad column
+  short a0, a1;    // 11-bit coefficients
+  int mx0;         // x0 | (x1 << 16): pixel indices for the ROI mask row
+};
+struct __align__(16) TapY {
+  int y0, y1;  // source rows; y0 < 0: pad row
+  short b0, b1;
+  int pad_;
+};
+
+// What the fused motion + letterbox pass needs for one (source size, letterbox geometry): arena offsets (in 16-byte
+// entries) of the column / row tap tables, of rowmap[src_h] (destination row whose FIRST source row is r, or -1)
+// and of colstart[strips + 1] (first destination column whose first tap lies in 256-pixel strip s).
+struct FusePlan {
+  int xtab, ytab, rowmap, colstart;
+  bool eligible;  // every destination row taps rows (y0, y0 + 1) or y0 alone, y0 strictly increasing; same for columns
+};
+int letterbox_fuse_plan(b200va_ctx* h, int src_h, int src_w, int new_h, int new_w, int pad_top, int pad_left, int dst_h,
+                        int dst_w, FusePlan* out);
+const int4* tap_arena(b200va_ctx* h);
+
 // per-module state owned by the handle
 int tap_cache_create(b200va_ctx* h);
 void tap_cache_destroy(b200va_ctx* h);

@@ -10,6 +10,8 @@
 //   BGR2GRAY   = (B*3735 + G*19235 + R*9798 + 16384) >> 15
 //   Gaussian   = separable [1 4 6 4 1], BORDER_REFLECT_101, one rounding (sum + 128) >> 8
 //   motion     = count(|new - prev| > 25); the new blurred gray always replaces the state.
+#include <cuda_fp16.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -484,7 +486,8 @@ constexpr int kTilePrev = kTileStrips * kStripPx;
 constexpr int kTileStage = kTileRaw + kTileMsk + kTilePrev;  // 10304, a multiple of 16
 constexpr int kTileStages = 5;                               // = the row-loop unroll factor
 constexpr int kTileThreads = (kTileStrips + 1) * 32;
-constexpr int kTileSmem = kTileStages * kTileStage + 2 * kTileStages * 8;
+constexpr int kTileRowsMax = 64;  // rows_per_task never exceeds this
+constexpr int kTileSmem = kTileStages * kTileStage + 2 * kTileStages * 8 + kTileRowsMax * 8;  // stages, barriers, fused-pass row table
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t d;
@@ -504,8 +507,96 @@ __device__ __forceinline__ uint32_t gray_ph3(uint32_t w0, uint32_t w1) { return 
 __device__ __forceinline__ uint32_t gray_ph6(uint32_t w1, uint32_t w2) { return __dp2a_lo(kR0, w2, __dp2a_hi(kBG, w1, kRnd)); }
 __device__ __forceinline__ uint32_t gray_ph9(uint32_t w2) { return __dp2a_hi(kGR, w2, __dp2a_lo(k0B, w2, kRnd)); }
 
-template <bool MASK>
-__global__ void __launch_bounds__(kTileThreads, 3) k_motion_tile(const __grid_constant__ MotionParams p) {
+// ---- fused letterbox (b200va_motion_preprocess) ---------------------------------------------------
+// The motion pass already stages every byte of the frame (and of its ROI mask) in shared memory, so the network
+// input can be produced from the same staged rows instead of reading the tapped rows (and their mask rows) from
+// HBM a second time: 11 MB of the 16 MB the masked 4K letterbox moves per frame.  When the row that has just
+// arrived is the SECOND source row of a destination row d (rowmap[r - 1] = d; the first one is still in the
+// previous stage: stages are released one row late in this variant), the warp interpolates the destination
+// columns whose first tap lies in its 256-pixel strip -- OpenCV's two-tap fixed-point formula, unchanged -- and
+// writes them to the planar output.  Pad rows / columns come from k_lb_pads.
+struct LbFrame {
+  int xtab, ytab, rowmap, colstart;  // offsets into the tap arena (16-byte entries)
+  int out_idx;                       // position in the output batch
+};
+constexpr int kFuseFrames = 32;  // per launch: the parameter block stays below 4 KB
+struct MotionLbParams {
+  MotionFrame f[kFuseFrames];
+  LbFrame lb[kFuseFrames];
+  int32_t* changed;
+  int rows_per_task;
+  const int4* tabs;
+  void* out;
+  int dst_h, dst_w;
+};
+static_assert(sizeof(MotionLbParams) <= 4000, "kernel parameter block too large");
+
+// one destination row, the columns [cb, ce) of this warp's strip; s0 / s1 = stages holding source rows y0 / y0 + 1
+template <int LB, bool MASK>
+__device__ __forceinline__ void lb_row(const uint8_t* __restrict__ s0, const uint8_t* __restrict__ s1,
+                                       const TapX* __restrict__ xt, const TapY ty, int cb, int ce, int lane, int tile_x0,
+                                       void* out_row0, size_t plane) {
+  const int b0 = ty.b0, b1 = ty.b1;
+  const int base = 16 - 3 * tile_x0, mbase = kTileRaw + 16 - tile_x0;
+  for (int c = cb + lane; c < ce; c += 32) {
+    const int4 e = __ldg(reinterpret_cast<const int4*>(xt) + c);
+    const TapX t = *reinterpret_cast<const TapX*>(&e);
+    const int o0 = base + t.off0, o1 = base + t.off1;
+    int a0 = t.a0, a1 = t.a1, c0 = a0, c1 = a1;
+    if (MASK) {  // apply_roi zeroes masked source pixels before the resize (pipeline.py:149-154)
+      const int m0 = mbase + (t.mx0 & 0xffff), m1 = mbase + ((unsigned)t.mx0 >> 16);
+      a0 = s0[m0] ? a0 : 0;
+      a1 = s0[m1] ? a1 : 0;
+      c0 = s1[m0] ? c0 : 0;
+      c1 = s1[m1] ? c1 : 0;
+    }
+    int v[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const int r0 = (int)s0[o0 + ch] * a0 + (int)s0[o1 + ch] * a1;
+      const int r1 = b1 ? (int)s1[o0 + ch] * c0 + (int)s1[o1 + ch] * c1 : 0;
+      v[ch] = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2;
+    }
+    if (LB == B200VA_OUT_F32_RGB_NCHW) {
+      const float k = __int_as_float(0x3B808081);  // float32(1.0/255.0), detector.py:251
+      float* o = (float*)out_row0 + c;
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) o[pl * plane] = __fmul_rn((float)v[2 - pl], k);
+    } else {
+      const float k = 0.0039215087890625f;  // float(float16(1.0/255.0))
+      __half* o = (__half*)out_row0 + c;
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) o[pl * plane] = __float2half_rn(__fmul_rn((float)v[2 - pl], k));
+    }
+  }
+}
+
+// pad rows and pad columns of the fused pass's output (copyMakeBorder value 114, detector.py:233-241)
+template <int LB>
+__global__ void __launch_bounds__(256) k_lb_pads(const __grid_constant__ MotionLbParams p) {
+  const LbFrame& L = p.lb[blockIdx.y];
+  const int d = blockIdx.x;
+  const TapX* xt = reinterpret_cast<const TapX*>(p.tabs + L.xtab);
+  const TapY ty = *reinterpret_cast<const TapY*>(p.tabs + L.ytab + d);
+  const size_t plane = (size_t)p.dst_h * p.dst_w;
+  const bool pad_row = ty.y0 < 0;
+  for (int c = threadIdx.x; c < p.dst_w; c += blockDim.x) {
+    if (!pad_row && xt[c].off0 >= 0) continue;
+    const size_t o = (size_t)L.out_idx * 3 * plane + (size_t)d * p.dst_w + c;
+    if (LB == B200VA_OUT_F32_RGB_NCHW) {
+      const float v = __fmul_rn(114.f, __int_as_float(0x3B808081));
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) ((float*)p.out)[o + pl * plane] = v;
+    } else {
+      const __half v = __float2half_rn(__fmul_rn(114.f, 0.0039215087890625f));
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) ((__half*)p.out)[o + pl * plane] = v;
+    }
+  }
+}
+
+template <bool MASK, int LB, typename P>
+__global__ void __launch_bounds__(kTileThreads, 3) k_motion_tile(const __grid_constant__ P p) {
   extern __shared__ __align__(16) uint8_t s_tile[];
   uint64_t* const full = reinterpret_cast<uint64_t*>(s_tile + kTileStages * kTileStage);
   uint64_t* const empty = full + kTileStages;
@@ -531,6 +622,22 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_motion_tile(const __grid_co
       mbar_init(&empty[s], (uint32_t)n_warps);
     }
     mbar_fence_init();
+  }
+  // fused letterbox: which rows of this tile are the first source row of a destination row, and that row's
+  // vertical weights -- looked up once per CTA, so the row loop never waits for a global load
+  int2* const s_lbrow = reinterpret_cast<int2*>(empty + kTileStages);
+  if constexpr (LB >= 0) {
+    const LbFrame& L = p.lb[blockIdx.y];
+    for (int i = threadIdx.x; i < ye - yb; i += kTileThreads) {
+      const int d = __ldg(reinterpret_cast<const int*>(p.tabs + L.rowmap) + yb + i);
+      int wts = 0;
+      if (d >= 0) {
+        const int4 te = __ldg(p.tabs + L.ytab + d);
+        const TapY ty = *reinterpret_cast<const TapY*>(&te);
+        wts = (int)(uint16_t)ty.b0 | ((int)(uint16_t)ty.b1 << 16);
+      }
+      s_lbrow[i] = make_int2(d, wts);
+    }
   }
   __syncthreads();
 
@@ -570,6 +677,24 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_motion_tile(const __grid_co
   const int msk_off = kTileRaw + 16 + warp * kStripPx + 8 * lane;
   const int prv_off = kTileRaw + kTileMsk + warp * kStripPx + 8 * lane;
   uint8_t* out_ptr = f.next + (size_t)yb * W + xl;
+  // fused letterbox: this warp's destination columns and the tables of the frame
+  const TapX* lb_xt = nullptr;
+  const int4* lb_yt = nullptr;
+  const int* lb_rowmap = nullptr;
+  int lb_cb = 0, lb_ce = 0;
+  size_t lb_plane = 0;
+  uint8_t* lb_out = nullptr;
+  if constexpr (LB >= 0) {
+    const LbFrame& L = p.lb[blockIdx.y];
+    lb_xt = reinterpret_cast<const TapX*>(p.tabs + L.xtab);
+    lb_yt = p.tabs + L.ytab;
+    lb_rowmap = reinterpret_cast<const int*>(p.tabs + L.rowmap);
+    const int* cs = reinterpret_cast<const int*>(p.tabs + L.colstart);
+    lb_cb = __ldg(cs + x0 / kStripPx);
+    lb_ce = __ldg(cs + x0 / kStripPx + 1);
+    lb_plane = (size_t)p.dst_h * p.dst_w;
+    lb_out = (uint8_t*)p.out + (size_t)L.out_idx * 3 * lb_plane * (LB == B200VA_OUT_F32_RGB_NCHW ? 4 : 2);
+  }
 
   uint32_t ring[5][4];
 #pragma unroll
@@ -643,8 +768,32 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_motion_tile(const __grid_co
         if (live) *reinterpret_cast<uint2*>(out_ptr) = make_uint2(o0, o1);
         out_ptr += W;
       }
-      __syncwarp();  // every lane has read this stage
-      if (lane == 0) mbar_arrive(&empty[u]);
+      if constexpr (LB >= 0) {
+        const int rp = r_first + k - 1;  // the previous row (still staged): first source row of a destination row?
+        if (k >= 1 && rp >= yb && rp < ye) {
+          const int2 e = s_lbrow[rp - yb];
+          if (e.x >= 0) {
+            // everything else the rare path needs is re-derived from the parameter block here, so that none of it
+            // stays live across the motion loop (hoisted, it cost 30 registers and one CTA per SM)
+            const LbFrame& L = p.lb[blockIdx.y];
+            const int d = e.x;
+            TapY ty;
+            ty.b0 = (short)(e.y & 0xffff);
+            ty.b1 = (short)((unsigned)e.y >> 16);
+            const int* cs = reinterpret_cast<const int*>(p.tabs + L.colstart) + x0 / kStripPx;
+            const size_t esz = LB == B200VA_OUT_F32_RGB_NCHW ? 4 : 2;
+            const size_t plane = (size_t)p.dst_h * p.dst_w;
+            uint8_t* orow = (uint8_t*)p.out + ((size_t)L.out_idx * 3 * plane + (size_t)d * p.dst_w) * esz;
+            lb_row<LB, MASK>(s_tile + ((u + 4) % 5) * kTileStage, st, reinterpret_cast<const TapX*>(p.tabs + L.xtab), ty,
+                             __ldg(cs), __ldg(cs + 1), lane, tile_x0, orow, plane);
+          }
+        }
+        __syncwarp();  // every lane has read this stage and the previous one
+        if (lane == 0 && k >= 1) mbar_arrive(&empty[(u + 4) % 5]);  // released one row late
+      } else {
+        __syncwarp();  // every lane has read this stage
+        if (lane == 0) mbar_arrive(&empty[u]);
+      }
     }
     parity ^= 1u;
   }
@@ -661,8 +810,12 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_motion_tile(const __grid_co
 }  // namespace
 
 int filters_configure(b200va_ctx* h) {  // called by b200va_create on the handle's device
-  CUDA_TRY(h, cudaFuncSetAttribute(k_motion_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
-  CUDA_TRY(h, cudaFuncSetAttribute(k_motion_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_motion_tile<true, -1, MotionParams>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_motion_tile<false, -1, MotionParams>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_motion_tile<true, 0, MotionLbParams>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_motion_tile<false, 0, MotionLbParams>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_motion_tile<true, 1, MotionLbParams>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_motion_tile<false, 1, MotionLbParams>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem));
   return B200VA_OK;
 }
 
@@ -857,12 +1010,127 @@ extern "C" int b200va_motion(b200va_handle h, const uint8_t* const* frames, cons
       p.changed = changed_out;
       if (tile) {
         dim3 grid(max_tasks, n);
-        if (with_mask) k_motion_tile<true><<<grid, kTileThreads, kTileSmem, st>>>(p);
-        else k_motion_tile<false><<<grid, kTileThreads, kTileSmem, st>>>(p);
+        if (with_mask) k_motion_tile<true, -1, MotionParams><<<grid, kTileThreads, kTileSmem, st>>>(p);
+        else k_motion_tile<false, -1, MotionParams><<<grid, kTileThreads, kTileSmem, st>>>(p);
       } else {
         dim3 grid((max_tasks + kMotionWarps - 1) / kMotionWarps, n);
         if (with_mask) k_motion<true><<<grid, kMotionWarps * 32, 0, st>>>(p, 0);
         else k_motion<false><<<grid, kMotionWarps * 32, 0, st>>>(p, 0);
+      }
+      LAUNCH_CHECK(h);
+    }
+  }
+  return B200VA_OK;
+}
+
+// ---- a11 + a1 in one pass over the frame ----------------------------------------------------------
+extern "C" int b200va_motion_preprocess(b200va_handle h, const uint8_t* const* frames, const int* src_h, const int* src_w,
+                                        const int64_t* src_pitch, int batch, const uint8_t* const* roi_masks,
+                                        const uint8_t* const* prev_gray, uint8_t* const* next_gray, const int* has_prev,
+                                        int32_t* changed_out, void* out, int dst_h, int dst_w, int out_format,
+                                        b200va_letterbox* meta_out, void* stream) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  REQUIRE(h, frames && src_h && src_w && next_gray && has_prev && changed_out && out, "NULL argument");
+  REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
+  REQUIRE(h, dst_h > 0 && dst_w > 0 && dst_w < 65536, "bad destination size %dx%d", dst_w, dst_h);
+  const int fmt = out_format & 0xff;
+  REQUIRE(h, (fmt == B200VA_OUT_F32_RGB_NCHW || fmt == B200VA_OUT_F16_RGB_NCHW) &&
+                 (out_format & ~(0xff | B200VA_OUT_FLAG_PADS_VALID)) == 0,
+          "b200va_motion_preprocess writes B200VA_OUT_F32_RGB_NCHW or B200VA_OUT_F16_RGB_NCHW, not format %d", out_format);
+  if (batch == 0) return B200VA_OK;
+  const size_t esz = fmt == B200VA_OUT_F32_RGB_NCHW ? 4 : 2;
+  const size_t frame_bytes = (size_t)3 * dst_h * dst_w * esz;
+  CUDA_TRY(h, cudaMemsetAsync(changed_out, 0, sizeof(int32_t) * batch, st));
+
+  std::vector<int> fused[2];  // by ROI mask
+  std::vector<FusePlan> plans(batch);
+  std::vector<b200va_letterbox> metas(batch);
+  for (int b = 0; b < batch; ++b) {
+    REQUIRE(h, frames[b] && next_gray[b], "frame %d: NULL frame or state buffer", b);
+    REQUIRE(h, src_h[b] > 0 && src_w[b] > 0, "frame %d has bad size", b);
+    REQUIRE(h, !has_prev[b] || (prev_gray && prev_gray[b]), "frame %d: has_prev without a previous buffer", b);
+    REQUIRE(h, !has_prev[b] || prev_gray[b] != next_gray[b], "frame %d: prev_gray and next_gray alias", b);
+    const int64_t pitch = src_pitch ? src_pitch[b] : (int64_t)3 * src_w[b];
+    REQUIRE(h, pitch >= (int64_t)3 * src_w[b], "frame %d: pitch smaller than 3*width", b);
+    b200va_letterbox& m = metas[b];
+    REQUIRE(h, b200va_letterbox_meta(src_h[b], src_w[b], dst_h, dst_w, &m) == B200VA_OK && m.new_h > 0 && m.new_w > 0,
+            "frame %d: bad size %dx%d", b, src_w[b], src_h[b]);
+    if (meta_out) meta_out[b] = m;
+    const bool with_mask = roi_masks && roi_masks[b];
+    const bool aligned = (src_w[b] % 16 == 0) && ((uintptr_t)frames[b] % 16 == 0) && (pitch % 16 == 0) &&
+                         ((uintptr_t)next_gray[b] % 16 == 0) && (!has_prev[b] || (uintptr_t)prev_gray[b] % 16 == 0) &&
+                         (!with_mask || (uintptr_t)roi_masks[b] % 16 == 0);
+    bool ok = aligned && src_w[b] >= 4 && src_h[b] >= 4;
+    if (ok) {
+      int rc = letterbox_fuse_plan(h, src_h[b], src_w[b], m.new_h, m.new_w, m.pad_top, m.pad_left, dst_h, dst_w, &plans[b]);
+      if (rc) return rc;
+      ok = plans[b].eligible;
+    }
+    if (ok) {
+      fused[with_mask ? 1 : 0].push_back(b);
+    } else {
+      // not a fusable frame (unaligned, tiny, or an up-scaling geometry): the two separate kernels, same results
+      const uint8_t* one_mask = with_mask ? roi_masks[b] : nullptr;
+      const uint8_t* one_prev = has_prev[b] ? prev_gray[b] : nullptr;
+      int rc = b200va_motion(h, frames + b, src_h + b, src_w + b, &pitch, 1, &one_mask, &one_prev, next_gray + b, has_prev + b,
+                             changed_out + b, stream);
+      if (rc) return rc;
+      rc = b200va_preprocess(h, frames + b, src_h + b, src_w + b, &pitch, 1, &one_mask, (uint8_t*)out + (size_t)b * frame_bytes,
+                             dst_h, dst_w, out_format, nullptr, stream);
+      if (rc) return rc;
+    }
+  }
+  for (int with_mask = 0; with_mask < 2; ++with_mask) {
+    const std::vector<int>& idx = fused[with_mask];
+    for (size_t base = 0; base < idx.size(); base += kFuseFrames) {
+      const int n = (int)std::min<size_t>(kFuseFrames, idx.size() - base);
+      MotionLbParams p;
+      memset(&p, 0, sizeof(p));
+      long long total_px = 0;
+      for (int i = 0; i < n; ++i) total_px += (long long)src_h[idx[base + i]] * src_w[idx[base + i]];
+      int rows = 64;
+      while (rows > 8 && total_px / ((long long)rows * kTileStrips * kStripPx) < (long long)h->num_sms * 3 * 5) rows >>= 1;
+      p.rows_per_task = rows;
+      int max_tasks = 0;
+      for (int i = 0; i < n; ++i) {
+        const int b = idx[base + i];
+        MotionFrame& f = p.f[i];
+        f.src = frames[b];
+        f.mask = with_mask ? roi_masks[b] : nullptr;
+        f.prev = has_prev[b] ? prev_gray[b] : nullptr;
+        f.next = next_gray[b];
+        f.pitch = src_pitch ? src_pitch[b] : 3ll * src_w[b];
+        f.h = src_h[b];
+        f.w = src_w[b];
+        f.has_prev = has_prev[b] ? 1 : 0;
+        f.out_idx = b;
+        f.fast = 1;
+        p.lb[i] = LbFrame{plans[b].xtab, plans[b].ytab, plans[b].rowmap, plans[b].colstart, b};
+        const int per_row = (f.w + kTileStrips * kStripPx - 1) / (kTileStrips * kStripPx);
+        const int row_tasks = (f.h + rows - 1) / rows;
+        if (per_row * row_tasks > max_tasks) max_tasks = per_row * row_tasks;
+      }
+      p.changed = changed_out;
+      p.tabs = tap_arena(h);
+      p.out = out;
+      p.dst_h = dst_h;
+      p.dst_w = dst_w;
+      if (!(out_format & B200VA_OUT_FLAG_PADS_VALID)) {
+        dim3 pgrid(dst_h, n);
+        if (fmt == B200VA_OUT_F32_RGB_NCHW) k_lb_pads<0><<<pgrid, 256, 0, st>>>(p);
+        else k_lb_pads<1><<<pgrid, 256, 0, st>>>(p);
+        LAUNCH_CHECK(h);
+      }
+      dim3 grid(max_tasks, n);
+      if (fmt == B200VA_OUT_F32_RGB_NCHW) {
+        if (with_mask) k_motion_tile<true, 0, MotionLbParams><<<grid, kTileThreads, kTileSmem, st>>>(p);
+        else k_motion_tile<false, 0, MotionLbParams><<<grid, kTileThreads, kTileSmem, st>>>(p);
+      } else {
+        if (with_mask) k_motion_tile<true, 1, MotionLbParams><<<grid, kTileThreads, kTileSmem, st>>>(p);
+        else k_motion_tile<false, 1, MotionLbParams><<<grid, kTileThreads, kTileSmem, st>>>(p);
       }
       LAUNCH_CHECK(h);
     }

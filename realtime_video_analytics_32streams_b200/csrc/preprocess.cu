@@ -22,17 +22,6 @@
 
 namespace {
 
-struct __align__(16) TapX {
-  int off0, off1;  // byte offsets of the two taps inside a source row; off0 < 0: pad column
-  short a0, a1;    // 11-bit coefficients
-  int mx0;         // x0 | (x1 << 16): pixel indices for the ROI mask row
-};
-struct __align__(16) TapY {
-  int y0, y1;  // source rows; y0 < 0: pad row
-  short b0, b1;
-  int pad_;
-};
-
 struct PreFrame {
   const uint8_t* src;
   const uint8_t* mask;  // optional ROI mask [src_h, src_w], 0 = outside
@@ -474,6 +463,81 @@ static int get_table(b200va_ctx* h, int axis, int src, int dst_new, int pad, int
   if (single_out) *single_out = single;
   return B200VA_OK;
 }
+
+// Auxiliary int tables for the fused pass, cached in the same arena under axis ids 2 (rowmap) and 3 (colstart).
+static int get_aux_table(b200va_ctx* h, int axis, int src, int dst_new, int pad, int dst_full, int* off_out, bool* ok_out) {
+  TapCache* tc = h->taps;
+  TapKey key{axis, src, dst_new, pad, dst_full};
+  auto it = tc->index.find(key);
+  if (it != tc->index.end()) {
+    *off_out = it->second.off;
+    *ok_out = it->second.single;
+    return B200VA_OK;
+  }
+  std::vector<int> vals;
+  bool ok = true;
+  if (axis == 2) {  // rowmap
+    vals.assign((size_t)src, -1);
+    int prev_y0 = -1;
+    for (int k = 0; k < dst_new; ++k) {
+      int y0, y1;
+      short b0, b1;
+      linear_tap(src, dst_new, k, false, &y0, &y1, &b0, &b1);
+      if (!(y0 > prev_y0) || !(b1 == 0 || y1 == y0 + 1) || y0 < 0 || y0 >= src) ok = false;
+      else vals[(size_t)y0] = k + pad;
+      prev_y0 = y0;
+    }
+  } else {  // colstart
+    const int strips = (src + 255) / 256;
+    vals.assign((size_t)strips + 1, pad + dst_new);
+    int prev_x0 = -1, s_next = 0;
+    for (int k = 0; k < dst_new; ++k) {
+      int x0, x1;
+      short a0, a1;
+      linear_tap(src, dst_new, k, true, &x0, &x1, &a0, &a1);
+      if (x0 < prev_x0 || !(a1 == 0 || x1 == x0 + 1 || x1 == x0)) ok = false;
+      prev_x0 = x0;
+      while (s_next <= strips && s_next * 256 <= x0) vals[(size_t)s_next++] = k + pad;
+    }
+  }
+  const size_t entries = (vals.size() + 3) / 4;
+  vals.resize(entries * 4, -1);
+  if (tc->used + entries > tc->capacity) {
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    tc->index.clear();
+    tc->used = 0;
+    if (entries > tc->capacity) return set_error(h, B200VA_ERR_CAPACITY, "table of %zu entries does not fit", entries);
+  }
+  const int off = (int)tc->used;
+  CUDA_TRY(h, cudaMemcpy(tc->arena + off, vals.data(), entries * sizeof(int4), cudaMemcpyHostToDevice));
+  tc->used += entries;
+  tc->index[key] = TapCache::Entry{off, ok};
+  *off_out = off;
+  *ok_out = ok;
+  return B200VA_OK;
+}
+
+int letterbox_fuse_plan(b200va_ctx* h, int src_h, int src_w, int new_h, int new_w, int pad_top, int pad_left, int dst_h,
+                        int dst_w, FusePlan* out) {
+  bool ok_r = false, ok_c = false;
+  // the aux tables first: they may reset the arena, the tap tables fetched after them stay valid
+  int rc = get_aux_table(h, 2, src_h, new_h, pad_top, dst_h, &out->rowmap, &ok_r);
+  if (rc) return rc;
+  rc = get_aux_table(h, 3, src_w, new_w, pad_left, dst_w, &out->colstart, &ok_c);
+  if (rc) return rc;
+  rc = get_table(h, 0, src_w, new_w, pad_left, dst_w, &out->xtab, nullptr);
+  if (rc) return rc;
+  rc = get_table(h, 1, src_h, new_h, pad_top, dst_h, &out->ytab, nullptr);
+  if (rc) return rc;
+  // a reset in between would have dropped the earlier offsets: make sure all four are still cached
+  TapCache* tc = h->taps;
+  const bool all_cached = tc->index.count(TapKey{2, src_h, new_h, pad_top, dst_h}) && tc->index.count(TapKey{3, src_w, new_w, pad_left, dst_w}) &&
+                          tc->index.count(TapKey{0, src_w, new_w, pad_left, dst_w}) && tc->index.count(TapKey{1, src_h, new_h, pad_top, dst_h});
+  out->eligible = ok_r && ok_c && all_cached;
+  return B200VA_OK;
+}
+
+const int4* tap_arena(b200va_ctx* h) { return h->taps->arena; }
 
 extern "C" int b200va_letterbox_meta(int src_h, int src_w, int dst_h, int dst_w, b200va_letterbox* out) {
   if (!out || src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0) return B200VA_ERR_INVALID;

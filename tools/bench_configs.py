@@ -99,9 +99,24 @@ def config4(B=32):
                ("postprocess", lambda k: h.postprocess(heads[k % sets], metas, 0.35, 0.5, filter_conf=0.35, out=dets)),
                ("tracker", lambda k: h.tracker_update(slots, dets, 30, 1, 0.5, out=tracks))], args.steps)
     h.poll_status()
+    # the same two steps as ONE pass over each frame (b200va_motion_preprocess)
+    rf = timed([("fused", lambda k: h.motion_preprocess(batches[k % sets], gray[(k + 1) % 2], gray[k % 2], (640, 640), 0,
+                                                        changed_out=changed, out=net))], args.steps)
+    rp = timed([("fused", lambda k: h.motion_preprocess(batches[k % sets], gray[(k + 1) % 2], gray[k % 2], (640, 640),
+                                                        0 | _native.OUT_FLAG_PADS_VALID, changed_out=changed, out=net))],
+               args.steps)
+    h.poll_status()
+    fused_bytes = B * (H * W * 3 + 3 * H * W + 3 * 640 * 640 * 4)  # frame + mask + prev gray + new gray + network input
+    r["motion+preprocess fused"] = rf["fused"]
+    r["motion+preprocess fused, pad rows kept"] = rp["fused"]
+    r["fused_GBps"] = fused_bytes / (rf["fused"] * 1e-3) / 1e9
+    r["fused_frac_of_peak"] = r["fused_GBps"] / PEAK
+    r["fused_algorithmic_bytes"] = fused_bytes
+    r["tick_total_fused"] = rf["fused"] + r["postprocess"] + r["tracker"]
     motion_bytes = B * (H * W * 3 + 3 * H * W)  # frame + mask + prev gray + new gray
     pre_bytes = B * (720 * W * 3 + 720 * W + 3 * 640 * 640 * 4)  # tapped rows (+ their mask rows) + output
-    r.update(config="4: 32x4K + ROI + motion", streams=B, frame=[H, W], frames_per_s=B / (r["tick_total"] * 1e-3),
+    r.update(config="4: 32x4K + ROI + motion", streams=B, frame=[H, W], frames_per_s=B / (r["tick_total_fused"] * 1e-3),
+             frames_per_s_separate_kernels=B / (r["tick_total"] * 1e-3),
              motion_GBps=motion_bytes / (r["motion(+roi)"] * 1e-3) / 1e9, motion_frac_of_peak=motion_bytes / (r["motion(+roi)"] * 1e-3) / 1e9 / PEAK,
              preprocess_GBps=pre_bytes / (r["preprocess(+roi)"] * 1e-3) / 1e9,
              preprocess_frac_of_peak=pre_bytes / (r["preprocess(+roi)"] * 1e-3) / 1e9 / PEAK,
