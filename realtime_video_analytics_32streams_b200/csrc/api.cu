@@ -57,6 +57,13 @@ static int create_impl(b200va_ctx* h) {
   if (rc) return rc;
   rc = tracker_state_create(h);
   if (rc) return rc;
+  if (cudaHostAlloc((void**)&h->nms_stats_host, 64, cudaHostAllocMapped) == cudaSuccess) {
+    memset(h->nms_stats_host, 0, 64);
+    if (cudaHostGetDevicePointer((void**)&h->nms_stats_dev, h->nms_stats_host, 0) != cudaSuccess) h->nms_stats_dev = nullptr;
+  } else {
+    cudaGetLastError();
+    h->nms_stats_host = nullptr;
+  }
   int prio_lo = 0, prio_hi = 0;
   CUDA_TRY(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   CUDA_TRY(h, cudaStreamCreateWithPriority(&h->side_stream, cudaStreamNonBlocking, prio_hi));
@@ -98,6 +105,7 @@ extern "C" int b200va_destroy(b200va_handle h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_decoded) cudaEventDestroy(h->ev_decoded);
+    if (h->nms_stats_host) cudaFreeHost(h->nms_stats_host);
     if (h->cand_key) cudaFree(h->cand_key);
     if (h->cand_box) cudaFree(h->cand_box);
     if (h->cand_cls) cudaFree(h->cand_cls);

@@ -54,6 +54,10 @@ struct b200va_ctx {
   cudaStream_t side_stream = nullptr;    // non-blocking, highest priority (its 32-CTA kernels slot in first)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_decoded = nullptr;
   cudaEvent_t hook_after_decode = nullptr;  // when set, b200va_postprocess records it right after the decode launch
+  // ---- NMS variant selection: host-mapped statistic written by k_sort_nms ----
+  int* nms_stats_host = nullptr;
+  int* nms_stats_dev = nullptr;
+  int nms_dense_ttl = 0;  // launches left on the grid variant after the last dense sighting
   // ---- developer phase timing (only written by builds with -DB200VA_PHASE_TIMING) ----
   long long* dbg = nullptr;  // device int64[DBG_SLOTS]
 };

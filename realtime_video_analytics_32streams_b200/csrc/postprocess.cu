@@ -396,6 +396,7 @@ struct NmsParams {
   // un-letterbox with f[frame]
   int ultra, ultra_agnostic, max_det_cap;
   int grid_off;  // byte offset of the NmsGrid in dynamic shared memory; 0 = no grid (survivors-vs-tail scan instead)
+  int* stats;    // host-mapped word: set by frames with more than 256 candidates (the host picks the next variant from it)
   double iou_thr64;
   PostFrame f[B200VA_LAUNCH_FRAMES];
 };
@@ -451,6 +452,10 @@ __device__ __forceinline__ void cell_range(const float4 b, float inv_w, float in
 
 constexpr int kNmsThreads = 1024;
 
+// GRID: carries the kept-box grid code.  Two instantiations because the grid path's registers and stack slots slow
+// the common small-n launch (which never runs it) from 9.5 to 14 us when it is compiled in; the host picks per launch
+// from the candidate counts the previous launch reported (NmsParams::stats).
+template <bool GRID>
 __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant__ NmsParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int frame = blockIdx.x;
@@ -476,6 +481,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
 
   __syncthreads();
   if (tid == 0) {
+    if (p.stats && n > 256) *(volatile int*)p.stats = n;  // posted write, dense frames only (an atomic to host memory cost 25 us)
     p.cand_count[frame] = 0;
     if (n_raw > p.max_cand) atomicOr(p.flags + FLAG_CAND_OVERFLOW, 1);
   }
@@ -563,9 +569,9 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
   const bool thr_nonneg = ultra ? p.iou_thr64 >= 0.0 : thr >= 0.f;
   const int nchunks = (n + 63) >> 6;
   // few candidates: the survivors-vs-tail scan is cheaper than keeping the grid
-  const bool use_grid = grid != nullptr && !ultra && thr_nonneg && n > 256;
+  const bool use_grid = GRID && grid != nullptr && !ultra && thr_nonneg && n > 256;
   const float inv_cw = (float)kGX / (p.f[frame].xmax + 1.0f), inv_ch = (float)kGY / (p.f[frame].ymax + 1.0f);
-  if (use_grid) {
+  if (GRID && use_grid) {
     for (int c = tid; c < kCells; c += kNmsThreads) grid->cnt[c] = 0;
     for (int w = tid; w < (n + 31) / 32; w += kNmsThreads) over_mark[w] = 0u;
     if (tid == 0) grid->n_over = 0;
@@ -588,7 +594,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
     // in this loop (all 32 warps busy on one SM), so what counts is warp-instructions: ~1.3 k per query warp and
     // chunk, against ~4 k per chunk for the survivors-vs-tail scan it replaces in dense scenes.
     // (Writes supp[], which (a) does not read: no barrier before (a).)
-    if (use_grid && ch > 0 && tid < 256) {
+    if (GRID && use_grid && ch > 0 && tid < 256) {
       const int i = tid >> 2, part = tid & 3;
       const bool active = i < m;
       const int self = c0 + (active ? i : 0);
@@ -686,7 +692,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
     // tail grows so that all 1024 threads stay busy.
     const unsigned long long kept = ((unsigned long long)keep_w[2 * ch + 1] << 32) | keep_w[2 * ch];
     const int tail = n - (c0 + 64);
-    if (use_grid) {
+    if (GRID && use_grid) {
       // (c') register this chunk's survivors in the cells they touch (16 threads per survivor)
       const int b = tid >> 4, part = tid & 15;
       if (tail > 0 && ((kept >> b) & 1ull)) {
@@ -862,7 +868,8 @@ size_t nms_smem_bytes(int max_cand) {
 int postprocess_configure(b200va_ctx* h) {
   const size_t smem = nms_smem_bytes(h->cfg.max_candidates);
   if (smem > 220 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_candidates %d needs %zu bytes of shared memory", h->cfg.max_candidates, smem);
-  CUDA_TRY(h, cudaFuncSetAttribute(k_sort_nms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_sort_nms<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(h, cudaFuncSetAttribute(k_sort_nms<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return B200VA_OK;
 }
 
@@ -998,7 +1005,24 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
     q.grid_off = (int)nms_grid_offset(h->cfg.max_candidates);
     q.iou_thr64 = iou_thr;  // torchvision's CPU kernel compares the float32 IoU with the double threshold
     memcpy(q.f, p.f, sizeof(q.f));
-    k_sort_nms<<<n, kNmsThreads, nms_smem_bytes(h->cfg.max_candidates), st>>>(q);
+    // dense scenes (more than 256 candidates in some frame of the previous launch) take the grid variant; the
+    // statistic is a host-mapped word that dense frames overwrite with a posted store: no synchronisation, at worst
+    // one launch late (both variants give identical results)
+    q.stats = h->nms_stats_dev;
+    bool dense = false;
+    if (h->nms_stats_host) {
+      // the host runs several launches ahead of the GPU, so one sighting keeps the grid variant for the next 64 launches
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(st, &cap);
+      if (*(volatile int*)h->nms_stats_host > 256) {
+        h->nms_dense_ttl = 64;
+        if (cap == cudaStreamCaptureStatusNone) *(volatile int*)h->nms_stats_host = 0;
+      }
+      dense = h->nms_dense_ttl > 0;
+      if (dense && cap == cudaStreamCaptureStatusNone) --h->nms_dense_ttl;
+    }
+    if (dense && q.grid_off) k_sort_nms<true><<<n, kNmsThreads, nms_smem_bytes(h->cfg.max_candidates), st>>>(q);
+    else k_sort_nms<false><<<n, kNmsThreads, nms_smem_bytes(h->cfg.max_candidates), st>>>(q);
     LAUNCH_CHECK(h);
   }
   return B200VA_OK;
