@@ -20,7 +20,7 @@ lines = ["# " + title, "", "## `ncu --set full` (one launch per kernel, cold cac
          "| kernel | " + " | ".join(n for _, n in idx) + " |", "|---|" + "---|" * len(idx)]
 seen = set()
 for r in rows[2:]:
-    name = r[ki].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
+    name = r[ki].rsplit("(", 1)[0].replace("<unnamed>::", "").replace("void ", "")
     if len(sys.argv) > 5 and sys.argv[5] == "all":
         name = f"{name} #{sum(1 for s_ in seen if s_.startswith(name + ' #')) + 1}"
     if name in seen:
@@ -50,7 +50,7 @@ lh = lr[0]
 k2, v2 = lh.index("Kernel Name"), lh.index("Metric Value")
 d = collections.OrderedDict()
 for r in lr[1:]:
-    name = r[k2].split("(")[0].replace("<unnamed>::", "").replace("void ", "")
+    name = r[k2].rsplit("(", 1)[0].replace("<unnamed>::", "").replace("void ", "")
     if name.startswith("at::") or name.startswith("at_cuda") or "nccl" in name.lower():
         continue  # torch's input generators / fills of the harness, not the product's kernels
     d.setdefault(name, []).append(float(r[v2].replace(",", "")) / 1e3)
