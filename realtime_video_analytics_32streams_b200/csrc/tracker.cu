@@ -75,10 +75,11 @@ __device__ __forceinline__ double iou64(double ax1, double ay1, double ax2, doub
   return __ddiv_rn(inter, uni);
 }
 
-// launched; a stream with few detections and tracks keeps only kTrkThreadsMin of them.  512, not 1024: a 1024-thread
+// launched; a stream with few detections and tracks keeps only kTrkThreadsMin of them.  512 by default, not 1024: a 1024-thread
 // CTA owns the whole register file of its SM until it retires, and in b200va_tick the tracker runs underneath the
 // letterbox -- 32 SMs closed to letterbox CTAs for 14 us cost the 32 x 1080p tick 3 us (dense tracker: 84 us at 512, 63 at 1024)
-constexpr int kTrkThreadsMax = 512;
+constexpr int kTrkThreadsMax = 1024;   // widest launch (dense scenes, see tracker_launch)
+constexpr int kTrkThreadsWide = 512;   // default launch width
 constexpr int kTrkThreadsMin = 256;
 constexpr int kDetChunk = 64;  // detections staged in shared memory at a time (two warps cover a chunk)
 constexpr int kCand = 6;        // candidate slots per detection and kind; more -> exact brute-force scan
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kTrkThreadsMax) k_tracker(const __grid_constan
   // 313 detections x 365 tracks: 131 us with 256 threads, 84 us with 512, 63 us with 1024), while a small stream
   // (25 x 25) only pays for the wider barriers (19 us with 256, 22 us with 1024): the surplus warps of a small
   // stream leave at once (a barrier counts the warps that are still alive); see kTrkThreadsMax for the width launched
-  const int kTrkThreads = (T0 > 96 || D > 64) ? kTrkThreadsMax : kTrkThreadsMin;
+  const int kTrkThreads = (T0 > 96 || D > 64) ? (int)blockDim.x : kTrkThreadsMin;
   if (tid >= kTrkThreads) return;
 
   for (int t = tid; t < T0; t += kTrkThreads) {
@@ -664,7 +665,9 @@ static int tracker_launch(b200va_ctx* h, TrkParams& p, const int* stream_slots, 
   p.o_new = new_counts;
   p.flags = h->status_flags;
   p.dbg = h->dbg;
-  k_tracker<<<batch, kTrkThreadsMax, (size_t)h->cfg.max_tracks * 46 + kDetChunk * 4 + 16, st>>>(p);
+  // dense scenes (the post-process saw more than 256 candidates in a frame lately) are worth a CTA that owns its SM
+  const int width = h->nms_dense_ttl > 0 ? kTrkThreadsMax : kTrkThreadsWide;
+  k_tracker<<<batch, width, (size_t)h->cfg.max_tracks * 46 + kDetChunk * 4 + 16, st>>>(p);
   LAUNCH_CHECK(h);
   return B200VA_OK;
 }
