@@ -181,3 +181,67 @@ def test_motion_32x1080p_static_scene_counts_zero_and_state_is_idempotent(H):
     omf.should_process(g9)
     omf.should_process(frames[9].cpu().numpy())
     assert int(cnt[9]) == omf.last_count
+
+
+def test_tick_32x1080p_graph_replay_equals_separate_calls():
+    """BASELINE config 3 shape through the bench's own path: the prepared b200va_tick replayed from a CUDA graph
+    (schedule 1, with and without B200VA_OUT_FLAG_PADS_VALID) against the three separate C-ABI calls on a second
+    handle -- network input, detections and track tables, three ticks, sparse and dense heads."""
+    import torch
+    from realtime_video_analytics_32streams_b200 import _native as N
+
+    B, hw, in_hw = 32, (1080, 1920), (640, 640)
+    mk = lambda: N.Handle(device=0, max_batch=B, max_anchors=8400, max_candidates=2048, max_dets=512, max_streams=B,
+                          max_tracks=1024)
+    ha, hb = mk(), mk()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    frames = torch.randint(0, 256, (B, *hw, 3), dtype=torch.uint8, device="cuda", generator=g)
+    fb = N.FrameBatch(list(frames.unbind(0)))
+    head = torch.empty((B, 84, 8400), dtype=torch.float32, device="cuda")
+    metas = (N.Letterbox * B)(*[N.letterbox_meta(*hw, *in_hw) for _ in range(B)])
+    net_a = torch.zeros((B, 3, *in_hw), dtype=torch.float32, device="cuda")
+    slots = list(range(B))
+    for pads_flag in (0, N.OUT_FLAG_PADS_VALID):
+        for s in slots:
+            ha.tracker_reset(s)
+            hb.tracker_reset(s)
+        ha.tracker_set_next_id(1)
+        hb.tracker_set_next_id(1)
+        if pads_flag:
+            ha.preprocess(fb, in_hw, N.OUT_F32_RGB_NCHW, out=net_a)  # the pad rows the flag relies on
+        plan = ha.plan_tick(frames=fb, net_out=net_a, dst_hw=in_hw, fmt=N.OUT_F32_RGB_NCHW | pads_flag, head=head,
+                            metas=metas, conf_thr=0.35, iou_thr=0.5, filter_conf=0.35, slots=slots,
+                            tracker_cfg=(30, 1, 0.5), schedule=1)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                ha.tick(plan)
+        torch.cuda.current_stream().wait_stream(side)
+        for t, (n_obj, dup) in enumerate([(24, 3), (300, 6), (24, 3)]):
+            frames.copy_(torch.randint(0, 256, frames.shape, dtype=torch.uint8, device="cuda", generator=g))
+            scenes = [synth.DenseScene(8000 + s, n_objects=n_obj, dup=dup, n_obj_classes=10) for s in range(B)]
+            head.copy_(torch.from_numpy(np.stack([sc.head(t) for sc in scenes])))
+            graph.replay()
+            net_b, _ = hb.preprocess(fb, in_hw, N.OUT_F32_RGB_NCHW)
+            dets_b = hb.postprocess(head, metas, 0.35, 0.5, filter_conf=0.35)
+            trk_b = hb.tracker_update(slots, dets_b, 30, 1, 0.5)
+            torch.cuda.synchronize()
+            assert torch.equal(net_a, net_b), (pads_flag, t)
+            assert torch.equal(plan.dets["count"], dets_b["count"]), (pads_flag, t)
+            live = torch.arange(plan.dets["conf"].shape[1], device="cuda")[None, :] < dets_b["count"][:, None]
+            for k in ("cls", "conf", "bbox_xyxy"):  # rows past the count are stale scratch
+                m = live if plan.dets[k].dim() == 2 else live[:, :, None].expand_as(plan.dets[k])
+                assert torch.equal(plan.dets[k][m], dets_b[k][m]), (pads_flag, t, k)
+            cnt = trk_b["count"]
+            assert torch.equal(plan.tracks["count"], cnt)
+            for k in ("track_id", "cls", "conf", "bbox_xyxy", "age", "hits"):
+                for s in (0, 13, 31):
+                    n = int(cnt[s])
+                    assert torch.equal(plan.tracks[k][s, :n], trk_b[k][s, :n]), (pads_flag, t, k, s)
+    ha.poll_status()
+    hb.poll_status()
+    ha.close()
+    hb.close()
