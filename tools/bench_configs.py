@@ -148,8 +148,22 @@ def letterbox_only(name, B, hw, fmt=0, mask=False):
     return r
 
 
+def dfl_only(B=32, nc=80):
+    """a14: raw Detect head [B, 64 + nc, 8400] -> decoded [B, 4 + nc, 8400]."""
+    h = _native.Handle(device=0, max_batch=B, max_anchors=8400, max_candidates=1024, max_dets=256, max_streams=B, max_tracks=256)
+    g = torch.Generator(device=dev); g.manual_seed(9)
+    raws = [torch.randn((B, 64 + nc, 8400), dtype=torch.float32, device=dev, generator=g) * 3 for _ in range(3)]
+    out_t = torch.empty((B, 4 + nc, 8400), dtype=torch.float32, device=dev)
+    r = timed([("dfl_decode", lambda k: h.dfl_decode(raws[k % 3], nc, out=out_t))], args.steps)
+    alg = B * 8400 * 4 * ((64 + nc) + (4 + nc))
+    r.update(config="a14: DFL decode of 32 raw heads [144, 8400]", streams=B, algorithmic_bytes=alg,
+             GBps=alg / (r["dfl_decode"] * 1e-3) / 1e9, frac_of_peak=alg / (r["dfl_decode"] * 1e-3) / 1e9 / PEAK)
+    h.close()
+    return r
+
+
 out = []
-todo = args.only.split(",") if args.only else ["1", "2", "5", "4"]
+todo = args.only.split(",") if args.only else ["1", "2", "5", "4", "D"]
 if "L" in todo:
     shapes = [("letterbox 32x1080p fp32", 32, (1080, 1920), 0, False), ("letterbox 32x1080p fp16", 32, (1080, 1920), 1, False),
               ("letterbox 32x4K fp32", 32, (2160, 3840), 0, False), ("letterbox 32x4K fp32 + ROI mask", 32, (2160, 3840), 0, True),
@@ -162,6 +176,7 @@ if "1" in todo: out.append(simple("1: 1 stream 1080p (pipeline-sim shape)", 1, (
 if "2" in todo: out.append(simple("2: 4 streams 1080p (pipeline-rtsp shape)", 4, (1080, 1920), 10, 1))
 if "5" in todo: out.append(simple("5: dense stress, 32 streams, ~1800 candidates -> ~300 kept", 32, (1080, 1920), 300, 6))
 if "4" in todo: out.append(config4())
+if "D" in todo: out.append(dfl_only())
 for r in out:
     print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()}))
 if args.out:
