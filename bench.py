@@ -233,6 +233,11 @@ def run_gpu(args) -> None:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = None
+    if world > 1 and not args.no_bind:
+        from realtime_video_analytics_32streams_b200.runtime import bind_process_to_gpu
+
+        numa_cores = bind_process_to_gpu(local)  # before any pinned allocation: first touch on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -526,7 +531,8 @@ def run_gpu(args) -> None:
                 "value_eager_tick": round(eager_value, 1), "value_three_serial_calls": round(serial_value, 1),
                 "value_pad_rows_written_once": round(pads_value, 1) if pads_value is not None else None,
                 "value_32_streams_total_strong_scaling": round(strong_value, 1) if strong_value is not None else None,
-                "clocks": clocks.summary(), "tracks_alive": n_tracks}
+                "clocks": clocks.summary(), "tracks_alive": n_tracks,
+                "cpu_affinity": (f"rank 0 pinned to {len(numa_cores)} NUMA-local cores" if numa_cores else "unchanged")}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_single_core_sample()
         else:
@@ -546,6 +552,7 @@ def main() -> None:
     ap.add_argument("--schedule", type=int, default=1, choices=[0, 1, 2],
                     help="b200va_tick schedule: 0 serial, 1 letterbox after decode (default), 2 fully parallel")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-bind", action="store_true", help="N > 1: do not pin each rank to its GPU's NUMA-local cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the single-core CPU sample")
     args = ap.parse_args()
     if args.impl == "reference":

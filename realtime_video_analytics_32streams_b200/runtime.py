@@ -42,6 +42,31 @@ def get_handle(device: Optional[int] = None, **overrides) -> "_native.Handle":
     return h
 
 
+def bind_process_to_gpu(device: int) -> Optional[List[int]]:
+    """Pin this process to the CPU cores that are local to ``device`` (NVML's affinity mask), so that the pinned
+    staging buffers it allocates afterwards are first-touched on the GPU's own NUMA node: with one process per GPU
+    and eight GPUs, host -> device copies that cross the socket interconnect are what limits the upload rate.
+    Returns the core list, or None when NVML or the affinity call is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[device]) if vis else device
+        handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_cpus = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (n_cpus + 63) // 64)
+        allowed = os.sched_getaffinity(0)
+        cores = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        cores = [c for c in cores if c in allowed]
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:  # pragma: no cover - best effort
+        return None
+
+
 def reset_handles() -> None:
     for h in _handles.values():
         h.close()
