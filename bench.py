@@ -1,22 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of the pre + post + track hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--schedule 0|1|2] [--no-graph] [--no-cpu]
 
 Workload at every N: each GPU serves 32 streams of 1080p BGR frames with a synthetic decoded
 YOLOv8 head [32, 84, 8400] (config 3 of BASELINE.json, the one the metric is quoted on); with
 N > 1 every rank (one process per GPU, torchrun) serves its own 32 streams -- weak scaling, no
 data-path collective.  One "step" is one tick: letterbox preprocess of the 32 frames, head decode +
-NMS of the 32 heads, tracker update of the 32 streams.  The detector forward is outside the
-measured path (north_star) -- the head tensors stand in for its output.
+NMS of the 32 heads, tracker update of the 32 streams -- one prepared `b200va_tick` call (letterbox on
+the caller's stream, decode -> NMS -> tracker on the library's second stream, fork and join inside the
+call).  The detector forward is outside the measured path (north_star): the head tensors stand in
+for its output.
 
-`value`   : frames/s with frames and heads already resident in HBM (CUDA events, max over ranks).
-`e2e`     : the same tick through the public API (HotPathEngine.tick) with HOST buffers: pinned
-            frames and heads are copied to the device and the track tables are read back and
-            turned into Track objects inside the timed region.
-`roofline`: the letterbox kernel's algorithmic bytes / its event-timed duration vs measured HBM peak.
+`value`   : frames/s with frames and heads already resident in HBM (CUDA events around the K steps,
+            max over ranks).  The tick is replayed from a CUDA graph per input set; every 10th step is
+            launched eagerly with an event pair around the letterbox launch (the live kernel timing of
+            `roofline`).  Four rotating input sets keep every step's reads out of the 126 MB L2.
+`roofline`: the letterbox kernel's algorithmic bytes / that event-timed duration vs the measured HBM peak.
+`e2e`     : the same tick through the public API (HotPathEngine.submit / collect, two ticks in flight)
+            with HOST buffers: pinned frames and heads are copied to the device and the result tables
+            are read back inside the timed region.
 `cpu_baseline` / `--impl reference`: the reference's own OpenCV/NumPy call sequence (oracle, cv2
-            back end) on the host cores of the same box.
+            back end) on the host cores of the same box (one thread / one process per core).
+Informational keys: value_eager_tick, value_three_serial_calls (the unfused call sequence),
+value_pad_rows_written_once (B200VA_OUT_FLAG_PADS_VALID), value_32_streams_total_strong_scaling (N > 1).
 """
 
 from __future__ import annotations
