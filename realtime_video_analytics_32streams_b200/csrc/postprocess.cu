@@ -592,14 +592,18 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
     const int m = min(64, n - c0);
     if (tid < 128) rows[tid >> 1][tid & 1] = 0u;
     __syncthreads();
-    // (q) grid mode: is box i of this chunk suppressed by a box kept in an EARLIER chunk?  Four threads per box
-    // (the first eight warps) take the cells it touches.  Pass 1 only collects the kept boxes that overlap box i
+    // (q) grid mode: is box i of this chunk suppressed by a box kept in an EARLIER chunk?  Eight threads per box
+    // (the first sixteen warps) take the cells it touches.  Pass 1 only collects the kept boxes that overlap box i
     // (four compares each); pass 2 runs the IoU formula on them with the warp converged.  The CTA is issue-bound
     // in this loop (all 32 warps busy on one SM), so what counts is warp-instructions: ~1.3 k per query warp and
     // chunk, against ~4 k per chunk for the survivors-vs-tail scan it replaces in dense scenes.
     // (Writes supp[], which (a) does not read: no barrier before (a).)
-    if (GRID && use_grid && ch > 0 && tid < 256) {
-      const int i = tid >> 2, part = tid & 3;
+    if (GRID && use_grid && ch > 0 && tid < 512) {
+      // eight lanes per box: lane = (cell slot 0..3, entry half 0..1); a lane tests at most four entries per cell visit
+      const int i = tid >> 3, part = tid & 3, half = (tid >> 2) & 1;
+#ifdef B200VA_PHASE_TIMING
+      long long q0 = clock64();
+#endif
       const bool active = i < m;
       const int self = c0 + (active ? i : 0);
       const float4 bi = box[self];
@@ -609,20 +613,26 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
       const int cw = cx1 - cx0 + 1, ncell = active ? cw * (cy1 - cy0 + 1) : 0;
       const float rcw = 1.0f / (float)cw;
       constexpr int kQ = 4;  // overlapping kept boxes a lane can defer; more are evaluated on the spot
-      int cand[kQ], nc = 0;
+      unsigned long long cand = 0ull;  // up to four 16-bit indices, packed (an indexed array would live in local memory)
+      int nc = 0;
       bool hit = false;
       auto consider = [&](int k) {
         const float4 bk = box[k];
         if (bk.z <= bi.x || bi.z <= bk.x || bk.w <= bi.y || bi.w <= bk.y) return;  // disjoint: IoU 0 <= thr
         if (aware && scl[k] != ci) return;
-        if (nc < kQ) cand[nc++] = k;
+        if (nc < kQ) cand |= (unsigned long long)k << (16 * nc++);
         else if (suppresses(bk, bi, thr)) hit = true;
       };
+#ifdef B200VA_PHASE_TIMING
+      long long q1 = clock64();
+#endif
+#pragma unroll 1
       for (int c = part; c < ncell; c += 4) {
         const int row = (int)(((float)c + 0.5f) * rcw);  // c / cw for these small integers
         const int cell = (cy0 + row) * kGX + cx0 + (c - row * cw);
         const int cnt = min(grid->cnt[cell], kCellCap);
-        for (int e = 0; e < cnt; e += 4) {  // one 8-byte load brings four indices
+#pragma unroll 1  // unrolled, this loop alone was 1700 instructions of mostly predicated-off code
+        for (int e = 4 * half; e < cnt; e += 8) {  // one 8-byte load brings four indices
           const uint2 kk = *reinterpret_cast<const uint2*>(&grid->list[cell][e]);
           const int k4[4] = {(int)(kk.x & 0xffffu), (int)(kk.x >> 16), (int)(kk.y & 0xffffu), (int)(kk.y >> 16)};
 #pragma unroll
@@ -630,16 +640,32 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
             if (e + u < cnt) consider(k4[u]);
         }
       }
+#ifdef B200VA_PHASE_TIMING
+      long long q2 = clock64();
+#endif
       if (active) {
         const int nover = grid->n_over;
-        for (int e = part; e < nover; e += 4) consider(over[e]);
+#pragma unroll 1
+        for (int e = (tid & 7); e < nover; e += 8) consider(over[e]);
       }
+#ifdef B200VA_PHASE_TIMING
+      long long q3 = clock64();
+#endif
 #pragma unroll
       for (int u = 0; u < kQ; ++u) {
         if (!__any_sync(0xffffffffu, u < nc && !hit)) break;
-        if (u < nc && !hit && suppresses(box[cand[u]], bi, thr)) hit = true;
+        if (u < nc && !hit && suppresses(box[(int)((cand >> (16 * u)) & 0xffffull)], bi, thr)) hit = true;
       }
       if (hit) atomicOr(&supp[self >> 5], 1u << (self & 31));
+#ifdef B200VA_PHASE_TIMING
+      if (blockIdx.x == 0 && tid == 0) {
+        const long long q4 = clock64();
+        p.dbg[32] += q1 - q0;
+        p.dbg[33] += q2 - q1;
+        p.dbg[34] += q3 - q2;
+        p.dbg[35] += q4 - q3;
+      }
+#endif
     }
     NMS_MARK(acc_q);
     // (a) in-chunk IoU bits: thread -> row i = tid / 16, columns 4 * (tid % 16) ..; the predicate is

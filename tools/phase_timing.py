@@ -27,6 +27,7 @@ print("tracker phases (SM cycles, block 0): start->staged-issue %d, ->dets stage
 print("tracker: phase A %d, phase B %d; first iterations of B: %s" % (v[7] - v[2], v[3] - v[7], [v[9 + i] - v[8 + i] for i in range(7)]))
 print("nms phases: count+keys %d, sort %d, gather %d, chunks %d, filter+emit %d" % tuple(v[16 + i + 1] - v[16 + i] for i in range(5)))
 print("nms chunk loop split: (q) grid query (warp 0) %d, (a) pair matrix %d, (b) resolve %d, (c) tail / insert %d" % (v[27], v[24], v[25], v[26]))
+print("grid query split (accumulated over launches, thread 0): setup %d, cells %d, overflow %d, pass2 %d" % (v[32], v[33], v[34], v[35]))
 print("grid: max entries per cell %d, overflow list %d, total entries %d" % (v[28], v[29], v[30]))
 print("dets per frame", dets["count"].cpu().tolist()[:8], "tracks", tracks["count"].cpu().tolist()[:8])
 
