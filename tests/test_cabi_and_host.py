@@ -190,6 +190,9 @@ def test_registration_shim_wires_the_reference_factory():
     cfg = rcfg.DetectorConfig(backend="b200", confidence_threshold=0.35, iou_threshold=0.5)
     cfg.validate()  # whitelisted now
     assert cfg.backend == "b200"
+    ucfg = rcfg.DetectorConfig(backend="b200_ultralytics")
+    ucfg.validate()  # the Ultralytics-semantics drop-in is whitelisted too
+    assert ucfg.backend == "b200_ultralytics"
     with pytest.raises(rcfg.ConfigError):
         rcfg.DetectorConfig(backend="nope").validate()
     if not torch.cuda.is_available():
