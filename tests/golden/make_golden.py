@@ -33,7 +33,7 @@ sys.path.insert(0, "/root/reference/src")
 
 import cv2  # noqa: E402
 from realtime_analytics.config import DetectorConfig, StreamConfig, TrackerConfig  # noqa: E402
-from realtime_analytics.detector import Detection, _TensorRTBaseDetector, filter_detections  # noqa: E402
+from realtime_analytics.detector import Detection, RKNNDetector, _TensorRTBaseDetector, filter_detections  # noqa: E402
 from realtime_analytics.pipeline import StreamHealth, StreamWorker, StreamWorkerContext  # noqa: E402
 from realtime_analytics.tracker import IouTracker  # noqa: E402
 from realtime_analytics.utils import MotionFilter, MotionFilterConfig, apply_roi, downsample  # noqa: E402
@@ -107,6 +107,43 @@ def gen_preprocess(out):
                 "seed": seed, "h": h, "w": w, "half": half, "sha256": sha(tensor),
                 "scale": meta["scale"], "pad": list(meta["pad"]),
             }
+    return digests
+
+
+def gen_preprocess_rknn(out):
+    """a2: ``RKNNDetector._preprocess`` (detector.py:777-839) -- letterbox that stays BGR uint8, NHWC or NCHW.
+    ``RKNNDetector.__init__`` imports the ``rknn`` runtime (absent here), so the instance is built with
+    ``object.__new__`` and given exactly the three attributes ``_preprocess`` reads."""
+
+    def make(input_hw, nhwc):
+        det = object.__new__(RKNNDetector)
+        det.config = DetectorConfig(backend="rknn")
+        det.input_hw = input_hw
+        det.use_nhwc = nhwc
+        return det
+
+    cases = [  # (seed, h, w, in_h, in_w, nhwc)
+        (111, 54, 96, 32, 32, True), (112, 100, 37, 64, 64, False), (113, 37, 100, 64, 64, True),
+        (114, 90, 160, 64, 96, False), (115, 48, 48, 64, 64, True), (116, 135, 240, 64, 64, False),
+        (117, 33, 77, 96, 64, True), (118, 216, 384, 64, 64, True),
+    ]
+    for i, (seed, h, w, ih, iw, nhwc) in enumerate(cases):
+        frame = synth.synth_frame(seed, h, w)
+        tensor, meta = make((ih, iw), nhwc)._preprocess(frame)
+        out[f"rk{i}_tensor"] = tensor
+        out[f"rk{i}_meta"] = np.array([meta["orig_shape"][0], meta["orig_shape"][1], meta["pad"][0], meta["pad"][1]], dtype=np.int64)
+        out[f"rk{i}_scale"] = np.array([meta["scale"]], dtype=np.float64)
+        out[f"rk{i}_cfg"] = np.array([seed, h, w, ih, iw, int(nhwc)], dtype=np.int64)
+    out["rk_n"] = np.array([len(cases)])
+    digests = {}
+    for name, seed, h, w in [("1080p", 1000, 1080, 1920), ("4k", 4000, 2160, 3840), ("720p", 720, 720, 1280),
+                             ("odd", 77, 1083, 1921), ("portrait", 91, 1920, 1080)]:
+        frame = synth.synth_frame(seed, h, w)
+        for nhwc in (True, False):
+            tensor, meta = make((640, 640), nhwc)._preprocess(frame)
+            digests[f"{name}_{'nhwc' if nhwc else 'nchw'}"] = {
+                "seed": seed, "h": h, "w": w, "nhwc": nhwc, "sha256": sha(tensor), "scale": meta["scale"],
+                "pad": list(meta["pad"])}
     return digests
 
 
@@ -300,11 +337,24 @@ def gen_pipeline(out):
             out[f"pipe_{k}_t{kk}"] = arr
 
 
+GENERATORS = (("preprocess", gen_preprocess), ("preprocess_rknn", gen_preprocess_rknn), ("postprocess", gen_postprocess),
+              ("tracker", gen_tracker), ("filters", gen_filters), ("pipeline", gen_pipeline))
+
+
 def main():
+    """``--only NAME [NAME ...]`` regenerates just those files and merges their digests into golden_meta.json."""
+    only = sys.argv[sys.argv.index("--only") + 1:] if "--only" in sys.argv else None
     meta = {"cv2": cv2.__version__, "numpy": np.__version__, "python": sys.version.split()[0],
             "reference": "/root/reference (skygazer42/realtime-video-analytics-32streams)"}
-    for name, fn in (("preprocess", gen_preprocess), ("postprocess", gen_postprocess), ("tracker", gen_tracker),
-                     ("filters", gen_filters), ("pipeline", gen_pipeline)):
+    meta_path = os.path.join(HERE, "golden_meta.json")
+    if only and os.path.exists(meta_path):
+        with open(meta_path) as fh:
+            old = json.load(fh)
+        assert (old["cv2"], old["numpy"]) == (meta["cv2"], meta["numpy"]), "library versions changed: regenerate everything"
+        meta = old
+    for name, fn in GENERATORS:
+        if only and name not in only:
+            continue
         out = {}
         digests = fn(out)
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)

@@ -61,6 +61,26 @@ def test_preprocess_full_size_digests(H, key):
     assert metas[0].scale == d["scale"] and [metas[0].pad_left, metas[0].pad_top] == d["pad"]
 
 
+def test_preprocess_rknn_u8_golden(H):
+    """a2: the uint8 BGR formats against vectors recorded from ``RKNNDetector._preprocess`` (detector.py:777-839)."""
+    from realtime_video_analytics_32streams_b200 import _native as N
+
+    z = G.load("preprocess_rknn")
+    for i in range(int(z["rk_n"][0])):
+        seed, h, w, ih, iw, nhwc = z[f"rk{i}_cfg"].tolist()
+        out, metas = H.preprocess([cu(synth.synth_frame(seed, h, w))], (ih, iw), N.OUT_U8_BGR_NHWC if nhwc else N.OUT_U8_BGR_NCHW)
+        got, ref = out.cpu().numpy(), z[f"rk{i}_tensor"]
+        assert got.dtype == ref.dtype and got.shape == ref.shape and np.array_equal(got, ref), f"case {i}"
+        oh, ow, left, top = z[f"rk{i}_meta"].tolist()
+        m = metas[0].as_meta()
+        assert m["orig_shape"] == (oh, ow) and m["pad"] == (left, top) and m["scale"] == float(z[f"rk{i}_scale"][0])
+    for key, d in G.meta()["preprocess_rknn_digests"].items():
+        frame = synth.synth_frame(d["seed"], d["h"], d["w"])
+        out, metas = H.preprocess([cu(frame)], (640, 640), N.OUT_U8_BGR_NHWC if d["nhwc"] else N.OUT_U8_BGR_NCHW)
+        assert G.sha(out.cpu().numpy()) == d["sha256"], key
+        assert metas[0].scale == d["scale"] and [metas[0].pad_left, metas[0].pad_top] == d["pad"]
+
+
 def test_preprocess_mixed_batch_and_formats(H):
     from realtime_video_analytics_32streams_b200 import _native as N
 

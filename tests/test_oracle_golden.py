@@ -34,6 +34,28 @@ def test_preprocess_full_size_digests(key):
     assert meta["scale"] == d["scale"] and list(meta["pad"]) == d["pad"]
 
 
+def test_preprocess_rknn_u8_variant_bit_exact():
+    """a2: the oracle's ``preprocess_u8`` against ``RKNNDetector._preprocess`` itself (detector.py:777-839)."""
+    z = G.load("preprocess_rknn")
+    for i in range(int(z["rk_n"][0])):
+        seed, h, w, ih, iw, nhwc = z[f"rk{i}_cfg"].tolist()
+        tensor, meta = O.preprocess_u8(synth.synth_frame(seed, h, w), (ih, iw), bool(nhwc))
+        ref = z[f"rk{i}_tensor"]
+        assert tensor.dtype == ref.dtype == np.uint8 and tensor.shape == ref.shape
+        assert np.array_equal(tensor, ref), f"case {i}"
+        oh, ow, left, top = z[f"rk{i}_meta"].tolist()
+        assert meta["orig_shape"] == (oh, ow) and meta["pad"] == (left, top)
+        assert meta["scale"] == float(z[f"rk{i}_scale"][0])
+
+
+@pytest.mark.parametrize("key", ["1080p_nhwc", "1080p_nchw", "4k_nhwc", "odd_nchw", "portrait_nhwc"])
+def test_preprocess_rknn_full_size_digests(key):
+    d = G.meta()["preprocess_rknn_digests"][key]
+    tensor, meta = O.preprocess_u8(synth.synth_frame(d["seed"], d["h"], d["w"]), (640, 640), d["nhwc"])
+    assert G.sha(tensor) == d["sha256"]
+    assert meta["scale"] == d["scale"] and list(meta["pad"]) == d["pad"]
+
+
 def test_postprocess_cases_bit_exact():
     z = G.load("postprocess")
     for name in z["post_names"].tolist():
