@@ -150,6 +150,38 @@ B200VA_API int64_t b200va_launch_count(b200va_handle h);
  * B200VA_OK.  The reference has no such limits; size the config so that this never fires. */
 B200VA_API int b200va_poll_status(b200va_handle h, void* stream);
 
+/* Asynchronous form for callers that already copy results back every tick: enqueues a copy of the status words
+ * (B200VA_STATUS_WORDS int32: [0] candidates > max_candidates, [1] detections > max_dets, [2] tracks > max_tracks,
+ * rest reserved) into host_out (HOST, pinned memory for a truly asynchronous copy) and, when clear != 0, resets them
+ * on the device afterwards, all on `stream`; nothing synchronises.  The words are valid once the caller has
+ * synchronised `stream` (e.g. with the event that guards its result tables). */
+#define B200VA_STATUS_WORDS 8
+B200VA_API int b200va_read_status_async(b200va_handle h, int32_t* host_out, int clear, void* stream);
+
+/* ---- per-phase device times and NVTX ranges ------------------------------------------------
+ * The reference times each packet on the host (`start = time.perf_counter()` ... `health.update_success(dt)`,
+ * pipeline.py:145, 200-201).  With the work on the GPU the caller needs device times instead: after
+ * b200va_set_profiling(h, 1) every entry point brackets its kernels with CUDA events (one pair per phase, on the
+ * stream the kernels run on; skipped while the stream is being captured into a CUDA graph), and
+ * b200va_get_phase_times waits for the pairs recorded since the last query and returns their durations in
+ * milliseconds (ms[phase] = -1 when the phase did not run).  Independently of that switch every entry point
+ * opens an NVTX range named "b200va:<phase>" around its launches (free when no tool is attached). */
+enum b200va_phase {
+  B200VA_PHASE_UPLOAD = 0,     /* b200va_upload_frames                                   */
+  B200VA_PHASE_ROI = 1,        /* b200va_roi_rasterize / b200va_apply_mask               */
+  B200VA_PHASE_RESIZE = 2,     /* b200va_resize_linear_u8                                */
+  B200VA_PHASE_MOTION = 3,     /* b200va_motion / b200va_motion_preprocess               */
+  B200VA_PHASE_PREPROCESS = 4, /* b200va_preprocess / b200va_preprocess_geom             */
+  B200VA_PHASE_DECODE = 5,     /* head decode + confidence filter (b200va_postprocess*)  */
+  B200VA_PHASE_NMS = 6,        /* sort + NMS + emit (b200va_postprocess*)                */
+  B200VA_PHASE_TRACKER = 7,    /* b200va_tracker_update*                                 */
+  B200VA_PHASE_DFL = 8,        /* b200va_dfl_decode                                      */
+  B200VA_PHASE_TICK = 9,       /* the whole b200va_tick call, fork to join               */
+  B200VA_PHASE_COUNT = 10
+};
+B200VA_API int b200va_set_profiling(b200va_handle h, int enable);
+B200VA_API int b200va_get_phase_times(b200va_handle h, float* ms /* HOST [B200VA_PHASE_COUNT] */);
+
 /* ---- a1: letterbox preprocess --------------------------------------------------------
  * Replaces _TensorRTBaseDetector._preprocess (detector.py:198-264) and
  * RKNNDetector._preprocess (detector.py:777-839) for a batch of frames.
@@ -329,7 +361,13 @@ B200VA_API int b200va_postprocess_ultralytics(b200va_handle h, const float* head
  * b200va_tracker_update; results are identical to calling those three in sequence.
  * schedule: 0 = serial on `stream`; 1 = the letterbox starts when the decode kernel has finished and
  *           overlaps NMS + tracker (the two HBM-bound kernels never share the bus); 2 = the letterbox
- *           overlaps the whole post-process branch.
+ *           overlaps the whole post-process branch; 3 = the decode kernel runs on `stream` and the letterbox
+ *           follows it there as a programmatic dependent launch that never waits for it -- its CTAs fill the SMs
+ *           beside the decode's as soon as all of those are running (HBM sees the decode's reads and the letterbox's
+ *           writes together, no kernel-to-kernel gap) -- while NMS + tracker run on the internal stream behind
+ *           an event recorded after the decode.
+ * Sparse scenes run NMS and the tracker update of the same rows as ONE kernel (a 256-thread CTA per stream);
+ * otherwise the two kernels are chained by programmatic dependent launch.
  * ev_pre_begin / ev_pre_end: optional cudaEvent_t recorded on `stream` around the letterbox launch. */
 typedef struct b200va_tick_args {
   /* b200va_preprocess */

@@ -79,7 +79,7 @@ class TickArgs(C.Structure):
     ]
 
 
-SCHEDULE_SERIAL, SCHEDULE_PRE_AFTER_DECODE, SCHEDULE_PRE_PARALLEL = 0, 1, 2
+SCHEDULE_SERIAL, SCHEDULE_PRE_AFTER_DECODE, SCHEDULE_PRE_PARALLEL, SCHEDULE_PRE_BESIDE_DECODE = 0, 1, 2, 3
 
 
 class TickPlan:
@@ -103,8 +103,10 @@ EXPORTS = (
     "b200va_postprocess", "b200va_tracker_update", "b200va_tracker_update_f64", "b200va_tracker_reset",
     "b200va_tracker_set_next_id", "b200va_upload_frames", "b200va_dfl_decode", "b200va_tick",
     "b200va_letterbox_meta_ultralytics", "b200va_preprocess_geom", "b200va_postprocess_ultralytics",
-    "b200va_motion_preprocess",
+    "b200va_motion_preprocess", "b200va_set_profiling", "b200va_get_phase_times",
+    "b200va_read_status_async",
 )
+PHASES = ("upload", "roi", "resize", "motion", "preprocess", "decode", "nms", "tracker", "dfl", "tick")  # enum b200va_phase
 
 _lib = None
 
@@ -159,6 +161,9 @@ def load_library() -> C.CDLL:
     lib.b200va_postprocess_ultralytics.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, C.c_int,
                                                    C.c_double, C.c_double, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int,
                                                    C.c_double, C.c_int, C.POINTER(Dets), vp]
+    lib.b200va_read_status_async.argtypes = [vp, vp, C.c_int, vp]
+    lib.b200va_set_profiling.argtypes = [vp, C.c_int]
+    lib.b200va_get_phase_times.argtypes = [vp, C.POINTER(C.c_float)]
     lib.b200va_tracker_reset.argtypes = [vp, C.c_int, vp]
     lib.b200va_tracker_set_next_id.argtypes = [vp, C.c_int64, vp]
     for name in EXPORTS:
@@ -272,6 +277,52 @@ class Handle:
         """Synchronise and raise if any capacity limit was hit since the last poll."""
         self._check(self.lib.b200va_poll_status(self._h, self._stream()))
 
+    STATUS_WORDS = 8
+    _STATUS_NAMES = ("candidates > max_candidates", "detections > max_dets", "tracks > max_tracks")
+
+    def read_status_async(self, host_out, clear: bool = True) -> None:
+        """Enqueue a copy of the capacity flags into ``host_out`` (pinned CPU int32 tensor of ``STATUS_WORDS``
+        elements) on the current stream; valid once that stream has been synchronised.  See ``status_message``."""
+        self._check(self.lib.b200va_read_status_async(self._h, C.c_void_p(host_out.data_ptr()), 1 if clear else 0,
+                                                      self._stream()))
+
+    @classmethod
+    def status_message(cls, words) -> Optional[str]:
+        """None when no capacity was exceeded, else what was truncated."""
+        hit = [n for n, w in zip(cls._STATUS_NAMES, list(words)[:3]) if int(w)]
+        return ("capacity exceeded (rows were dropped; the reference is unbounded -- raise the handle's limits): "
+                + ", ".join(hit)) if hit else None
+
+    # -- tracker stream slots ----------------------------------------------------------------
+    # The track tables and the id counter live in the handle, so the handle owns the slot numbers: two trackers (or
+    # engines) on one handle get disjoint slots, a slot is emptied when it is claimed, and the id counter restarts
+    # at 1 (itertools.count(1), tracker.py:47) whenever the first tracker of an otherwise idle handle claims a slot.
+    def claim_slot(self) -> int:
+        free = self.__dict__.setdefault("_free_slots", list(range(self.cfg.max_streams - 1, -1, -1)))
+        if not free:
+            raise B200VAError(ERR_CAPACITY, f"all {self.cfg.max_streams} tracker stream slots are in use")
+        if len(free) == self.cfg.max_streams:
+            self.tracker_set_next_id(1)
+        slot = free.pop()
+        self.tracker_reset(slot)
+        return slot
+
+    def release_slot(self, slot: int) -> None:
+        free = self.__dict__.setdefault("_free_slots", list(range(self.cfg.max_streams - 1, -1, -1)))
+        if slot not in free:
+            free.append(int(slot))
+
+    def set_profiling(self, enable: bool = True) -> None:
+        """Bracket every phase's kernels with CUDA events (``b200va_set_profiling``); read with ``phase_times``."""
+        self._check(self.lib.b200va_set_profiling(self._h, 1 if enable else 0))
+
+    def phase_times(self) -> dict:
+        """Device milliseconds of the phases that ran since the last query, e.g. ``{"preprocess": 0.041, ...}``
+        (waits for them to finish).  The per-packet ``dt`` of pipeline.py:145, 200-201, measured on the GPU."""
+        ms = (C.c_float * len(PHASES))()
+        self._check(self.lib.b200va_get_phase_times(self._h, ms))
+        return {name: float(ms[i]) for i, name in enumerate(PHASES) if ms[i] >= 0.0}
+
     @staticmethod
     def _batch(frames, roi_masks=None) -> FrameBatch:
         return frames if isinstance(frames, FrameBatch) else FrameBatch(frames, roi_masks)
@@ -314,10 +365,15 @@ class Handle:
         return out, [fb.metas[i] for i in range(b)]
 
     # -- a10 --------------------------------------------------------------------------------
-    def resize(self, frames, dst_hw_list, roi_masks=None):
-        """``cv2.resize(frame, (w, h), INTER_LINEAR)`` per frame; returns new uint8 HWC tensors."""
+    def resize(self, frames, dst_hw_list, roi_masks=None, outs=None):
+        """``cv2.resize(frame, (w, h), INTER_LINEAR)`` per frame; returns uint8 HWC tensors (``outs`` when given:
+        contiguous CUDA uint8 [h, w, 3] tensors the caller keeps, else freshly allocated ones)."""
         t = self.torch
-        outs = [t.empty((int(h), int(w), 3), dtype=t.uint8, device=self.device) for h, w in dst_hw_list]
+        if outs is None:
+            outs = [t.empty((int(h), int(w), 3), dtype=t.uint8, device=self.device) for h, w in dst_hw_list]
+        elif any(tuple(o.shape) != (int(h), int(w), 3) or o.dtype != t.uint8 or not o.is_contiguous() or not o.is_cuda
+                 for o, (h, w) in zip(outs, dst_hw_list)) or len(outs) != len(dst_hw_list):
+            raise ValueError("resize: `outs` must be contiguous CUDA uint8 tensors [h, w, 3] matching dst_hw_list")
         fb = self._batch(frames, roi_masks)
         if fb.n:
             self._check(self.lib.b200va_resize_linear_u8(

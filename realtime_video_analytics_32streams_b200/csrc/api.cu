@@ -1,5 +1,9 @@
 // Library entry points that are not tied to one kernel family: handle life cycle, error text,
 // launch accounting and the capacity flags the kernels raise.
+#include <nvtx3/nvToolsExt.h>
+
+#include <cstdlib>
+
 #include "common.cuh"
 
 int postprocess_configure(b200va_ctx* h);  // postprocess.cu
@@ -19,8 +23,69 @@ extern "C" const char* b200va_error_string(int status) {
   }
 }
 
+const char* phase_name(int phase) {
+  static const char* names[B200VA_PHASE_COUNT] = {"b200va:upload", "b200va:roi", "b200va:resize", "b200va:motion",
+                                                  "b200va:preprocess", "b200va:decode", "b200va:nms", "b200va:tracker",
+                                                  "b200va:dfl", "b200va:tick"};
+  return phase >= 0 && phase < B200VA_PHASE_COUNT ? names[phase] : "b200va:?";
+}
+
+PhaseScope::PhaseScope(b200va_ctx* h_, int phase_, cudaStream_t st_) : h(h_), phase(phase_), st(st_) {
+  nvtxRangePushA(phase_name(phase));
+  if (!h->profiling) return;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return;
+  }
+  timed = cudaEventRecord(h->prof_ev[phase][0], st) == cudaSuccess;
+}
+
+PhaseScope::~PhaseScope() {
+  if (timed && cudaEventRecord(h->prof_ev[phase][1], st) == cudaSuccess) h->prof_rec[phase] = true;
+  nvtxRangePop();
+}
+
+extern "C" int b200va_set_profiling(b200va_handle h, int enable) {
+  if (!h) return B200VA_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  if (enable && !h->prof_ev[0][0])
+    for (int p = 0; p < B200VA_PHASE_COUNT; ++p)
+      for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaEventCreate(&h->prof_ev[p][k]));
+  h->profiling = enable != 0;
+  for (int p = 0; p < B200VA_PHASE_COUNT; ++p) h->prof_rec[p] = false;
+  return B200VA_OK;
+}
+
+extern "C" int b200va_get_phase_times(b200va_handle h, float* ms) {
+  if (!h || !ms) return B200VA_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  for (int p = 0; p < B200VA_PHASE_COUNT; ++p) {
+    ms[p] = -1.f;
+    if (!h->prof_rec[p]) continue;
+    h->prof_rec[p] = false;
+    CUDA_TRY(h, cudaEventSynchronize(h->prof_ev[p][1]));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms[p], h->prof_ev[p][0], h->prof_ev[p][1]));
+  }
+  return B200VA_OK;
+}
+
+static int env_int(const char* name) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : 0;
+}
+
 static int create_impl(b200va_ctx* h) {
   const b200va_config& c = h->cfg;
+  h->tune.decode_impl = env_int("B200VA_DECODE_IMPL");
+  h->tune.decode_ta = env_int("B200VA_DECODE_TA");
+  h->tune.decode_rows = env_int("B200VA_DECODE_ROWS");
+  h->tune.decode_stages = env_int("B200VA_DECODE_STAGES");
+  h->tune.decode_ctas_per_sm = env_int("B200VA_DECODE_CTAS_PER_SM");
+  if (getenv("B200VA_FUSE_POST_TRACK")) h->tune.fuse_post_track = env_int("B200VA_FUSE_POST_TRACK");
+  if (getenv("B200VA_PDL")) h->tune.pdl = env_int("B200VA_PDL");
   REQUIRE(h, c.max_batch >= 1 && c.max_batch <= B200VA_MAX_BATCH, "max_batch must be in [1, %d]", B200VA_MAX_BATCH);
   REQUIRE(h, c.max_anchors >= 1 && c.max_anchors <= 262144, "max_anchors must be in [1, 262144]");
   REQUIRE(h, c.max_candidates >= 1 && c.max_candidates <= 8192, "max_candidates must be in [1, 8192]");
@@ -105,6 +170,9 @@ extern "C" int b200va_destroy(b200va_handle h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_decoded) cudaEventDestroy(h->ev_decoded);
+    for (int p = 0; p < B200VA_PHASE_COUNT; ++p)
+      for (int k = 0; k < 2; ++k)
+        if (h->prof_ev[p][k]) cudaEventDestroy(h->prof_ev[p][k]);
     if (h->nms_stats_host) cudaFreeHost(h->nms_stats_host);
     if (h->cand_key) cudaFree(h->cand_key);
     if (h->cand_box) cudaFree(h->cand_box);
@@ -137,6 +205,17 @@ extern "C" int b200va_poll_status(b200va_handle h, void* stream) {
                      flags[FLAG_DET_OVERFLOW] ? " detections>max_dets" : "",
                      flags[FLAG_TRACK_OVERFLOW] ? " tracks>max_tracks" : "");
   }
+  return B200VA_OK;
+}
+
+static_assert(B200VA_STATUS_WORDS == FLAG_COUNT, "status word count");
+extern "C" int b200va_read_status_async(b200va_handle h, int32_t* host_out, int clear, void* stream) {
+  if (!h || !host_out) return B200VA_ERR_INVALID;
+  std::lock_guard<std::recursive_mutex> lock(h->mu);
+  DeviceGuard guard(h->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(h, cudaMemcpyAsync(host_out, h->status_flags, sizeof(int32_t) * FLAG_COUNT, cudaMemcpyDeviceToHost, st));
+  if (clear) CUDA_TRY(h, cudaMemsetAsync(h->status_flags, 0, sizeof(int32_t) * FLAG_COUNT, st));
   return B200VA_OK;
 }
 

@@ -12,6 +12,7 @@
 #include <mutex>
 #include <string>
 #include <tuple>
+#include <utility>
 #include <vector>
 
 #include "b200va.h"
@@ -54,10 +55,26 @@ struct b200va_ctx {
   cudaStream_t side_stream = nullptr;    // non-blocking, highest priority (its 32-CTA kernels slot in first)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_decoded = nullptr;
   cudaEvent_t hook_after_decode = nullptr;  // when set, b200va_postprocess records it right after the decode launch
+  bool hook_recorded = false;               // ... and reports here that it did
+  // b200va_tick schedule 3: the decode kernel runs on the caller's stream, everything after it (NMS, tracker) on
+  // `post_tail_stream`, which first waits for the hook event; the letterbox launched next on the caller's stream is
+  // a programmatic dependent of the decode kernel (`pdl_preprocess`) and fills the SMs next to it
+  cudaStream_t post_tail_stream = nullptr;
+  bool pdl_preprocess = false;
   // ---- NMS variant selection: host-mapped statistic written by k_sort_nms ----
   int* nms_stats_host = nullptr;
   int* nms_stats_dev = nullptr;
   int nms_dense_ttl = 0;  // launches left on the grid variant after the last dense sighting
+  // ---- b200va_set_profiling: one timed event pair per phase ----
+  bool profiling = false;
+  cudaEvent_t prof_ev[B200VA_PHASE_COUNT][2] = {};
+  bool prof_rec[B200VA_PHASE_COUNT] = {};
+  // ---- developer tuning knobs, read once from B200VA_* environment variables (0 = automatic) ----
+  struct Tune {
+    int decode_impl = 0, decode_ta = 0, decode_rows = 0, decode_stages = 0, decode_ctas_per_sm = 0;
+    int fuse_post_track = 1;  // B200VA_FUSE_POST_TRACK=0: always launch NMS and tracker as two kernels
+    int pdl = 1;              // B200VA_PDL=0: no programmatic dependent launches
+  } tune;
   // ---- developer phase timing (only written by builds with -DB200VA_PHASE_TIMING) ----
   long long* dbg = nullptr;  // device int64[DBG_SLOTS]
 };
@@ -110,6 +127,39 @@ inline int set_error(b200va_ctx* h, int code, const char* fmt, ...) {
     if (!(cond)) return set_error((h), B200VA_ERR_INVALID, __VA_ARGS__); \
   } while (0)
 
+// NVTX range "b200va:<phase>" around an entry point's launches, plus the phase's event pair when profiling is on.
+// Declared after the argument checks, so error returns before it record nothing.
+const char* phase_name(int phase);  // api.cu
+struct PhaseScope {
+  b200va_ctx* h;
+  int phase;
+  cudaStream_t st;
+  bool timed = false;
+  PhaseScope(b200va_ctx* h_, int phase_, cudaStream_t st_);
+  ~PhaseScope();
+  PhaseScope(const PhaseScope&) = delete;
+  PhaseScope& operator=(const PhaseScope&) = delete;
+};
+
+#ifdef __CUDACC__
+// launch on `st` as a programmatic dependent of the kernel before it (its prologue overlaps that kernel's tail)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+#endif
+
 struct DeviceGuard {
   int prev = -1;
   explicit DeviceGuard(int dev) {
@@ -157,6 +207,12 @@ __device__ __forceinline__ int warp_sum(int v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running; everything before griddep_wait() overlaps the predecessor's
+// tail, everything after it sees the predecessor's writes (a no-op for ordinary launches)
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---- mbarrier + 1-D bulk async copy (TMA engine, UBLKCP in SASS) -----------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

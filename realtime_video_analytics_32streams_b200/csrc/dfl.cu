@@ -118,6 +118,7 @@ extern "C" int b200va_dfl_decode(b200va_handle h, const float* raw, int batch, i
   p.reg_max = reg_max;
   p.A = total;
   p.n_levels = n_levels;
+  PhaseScope phase(h, B200VA_PHASE_DFL, (cudaStream_t)stream);
   dim3 grid((total + 127) / 128, batch);
   if (reg_max == 16) k_dfl_decode<16><<<grid, 128, 0, (cudaStream_t)stream>>>(p);
   else k_dfl_decode<0><<<grid, 128, 0, (cudaStream_t)stream>>>(p);

@@ -904,6 +904,7 @@ extern "C" int b200va_roi_rasterize(b200va_handle h, const int32_t* pts, const i
   const size_t lo = (eb + 255) & ~(size_t)255;
   if (lo + lb > ROI_SCRATCH_BYTES) return set_error(h, B200VA_ERR_CAPACITY, "polygons too complex: %zu edges", edges.size());
   uint8_t* scratch = (uint8_t*)h->roi_scratch;
+  PhaseScope phase(h, B200VA_PHASE_ROI, st);
   if (eb) CUDA_TRY(h, cudaMemcpyAsync(scratch, edges.data(), eb, cudaMemcpyHostToDevice, st));
   if (lb) CUDA_TRY(h, cudaMemcpyAsync(scratch + lo, lines.data(), lb, cudaMemcpyHostToDevice, st));
   const int chunks = (width + 15) / 16;
@@ -933,6 +934,7 @@ extern "C" int b200va_apply_mask(b200va_handle h, const uint8_t* src, int64_t sr
   const long long threads = (long long)chunks * height;
   const int vec_ok = (width % 16 == 0) && ((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0) &&
                      ((uintptr_t)mask % 16 == 0) && (src_pitch % 16 == 0) && (dst_pitch % 16 == 0);
+  PhaseScope phase(h, B200VA_PHASE_ROI, (cudaStream_t)stream);
   k_apply_mask<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, src_pitch, mask, height, width, dst,
                                                                                   dst_pitch, vec_ok);
   LAUNCH_CHECK(h);
@@ -950,6 +952,7 @@ extern "C" int b200va_motion(b200va_handle h, const uint8_t* const* frames, cons
   REQUIRE(h, frames && src_h && src_w && next_gray && has_prev && changed_out, "NULL argument");
   REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
   if (batch == 0) return B200VA_OK;
+  PhaseScope phase(h, B200VA_PHASE_MOTION, st);
   CUDA_TRY(h, cudaMemsetAsync(changed_out, 0, sizeof(int32_t) * batch, st));
   // frames with and without an ROI mask go to separate launches (the mask is a template switch), and so do
   // 16-byte aligned frames (tile kernel, TMA-fed) and everything else (generic kernel); `changed` is indexed
@@ -1043,6 +1046,7 @@ extern "C" int b200va_motion_preprocess(b200va_handle h, const uint8_t* const* f
   if (batch == 0) return B200VA_OK;
   const size_t esz = fmt == B200VA_OUT_F32_RGB_NCHW ? 4 : 2;
   const size_t frame_bytes = (size_t)3 * dst_h * dst_w * esz;
+  PhaseScope phase(h, B200VA_PHASE_MOTION, st);
   CUDA_TRY(h, cudaMemsetAsync(changed_out, 0, sizeof(int32_t) * batch, st));
 
   std::vector<int> fused[2];  // by ROI mask

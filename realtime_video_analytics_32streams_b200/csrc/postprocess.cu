@@ -12,11 +12,14 @@
 //       memory, then exact greedy NMS in 64-box chunks -- an in-chunk 64x64 IoU bit matrix
 //       resolved by one warp, after which the chunk's survivors suppress every later box in
 //       parallel -- and ordered emission with the float64 re-threshold folded in.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include <cuda_fp16.h>
 
+#include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
+#include "tracker_body.cuh"
 
 namespace {
 
@@ -101,6 +104,7 @@ __device__ __forceinline__ void emit_candidate(const PostParams& p, int frame, i
 // per thread keep HBM busy.
 template <int VEC>
 __global__ void __launch_bounds__(64) k_decode_cm(const __grid_constant__ PostParams p, int frame0) {
+  griddep_launch_dependents();  // the NMS kernel may start its prologue now; its griddep_wait() still waits for this grid
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int a0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
@@ -231,6 +235,7 @@ __global__ void __launch_bounds__(64) k_decode_cm(const __grid_constant__ PostPa
 // At 32 frames per launch the kernel is HBM-bound and this variant is slower (22 us against 20 us): the host picks.
 template <int kSplitParts, int kSplitRows>  // kSplitRows: rows one warp holds in flight (<= kSplitParts * kSplitRows class rows)
 __global__ void __launch_bounds__(32 * kSplitParts) k_decode_cm_split(const __grid_constant__ PostParams p, int frame0) {
+  griddep_launch_dependents();  // the NMS kernel may start its prologue now; its griddep_wait() still waits for this grid
   __shared__ float s_best[kSplitParts - 1][4][32];
   __shared__ int s_cls[kSplitParts - 1][4][32];
   __shared__ unsigned s_nan[kSplitParts - 1][32];
@@ -329,8 +334,222 @@ __global__ void __launch_bounds__(32 * kSplitParts) k_decode_cm_split(const __gr
   }
 }
 
+// channel-major head, TMA-fed and persistent -- the LARGE-BATCH variant.  k_decode_cm is a one-wave kernel whose CTAs
+// walk the class rows in lock step: every thread waits ~10 dependent load round trips, nothing is in flight while the
+// last one drains and the epilogue runs, and launch, ramp and tail are paid on a 14 us stream (0.70 of the HBM peak
+// at [32, 84, 8400]).  Here a CTA is a producer warp plus consumer warps around a shared-memory ring, like
+// k_letterbox / k_motion_tile: one elected lane feeds the bulk-copy engine (cp.async.bulk -> UBLKCP) with row pieces
+// of `ta` anchors (1-2 KB each), `rows` channel rows per stage, always `stages` stages ahead and running on into the
+// CTA's next tile while the consumers finish the current one; consumer thread g owns anchors 4g..4g+3 of the tile
+// and reads its rows from shared memory with conflict-free 16-byte loads.  The grid is sized so that every CTA is
+// resident and owns the same number of tiles: all CTAs share the bus equally and finish together.
+constexpr int kRingMaxStages = 8;
+constexpr int kRingWarps = 4;  // consumer warps -> tiles of up to 512 anchors
+struct RingCfg {
+  int ta;               // anchors per tile = boxes * bw
+  int bw;               // anchors per TMA box (<= 256: the box-dimension limit), multiple of 4
+  int boxes;            // boxes per stage (1 or 2)
+  int rows;             // channel rows per stage (= box height, >= cls0 + 1)
+  int stages;           // ring depth
+  int tiles_per_frame;  // ceil(A / ta)
+  int n_tiles;          // tiles_per_frame * frames of the launch
+  int warps;            // consumer warps that own anchors: ceil(ta / 128)
+};
+
+// candidate filter + warp-aggregated compaction + emit for the four anchors a0..a0+3 of one thread; called by all 32
+// lanes of a warp (lanes without anchors pass in_range = false)
+__device__ __forceinline__ void emit_quad(const PostParams& p, int frame, int lane, int a0, bool in_range, const float (&best)[4],
+                                          const int (&cls)[4], unsigned nan_seen, const float4 cx, const float4 cy,
+                                          const float4 w, const float4 h) {
+  unsigned pass = 0;
+  if (in_range) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (!((nan_seen >> k) & 1u) && (p.ultra ? best[k] > p.conf_thr : best[k] >= p.conf_thr) && class_allowed(p, cls[k]))
+        pass |= 1u << k;
+  }
+  const int mine = __popc(pass);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  int base = 0;
+  if (lane == 31) base = atomicAdd(p.cand_count + frame, total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  int pos = base + incl - mine;
+  if (pass) {
+    const float cxa[4] = {cx.x, cx.y, cx.z, cx.w}, cya[4] = {cy.x, cy.y, cy.z, cy.w};
+    const float wa[4] = {w.x, w.y, w.z, w.w}, ha[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (pass & (1u << k)) {
+        emit_candidate(p, frame, pos, a0 + k, best[k], cls[k], decode_box(cxa[k], cya[k], wa[k], ha[k], p.f[frame], p.ultra != 0));
+        ++pos;
+      }
+  }
+}
+
+// NaN-propagating maximum (FMNMX.NAN / FMNMX3.NAN): the result is NaN as soon as one input is
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float max3_nan(float a, float b, float c) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// One stage = `rows` consecutive channel rows of a tile, fetched by ONE tensor-map copy per 256-anchor box
+// (cp.async.bulk.tensor.3d -> UTMALDG): coordinates (anchor, channel, frame) of a [B, C, A] float32 tensor; rows past C
+// and anchors past A are out of bounds for the map and arrive as zeros without touching memory.  Row-by-row 1-D bulk
+// copies are NOT an option here: one thread sustains only ~4 M cp.async.bulk per second (250 ns each, measured with
+// tools/scratch/readbw.cu), so 1-2 KB row pieces cap a CTA at 4-8 GB/s -- 2 KB pieces reached 3.1 TB/s, 1 KB 1.8 TB/s.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__global__ void __launch_bounds__(32 * (kRingWarps + 1)) k_decode_ring(const __grid_constant__ PostParams p, int frame0,
+                                                                        const RingCfg rc,
+                                                                        const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) uint8_t s_ring[];
+  __shared__ __align__(8) uint64_t full[kRingMaxStages], empty[kRingMaxStages];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = p.C, A = p.A, S = rc.stages, cls0 = p.cls0;
+  const uint32_t box_bytes = (uint32_t)rc.rows * (uint32_t)rc.bw * 4u;
+  const uint32_t stage_bytes = box_bytes * (uint32_t)rc.boxes;
+  griddep_launch_dependents();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], (uint32_t)rc.warps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == kRingWarps) {
+    // ---- producer: one lane drives the TMA engine, a ring ahead of the consumers ----
+    if (lane != 0) return;
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap)) : "memory");
+    int st = 0, use = 0;
+    for (int tile = blockIdx.x; tile < rc.n_tiles; tile += gridDim.x) {
+      const int frame = tile / rc.tiles_per_frame;
+      const int a0 = (tile - frame * rc.tiles_per_frame) * rc.ta;
+      for (int r0 = 0; r0 < C; r0 += rc.rows) {
+        if (use > 0) mbar_wait(&empty[st], (uint32_t)(use - 1) & 1u);
+        const int nb = min(rc.boxes, (A - a0 + rc.bw - 1) / rc.bw);  // boxes wholly past the last anchor are not fetched
+        mbar_expect_tx(&full[st], (uint32_t)nb * box_bytes);
+        uint8_t* dst = s_ring + (size_t)st * stage_bytes;
+        for (int b = 0; b < nb; ++b) tma_load_3d(dst + (size_t)b * box_bytes, &tmap, a0 + b * rc.bw, r0, frame, &full[st]);  // the map starts at frame0
+        if (++st == S) {
+          st = 0;
+          ++use;
+        }
+      }
+    }
+    return;
+  }
+  if (warp >= rc.warps) return;
+
+  // ---- consumers: thread g owns anchors 4g .. 4g+3 of the tile ----
+  // The class scan is the instruction-heavy part (80 rows x 4 anchors per thread): rows are taken four at a time,
+  // the group's maximum (FMNMX3) is compared with the running best, and only the index of the winning GROUP is
+  // kept -- 9 instructions per anchor and group instead of ~11 per anchor and ROW.  `>` on the group maxima keeps
+  // the first group that reaches the overall maximum and emit resolves the first row inside it (np.argmax: first
+  // maximum wins).  The maxima are NaN-propagating: one NaN score turns `best` into NaN for good, which fails the
+  // confidence filter exactly like NumPy's argmax landing on the NaN does.
+  const int g = warp * 32 + lane;
+  const int ta = rc.ta, bw = rc.bw;
+  const int gbox = (4 * g) / bw;                                 // which box of a stage holds this thread's anchors
+  const uint32_t goff = (uint32_t)gbox * box_bytes + (uint32_t)(4 * g - gbox * bw) * 4u;
+  const float ninf = __int_as_float(0xff800000);
+  int st = 0;
+  uint32_t ph = 0;
+  for (int tile = blockIdx.x; tile < rc.n_tiles; tile += gridDim.x) {
+    const int frame = tile / rc.tiles_per_frame;
+    const int a_tile = (tile - frame * rc.tiles_per_frame) * ta;
+    const bool active = 4 * g < min(ta, A - a_tile);
+    float4 cx, cy, bwid, bh, obj = make_float4(1.f, 1.f, 1.f, 1.f);  // x * 1.0f is exact: scores = pred[:, 4:]
+    float best[4] = {ninf, ninf, ninf, ninf};
+    int grp[4] = {0, 0, 0, 0};  // first class of the winning group
+    for (int r0 = 0; r0 < C; r0 += rc.rows) {
+      const int r1 = min(C, r0 + rc.rows);
+      mbar_wait(&full[st], ph);
+      const float* rowp = reinterpret_cast<const float*>(s_ring + (size_t)st * stage_bytes + (active ? goff : 0u));
+      if (r0 == 0) {
+        cx = *reinterpret_cast<const float4*>(rowp);
+        cy = *reinterpret_cast<const float4*>(rowp + bw);
+        bwid = *reinterpret_cast<const float4*>(rowp + 2 * bw);
+        bh = *reinterpret_cast<const float4*>(rowp + 3 * bw);
+        if (p.use_obj) obj = *reinterpret_cast<const float4*>(rowp + 4 * bw);  // column 4 as objectness (detector.py:294-305)
+        rowp += (size_t)cls0 * bw;
+      }
+      int c = (r0 == 0 ? cls0 : r0) - cls0;  // class index of the stage's first class row
+      const int c_end = r1 - cls0;
+      for (; c + 4 <= c_end; c += 4, rowp += 4 * bw) {
+        const float4 v0 = *reinterpret_cast<const float4*>(rowp), v1 = *reinterpret_cast<const float4*>(rowp + bw);
+        const float4 v2 = *reinterpret_cast<const float4*>(rowp + 2 * bw), v3 = *reinterpret_cast<const float4*>(rowp + 3 * bw);
+        const float m[4] = {
+            max_nan(max3_nan(__fmul_rn(v0.x, obj.x), __fmul_rn(v1.x, obj.x), __fmul_rn(v2.x, obj.x)), __fmul_rn(v3.x, obj.x)),
+            max_nan(max3_nan(__fmul_rn(v0.y, obj.y), __fmul_rn(v1.y, obj.y), __fmul_rn(v2.y, obj.y)), __fmul_rn(v3.y, obj.y)),
+            max_nan(max3_nan(__fmul_rn(v0.z, obj.z), __fmul_rn(v1.z, obj.z), __fmul_rn(v2.z, obj.z)), __fmul_rn(v3.z, obj.z)),
+            max_nan(max3_nan(__fmul_rn(v0.w, obj.w), __fmul_rn(v1.w, obj.w), __fmul_rn(v2.w, obj.w)), __fmul_rn(v3.w, obj.w))};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          grp[k] = m[k] > best[k] ? c : grp[k];
+          best[k] = max_nan(best[k], m[k]);
+        }
+      }
+      for (; c < c_end; ++c, rowp += bw) {  // fewer than four rows left in the stage: groups of one
+        const float4 v = *reinterpret_cast<const float4*>(rowp);
+        const float m[4] = {__fmul_rn(v.x, obj.x), __fmul_rn(v.y, obj.y), __fmul_rn(v.z, obj.z), __fmul_rn(v.w, obj.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          grp[k] = m[k] > best[k] ? c : grp[k];
+          best[k] = max_nan(best[k], m[k]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+      if (++st == S) {
+        st = 0;
+        ph ^= 1u;
+      }
+    }
+    // resolve the class of the (rare) anchors that pass the confidence filter: first row of the winning group whose
+    // score equals the maximum; the rows come back from L2
+    int cls[4] = {0, 0, 0, 0};
+    if (active) {
+      const float* hd = p.head + (size_t)(frame0 + frame) * C * A + a_tile + 4 * g;
+      const float oa[4] = {obj.x, obj.y, obj.z, obj.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!(p.ultra ? best[k] > p.conf_thr : best[k] >= p.conf_thr)) continue;
+        cls[k] = grp[k];
+        for (int j = 0; j < 4 && grp[k] + j < C - cls0; ++j)
+          if (__fmul_rn(__ldg(hd + (size_t)(cls0 + grp[k] + j) * A + k), oa[k]) == best[k]) {
+            cls[k] = grp[k] + j;
+            break;
+          }
+      }
+    }
+    emit_quad(p, frame, lane, a_tile + 4 * g, active, best, cls, 0u, cx, cy, bwid, bh);
+  }
+}
+
 // anchor-major head [B, A, C]: a warp owns one anchor and strides its lanes over the channels
 __global__ void __launch_bounds__(256) k_decode_am(const __grid_constant__ PostParams p, int frame0) {
+  griddep_launch_dependents();  // the NMS kernel may start its prologue now; its griddep_wait() still waits for this grid
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -450,15 +669,17 @@ __device__ __forceinline__ void cell_range(const float4 b, float inv_w, float in
   if (cy1 < cy0) cy1 = cy0;
 }
 
-constexpr int kNmsThreads = 1024;
+constexpr int kNmsThreads = 1024;     // k_sort_nms
+constexpr int kNmsThreadsSmall = 256;  // k_post_track: sparse scenes, NMS and tracker of a stream in one CTA
 
+// Sort + NMS + emit of one frame by one CTA of NT threads.
 // GRID: carries the kept-box grid code.  Two instantiations because the grid path's registers and stack slots slow
 // the common small-n launch (which never runs it) from 9.5 to 14 us when it is compiled in; the host picks per launch
 // from the candidate counts the previous launch reported (NmsParams::stats).
-template <bool GRID>
-__global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant__ NmsParams p) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  const int frame = blockIdx.x;
+template <bool GRID, int NT>
+__device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, uint8_t* const smem_raw) {
+  static_assert(!GRID || NT == 1024, "the kept-box grid code assumes 1024 threads");
+  static_assert(NT >= 128 && NT % 32 == 0, "bad CTA width");
   const int tid = threadIdx.x;
   PHASE_STAMP(p.dbg, 16);
   const int n_raw = p.cand_count[frame];
@@ -490,8 +711,8 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
     return;
   }
   const size_t cbase = (size_t)frame * p.max_cand;
-  for (int i = tid; i < np2; i += kNmsThreads) keys[i] = i < n ? p.cand_key[cbase + i] : 0ull;
-  for (int i = tid; i < np2 / 32; i += kNmsThreads) supp[i] = 0u;
+  for (int i = tid; i < np2; i += NT) keys[i] = i < n ? p.cand_key[cbase + i] : 0ull;
+  for (int i = tid; i < np2 / 32; i += NT) supp[i] = 0u;
   __syncthreads();
 
   PHASE_STAMP(p.dbg, 17);
@@ -500,7 +721,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
     // streams the whole key array from shared memory (broadcast reads) -- two barriers in total
     // where a bitonic network needs one per round.  O(n^2) compares: only worth it for small n.
     unsigned long long* sorted = reinterpret_cast<unsigned long long*>(box);  // box[] is not live yet
-    for (int i = tid; i < n; i += kNmsThreads) {
+    for (int i = tid; i < n; i += NT) {
       const unsigned long long ki = keys[i];
       int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
       int j = 0;
@@ -514,14 +735,14 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
       sorted[r0 + r1 + r2 + r3] = ki;
     }
     __syncthreads();
-    for (int i = tid; i < n; i += kNmsThreads) keys[i] = sorted[i];
+    for (int i = tid; i < n; i += NT) keys[i] = sorted[i];
     __syncthreads();
   } else {
     // bitonic sort, descending.  Only the warps that own a compare-exchange take part (named barrier 1).
     // Thread q owns the q-th pair of a step; for j <= 32 the 32 pairs of a warp lie inside one aligned block of 64
     // keys, so consecutive steps with j <= 32 depend on nothing another warp writes and a __syncwarp separates
     // them; the block-wide barrier is paid only around the steps with j > 32 (20 of the 66 steps at 2048 keys).
-    const int sort_threads = min(kNmsThreads, max(32, np2 >> 1));
+    const int sort_threads = min(NT, max(32, np2 >> 1));
     if (tid < sort_threads) {
       for (int k = 2; k <= np2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -545,24 +766,17 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
     __syncthreads();
   }
   PHASE_STAMP(p.dbg, 18);
-  // gather boxes (to shared memory) and class ids (to registers) of the sorted candidates in one
-  // round of global loads; element i = tid + 1024 * k lives in slot k of the thread
-  int my_cls[8];  // max_candidates <= 8192
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int i = tid + k * kNmsThreads;
-    my_cls[k] = 0;
-    if (i < n) {
-      const size_t o = cbase + (keys[i] & 0x3fffull);
-      float4 b = p.cand_box[o];
-      my_cls[k] = p.cand_cls[o];
-      if (p.ultra && !p.ultra_agnostic) {  // boxes = x[:, :4] + x[:, 5:6] * max_wh, float32 (the rounding is part of the semantics)
-        const float c = __fmul_rn((float)my_cls[k], 7680.f);
-        b = make_float4(__fadd_rn(b.x, c), __fadd_rn(b.y, c), __fadd_rn(b.z, c), __fadd_rn(b.w, c));
-      }
-      box[i] = b;
-      scl[i] = (uint16_t)my_cls[k];
+  // gather boxes and class ids of the sorted candidates into shared memory in one round of global loads
+  for (int i = tid; i < n; i += NT) {
+    const size_t o = cbase + (keys[i] & 0x3fffull);
+    float4 b = p.cand_box[o];
+    const int cl = p.cand_cls[o];
+    if (p.ultra && !p.ultra_agnostic) {  // boxes = x[:, :4] + x[:, 5:6] * max_wh, float32 (the rounding is part of the semantics)
+      const float c = __fmul_rn((float)cl, 7680.f);
+      b = make_float4(__fadd_rn(b.x, c), __fadd_rn(b.y, c), __fadd_rn(b.z, c), __fadd_rn(b.w, c));
     }
+    box[i] = b;
+    scl[i] = (uint16_t)cl;
   }
   __syncthreads();
 
@@ -576,8 +790,8 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
   const bool use_grid = GRID && grid != nullptr && !ultra && thr_nonneg && n > 256;
   const float inv_cw = (float)kGX / (p.f[frame].xmax + 1.0f), inv_ch = (float)kGY / (p.f[frame].ymax + 1.0f);
   if (GRID && use_grid) {
-    for (int c = tid; c < kCells; c += kNmsThreads) grid->cnt[c] = 0;
-    for (int w = tid; w < (n + 31) / 32; w += kNmsThreads) over_mark[w] = 0u;
+    for (int c = tid; c < kCells; c += NT) grid->cnt[c] = 0;
+    for (int w = tid; w < (n + 31) / 32; w += NT) over_mark[w] = 0u;
     if (tid == 0) grid->n_over = 0;
     __syncthreads();
   }
@@ -670,8 +884,8 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
     NMS_MARK(acc_q);
     // (a) in-chunk IoU bits: thread -> row i = tid / 16, columns 4 * (tid % 16) ..; the predicate is
     // symmetric, so only pairs j > i are evaluated and a hit sets both (i, j) and (j, i)
-    {
-      const int i = tid >> 4, jb = (tid & 15) << 2;
+    for (int task = tid; task < 1024; task += NT) {
+      const int i = task >> 4, jb = (task & 15) << 2;
       if (i < m && jb + 3 > i) {
         const float4 bi = box[c0 + i];
 #pragma unroll
@@ -754,12 +968,12 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
       }
       __syncthreads();
       int g = 16;
-      while (g > 1 && tail * g > kNmsThreads) g >>= 1;
+      while (g > 1 && tail * g > NT) g >>= 1;
       const int part = tid & (g - 1);
       const int per = (nk + g - 1) / g;
       const int qb = part * per, qe = min(nk, qb + per);
       if (qb < qe) {
-        for (int j = c0 + 64 + tid / g; j < n; j += kNmsThreads / g) {
+        for (int j = c0 + 64 + tid / g; j < n; j += NT / g) {
           if ((supp[j >> 5] >> (j & 31)) & 1u) continue;
           const float4 bj = box[j];
           const int cj = scl[j];
@@ -837,7 +1051,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
   }
   // filter_detections (detector.py:99-103): float64 compare on the kept boxes only
   if (p.use_filter) {
-    for (int i = tid; i < n; i += kNmsThreads) {
+    for (int i = tid; i < n; i += NT) {
       if ((keep_w[i >> 5] >> (i & 31)) & 1u) {
         const float conf = unorder_bits((uint32_t)(keys[i] >> 32));
         if (!((double)conf >= p.filter_thr)) atomicAnd(&keep_w[i >> 5], ~(1u << (i & 31)));
@@ -856,10 +1070,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
     if (acc > p.max_dets) atomicOr(p.flags + FLAG_DET_OVERFLOW, 1);
   }
   __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int i = tid + k * kNmsThreads;
-    if (i >= n) break;
+  for (int i = tid; i < n; i += NT) {
     const unsigned long long w = ((unsigned long long)keep_w[2 * (i >> 6) + 1] << 32) | keep_w[2 * (i >> 6)];
     if ((w >> (i & 63)) & 1ull) {
       const int pos = keep_off[i >> 6] + __popcll(w & ((1ull << (i & 63)) - 1ull));
@@ -869,11 +1080,33 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
         if (ultra) b = ultra_scale_box(p.cand_box[cbase + (keys[i] & 0x3fffull)], p.f[frame]);  // the un-shifted box
         reinterpret_cast<float4*>(p.out_box)[o] = b;
         p.out_conf[o] = unorder_bits((uint32_t)(keys[i] >> 32));
-        p.out_cls[o] = my_cls[k];
+        p.out_cls[o] = p.cand_cls[cbase + (keys[i] & 0x3fffull)];  // the full int32 class id (scl[] holds 16 bits)
       }
     }
   }
   PHASE_STAMP(p.dbg, 21);
+}
+
+template <bool GRID>
+__global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant__ NmsParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  griddep_launch_dependents();  // a tracker kernel behind this one may be scheduled; its griddep_wait() waits for this grid
+  griddep_wait();
+  nms_frame<GRID, kNmsThreads>(p, blockIdx.x, smem_raw);
+}
+
+// Sparse scenes: sort + NMS + emit of frame i followed by the tracker update of stream i in ONE CTA of 256 threads.
+// The detections never leave the SM's caches between the two halves, one launch and one kernel-to-kernel dependency
+// disappear from the critical chain decode -> NMS -> tracker (what a tick of a few streams per GPU is made of), and
+// 256-thread barriers replace 1024-thread ones.  Any candidate count is handled correctly (just more slowly than by
+// the 1024-thread grid variant), so the host's choice between the two never changes a result.
+__global__ void __launch_bounds__(kNmsThreadsSmall) k_post_track(const __grid_constant__ NmsParams q,
+                                                                  const __grid_constant__ TrkParams t) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  griddep_wait();
+  nms_frame<false, kNmsThreadsSmall>(q, blockIdx.x, smem_raw);
+  __syncthreads();  // this frame's detections were written by this CTA: visible to all of its threads from here on
+  tracker_stream(t, blockIdx.x, smem_raw);
 }
 
 static int next_pow2(int v) {
@@ -895,15 +1128,126 @@ size_t nms_smem_bytes(int max_cand) {
   return nms_base_bytes(max_cand) + (nms_grid_offset(max_cand) ? sizeof(NmsGrid) + cap / 8 + cap * 2 : 0);
 }
 
+static const int kRingSmemMax = 96 * 1024;
+
+// Tile width, stage shape and grid of k_decode_ring for `frames` heads of [C, A].  Every CTA must be resident
+// (ctas_per_sm per SM) and should own the same number of tiles: the widest tile whose busiest CTA carries at most
+// 2 % more than the mean wins.  B200VA_DECODE_TA / _ROWS / _STAGES / _CTAS_PER_SM override the choice
+// (tools/bench_decode.py sweeps them).
+static void ring_plan(const b200va_ctx* h, int frames, int C, int A, int cls0, RingCfg* rc, int* n_cta, size_t* smem) {
+  const int per_sm = h->tune.decode_ctas_per_sm > 0 ? h->tune.decode_ctas_per_sm : 3;
+  const int cap = h->num_sms * per_sm;
+  auto eval = [&](int ta, int* ctas) {
+    const long long tiles = (long long)((A + ta - 1) / ta) * frames;
+    const long long tpc = (tiles + cap - 1) / cap;
+    *ctas = (int)((tiles + tpc - 1) / tpc);
+    return (double)frames * A / ((double)*ctas * (double)tpc * ta);
+  };
+  // a tile is one TMA box of up to 256 anchors, or two boxes; a box row is a multiple of 128 bytes so that every
+  // box and stage starts 128-byte aligned in shared memory (a TMA requirement)
+  auto valid = [](int t) { return t >= 64 && t <= 512 && (t <= 256 ? t % 32 == 0 : t % 64 == 0); };
+  int ta = h->tune.decode_ta, ctas = 0;
+  if (!valid(ta)) {
+    double best = -1.0;
+    ta = 128;
+    for (int t = 256; t >= 128; t -= 32) {
+      int c;
+      const double e = eval(t, &c);
+      if (e >= 0.98) {
+        ta = t;
+        break;
+      }
+      if (e > best) best = e, ta = t;
+    }
+  }
+  eval(ta, &ctas);
+  rc->ta = ta;
+  rc->boxes = ta > 256 ? 2 : 1;
+  rc->bw = ta / rc->boxes;
+  rc->tiles_per_frame = (A + ta - 1) / ta;
+  rc->n_tiles = rc->tiles_per_frame * frames;
+  rc->warps = (ta / 4 + 31) / 32;
+  // rows per stage: ~20 KB stages by default, as equal as possible over the C rows, never fewer than the box rows +
+  // objectness + one class row (the consumers expect them in a tile's first stage)
+  int rows = h->tune.decode_rows;
+  if (rows <= 0) {
+    const int want = (20 * 1024) / (ta * 4);
+    const int n_stage = (C + want - 1) / (want > 0 ? want : 1);
+    rows = (C + n_stage - 1) / n_stage;
+  }
+  if (rows < cls0 + 1) rows = cls0 + 1;
+  if (rows > 256) rows = 256;
+  if (rows > C) rows = C;
+  rc->rows = rows;
+  const size_t stage = (size_t)rows * ta * 4;
+  int stages = h->tune.decode_stages > 0 ? h->tune.decode_stages : (int)((size_t)(64 * 1024) / stage);
+  if (stages < 2) stages = 2;
+  if (stages > kRingMaxStages) stages = kRingMaxStages;
+  while (stages > 2 && stages * stage > (size_t)kRingSmemMax) --stages;
+  rc->stages = stages;
+  *n_cta = ctas;
+  *smem = stages * stage;
+}
+
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// tensor map over a head [B, C, A] float32 with boxes of `bw` anchors x `rows` channel rows of one frame
+static bool head_tensor_map(const float* head, int B, int C, int A, int bw, int rows, CUtensorMap* out) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)A, (cuuint64_t)C, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)A * 4, (cuuint64_t)A * 4 * (cuuint64_t)C};
+  const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(head), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int postprocess_configure(b200va_ctx* h) {
+  CUDA_TRY(h, cudaFuncSetAttribute(k_decode_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmemMax));
   const size_t smem = nms_smem_bytes(h->cfg.max_candidates);
   if (smem > 220 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_candidates %d needs %zu bytes of shared memory", h->cfg.max_candidates, smem);
+  {
+    const size_t fused = std::max(smem, tracker_smem_bytes(h->cfg.max_tracks));
+    if (fused <= 200 * 1024) CUDA_TRY(h, cudaFuncSetAttribute(k_post_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused));
+  }
   CUDA_TRY(h, cudaFuncSetAttribute(k_sort_nms<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_TRY(h, cudaFuncSetAttribute(k_sort_nms<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return B200VA_OK;
 }
 
 namespace {
+// b200va_tick: the tracker update that follows this post-process on the same stream.  When the launch qualifies, NMS
+// and tracker run as one kernel (k_post_track) and `done` is set; otherwise the caller launches the tracker itself.
+struct FuseReq {
+  const int* stream_slots;
+  int batch, max_dets;
+  const double* det_scale;
+  const uint8_t* skip;
+  const b200va_tracker_cfg* cfg;
+  const int64_t* id_base;
+  const b200va_tracks* out;
+  int32_t* new_counts;
+  bool done;
+  bool tail_on_side;  // schedule 3: NMS (and the fused tracker) went to the handle's tail stream
+};
+
 struct UltraOpts {  // b200va_postprocess_ultralytics
   const int* src_h;
   const int* src_w;
@@ -915,7 +1259,7 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
                                   const b200va_letterbox* meta, double conf_thr, double iou_thr,
                                   const int32_t* classes, int n_classes, int score_mode, int nms_mode,
                                   double filter_conf_thr_f64, int use_filter, const b200va_dets* out, void* stream,
-                                  const UltraOpts* ultra) {
+                                  const UltraOpts* ultra, FuseReq* fuse = nullptr) {
   if (!h) return B200VA_ERR_INVALID;
   std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
@@ -984,6 +1328,8 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
     p.cls0 = p.use_obj ? 5 : 4;
     p.conf_thr = (float)conf_thr;  // NEP-50 weak scalar: compared in float32 (detector.py:312)
     p.ultra = ultra ? 1 : 0;
+    {
+    PhaseScope phase(h, B200VA_PHASE_DECODE, st);
     if (layout == B200VA_HEAD_CHANNEL_MAJOR) {
       // 16-byte loads need every channel row (A floats) and the tensor base 16-byte aligned
       // (a TMA-staged variant -- all C rows of a 128-anchor tile bulk-copied to shared memory -- measured
@@ -991,10 +1337,29 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
       // 33.6 KB stride bound both; block sizes 64..256 are equivalent, 512 is slower)
       const int n_cls_rows = channels - p.cls0;
       const bool vec4 = anchors % 4 == 0 && ((uintptr_t)head % 16 == 0);
-      // few frames: latency-bound, split the class rows over 8 warps; many frames: HBM-bound, one thread per anchor quad
-      if (vec4 && n <= 8 && n_cls_rows >= 16 && n_cls_rows <= 96) {
+      // few frames: latency-bound, split the class rows over 8 warps; many frames: HBM-bound, the TMA-fed persistent ring
+      const int impl = h->tune.decode_impl;  // 0 auto, 1 registers (k_decode_cm), 2 ring, 3 split
+      const bool split_ok = vec4 && n_cls_rows >= 16 && n_cls_rows <= 96;
+      // The ring kernel is opt-in (B200VA_DECODE_IMPL=2): measured on [32, 84, 8400] it is no faster than the register
+      // kernel, and neither can be -- a pure 90 MB read of this tensor takes 19.4 us on a B200 whatever fetches it
+      // (linear LDG, 1-D bulk copies with enough issuing warps, tensor-map boxes: tools/readbw.cu,
+      // profiles/r2_readbw.log), and k_decode_cm<4> needs 20.1 us.
+      bool ring_ok = vec4 && anchors >= 128 && impl == 2;
+      RingCfg rc;
+      int ring_ctas = 0;
+      size_t ring_smem = 0;
+      alignas(64) CUtensorMap tmap;
+      if (ring_ok) {
+        ring_plan(h, n, channels, anchors, p.cls0, &rc, &ring_ctas, &ring_smem);
+        // the map spans the frames of this launch only (coordinate 2 = frame index inside the launch)
+        ring_ok = ring_smem <= (size_t)kRingSmemMax &&
+                  head_tensor_map(head + (size_t)base * channels * anchors, n, channels, anchors, rc.bw, rc.rows, &tmap);
+      }
+      if (split_ok && (impl == 3 || (impl == 0 && n <= 8))) {
         dim3 grid((anchors / 4 + 31) / 32, n);
         k_decode_cm_split<8, 12><<<grid, 256, 0, st>>>(p, base);
+      } else if (ring_ok) {
+        k_decode_ring<<<ring_ctas, 32 * (kRingWarps + 1), ring_smem, st>>>(p, base, rc, tmap);
       } else if (vec4) {
         dim3 grid((anchors / 4 + 63) / 64, n);
         k_decode_cm<4><<<grid, 64, 0, st>>>(p, base);
@@ -1007,8 +1372,20 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
       k_decode_am<<<grid, 256, 0, st>>>(p, base);
     }
     LAUNCH_CHECK(h);
+    }
     // b200va_tick, schedule 1: the letterbox on the caller's stream starts when the (HBM-bound) decode is done
-    if (h->hook_after_decode && base + n >= batch) CUDA_TRY(h, cudaEventRecord(h->hook_after_decode, st));
+    if (h->hook_after_decode && base + n >= batch) {
+      CUDA_TRY(h, cudaEventRecord(h->hook_after_decode, st));
+      h->hook_recorded = true;
+    }
+    // schedule 3 of b200va_tick (single launch group only): the rest of the post-process moves to the tail stream
+    cudaStream_t decode_st = st;
+    const bool split_streams = h->post_tail_stream && h->hook_recorded && base == 0 && n == batch;
+    if (split_streams) {
+      CUDA_TRY(h, cudaStreamWaitEvent(h->post_tail_stream, h->hook_after_decode, 0));
+      st = h->post_tail_stream;
+    }
+    (void)decode_st;
 
     NmsParams q;
     memset(&q, 0, sizeof(q));
@@ -1051,9 +1428,32 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
       dense = h->nms_dense_ttl > 0;
       if (dense && cap == cudaStreamCaptureStatusNone) --h->nms_dense_ttl;
     }
-    if (dense && q.grid_off) k_sort_nms<true><<<n, kNmsThreads, nms_smem_bytes(h->cfg.max_candidates), st>>>(q);
-    else k_sort_nms<false><<<n, kNmsThreads, nms_smem_bytes(h->cfg.max_candidates), st>>>(q);
+    PhaseScope phase(h, B200VA_PHASE_NMS, st);
+    const size_t nms_smem = nms_smem_bytes(h->cfg.max_candidates);
+    const bool pdl = h->tune.pdl != 0 && !split_streams;  // across streams the event carries the dependency
+    // sparse scene, one launch group, detection rows = this handle's tables: NMS + tracker in one 256-thread CTA
+    const size_t fused_smem = std::max(nms_smem, tracker_smem_bytes(h->cfg.max_tracks));
+    if (fuse && fuse->stream_slots && fuse->cfg && !dense && h->tune.fuse_post_track != 0 && base == 0 && n == batch && fuse->batch == batch &&
+        fuse->max_dets == h->cfg.max_dets && fused_smem <= 200 * 1024) {
+      TrkParams t;
+      memset(&t, 0, sizeof(t));
+      t.f_box = out->bbox_xyxy;
+      t.f_conf = out->conf;
+      t.d_cls = out->cls;
+      t.d_count = out->count;
+      t.max_dets = fuse->max_dets;
+      const int rc = tracker_fill_params(h, t, fuse->stream_slots, fuse->batch, fuse->det_scale, fuse->skip, fuse->cfg,
+                                         fuse->id_base, fuse->out, fuse->new_counts);
+      if (rc != B200VA_OK) return rc;
+      CUDA_TRY(h, launch_pdl(k_post_track, dim3(n), dim3(kNmsThreadsSmall), fused_smem, st, pdl, q, t));
+      fuse->done = true;
+    } else if (dense && q.grid_off) {
+      CUDA_TRY(h, launch_pdl(k_sort_nms<true>, dim3(n), dim3(kNmsThreads), nms_smem, st, pdl, q));
+    } else {
+      CUDA_TRY(h, launch_pdl(k_sort_nms<false>, dim3(n), dim3(kNmsThreads), nms_smem, st, pdl, q));
+    }
     LAUNCH_CHECK(h);
+    if (fuse) fuse->tail_on_side = split_streams;
   }
   return B200VA_OK;
 }
@@ -1074,4 +1474,18 @@ extern "C" int b200va_postprocess_ultralytics(b200va_handle h, const float* head
   const UltraOpts u{src_h, src_w, in_h, in_w, agnostic ? 1 : 0, max_det};
   return postprocess_impl(h, head, layout, batch, channels, anchors, nullptr, conf_thr, iou_thr, classes, n_classes,
                           B200VA_SCORE_V8_NATIVE, B200VA_NMS_AGNOSTIC, filter_conf_thr_f64, use_filter, out, stream, &u);
+}
+
+// b200va_tick: post-process followed by the tracker update of the same rows; *fused tells the caller whether the
+// tracker already ran inside the post-process's second kernel.
+int postprocess_then_track(b200va_handle h, const b200va_tick_args* a, void* stream, bool* fused, bool* tail_on_side) {
+  FuseReq f{a->stream_slots, a->trk_batch, a->max_dets, a->det_scale, a->skip, a->trk_cfg, a->id_base, a->tracks, a->new_counts, false, false};
+  const bool want = a->stream_slots != nullptr && a->trk_batch > 0 && a->trk_batch == a->head_batch && a->trk_cfg != nullptr;
+  const int rc = postprocess_impl(h, a->head, a->layout, a->head_batch, a->channels, a->anchors, a->meta, a->conf_thr, a->iou_thr,
+                                  a->classes, a->n_classes, a->score_mode, a->nms_mode, a->filter_conf_thr_f64, a->use_filter,
+                                  a->dets, stream, nullptr, &f);
+  *fused = f.done;
+  *tail_on_side = f.tail_on_side;
+  (void)want;
+  return rc;
 }

@@ -553,15 +553,17 @@ extern "C" int b200va_letterbox_meta(int src_h, int src_w, int dst_h, int dst_w,
   return B200VA_OK;
 }
 
+// pdl: launch as a programmatic dependent of the kernel before it in the stream WITHOUT ever waiting for it
+// (b200va_tick schedule 3: the letterbox shares no data with the decode kernel it follows, it only wants to start
+// filling the SMs that kernel leaves free)
 template <int FMT, bool MASK>
-static cudaError_t launch_one(const PreParams& p, dim3 grid, size_t smem, cudaStream_t st) {
-  k_letterbox<FMT, MASK><<<grid, kThreads, smem, st>>>(p);
-  return cudaGetLastError();
+static cudaError_t launch_one(const PreParams& p, dim3 grid, size_t smem, cudaStream_t st, bool pdl) {
+  return launch_pdl(k_letterbox<FMT, MASK>, grid, dim3(kThreads), smem, st, pdl, p);
 }
 
 template <int FMT>
-static cudaError_t launch_letterbox(const PreParams& p, bool mask, dim3 grid, size_t smem, cudaStream_t st) {
-  return mask ? launch_one<FMT, true>(p, grid, smem, st) : launch_one<FMT, false>(p, grid, smem, st);
+static cudaError_t launch_letterbox(const PreParams& p, bool mask, dim3 grid, size_t smem, cudaStream_t st, bool pdl) {
+  return mask ? launch_one<FMT, true>(p, grid, smem, st, pdl) : launch_one<FMT, false>(p, grid, smem, st, pdl);
 }
 
 static const int kLetterboxSmemMax = 200 * 1024;
@@ -590,6 +592,7 @@ static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* 
   const int fmt = fmt_and_flags & 0xff;
   REQUIRE(h, fmt >= 0 && fmt <= 3 && (fmt_and_flags & ~(0xff | B200VA_OUT_FLAG_PADS_VALID)) == 0, "unknown output format %d",
           fmt_and_flags);
+  PhaseScope phase(h, outs ? B200VA_PHASE_RESIZE : B200VA_PHASE_PREPROCESS, st);
   std::vector<int> order[2];
   for (int b = 0; b < batch; ++b) order[(roi_masks && roi_masks[b]) ? 1 : 0].push_back(b);
   for (int with_mask = 0; with_mask < 2; ++with_mask) {
@@ -666,11 +669,13 @@ static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* 
       dim3 grid((dst_h + rpc - 1) / rpc, n);
       const size_t smem = (size_t)stages * per_stage;
       cudaError_t e;
+      const bool pdl = h->pdl_preprocess && h->tune.pdl != 0;
+      h->pdl_preprocess = false;  // only the first launch of the call directly follows the decode kernel
       switch (fmt) {
-        case B200VA_OUT_F32_RGB_NCHW: e = launch_letterbox<B200VA_OUT_F32_RGB_NCHW>(p, with_mask, grid, smem, st); break;
-        case B200VA_OUT_F16_RGB_NCHW: e = launch_letterbox<B200VA_OUT_F16_RGB_NCHW>(p, with_mask, grid, smem, st); break;
-        case B200VA_OUT_U8_BGR_NCHW: e = launch_letterbox<B200VA_OUT_U8_BGR_NCHW>(p, with_mask, grid, smem, st); break;
-        default: e = launch_letterbox<B200VA_OUT_U8_BGR_NHWC>(p, with_mask, grid, smem, st); break;
+        case B200VA_OUT_F32_RGB_NCHW: e = launch_letterbox<B200VA_OUT_F32_RGB_NCHW>(p, with_mask, grid, smem, st, pdl); break;
+        case B200VA_OUT_F16_RGB_NCHW: e = launch_letterbox<B200VA_OUT_F16_RGB_NCHW>(p, with_mask, grid, smem, st, pdl); break;
+        case B200VA_OUT_U8_BGR_NCHW: e = launch_letterbox<B200VA_OUT_U8_BGR_NCHW>(p, with_mask, grid, smem, st, pdl); break;
+        default: e = launch_letterbox<B200VA_OUT_U8_BGR_NHWC>(p, with_mask, grid, smem, st, pdl); break;
       }
       h->launches.fetch_add(1, std::memory_order_relaxed);
       if (e != cudaSuccess) return set_error(h, B200VA_ERR_CUDA, "letterbox launch failed: %s", cudaGetErrorString(e));
@@ -868,6 +873,7 @@ extern "C" int b200va_upload_frames(b200va_handle h, const uint8_t* const* host_
   cudaStream_t st = (cudaStream_t)stream;
   REQUIRE(h, host_frames && dev_frames && src_h && src_w, "NULL argument");
   REQUIRE(h, batch >= 0, "negative batch");
+  PhaseScope phase(h, B200VA_PHASE_UPLOAD, st);
   int64_t total = 0;
   for (int b = 0; b < batch; ++b) {
     REQUIRE(h, host_frames[b] && dev_frames[b] && src_h[b] > 0 && src_w[b] > 0, "frame %d: bad arguments", b);

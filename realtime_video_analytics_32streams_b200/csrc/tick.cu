@@ -2,42 +2,62 @@
 // the last head tensor as two branches of one call (fork / join on events, capturable in a graph).
 #include "common.cuh"
 
+int postprocess_then_track(b200va_handle h, const b200va_tick_args* a, void* stream, bool* fused, bool* tail_on_side);  // postprocess.cu
+
 extern "C" int b200va_tick(b200va_handle h, const b200va_tick_args* a, void* stream) {
   if (!h || !a) return B200VA_ERR_INVALID;
   std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
-  REQUIRE(h, a->schedule >= 0 && a->schedule <= 2, "unknown schedule %d", a->schedule);
+  REQUIRE(h, a->schedule >= 0 && a->schedule <= 3, "unknown schedule %d", a->schedule);
   cudaStream_t main_st = (cudaStream_t)stream;
   const bool has_pre = a->frames != nullptr && a->batch > 0;
   const bool has_post = a->head != nullptr && a->head_batch > 0;
   const bool has_trk = a->stream_slots != nullptr && a->trk_batch > 0;
   const bool fork = a->schedule != 0 && has_pre && (has_post || has_trk);
-  cudaStream_t post_st = fork ? h->side_stream : main_st;
-  int rc = B200VA_OK;
-  if (fork) {
+  // schedule 3: the decode kernel stays on the caller's stream and the letterbox follows it there as a programmatic
+  // dependent that never waits: its CTAs start as soon as every decode CTA is running and fill the SMs beside them, so
+  // HBM sees the decode's reads and the letterbox's writes together and no kernel-to-kernel gap separates the two;
+  // NMS + tracker move to the side stream behind an event recorded right after the decode.
+  const bool sched3 = a->schedule == 3 && fork && has_post && a->head_batch <= B200VA_LAUNCH_FRAMES;
+  cudaStream_t post_st = (fork && !sched3) ? h->side_stream : main_st;
+  PhaseScope phase(h, B200VA_PHASE_TICK, main_st);
+  if (fork && !sched3) {
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, main_st));
     CUDA_TRY(h, cudaStreamWaitEvent(post_st, h->ev_fork, 0));
   }
+  // From here on the side stream is forked: every path, errors included, must reach the join below (an unjoined
+  // stream invalidates a CUDA-graph capture), so failures are collected in `rc` instead of returning early.
+  int rc = B200VA_OK;
+  bool tracked = false, tail_on_side = false;
+  auto note = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && rc == B200VA_OK) rc = set_error(h, B200VA_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+  };
   if (has_post) {
-    h->hook_after_decode = (fork && a->schedule == 1) ? h->ev_decoded : nullptr;
-    rc = b200va_postprocess(h, a->head, a->layout, a->head_batch, a->channels, a->anchors, a->meta, a->conf_thr,
-                            a->iou_thr, a->classes, a->n_classes, a->score_mode, a->nms_mode, a->filter_conf_thr_f64,
-                            a->use_filter, a->dets, post_st);
-    const bool hooked = h->hook_after_decode != nullptr;
+    h->hook_after_decode = (fork && (a->schedule == 1 || sched3)) ? h->ev_decoded : nullptr;
+    h->hook_recorded = false;
+    h->post_tail_stream = sched3 ? h->side_stream : nullptr;
+    // sparse scenes: NMS and the tracker update of the same rows run as ONE kernel (k_post_track)
+    rc = postprocess_then_track(h, a, post_st, &tracked, &tail_on_side);
     h->hook_after_decode = nullptr;
-    if (rc == B200VA_OK && hooked && a->channels >= 5 && a->anchors > 0)
-      CUDA_TRY(h, cudaStreamWaitEvent(main_st, h->ev_decoded, 0));
+    h->post_tail_stream = nullptr;
+    // the post-process reports whether it recorded the hook (it does not for empty or malformed heads)
+    if (h->hook_recorded && !sched3) note(cudaStreamWaitEvent(main_st, h->ev_decoded, 0), "cudaStreamWaitEvent(decoded)");
+    if (tail_on_side) post_st = h->side_stream;
   }
-  if (rc == B200VA_OK && has_trk)
+  if (rc == B200VA_OK && has_trk && !tracked)
     rc = b200va_tracker_update(h, a->stream_slots, a->trk_batch, a->dets, a->max_dets, a->det_scale, a->skip, a->trk_cfg,
                                a->id_base, a->tracks, a->new_counts, post_st);
-  if (fork) CUDA_TRY(h, cudaEventRecord(h->ev_join, post_st));  // always rejoin, also after an error
+  const bool joined = fork && post_st == h->side_stream;
+  if (joined) note(cudaEventRecord(h->ev_join, post_st), "cudaEventRecord(join)");
+  h->pdl_preprocess = sched3 && tail_on_side;
   if (rc == B200VA_OK && has_pre) {
-    if (a->ev_pre_begin) CUDA_TRY(h, cudaEventRecord((cudaEvent_t)a->ev_pre_begin, main_st));
-    rc = b200va_preprocess(h, a->frames, a->src_h, a->src_w, a->src_pitch, a->batch, a->roi_masks, a->net_out, a->dst_h,
-                           a->dst_w, a->out_format, a->meta_out, main_st);
-    if (rc == B200VA_OK && a->ev_pre_end) CUDA_TRY(h, cudaEventRecord((cudaEvent_t)a->ev_pre_end, main_st));
+    if (a->ev_pre_begin) note(cudaEventRecord((cudaEvent_t)a->ev_pre_begin, main_st), "cudaEventRecord(pre_begin)");
+    if (rc == B200VA_OK)
+      rc = b200va_preprocess(h, a->frames, a->src_h, a->src_w, a->src_pitch, a->batch, a->roi_masks, a->net_out, a->dst_h,
+                             a->dst_w, a->out_format, a->meta_out, main_st);
+    if (rc == B200VA_OK && a->ev_pre_end) note(cudaEventRecord((cudaEvent_t)a->ev_pre_end, main_st), "cudaEventRecord(pre_end)");
   }
-  if (fork) CUDA_TRY(h, cudaStreamWaitEvent(main_st, h->ev_join, 0));
+  h->pdl_preprocess = false;
+  if (joined) note(cudaStreamWaitEvent(main_st, h->ev_join, 0), "cudaStreamWaitEvent(join)");
   return rc;
 }

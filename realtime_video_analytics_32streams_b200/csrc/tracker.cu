@@ -10,554 +10,14 @@
 // buffer, which preserves dict insertion order.  Track ids come from one counter shared by all
 // streams (tracker.py:47): CTAs hand out provisional ordinals and the last CTA to finish turns
 // them into ids in batch order -- the order one shared IouTracker would have been called in.
-#include "common.cuh"
-
-struct TrackerState {
-  // ping-pong buffers, each [max_streams, max_tracks]
-  long long* id[2];
-  int32_t* cls[2];
-  double* conf[2];
-  double* box[2];  // [.., 4]
-  int32_t* age[2];
-  int32_t* hits[2];
-  uint8_t* touched;   // [max_streams, max_tracks]
-  int32_t* count;     // [max_streams]
-  int32_t* cur;       // [max_streams] current buffer index
-  long long* next_id; // shared counter
-  uint32_t* ticket;   // last-CTA election
-  int32_t* new_count; // [max_batch] scratch
-  void* base = nullptr;
-};
+#include "tracker_body.cuh"
 
 namespace {
 
-struct TrkParams {
-  TrackerState st;
-  int slots[B200VA_MAX_BATCH];
-  double det_scale[B200VA_MAX_BATCH];
-  long long id_base[B200VA_MAX_BATCH];
-  uint8_t skip[B200VA_MAX_BATCH];
-  // detections (one of the two sources)
-  const float* f_box;
-  const float* f_conf;
-  const double* d_box;
-  const double* d_conf;
-  const int32_t* d_cls;
-  const int32_t* d_count;
-  int max_dets, max_tracks, batch;
-  int max_age, min_hits;
-  double thr;
-  int has_id_base, has_scale;
-  // outputs (optional)
-  long long* o_id;
-  int32_t* o_cls;
-  double* o_conf;
-  double* o_box;
-  int32_t* o_age;
-  int32_t* o_hits;
-  int32_t* o_count;
-  int32_t* o_new;
-  int32_t* flags;
-  long long* dbg;
-};
-
-
-// tracker.py:129-147, IEEE double, no contraction.
-__device__ __forceinline__ double iou64(double ax1, double ay1, double ax2, double ay2, double bx1, double by1,
-                                        double bx2, double by2) {
-  const double iw = fmax(0.0, __dsub_rn(fmin(ax2, bx2), fmax(ax1, bx1)));
-  const double ih = fmax(0.0, __dsub_rn(fmin(ay2, by2), fmax(ay1, by1)));
-  const double inter = __dmul_rn(iw, ih);
-  const double area_a = __dmul_rn(fmax(0.0, __dsub_rn(ax2, ax1)), fmax(0.0, __dsub_rn(ay2, ay1)));
-  const double area_b = __dmul_rn(fmax(0.0, __dsub_rn(bx2, bx1)), fmax(0.0, __dsub_rn(by2, by1)));
-  const double uni = __dsub_rn(__dadd_rn(area_a, area_b), inter);
-  if (uni <= 0.0) return 0.0;
-  return __ddiv_rn(inter, uni);
-}
-
-// launched; a stream with few detections and tracks keeps only kTrkThreadsMin of them.  512 by default, not 1024: a 1024-thread
-// CTA owns the whole register file of its SM until it retires, and in b200va_tick the tracker runs underneath the
-// letterbox -- 32 SMs closed to letterbox CTAs for 14 us cost the 32 x 1080p tick 3 us (dense tracker: 84 us at 512, 63 at 1024)
-constexpr int kTrkThreadsMax = 1024;   // widest launch (dense scenes, see tracker_launch)
-constexpr int kTrkThreadsWide = 512;   // default launch width
-constexpr int kTrkThreadsMin = 256;
-constexpr int kDetChunk = 64;  // detections staged in shared memory at a time (two warps cover a chunk)
-constexpr int kCand = 6;        // candidate slots per detection and kind; more -> exact brute-force scan
-
-struct DetStage {
-  double4 box[kDetChunk];
-  double conf[kDetChunk];
-  int cls[kDetChunk];
-};
-struct Cand {
-  double iou;
-  int idx;  // track index (c_trk) or chunk-local detection index (c_det)
-  int pad_;
-};
-
-// Boxes whose intersection is empty have IoU 0, which can never beat best_iou = 0.0 (tracker.py:100-106).
-__device__ __forceinline__ bool overlaps(const double4 a, const double4 b) {
-  return (a.z > b.x) & (b.z > a.x) & (a.z > a.x) & (b.z > b.x) & (a.w > b.y) & (b.w > a.y) & (a.w > a.y) & (b.w > b.y);
-}
-
-// Best track for one detection among tracks t = first, first + stride, ... (tracker.py:97-109).
-__device__ __forceinline__ void scan_tracks(const double* __restrict__ sbox, const int32_t* __restrict__ scls, int T,
-                                            int first, int stride, const double4 db, int dcls, double thr,
-                                            double& best, int& best_t) {
-  best = 0.0;  // best_iou starts at 0.0 and must be beaten strictly
-  best_t = 0x7fffffff;
-  for (int t = first; t < T; t += stride) {
-    if (scls[t] != dcls) continue;
-    const double4 tb = reinterpret_cast<const double4*>(sbox)[t];
-    if (!overlaps(tb, db)) continue;
-    const double v = iou64(tb.x, tb.y, tb.z, tb.w, db.x, db.y, db.z, db.w);
-    if (v >= thr && v > best) {
-      best = v;
-      best_t = t;
-    }
-  }
-}
-
-__device__ __forceinline__ void warp_argmax(double& best, int& best_t) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int ot = __shfl_xor_sync(0xffffffffu, best_t, o);
-    if (ob > best || (ob == best && ot < best_t)) {  // ties: earliest-inserted track
-      best = ob;
-      best_t = ot;
-    }
-  }
-}
-
-// The matching is sequential in the reference, but every IoU it can ever ask for within one chunk of
-// detections is known up front: detection i against a track as it stood at the start of the chunk,
-// or against an earlier detection of the chunk (a matched or new track carries exactly that box).
-//
-//   phase A   all threads: those float64 IoUs; per detection keep the few that pass the threshold
-//             (c_trk: vs tracks, c_det: vs earlier detections) and count how many detections claim
-//             each track.
-//   phase A2  a thread per detection: a detection is SIMPLE when it has no detection-detection edge
-//             and every track it could match is claimed by it alone -- nothing another detection does
-//             can change its outcome, so it is resolved right away (arg-max over its own list).
-//   phase B   one warp walks the remaining CONFLICTED detections in order, look-ups only:
-//             aux[key] = last conflicted detection that took the track `key`; a track created by
-//             detection j of the chunk has the virtual key Tc + j until phase C numbers it.
-//   phase C   all threads: number the new tracks in detection order (prefix sum), add the hits, and
-//             let the last detection matched to each track write its box.
-//   A chunk in which some detection has more than kCand candidates falls back to the plain
-//   sequential scan (exact, slower).  Nothing in the sequential parts touches global memory:
-//   confidence, age and id of a touched track are derived from last_det[] at write-back.
 __global__ void __launch_bounds__(kTrkThreadsMax) k_tracker(const __grid_constant__ TrkParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  double* sbox = reinterpret_cast<double*>(smem_raw);                            // [max_tracks][4]
-  int32_t* scls = reinterpret_cast<int32_t*>(sbox + (size_t)p.max_tracks * 4);   // [max_tracks]
-  int32_t* shits = scls + p.max_tracks;                                          // [max_tracks]
-  int32_t* aux = shits + p.max_tracks;                                           // [max_tracks + kDetChunk] claims, then phase-B state
-  int16_t* last_det = reinterpret_cast<int16_t*>(aux + p.max_tracks + kDetChunk);  // [max_tracks] detection holding the track's box now, -1 untouched
-  __shared__ DetStage sd;
-  __shared__ Cand c_trk[kDetChunk][kCand], c_det[kDetChunk][kCand];
-  __shared__ int n_trk[kDetChunk], n_det[kDetChunk], key[kDetChunk], conflicted[kDetChunk], clist[kDetChunk];
-  __shared__ int s_T, s_new, s_is_last, s_fallback, s_nconf;
-  __shared__ int wsum[kTrkThreadsMax / 32];
-
-  const int bi = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  PHASE_STAMP(p.dbg, 0);
-  const int slot = p.slots[bi];
-  const TrackerState& S = p.st;
-  const int cur = S.cur[slot];
-  const size_t sb = (size_t)slot * p.max_tracks;
-  long long* id_c = S.id[cur] + sb;
-  int32_t* cls_c = S.cls[cur] + sb;
-  double* conf_c = S.conf[cur] + sb;
-  double* box_c = S.box[cur] + sb * 4;
-  int32_t* age_c = S.age[cur] + sb;
-  int32_t* hits_c = S.hits[cur] + sb;
-  const int T0 = S.count[slot];
-  const int D = p.skip[bi] ? 0 : min(p.d_count[bi], p.max_dets);
-  // phase A is bound by dependent shared-memory latency on one SM and scales with the warp count (dense config,
-  // 313 detections x 365 tracks: 131 us with 256 threads, 84 us with 512, 63 us with 1024), while a small stream
-  // (25 x 25) only pays for the wider barriers (19 us with 256, 22 us with 1024): the surplus warps of a small
-  // stream leave at once (a barrier counts the warps that are still alive); see kTrkThreadsMax for the width launched
-  const int kTrkThreads = (T0 > 96 || D > 64) ? (int)blockDim.x : kTrkThreadsMin;
-  if (tid >= kTrkThreads) return;
-
-  for (int t = tid; t < T0; t += kTrkThreads) {
-    const double4 b0 = reinterpret_cast<const double4*>(box_c)[t];
-    reinterpret_cast<double4*>(sbox)[t] = b0;
-    scls[t] = cls_c[t];
-    shits[t] = hits_c[t];
-    last_det[t] = -1;
-  }
-  if (tid == 0) {
-    s_T = T0;
-    s_new = 0;
-  }
-
-  const size_t db = (size_t)bi * p.max_dets;
-  const double scale = p.det_scale[bi];
-
-  PHASE_STAMP(p.dbg, 1);
-  for (int d0 = 0; d0 < D; d0 += kDetChunk) {
-    const int nd = min(kDetChunk, D - d0);
-    if (d0) __syncthreads();  // previous chunk fully consumed
-    for (int i = tid; i < nd; i += kTrkThreads) {
-      const int d = d0 + i;
-      double4 b;
-      double cf;
-      if (p.f_box) {
-        const float4 f4 = reinterpret_cast<const float4*>(p.f_box)[db + d];
-        b = make_double4(f4.x, f4.y, f4.z, f4.w);
-        cf = (double)p.f_conf[db + d];
-        if (p.has_scale) {  // StreamWorker._rescale_detections, pipeline.py:224-240: float64 multiply
-          b.x = __dmul_rn(b.x, scale);
-          b.y = __dmul_rn(b.y, scale);
-          b.z = __dmul_rn(b.z, scale);
-          b.w = __dmul_rn(b.w, scale);
-        }
-      } else {
-        b = reinterpret_cast<const double4*>(p.d_box)[db + d];
-        cf = p.d_conf[db + d];
-      }
-      sd.box[i] = b;
-      sd.conf[i] = cf;
-      sd.cls[i] = p.d_cls[db + d];
-      n_trk[i] = 0;
-      n_det[i] = 0;
-    }
-    if (tid == 0) {
-      s_fallback = 0;
-      s_nconf = 0;
-    }
-    __syncthreads();
-    PHASE_STAMP(p.dbg, 2);
-
-    // ---- phase A: every IoU the chunk can need.  Warp w takes detections w, w+8, ..; lanes take tracks ----
-    const int Tc = s_T;
-    for (int t = tid; t < Tc + kDetChunk; t += kTrkThreads) aux[t] = 0;  // claims per track
-    __syncthreads();
-    for (int i = warp; i < nd; i += kTrkThreads / 32) {
-      const double4 bx = sd.box[i];
-      const int dcls = sd.cls[i];
-      for (int t = lane; t < Tc; t += 32) {
-        if (scls[t] != dcls) continue;
-        const double4 tb = reinterpret_cast<const double4*>(sbox)[t];
-        if (!overlaps(tb, bx)) continue;
-        const double v = iou64(tb.x, tb.y, tb.z, tb.w, bx.x, bx.y, bx.z, bx.w);
-        if (v >= p.thr && v > 0.0) {
-          const int k = atomicAdd(&n_trk[i], 1);
-          if (k < kCand) {
-            c_trk[i][k].iou = v;
-            c_trk[i][k].idx = t;
-          }
-          atomicAdd(&aux[t], 1);
-        }
-      }
-      for (int e = lane; e < i; e += 32) {
-        if (sd.cls[e] != dcls) continue;
-        const double4 eb = sd.box[e];
-        if (!overlaps(eb, bx)) continue;
-        const double v = iou64(eb.x, eb.y, eb.z, eb.w, bx.x, bx.y, bx.z, bx.w);
-        if (v >= p.thr && v > 0.0) {
-          const int k = atomicAdd(&n_det[i], 1);
-          if (k < kCand) {
-            c_det[i][k].iou = v;
-            c_det[i][k].idx = e;
-          }
-        }
-      }
-    }
-    __syncthreads();
-
-    // ---- phase A2: classify; simple detections are resolved here ----
-    {
-      bool conf = false;
-      if (tid < nd) {
-        const int i = tid;
-        const int nt = n_trk[i], ne = n_det[i];
-        if (nt > kCand || ne > kCand) atomicOr(&s_fallback, 1);
-        conf = ne > 0;
-        double best = 0.0;
-        int best_t = 0x7fffffff;
-        for (int k = 0; k < min(nt, kCand); ++k) {
-          const Cand c = c_trk[i][k];
-          conf |= aux[c.idx] > 1;
-          if (c.iou > best || (c.iou == best && c.idx < best_t)) {
-            best = c.iou;
-            best_t = c.idx;
-          }
-        }
-        conflicted[i] = conf;
-        key[i] = conf ? -1 : (best_t == 0x7fffffff ? Tc + i : best_t);
-      }
-      // ordered list of the conflicted detections (kDetChunk <= 64: two warps cover the chunk)
-      const unsigned bal = __ballot_sync(0xffffffffu, conf);
-      if (warp < 2 && lane == 0) wsum[warp] = __popc(bal);
-      __syncthreads();
-      if (tid < nd && conf) clist[(warp ? wsum[0] : 0) + __popc(bal & ((1u << lane) - 1u))] = tid;
-      if (tid == 0) s_nconf = wsum[0] + (nd > 32 ? wsum[1] : 0);
-      // phase-B state: aux[key] = last conflicted detection that took `key` (-1: none)
-      __syncthreads();
-      for (int t = tid; t < Tc + kDetChunk; t += kTrkThreads) aux[t] = -1;
-      __syncthreads();
-    }
-    PHASE_STAMP(p.dbg, 7);
-
-    if (s_fallback) {
-      // ---- crowded chunk: plain sequential scan of the live table, exact (tracker.py:50-109) ----
-      if (warp == 0) {
-        for (int i = 0; i < nd; ++i) {
-          const int T = s_T;
-          const int dcls = sd.cls[i];
-          double best;
-          int best_t;
-          scan_tracks(sbox, scls, T, lane, 32, sd.box[i], dcls, p.thr, best, best_t);
-          const unsigned cand = __ballot_sync(0xffffffffu, best_t != 0x7fffffff);
-          int match = 0x7fffffff;
-          if (cand) {
-            warp_argmax(best, best_t);
-            match = best_t;
-          }
-          if (lane == 0) {
-            int t = match;
-            if (t == 0x7fffffff) {
-              t = T;
-              if (t < p.max_tracks) {
-                scls[t] = dcls;
-                shits[t] = 1;
-                s_new = s_new + 1;
-                s_T = T + 1;
-              } else {
-                atomicOr(p.flags + FLAG_TRACK_OVERFLOW, 1);
-                t = -1;
-              }
-            } else {
-              shits[t] += 1;
-            }
-            if (t >= 0) {
-              last_det[t] = (int16_t)(d0 + i);
-              reinterpret_cast<double4*>(sbox)[t] = sd.box[i];
-            }
-          }
-          __syncwarp();
-        }
-      }
-    } else {
-      // ---- phase B: conflicted detections, in order, look-ups only ----
-      if (warp == 0) {
-        const int nconf = s_nconf;
-        for (int q = 0; q < nconf; ++q) {
-          const int i = clist[q];
-          const int nt = n_trk[i], ne = n_det[i];
-          double best = 0.0;
-          int best_t = 0x7fffffff;
-          if (lane < nt) {
-            const Cand c = c_trk[i][lane];
-            if (aux[c.idx] < 0) {  // nobody re-boxed this track yet in the chunk
-              best = c.iou;
-              best_t = c.idx;
-            }
-          } else if (lane >= kCand && lane - kCand < ne) {
-            const Cand c = c_det[i][lane - kCand];
-            const int e = c.idx, k = key[e];  // the track detection e was given (k >= 0: e precedes i)
-            // still carrying e's box: e was the last to take it (conflicted e), or nobody took it after a simple e
-            if (k >= 0 && (conflicted[e] ? aux[k] == e : aux[k] < 0)) {
-              best = c.iou;
-              best_t = k;
-            }
-          }
-          const unsigned cand = __ballot_sync(0xffffffffu, best_t != 0x7fffffff);
-          int match = Tc + i;  // no match: new track (virtual key)
-          if (cand) {
-            if (cand & (cand - 1)) {
-              warp_argmax(best, best_t);
-              match = best_t;
-            } else {
-              match = __shfl_sync(0xffffffffu, best_t, __ffs(cand) - 1);
-            }
-          }
-          if (lane == 0) {
-            key[i] = match;
-            aux[match] = i;
-          }
-          __syncwarp();
-        }
-      }
-      __syncthreads();
-
-      // ---- phase C: number the new tracks in detection order, count hits, write the final boxes ----
-      {
-        const int i = tid;
-        const int k = i < nd ? key[i] : -1;
-        const bool is_new = i < nd && k == Tc + i;
-        const unsigned bal = __ballot_sync(0xffffffffu, is_new);
-        if (warp < 2 && lane == 0) wsum[warp] = __popc(bal);
-        __syncthreads();
-        const int total_new = wsum[0] + (nd > 32 ? wsum[1] : 0);
-        const int room = p.max_tracks - Tc;
-        if (is_new) {
-          const int rank = (warp ? wsum[0] : 0) + __popc(bal & ((1u << lane) - 1u));
-          clist[i] = rank;  // clist is free again: rank of the track created by detection i
-          if (rank < room) {
-            scls[Tc + rank] = sd.cls[i];
-            shits[Tc + rank] = 0;
-            last_det[Tc + rank] = -1;
-          }
-        }
-        __syncthreads();
-        if (i < nd) {
-          const int r = k < Tc ? k : Tc + clist[k - Tc];
-          if (r < p.max_tracks) {
-            atomicAdd(&shits[r], 1);
-            // the last detection matched to a track leaves its box there
-            const bool last = conflicted[i] ? aux[k] == i : aux[k] < 0;
-            if (last) {
-              last_det[r] = (int16_t)(d0 + i);
-              reinterpret_cast<double4*>(sbox)[r] = sd.box[i];
-            }
-          }
-        }
-        if (tid == 0) {
-          const int made = min(total_new, room);
-          if (total_new > room) atomicOr(p.flags + FLAG_TRACK_OVERFLOW, 1);
-          s_new += made;
-          s_T = Tc + made;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  PHASE_STAMP(p.dbg, 3);
-
-  // ---- prune + stable compaction into the other buffer (tracker.py:111-126) ----
-  const int T = s_T;
-  const int nxt = cur ^ 1;
-  long long* id_n = S.id[nxt] + sb;
-  int32_t* cls_n = S.cls[nxt] + sb;
-  double* conf_n = S.conf[nxt] + sb;
-  double* box_n = S.box[nxt] + sb * 4;
-  int32_t* age_n = S.age[nxt] + sb;
-  int32_t* hits_n = S.hits[nxt] + sb;
-  const size_t ob = (size_t)bi * p.max_tracks;
-  __shared__ int warp_cnt[kTrkThreadsMax / 32];
-  __shared__ int s_base;
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (int t0 = 0; t0 < T; t0 += kTrkThreads) {
-    const int t = t0 + tid;
-    bool keep = false;
-    int age = 0, hits = 0;
-    int ld = -1;
-    if (t < T) {
-      ld = last_det[t];
-      hits = shits[t];
-      if (ld >= 0) {  // matched or created this frame: age = 0 (tracker.py:85)
-        keep = true;
-      } else {
-        age = age_c[t] + 1;
-        keep = !(age > p.max_age || hits < p.min_hits);
-      }
-    }
-    const unsigned bal = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_cnt[warp] = __popc(bal);
-    __syncthreads();
-    int off = s_base;
-    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
-    if (keep) {
-      const int dst = off + __popc(bal & ((1u << lane) - 1u));
-      // tracks appended this frame sit at t >= T0 in creation order: provisional id = -(ordinal + 1)
-      const long long idv = t < T0 ? id_c[t]
-                                   : (p.has_id_base ? p.id_base[bi] + (t - T0) : -(long long)(t - T0 + 1));
-      double cf;
-      if (ld < 0) cf = conf_c[t];
-      else if (p.f_box) cf = (double)p.f_conf[db + ld];
-      else cf = p.d_conf[db + ld];
-      const double4 b = reinterpret_cast<const double4*>(sbox)[t];
-      id_n[dst] = idv;
-      cls_n[dst] = scls[t];
-      conf_n[dst] = cf;
-      reinterpret_cast<double4*>(box_n)[dst] = b;
-      age_n[dst] = age;
-      hits_n[dst] = hits;
-      if (p.o_id) {
-        p.o_id[ob + dst] = idv;
-        p.o_cls[ob + dst] = scls[t];
-        p.o_conf[ob + dst] = cf;
-        reinterpret_cast<double4*>(p.o_box)[ob + dst] = b;
-        p.o_age[ob + dst] = age;
-        p.o_hits[ob + dst] = hits;
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int tot = 0;
-      for (int w = 0; w < kTrkThreads / 32; ++w) tot += warp_cnt[w];
-      s_base += tot;
-    }
-    __syncthreads();
-  }
-  if (tid == 0) {
-    S.count[slot] = s_base;
-    S.cur[slot] = nxt;
-    S.new_count[bi] = s_new;
-    if (p.o_count) p.o_count[bi] = s_base;
-    if (p.o_new) p.o_new[bi] = s_new;
-  }
-
-  // ---- shared id counter: last CTA converts provisional ordinals to ids in batch order ----
-  PHASE_STAMP(p.dbg, 4);
-  if (p.has_id_base) return;
-  __threadfence();
-  __syncthreads();
-  PHASE_STAMP(p.dbg, 5);
-  if (tid == 0) {
-    const unsigned tk = atomicAdd(S.ticket, 1u);
-    s_is_last = (tk == (unsigned)p.batch - 1u);
-  }
-  __syncthreads();
-  PHASE_STAMP(p.dbg, 6);
-  if (!s_is_last) return;
-  __threadfence();
-  // every stream's new-track count, buffer index and length are fetched in parallel (one thread
-  // per stream), prefix-summed in batch order, then only streams that created tracks are patched
-  __shared__ int f_new[B200VA_MAX_BATCH], f_cur[B200VA_MAX_BATCH], f_cnt[B200VA_MAX_BATCH], f_pre[B200VA_MAX_BATCH];
-  __shared__ long long f_next;
-  if (tid < p.batch) {
-    const int sl = p.slots[tid];
-    f_new[tid] = ((volatile int32_t*)S.new_count)[tid];
-    f_cur[tid] = ((volatile int32_t*)S.cur)[sl];
-    f_cnt[tid] = ((volatile int32_t*)S.count)[sl];
-  }
-  if (tid == kTrkThreads - 1) f_next = *((volatile long long*)S.next_id);
-  __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    for (int i = 0; i < p.batch; ++i) {
-      f_pre[i] = acc;
-      acc += f_new[i];
-    }
-    *S.next_id = f_next + acc;
-    *S.ticket = 0u;
-  }
-  __syncthreads();
-  const long long next = f_next;
-  // a warp per stream: new tracks sit at the tail of the table (creation order)
-  for (int i = warp; i < p.batch; i += kTrkThreads / 32) {
-    const int nnew = f_new[i];
-    if (nnew == 0) continue;
-    const int sl = p.slots[i];
-    long long* ids = S.id[f_cur[i]] + (size_t)sl * p.max_tracks;
-    const int cnt = f_cnt[i];
-    for (int t = lane; t < cnt; t += 32) {
-      const long long v = ((volatile long long*)ids)[t];
-      if (v < 0) {
-        const long long real = next + f_pre[i] + (-v - 1);
-        ids[t] = real;
-        if (p.o_id) p.o_id[(size_t)i * p.max_tracks + t] = real;
-      }
-    }
-  }
+  griddep_wait();  // launched as a programmatic dependent of the NMS kernel: everything above overlapped its tail
+  tracker_stream(p, blockIdx.x, smem_raw);
 }
 
 __global__ void k_tracker_reset(TrackerState S, int slot) {
@@ -612,7 +72,7 @@ int tracker_state_create(b200va_ctx* h) {
   S->new_count = (int32_t*)(b + o_new);
   const long long one = 1;  // itertools.count(1), tracker.py:47
   CUDA_TRY(h, cudaMemcpy(S->next_id, &one, 8, cudaMemcpyHostToDevice));
-  const size_t smem = (size_t)h->cfg.max_tracks * 46 + kDetChunk * 4 + 16;
+  const size_t smem = tracker_smem_bytes(h->cfg.max_tracks);
   if (smem > 190 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_tracks %d too large (<= 4096)", h->cfg.max_tracks);
   CUDA_TRY(h, cudaFuncSetAttribute(k_tracker, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   return B200VA_OK;
@@ -625,12 +85,11 @@ void tracker_state_destroy(b200va_ctx* h) {
   h->tracker = nullptr;
 }
 
-static int tracker_launch(b200va_ctx* h, TrkParams& p, const int* stream_slots, int batch, const double* det_scale,
-                          const uint8_t* skip, const b200va_tracker_cfg* cfg, const int64_t* id_base,
-                          const b200va_tracks* out, int32_t* new_counts, cudaStream_t st) {
+int tracker_fill_params(b200va_ctx* h, TrkParams& p, const int* stream_slots, int batch, const double* det_scale,
+                        const uint8_t* skip, const b200va_tracker_cfg* cfg, const int64_t* id_base,
+                        const b200va_tracks* out, int32_t* new_counts) {
   REQUIRE(h, stream_slots && cfg, "NULL argument");
   REQUIRE(h, batch >= 0 && batch <= h->cfg.max_batch && batch <= B200VA_MAX_BATCH, "batch %d outside [0, %d]", batch, h->cfg.max_batch);
-  if (batch == 0) return B200VA_OK;
   uint8_t seen[4096 / 8] = {0};
   for (int i = 0; i < batch; ++i) {
     const int s = stream_slots[i];
@@ -665,9 +124,18 @@ static int tracker_launch(b200va_ctx* h, TrkParams& p, const int* stream_slots, 
   p.o_new = new_counts;
   p.flags = h->status_flags;
   p.dbg = h->dbg;
+  return B200VA_OK;
+}
+
+static int tracker_launch(b200va_ctx* h, TrkParams& p, const int* stream_slots, int batch, const double* det_scale,
+                          const uint8_t* skip, const b200va_tracker_cfg* cfg, const int64_t* id_base,
+                          const b200va_tracks* out, int32_t* new_counts, cudaStream_t st) {
+  const int rc = tracker_fill_params(h, p, stream_slots, batch, det_scale, skip, cfg, id_base, out, new_counts);
+  if (rc != B200VA_OK || batch == 0) return rc;
+  PhaseScope phase(h, B200VA_PHASE_TRACKER, st);
   // dense scenes (the post-process saw more than 256 candidates in a frame lately) are worth a CTA that owns its SM
   const int width = h->nms_dense_ttl > 0 ? kTrkThreadsMax : kTrkThreadsWide;
-  k_tracker<<<batch, width, (size_t)h->cfg.max_tracks * 46 + kDetChunk * 4 + 16, st>>>(p);
+  CUDA_TRY(h, launch_pdl(k_tracker, dim3(batch), dim3(width), tracker_smem_bytes(h->cfg.max_tracks), st, h->tune.pdl != 0, p));
   LAUNCH_CHECK(h);
   return B200VA_OK;
 }

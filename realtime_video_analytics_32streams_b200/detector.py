@@ -45,6 +45,18 @@ class B200Detector:
         self._stager = FrameStager(self.h)
         # fold_filter=True applies filter_detections (pipeline.py:182) inside the kernel
         self.fold_filter = fold_filter
+        self._bufs = {}  # batch size -> (device detection SoA, pinned host mirror, numpy views, pinned status words)
+
+    def _result_buffers(self, batch: int):
+        """Persistent result tables per batch size: the post-process writes the device SoA, ONE copy of its flat
+        buffer (plus the capacity flags) brings a call's detections back."""
+        b = self._bufs.get(batch)
+        if b is None:
+            t = self.h.torch
+            dev, host = self.h.alloc_dets(batch), self.h.alloc_dets(batch, pinned_host=True)
+            b = self._bufs[batch] = (dev, host, {k: v.numpy() for k, v in host.items() if not k.startswith("_")},
+                                     t.zeros(self.h.STATUS_WORDS, dtype=t.int32).pin_memory())
+        return b
 
     # ---- the three reference steps ---------------------------------------------------------
     @property
@@ -52,13 +64,15 @@ class B200Detector:
         return _native.OUT_F16_RGB_NCHW if getattr(self.config, "half", False) else _native.OUT_F32_RGB_NCHW
 
     def _preprocess(self, frame, roi_mask=None):
-        """detector.py:198-264.  Returns (CUDA tensor [1,3,H,W], meta dict)."""
-        dev = self._stager.upload([frame])
+        """detector.py:198-264.  Returns (CUDA tensor [1,3,H,W], meta dict).  A host frame is staged into a
+        device buffer only this detector reads, so just the rows the letterbox taps cross PCIe (one in three
+        for 1080p -> 640x360)."""
+        dev = self._stager.upload([frame], sparse_for=self.input_hw)
         tensor, metas = self.h.preprocess(dev, self.input_hw, self._fmt, [roi_mask] if roi_mask is not None else None)
         return tensor, metas[0].as_meta()
 
     def _preprocess_batch(self, frames, roi_masks=None):
-        dev = self._stager.upload(frames)
+        dev = self._stager.upload(frames, sparse_for=self.input_hw)
         return self.h.preprocess(dev, self.input_hw, self._fmt, roi_masks)
 
     def _infer(self, tensor):
@@ -100,7 +114,7 @@ class B200Detector:
         # honour a caller-edited meta (scale / pad) exactly like _scale_boxes would
         lb.scale = float(meta["scale"])
         lb.pad_left, lb.pad_top = int(meta["pad"][0]), int(meta["pad"][1])
-        dets = self._run_post(head, [lb])
+        dets = self._run_post(head, [lb], self._result_buffers(1)[0])
         return self._to_detections(dets, [packet])[0]
 
     # ---- public API ------------------------------------------------------------------------
@@ -112,7 +126,7 @@ class B200Detector:
     def predict_batch(self, packets: Sequence[FramePacket], roi_masks=None) -> List[List[Detection]]:
         if not packets:
             return []
-        dets, _ = self.predict_batch_device([p.frame for p in packets], roi_masks)
+        dets, _ = self.predict_batch_device([p.frame for p in packets], roi_masks, self._result_buffers(len(packets))[0])
         return self._to_detections(dets, packets)
 
     def predict_batch_device(self, frames, roi_masks=None, dets_out=None):
@@ -130,20 +144,33 @@ class B200Detector:
                                   filter_conf=thr if self.fold_filter else None, out=dets_out)
 
     def _to_detections(self, dets, packets) -> List[List[Detection]]:
-        counts = dets["count"].cpu().numpy()  # synchronises the current stream
-        kmax = int(counts.max()) if len(counts) else 0
-        if kmax == 0:
-            return [[] for _ in packets]
-        box = dets["bbox_xyxy"][:, :kmax].cpu().numpy()
-        conf = dets["conf"][:, :kmax].cpu().numpy()
-        cls = dets["cls"][:, :kmax].cpu().numpy()
+        """Device SoA -> ``Detection`` objects: one pinned device->host copy of the flat table (and the capacity
+        flags), one synchronisation."""
+        h, t = self.h, self.h.torch
+        nb = len(packets)
+        dev, host, views, status = self._result_buffers(nb)
+        if dets is not dev:  # a caller-owned SoA: bring it into the persistent table first (device-side copy)
+            dev["_flat"].copy_(dets["_flat"]) if "_flat" in dets and dets["_flat"].numel() == dev["_flat"].numel() else [
+                dev[k][:nb].copy_(dets[k][:nb]) for k in ("bbox_xyxy", "conf", "cls", "count")]
+        host["_flat"].copy_(dev["_flat"], non_blocking=True)
+        h.read_status_async(status)
+        t.cuda.current_stream(h.device).synchronize()
+        msg = h.status_message(status.tolist())
+        if msg:
+            raise _native.B200VAError(_native.ERR_CAPACITY, msg)
+        counts = views["count"].tolist()
         out = []
         for b, packet in enumerate(packets):
             n = int(counts[b])
+            if n == 0:
+                out.append([])
+                continue
             name = getattr(packet.stream, "name", str(packet.stream))
-            out.append([Detection(name, packet.frame_id, int(cls[b, i]), float(conf[b, i]),
-                                  (float(box[b, i, 0]), float(box[b, i, 1]), float(box[b, i, 2]), float(box[b, i, 3])))
-                        for i in range(n)])
+            fid = packet.frame_id
+            # float32 -> Python float exactly as `float(np.float32)` in detector.py:330-336
+            out.append([Detection(name, fid, c, f, tuple(bx)) for c, f, bx in
+                        zip(views["cls"][b, :n].tolist(), views["conf"][b, :n].astype(np.float64).tolist(),
+                            views["bbox_xyxy"][b, :n].astype(np.float64).tolist())])
         return out
 
 
@@ -176,7 +203,7 @@ class B200UltralyticsDetector(B200Detector):
         return geoms, next(iter(outs))
 
     def _preprocess(self, frame, roi_mask=None):
-        dev = self._stager.upload([frame])
+        dev = self._stager.upload([frame])  # every row: the sparse upload pattern is the reference letterbox's
         geoms, in_hw = self._geometry([dev[0].shape[:2]])
         tensor = self.h.preprocess_geom(dev, geoms, in_hw, self._fmt, [roi_mask] if roi_mask is not None else None)
         return tensor, {"orig_shape": tuple(int(v) for v in dev[0].shape[:2]), "in_shape": in_hw}
@@ -185,7 +212,7 @@ class B200UltralyticsDetector(B200Detector):
         head = self._as_head(predictions)
         if head.dim() == 2:
             head = head[None]
-        dets = self._run_post_ultra(head, [meta["orig_shape"]], meta["in_shape"])
+        dets = self._run_post_ultra(head, [meta["orig_shape"]], meta["in_shape"], self._result_buffers(1)[0])
         return self._to_detections(dets, [packet])[0]
 
     def predict_batch_device(self, frames, roi_masks=None, dets_out=None):

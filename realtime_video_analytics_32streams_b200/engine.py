@@ -18,6 +18,7 @@ PCIe upload of the next frames with the host-side handling of the current result
 
 from __future__ import annotations
 
+import logging
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence
 
@@ -29,6 +30,8 @@ from .frame_filter import MotionFilter, roi_mask
 from .runtime import FrameStager, get_handle
 from .tracker import B200IouTracker
 from .types import Detection, MotionFilterConfig, Track
+
+LOGGER = logging.getLogger(__name__)
 
 
 @dataclass
@@ -69,27 +72,40 @@ class _StreamState:
 class FrameResult:
     """What one stream produced in one tick.  ``n_detections`` / ``n_tracks`` and the ``*_arrays``
     are plain host data; ``detections`` / ``tracks`` build the reference's ``Detection`` / ``Track``
-    objects on first access (the sinks that want objects pay for them, nobody else does)."""
+    objects on first access (the sinks that want objects pay for them, nobody else does).
+
+    Lifetime: the arrays are views into the pinned result buffers of the tick that produced them, and those
+    buffers are reused ``depth`` submits later.  Read (or ``.copy()``) them before then; an access after the
+    buffers were handed to a newer tick raises instead of returning the newer tick's rows.  ``device_ms`` is the
+    GPU time of the tick's phases (``Handle.phase_times``) when the engine was built with ``profile=True`` -- the
+    ``dt`` the reference feeds to ``health.update_success`` (pipeline.py:145, 200-201)."""
 
     __slots__ = ("stream_name", "frame_id", "processed", "skip_reason", "n_detections", "n_tracks", "_ctx", "_pos",
-                 "_dets", "_tracks")
+                 "_dets", "_tracks", "_gen", "device_ms")
 
-    def __init__(self, stream_name, frame_id, processed, skip_reason, n_det, n_trk, ctx, pos):
+    def __init__(self, stream_name, frame_id, processed, skip_reason, n_det, n_trk, ctx, pos, device_ms=None):
         self.stream_name, self.frame_id, self.processed, self.skip_reason = stream_name, frame_id, processed, skip_reason
         self.n_detections, self.n_tracks = n_det, n_trk
-        self._ctx, self._pos = ctx, pos
+        self._ctx, self._pos, self._gen = ctx, pos, ctx.gen
         self._dets = self._tracks = None
+        self.device_ms = device_ms
+
+    def _live_ctx(self):
+        if self._ctx.gen != self._gen:
+            raise RuntimeError("FrameResult read after its result buffers were reused by a later tick: read or copy the "
+                               "arrays before submitting `depth` more ticks")
+        return self._ctx
 
     @property
     def track_arrays(self) -> Dict[str, np.ndarray]:
         """Host views: track_id, cls, conf, bbox_xyxy, age, hits -- rows [0, n_tracks)."""
-        h, n, p = self._ctx.host_tracks, self.n_tracks, self._pos
+        h, n, p = self._live_ctx().host_tracks, self.n_tracks, self._pos
         return {k: h[k][p, :n] for k in ("track_id", "cls", "conf", "bbox_xyxy", "age", "hits")}
 
     @property
     def detection_arrays(self) -> Dict[str, np.ndarray]:
         """Host views: cls, conf (float64), bbox_xyxy (float64, rescaled like pipeline.py:224-240)."""
-        h, n, p = self._ctx.host_dets, self.n_detections, self._pos
+        h, n, p = self._live_ctx().host_dets, self.n_detections, self._pos
         box = h["bbox_xyxy"][p, :n].astype(np.float64)
         sc = self._ctx.scale[p]
         if sc != 1.0:
@@ -129,8 +145,12 @@ class _TickCtx:
         self.host_tracks_t = h.alloc_tracks(n, pinned_host=True)
         self.host_dets = {k: v.numpy() for k, v in self.host_dets_t.items() if not k.startswith("_")}
         self.host_tracks = {k: v.numpy() for k, v in self.host_tracks_t.items() if not k.startswith("_")}
+        self.status = t.zeros(h.STATUS_WORDS, dtype=t.int32).pin_memory()  # capacity flags, copied back with the tables
         self.done = t.cuda.Event()
         self.busy = False
+        self.gen = 0       # bumped by every submit that takes these buffers (FrameResult lifetime check)
+        self.keep = None   # upload sources of this tick: alive until it is collected (raw async copies read them)
+        self.phase_ms = None
         # filled by submit()
         self.order: List[int] = []
         self.n_act = 0
@@ -146,8 +166,17 @@ class HotPathEngine:
     """pre + post + track for a set of streams, one tick at a time."""
 
     def __init__(self, streams: Sequence, detector_config, tracker_config, infer: Callable,
-                 handle: Optional[_native.Handle] = None, input_hw=None, depth: int = 2, static_pads: bool = True):
+                 handle: Optional[_native.Handle] = None, input_hw=None, depth: int = 2, static_pads: bool = True,
+                 on_overflow: str = "raise", profile: bool = False):
+        """``on_overflow``: what ``collect`` does when a frame exceeded ``max_candidates`` / ``max_dets`` /
+        ``max_tracks`` (rows were dropped; the reference has no such limits): "raise" (default) or "warn".
+        ``profile``: record per-phase device times (``FrameResult.device_ms``); costs one event pair per phase."""
+        if on_overflow not in ("raise", "warn"):
+            raise ValueError("on_overflow must be 'raise' or 'warn'")
+        self.on_overflow, self.profile = on_overflow, bool(profile)
         self.h = handle if handle is not None else get_handle()
+        if self.profile:
+            self.h.set_profiling(True)
         self.streams = list(streams)
         self.detector = B200Detector(detector_config, input_hw=input_hw, infer=infer, handle=self.h, fold_filter=True)
         self.tracker = B200IouTracker(tracker_config, handle=self.h)
@@ -156,8 +185,11 @@ class HotPathEngine:
         n = max(len(self.streams), 1)
         self._ctxs = [_TickCtx(self.h, n) for _ in range(max(depth, 1))]
         self._turn = 0
+        self.active_streams: List[int] = []
         self._changed = self.h.torch.empty((n,), dtype=self.h.torch.int32, device=self.h.device)
         self._batches: Dict[tuple, _native.FrameBatch] = {}
+        self._persistent = set()  # ids of the engine's own persistent device tensors (downsample outputs)
+        self._small: Dict[tuple, object] = {}
         self._net = None
         self._net_shapes = []
         # the network-input buffer is persistent: pad rows are written once per geometry (B200VA_OUT_FLAG_PADS_VALID).
@@ -170,6 +202,10 @@ class HotPathEngine:
     # --------------------------------------------------------------------------------------
     def _frame_batch(self, frames, masks):
         """Argument arrays are cached per set of device pointers (staging buffers are persistent)."""
+        if not all(self.stager.owns(f) or id(f) in self._persistent for f in frames):
+            # caller-supplied CUDA frames: their addresses change from tick to tick, and a cached batch would
+            # keep the tensors (and their HBM) alive -- build the argument arrays for this tick only
+            return _native.FrameBatch(frames, masks)
         key = tuple((f.data_ptr(), f.shape[0], f.shape[1], f.stride(0), m.data_ptr() if m is not None else 0)
                     for f, m in zip(frames, masks))
         fb = self._batches.get(key)
@@ -221,6 +257,8 @@ class HotPathEngine:
             sparse_ok[i] = (not getattr(st.cfg, "motion_filter", False)
                             and float(getattr(st.cfg, "downsample_ratio", 1.0)) >= 0.999)
         staged = self.stager.upload(list(frames), sparse_for=self.detector.input_hw, sparse_ok=sparse_ok)
+        ctx.keep = self.stager.take_sources()
+        ctx.gen += 1
         dev_frames = [staged[i] for i in live]
         for st in states:
             st.frame_index += 1
@@ -237,7 +275,15 @@ class HotPathEngine:
         work_masks = list(masks)
         if down:
             sizes = [(int(dev_frames[k].shape[0] * ratios[k]), int(dev_frames[k].shape[1] * ratios[k])) for k in down]
-            small = self.h.resize([dev_frames[k] for k in down], sizes, [masks[k] for k in down])
+            outs = []
+            for k, sz in zip(down, sizes):  # one persistent output per (stream, size): stable addresses, no per-tick allocation
+                key = (live[k], sz)
+                buf = self._small.get(key)
+                if buf is None:
+                    buf = self._small[key] = self.h.torch.empty((sz[0], sz[1], 3), dtype=self.h.torch.uint8, device=self.h.device)
+                    self._persistent.add(id(buf))
+                outs.append(buf)
+            small = self.h.resize([dev_frames[k] for k in down], sizes, [masks[k] for k in down], outs=outs)
             for k, s in zip(down, small):
                 work[k] = s
                 work_masks[k] = None  # the ROI is already baked into the downsampled frame
@@ -280,6 +326,9 @@ class HotPathEngine:
             tensor, metas = self.h.preprocess(self._frame_batch(act_frames, [work_masks[k] for k in active]),
                                               self.detector.input_hw, self.detector._fmt | self._pads_flag(act_frames),
                                               out=net)
+            # which stream each row of `tensor` belongs to (index into self.streams), for callers whose forward
+            # is per-stream (model selection, synthetic heads in tests)
+            self.active_streams = [live[k] for k in active]
             head = self.detector._infer(tensor) if infer_ctx is None else self.detector._infer_fn(tensor, infer_ctx)
             head = self.detector._as_head(head)
             if head.dim() != 3 or head.shape[0] != n_act:
@@ -293,6 +342,7 @@ class HotPathEngine:
         # 9. one device -> host copy per result table, into pinned memory
         ctx.host_dets_t["_flat"].copy_(ctx.dets["_flat"], non_blocking=True)
         ctx.host_tracks_t["_flat"].copy_(ctx.tracks["_flat"], non_blocking=True)
+        self.h.read_status_async(ctx.status)
         ctx.done.record()
         ctx.busy = True
         ctx.order, ctx.n_act, ctx.names, ctx.ids, ctx.states = order, n_act, names, ids, states
@@ -304,6 +354,13 @@ class HotPathEngine:
         one FrameResult per live stream, in stream order."""
         ctx.done.synchronize()
         ctx.busy = False
+        ctx.keep = None
+        msg = self.h.status_message(ctx.status.tolist())
+        if msg:
+            if self.on_overflow == "raise":
+                raise _native.B200VAError(_native.ERR_CAPACITY, msg)
+            LOGGER.warning("HotPathEngine: %s", msg)
+        phase_ms = self.h.phase_times() if self.profile else None
         det_counts = ctx.host_dets["count"]
         trk_counts = ctx.host_tracks["count"]
         results: List[Optional[FrameResult]] = [None] * len(ctx.order)
@@ -312,5 +369,5 @@ class HotPathEngine:
             n_det = int(det_counts[pos]) if processed else 0
             n_trk = int(trk_counts[pos])
             ctx.states[k].adjust(n_det, n_trk)
-            results[k] = FrameResult(ctx.names[k], ctx.ids[k], processed, ctx.skip_reason[k], n_det, n_trk, ctx, pos)
+            results[k] = FrameResult(ctx.names[k], ctx.ids[k], processed, ctx.skip_reason[k], n_det, n_trk, ctx, pos, phase_ms)
         return results  # type: ignore[return-value]

@@ -84,8 +84,19 @@ class FrameStager:
     def __init__(self, handle: "_native.Handle"):
         self.h = handle
         self._dev: Dict[tuple, object] = {}
+        self._ids = set()
         self._keep: List = []
         self.bytes_moved = 0
+
+    def owns(self, tensor) -> bool:
+        """True for this stager's persistent device buffers (their addresses never change)."""
+        return id(tensor) in self._ids
+
+    def take_sources(self) -> List:
+        """Hand the host sources of the last ``upload`` to the caller, who keeps them alive until the copies have
+        run (the raw ``cudaMemcpy2DAsync`` calls are invisible to torch's caching host allocator)."""
+        keep, self._keep = self._keep, []
+        return keep
 
     def device_buffer(self, k: int, shape):
         t = self.h.torch
@@ -93,6 +104,7 @@ class FrameStager:
         buf = self._dev.get(key)
         if buf is None:
             buf = self._dev[key] = t.zeros(tuple(shape), dtype=t.uint8, device=self.h.device)
+            self._ids.add(id(buf))
         return buf
 
     def upload(self, frames: Sequence, sparse_for=None, sparse_ok: Optional[Sequence[bool]] = None) -> List:

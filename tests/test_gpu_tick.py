@@ -55,11 +55,16 @@ def _check(h, want, net, tracks, t):
         assert rows == trk[s], (t, s)
 
 
-@pytest.mark.parametrize("schedule", [0, 1, 2])
-def test_tick_matches_oracle(schedule):
+@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("schedule", [0, 1, 2, 3])
+def test_tick_matches_oracle(schedule, fused, monkeypatch):
+    """fused=1: NMS + tracker as one kernel (k_post_track, the default for sparse scenes); fused=0: two kernels
+    chained by programmatic dependent launch.  Schedule 3 also launches the letterbox as a programmatic dependent
+    of the decode kernel."""
     import torch
     from realtime_video_analytics_32streams_b200 import _native as N
 
+    monkeypatch.setenv("B200VA_FUSE_POST_TRACK", str(fused))
     n_ticks = 3
     frames, heads = _inputs(n_ticks)
     want = _oracle(frames, heads)
@@ -84,10 +89,13 @@ def test_tick_matches_oracle(schedule):
     h.close()
 
 
-def test_tick_graph_replay_matches_oracle():
+@pytest.mark.parametrize("pdl", [1, 0])
+@pytest.mark.parametrize("schedule", [1, 3])
+def test_tick_graph_replay_matches_oracle(schedule, pdl, monkeypatch):
     import torch
     from realtime_video_analytics_32streams_b200 import _native as N
 
+    monkeypatch.setenv("B200VA_PDL", str(pdl))
     n_ticks = 3
     frames, heads = _inputs(n_ticks)
     want = _oracle(frames, heads)
@@ -97,7 +105,7 @@ def test_tick_graph_replay_matches_oracle():
     dev = [torch.empty((*HW, 3), dtype=torch.uint8, device="cuda") for _ in range(B)]
     head = torch.empty((B, 84, 8400), dtype=torch.float32, device="cuda")
     plan = h.plan_tick(frames=dev, net_out=net, dst_hw=IN_HW, head=head, metas=metas, conf_thr=CONF, iou_thr=IOU,
-                       filter_conf=CONF, slots=list(range(B)), tracker_cfg=TRK, schedule=1)
+                       filter_conf=CONF, slots=list(range(B)), tracker_cfg=TRK, schedule=schedule)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     graph = torch.cuda.CUDAGraph()
@@ -113,6 +121,7 @@ def test_tick_graph_replay_matches_oracle():
         for s in range(B):
             dev[s].copy_(torch.from_numpy(frames[t][s]))
         head.copy_(torch.from_numpy(heads[t]))
+        net.zero_()
         graph.replay()
         torch.cuda.synchronize()
         _check(h, want, net, plan.tracks, t)
