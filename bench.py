@@ -532,7 +532,8 @@ def run_gpu(args) -> None:
                 "schedule": {0: "serial", 1: "letterbox after decode, overlapping NMS + tracker (b200va_tick)",
                              2: "letterbox overlapping decode + NMS + tracker (b200va_tick)",
                              3: "letterbox launched beside the decode kernel (programmatic dependent launch), NMS + tracker "
-                                "on the second stream (b200va_tick)"}[args.schedule],
+                                "on the second stream (b200va_tick)",
+                             4: "software-pipelined b200va_tick: decode + letterbox of step k beside NMS + tracker of step k-1"}[args.schedule],
                 "launch": ("CUDA graph replay of the prepared b200va_tick (one graph per input set); every "
                            f"{SAMPLE_EVERY}th step is launched eagerly with an event pair around the letterbox kernel"
                            if graphs is not None else "eager b200va_tick every step, event pair around the letterbox kernel"),
@@ -558,7 +559,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--schedule", type=int, default=1, choices=[0, 1, 2, 3],
+    ap.add_argument("--schedule", type=int, default=1, choices=[0, 1, 2, 3, 4],
                     help="b200va_tick schedule: 0 serial, 1 letterbox after decode (default), 2 fully parallel")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-bind", action="store_true", help="N > 1: do not pin each rank to its GPU's NUMA-local cores")

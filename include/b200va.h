@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200VA_VERSION 100 /* 0.1.0 */
+#define B200VA_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define B200VA_API __attribute__((visibility("default")))
@@ -134,6 +134,10 @@ typedef struct b200va_tracks {
   int32_t* age;      /* [B, max_tracks] */
   int32_t* hits;     /* [B, max_tracks] */
   int32_t* count;    /* [B] */
+  int32_t rows;      /* rows per stream of the arrays above; 0 = max_tracks.  A caller that copies the tables to the host
+                      * every tick allocates fewer rows than the state can hold: `count` always reports the true number
+                      * of tracks, rows beyond `rows` are not written and status word [3] is raised.  (New in 0.2.0:
+                      * zero-initialise the struct.) */
 } b200va_tracks;
 
 /* ---- library ------------------------------------------------------------------------ */
@@ -152,7 +156,7 @@ B200VA_API int b200va_poll_status(b200va_handle h, void* stream);
 
 /* Asynchronous form for callers that already copy results back every tick: enqueues a copy of the status words
  * (B200VA_STATUS_WORDS int32: [0] candidates > max_candidates, [1] detections > max_dets, [2] tracks > max_tracks,
- * rest reserved) into host_out (HOST, pinned memory for a truly asynchronous copy) and, when clear != 0, resets them
+ * [3] tracks > b200va_tracks.rows (state intact, output truncated), rest reserved) into host_out (HOST, pinned memory for a truly asynchronous copy) and, when clear != 0, resets them
  * on the device afterwards, all on `stream`; nothing synchronises.  The words are valid once the caller has
  * synchronised `stream` (e.g. with the event that guards its result tables). */
 #define B200VA_STATUS_WORDS 8
@@ -366,6 +370,12 @@ B200VA_API int b200va_postprocess_ultralytics(b200va_handle h, const float* head
  *           beside the decode's as soon as all of those are running (HBM sees the decode's reads and the letterbox's
  *           writes together, no kernel-to-kernel gap) -- while NMS + tracker run on the internal stream behind
  *           an event recorded after the decode.
+ *           4 = software-pipelined: this call only DECODES its head (into one of two candidate sets) and letterboxes
+ *           its frames; NMS + tracker of the head the PREVIOUS call decoded run beside them on the internal stream.
+ *           The latency-bound chain decode -> NMS -> tracker, which bounds schedules 1-3, leaves the critical path.
+ *           The result tables of call k are complete after call k + 1 has run (or after a final call with neither
+ *           frames nor head, which only drains the pipeline); `dets`, `tracks`, `new_counts` and the buffers they
+ *           point to must stay valid and untouched until then.  A call with another schedule first runs what is owed.
  * Sparse scenes run NMS and the tracker update of the same rows as ONE kernel (a 256-thread CTA per stream);
  * otherwise the two kernels are chained by programmatic dependent launch.
  * ev_pre_begin / ev_pre_end: optional cudaEvent_t recorded on `stream` around the letterbox launch. */

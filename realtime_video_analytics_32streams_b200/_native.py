@@ -57,7 +57,7 @@ class TrackerCfg(C.Structure):
 
 class Tracks(C.Structure):
     _fields_ = [("track_id", C.c_void_p), ("cls", C.c_void_p), ("conf", C.c_void_p), ("bbox_xyxy", C.c_void_p),
-                ("age", C.c_void_p), ("hits", C.c_void_p), ("count", C.c_void_p)]
+                ("age", C.c_void_p), ("hits", C.c_void_p), ("count", C.c_void_p), ("rows", C.c_int32)]
 
 
 class TickArgs(C.Structure):
@@ -80,6 +80,7 @@ class TickArgs(C.Structure):
 
 
 SCHEDULE_SERIAL, SCHEDULE_PRE_AFTER_DECODE, SCHEDULE_PRE_PARALLEL, SCHEDULE_PRE_BESIDE_DECODE = 0, 1, 2, 3
+SCHEDULE_SOFTWARE_PIPELINED = 4  # decode + letterbox of this call beside NMS + tracker of the previous call's head
 
 
 class TickPlan:
@@ -278,7 +279,8 @@ class Handle:
         self._check(self.lib.b200va_poll_status(self._h, self._stream()))
 
     STATUS_WORDS = 8
-    _STATUS_NAMES = ("candidates > max_candidates", "detections > max_dets", "tracks > max_tracks")
+    _STATUS_NAMES = ("candidates > max_candidates", "detections > max_dets", "tracks > max_tracks",
+                     "tracks > rows of the result table")
 
     def read_status_async(self, host_out, clear: bool = True) -> None:
         """Enqueue a copy of the capacity flags into ``host_out`` (pinned CPU int32 tensor of ``STATUS_WORDS``
@@ -289,7 +291,7 @@ class Handle:
     @classmethod
     def status_message(cls, words) -> Optional[str]:
         """None when no capacity was exceeded, else what was truncated."""
-        hit = [n for n, w in zip(cls._STATUS_NAMES, list(words)[:3]) if int(w)]
+        hit = [n for n, w in zip(cls._STATUS_NAMES, list(words)[:4]) if int(w)]
         return ("capacity exceeded (rows were dropped; the reference is unbounded -- raise the handle's limits): "
                 + ", ".join(hit)) if hit else None
 
@@ -569,8 +571,17 @@ class Handle:
         return out
 
     # -- a8 ---------------------------------------------------------------------------------
-    def alloc_tracks(self, batch: int, pinned_host: bool = False):
-        return self._alloc_soa(self._TRK_FIELDS, batch, self.cfg.max_tracks, ("count", "new_count"), pinned_host)
+    def alloc_tracks(self, batch: int, pinned_host: bool = False, rows: Optional[int] = None):
+        """Track result tables.  ``rows`` (default ``max_tracks``) is how many rows per stream the caller wants back:
+        the state always holds up to ``max_tracks``; ``count`` reports the true number and a capacity flag is raised
+        when it exceeds ``rows``."""
+        rows = self.cfg.max_tracks if rows is None else max(1, min(int(rows), self.cfg.max_tracks))
+        return self._alloc_soa(self._TRK_FIELDS, batch, rows, ("count", "new_count"), pinned_host)
+
+    @staticmethod
+    def _tracks_struct(out) -> Tracks:
+        return Tracks(out["track_id"].data_ptr(), out["cls"].data_ptr(), out["conf"].data_ptr(), out["bbox_xyxy"].data_ptr(),
+                      out["age"].data_ptr(), out["hits"].data_ptr(), out["count"].data_ptr(), int(out["track_id"].shape[1]))
 
     def tracker_update(self, slots, dets, max_age: int, min_hits: int, max_iou_distance: float, det_scale=None,
                        skip=None, id_base=None, out=None, f64: bool = False):
@@ -579,9 +590,7 @@ class Handle:
             out = self.alloc_tracks(b)
         cfg = TrackerCfg(int(max_age), int(min_hits), float(max_iou_distance))
         slot_arr = slots if isinstance(slots, C.Array) else _int_array(slots)
-        ts = Tracks(out["track_id"].data_ptr(), out["cls"].data_ptr(), out["conf"].data_ptr(),
-                    out["bbox_xyxy"].data_ptr(), out["age"].data_ptr(), out["hits"].data_ptr(),
-                    out["count"].data_ptr())
+        ts = self._tracks_struct(out)
         skip_arr = (C.c_uint8 * b)(*[1 if s else 0 for s in skip]) if skip is not None else None
         idb = (C.c_int64 * b)(*[int(v) for v in id_base]) if id_base is not None else None
         max_dets = int(dets["conf"].shape[1])
@@ -654,9 +663,7 @@ class Handle:
                 keep.append(ds)
             cfg = TrackerCfg(int(tracker_cfg[0]), int(tracker_cfg[1]), float(tracker_cfg[2]))
             slot_arr = slots if isinstance(slots, C.Array) else _int_array(slots)
-            ts = Tracks(tracks["track_id"].data_ptr(), tracks["cls"].data_ptr(), tracks["conf"].data_ptr(),
-                        tracks["bbox_xyxy"].data_ptr(), tracks["age"].data_ptr(), tracks["hits"].data_ptr(),
-                        tracks["count"].data_ptr())
+            ts = self._tracks_struct(tracks)
             sc = (C.c_double * b)(*[float(v) for v in det_scale]) if det_scale is not None else None
             skip_arr = (C.c_uint8 * b)(*[1 if s else 0 for s in skip]) if skip is not None else None
             a.stream_slots, a.trk_batch, a.max_dets = slot_arr, b, int(dets["conf"].shape[1])

@@ -7,6 +7,7 @@
 #include "common.cuh"
 
 int postprocess_configure(b200va_ctx* h);  // postprocess.cu
+void postprocess_release(b200va_ctx* h);   // postprocess.cu
 int preprocess_configure(b200va_ctx* h);   // preprocess.cu
 int filters_configure(b200va_ctx* h);      // filters.cu
 
@@ -86,6 +87,7 @@ static int create_impl(b200va_ctx* h) {
   h->tune.decode_ctas_per_sm = env_int("B200VA_DECODE_CTAS_PER_SM");
   if (getenv("B200VA_FUSE_POST_TRACK")) h->tune.fuse_post_track = env_int("B200VA_FUSE_POST_TRACK");
   if (getenv("B200VA_PDL")) h->tune.pdl = env_int("B200VA_PDL");
+  h->tune.uniform_carveout = env_int("B200VA_UNIFORM_CARVEOUT");
   REQUIRE(h, c.max_batch >= 1 && c.max_batch <= B200VA_MAX_BATCH, "max_batch must be in [1, %d]", B200VA_MAX_BATCH);
   REQUIRE(h, c.max_anchors >= 1 && c.max_anchors <= 262144, "max_anchors must be in [1, 262144]");
   REQUIRE(h, c.max_candidates >= 1 && c.max_candidates <= 8192, "max_candidates must be in [1, 8192]");
@@ -102,11 +104,13 @@ static int create_impl(b200va_ctx* h) {
   h->num_sms = prop.multiProcessorCount;
   const size_t frames = c.max_batch < B200VA_LAUNCH_FRAMES ? c.max_batch : B200VA_LAUNCH_FRAMES;
   const size_t n = frames * (size_t)c.max_candidates;
-  CUDA_TRY(h, cudaMalloc(&h->cand_key, n * sizeof(unsigned long long)));
-  CUDA_TRY(h, cudaMalloc(&h->cand_box, n * sizeof(float4)));
-  CUDA_TRY(h, cudaMalloc(&h->cand_cls, n * sizeof(int32_t)));
-  CUDA_TRY(h, cudaMalloc(&h->cand_count, frames * sizeof(int32_t)));
-  CUDA_TRY(h, cudaMemset(h->cand_count, 0, frames * sizeof(int32_t)));
+  h->cand_set_elems = n;
+  h->cand_set_frames = (int)frames;
+  CUDA_TRY(h, cudaMalloc(&h->cand_key, 2 * n * sizeof(unsigned long long)));
+  CUDA_TRY(h, cudaMalloc(&h->cand_box, 2 * n * sizeof(float4)));
+  CUDA_TRY(h, cudaMalloc(&h->cand_cls, 2 * n * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMalloc(&h->cand_count, 2 * frames * sizeof(int32_t)));
+  CUDA_TRY(h, cudaMemset(h->cand_count, 0, 2 * frames * sizeof(int32_t)));
   CUDA_TRY(h, cudaMalloc(&h->status_flags, FLAG_COUNT * sizeof(int32_t)));
   CUDA_TRY(h, cudaMemset(h->status_flags, 0, FLAG_COUNT * sizeof(int32_t)));
   CUDA_TRY(h, cudaMalloc(&h->roi_scratch, ROI_SCRATCH_BYTES));
@@ -164,6 +168,7 @@ extern "C" int b200va_destroy(b200va_handle h) {
   {
     DeviceGuard guard(h->cfg.device);
     cudaDeviceSynchronize();
+    postprocess_release(h);
     tracker_state_destroy(h);
     tap_cache_destroy(h);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -198,12 +203,13 @@ extern "C" int b200va_poll_status(b200va_handle h, void* stream) {
   int32_t flags[FLAG_COUNT];
   CUDA_TRY(h, cudaMemcpyAsync(flags, h->status_flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(h, cudaStreamSynchronize(st));
-  if (flags[FLAG_CAND_OVERFLOW] || flags[FLAG_DET_OVERFLOW] || flags[FLAG_TRACK_OVERFLOW]) {
+  if (flags[FLAG_CAND_OVERFLOW] || flags[FLAG_DET_OVERFLOW] || flags[FLAG_TRACK_OVERFLOW] || flags[FLAG_TRACK_ROWS]) {
     CUDA_TRY(h, cudaMemsetAsync(h->status_flags, 0, sizeof(flags), st));
-    return set_error(h, B200VA_ERR_CAPACITY, "capacity exceeded since the last poll:%s%s%s",
+    return set_error(h, B200VA_ERR_CAPACITY, "capacity exceeded since the last poll:%s%s%s%s",
                      flags[FLAG_CAND_OVERFLOW] ? " candidates>max_candidates" : "",
                      flags[FLAG_DET_OVERFLOW] ? " detections>max_dets" : "",
-                     flags[FLAG_TRACK_OVERFLOW] ? " tracks>max_tracks" : "");
+                     flags[FLAG_TRACK_OVERFLOW] ? " tracks>max_tracks" : "",
+                     flags[FLAG_TRACK_ROWS] ? " tracks>output rows" : "");
   }
   return B200VA_OK;
 }
@@ -225,5 +231,17 @@ extern "C" B200VA_API int b200va_debug_read(b200va_handle h, int64_t* out, int n
   DeviceGuard guard(h->cfg.device);
   CUDA_TRY(h, cudaDeviceSynchronize());
   CUDA_TRY(h, cudaMemcpy(out, h->dbg, sizeof(long long) * n, cudaMemcpyDeviceToHost));
+  return B200VA_OK;
+}
+
+// Developer aid: arm the timeline slots (min-start slots to +inf, max-end slots to 0) before a measured tick.
+extern "C" B200VA_API int b200va_debug_reset(b200va_handle h) {
+  if (!h) return B200VA_ERR_INVALID;
+  DeviceGuard guard(h->cfg.device);
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  long long host[DBG_SLOTS];
+  memset(host, 0, sizeof(host));
+  for (int s = 40; s < 48; s += 2) host[s] = -1ll;  // all ones = UINT64_MAX for atomicMin
+  CUDA_TRY(h, cudaMemcpy(h->dbg, host, sizeof(host), cudaMemcpyHostToDevice));
   return B200VA_OK;
 }

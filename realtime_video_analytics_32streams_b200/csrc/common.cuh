@@ -29,6 +29,7 @@ enum {
   FLAG_CAND_OVERFLOW = 0,   // a frame produced more candidates than max_candidates
   FLAG_DET_OVERFLOW = 1,    // a frame kept more detections than max_dets
   FLAG_TRACK_OVERFLOW = 2,  // a stream needed more than max_tracks live tracks
+  FLAG_TRACK_ROWS = 3,      // a stream holds more tracks than the caller's output table has rows (b200va_tracks.rows)
   FLAG_COUNT = 8
 };
 
@@ -44,6 +45,12 @@ struct b200va_ctx {
   float4* cand_box = nullptr;              // xyxy, frame pixels
   int32_t* cand_cls = nullptr;
   int32_t* cand_count = nullptr;           // [max_batch]
+  // b200va_tick schedule 4 (software-pipelined tick) decodes tick k into one candidate set while NMS + tracker of
+  // tick k-1 still read the other: every cand_* array holds two sets, `cand_set` is the one the next decode writes
+  size_t cand_set_elems = 0;               // elements per set of cand_key / cand_box / cand_cls
+  int cand_set_frames = 0;                 // frames per set (entries of cand_count per set)
+  int cand_set = 0;
+  void* pending_chain = nullptr;           // postprocess.cu: parameters of the NMS + tracker launch still owed
   int32_t* status_flags = nullptr;         // device int32[FLAG_COUNT]
   // ---- preprocess ----
   TapCache* taps = nullptr;
@@ -74,6 +81,7 @@ struct b200va_ctx {
     int decode_impl = 0, decode_ta = 0, decode_rows = 0, decode_stages = 0, decode_ctas_per_sm = 0;
     int fuse_post_track = 1;  // B200VA_FUSE_POST_TRACK=0: always launch NMS and tracker as two kernels
     int pdl = 1;              // B200VA_PDL=0: no programmatic dependent launches
+    int uniform_carveout = 0; // B200VA_UNIFORM_CARVEOUT=1: every tick kernel prefers the all-shared-memory split
   } tune;
   // ---- developer phase timing (only written by builds with -DB200VA_PHASE_TIMING) ----
   long long* dbg = nullptr;  // device int64[DBG_SLOTS]
@@ -89,6 +97,30 @@ struct b200va_ctx {
 #define PHASE_STAMP(buf, slot) \
   do {                         \
   } while (0)
+#endif
+
+// Timeline stamps (timing builds only): first CTA start / last CTA end of a kernel in %globaltimer nanoseconds,
+// dbg[slot] = min start, dbg[slot + 1] = max end.  Slots: 40 decode, 42 letterbox, 44 NMS / fused NMS + tracker, 46 tracker.
+#ifdef B200VA_PHASE_TIMING
+#define TIMELINE_BEGIN(buf, slot)                                                                   \
+  do {                                                                                              \
+    if (threadIdx.x == 0) {                                                                         \
+      unsigned long long _t;                                                                        \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                        \
+      atomicMin((unsigned long long*)&(buf)[slot], _t);                                             \
+    }                                                                                               \
+  } while (0)
+#define TIMELINE_END(buf, slot)                                                                     \
+  do {                                                                                              \
+    if (threadIdx.x == 0) {                                                                         \
+      unsigned long long _t;                                                                        \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                        \
+      atomicMax((unsigned long long*)&(buf)[(slot) + 1], _t);                                       \
+    }                                                                                               \
+  } while (0)
+#else
+#define TIMELINE_BEGIN(buf, slot) do { } while (0)
+#define TIMELINE_END(buf, slot) do { } while (0)
 #endif
 
 #define ROI_SCRATCH_BYTES (1 << 20)
@@ -142,6 +174,17 @@ struct PhaseScope {
 };
 
 #ifdef __CUDACC__
+// An SM can only change its L1 / shared-memory carve-out while it is empty, so kernels with different preferences
+// never share an SM: measured with the timing build's timeline (tools/timeline.py), a letterbox launched as a
+// programmatic dependent of the (shared-memory-free) decode kernel does not start until the decode CTAs begin to retire,
+// and does start at t = 2 us once every kernel of the tick asks for the same split (B200VA_UNIFORM_CARVEOUT=1).  It is
+// NOT the default: k_decode_cm keeps ~114 KB of loads in flight per SM through L1 and slows from 22.7 to 30.3 us with
+// the 28 KB L1 that is left, which costs more than the overlap gains (tick 72 us against 64.5 us).
+template <typename K>
+inline cudaError_t prefer_max_shared(K kernel) {
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+
 // launch on `st` as a programmatic dependent of the kernel before it (its prologue overlaps that kernel's tail)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {

@@ -39,6 +39,7 @@ struct PostParams {
   int cls0;     // first class channel: 5 (column 4 is objectness) or 4 (scores = pred[:, 4:])
   int use_obj;  // multiply class scores by column 4
   float conf_thr;
+  long long* dbg;  // timing builds: timeline stamps
   int ultra;    // Ultralytics semantics: strict `>` threshold, boxes stay in network-input pixels, equal scores keep
                 // the lower anchor first (torchvision's stable descending sort)
 };
@@ -105,6 +106,7 @@ __device__ __forceinline__ void emit_candidate(const PostParams& p, int frame, i
 template <int VEC>
 __global__ void __launch_bounds__(64) k_decode_cm(const __grid_constant__ PostParams p, int frame0) {
   griddep_launch_dependents();  // the NMS kernel may start its prologue now; its griddep_wait() still waits for this grid
+  TIMELINE_BEGIN(p.dbg, 40);
   const int frame = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int a0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
@@ -206,7 +208,10 @@ __global__ void __launch_bounds__(64) k_decode_cm(const __grid_constant__ PostPa
     if (lane >= o) incl += t;
   }
   const int total = __shfl_sync(0xffffffffu, incl, 31);
-  if (total == 0) return;
+  if (total == 0) {
+    TIMELINE_END(p.dbg, 40);
+    return;
+  }
   int base = 0;
   if (lane == 31) base = atomicAdd(p.cand_count + frame, total);
   base = __shfl_sync(0xffffffffu, base, 31);
@@ -224,6 +229,7 @@ __global__ void __launch_bounds__(64) k_decode_cm(const __grid_constant__ PostPa
         ++pos;
       }
   }
+  TIMELINE_END(p.dbg, 40);
 }
 
 // channel-major head, class rows split over the warps of a CTA -- the SMALL-BATCH variant.  k_decode_cm walks its
@@ -1104,9 +1110,13 @@ __global__ void __launch_bounds__(kNmsThreadsSmall) k_post_track(const __grid_co
                                                                   const __grid_constant__ TrkParams t) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   griddep_wait();
+  TIMELINE_BEGIN(q.dbg, 44);
   nms_frame<false, kNmsThreadsSmall>(q, blockIdx.x, smem_raw);
   __syncthreads();  // this frame's detections were written by this CTA: visible to all of its threads from here on
+  TIMELINE_END(q.dbg, 44);
+  TIMELINE_BEGIN(q.dbg, 46);
   tracker_stream(t, blockIdx.x, smem_raw);
+  TIMELINE_END(q.dbg, 46);  // (threads the tracker retires early never get here; thread 0 always does)
 }
 
 static int next_pow2(int v) {
@@ -1221,6 +1231,16 @@ static bool head_tensor_map(const float* head, int B, int C, int A, int bw, int 
 
 int postprocess_configure(b200va_ctx* h) {
   CUDA_TRY(h, cudaFuncSetAttribute(k_decode_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmemMax));
+  if (h->tune.uniform_carveout) {  // B200VA_UNIFORM_CARVEOUT=1 (experiment, see prefer_max_shared)
+    CUDA_TRY(h, prefer_max_shared(k_decode_cm<4>));
+    CUDA_TRY(h, prefer_max_shared(k_decode_cm<1>));
+    CUDA_TRY(h, prefer_max_shared(k_decode_cm_split<8, 12>));
+    CUDA_TRY(h, prefer_max_shared(k_decode_am));
+    CUDA_TRY(h, prefer_max_shared(k_decode_ring));
+    CUDA_TRY(h, prefer_max_shared(k_sort_nms<false>));
+    CUDA_TRY(h, prefer_max_shared(k_sort_nms<true>));
+    CUDA_TRY(h, prefer_max_shared(k_post_track));
+  }
   const size_t smem = nms_smem_bytes(h->cfg.max_candidates);
   if (smem > 220 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_candidates %d needs %zu bytes of shared memory", h->cfg.max_candidates, smem);
   {
@@ -1246,6 +1266,15 @@ struct FuseReq {
   int32_t* new_counts;
   bool done;
   bool tail_on_side;  // schedule 3: NMS (and the fused tracker) went to the handle's tail stream
+  bool defer;         // schedule 4: only decode now; NMS + tracker are stashed in the handle and launched by the next tick
+};
+
+// schedule 4: the NMS (+ tracker) launch a decode still owes, with everything it needs held by value
+struct PendingChain {
+  NmsParams q;
+  TrkParams t;
+  bool has_trk;  // t is filled: the tracker update of the same rows follows the NMS
+  int n;         // frames
 };
 
 struct UltraOpts {  // b200va_postprocess_ultralytics
@@ -1314,14 +1343,17 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
       for (int k = 0; k < n_classes; ++k)
         if (classes[k] >= 0 && classes[k] < 2048) p.class_mask[classes[k] >> 5] |= 1u << (classes[k] & 31);
     }
+    const bool defer = fuse && fuse->defer && base == 0 && n == batch;
+    const int set = defer ? h->cand_set : 0;  // ordinary calls always use set 0 (decode and NMS in the same call)
     p.head = head;
-    p.cand_key = h->cand_key;
-    p.cand_box = h->cand_box;
-    p.cand_cls = h->cand_cls;
-    p.cand_count = h->cand_count;
+    p.cand_key = h->cand_key + (size_t)set * h->cand_set_elems;
+    p.cand_box = h->cand_box + (size_t)set * h->cand_set_elems;
+    p.cand_cls = h->cand_cls + (size_t)set * h->cand_set_elems;
+    p.cand_count = h->cand_count + (size_t)set * h->cand_set_frames;
     p.C = channels;
     p.A = anchors;
     p.max_cand = h->cfg.max_candidates;
+    p.dbg = h->dbg;
     // REF_COMPAT (detector.py:294-307): C > 5 -> class columns 5.. times column 4; C == 5 -> pred[:, 4:].
     // V8_NATIVE: class columns 4.. as they are (what a YOLOv8 export actually contains).
     p.use_obj = (score_mode == B200VA_SCORE_REF_COMPAT && channels > 5) ? 1 : 0;
@@ -1389,10 +1421,10 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
 
     NmsParams q;
     memset(&q, 0, sizeof(q));
-    q.cand_key = h->cand_key;
-    q.cand_box = h->cand_box;
-    q.cand_cls = h->cand_cls;
-    q.cand_count = h->cand_count;
+    q.cand_key = p.cand_key;
+    q.cand_box = p.cand_box;
+    q.cand_cls = p.cand_cls;
+    q.cand_count = p.cand_count;
     q.flags = h->status_flags;
     q.out_box = out->bbox_xyxy + (size_t)base * h->cfg.max_dets * 4;
     q.out_conf = out->conf + (size_t)base * h->cfg.max_dets;
@@ -1427,6 +1459,29 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
       }
       dense = h->nms_dense_ttl > 0;
       if (dense && cap == cudaStreamCaptureStatusNone) --h->nms_dense_ttl;
+    }
+    if (defer) {
+      // stash the chain: the next b200va_tick launches it beside its own decode and letterbox
+      PendingChain* pc = (PendingChain*)h->pending_chain;
+      if (!pc) h->pending_chain = pc = new PendingChain();
+      pc->q = q;
+      pc->n = n;
+      pc->has_trk = false;
+      if (fuse->stream_slots && fuse->cfg && fuse->batch == batch) {
+        memset(&pc->t, 0, sizeof(pc->t));
+        pc->t.f_box = out->bbox_xyxy;
+        pc->t.f_conf = out->conf;
+        pc->t.d_cls = out->cls;
+        pc->t.d_count = out->count;
+        pc->t.max_dets = fuse->max_dets;
+        const int rc = tracker_fill_params(h, pc->t, fuse->stream_slots, fuse->batch, fuse->det_scale, fuse->skip, fuse->cfg,
+                                           fuse->id_base, fuse->out, fuse->new_counts);
+        if (rc != B200VA_OK) return rc;
+        pc->has_trk = true;
+        fuse->done = true;  // the tracker update is owed together with the NMS
+      }
+      h->cand_set ^= 1;
+      return B200VA_OK;
     }
     PhaseScope phase(h, B200VA_PHASE_NMS, st);
     const size_t nms_smem = nms_smem_bytes(h->cfg.max_candidates);
@@ -1476,10 +1531,55 @@ extern "C" int b200va_postprocess_ultralytics(b200va_handle h, const float* head
                           B200VA_SCORE_V8_NATIVE, B200VA_NMS_AGNOSTIC, filter_conf_thr_f64, use_filter, out, stream, &u);
 }
 
+// schedule 4: launch the NMS (+ tracker) a previous tick's decode left behind, on `stream`
+int postprocess_run_pending(b200va_handle h, void* stream) {
+  PendingChain* pc = (PendingChain*)h->pending_chain;
+  if (!pc || pc->n == 0) return B200VA_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = pc->n;
+  pc->n = 0;
+  bool dense = false;
+  if (h->nms_stats_host) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (*(volatile int*)h->nms_stats_host > 256) {
+      h->nms_dense_ttl = 64;
+      if (cap == cudaStreamCaptureStatusNone) *(volatile int*)h->nms_stats_host = 0;
+    }
+    dense = h->nms_dense_ttl > 0;
+    if (dense && cap == cudaStreamCaptureStatusNone) --h->nms_dense_ttl;
+  }
+  const size_t nms_smem = nms_smem_bytes(h->cfg.max_candidates);
+  const size_t fused_smem = std::max(nms_smem, tracker_smem_bytes(h->cfg.max_tracks));
+  {
+    PhaseScope phase(h, B200VA_PHASE_NMS, st);
+    if (pc->has_trk && !dense && h->tune.fuse_post_track != 0 && pc->t.max_dets == h->cfg.max_dets && fused_smem <= 200 * 1024) {
+      CUDA_TRY(h, launch_pdl(k_post_track, dim3(n), dim3(kNmsThreadsSmall), fused_smem, st, false, pc->q, pc->t));
+      LAUNCH_CHECK(h);
+      return B200VA_OK;
+    }
+    if (dense && pc->q.grid_off) CUDA_TRY(h, launch_pdl(k_sort_nms<true>, dim3(n), dim3(kNmsThreads), nms_smem, st, false, pc->q));
+    else CUDA_TRY(h, launch_pdl(k_sort_nms<false>, dim3(n), dim3(kNmsThreads), nms_smem, st, false, pc->q));
+    LAUNCH_CHECK(h);
+  }
+  if (pc->has_trk) return tracker_launch_params(h, pc->t, n, st);
+  return B200VA_OK;
+}
+
+bool postprocess_has_pending(b200va_handle h) {
+  const PendingChain* pc = (const PendingChain*)h->pending_chain;
+  return pc && pc->n > 0;
+}
+
+void postprocess_release(b200va_ctx* h) {
+  delete (PendingChain*)h->pending_chain;
+  h->pending_chain = nullptr;
+}
+
 // b200va_tick: post-process followed by the tracker update of the same rows; *fused tells the caller whether the
 // tracker already ran inside the post-process's second kernel.
-int postprocess_then_track(b200va_handle h, const b200va_tick_args* a, void* stream, bool* fused, bool* tail_on_side) {
-  FuseReq f{a->stream_slots, a->trk_batch, a->max_dets, a->det_scale, a->skip, a->trk_cfg, a->id_base, a->tracks, a->new_counts, false, false};
+int postprocess_then_track(b200va_handle h, const b200va_tick_args* a, void* stream, bool* fused, bool* tail_on_side, bool defer) {
+  FuseReq f{a->stream_slots, a->trk_batch, a->max_dets, a->det_scale, a->skip, a->trk_cfg, a->id_base, a->tracks, a->new_counts, false, false, defer};
   const bool want = a->stream_slots != nullptr && a->trk_batch > 0 && a->trk_batch == a->head_batch && a->trk_cfg != nullptr;
   const int rc = postprocess_impl(h, a->head, a->layout, a->head_batch, a->channels, a->anchors, a->meta, a->conf_thr, a->iou_thr,
                                   a->classes, a->n_classes, a->score_mode, a->nms_mode, a->filter_conf_thr_f64, a->use_filter,

@@ -41,6 +41,7 @@ struct PreParams {
   int row_stride, mask_stride, stages, vec_ok;
   int rows_per_stage;  // 1 when no frame of the launch ever needs the second source row
   int keep_pad_rows;   // B200VA_OUT_FLAG_PADS_VALID: full-width pad rows of `out` already hold the pad value
+  long long* dbg;      // timing builds: timeline stamps
 };
 static_assert(sizeof(PreParams) <= 4000, "kernel parameter block too large");
 
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(kThreads) k_letterbox(const __grid_constant__ 
   __shared__ __align__(8) uint64_t full[kMaxStages];
   __shared__ TapY s_ty[kMaxRowsPerCta];
 
+  TIMELINE_BEGIN(p.dbg, 42);
   const int frame = blockIdx.y;
   const PreFrame& f = p.f[frame];
   const TapX* __restrict__ xt = reinterpret_cast<const TapX*>(p.tabs + f.xtab);
@@ -338,6 +340,7 @@ __global__ void __launch_bounds__(kThreads) k_letterbox(const __grid_constant__ 
     if (!pad_row) __syncthreads();
     s = s + 1 == S ? 0 : s + 1;
   }
+  TIMELINE_END(p.dbg, 42);
 }
 
 // ---- host side ---------------------------------------------------------------------------
@@ -569,17 +572,22 @@ static cudaError_t launch_letterbox(const PreParams& p, bool mask, dim3 grid, si
 static const int kLetterboxSmemMax = 200 * 1024;
 
 template <int FMT>
-static cudaError_t configure_fmt() {
+static cudaError_t configure_fmt(bool uniform_carveout) {
   cudaError_t e = cudaFuncSetAttribute(k_letterbox<FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_letterbox<FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax);
+  e = cudaFuncSetAttribute(k_letterbox<FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax);
+  if (e != cudaSuccess) return e;
+  if (!uniform_carveout) return e;
+  e = prefer_max_shared(k_letterbox<FMT, false>);
+  if (e != cudaSuccess) return e;
+  return prefer_max_shared(k_letterbox<FMT, true>);
 }
 
 int preprocess_configure(b200va_ctx* h) {
-  CUDA_TRY(h, configure_fmt<B200VA_OUT_F32_RGB_NCHW>());
-  CUDA_TRY(h, configure_fmt<B200VA_OUT_F16_RGB_NCHW>());
-  CUDA_TRY(h, configure_fmt<B200VA_OUT_U8_BGR_NCHW>());
-  CUDA_TRY(h, configure_fmt<B200VA_OUT_U8_BGR_NHWC>());
+  CUDA_TRY(h, configure_fmt<B200VA_OUT_F32_RGB_NCHW>(h->tune.uniform_carveout != 0));
+  CUDA_TRY(h, configure_fmt<B200VA_OUT_F16_RGB_NCHW>(h->tune.uniform_carveout != 0));
+  CUDA_TRY(h, configure_fmt<B200VA_OUT_U8_BGR_NCHW>(h->tune.uniform_carveout != 0));
+  CUDA_TRY(h, configure_fmt<B200VA_OUT_U8_BGR_NHWC>(h->tune.uniform_carveout != 0));
   return B200VA_OK;
 }
 
@@ -631,6 +639,7 @@ static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* 
         if (src_w[b] > max_w) max_w = src_w[b];
       }
       p.tabs = h->taps->arena;
+      p.dbg = h->dbg;
       p.out = out;
       p.dst_h = dst_h;
       p.dst_w = dst_w;

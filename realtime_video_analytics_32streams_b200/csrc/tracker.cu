@@ -75,6 +75,7 @@ int tracker_state_create(b200va_ctx* h) {
   const size_t smem = tracker_smem_bytes(h->cfg.max_tracks);
   if (smem > 190 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_tracks %d too large (<= 4096)", h->cfg.max_tracks);
   CUDA_TRY(h, cudaFuncSetAttribute(k_tracker, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (h->tune.uniform_carveout) CUDA_TRY(h, prefer_max_shared(k_tracker));
   return B200VA_OK;
 }
 
@@ -120,6 +121,8 @@ int tracker_fill_params(b200va_ctx* h, TrkParams& p, const int* stream_slots, in
     p.o_age = out->age;
     p.o_hits = out->hits;
     p.o_count = out->count;
+    REQUIRE(h, out->rows >= 0 && out->rows <= h->cfg.max_tracks, "b200va_tracks.rows %d outside [0, max_tracks]", out->rows);
+    p.o_rows = out->rows > 0 ? out->rows : h->cfg.max_tracks;
   }
   p.o_new = new_counts;
   p.flags = h->status_flags;
@@ -134,6 +137,15 @@ static int tracker_launch(b200va_ctx* h, TrkParams& p, const int* stream_slots, 
   if (rc != B200VA_OK || batch == 0) return rc;
   PhaseScope phase(h, B200VA_PHASE_TRACKER, st);
   // dense scenes (the post-process saw more than 256 candidates in a frame lately) are worth a CTA that owns its SM
+  const int width = h->nms_dense_ttl > 0 ? kTrkThreadsMax : kTrkThreadsWide;
+  CUDA_TRY(h, launch_pdl(k_tracker, dim3(batch), dim3(width), tracker_smem_bytes(h->cfg.max_tracks), st, h->tune.pdl != 0, p));
+  LAUNCH_CHECK(h);
+  return B200VA_OK;
+}
+
+// launch k_tracker for parameters filled earlier (schedule 4 of b200va_tick)
+int tracker_launch_params(b200va_ctx* h, const TrkParams& p, int batch, cudaStream_t st) {
+  PhaseScope phase(h, B200VA_PHASE_TRACKER, st);
   const int width = h->nms_dense_ttl > 0 ? kTrkThreadsMax : kTrkThreadsWide;
   CUDA_TRY(h, launch_pdl(k_tracker, dim3(batch), dim3(width), tracker_smem_bytes(h->cfg.max_tracks), st, h->tune.pdl != 0, p));
   LAUNCH_CHECK(h);

@@ -20,8 +20,6 @@ struct TrackerState {
   void* base = nullptr;
 };
 
-namespace {
-
 struct TrkParams {
   TrackerState st;
   int slots[B200VA_MAX_BATCH];
@@ -48,9 +46,12 @@ struct TrkParams {
   int32_t* o_hits;
   int32_t* o_count;
   int32_t* o_new;
+  int o_rows;  // rows per stream of the output arrays
   int32_t* flags;
   long long* dbg;
 };
+
+namespace {
 
 
 // tracker.py:129-147, IEEE double, no contraction.
@@ -428,7 +429,7 @@ __device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi,
   double* box_n = S.box[nxt] + sb * 4;
   int32_t* age_n = S.age[nxt] + sb;
   int32_t* hits_n = S.hits[nxt] + sb;
-  const size_t ob = (size_t)bi * p.max_tracks;
+  const size_t ob = (size_t)bi * p.o_rows;
   __shared__ int warp_cnt[kTrkThreadsMax / 32];
   __shared__ int s_base;
   if (tid == 0) s_base = 0;
@@ -469,7 +470,7 @@ __device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi,
       reinterpret_cast<double4*>(box_n)[dst] = b;
       age_n[dst] = age;
       hits_n[dst] = hits;
-      if (p.o_id) {
+      if (p.o_id && dst < p.o_rows) {
         p.o_id[ob + dst] = idv;
         p.o_cls[ob + dst] = scls[t];
         p.o_conf[ob + dst] = cf;
@@ -491,6 +492,7 @@ __device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi,
     S.cur[slot] = nxt;
     S.new_count[bi] = s_new;
     if (p.o_count) p.o_count[bi] = s_base;
+    if (p.o_id && s_base > p.o_rows) atomicOr(p.flags + FLAG_TRACK_ROWS, 1);
     if (p.o_new) p.o_new[bi] = s_new;
   }
 
@@ -543,7 +545,7 @@ __device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi,
       if (v < 0) {
         const long long real = next + f_pre[i] + (-v - 1);
         ids[t] = real;
-        if (p.o_id) p.o_id[(size_t)i * p.max_tracks + t] = real;
+        if (p.o_id && t < p.o_rows) p.o_id[(size_t)i * p.o_rows + t] = real;
       }
     }
   }
@@ -558,3 +560,4 @@ inline size_t tracker_smem_bytes(int max_tracks) { return (size_t)max_tracks * 4
 int tracker_fill_params(b200va_ctx* h, TrkParams& p, const int* stream_slots, int batch, const double* det_scale,
                         const uint8_t* skip, const b200va_tracker_cfg* cfg, const int64_t* id_base,
                         const b200va_tracks* out, int32_t* new_counts);
+int tracker_launch_params(b200va_ctx* h, const TrkParams& p, int batch, cudaStream_t st);

@@ -99,6 +99,7 @@ int main(int argc, char** argv) {
 
   /* a8: tracker, two updates with the same detections (the second one matches every track) */
   b200va_tracks trk;
+  memset(&trk, 0, sizeof(trk)); /* rows = 0: the arrays hold max_tracks rows per stream */
   int32_t* d_new;
   CHECK_CUDA(cudaMalloc((void**)&trk.track_id, MAX_TRACKS * sizeof(int64_t)));
   CHECK_CUDA(cudaMalloc((void**)&trk.cls, MAX_TRACKS * sizeof(int32_t)));

@@ -16,7 +16,7 @@ STRUCTS = {
     "b200va_dets": ("Dets", ["bbox_xyxy", "conf", "cls", "count"]),
     "b200va_dets64": ("Dets64", ["bbox_xyxy", "conf", "cls", "count"]),
     "b200va_tracker_cfg": ("TrackerCfg", ["max_age", "min_hits", "max_iou_distance"]),
-    "b200va_tracks": ("Tracks", ["track_id", "cls", "conf", "bbox_xyxy", "age", "hits", "count"]),
+    "b200va_tracks": ("Tracks", ["track_id", "cls", "conf", "bbox_xyxy", "age", "hits", "count", "rows"]),
     "b200va_tick_args": ("TickArgs", None),  # every field, in ctypes order
 }
 

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert declared <= set(_native.EXPORTS) | {"b200va_debug_read"}
-    assert lib.b200va_version() == 100
+    assert lib.b200va_version() == 200
     assert lib.b200va_error_string(-3) == b"configured capacity exceeded"
 
 

@@ -89,6 +89,103 @@ def test_tick_matches_oracle(schedule, fused, monkeypatch):
     h.close()
 
 
+@pytest.mark.parametrize("fused", [1, 0])
+def test_tick_software_pipelined_schedule_lags_one_call(fused, monkeypatch):
+    """Schedule 4: call k decodes head k and letterboxes frames k while NMS + tracker of head k-1 run beside them;
+    the tables of tick k are complete after call k+1, the last one after a call without inputs.  Same results."""
+    import torch
+    from realtime_video_analytics_32streams_b200 import _native as N
+
+    monkeypatch.setenv("B200VA_FUSE_POST_TRACK", str(fused))
+    n_ticks = 4
+    frames, heads = _inputs(n_ticks)
+    want = _oracle(frames, heads)
+    h = _handle()
+    nets = [torch.zeros((B, 3, *IN_HW), dtype=torch.float32, device="cuda") for _ in range(n_ticks)]
+    metas = [N.letterbox_meta(*HW, *IN_HW) for _ in range(B)]
+    plans = []
+    for t in range(n_ticks):
+        dev = [torch.from_numpy(f).cuda() for f in frames[t]]
+        plans.append(h.plan_tick(frames=dev, net_out=nets[t], dst_hw=IN_HW, head=torch.from_numpy(heads[t]).cuda(), metas=metas,
+                                 conf_thr=CONF, iou_thr=IOU, filter_conf=CONF, slots=list(range(B)), tracker_cfg=TRK,
+                                 schedule=N.SCHEDULE_SOFTWARE_PIPELINED))
+        h.tick(plans[t])
+        torch.cuda.synchronize()
+        if t == 0:
+            assert int(plans[0].tracks["count"].sum().item()) == 0  # nothing ran for tick 0 yet
+        else:
+            _check(h, want, nets[t - 1], plans[t - 1].tracks, t - 1)
+    h.tick(h.plan_tick(schedule=N.SCHEDULE_SOFTWARE_PIPELINED))  # drain: the chain of the last head
+    torch.cuda.synchronize()
+    _check(h, want, nets[-1], plans[-1].tracks, n_ticks - 1)
+    # leaving the schedule with a chain still owed: the next tick of any schedule runs it first
+    extra = h.plan_tick(frames=[torch.from_numpy(f).cuda() for f in frames[0]], net_out=nets[0], dst_hw=IN_HW,
+                        head=torch.from_numpy(heads[0]).cuda(), metas=metas, conf_thr=CONF, iou_thr=IOU, filter_conf=CONF,
+                        slots=list(range(B)), tracker_cfg=TRK, schedule=N.SCHEDULE_SOFTWARE_PIPELINED)
+    h.tick(extra)
+    other = h.plan_tick(head=torch.from_numpy(heads[1]).cuda(), metas=metas, conf_thr=CONF, iou_thr=IOU, filter_conf=CONF,
+                        slots=list(range(B)), tracker_cfg=TRK, schedule=1)
+    h.tick(other)
+    torch.cuda.synchronize()
+    assert int(extra.tracks["count"].sum().item()) > 0 and int(other.tracks["count"].sum().item()) > 0
+    h.poll_status()
+    h.close()
+
+
+def test_tick_software_pipelined_graph_replay():
+    """Schedule 4 replayed from CUDA graphs: the stashed chain is captured with the call that launches it."""
+    import torch
+    from realtime_video_analytics_32streams_b200 import _native as N
+
+    n_ticks = 5
+    frames, heads = _inputs(n_ticks)
+    want = _oracle(frames, heads)
+    h = _handle()
+    net = torch.empty((B, 3, *IN_HW), dtype=torch.float32, device="cuda")
+    metas = [N.letterbox_meta(*HW, *IN_HW) for _ in range(B)]
+    dev = [torch.empty((*HW, 3), dtype=torch.uint8, device="cuda") for _ in range(B)]
+    head = torch.empty((B, 84, 8400), dtype=torch.float32, device="cuda")
+    plan = h.plan_tick(frames=dev, net_out=net, dst_hw=IN_HW, head=head, metas=metas, conf_thr=CONF, iou_thr=IOU,
+                       filter_conf=CONF, slots=list(range(B)), tracker_cfg=TRK, schedule=N.SCHEDULE_SOFTWARE_PIPELINED)
+    # prime the pipeline eagerly (tick 0: decode only), then capture the steady-state call twice: the candidate sets
+    # alternate, so an even and an odd graph are needed
+    for s in range(B):
+        dev[s].copy_(torch.from_numpy(frames[0][s]))
+    head.copy_(torch.from_numpy(heads[0]))
+    h.tick(plan)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graphs = []
+    with torch.cuda.stream(side):
+        for k in range(2):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=side):
+                h.tick(plan)
+            graphs.append(gr)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    for t in range(1, n_ticks):
+        for s in range(B):
+            dev[s].copy_(torch.from_numpy(frames[t][s]))
+        head.copy_(torch.from_numpy(heads[t]))
+        graphs[(t - 1) % 2].replay()
+        torch.cuda.synchronize()
+        _check(h, want, net, plan.tracks, t - 1) if False else None  # net holds tick t's letterbox, tracks tick t-1's
+        tensors, trk = want[t - 1]
+        for s in range(B):
+            n = int(plan.tracks["count"][s].item())
+            rows = list(zip(plan.tracks["track_id"][s, :n].cpu().tolist(), plan.tracks["cls"][s, :n].cpu().tolist(),
+                            plan.tracks["hits"][s, :n].cpu().tolist(),
+                            [tuple(b) for b in plan.tracks["bbox_xyxy"][s, :n].cpu().tolist()]))
+            assert rows == trk[s], (t, s)
+        got = net.cpu().numpy()
+        for s in range(B):
+            assert np.array_equal(got[s].view(np.uint8), want[t][0][s].view(np.uint8)), (t, s)
+    h.poll_status()
+    h.close()
+
+
 @pytest.mark.parametrize("pdl", [1, 0])
 @pytest.mark.parametrize("schedule", [1, 3])
 def test_tick_graph_replay_matches_oracle(schedule, pdl, monkeypatch):

@@ -1,86 +1,119 @@
-"""Device-time per tick for the BASELINE.json configurations that are not the bench.py line
-(configs 1, 2, 4, 5 of SURVEY.md §8d).  Inputs resident in HBM, CUDA events around every C-ABI call,
-medians over `--steps` ticks.  Writes profiles/r1_configs.json when --out is given."""
-import argparse, json, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+"""Device time per tick for the BASELINE.json configurations that are not the bench.py headline
+(configs 1, 2, 4, 5 of SURVEY.md §8d), the letterbox on other shapes, the DFL decode, and the literal
+drop-in path (`predict` + `filter_detections` + `update` per frame) next to the CPU path.
+
+Importable (`bench.py` runs `run_all` for its `configs` block) and a CLI:
+
+    python tools/bench_configs.py [--steps 30] [--only 1,2,5,4,D,L,P] [--out profiles/r2_configs.json]
+
+Inputs are resident in HBM, CUDA events bracket every C-ABI call, medians over `steps` ticks; `tick_graph` is one
+prepared `b200va_tick` replayed from a CUDA graph (what a deployed loop runs)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
 from realtime_video_analytics_32streams_b200 import _native, synth
 
-ap = argparse.ArgumentParser(); ap.add_argument("--steps", type=int, default=30); ap.add_argument("--out", default="")
-ap.add_argument("--only", default="")
-ap.add_argument("--lshape", type=int, default=-1, help="with --only L: run just this letterbox shape (0-5)")
-args = ap.parse_args()
-dev = torch.device("cuda", 0)
-PEAK = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] \
-    if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")) else 6650.0
+
+def peak_gbps() -> float:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
 
 
 def timed(fns, steps, warm=5):
-    """fns: list of (name, callable). Returns {name: median ms} and total."""
+    """fns: list of (name, callable(k)).  Returns {name: median ms} plus the whole sequence as `tick_total`."""
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(fns) + 1)] for _ in range(steps)]
     for k in range(warm):
-        for _, f in fns: f(k)
+        for _, f in fns:
+            f(k)
     torch.cuda.synchronize()
     for k in range(steps):
         ev[k][0].record()
         for i, (_, f) in enumerate(fns):
-            f(warm + k); ev[k][i + 1].record()
+            f(warm + k)
+            ev[k][i + 1].record()
     torch.cuda.synchronize()
     res = {n: float(np.median([e[i].elapsed_time(e[i + 1]) for e in ev])) for i, (n, _) in enumerate(fns)}
     res["tick_total"] = float(np.median([e[0].elapsed_time(e[-1]) for e in ev]))
     return res
 
 
-def simple(name, B, hw, n_obj, dup, conf=0.35, iou=0.5, trk=(30, 1, 0.5)):
+def _graph_tick_ms(h, plans, reps):
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graphs = []
+    with torch.cuda.stream(side):
+        for plan in plans:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=side):
+                h.tick(plan)
+            graphs.append(gr)
+    torch.cuda.current_stream().wait_stream(side)
+    for k in range(5):
+        graphs[k % len(graphs)].replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for k in range(reps):
+        graphs[k % len(graphs)].replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def simple(name, B, hw, n_obj, dup, steps=30, conf=0.35, iou=0.5, trk=(30, 1, 0.5), max_tracks=4096, schedule=3):
     H, W = hw
-    h = _native.Handle(device=0, max_batch=max(B, 1), max_anchors=8400, max_candidates=4096, max_dets=1024, max_streams=B, max_tracks=2048)
-    g = torch.Generator(device=dev); g.manual_seed(5)
+    dev = _dev()
+    h = _native.Handle(device=dev.index, max_batch=max(B, 1), max_anchors=8400, max_candidates=4096, max_dets=1024,
+                       max_streams=B, max_tracks=max_tracks)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
     sets = 4
     frames = [torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev, generator=g) for _ in range(sets)]
     batches = [_native.FrameBatch(list(f.unbind(0))) for f in frames]
     scenes = [synth.DenseScene(9000 + s, n_objects=n_obj, dup=dup, n_obj_classes=10) for s in range(B)]
     heads = [torch.from_numpy(np.stack([sc.head(t) for sc in scenes])).to(dev) for t in range(sets)]
     metas = (_native.Letterbox * B)(*[_native.letterbox_meta(H, W, 640, 640) for _ in range(B)])
-    net = torch.empty((B, 3, 640, 640), dtype=torch.float32, device=dev)
+    nets = [torch.empty((B, 3, 640, 640), dtype=torch.float32, device=dev) for _ in range(sets)]
     dets, tracks = h.alloc_dets(B), h.alloc_tracks(B)
     slots = _native._int_array(list(range(B)))
-    r = timed([("preprocess", lambda k: h.preprocess(batches[k % sets], (640, 640), 0, out=net)),
+    r = timed([("preprocess", lambda k: h.preprocess(batches[k % sets], (640, 640), 0, out=nets[k % sets])),
                ("postprocess", lambda k: h.postprocess(heads[k % sets], metas, conf, iou, filter_conf=conf, out=dets)),
-               ("tracker", lambda k: h.tracker_update(slots, dets, trk[0], trk[1], trk[2], out=tracks))], args.steps)
+               ("tracker", lambda k: h.tracker_update(slots, dets, trk[0], trk[1], trk[2], out=tracks))], steps)
     h.poll_status()
-    # the same tick as one prepared b200va_tick replayed from a CUDA graph (what a deployed loop runs: no host
-    # launch gaps -- with 1-4 streams three Python calls cost more than the kernels -- and NMS + tracker under the letterbox)
-    plans = [h.plan_tick(frames=batches[k], net_out=net, dst_hw=(640, 640), head=heads[k], metas=metas, conf_thr=conf,
-                         iou_thr=iou, filter_conf=conf, dets=dets, slots=slots, tracker_cfg=trk, tracks=tracks)
-             for k in range(sets)]
-    side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream()); graphs = []
-    with torch.cuda.stream(side):
-        for k in range(sets):
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr, stream=side):
-                h.tick(plans[k])
-            graphs.append(gr)
-    torch.cuda.current_stream().wait_stream(side)
-    for k in range(5): graphs[k % sets].replay()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize(); e0.record()
-    n_rep = max(args.steps, 50)
-    for k in range(n_rep): graphs[k % sets].replay()
-    e1.record(); torch.cuda.synchronize()
-    r["tick_graph"] = e0.elapsed_time(e1) / n_rep
+    plans = [h.plan_tick(frames=batches[k], net_out=nets[k], dst_hw=(640, 640), head=heads[k], metas=metas, conf_thr=conf,
+                         iou_thr=iou, filter_conf=conf, dets=dets, slots=slots, tracker_cfg=trk, tracks=tracks,
+                         schedule=schedule) for k in range(sets)]
+    r["tick_graph"] = _graph_tick_ms(h, plans, max(steps, 50))
     h.poll_status()
-    r.update(config=name, streams=B, frame=[H, W], frames_per_s=B / (r["tick_graph"] * 1e-3),
+    r.update(config=name, streams=B, frame=[H, W], max_tracks=max_tracks, frames_per_s=B / (r["tick_graph"] * 1e-3),
              frames_per_s_serial_calls=B / (r["tick_total"] * 1e-3),
              dets_per_frame=float(dets["count"].float().mean()), tracks_per_stream=float(tracks["count"].float().mean()))
     h.close()
     return r
 
 
-def config4(B=32):
+def config4(B=32, steps=30):
     """32 x 4K with per-stream ROI polygons and the motion gate (every pixel is read)."""
     H, W = 2160, 3840
-    h = _native.Handle(device=0, max_batch=B, max_anchors=8400, max_candidates=4096, max_dets=1024, max_streams=B, max_tracks=2048)
-    g = torch.Generator(device=dev); g.manual_seed(7)
+    dev = _dev()
+    PEAK = peak_gbps()
+    h = _native.Handle(device=dev.index, max_batch=B, max_anchors=8400, max_candidates=4096, max_dets=1024, max_streams=B,
+                       max_tracks=4096)
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
     sets = 2
     frames = [torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev, generator=g) for _ in range(sets)]
     masks = [h.roi_rasterize(synth.synth_polygons(4000 + s, H, W), H, W) for s in range(B)]
@@ -97,27 +130,21 @@ def config4(B=32):
     r = timed([("motion(+roi)", lambda k: h.motion(batches[k % sets], gray[(k + 1) % 2], gray[k % 2], changed_out=changed)),
                ("preprocess(+roi)", lambda k: h.preprocess(batches[k % sets], (640, 640), 0, out=net)),
                ("postprocess", lambda k: h.postprocess(heads[k % sets], metas, 0.35, 0.5, filter_conf=0.35, out=dets)),
-               ("tracker", lambda k: h.tracker_update(slots, dets, 30, 1, 0.5, out=tracks))], args.steps)
+               ("tracker", lambda k: h.tracker_update(slots, dets, 30, 1, 0.5, out=tracks))], steps)
     h.poll_status()
     # the same two steps as ONE pass over each frame (b200va_motion_preprocess)
     rf = timed([("fused", lambda k: h.motion_preprocess(batches[k % sets], gray[(k + 1) % 2], gray[k % 2], (640, 640), 0,
-                                                        changed_out=changed, out=net))], args.steps)
-    rp = timed([("fused", lambda k: h.motion_preprocess(batches[k % sets], gray[(k + 1) % 2], gray[k % 2], (640, 640),
-                                                        0 | _native.OUT_FLAG_PADS_VALID, changed_out=changed, out=net))],
-               args.steps)
+                                                        changed_out=changed, out=net))], steps)
     h.poll_status()
     fused_bytes = B * (H * W * 3 + 3 * H * W + 3 * 640 * 640 * 4)  # frame + mask + prev gray + new gray + network input
     r["motion+preprocess fused"] = rf["fused"]
-    r["motion+preprocess fused, pad rows kept"] = rp["fused"]
-    r["fused_GBps"] = fused_bytes / (rf["fused"] * 1e-3) / 1e9
-    r["fused_frac_of_peak"] = r["fused_GBps"] / PEAK
-    r["fused_algorithmic_bytes"] = fused_bytes
+    r["fused_frac_of_peak"] = fused_bytes / (rf["fused"] * 1e-3) / 1e9 / PEAK
     r["tick_total_fused"] = rf["fused"] + r["postprocess"] + r["tracker"]
     motion_bytes = B * (H * W * 3 + 3 * H * W)  # frame + mask + prev gray + new gray
     pre_bytes = B * (720 * W * 3 + 720 * W + 3 * 640 * 640 * 4)  # tapped rows (+ their mask rows) + output
-    r.update(config="4: 32x4K + ROI + motion", streams=B, frame=[H, W], frames_per_s=B / (r["tick_total_fused"] * 1e-3),
-             frames_per_s_separate_kernels=B / (r["tick_total"] * 1e-3),
-             motion_GBps=motion_bytes / (r["motion(+roi)"] * 1e-3) / 1e9, motion_frac_of_peak=motion_bytes / (r["motion(+roi)"] * 1e-3) / 1e9 / PEAK,
+    r.update(config="4: 32x4K + ROI + motion", streams=B, frame=[H, W], frames_per_s=B / (r["tick_total"] * 1e-3),
+             motion_GBps=motion_bytes / (r["motion(+roi)"] * 1e-3) / 1e9,
+             motion_frac_of_peak=motion_bytes / (r["motion(+roi)"] * 1e-3) / 1e9 / PEAK,
              preprocess_GBps=pre_bytes / (r["preprocess(+roi)"] * 1e-3) / 1e9,
              preprocess_frac_of_peak=pre_bytes / (r["preprocess(+roi)"] * 1e-3) / 1e9 / PEAK,
              motion_algorithmic_bytes=motion_bytes, preprocess_algorithmic_bytes=pre_bytes)
@@ -125,21 +152,35 @@ def config4(B=32):
     return r
 
 
-def letterbox_only(name, B, hw, fmt=0, mask=False):
+def tapped_rows(src: int, dst: int) -> int:
+    """How many source rows carry a non-zero vertical weight in an 8-bit INTER_LINEAR resize src -> dst (the rows the
+    letterbox kernel reads; OpenCV's float32 tap arithmetic with 11-bit rounded coefficients)."""
+    d = np.arange(dst, dtype=np.float64)
+    fy = ((d + 0.5) * (1.0 / (dst / src)) - 0.5).astype(np.float32)
+    sy = np.floor(fy).astype(np.int64)
+    fy = fy - sy.astype(np.float32)
+    b1 = np.rint(fy * np.float32(2048)).astype(np.int64)
+    b0 = np.rint((np.float32(1) - fy) * np.float32(2048)).astype(np.int64)
+    y0, y1 = np.clip(sy, 0, src - 1), np.clip(sy + 1, 0, src - 1)
+    return len(set(y0[b0 != 0].tolist()) | set(y1[b1 != 0].tolist()))
+
+
+def letterbox_only(name, B, hw, fmt=0, mask=False, steps=30):
     H, W = hw
-    h = _native.Handle(device=0, max_batch=B, max_anchors=8400, max_candidates=1024, max_dets=256, max_streams=B, max_tracks=256)
-    g = torch.Generator(device=dev); g.manual_seed(5)
+    dev = _dev()
+    PEAK = peak_gbps()
+    h = _native.Handle(device=dev.index, max_batch=B, max_anchors=8400, max_candidates=1024, max_dets=256, max_streams=B,
+                       max_tracks=256)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
     frames = [torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev, generator=g) for _ in range(2)]
     masks = [h.roi_rasterize(synth.synth_polygons(4000 + s, H, W), H, W) for s in range(B)] if mask else None
     batches = [_native.FrameBatch(list(f.unbind(0)), masks) for f in frames]
     dt = {0: torch.float32, 1: torch.float16}.get(fmt, torch.uint8)
-    net = torch.empty((B, 3, 640, 640), dtype=dt, device=dev)
-    r = timed([("preprocess", lambda k: h.preprocess(batches[k % 2], (640, 640), fmt, out=net))], args.steps)
+    nets = [torch.empty((B, 3, 640, 640), dtype=dt, device=dev) for _ in range(2)]
+    r = timed([("preprocess", lambda k: h.preprocess(batches[k % 2], (640, 640), fmt, out=nets[k % 2]))], steps)
     m = _native.letterbox_meta(H, W, 640, 640)
-    ys = set()
-    from oracle import cv_restate as cvr
-    y0, y1, b0, b1 = cvr.linear_taps(H, m.new_h, False)
-    rows = len(set(y0[b0 != 0].tolist()) | set(y1[b1 != 0].tolist()))
+    rows = tapped_rows(H, m.new_h)
     esz = {0: 4, 1: 2}.get(fmt, 1)
     alg = B * (rows * W * 3 + (rows * W if mask else 0) + 3 * 640 * 640 * esz)
     r.update(config=name, streams=B, frame=[H, W], algorithmic_bytes=alg, GBps=alg / (r["preprocess"] * 1e-3) / 1e9,
@@ -148,13 +189,17 @@ def letterbox_only(name, B, hw, fmt=0, mask=False):
     return r
 
 
-def dfl_only(B=32, nc=80):
+def dfl_only(B=32, nc=80, steps=30):
     """a14: raw Detect head [B, 64 + nc, 8400] -> decoded [B, 4 + nc, 8400]."""
-    h = _native.Handle(device=0, max_batch=B, max_anchors=8400, max_candidates=1024, max_dets=256, max_streams=B, max_tracks=256)
-    g = torch.Generator(device=dev); g.manual_seed(9)
+    dev = _dev()
+    PEAK = peak_gbps()
+    h = _native.Handle(device=dev.index, max_batch=B, max_anchors=8400, max_candidates=1024, max_dets=256, max_streams=B,
+                       max_tracks=256)
+    g = torch.Generator(device=dev)
+    g.manual_seed(9)
     raws = [torch.randn((B, 64 + nc, 8400), dtype=torch.float32, device=dev, generator=g) * 3 for _ in range(3)]
-    out_t = torch.empty((B, 4 + nc, 8400), dtype=torch.float32, device=dev)
-    r = timed([("dfl_decode", lambda k: h.dfl_decode(raws[k % 3], nc, out=out_t))], args.steps)
+    outs = [torch.empty((B, 4 + nc, 8400), dtype=torch.float32, device=dev) for _ in range(3)]
+    r = timed([("dfl_decode", lambda k: h.dfl_decode(raws[k % 3], nc, out=outs[k % 3]))], steps)
     alg = B * 8400 * 4 * ((64 + nc) + (4 + nc))
     r.update(config="a14: DFL decode of 32 raw heads [144, 8400]", streams=B, algorithmic_bytes=alg,
              GBps=alg / (r["dfl_decode"] * 1e-3) / 1e9, frac_of_peak=alg / (r["dfl_decode"] * 1e-3) / 1e9 / PEAK)
@@ -162,22 +207,107 @@ def dfl_only(B=32, nc=80):
     return r
 
 
-out = []
-todo = args.only.split(",") if args.only else ["1", "2", "5", "4", "D"]
-if "L" in todo:
-    shapes = [("letterbox 32x1080p fp32", 32, (1080, 1920), 0, False), ("letterbox 32x1080p fp16", 32, (1080, 1920), 1, False),
-              ("letterbox 32x4K fp32", 32, (2160, 3840), 0, False), ("letterbox 32x4K fp32 + ROI mask", 32, (2160, 3840), 0, True),
-              ("letterbox 32x720p fp32", 32, (720, 1280), 0, False),
-              ("letterbox 32x1440p fp32 (non-integer ratio)", 32, (1440, 2560), 0, False)]
-    for i, (nm, b, hw, fmt, mask) in enumerate(shapes):
-        if args.lshape < 0 or args.lshape == i:
-            out.append(letterbox_only(nm, b, hw, fmt=fmt, mask=mask))
-if "1" in todo: out.append(simple("1: 1 stream 1080p (pipeline-sim shape)", 1, (1080, 1920), 10, 1))
-if "2" in todo: out.append(simple("2: 4 streams 1080p (pipeline-rtsp shape)", 4, (1080, 1920), 10, 1))
-if "5" in todo: out.append(simple("5: dense stress, 32 streams, ~1800 candidates -> ~300 kept", 32, (1080, 1920), 300, 6))
-if "4" in todo: out.append(config4())
-if "D" in todo: out.append(dfl_only())
-for r in out:
-    print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()}))
-if args.out:
-    json.dump({"peak_GBps": PEAK, "results": out}, open(args.out, "w"), indent=1)
+def dropin(name, B, n_frames=60):
+    """The literal drop-in the reference's pipeline reaches today (`backend: b200`, one StreamWorker per stream,
+    pipeline.py:172-188): per frame `detector.predict(packet)` -> `filter_detections` -> `tracker.update(stream, dets)`
+    with a HOST ndarray frame in and Python Detection / Track objects out, wall clock per frame; and the same call
+    sequence on the CPU (oracle, cv2 back end = the reference's own OpenCV / NumPy calls), one thread."""
+    from oracle import hotpath as O
+    from realtime_video_analytics_32streams_b200 import (B200Detector, B200IouTracker, DetectorConfig, FramePacket,
+                                                         StreamConfig, TrackerConfig, filter_detections)
+
+    dev = _dev()
+    h = _native.Handle(device=dev.index, max_batch=max(B, 1), max_anchors=8400, max_candidates=2048, max_dets=512,
+                       max_streams=max(B, 1), max_tracks=4096)
+    H, W = 1080, 1920
+    frames = [synth.synth_frame(1000 + s, H, W) for s in range(B)]
+    scenes = [synth.DenseScene(9000 + s, n_objects=10, dup=1, n_obj_classes=10) for s in range(B)]
+    n_heads = 8
+    heads_np = [[sc.head(t) for t in range(n_heads)] for sc in scenes]
+    heads = [[torch.from_numpy(hd[None]).to(dev) for hd in per] for per in heads_np]
+    cur = {"s": 0, "t": 0}
+    det = B200Detector(DetectorConfig(confidence_threshold=0.35, iou_threshold=0.5), input_hw=(640, 640),
+                       infer=lambda tensor: heads[cur["s"]][cur["t"] % n_heads], handle=h)
+    trk = B200IouTracker(TrackerConfig(max_age=30, max_iou_distance=0.5, min_hits=1), handle=h)
+    streams = [StreamConfig(name=f"cam{s}") for s in range(B)]
+
+    def gpu_frame(s, t):
+        cur["s"], cur["t"] = s, t
+        dets = filter_detections(det.predict(FramePacket(streams[s], frames[s], t, 0.0)), 0.35)
+        return trk.update(streams[s].name, dets)
+
+    for t in range(5):
+        for s in range(B):
+            gpu_frame(s, t)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_trk = 0
+    for t in range(n_frames):
+        for s in range(B):
+            n_trk += len(gpu_frame(s, 5 + t))
+    gpu_ms = 1e3 * (time.perf_counter() - t0) / (n_frames * B)
+    trk.close()
+    h.close()
+    # CPU: the reference's call sequence
+    import cv2
+
+    cv2.setNumThreads(1)
+    ora = O.IouTracker(30, 0.5, 1)
+
+    def cpu_frame(s, t):
+        tensor, meta = O.preprocess(frames[s], (640, 640), False, backend="cv2")
+        dets = O.filter_detections(O.postprocess(heads_np[s][t % n_heads][None], meta, 0.35, 0.5), 0.35)
+        return ora.update(f"cam{s}", dets)
+
+    for s in range(B):
+        cpu_frame(s, 0)
+    n_cpu = max(10, n_frames // 3)
+    t0 = time.perf_counter()
+    for t in range(n_cpu):
+        for s in range(B):
+            cpu_frame(s, 1 + t)
+    cpu_ms = 1e3 * (time.perf_counter() - t0) / (n_cpu * B)
+    return {"config": name, "streams": B, "frame": [H, W], "api": "B200Detector.predict + filter_detections + B200IouTracker.update "
+            "per frame (host ndarray in, Python objects out)", "gpu_ms_per_frame": gpu_ms, "cpu_reference_ms_per_frame": cpu_ms,
+            "speedup": cpu_ms / gpu_ms, "tracks_per_frame": n_trk / (n_frames * B),
+            "h2d_bytes_per_frame": 360 * W * 3, "frames_timed": n_frames * B}
+
+
+def run_all(todo=("1", "2", "5", "4", "P"), steps=30, lshape=-1):
+    out = []
+    if "L" in todo:
+        shapes = [("letterbox 32x1080p fp32", 32, (1080, 1920), 0, False), ("letterbox 32x1080p fp16", 32, (1080, 1920), 1, False),
+                  ("letterbox 32x4K fp32", 32, (2160, 3840), 0, False), ("letterbox 32x4K fp32 + ROI mask", 32, (2160, 3840), 0, True),
+                  ("letterbox 32x720p fp32", 32, (720, 1280), 0, False),
+                  ("letterbox 32x1440p fp32 (non-integer ratio)", 32, (1440, 2560), 0, False)]
+        for i, (nm, b, hw, fmt, mask) in enumerate(shapes):
+            if lshape < 0 or lshape == i:
+                out.append(letterbox_only(nm, b, hw, fmt=fmt, mask=mask, steps=steps))
+    if "1" in todo:
+        out.append(simple("1: 1 stream 1080p (pipeline-sim shape)", 1, (1080, 1920), 10, 1, steps))
+    if "2" in todo:
+        out.append(simple("2: 4 streams 1080p (pipeline-rtsp shape)", 4, (1080, 1920), 10, 1, steps))
+    if "5" in todo:
+        out.append(simple("5: dense stress, 32 streams, ~1800 candidates -> ~300 kept", 32, (1080, 1920), 300, 6, steps))
+    if "4" in todo:
+        out.append(config4(steps=steps))
+    if "D" in todo:
+        out.append(dfl_only(steps=steps))
+    if "P" in todo:
+        out.append(dropin("1 (drop-in API): 1 stream 1080p through predict / update", 1))
+        out.append(dropin("2 (drop-in API): 4 streams 1080p through predict / update", 4, n_frames=30))
+    return [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in out]
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--out", default="")
+    ap.add_argument("--only", default="")
+    ap.add_argument("--lshape", type=int, default=-1, help="with --only L: run just this letterbox shape (0-5)")
+    args = ap.parse_args()
+    res = run_all(args.only.split(",") if args.only else ("1", "2", "5", "4", "D", "P"), args.steps, args.lshape)
+    for r in res:
+        print(json.dumps(r))
+    if args.out:
+        json.dump({"peak_GBps": peak_gbps(), "results": res}, open(args.out, "w"), indent=1)
