@@ -75,8 +75,9 @@ def make_heads(stream: int, n_sets: int) -> np.ndarray:
 # clocks
 # --------------------------------------------------------------------------------------------
 class ClockSampler:
-    def __init__(self, device_index: int):
+    def __init__(self, device_index: int, period_s: float = 0.002):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.period_s = period_s
         self._stop = threading.Event()
         self._thread = None
         try:
@@ -113,7 +114,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            self._stop.wait(0.002)
+            self._stop.wait(self.period_s)
 
     def start(self):
         if self.nv is not None:
@@ -226,6 +227,71 @@ def run_reference(args) -> None:
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+WINDOWS = 15          # the K-step timed window is repeated this many times; the median window is the headline
+KERNEL_SAMPLES = 24   # eager ticks with per-kernel CUDA-event pairs (b200va_set_profiling), whatever --steps is
+HEAD_BYTES_PER_FRAME = C * A * 4
+
+
+def _capture(torch, h, plans):
+    """One CUDA graph per prepared tick (fork / join and programmatic dependent launches included)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graphs = []
+    l0 = h.launch_count
+    with torch.cuda.stream(side):
+        for plan in plans:
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=side):
+                plan.set_events(None, None)
+                h.tick(plan)
+            graphs.append(gr)
+    torch.cuda.current_stream().wait_stream(side)
+    return graphs, (h.launch_count - l0) // max(len(plans), 1)
+
+
+def parity_check(torch, h, frame_sets, heads_np, plans, nets, tracks, dets) -> dict:
+    """Two ticks from an empty tracker (input sets 0 and 1) compared with the CPU oracle: every network-input tensor
+    bit for bit, every detection table, every track table (ids, classes, boxes, hits).  The oracle is only the checker
+    here; nothing it computes is timed or shipped."""
+    from oracle import hotpath as O
+
+    for s in range(STREAMS):
+        h.tracker_reset(s)
+    h.tracker_set_next_id(1)
+    ora = O.IouTracker(TRK["max_age"], TRK["max_iou_distance"], TRK["min_hits"])
+    checked = {"ticks": 2, "streams": STREAMS, "letterbox_tensors": 0, "detections": 0, "tracks": 0}
+    for t in range(2):
+        h.tick(plans[t])
+        torch.cuda.synchronize()
+        got_net = nets[t].cpu().numpy()
+        d = {k: v.cpu().numpy() for k, v in dets.items() if not k.startswith("_")}
+        tr = {k: v.cpu().numpy() for k, v in tracks.items() if not k.startswith("_")}
+        frames = frame_sets[t].cpu().numpy()
+        for s in range(STREAMS):
+            tensor, meta = O.preprocess(frames[s], IN_HW, False, backend="cv2")
+            if not np.array_equal(got_net[s].view(np.uint8), tensor[0].view(np.uint8)):
+                raise SystemExit(f"bench parity: letterbox tensor of stream {s}, tick {t} differs from the oracle")
+            want_d = O.filter_detections(O.postprocess(heads_np[t][s][None], meta, CONF, IOU), CONF)
+            n = int(d["count"][s])
+            if n != len(want_d) or not np.array_equal(
+                    d["bbox_xyxy"][s, :n], np.array([w.bbox_xyxy for w in want_d], dtype=np.float32).reshape(n, 4)) \
+                    or d["cls"][s, :n].tolist() != [w.class_id for w in want_d] \
+                    or not np.array_equal(d["conf"][s, :n], np.array([w.confidence for w in want_d], dtype=np.float32)):
+                raise SystemExit(f"bench parity: detections of stream {s}, tick {t} differ from the oracle")
+            want_t = ora.update(f"s{s}", want_d)
+            m = int(tr["count"][s])
+            if m != len(want_t) or tr["track_id"][s, :m].tolist() != [w.track_id for w in want_t] \
+                    or tr["cls"][s, :m].tolist() != [w.class_id for w in want_t] \
+                    or tr["hits"][s, :m].tolist() != [w.hits for w in want_t] \
+                    or not np.array_equal(tr["bbox_xyxy"][s, :m],
+                                          np.array([w.bbox_xyxy for w in want_t], dtype=np.float32).reshape(m, 4)):
+                raise SystemExit(f"bench parity: track table of stream {s}, tick {t} differs from the oracle")
+            checked["letterbox_tensors"] += 1
+            checked["detections"] += n
+            checked["tracks"] += m
+    return checked
+
+
 def run_gpu(args) -> None:
     import torch
     import torch.distributed as dist
@@ -253,8 +319,20 @@ def run_gpu(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gather(values):
+        """[world][len(values)] float64: every rank's list, on every rank."""
+        mine = torch.tensor(list(values), dtype=torch.float64, device=dev)
+        if world == 1:
+            return [mine.cpu().tolist()]
+        out = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(out, mine)
+        return [o.cpu().tolist() for o in out]
+
+    K = args.steps
+    warm = max(args.warmup, 3)
+    # max_tracks 4096: SURVEY.md's sizing note (a stream's table, counted before the prune, must fit)
     h = _native.Handle(device=local, max_batch=STREAMS, max_anchors=A, max_candidates=2048, max_dets=512,
-                       max_streams=2 * STREAMS, max_tracks=1024)
+                       max_streams=2 * STREAMS, max_tracks=4096)
     # ---- synthetic inputs, resident in HBM --------------------------------------------------
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
@@ -263,56 +341,52 @@ def run_gpu(args) -> None:
     heads_np = np.stack([make_heads(rank * STREAMS + s, N_SETS) for s in range(STREAMS)], axis=1)  # [sets, 32, C, A]
     head_sets = [torch.from_numpy(heads_np[k]).to(dev) for k in range(N_SETS)]
     metas = (_native.Letterbox * STREAMS)(*[_native.letterbox_meta(H, W, *IN_HW) for _ in range(STREAMS)])
-    net_in = torch.empty((STREAMS, 3, *IN_HW), dtype=torch.float32, device=dev)
+    # the network-input tensor rotates with the input sets (4 x 157 MB): a step's writes never land on lines that
+    # are still dirty in L2 from the step before
+    nets = [torch.empty((STREAMS, 3, *IN_HW), dtype=torch.float32, device=dev) for _ in range(N_SETS)]
     dets = h.alloc_dets(STREAMS)
     tracks = h.alloc_tracks(STREAMS)
     slots = _native._int_array(list(range(STREAMS)))
-    # argument arrays are built once per input set: the per-step host work is three foreign calls
+    trk_cfg = (TRK["max_age"], TRK["min_hits"], TRK["max_iou_distance"])
+    # argument arrays are built once per input set: the per-step host work is one foreign call
     batches = [_native.FrameBatch(list(fs.unbind(0))) for fs in frame_sets]
 
-    # one prepared b200va_tick per input set: letterbox on the caller's stream, decode -> NMS -> tracker on the
-    # library's second stream (schedule 1: the letterbox starts when the decode kernel is done and overlaps
-    # NMS + tracker, so the two HBM-bound kernels never share the bus); fork and join are inside every step
-    plans = [h.plan_tick(frames=batches[k], net_out=net_in, dst_hw=IN_HW, fmt=_native.OUT_F32_RGB_NCHW,
-                         head=head_sets[k], metas=metas, conf_thr=CONF, iou_thr=IOU, filter_conf=CONF, dets=dets,
-                         slots=slots, tracker_cfg=(TRK["max_age"], TRK["min_hits"], TRK["max_iou_distance"]),
-                         tracks=tracks, schedule=args.schedule) for k in range(N_SETS)]
+    def make_plans(fmt=_native.OUT_F32_RGB_NCHW, m=STREAMS, p_dets=dets, p_tracks=tracks, p_slots=slots, p_metas=metas):
+        return [h.plan_tick(frames=batches[k] if m == STREAMS else _native.FrameBatch(list(frame_sets[k][:m].unbind(0))),
+                            net_out=nets[k][:m], dst_hw=IN_HW, fmt=fmt, head=head_sets[k][:m], metas=p_metas,
+                            conf_thr=CONF, iou_thr=IOU, filter_conf=CONF, dets=p_dets, slots=p_slots, tracker_cfg=trk_cfg,
+                            tracks=p_tracks, schedule=args.schedule) for k in range(N_SETS)]
 
-    def step(k, ev=None):
-        plan = plans[k % N_SETS]
-        plan.set_events(*(ev if ev is not None else (None, None)))
-        h.tick(plan)
+    # one prepared b200va_tick per input set: decode -> NMS -> tracker on the library's second stream, letterbox on the
+    # caller's (schedule 1: it starts when the decode kernel is done and overlaps NMS + tracker); fork and join inside
+    plans = make_plans()
+
+    # ---- parity of the timed computation (before anything is timed) -------------------------
+    parity = None
+    if not args.no_parity:
+        if rank == 0:
+            parity = parity_check(torch, h, frame_sets, heads_np, plans, nets, tracks, dets)
+        barrier()
+    for s in range(STREAMS):
+        h.tracker_reset(s)
+
+    def step(k):
+        h.tick(plans[k % N_SETS])
 
     def serial_step(k):
-        h.preprocess(batches[k % N_SETS], IN_HW, _native.OUT_F32_RGB_NCHW, out=net_in)
+        h.preprocess(batches[k % N_SETS], IN_HW, _native.OUT_F32_RGB_NCHW, out=nets[k % N_SETS])
         h.postprocess(head_sets[k % N_SETS], metas, CONF, IOU, filter_conf=CONF, out=dets)
-        h.tracker_update(slots, dets, TRK["max_age"], TRK["min_hits"], TRK["max_iou_distance"], out=tracks)
+        h.tracker_update(slots, dets, *trk_cfg, out=tracks)
 
-    # the tick is captured once per input set in a CUDA graph (fork / join included): the timed loop replays
-    # graphs, except that every SAMPLE_EVERY-th step runs the same tick eagerly with an event pair around the
-    # letterbox launch -- the live kernel timing the roofline is computed from
-    SAMPLE_EVERY = 10
-    for k in range(max(args.warmup, 3)):
+    for k in range(warm):
         step(k)
     barrier()
     h.poll_status()
     graphs, kernels_per_graph = None, 0
     if not args.no_graph:
         try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            graphs = []
-            l0 = h.launch_count
-            with torch.cuda.stream(side):
-                for k in range(N_SETS):
-                    gr = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(gr, stream=side):
-                        plans[k].set_events(None, None)
-                        h.tick(plans[k])
-                    graphs.append(gr)
-            torch.cuda.current_stream().wait_stream(side)
-            kernels_per_graph = (h.launch_count - l0) // N_SETS
-            for k in range(max(args.warmup, 3)):
+            graphs, kernels_per_graph = _capture(torch, h, plans)
+            for k in range(warm):
                 graphs[k % N_SETS].replay()
         except Exception as exc:  # pragma: no cover - capture refused: every step is launched eagerly instead
             print(f"bench: CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
@@ -320,122 +394,109 @@ def run_gpu(args) -> None:
             torch.cuda.synchronize()
         barrier()
 
-    def timed_step(k, ev):
-        if graphs is None or ev is not None:
-            step(k, ev)
-            return 0
-        graphs[k % N_SETS].replay()
-        return kernels_per_graph
+    def run_step(k):
+        if graphs is None:
+            step(k)
+        else:
+            graphs[k % N_SETS].replay()
 
-    clocks = ClockSampler(local)
-    n_samples = (args.steps + SAMPLE_EVERY - 1) // SAMPLE_EVERY if graphs is not None else args.steps
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_samples)]
-    for a, b in kev:  # torch creates the CUDA event on its first record; the library records it afterwards
-        a.record()
-        b.record()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    def windows(fn, n_windows, frames_per_step=STREAMS):
+        """`n_windows` timed windows of EXACTLY K steps each, every one bracketed by barrier + synchronize on both
+        sides and timed with CUDA events on the launching stream.  Per window the job time is the max over ranks;
+        the reported time is the median window.  Returns (median ms, stats)."""
+        for k in range(warm):
+            fn(k)
+        per = []
+        for w in range(n_windows):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for k in range(K):
+                fn(w * K + k)
+            e1.record()
+            barrier()
+            per.append(e0.elapsed_time(e1))
+        allr = np.array(gather(per))          # [world, windows]
+        job = allr.max(axis=0)                # max over ranks, per window
+        med = float(np.median(job))
+        stats = {"windows": n_windows, "steps_per_window": K,
+                 "job_ms_per_step": {"min": round(float(job.min()) / K, 5), "median": round(med / K, 5),
+                                     "max": round(float(job.max()) / K, 5)},
+                 "per_rank_ms_per_step": [{"rank": r, "min": round(float(allr[r].min()) / K, 5),
+                                           "median": round(float(np.median(allr[r])) / K, 5),
+                                           "max": round(float(allr[r].max()) / K, 5)} for r in range(world)]}
+        return med, stats
+
+    # ---- the timed region --------------------------------------------------------------------
+    clocks = ClockSampler(local, period_s=0.010)
     launches0 = h.launch_count
-    replayed = 0
-    barrier()
     clocks.start()
-    start.record()
-    for k in range(args.steps):
-        sample = graphs is None or k % SAMPLE_EVERY == 0
-        replayed += timed_step(args.warmup + k, kev[k // SAMPLE_EVERY if graphs is not None else k] if sample else None)
-    end.record()
-    barrier()
+    ms, win_stats = windows(run_step, WINDOWS)
     clocks.stop()
-    launches = h.launch_count - launches0 + replayed
-    ms = start.elapsed_time(end)
-    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    # per-call device time (separate untimed loop, events around each C-ABI call)
-    bev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(20)]
-    for k, e in enumerate(bev):
-        e[0].record()
-        h.preprocess(batches[k % N_SETS], IN_HW, _native.OUT_F32_RGB_NCHW, out=net_in)
-        e[1].record()
-        h.postprocess(head_sets[k % N_SETS], metas, CONF, IOU, filter_conf=CONF, out=dets)
-        e[2].record()
-        h.tracker_update(slots, dets, TRK["max_age"], TRK["min_hits"], TRK["max_iou_distance"], out=tracks)
-        e[3].record()
-    torch.cuda.synchronize()
-    breakdown = {name: round(float(np.median([e[i].elapsed_time(e[i + 1]) for e in bev])), 4)
-                 for i, name in enumerate(("preprocess", "postprocess(decode+sort_nms)", "tracker_update"))}
+    launches_per_step = kernels_per_graph if graphs is not None else (h.launch_count - launches0) / ((WINDOWS * K) + warm)
+    value = world * STREAMS * K / (ms * 1e-3)
     n_tracks = int(tracks["count"].sum().item())
     h.poll_status()
+    # clocks under the same load, sampled densely in a window of their own (the thread above polls every 10 ms so
+    # that it does not compete with the launching thread inside the short timed windows)
+    load_clocks = ClockSampler(local, period_s=0.002)
+    barrier()
+    load_clocks.start()
+    t_end = time.perf_counter() + 0.25
+    k = 0
+    while time.perf_counter() < t_end:
+        run_step(k)
+        k += 1
+        if k % 64 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    load_clocks.stop()
+    barrier()
 
-    def timed_variant(fn):
-        for k in range(8):
-            fn(k)
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for k in range(args.steps):
-            fn(k)
-        s1.record()
-        barrier()
-        v_ms = s0.elapsed_time(s1)
-        if world > 1:
-            tmax = torch.tensor([v_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            v_ms = float(tmax.item())
-        return world * STREAMS * args.steps / (v_ms * 1e-3)
+    # ---- live per-kernel device times: eager ticks, one CUDA-event pair per phase on the launching stream -----
+    h.set_profiling(True)
+    samples = {}
+    for k in range(KERNEL_SAMPLES + 4):
+        step(k)
+        pt = h.phase_times()
+        if k >= 4:
+            for name, v in pt.items():
+                samples.setdefault(name, []).append(v)
+    h.set_profiling(False)
+    kern_ms = {name: float(np.median(v)) for name, v in samples.items()}
+    h.poll_status()
+    barrier()
 
-    # informational: the same tick launched eagerly every step, and as three separate C-ABI calls on one stream
-    eager_value = timed_variant(lambda k: step(k))
-    serial_value = timed_variant(serial_step)
-    # informational: the same tick with B200VA_OUT_FLAG_PADS_VALID -- the 280 pad rows of every 640 x 640 input (44 % of
-    # the letterbox output) were written by the earlier steps into the same persistent buffer and are not written
-    # again.  Not the headline: `value` rewrites the whole tensor every step, like the reference does.
-    pads_value = None
+    # ---- informational variants (5 windows each) --------------------------------------------
+    eager_ms, _ = windows(step, 5)
+    serial_ms, _ = windows(serial_step, 5)
+    # the same tick with B200VA_OUT_FLAG_PADS_VALID -- the 280 pad rows of every 640 x 640 input (44 % of the letterbox
+    # output) were written by the earlier steps into the same persistent buffers and are not written again.  Not the
+    # headline: `value` rewrites the whole tensor every step, like the reference does.
+    pads_ms = None
     if graphs is not None:
-        p_plans = [h.plan_tick(frames=batches[k], net_out=net_in, dst_hw=IN_HW,
-                               fmt=_native.OUT_F32_RGB_NCHW | _native.OUT_FLAG_PADS_VALID, head=head_sets[k], metas=metas,
-                               conf_thr=CONF, iou_thr=IOU, filter_conf=CONF, dets=dets, slots=slots,
-                               tracker_cfg=(TRK["max_age"], TRK["min_hits"], TRK["max_iou_distance"]), tracks=tracks,
-                               schedule=args.schedule) for k in range(N_SETS)]
-        side3 = torch.cuda.Stream()
-        side3.wait_stream(torch.cuda.current_stream())
-        p_graphs = []
-        with torch.cuda.stream(side3):
-            for k in range(N_SETS):
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=side3):
-                    h.tick(p_plans[k])
-                p_graphs.append(gr)
-        torch.cuda.current_stream().wait_stream(side3)
-        pads_value = timed_variant(lambda k: p_graphs[k % N_SETS].replay())
+        p_graphs, _ = _capture(torch, h, make_plans(fmt=_native.OUT_F32_RGB_NCHW | _native.OUT_FLAG_PADS_VALID))
+        pads_ms, _ = windows(lambda k: p_graphs[k % N_SETS].replay(), 5)
         h.poll_status()
-    # informational, N > 1: BASELINE.json's deployment shape -- 32 streams IN TOTAL, 32 / N per GPU (strong scaling).
-    # The kernels are latency-bound at 4 streams per launch, so this is far from N x the single-GPU number.
-    strong_value = None
-    if world > 1 and STREAMS % world == 0 and graphs is not None:
+    # BASELINE.json's deployment shape: 32 streams IN TOTAL, 32 / N per GPU (strong scaling); at N = 1 this is the
+    # headline itself.  One tick of 32 / N streams per GPU, same kernels, same graph replay.
+    strong = None
+    if STREAMS % world == 0:
         m = STREAMS // world
-        s_dets, s_tracks = h.alloc_dets(m), h.alloc_tracks(m)
-        s_slots = _native._int_array([STREAMS + i for i in range(m)])
-        s_metas = (_native.Letterbox * m)(*[metas[i] for i in range(m)])
-        s_plans = [h.plan_tick(frames=_native.FrameBatch(list(frame_sets[k][:m].unbind(0))), net_out=net_in[:m], dst_hw=IN_HW,
-                               fmt=_native.OUT_F32_RGB_NCHW, head=head_sets[k][:m], metas=s_metas, conf_thr=CONF,
-                               iou_thr=IOU, filter_conf=CONF, dets=s_dets, slots=s_slots,
-                               tracker_cfg=(TRK["max_age"], TRK["min_hits"], TRK["max_iou_distance"]), tracks=s_tracks,
-                               schedule=args.schedule) for k in range(N_SETS)]
-        side2 = torch.cuda.Stream()
-        side2.wait_stream(torch.cuda.current_stream())
-        s_graphs = []
-        with torch.cuda.stream(side2):
-            for k in range(N_SETS):
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=side2):
-                    h.tick(s_plans[k])
-                s_graphs.append(gr)
-        torch.cuda.current_stream().wait_stream(side2)
-        strong_value = timed_variant(lambda k: s_graphs[k % N_SETS].replay()) / world  # m * world = 32 frames per step
-        h.poll_status()
-    if world > 1:
-        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
-    value = world * STREAMS * args.steps / (ms * 1e-3)
+        if world == 1:
+            strong = {"streams_total": STREAMS, "streams_per_gpu": m, "value": round(value, 1), "unit": "frames/s",
+                      "ms_per_tick": round(ms / K, 5)}
+        elif graphs is not None:
+            s_dets, s_tracks = h.alloc_dets(m), h.alloc_tracks(m)
+            s_slots = _native._int_array([STREAMS + i for i in range(m)])
+            s_metas = (_native.Letterbox * m)(*[metas[i] for i in range(m)])
+            s_graphs, _ = _capture(torch, h, make_plans(m=m, p_dets=s_dets, p_tracks=s_tracks, p_slots=s_slots,
+                                                        p_metas=s_metas))
+            s_ms, s_stats = windows(lambda k: s_graphs[k % N_SETS].replay(), WINDOWS)
+            strong = {"streams_total": STREAMS, "streams_per_gpu": m, "value": round(STREAMS * K / (s_ms * 1e-3), 1),
+                      "unit": "frames/s", "ms_per_tick": round(s_ms / K, 5),
+                      "per_rank_ms_per_tick": s_stats["per_rank_ms_per_step"]}
+            h.poll_status()
 
     # ---- end to end through the public API with host buffers ---------------------------------
     streams = [StreamConfig(name=f"r{rank}s{s}") for s in range(STREAMS)]
@@ -452,14 +513,12 @@ def run_gpu(args) -> None:
 
     eng = HotPathEngine(streams, DetectorConfig(confidence_threshold=CONF, iou_threshold=IOU),
                         TrackerConfig(**TRK), infer=infer, handle=h, input_hw=IN_HW, depth=2)
-    eng.tracker._slots = {st.name: STREAMS + s for s, st in enumerate(streams)}
-    e2e_steps = max(3, min(args.steps, 100))
+    e2e_steps = max(3, min(K, 100))
 
     def e2e_run(objects: bool):
         """`e2e_steps` ticks, tick k+1 submitted before tick k is collected (uploads overlap the
         host-side handling of results).  Every tick's H2D and D2H copies are inside the timed region."""
-        for s in range(STREAMS):
-            h.tracker_reset(STREAMS + s)
+        eng.reset_tracks()
         checksum = 0
         for k in range(3):
             tick_no[0] = k
@@ -479,10 +538,7 @@ def run_gpu(args) -> None:
             checksum += (len(r.tracks) + len(r.detections)) if objects else (r.n_tracks + r.n_detections)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        if world > 1:
-            tmax = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            dt = float(tmax.item())
+        dt = float(np.max(gather([dt])))
         assert checksum > 0
         return world * STREAMS * e2e_steps / dt, dt, (eng.stager.bytes_moved - moved0) // e2e_steps
 
@@ -491,8 +547,24 @@ def run_gpu(args) -> None:
     heads_from_host[0] = False
     e2e_dev_heads, _, _ = e2e_run(objects=False)
     ctx0 = eng._ctxs[0]
-    d2h = int(ctx0.dets["_flat"].numel() + ctx0.tracks["_flat"].numel())
+    d2h = int(ctx0.host_dets_t["_flat"].numel() * ctx0.host_dets_t["_flat"].element_size()
+              + ctx0.host_tracks_t["_flat"].numel() * ctx0.host_tracks_t["_flat"].element_size())
     h.poll_status()
+    h.close()
+
+    # ---- the other BASELINE.json configurations, driver-run (N = 1 only; a few steps each) ---------------
+    configs_block = None
+    used_graphs = graphs is not None
+    if world == 1 and not args.no_configs:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_configs
+
+            del frame_sets, head_sets, nets, batches, plans, graphs
+            torch.cuda.empty_cache()
+            configs_block = bench_configs.run_all(("1", "2", "5", "4", "D", "P"), steps=max(10, min(K, 30)))
+        except Exception as exc:  # pragma: no cover - informational block: never lose the headline line over it
+            configs_block = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -501,20 +573,70 @@ def run_gpu(args) -> None:
                 peak, peak_src = float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy, burst)"
         else:
             peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        achieved = LETTERBOX_BYTES_PER_FRAME * STREAMS / (k1_ms * 1e-3) / 1e9
-        traffic = None
+        traffic = {}
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as fh:
-                traffic = json.load(fh).get("k_letterbox_dram_bytes_per_launch")
-        line = {"metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+                traffic = json.load(fh)
+
+        def roof(kernel, bytes_per_launch, ms_launch, traffic_key, note=None):
+            ach = bytes_per_launch / (ms_launch * 1e-3) / 1e9
+            tr = traffic.get(traffic_key)
+            r = {"bound": "hbm", "kernel": kernel, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                 "frac": round(ach / peak, 4), "traffic": tr,
+                 "frac_dram": round(tr / (ms_launch * 1e-3) / 1e9 / peak, 4) if tr else None,
+                 "kernel_ms": round(ms_launch, 5), "algorithmic_bytes_per_launch": int(bytes_per_launch),
+                 "samples": KERNEL_SAMPLES}
+            if note:
+                r["note"] = note
+            return r
+
+        k1_ms = kern_ms["preprocess"]
+        roofline = roof("k_letterbox<F32_RGB_NCHW> (32 x 1080p per launch)", LETTERBOX_BYTES_PER_FRAME * STREAMS, k1_ms,
+                        "k_letterbox_dram_bytes_per_launch")
+        roofline["peak_source"] = peak_src
+        roofline["how"] = ("median of %d eager ticks, one CUDA-event pair around the launch on the stream it is launched on "
+                           "(b200va_set_profiling); `traffic` = dram__bytes_read + dram__bytes_write of one launch from the "
+                           "ncu --set full capture summarised in profiles/ (static, not re-measured in this run); frac_dram = "
+                           "traffic / kernel_ms / peak" % KERNEL_SAMPLES)
+        roofline_kernels = [roofline]
+        if "decode" in kern_ms:
+            roofline_kernels.append(roof("k_decode_cm<4> (32 heads [84, 8400] per launch, read-only)",
+                                         HEAD_BYTES_PER_FRAME * STREAMS, kern_ms["decode"], "k_decode_dram_bytes_per_launch",
+                                         "a read-only kernel: tools/readbw.cu measures 4.65 TB/s as this GPU's read-only "
+                                         "ceiling (profiles/r2_readbw.log), 0.72 of the copy peak used here"))
+        for c in configs_block if isinstance(configs_block, list) else []:
+            if str(c.get("config", "")).startswith("4:"):
+                roofline_kernels.append(roof("k_motion_tile + ROI (32 x 4K per launch)", c["motion_algorithmic_bytes"],
+                                             c["motion(+roi)"], "k_motion_tile_dram_bytes_per_launch"))
+                roofline_kernels.append(roof("k_letterbox<F32_RGB_NCHW, masked> (32 x 4K + ROI per launch)",
+                                             c["preprocess_algorithmic_bytes"], c["preprocess(+roi)"],
+                                             "k_letterbox_4k_masked_dram_bytes_per_launch"))
+            if str(c.get("config", "")).startswith("a14"):
+                roofline_kernels.append(roof("k_dfl_decode (32 raw heads [144, 8400] per launch)", c["algorithmic_bytes"],
+                                             c["dfl_decode"], "k_dfl_decode_dram_bytes_per_launch"))
+        tick_bytes = (LETTERBOX_BYTES_PER_FRAME + HEAD_BYTES_PER_FRAME) * STREAMS
+
+        def fps(ms_window):
+            return round(world * STREAMS * K / (ms_window * 1e-3), 1)
+
+        sched = {0: "serial", 1: "letterbox after decode, overlapping NMS + tracker (b200va_tick)",
+                 2: "letterbox overlapping decode + NMS + tracker (b200va_tick)",
+                 3: "letterbox launched beside the decode kernel (programmatic dependent launch), NMS + tracker "
+                    "on the second stream (b200va_tick)",
+                 4: "software-pipelined b200va_tick: decode + letterbox of step k beside NMS + tracker of step k-1"}
+        line = {"metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": K,
+                "warmup": warm, "ms_per_step": round(ms / K, 5), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
                 "config": workload_config(world),
-                "roofline": {"bound": "hbm", "kernel": "k_letterbox<F32_RGB_NCHW> (32 x 1080p per launch)",
-                             "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                             "traffic": traffic, "kernel_ms": round(k1_ms, 4),
-                             "algorithmic_bytes_per_launch": LETTERBOX_BYTES_PER_FRAME * STREAMS, "peak_source": peak_src},
+                "timing": dict(win_stats, how="CUDA events around each K-step window, barrier + synchronize on both sides, "
+                                              "max over ranks per window, median over the windows"),
+                "parity_checked": parity is not None, "parity": parity,
+                "roofline": roofline, "roofline_kernels": roofline_kernels,
+                "tick_hbm": {"algorithmic_bytes_per_tick": tick_bytes,
+                             "floor_ms_at_peak": round(tick_bytes / peak / 1e6, 5),
+                             "frac": round(tick_bytes / peak / 1e6 / (ms / K), 4)},
+                "kernel_ms": {k_: round(v, 5) for k_, v in kern_ms.items()},
                 "e2e": {"value": round(e2e_value, 1), "unit": "frames/s",
                         "h2d_bytes_per_step": int(frame_bytes_per_step + STREAMS * C * A * 4), "d2h_bytes_per_step": d2h,
                         "h2d_frame_bytes_per_step": int(frame_bytes_per_step), "h2d_head_bytes_per_step": STREAMS * C * A * 4,
@@ -527,22 +649,19 @@ def run_gpu(args) -> None:
                                "pinned host memory every step (conservative: a GPU-resident detector would leave "
                                "them on the device, see value_heads_resident_on_device); value_with_python_objects "
                                "additionally builds every Detection / Track object"},
-                "gpu_launches": int(launches), "launches_per_step": launches / max(args.steps, 1),
-                "breakdown_ms": breakdown,
-                "schedule": {0: "serial", 1: "letterbox after decode, overlapping NMS + tracker (b200va_tick)",
-                             2: "letterbox overlapping decode + NMS + tracker (b200va_tick)",
-                             3: "letterbox launched beside the decode kernel (programmatic dependent launch), NMS + tracker "
-                                "on the second stream (b200va_tick)",
-                             4: "software-pipelined b200va_tick: decode + letterbox of step k beside NMS + tracker of step k-1"}[args.schedule],
-                "launch": ("CUDA graph replay of the prepared b200va_tick (one graph per input set); every "
-                           f"{SAMPLE_EVERY}th step is launched eagerly with an event pair around the letterbox kernel"
-                           if graphs is not None else "eager b200va_tick every step, event pair around the letterbox kernel"),
-                "letterbox_samples": len(kev),
-                "value_eager_tick": round(eager_value, 1), "value_three_serial_calls": round(serial_value, 1),
-                "value_pad_rows_written_once": round(pads_value, 1) if pads_value is not None else None,
-                "value_32_streams_total_strong_scaling": round(strong_value, 1) if strong_value is not None else None,
-                "clocks": clocks.summary(), "tracks_alive": n_tracks,
-                "cpu_affinity": (f"rank 0 pinned to {len(numa_cores)} NUMA-local cores" if numa_cores else "unchanged")}
+                "gpu_launches": int(round(launches_per_step * K)), "launches_per_step": launches_per_step,
+                "schedule": sched[args.schedule],
+                "launch": ("CUDA graph replay of the prepared b200va_tick (one graph per input set)"
+                           if used_graphs else "eager b200va_tick every step"),
+                "value_eager_tick": fps(eager_ms), "value_three_serial_calls": fps(serial_ms),
+                "value_pad_rows_written_once": fps(pads_ms) if pads_ms is not None else None,
+                "strong_scaling_32_streams_total": strong,
+                "clocks": dict(load_clocks.summary(), during_timed_windows=clocks.summary(),
+                               how="sm_mhz: median of 2 ms NVML polls while the same graph replay loop runs for 0.25 s right "
+                                   "after the timed windows; during_timed_windows: 10 ms polls while the windows ran"),
+                "tracks_alive": n_tracks,
+                "cpu_affinity": (f"rank 0 pinned to {len(numa_cores)} NUMA-local cores" if numa_cores else "unchanged"),
+                "configs": configs_block}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_single_core_sample()
         else:
@@ -564,6 +683,8 @@ def main() -> None:
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-bind", action="store_true", help="N > 1: do not pin each rank to its GPU's NUMA-local cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the single-core CPU sample")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` block (BASELINE.json configs 1, 2, 4, 5)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of two ticks before the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

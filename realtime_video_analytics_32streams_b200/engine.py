@@ -81,7 +81,7 @@ class FrameResult:
     ``dt`` the reference feeds to ``health.update_success`` (pipeline.py:145, 200-201)."""
 
     __slots__ = ("stream_name", "frame_id", "processed", "skip_reason", "n_detections", "n_tracks", "_ctx", "_pos",
-                 "_dets", "_tracks", "_gen", "device_ms")
+                 "_dets", "_tracks", "_gen", "device_ms", "adaptive_state")
 
     def __init__(self, stream_name, frame_id, processed, skip_reason, n_det, n_trk, ctx, pos, device_ms=None):
         self.stream_name, self.frame_id, self.processed, self.skip_reason = stream_name, frame_id, processed, skip_reason
@@ -89,6 +89,7 @@ class FrameResult:
         self._ctx, self._pos, self._gen = ctx, pos, ctx.gen
         self._dets = self._tracks = None
         self.device_ms = device_ms
+        self.adaptive_state = None  # (process_every, idle_frames) after this frame (pipeline.py:242-262), set by collect()
 
     def _live_ctx(self):
         if self._ctx.gen != self._gen:
@@ -198,6 +199,11 @@ class HotPathEngine:
         # a tick's gates depend on the previous tick's results for these features
         self.sequential = any(getattr(s, "motion_filter", False) or getattr(s, "adaptive_fps", False)
                               for s in self.streams)
+
+    def reset_tracks(self) -> None:
+        """Drop every stream's tracks (the id counter keeps running, like a reference tracker that lost its streams)."""
+        for st in self.streams:
+            self.tracker.reset(st.name)
 
     # --------------------------------------------------------------------------------------
     def _frame_batch(self, frames, masks):
@@ -370,4 +376,5 @@ class HotPathEngine:
             n_trk = int(trk_counts[pos])
             ctx.states[k].adjust(n_det, n_trk)
             results[k] = FrameResult(ctx.names[k], ctx.ids[k], processed, ctx.skip_reason[k], n_det, n_trk, ctx, pos, phase_ms)
+            results[k].adaptive_state = (ctx.states[k].process_every, ctx.states[k].idle_frames)
         return results  # type: ignore[return-value]

@@ -5,7 +5,9 @@ detector.py:54-96) and hard-codes ``IouTracker`` (pipeline.py:452).  ``register_
 patches those three places at import time so that a YAML with ``backend: b200`` (or
 ``b200_ultralytics``: the Ultralytics pre / post semantics of detector.py:106-179) and
 ``tracker.type: b200_iou`` runs this package's kernels behind the reference's own pipeline, and
-swaps the frame-filter functions the pipeline imported by name (pipeline.py:33).
+swaps the frame-filter functions the pipeline imported by name (pipeline.py:33).  With ``batched=True`` it also
+installs the tick collector (``collector.py``): the reference's per-stream workers then share ONE batched
+``HotPathEngine.tick`` instead of calling the kernels 32 times at batch 1 (pipeline.py:118-212, 460-515).
 INTEGRATION.md shows the equivalent two-line source change for maintainers who prefer a patch.
 """
 
@@ -14,9 +16,13 @@ from __future__ import annotations
 from typing import Callable, Optional
 
 
-def register_with_reference(infer_factory: Optional[Callable] = None) -> None:
+def register_with_reference(infer_factory: Optional[Callable] = None, batched: bool = False,
+                            engine_factory: Optional[Callable] = None, max_wait_s: float = 0.010) -> None:
     """``infer_factory(config) -> callable`` builds the detector forward for a DetectorConfig
-    (e.g. loads the YOLO weights with PyTorch); it is required for ``backend: b200``."""
+    (e.g. loads the YOLO weights with PyTorch); it is required for ``backend: b200``.
+    ``batched=True``: all stream workers of a pipeline share one tick (``collector.install``); ``engine_factory(streams,
+    detector, pipeline_config)`` overrides the engine it drives (default: ``HotPathEngine`` on the detector's handle) and
+    ``max_wait_s`` bounds how long a tick waits for a late stream."""
     import realtime_analytics.config as rcfg  # the reference, must be importable
     import realtime_analytics.detector as rdet
     import realtime_analytics.pipeline as rpipe
@@ -64,3 +70,9 @@ def register_with_reference(infer_factory: Optional[Callable] = None) -> None:
     rpipe._ReferenceIouTracker = rpipe.IouTracker
     rpipe.IouTracker = _Tracker
     rpipe.apply_roi, rpipe.downsample, rpipe.MotionFilter = apply_roi, downsample, MotionFilter
+
+    # 4. one tick for all workers (pipeline.py:118-212, 460-515)
+    if batched:
+        from . import collector
+
+        collector.install(rpipe, engine_factory or collector.default_engine_factory, max_wait_s)

@@ -205,3 +205,10 @@ def test_registration_shim_wires_the_reference_factory():
     # the YAML authored for config 4 loads with the reference's own loader
     full = rcfg.load_config(os.path.join(REPO, "config", "pipeline-4k-roi.yaml"))
     assert full.detector.backend == "b200" and full.streams[0].motion_filter and len(full.streams[0].roi_polygons) == 2
+    # all 32 streams are spelled out, every one with its own hexagon + triangle, the motion gate and adaptive FPS
+    from realtime_video_analytics_32streams_b200 import synth
+
+    assert len(full.streams) == 32 and len({s.name for s in full.streams}) == 32
+    for i, s in enumerate(full.streams):
+        assert s.motion_filter and s.adaptive_fps and s.idle_frame_tolerance == 60 and s.min_target_fps == 5
+        assert [[tuple(p) for p in poly] for poly in s.roi_polygons] == synth.synth_polygons(4000 + i, 2160, 3840)
