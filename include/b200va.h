@@ -370,6 +370,8 @@ B200VA_API int b200va_postprocess_ultralytics(b200va_handle h, const float* head
  *           beside the decode's as soon as all of those are running (HBM sees the decode's reads and the letterbox's
  *           writes together, no kernel-to-kernel gap) -- while NMS + tracker run on the internal stream behind
  *           an event recorded after the decode.
+ *           5 = like 3, but the letterbox waits (griddepcontrol.wait) for the decode grid to drain before its first
+ *           load: back to back on the bus instead of side by side, without a launch gap in between.
  *           4 = software-pipelined: this call only DECODES its head (into one of two candidate sets) and letterboxes
  *           its frames; NMS + tracker of the head the PREVIOUS call decoded run beside them on the internal stream.
  *           The latency-bound chain decode -> NMS -> tracker, which bounds schedules 1-3, leaves the critical path.

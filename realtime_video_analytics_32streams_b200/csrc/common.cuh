@@ -68,10 +68,13 @@ struct b200va_ctx {
   // a programmatic dependent of the decode kernel (`pdl_preprocess`) and fills the SMs next to it
   cudaStream_t post_tail_stream = nullptr;
   bool pdl_preprocess = false;
+  bool pdl_preprocess_wait = false;  // ... and the letterbox waits for its primary's completion before its first load
   // ---- NMS variant selection: host-mapped statistic written by k_sort_nms ----
   int* nms_stats_host = nullptr;
   int* nms_stats_dev = nullptr;
   int nms_dense_ttl = 0;  // launches left on the grid variant after the last dense sighting
+  int trk_rows = 512;     // rows of the tracker's shared-memory working table (tracker_pick_smem_tracks)
+  int trk_rows_ttl = 0;   // launches left before trk_rows falls back to 512
   // ---- b200va_set_profiling: one timed event pair per phase ----
   bool profiling = false;
   cudaEvent_t prof_ev[B200VA_PHASE_COUNT][2] = {};
@@ -82,6 +85,8 @@ struct b200va_ctx {
     int fuse_post_track = 1;  // B200VA_FUSE_POST_TRACK=0: always launch NMS and tracker as two kernels
     int pdl = 1;              // B200VA_PDL=0: no programmatic dependent launches
     int uniform_carveout = 0; // B200VA_UNIFORM_CARVEOUT=1: every tick kernel prefers the all-shared-memory split
+    int post_carveout = -1;   // B200VA_POST_CARVEOUT=pct: preferred shared-memory carve-out of k_post_track (0: driver default)
+    int trk_smem_tracks = 0;  // B200VA_TRK_SMEM_TRACKS=n: fix the tracker's shared-memory table at n rows (tests)
   } tune;
   // ---- developer phase timing (only written by builds with -DB200VA_PHASE_TIMING) ----
   long long* dbg = nullptr;  // device int64[DBG_SLOTS]

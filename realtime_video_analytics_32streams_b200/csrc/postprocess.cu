@@ -1244,8 +1244,13 @@ int postprocess_configure(b200va_ctx* h) {
   const size_t smem = nms_smem_bytes(h->cfg.max_candidates);
   if (smem > 220 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_candidates %d needs %zu bytes of shared memory", h->cfg.max_candidates, smem);
   {
-    const size_t fused = std::max(smem, tracker_smem_bytes(h->cfg.max_tracks));
-    if (fused <= 200 * 1024) CUDA_TRY(h, cudaFuncSetAttribute(k_post_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused));
+    const size_t fused = std::min<size_t>(200 * 1024, std::max(smem, tracker_smem_bytes(h->cfg.max_tracks)));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_post_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused));
+    // k_post_track runs beside the letterbox in b200va_tick, and an SM only hosts kernels that agree on its L1 /
+    // shared-memory split (see prefer_max_shared): ask for the split the 1080p letterbox launch gets (164 KB, six
+    // 24.5 KB CTAs) instead of the one the driver would derive from this kernel's own occupancy
+    const int pct = h->tune.post_carveout >= 0 ? h->tune.post_carveout : 71;
+    if (pct > 0) CUDA_TRY(h, cudaFuncSetAttribute(k_post_track, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
   }
   CUDA_TRY(h, cudaFuncSetAttribute(k_sort_nms<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CUDA_TRY(h, cudaFuncSetAttribute(k_sort_nms<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1487,9 +1492,14 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
     const size_t nms_smem = nms_smem_bytes(h->cfg.max_candidates);
     const bool pdl = h->tune.pdl != 0 && !split_streams;  // across streams the event carries the dependency
     // sparse scene, one launch group, detection rows = this handle's tables: NMS + tracker in one 256-thread CTA
-    const size_t fused_smem = std::max(nms_smem, tracker_smem_bytes(h->cfg.max_tracks));
-    if (fuse && fuse->stream_slots && fuse->cfg && !dense && h->tune.fuse_post_track != 0 && base == 0 && n == batch && fuse->batch == batch &&
-        fuse->max_dets == h->cfg.max_dets && fused_smem <= 200 * 1024) {
+    // (the tracker's working table gets tracker_pick_smem_tracks rows of shared memory, 512 in a sparse scene: the CTA
+    // leaves most of its SM to the letterbox CTAs it runs beside)
+    const bool fusable = fuse && fuse->stream_slots && fuse->cfg && !dense && h->tune.fuse_post_track != 0 && base == 0 &&
+                         n == batch && fuse->batch == batch && fuse->max_dets == h->cfg.max_dets;
+    const int trk_rows = fusable ? tracker_pick_smem_tracks(h, st) : 0;
+    const size_t nms_plain = nms_base_bytes(h->cfg.max_candidates);  // the variants without the kept-box grid
+    const size_t fused_smem = std::max(nms_plain, tracker_smem_bytes(trk_rows));
+    if (fusable && fused_smem <= 200 * 1024) {
       TrkParams t;
       memset(&t, 0, sizeof(t));
       t.f_box = out->bbox_xyxy;
@@ -1500,12 +1510,13 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
       const int rc = tracker_fill_params(h, t, fuse->stream_slots, fuse->batch, fuse->det_scale, fuse->skip, fuse->cfg,
                                          fuse->id_base, fuse->out, fuse->new_counts);
       if (rc != B200VA_OK) return rc;
+      t.smem_tracks = trk_rows;
       CUDA_TRY(h, launch_pdl(k_post_track, dim3(n), dim3(kNmsThreadsSmall), fused_smem, st, pdl, q, t));
       fuse->done = true;
     } else if (dense && q.grid_off) {
       CUDA_TRY(h, launch_pdl(k_sort_nms<true>, dim3(n), dim3(kNmsThreads), nms_smem, st, pdl, q));
     } else {
-      CUDA_TRY(h, launch_pdl(k_sort_nms<false>, dim3(n), dim3(kNmsThreads), nms_smem, st, pdl, q));
+      CUDA_TRY(h, launch_pdl(k_sort_nms<false>, dim3(n), dim3(kNmsThreads), nms_plain, st, pdl, q));
     }
     LAUNCH_CHECK(h);
     if (fuse) fuse->tail_on_side = split_streams;
@@ -1550,16 +1561,20 @@ int postprocess_run_pending(b200va_handle h, void* stream) {
     if (dense && cap == cudaStreamCaptureStatusNone) --h->nms_dense_ttl;
   }
   const size_t nms_smem = nms_smem_bytes(h->cfg.max_candidates);
-  const size_t fused_smem = std::max(nms_smem, tracker_smem_bytes(h->cfg.max_tracks));
+  const bool fusable = pc->has_trk && !dense && h->tune.fuse_post_track != 0 && pc->t.max_dets == h->cfg.max_dets;
+  const int trk_rows = fusable ? tracker_pick_smem_tracks(h, st) : 0;
+  const size_t nms_plain = nms_base_bytes(h->cfg.max_candidates);
+  const size_t fused_smem = std::max(nms_plain, tracker_smem_bytes(trk_rows));
   {
     PhaseScope phase(h, B200VA_PHASE_NMS, st);
-    if (pc->has_trk && !dense && h->tune.fuse_post_track != 0 && pc->t.max_dets == h->cfg.max_dets && fused_smem <= 200 * 1024) {
+    if (fusable && fused_smem <= 200 * 1024) {
+      pc->t.smem_tracks = trk_rows;
       CUDA_TRY(h, launch_pdl(k_post_track, dim3(n), dim3(kNmsThreadsSmall), fused_smem, st, false, pc->q, pc->t));
       LAUNCH_CHECK(h);
       return B200VA_OK;
     }
     if (dense && pc->q.grid_off) CUDA_TRY(h, launch_pdl(k_sort_nms<true>, dim3(n), dim3(kNmsThreads), nms_smem, st, false, pc->q));
-    else CUDA_TRY(h, launch_pdl(k_sort_nms<false>, dim3(n), dim3(kNmsThreads), nms_smem, st, false, pc->q));
+    else CUDA_TRY(h, launch_pdl(k_sort_nms<false>, dim3(n), dim3(kNmsThreads), nms_plain, st, false, pc->q));
     LAUNCH_CHECK(h);
   }
   if (pc->has_trk) return tracker_launch_params(h, pc->t, n, st);

@@ -42,6 +42,7 @@ struct PreParams {
   int rows_per_stage;  // 1 when no frame of the launch ever needs the second source row
   int keep_pad_rows;   // B200VA_OUT_FLAG_PADS_VALID: full-width pad rows of `out` already hold the pad value
   long long* dbg;      // timing builds: timeline stamps
+  int pdl_wait;        // launched as a programmatic dependent that must not touch HBM before its primary is done (tick schedule 5)
 };
 static_assert(sizeof(PreParams) <= 4000, "kernel parameter block too large");
 
@@ -208,6 +209,9 @@ __global__ void __launch_bounds__(kThreads) k_letterbox(const __grid_constant__ 
     mbar_fence_init();
   }
   __syncthreads();
+  // tick schedule 5: this grid was launched while the decode kernel still runs; its CTAs are resident and set up, and
+  // their first bulk copy goes out the moment that grid has drained (no launch latency between the two HBM kernels)
+  if (p.pdl_wait) griddep_wait();
 
   // one elected thread feeds the TMA engine: whole source rows, one bulk copy each
   auto issue = [&](int i, int s) {
@@ -640,6 +644,7 @@ static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* 
       }
       p.tabs = h->taps->arena;
       p.dbg = h->dbg;
+      p.pdl_wait = (h->pdl_preprocess && h->pdl_preprocess_wait) ? 1 : 0;
       p.out = out;
       p.dst_h = dst_h;
       p.dst_w = dst_w;

@@ -11,7 +11,7 @@ extern "C" int b200va_tick(b200va_handle h, const b200va_tick_args* a, void* str
   if (!h || !a) return B200VA_ERR_INVALID;
   std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
-  REQUIRE(h, a->schedule >= 0 && a->schedule <= 4, "unknown schedule %d", a->schedule);
+  REQUIRE(h, a->schedule >= 0 && a->schedule <= 5, "unknown schedule %d", a->schedule);
   cudaStream_t main_st = (cudaStream_t)stream;
   const bool has_pre = a->frames != nullptr && a->batch > 0;
   const bool has_post = a->head != nullptr && a->head_batch > 0;
@@ -66,7 +66,10 @@ extern "C" int b200va_tick(b200va_handle h, const b200va_tick_args* a, void* str
   // dependent that never waits: its CTAs start as soon as SM resources allow (see prefer_max_shared in common.cuh for
   // why that is only the decode's tail today); NMS + tracker move to the side stream behind an event recorded right
   // after the decode.
-  const bool sched3 = a->schedule == 3 && fork && has_post && a->head_batch <= B200VA_LAUNCH_FRAMES;
+  // schedule 5: the same launch, but the letterbox executes griddepcontrol.wait before its first load: the two HBM
+  // kernels never share the bus (their mix is slower than their sequence, tools/membw.cu) and no launch latency
+  // separates them.
+  const bool sched3 = (a->schedule == 3 || a->schedule == 5) && fork && has_post && a->head_batch <= B200VA_LAUNCH_FRAMES;
   cudaStream_t post_st = (fork && !sched3) ? h->side_stream : main_st;
   if (fork && !sched3) {
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, main_st));
@@ -93,6 +96,7 @@ extern "C" int b200va_tick(b200va_handle h, const b200va_tick_args* a, void* str
   const bool joined = fork && post_st == h->side_stream;
   if (joined) note(cudaEventRecord(h->ev_join, post_st), "cudaEventRecord(join)");
   h->pdl_preprocess = sched3 && tail_on_side;
+  h->pdl_preprocess_wait = a->schedule == 5;
   if (rc == B200VA_OK && has_pre) {
     if (a->ev_pre_begin) note(cudaEventRecord((cudaEvent_t)a->ev_pre_begin, main_st), "cudaEventRecord(pre_begin)");
     if (rc == B200VA_OK)
@@ -101,6 +105,7 @@ extern "C" int b200va_tick(b200va_handle h, const b200va_tick_args* a, void* str
     if (rc == B200VA_OK && a->ev_pre_end) note(cudaEventRecord((cudaEvent_t)a->ev_pre_end, main_st), "cudaEventRecord(pre_end)");
   }
   h->pdl_preprocess = false;
+  h->pdl_preprocess_wait = false;
   if (joined) note(cudaStreamWaitEvent(main_st, h->ev_join, 0), "cudaStreamWaitEvent(join)");
   return rc;
 }

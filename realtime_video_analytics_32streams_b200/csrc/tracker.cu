@@ -53,6 +53,9 @@ int tracker_state_create(b200va_ctx* h) {
   size_t o_next = take(8);
   size_t o_ticket = take(4);
   size_t o_new = take((size_t)B200VA_MAX_BATCH * 4);
+  size_t o_need = take(4);
+  const size_t scratch_stride = (tracker_smem_bytes(h->cfg.max_tracks) + 255) & ~(size_t)255;
+  size_t o_scratch = take((size_t)std::min(h->cfg.max_batch, B200VA_MAX_BATCH) * scratch_stride);
   CUDA_TRY(h, cudaMalloc(&S->base, bytes));
   CUDA_TRY(h, cudaMemset(S->base, 0, bytes));
   uint8_t* b = (uint8_t*)S->base;
@@ -70,6 +73,9 @@ int tracker_state_create(b200va_ctx* h) {
   S->next_id = (long long*)(b + o_next);
   S->ticket = (uint32_t*)(b + o_ticket);
   S->new_count = (int32_t*)(b + o_new);
+  S->need_max = (int32_t*)(b + o_need);
+  S->scratch = b + o_scratch;
+  S->scratch_stride = scratch_stride;
   const long long one = 1;  // itertools.count(1), tracker.py:47
   CUDA_TRY(h, cudaMemcpy(S->next_id, &one, 8, cudaMemcpyHostToDevice));
   const size_t smem = tracker_smem_bytes(h->cfg.max_tracks);
@@ -127,7 +133,32 @@ int tracker_fill_params(b200va_ctx* h, TrkParams& p, const int* stream_slots, in
   p.o_new = new_counts;
   p.flags = h->status_flags;
   p.dbg = h->dbg;
+  p.stats = h->nms_stats_dev;
   return B200VA_OK;
+}
+
+// Rows of the shared-memory working table for the next tracker launch.  512 rows (24 KB) unless a recent launch
+// reported a stream that needed more (TrkParams::stats, posted by the launch's last CTA): then twice that need, rounded
+// up to 1024 / 2048 / max_tracks, for the next 64 launches.  A stream that still does not fit runs from its global
+// scratch -- the choice only moves time, never results.  Under stream capture the size is frozen into the graph.
+int tracker_pick_smem_tracks(b200va_ctx* h, cudaStream_t st) {
+  const int cap = h->cfg.max_tracks;
+  if (h->tune.trk_smem_tracks > 0) return std::min(cap, h->tune.trk_smem_tracks);  // B200VA_TRK_SMEM_TRACKS (tests)
+  if (h->nms_stats_host) {
+    cudaStreamCaptureStatus capt = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &capt);
+    const int need = ((volatile int*)h->nms_stats_host)[1];
+    if (need > 0) {
+      int rows = 512;
+      while (rows < 2 * need && rows < cap) rows <<= 1;
+      if (rows >= h->trk_rows || h->trk_rows_ttl <= 0) h->trk_rows = rows;
+      h->trk_rows_ttl = 64;
+      if (capt == cudaStreamCaptureStatusNone) ((volatile int*)h->nms_stats_host)[1] = 0;
+    } else if (h->trk_rows_ttl > 0 && capt == cudaStreamCaptureStatusNone) {
+      if (--h->trk_rows_ttl == 0) h->trk_rows = 512;
+    }
+  }
+  return std::min(cap, std::max(h->trk_rows, 512));
 }
 
 static int tracker_launch(b200va_ctx* h, TrkParams& p, const int* stream_slots, int batch, const double* det_scale,
@@ -138,16 +169,19 @@ static int tracker_launch(b200va_ctx* h, TrkParams& p, const int* stream_slots, 
   PhaseScope phase(h, B200VA_PHASE_TRACKER, st);
   // dense scenes (the post-process saw more than 256 candidates in a frame lately) are worth a CTA that owns its SM
   const int width = h->nms_dense_ttl > 0 ? kTrkThreadsMax : kTrkThreadsWide;
-  CUDA_TRY(h, launch_pdl(k_tracker, dim3(batch), dim3(width), tracker_smem_bytes(h->cfg.max_tracks), st, h->tune.pdl != 0, p));
+  p.smem_tracks = tracker_pick_smem_tracks(h, st);
+  CUDA_TRY(h, launch_pdl(k_tracker, dim3(batch), dim3(width), tracker_smem_bytes(p.smem_tracks), st, h->tune.pdl != 0, p));
   LAUNCH_CHECK(h);
   return B200VA_OK;
 }
 
 // launch k_tracker for parameters filled earlier (schedule 4 of b200va_tick)
-int tracker_launch_params(b200va_ctx* h, const TrkParams& p, int batch, cudaStream_t st) {
+int tracker_launch_params(b200va_ctx* h, const TrkParams& p0, int batch, cudaStream_t st) {
   PhaseScope phase(h, B200VA_PHASE_TRACKER, st);
   const int width = h->nms_dense_ttl > 0 ? kTrkThreadsMax : kTrkThreadsWide;
-  CUDA_TRY(h, launch_pdl(k_tracker, dim3(batch), dim3(width), tracker_smem_bytes(h->cfg.max_tracks), st, h->tune.pdl != 0, p));
+  TrkParams p = p0;
+  p.smem_tracks = tracker_pick_smem_tracks(h, st);
+  CUDA_TRY(h, launch_pdl(k_tracker, dim3(batch), dim3(width), tracker_smem_bytes(p.smem_tracks), st, h->tune.pdl != 0, p));
   LAUNCH_CHECK(h);
   return B200VA_OK;
 }

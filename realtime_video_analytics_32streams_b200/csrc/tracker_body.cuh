@@ -17,6 +17,9 @@ struct TrackerState {
   long long* next_id; // shared counter
   uint32_t* ticket;   // last-CTA election
   int32_t* new_count; // [max_batch] scratch
+  int32_t* need_max;  // largest table a stream of the running launch needed (live tracks + detections)
+  uint8_t* scratch;   // [max_batch][scratch_stride]: the working table of a stream that does not fit the launch's shared memory
+  size_t scratch_stride;
   void* base = nullptr;
 };
 
@@ -49,6 +52,13 @@ struct TrkParams {
   int o_rows;  // rows per stream of the output arrays
   int32_t* flags;
   long long* dbg;
+  // The working table (boxes, classes, hits, claims, last detection: 46 bytes per track) of a stream lives in shared
+  // memory when `live tracks + detections <= smem_tracks`, in the stream's global scratch otherwise (same code, exact,
+  // slower).  The launch sizes its dynamic shared memory for smem_tracks, not for max_tracks: a CTA that asks for
+  // 188 KB closes its SM to the letterbox CTAs it runs beside in b200va_tick (measured: 32 x 1080p letterbox 36 us
+  // alone, 41.5 us beside 32 such CTAs).  The host picks smem_tracks from what earlier launches needed (`stats`).
+  int smem_tracks;
+  int* stats;  // host-mapped words (b200va_ctx::nms_stats_dev): [1] = largest need of the last launch, posted by its last CTA
 };
 
 namespace {
@@ -140,17 +150,50 @@ __device__ __forceinline__ void warp_argmax(double& best, int& best_t) {
 //   A chunk in which some detection has more than kCand candidates falls back to the plain
 //   sequential scan (exact, slower).  Nothing in the sequential parts touches global memory:
 //   confidence, age and id of a touched track are derived from last_det[] at write-back.
-__device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi, uint8_t* const smem_raw) {
-  double* sbox = reinterpret_cast<double*>(smem_raw);                            // [max_tracks][4]
-  int32_t* scls = reinterpret_cast<int32_t*>(sbox + (size_t)p.max_tracks * 4);   // [max_tracks]
-  int32_t* shits = scls + p.max_tracks;                                          // [max_tracks]
-  int32_t* aux = shits + p.max_tracks;                                           // [max_tracks + kDetChunk] claims, then phase-B state
-  int16_t* last_det = reinterpret_cast<int16_t*>(aux + p.max_tracks + kDetChunk);  // [max_tracks] detection holding the track's box now, -1 untouched
-  __shared__ DetStage sd;
-  __shared__ Cand c_trk[kDetChunk][kCand], c_det[kDetChunk][kCand];
-  __shared__ int n_trk[kDetChunk], n_det[kDetChunk], key[kDetChunk], conflicted[kDetChunk], clist[kDetChunk];
-  __shared__ int s_T, s_new, s_is_last, s_fallback, s_nconf;
-  __shared__ int wsum[kTrkThreadsMax / 32];
+// TAB_GLOBAL only tells the two instantiations apart: `tab` is shared memory in one and global memory in the other, and
+// the compiler specialises the loads and stores of each inlined copy from the pointer's provenance.
+struct TrkShared {
+  DetStage sd;
+  Cand c_trk[kDetChunk][kCand], c_det[kDetChunk][kCand];
+  int n_trk[kDetChunk], n_det[kDetChunk], key[kDetChunk], conflicted[kDetChunk], clist[kDetChunk];
+  int s_T, s_new, s_is_last, s_fallback, s_nconf;
+  int wsum[kTrkThreadsMax / 32];
+  int warp_cnt[kTrkThreadsMax / 32];
+  int s_base;
+  int f_new[B200VA_MAX_BATCH], f_cur[B200VA_MAX_BATCH], f_cnt[B200VA_MAX_BATCH], f_pre[B200VA_MAX_BATCH];
+  long long f_next;
+};
+
+template <bool TAB_GLOBAL>
+__device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const int bi, uint8_t* const tab, const int cap,
+                                                    TrkShared& sh) {
+  double* sbox = reinterpret_cast<double*>(tab);                           // [cap][4]
+  int32_t* scls = reinterpret_cast<int32_t*>(sbox + (size_t)cap * 4);      // [cap]
+  int32_t* shits = scls + cap;                                             // [cap]
+  int32_t* aux = shits + cap;                                              // [cap + kDetChunk] claims, then phase-B state
+  int16_t* last_det = reinterpret_cast<int16_t*>(aux + cap + kDetChunk);   // [cap] detection holding the track's box now, -1 untouched
+  // one set of statically allocated shared variables for both instantiations (declared by tracker_stream)
+  DetStage& sd = sh.sd;
+  auto& c_trk = sh.c_trk;
+  auto& c_det = sh.c_det;
+  auto& n_trk = sh.n_trk;
+  auto& n_det = sh.n_det;
+  auto& key = sh.key;
+  auto& conflicted = sh.conflicted;
+  auto& clist = sh.clist;
+  int& s_T = sh.s_T;
+  int& s_new = sh.s_new;
+  int& s_is_last = sh.s_is_last;
+  int& s_fallback = sh.s_fallback;
+  int& s_nconf = sh.s_nconf;
+  auto& wsum = sh.wsum;
+  auto& warp_cnt = sh.warp_cnt;
+  int& s_base = sh.s_base;
+  auto& f_new = sh.f_new;
+  auto& f_cur = sh.f_cur;
+  auto& f_cnt = sh.f_cnt;
+  auto& f_pre = sh.f_pre;
+  long long& f_next = sh.f_next;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   PHASE_STAMP(p.dbg, 0);
@@ -430,8 +473,6 @@ __device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi,
   int32_t* age_n = S.age[nxt] + sb;
   int32_t* hits_n = S.hits[nxt] + sb;
   const size_t ob = (size_t)bi * p.o_rows;
-  __shared__ int warp_cnt[kTrkThreadsMax / 32];
-  __shared__ int s_base;
   if (tid == 0) s_base = 0;
   __syncthreads();
   for (int t0 = 0; t0 < T; t0 += kTrkThreads) {
@@ -512,8 +553,6 @@ __device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi,
   __threadfence();
   // every stream's new-track count, buffer index and length are fetched in parallel (one thread
   // per stream), prefix-summed in batch order, then only streams that created tracks are patched
-  __shared__ int f_new[B200VA_MAX_BATCH], f_cur[B200VA_MAX_BATCH], f_cnt[B200VA_MAX_BATCH], f_pre[B200VA_MAX_BATCH];
-  __shared__ long long f_next;
   if (tid < p.batch) {
     const int sl = p.slots[tid];
     f_new[tid] = ((volatile int32_t*)S.new_count)[tid];
@@ -530,6 +569,11 @@ __device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi,
     }
     *S.next_id = f_next + acc;
     *S.ticket = 0u;
+    // every stream of the launch has posted its need by now: report the largest to the host (one posted write; it is
+    // only a hint for the next launch's shared-memory size) and re-arm the device word
+    const int need = *((volatile int32_t*)S.need_max);
+    *S.need_max = 0;
+    if (p.stats && (need > 256 || need > p.smem_tracks)) ((volatile int*)p.stats)[1] = need;
   }
   __syncthreads();
   const long long next = f_next;
@@ -552,10 +596,23 @@ __device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi,
 }
 
 
+// One stream's tracker update.  The table never grows past `live tracks + detections` within the call, so that sum
+// decides (uniformly for the CTA) whether the working table fits the shared memory this launch was given.
+__device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi, uint8_t* const smem_raw) {
+  const int slot = p.slots[bi];
+  const int need = p.st.count[slot] + (p.skip[bi] ? 0 : min(p.d_count[bi], p.max_dets));
+  if (threadIdx.x == 0 && need > 256) atomicMax(p.st.need_max, need);
+  __shared__ TrkShared sh;
+  if (need <= p.smem_tracks) tracker_stream_impl<false>(p, bi, smem_raw, p.smem_tracks, sh);
+  else tracker_stream_impl<true>(p, bi, p.st.scratch + (size_t)bi * p.st.scratch_stride, p.max_tracks, sh);
+}
+
 }  // namespace
 
-// shared-memory bytes tracker_stream needs for a handle's max_tracks
-inline size_t tracker_smem_bytes(int max_tracks) { return (size_t)max_tracks * 46 + kDetChunk * 4 + 16; }
+// shared-memory bytes tracker_stream needs for a working table of `tracks` rows
+inline size_t tracker_smem_bytes(int tracks) { return (size_t)tracks * 46 + kDetChunk * 4 + 16; }
+// rows of the shared-memory working table the next launch gets (host side, tracker.cu)
+int tracker_pick_smem_tracks(b200va_ctx* h, cudaStream_t st);
 // validates the host arguments of a tracker update and fills the launch parameters (tracker.cu)
 int tracker_fill_params(b200va_ctx* h, TrkParams& p, const int* stream_slots, int batch, const double* det_scale,
                         const uint8_t* skip, const b200va_tracker_cfg* cfg, const int64_t* id_base,

@@ -15,6 +15,26 @@ from __future__ import annotations
 
 from typing import Callable, Optional
 
+_ORIGINALS = {}  # (module or class, attribute) -> the reference's own object, for unregister_from_reference
+
+
+def _patch(owner, name, value):
+    _ORIGINALS.setdefault((owner, name), getattr(owner, name))
+    setattr(owner, name, value)
+
+
+def unregister_from_reference() -> None:
+    """Put back everything ``register_with_reference`` replaced (tests; a process that wants the stock pipeline again)."""
+    for (owner, name), value in list(_ORIGINALS.items()):
+        setattr(owner, name, value)
+    _ORIGINALS.clear()
+    try:
+        import realtime_analytics.pipeline as rpipe
+
+        rpipe.StreamWorker._b200va_batched = False
+    except Exception:  # pragma: no cover
+        pass
+
 
 def register_with_reference(infer_factory: Optional[Callable] = None, batched: bool = False,
                             engine_factory: Optional[Callable] = None, max_wait_s: float = 0.010) -> None:
@@ -44,7 +64,7 @@ def register_with_reference(infer_factory: Optional[Callable] = None, batched: b
         else:
             orig_validate(self)
 
-    rcfg.DetectorConfig.validate = validate
+    _patch(rcfg.DetectorConfig, "validate", validate)
 
     # 2. dispatch (detector.py:54-96)
     orig_create = rdet.create_detector
@@ -57,8 +77,8 @@ def register_with_reference(infer_factory: Optional[Callable] = None, batched: b
             return cls(config, infer=infer_factory(config))
         return orig_create(config)
 
-    rdet.create_detector = create_detector
-    rpipe.create_detector = create_detector
+    _patch(rdet, "create_detector", create_detector)
+    _patch(rpipe, "create_detector", create_detector)
 
     # 3. tracker (pipeline.py:452) keyed on tracker.type, and the frame filters (pipeline.py:33)
     class _Tracker:
@@ -67,12 +87,18 @@ def register_with_reference(infer_factory: Optional[Callable] = None, batched: b
                 return B200IouTracker(config)
             return rpipe._ReferenceIouTracker(config)
 
-    rpipe._ReferenceIouTracker = rpipe.IouTracker
-    rpipe.IouTracker = _Tracker
-    rpipe.apply_roi, rpipe.downsample, rpipe.MotionFilter = apply_roi, downsample, MotionFilter
+    if not hasattr(rpipe, "_ReferenceIouTracker"):
+        rpipe._ReferenceIouTracker = rpipe.IouTracker
+    _patch(rpipe, "IouTracker", _Tracker)
+    _patch(rpipe, "apply_roi", apply_roi)
+    _patch(rpipe, "downsample", downsample)
+    _patch(rpipe, "MotionFilter", MotionFilter)
 
     # 4. one tick for all workers (pipeline.py:118-212, 460-515)
     if batched:
         from . import collector
 
+        for owner, name in ((rpipe.AnalyticsPipeline, "__init__"), (rpipe.AnalyticsPipeline, "wait_closed"),
+                            (rpipe.StreamWorker, "__init__"), (rpipe.StreamWorker, "run"), (rpipe.StreamWorker, "_process_packet")):
+            _ORIGINALS.setdefault((owner, name), getattr(owner, name))
         collector.install(rpipe, engine_factory or collector.default_engine_factory, max_wait_s)

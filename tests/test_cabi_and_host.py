@@ -186,7 +186,22 @@ def test_registration_shim_wires_the_reference_factory():
 
     with pytest.raises(rcfg.ConfigError):
         rcfg.DetectorConfig(backend="b200").validate()
-    register_with_reference(infer_factory=lambda cfg: (lambda x: x))
+    from realtime_video_analytics_32streams_b200.integration import unregister_from_reference
+
+    register_with_reference(infer_factory=lambda cfg: (lambda x: x), batched=True)
+    try:
+        _check_registered_reference(rcfg, rdet, rpipe, torch)
+    finally:
+        unregister_from_reference()
+    # everything is back: the backend id is unknown again, the stock tracker and frame filters are in place
+    with pytest.raises(rcfg.ConfigError):
+        rcfg.DetectorConfig(backend="b200").validate()
+    assert rpipe.IouTracker.__name__ == "IouTracker" and rpipe.apply_roi.__module__.startswith("realtime_analytics")
+    assert not rpipe.StreamWorker._b200va_batched
+
+
+def _check_registered_reference(rcfg, rdet, rpipe, torch):
+    assert rpipe.StreamWorker._b200va_batched  # the tick collector is installed (collector.py, tests/test_collector.py)
     cfg = rcfg.DetectorConfig(backend="b200", confidence_threshold=0.35, iou_threshold=0.5)
     cfg.validate()  # whitelisted now
     assert cfg.backend == "b200"

@@ -114,6 +114,45 @@ def test_tracker_many_detections_cross_chunks_and_overflow(H):
     _tracker_run(H, rng, 8, gen, max_age=3, thr=0.4, min_hits=1, f64=False)
 
 
+def test_tracker_working_table_in_global_scratch(monkeypatch):
+    """The tracker's working table lives in shared memory only when `live tracks + detections` fits the rows the launch
+    was given; otherwise the same code runs on the stream's global scratch.  Force that path (8 shared rows) through the
+    conflict-heavy and the multi-chunk scenarios, and let a default handle (512 rows, then adapted from the need the
+    kernel reports) cross the limit in both directions: results never change."""
+    from realtime_video_analytics_32streams_b200 import _native
+
+    def storm(rng, t, s, centers=np.random.default_rng(5).uniform(100, 900, (3, 5, 2))):
+        rows = []
+        for c in range(5):
+            cx, cy = centers[s, c] + rng.normal(0, 3, 2) + t * 2
+            for _ in range(int(rng.integers(0, 7))):
+                b = np.array([cx - 40, cy - 30, cx + 40, cy + 30]) + rng.normal(0, 6, 4)
+                rows.append((int(rng.integers(0, 2)), np.float32(rng.uniform(0.3, 1)), b.astype(np.float32)))
+        return [rows[i] for i in rng.permutation(len(rows))]
+
+    def crowd(rng, t, s):
+        # the population swells to ~450 boxes (need ~900 > 512 rows) and shrinks again
+        n = (40, 450, 450, 450, 60, 30, 30, 420, 20, 20)[t % 10]
+        k = np.arange(n)
+        cx, cy = 30 + (k % 30) * 60 + rng.normal(0, 1.5, n), 30 + (k // 30) * 60 + rng.normal(0, 1.5, n)
+        return [(int(i % 3), np.float32(rng.uniform(0.3, 1)), np.array([x - 20, y - 20, x + 20, y + 20], np.float32))
+                for i, x, y in zip(k, cx, cy)]
+
+    monkeypatch.setenv("B200VA_TRK_SMEM_TRACKS", "8")
+    h = _native.Handle(device=0, max_batch=4, max_anchors=256, max_candidates=1024, max_dets=512, max_streams=4, max_tracks=1024)
+    try:
+        _tracker_run(h, np.random.default_rng(11), 10, storm, max_age=2, thr=0.3, min_hits=0, f64=False)
+        _tracker_run(h, np.random.default_rng(12), 10, crowd, max_age=1, thr=0.4, min_hits=1, f64=True)
+    finally:
+        h.close()
+    monkeypatch.delenv("B200VA_TRK_SMEM_TRACKS")
+    h = _native.Handle(device=0, max_batch=4, max_anchors=256, max_candidates=1024, max_dets=512, max_streams=4, max_tracks=2048)
+    try:
+        _tracker_run(h, np.random.default_rng(13), 30, crowd, max_age=1, thr=0.4, min_hits=1, f64=False)
+    finally:
+        h.close()
+
+
 def test_tracker_capacity_flag(H):
     from realtime_video_analytics_32streams_b200 import _native as N
 
