@@ -190,6 +190,17 @@ inline cudaError_t prefer_max_shared(K kernel) {
   return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
 }
 
+// The dynamic shared-memory limit is a property of the FUNCTION, shared by every handle of the process: only ever
+// raise it (a second handle with smaller capacities must not pull it below what the first one launches with).
+template <typename K>
+inline cudaError_t raise_dyn_smem(K kernel, size_t bytes) {
+  cudaFuncAttributes a;
+  cudaError_t e = cudaFuncGetAttributes(&a, kernel);
+  if (e != cudaSuccess) return e;
+  if ((size_t)a.maxDynamicSharedSizeBytes >= bytes) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
 // launch on `st` as a programmatic dependent of the kernel before it (its prologue overlaps that kernel's tail)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {

@@ -1245,15 +1245,15 @@ int postprocess_configure(b200va_ctx* h) {
   if (smem > 220 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_candidates %d needs %zu bytes of shared memory", h->cfg.max_candidates, smem);
   {
     const size_t fused = std::min<size_t>(200 * 1024, std::max(smem, tracker_smem_bytes(h->cfg.max_tracks)));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_post_track, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused));
+    CUDA_TRY(h, raise_dyn_smem(k_post_track, fused));
     // k_post_track runs beside the letterbox in b200va_tick, and an SM only hosts kernels that agree on its L1 /
     // shared-memory split (see prefer_max_shared): ask for the split the 1080p letterbox launch gets (164 KB, six
     // 24.5 KB CTAs) instead of the one the driver would derive from this kernel's own occupancy
     const int pct = h->tune.post_carveout >= 0 ? h->tune.post_carveout : 71;
     if (pct > 0) CUDA_TRY(h, cudaFuncSetAttribute(k_post_track, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
   }
-  CUDA_TRY(h, cudaFuncSetAttribute(k_sort_nms<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CUDA_TRY(h, cudaFuncSetAttribute(k_sort_nms<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(h, raise_dyn_smem(k_sort_nms<false>, smem));
+  CUDA_TRY(h, raise_dyn_smem(k_sort_nms<true>, smem));
   return B200VA_OK;
 }
 

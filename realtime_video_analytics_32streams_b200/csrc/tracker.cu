@@ -80,7 +80,7 @@ int tracker_state_create(b200va_ctx* h) {
   CUDA_TRY(h, cudaMemcpy(S->next_id, &one, 8, cudaMemcpyHostToDevice));
   const size_t smem = tracker_smem_bytes(h->cfg.max_tracks);
   if (smem > 190 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_tracks %d too large (<= 4096)", h->cfg.max_tracks);
-  CUDA_TRY(h, cudaFuncSetAttribute(k_tracker, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CUDA_TRY(h, raise_dyn_smem(k_tracker, smem));
   if (h->tune.uniform_carveout) CUDA_TRY(h, prefer_max_shared(k_tracker));
   return B200VA_OK;
 }

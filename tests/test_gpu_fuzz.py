@@ -297,3 +297,29 @@ def test_motion_random_sizes_and_masks(H):
         mf.should_process(O.apply_roi(f1, polys) if polys else f1)
         assert np.array_equal(b.cpu().numpy(), mf.previous_gray), (h, w)
         assert int(c[0]) == mf.last_count
+
+
+def test_second_handle_with_smaller_capacities_does_not_break_the_first():
+    """Kernel attributes (dynamic shared-memory limit) are per function, not per handle: creating a small handle must
+    not lower what a big handle launches with."""
+    import torch
+    from realtime_video_analytics_32streams_b200 import _native
+
+    big = _native.Handle(device=0, max_batch=2, max_anchors=8400, max_candidates=4096, max_dets=1024, max_streams=2, max_tracks=4096)
+    small = None
+    try:
+        heads = np.stack([synth.DenseScene(77 + s).head(0) for s in range(2)])
+        lbs = [_native.letterbox_meta(1080, 1920, 640, 640)] * 2
+        want = [len(O.filter_detections(O.postprocess(heads[s][None], O.letterbox_meta(1080, 1920, 640, 640), 0.35, 0.5), 0.35))
+                for s in range(2)]
+        for rnd in range(3):
+            if rnd == 1:
+                small = _native.Handle(device=0, max_batch=1, max_anchors=256, max_candidates=64, max_dets=16, max_streams=1, max_tracks=32)
+            dets = big.postprocess(torch.from_numpy(heads).cuda(), lbs, 0.35, 0.5, filter_conf=0.35)
+            trk = big.tracker_update([0, 1], dets, 30, 1, 0.5)
+            assert dets["count"].cpu().tolist() == want and trk["count"].cpu().tolist() == want
+            big.poll_status()
+    finally:
+        big.close()
+        if small is not None:
+            small.close()
