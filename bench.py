@@ -596,7 +596,7 @@ def run_gpu(args) -> None:
 
             del frame_sets, head_sets, nets, batches, plans, graphs
             torch.cuda.empty_cache()
-            configs_block = bench_configs.run_all(("1", "2", "5", "4", "D", "P"), steps=max(10, min(K, 30)))
+            configs_block = bench_configs.run_all(("1", "2", "5", "4", "D", "E", "P"), steps=max(10, min(K, 30)))
         except Exception as exc:  # pragma: no cover - informational block: never lose the headline line over it
             configs_block = {"error": f"{type(exc).__name__}: {exc}"}
 

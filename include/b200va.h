@@ -181,7 +181,8 @@ enum b200va_phase {
   B200VA_PHASE_TRACKER = 7,    /* b200va_tracker_update*                                 */
   B200VA_PHASE_DFL = 8,        /* b200va_dfl_decode                                      */
   B200VA_PHASE_TICK = 9,       /* the whole b200va_tick call, fork to join               */
-  B200VA_PHASE_COUNT = 10
+  B200VA_PHASE_EGRESS = 10,    /* b200va_resize_area_u8 / b200va_draw_rects              */
+  B200VA_PHASE_COUNT = 11
 };
 B200VA_API int b200va_set_profiling(b200va_handle h, int enable);
 B200VA_API int b200va_get_phase_times(b200va_handle h, float* ms /* HOST [B200VA_PHASE_COUNT] */);
@@ -417,6 +418,46 @@ typedef struct b200va_tick_args {
   void* ev_pre_end;
 } b200va_tick_args;
 B200VA_API int b200va_tick(b200va_handle h, const b200va_tick_args* args, void* stream);
+
+/* ---- 8f-3: egress (the preview and the event the sink publishes) -------------------------------
+ * Replaces, for a frame that is already in HBM, the pixel work of KafkaSink._render_frame
+ * (sinks/kafka_sink.py:200-267) and the serialisation of KafkaSink.send_tracks (:105-134 with the producer's
+ * value_serializer json.dumps, :88).  Glyph rasterisation (cv2.putText) and the JPEG / WebP encoder stay with the
+ * caller: they are the reference's own OpenCV calls on the (much smaller) annotated preview.
+ *
+ * b200va_resize_area_u8: cv2.resize(frame, (dst_w, dst_h), interpolation=cv2.INTER_AREA) for BGR uint8 HWC frames,
+ * shrinking only (kafka_sink.py:227-232 downscales frames above 1920x1080).  Bit-exact with OpenCV 4.x: whole 2x2
+ * blocks round half up ((a+b+c+d+2)>>2, the vector kernel), other whole blocks multiply by float(1/area) and round
+ * half to even, fractional ratios accumulate float32 products in computeResizeAreaTab order.
+ * frames / dst: HOST arrays [batch] of DEVICE pointers; dst pitch = 3 * dst_w. */
+B200VA_API int b200va_resize_area_u8(b200va_handle h, const uint8_t* const* frames, const int* src_h, const int* src_w,
+                                     const int64_t* src_pitch, int batch, uint8_t* const* dst, const int* dst_h,
+                                     const int* dst_w, void* stream);
+
+/* b200va_draw_rects: the rectangles of kafka_sink.py:240 (cv2.rectangle(img, p1, p2, color, 2): kind 0) and
+ * :249-255 (cv2.rectangle(.., color, -1): kind 1) drawn into BGR uint8 images IN LIST ORDER (a later rectangle
+ * overwrites an earlier one, like successive cv2 calls).  Corner points may lie outside the image (clipped) and in
+ * any order.  ops: HOST array; image b owns ops[op_offsets[b] .. op_offsets[b + 1]).  images: HOST array [batch] of
+ * DEVICE pointers, pitch in bytes (NULL = 3 * w). */
+typedef struct b200va_rect_op {
+  int32_t kind;           /* 0 = outline, thickness 2; 1 = filled */
+  int32_t x1, y1, x2, y2; /* the two corner points, inclusive */
+  uint8_t b, g, r, pad_;
+} b200va_rect_op;
+B200VA_API int b200va_draw_rects(b200va_handle h, uint8_t* const* images, const int* img_h, const int* img_w,
+                                 const int64_t* pitch, int batch, const b200va_rect_op* ops, const int* op_offsets,
+                                 void* stream);
+
+/* b200va_tracks_json: the bytes of json.dumps({"stream": .., "frame_id": .., "tracks": [{"track_id", "class_id",
+ * "confidence", "bbox_xyxy"}, ..], "is_temporal": false[, "frame_jpeg": frame_data_url]}) exactly as CPython writes
+ * them (", " / ": " separators, float.__repr__ shortest round-trip digits, ensure_ascii escapes, NaN / Infinity).
+ * Host-only (no handle, no device work): all pointers are HOST arrays, e.g. rows of the pinned result tables
+ * (track_id [n], cls [n], conf [n] float64, bbox_xyxy [n, 4] float64).  Writes at most `cap` bytes to `out` (not
+ * NUL-terminated) and returns the number of bytes the document needs (call again with a larger buffer when the
+ * return value exceeds cap); -1 on invalid arguments. */
+B200VA_API int64_t b200va_tracks_json(const char* stream_name, int64_t frame_id, const int64_t* track_id, const int32_t* cls,
+                                      const double* conf, const double* bbox_xyxy, int n, const char* frame_data_url,
+                                      char* out, int64_t cap);
 
 #ifdef __cplusplus
 }

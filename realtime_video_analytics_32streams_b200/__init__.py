@@ -18,13 +18,13 @@ from .types import Detection, DetectorConfig, FramePacket, MotionFilterConfig, S
 
 __all__ = ["Detection", "DetectorConfig", "FramePacket", "FrameResult", "MotionFilterConfig", "StreamConfig", "Track",
            "TrackerConfig", "B200Detector", "B200UltralyticsDetector", "B200IouTracker", "HotPathEngine", "MotionFilter", "apply_roi",
-           "downsample", "filter_detections", "get_handle", "register_with_reference", "TickCollector"]
+           "downsample", "filter_detections", "get_handle", "register_with_reference", "TickCollector", "B200KafkaSink"]
 
 _LAZY = {
     "B200Detector": "detector", "B200UltralyticsDetector": "detector", "filter_detections": "detector", "B200IouTracker": "tracker",
     "HotPathEngine": "engine", "FrameResult": "engine", "MotionFilter": "frame_filter", "apply_roi": "frame_filter",
     "downsample": "frame_filter", "roi_mask": "frame_filter", "get_handle": "runtime",
-    "register_with_reference": "integration", "TickCollector": "collector",
+    "register_with_reference": "integration", "TickCollector": "collector", "B200KafkaSink": "sinks",
 }
 
 

@@ -60,6 +60,13 @@ class Tracks(C.Structure):
                 ("age", C.c_void_p), ("hits", C.c_void_p), ("count", C.c_void_p), ("rows", C.c_int32)]
 
 
+class RectOp(C.Structure):
+    """``b200va_rect_op`` (include/b200va.h): kind 0 = thickness-2 outline, 1 = filled."""
+
+    _fields_ = [("kind", C.c_int32), ("x1", C.c_int32), ("y1", C.c_int32), ("x2", C.c_int32), ("y2", C.c_int32),
+                ("b", C.c_uint8), ("g", C.c_uint8), ("r", C.c_uint8), ("pad_", C.c_uint8)]
+
+
 class TickArgs(C.Structure):
     """``b200va_tick_args`` (include/b200va.h)."""
 
@@ -106,9 +113,9 @@ EXPORTS = (
     "b200va_tracker_set_next_id", "b200va_upload_frames", "b200va_dfl_decode", "b200va_tick",
     "b200va_letterbox_meta_ultralytics", "b200va_preprocess_geom", "b200va_postprocess_ultralytics",
     "b200va_motion_preprocess", "b200va_set_profiling", "b200va_get_phase_times",
-    "b200va_read_status_async",
+    "b200va_read_status_async", "b200va_resize_area_u8", "b200va_draw_rects", "b200va_tracks_json",
 )
-PHASES = ("upload", "roi", "resize", "motion", "preprocess", "decode", "nms", "tracker", "dfl", "tick")  # enum b200va_phase
+PHASES = ("upload", "roi", "resize", "motion", "preprocess", "decode", "nms", "tracker", "dfl", "tick", "egress")  # enum b200va_phase
 
 _lib = None
 
@@ -168,10 +175,42 @@ def load_library() -> C.CDLL:
     lib.b200va_get_phase_times.argtypes = [vp, C.POINTER(C.c_float)]
     lib.b200va_tracker_reset.argtypes = [vp, C.c_int, vp]
     lib.b200va_tracker_set_next_id.argtypes = [vp, C.c_int64, vp]
+    lib.b200va_resize_area_u8.argtypes = [vp, C.POINTER(vp), ip, ip, i64p, C.c_int, C.POINTER(vp), ip, ip, vp]
+    lib.b200va_draw_rects.argtypes = [vp, C.POINTER(vp), ip, ip, i64p, C.c_int, C.POINTER(RectOp), ip, vp]
+    lib.b200va_tracks_json.restype = C.c_int64
+    lib.b200va_tracks_json.argtypes = [C.c_char_p, C.c_int64, vp, vp, vp, vp, C.c_int, C.c_char_p, vp, C.c_int64]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError here = header / library mismatch
     _lib = lib
     return lib
+
+
+def tracks_json(stream_name: str, frame_id: int, track_id, cls, conf, bbox_xyxy, frame_data_url: Optional[str] = None) -> bytes:
+    """``json.dumps(payload).encode()`` of the reference's track event (kafka_sink.py:88, 105-134), written by
+    ``b200va_tracks_json`` straight from result-table rows: ``track_id`` int64 [n], ``cls`` int32 [n], ``conf`` float64 [n],
+    ``bbox_xyxy`` float64 [n, 4] (C-contiguous NumPy arrays, e.g. ``FrameResult.track_arrays``).  Host-only; needs no GPU."""
+    import numpy as np
+
+    lib = load_library()
+    ids = np.ascontiguousarray(track_id, dtype=np.int64)
+    cl = np.ascontiguousarray(cls, dtype=np.int32)
+    cf = np.ascontiguousarray(conf, dtype=np.float64)
+    bx = np.ascontiguousarray(bbox_xyxy, dtype=np.float64).reshape(-1, 4)
+    n = int(ids.shape[0])
+    if not (cl.shape[0] == n and cf.shape[0] == n and bx.shape[0] == n):
+        raise ValueError("tracks_json: the four arrays must have one row per track")
+    name = stream_name.encode("utf-8")
+    url = frame_data_url.encode("ascii") if frame_data_url is not None else None
+    cap = 96 + len(name) * 6 + n * 160 + (len(url) + 32 if url else 0)
+    while True:
+        buf = C.create_string_buffer(cap)
+        need = lib.b200va_tracks_json(name, int(frame_id), ids.ctypes.data, cl.ctypes.data, cf.ctypes.data, bx.ctypes.data, n,
+                                      url, C.cast(buf, C.c_void_p), cap)
+        if need < 0:
+            raise B200VAError(ERR_INVALID, "b200va_tracks_json: invalid arguments")
+        if need <= cap:
+            return buf.raw[:need]
+        cap = int(need)
 
 
 def letterbox_meta(src_h: int, src_w: int, dst_h: int, dst_w: int) -> Letterbox:
@@ -384,6 +423,39 @@ class Handle:
                 _ptr_array([o.data_ptr() for o in outs]), _int_array([h for h, _ in dst_hw_list]),
                 _int_array([w for _, w in dst_hw_list]), self._stream()))
         return outs
+
+    # -- 8f-3 -------------------------------------------------------------------------------
+    def resize_area(self, frames, dst_hw_list, outs=None):
+        """``cv2.resize(frame, (w, h), interpolation=cv2.INTER_AREA)`` per frame, shrinking only (kafka_sink.py:227-232)."""
+        t = self.torch
+        if outs is None:
+            outs = [t.empty((int(h), int(w), 3), dtype=t.uint8, device=self.device) for h, w in dst_hw_list]
+        elif any(tuple(o.shape) != (int(h), int(w), 3) or o.dtype != t.uint8 or not o.is_contiguous() or not o.is_cuda
+                 for o, (h, w) in zip(outs, dst_hw_list)) or len(outs) != len(dst_hw_list):
+            raise ValueError("resize_area: `outs` must be contiguous CUDA uint8 tensors [h, w, 3] matching dst_hw_list")
+        fb = self._batch(frames)
+        if fb.n:
+            self._check(self.lib.b200va_resize_area_u8(
+                self._h, fb.ptrs, fb.hs, fb.ws, fb.pitch, fb.n, _ptr_array([o.data_ptr() for o in outs]),
+                _int_array([h for h, _ in dst_hw_list]), _int_array([w for _, w in dst_hw_list]), self._stream()))
+        return outs
+
+    def draw_rects(self, images, ops_per_image) -> None:
+        """Draw, in place and in list order, ``(kind, x1, y1, x2, y2, (b, g, r))`` rectangles into CUDA uint8 [H, W, 3]
+        images: kind 0 = ``cv2.rectangle(.., color, 2)``, kind 1 = ``cv2.rectangle(.., color, -1)`` (kafka_sink.py:240, 249-255)."""
+        fb = self._batch(images)
+        if not fb.n:
+            return
+        if len(ops_per_image) != fb.n:
+            raise ValueError("draw_rects: one operation list per image")
+        offs, flat = [0], []
+        for ops in ops_per_image:
+            flat.extend(ops)
+            offs.append(len(flat))
+        arr = (RectOp * max(len(flat), 1))()
+        for i, (kind, x1, y1, x2, y2, col) in enumerate(flat):
+            arr[i] = RectOp(int(kind), int(x1), int(y1), int(x2), int(y2), int(col[0]), int(col[1]), int(col[2]), 0)
+        self._check(self.lib.b200va_draw_rects(self._h, fb.ptrs, fb.hs, fb.ws, fb.pitch, fb.n, arr, _int_array(offs), self._stream()))
 
     # -- a9 ---------------------------------------------------------------------------------
     def roi_rasterize(self, polygons, height: int, width: int):

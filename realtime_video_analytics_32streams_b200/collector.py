@@ -165,7 +165,9 @@ def make_process_packet(collector_of: Callable):
                 tracks = r.tracks
                 self.ctx.metrics.update_counters(stream=name, frames_processed=1, detections_emitted=r.n_detections,
                                                  active_tracks=len(tracks))
-                await self.ctx.kafka.send_tracks(stream_name=name, frame_id=packet.frame_id, tracks=tracks,
+                # a sink that reads result tables (B200KafkaSink) gets the FrameResult, anything else the Track objects
+                payload = r if getattr(self.ctx.kafka, "accepts_results", False) else tracks
+                await self.ctx.kafka.send_tracks(stream_name=name, frame_id=packet.frame_id, tracks=payload,
                                                  frame=packet.frame)
                 self._maybe_save_snapshot(packet, tracks)
             else:  # pipeline.py:214-222 (_skip_frame): counters only, nothing is published

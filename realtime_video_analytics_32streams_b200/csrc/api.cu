@@ -8,6 +8,7 @@
 
 int postprocess_configure(b200va_ctx* h);  // postprocess.cu
 void postprocess_release(b200va_ctx* h);   // postprocess.cu
+void egress_destroy(b200va_ctx* h);        // egress.cu
 int preprocess_configure(b200va_ctx* h);   // preprocess.cu
 int filters_configure(b200va_ctx* h);      // filters.cu
 
@@ -27,7 +28,7 @@ extern "C" const char* b200va_error_string(int status) {
 const char* phase_name(int phase) {
   static const char* names[B200VA_PHASE_COUNT] = {"b200va:upload", "b200va:roi", "b200va:resize", "b200va:motion",
                                                   "b200va:preprocess", "b200va:decode", "b200va:nms", "b200va:tracker",
-                                                  "b200va:dfl", "b200va:tick"};
+                                                  "b200va:dfl", "b200va:tick", "b200va:egress"};
   return phase >= 0 && phase < B200VA_PHASE_COUNT ? names[phase] : "b200va:?";
 }
 
@@ -171,6 +172,7 @@ extern "C" int b200va_destroy(b200va_handle h) {
     DeviceGuard guard(h->cfg.device);
     cudaDeviceSynchronize();
     postprocess_release(h);
+    egress_destroy(h);
     tracker_state_destroy(h);
     tap_cache_destroy(h);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);

@@ -58,6 +58,7 @@ struct b200va_ctx {
   void* roi_scratch = nullptr;  // device, ROI_SCRATCH_BYTES
   // ---- tracker ----
   TrackerState* tracker = nullptr;
+  void* egress = nullptr;  // egress.cu: INTER_AREA tables per geometry, device copy of the rectangle list
   // ---- b200va_tick: second stream for the post-process + tracker branch ----
   cudaStream_t side_stream = nullptr;    // non-blocking, highest priority (its 32-CTA kernels slot in first)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_decoded = nullptr;

@@ -37,12 +37,15 @@ def unregister_from_reference() -> None:
 
 
 def register_with_reference(infer_factory: Optional[Callable] = None, batched: bool = False,
-                            engine_factory: Optional[Callable] = None, max_wait_s: float = 0.010) -> None:
+                            engine_factory: Optional[Callable] = None, max_wait_s: float = 0.010,
+                            gpu_sink: bool = False) -> None:
     """``infer_factory(config) -> callable`` builds the detector forward for a DetectorConfig
     (e.g. loads the YOLO weights with PyTorch); it is required for ``backend: b200``.
     ``batched=True``: all stream workers of a pipeline share one tick (``collector.install``); ``engine_factory(streams,
     detector, pipeline_config)`` overrides the engine it drives (default: ``HotPathEngine`` on the detector's handle) and
-    ``max_wait_s`` bounds how long a tick waits for a late stream."""
+    ``max_wait_s`` bounds how long a tick waits for a late stream.
+    ``gpu_sink=True``: the pipeline's ``KafkaSink`` (pipeline.py:453) becomes ``B200KafkaSink`` -- same messages, the
+    preview's downscale / boxes and the event serialisation done by the library (sinks.py)."""
     import realtime_analytics.config as rcfg  # the reference, must be importable
     import realtime_analytics.detector as rdet
     import realtime_analytics.pipeline as rpipe
@@ -102,3 +105,9 @@ def register_with_reference(infer_factory: Optional[Callable] = None, batched: b
                             (rpipe.StreamWorker, "__init__"), (rpipe.StreamWorker, "run"), (rpipe.StreamWorker, "_process_packet")):
             _ORIGINALS.setdefault((owner, name), getattr(owner, name))
         collector.install(rpipe, engine_factory or collector.default_engine_factory, max_wait_s)
+
+    # 5. egress (pipeline.py:453, sinks/kafka_sink.py)
+    if gpu_sink:
+        from .sinks import B200KafkaSink
+
+        _patch(rpipe, "KafkaSink", B200KafkaSink)

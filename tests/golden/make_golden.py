@@ -41,6 +41,9 @@ from realtime_analytics.video_stream import FramePacket  # noqa: E402
 
 from realtime_video_analytics_32streams_b200 import synth  # noqa: E402
 
+sys.path.insert(0, os.path.dirname(HERE))
+from golden_util import egress_case  # noqa: E402  (seeded inputs shared with the tests)
+
 
 class StubDetector(_TensorRTBaseDetector):
     """The reference's numpy pre/post path with the model forward replaced by a lookup."""
@@ -337,7 +340,50 @@ def gen_pipeline(out):
             out[f"pipe_{k}_t{kk}"] = arr
 
 
-GENERATORS = (("preprocess", gen_preprocess), ("preprocess_rknn", gen_preprocess_rknn), ("postprocess", gen_postprocess),
+def gen_egress(out):
+    """KafkaSink.send_tracks / _render_frame (sinks/kafka_sink.py:93-149, 200-301) with a stub producer: the payload
+    bytes the producer's value_serializer writes, and the image handed to cv2.imencode (captured, the encoder still runs)."""
+    from realtime_analytics.config import KafkaSinkConfig
+    from realtime_analytics.sinks.kafka_sink import KafkaSink
+    from realtime_analytics.tracker import Track
+
+    digests = {}
+    for name in ("small", "small_overlap", "hd_plus", "uhd", "uhd_dense", "qhd"):
+        frame, ids, cls, conf, box = egress_case(name)
+        tracks = [Track(int(i), int(c), float(f), tuple(float(v) for v in b)) for i, c, f, b in zip(ids, cls, conf, box)]
+        sink = KafkaSink(KafkaSinkConfig(enabled=True, include_frames=True, frame_quality=75))
+        sent, captured = [], []
+
+        class Producer:
+            async def send_and_wait(self, topic, payload):
+                sent.append(json.dumps(payload).encode("utf-8"))  # the value_serializer of kafka_sink.py:88
+
+        sink._producer = Producer()
+        real_imencode = cv2.imencode
+
+        def spy(ext, img, params=None):
+            captured.append((ext, img.copy(), list(params or [])))
+            return real_imencode(ext, img, params)
+
+        cv2.imencode = spy
+        try:
+            asyncio.run(sink.send_tracks(f"cam-{name}", 1234, tracks, frame=frame))
+        finally:
+            cv2.imencode = real_imencode
+        assert len(sent) == 1 and len(captured) == 1
+        ext, image, params = captured[0]
+        body = sent[0]
+        cut = body.index(b', "frame_jpeg": ')
+        digests[name] = {"image_sha256": sha(image), "image_shape": list(image.shape), "ext": ext, "params": [int(p) for p in params],
+                         "body_sha256": hashlib.sha256(body).hexdigest(), "body_len": len(body)}
+        out[f"{name}_event"] = np.frombuffer(body[:cut] + b"}", dtype=np.uint8)  # the document without the preview
+        if image.size <= 170000:
+            out[f"{name}_image"] = image
+            out[f"{name}_body"] = np.frombuffer(body, dtype=np.uint8)
+    return digests
+
+
+GENERATORS = (("egress", gen_egress), ("preprocess", gen_preprocess), ("preprocess_rknn", gen_preprocess_rknn), ("postprocess", gen_postprocess),
               ("tracker", gen_tracker), ("filters", gen_filters), ("pipeline", gen_pipeline))
 
 

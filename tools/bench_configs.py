@@ -4,7 +4,7 @@ drop-in path (`predict` + `filter_detections` + `update` per frame) next to the 
 
 Importable (`bench.py` runs `run_all` for its `configs` block) and a CLI:
 
-    python tools/bench_configs.py [--steps 30] [--only 1,2,5,4,D,L,P] [--out profiles/r2_configs.json]
+    python tools/bench_configs.py [--steps 30] [--only 1,2,5,4,D,E,L,P] [--out profiles/r2_configs.json]
 
 Inputs are resident in HBM, CUDA events bracket every C-ABI call, medians over `steps` ticks; `tick_graph` is one
 prepared `b200va_tick` replayed from a CUDA graph (what a deployed loop runs)."""
@@ -273,6 +273,67 @@ def dropin(name, B, n_frames=60):
             "h2d_bytes_per_frame": 360 * W * 3, "frames_timed": n_frames * B}
 
 
+def egress_bench(B=32, steps=10):
+    """8f-3: the preview of KafkaSink._render_frame for 32 x 4K frames resident in HBM (INTER_AREA to 1920x1080 + 25 boxes
+    and label backgrounds each) and the event serialisation of 300 tracks, next to the reference's own OpenCV / json calls."""
+    import cv2
+
+    from realtime_video_analytics_32streams_b200 import sinks
+
+    H, W = 2160, 3840
+    dev = _dev()
+    PEAK = peak_gbps()
+    h = _native.Handle(device=dev.index, max_batch=B, max_anchors=256, max_candidates=256, max_dets=64, max_streams=B, max_tracks=64)
+    g = torch.Generator(device=dev)
+    g.manual_seed(11)
+    frames = [torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device=dev, generator=g) for _ in range(2)]
+    batches = [_native.FrameBatch(list(f.unbind(0))) for f in frames]
+    outs = [torch.empty((1080, 1920, 3), dtype=torch.uint8, device=dev) for _ in range(B)]
+    rng = np.random.default_rng(3)
+    ops = []
+    for _ in range(B):
+        o = []
+        for k in range(25):
+            x1, y1 = int(rng.integers(0, 1700)), int(rng.integers(40, 900))
+            col = sinks.color_for(int(rng.integers(0, 80)))
+            o += [(0, x1, y1, x1 + 160, y1 + 120, col), (1, x1, y1 - 20, x1 + 60, y1, col)]
+        ops.append(o)
+    r = timed([("resize_area", lambda k: h.resize_area(batches[k % 2], [(1080, 1920)] * B, outs=outs)),
+               ("draw_rects", lambda k: h.draw_rects(outs, ops))], steps)
+    alg = B * (H * W * 3 + 1080 * 1920 * 3)
+    host = frames[0][0].cpu().numpy()
+    cv2.setNumThreads(1)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        img = cv2.resize(host, (1920, 1080), interpolation=cv2.INTER_AREA)
+        for kind, x1, y1, x2, y2, col in ops[0]:
+            cv2.rectangle(img, (x1, y1), (x2, y2), col, -1 if kind else 2)
+    cpu_ms = 1e3 * (time.perf_counter() - t0) / 5
+    n = 300
+    ids, cls = np.arange(1, n + 1, dtype=np.int64), rng.integers(0, 80, n).astype(np.int32)
+    conf = rng.uniform(0.3, 1, n).astype(np.float32).astype(np.float64)
+    box = rng.uniform(0, 3000, (n, 4)).astype(np.float32).astype(np.float64)
+    import json
+
+    t0 = time.perf_counter()
+    for _ in range(200):
+        body = _native.tracks_json("cam-00", 7, ids, cls, conf, box)
+    c_us = 1e6 * (time.perf_counter() - t0) / 200
+    t0 = time.perf_counter()
+    for _ in range(200):
+        tl = [{"track_id": int(i), "class_id": int(c), "confidence": float(f), "bbox_xyxy": tuple(b)}
+              for i, c, f, b in zip(ids.tolist(), cls.tolist(), conf.tolist(), box.tolist())]
+        ref = json.dumps({"stream": "cam-00", "frame_id": 7, "tracks": tl, "is_temporal": False}).encode()
+    py_us = 1e6 * (time.perf_counter() - t0) / 200
+    assert body == ref
+    r.update(config="8f-3: preview of 32 x 4K frames (INTER_AREA -> 1080p, 50 rectangles each) + event JSON of 300 tracks",
+             streams=B, frame=[H, W], algorithmic_bytes=alg, resize_area_GBps=alg / (r["resize_area"] * 1e-3) / 1e9,
+             resize_area_frac_of_peak=alg / (r["resize_area"] * 1e-3) / 1e9 / PEAK, gpu_ms_per_frame=r["tick_total"] / B,
+             cpu_reference_ms_per_frame=cpu_ms, json_us_300_tracks=c_us, json_dumps_us_300_tracks=py_us)
+    h.close()
+    return r
+
+
 def run_all(todo=("1", "2", "5", "4", "P"), steps=30, lshape=-1):
     out = []
     if "L" in todo:
@@ -293,6 +354,8 @@ def run_all(todo=("1", "2", "5", "4", "P"), steps=30, lshape=-1):
         out.append(config4(steps=steps))
     if "D" in todo:
         out.append(dfl_only(steps=steps))
+    if "E" in todo:
+        out.append(egress_bench(steps=max(5, min(steps, 10))))
     if "P" in todo:
         out.append(dropin("1 (drop-in API): 1 stream 1080p through predict / update", 1))
         out.append(dropin("2 (drop-in API): 4 streams 1080p through predict / update", 4, n_frames=30))
@@ -306,7 +369,7 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="")
     ap.add_argument("--lshape", type=int, default=-1, help="with --only L: run just this letterbox shape (0-5)")
     args = ap.parse_args()
-    res = run_all(args.only.split(",") if args.only else ("1", "2", "5", "4", "D", "P"), args.steps, args.lshape)
+    res = run_all(args.only.split(",") if args.only else ("1", "2", "5", "4", "D", "E", "P"), args.steps, args.lshape)
     for r in res:
         print(json.dumps(r))
     if args.out:
