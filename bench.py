@@ -486,6 +486,10 @@ def run_gpu(args) -> None:
 
     lb_b2b_ms = back_to_back(lambda k: h.preprocess(batches[k % N_SETS], IN_HW, _native.OUT_F32_RGB_NCHW, out=nets[k % N_SETS]))
     post_b2b_ms = back_to_back(lambda k: h.postprocess(head_sets[k % N_SETS], metas, CONF, IOU, filter_conf=CONF, out=dets))
+    # the decode kernel has no entry point of its own: with a confidence threshold no score can reach, b200va_postprocess
+    # is the full decode pass over the 32 heads (every row is read and scored, nothing is emitted) plus an NMS launch
+    # that finds no candidates and returns at once
+    dec_b2b_ms = back_to_back(lambda k: h.postprocess(head_sets[k % N_SETS], metas, 2.0, IOU, out=dets))
     pair = []
     for r in range(9):
         filler.fill_(r & 1)
@@ -640,11 +644,16 @@ def run_gpu(args) -> None:
                            "dram__bytes_read + dram__bytes_write of one launch from the ncu --set full capture summarised in "
                            "profiles/ (static, not re-measured in this run); frac_dram = traffic / kernel_ms / peak" % KERNEL_SAMPLES)
         roofline_kernels = [roofline]
+        dec = roof("k_decode_cm<4> (32 heads [84, 8400] per launch, read-only)", HEAD_BYTES_PER_FRAME * STREAMS, dec_b2b_ms,
+                   "k_decode_dram_bytes_per_launch",
+                   "kernel_ms: 24 back-to-back b200va_postprocess calls with an unreachable confidence threshold (the full decode "
+                   "pass + an NMS launch that returns at once) in one event pair.  A 90 MB read-only kernel is launch / ramp "
+                   "bound on this GPU: tools/membw.cu times a pure 90 MB read at 18.4 us between events (4.9 TB/s) against "
+                   "6.9 TB/s for 1 GB; profiles/r2_membw.log")
+        dec["samples"] = 5 * 24
         if "decode" in kern_ms:
-            roofline_kernels.append(roof("k_decode_cm<4> (32 heads [84, 8400] per launch, read-only)",
-                                         HEAD_BYTES_PER_FRAME * STREAMS, kern_ms["decode"], "k_decode_dram_bytes_per_launch",
-                                         "a read-only kernel: tools/readbw.cu measures 4.65 TB/s as this GPU's read-only "
-                                         "ceiling (profiles/r2_readbw.log), 0.72 of the copy peak used here"))
+            dec["kernel_ms_event_pair_in_tick"] = round(kern_ms["decode"], 5)
+        roofline_kernels.append(dec)
         for c in configs_block if isinstance(configs_block, list) else []:
             if str(c.get("config", "")).startswith("4:"):
                 roofline_kernels.append(roof("k_motion_tile + ROI (32 x 4K per launch)", c["motion_algorithmic_bytes"],
@@ -652,6 +661,9 @@ def run_gpu(args) -> None:
                 roofline_kernels.append(roof("k_letterbox<F32_RGB_NCHW, masked> (32 x 4K + ROI per launch)",
                                              c["preprocess_algorithmic_bytes"], c["preprocess(+roi)"],
                                              "k_letterbox_4k_masked_dram_bytes_per_launch"))
+            if str(c.get("config", "")).startswith("8f-3"):
+                roofline_kernels.append(roof("k_area_fast (INTER_AREA 32 x 4K -> 1080p per call)", c["algorithmic_bytes"],
+                                             c["resize_area"], "k_area_fast_dram_bytes_per_launch"))
             if str(c.get("config", "")).startswith("a14"):
                 roofline_kernels.append(roof("k_dfl_decode (32 raw heads [144, 8400] per launch)", c["algorithmic_bytes"],
                                              c["dfl_decode"], "k_dfl_decode_dram_bytes_per_launch"))
@@ -680,6 +692,7 @@ def run_gpu(args) -> None:
                              "frac": round(tick_bytes / peak / 1e6 / (ms / K), 4)},
                 "kernel_ms": dict({k_: round(v, 5) for k_, v in kern_ms.items()},
                                   preprocess_back_to_back=round(lb_b2b_ms, 5), postprocess_back_to_back=round(post_b2b_ms, 5),
+                                  decode_back_to_back=round(dec_b2b_ms, 5),
                                   how="event pair per phase in eager ticks; *_back_to_back: 24 launches in one pair"),
                 "e2e": {"value": round(e2e_value, 1), "unit": "frames/s",
                         "h2d_bytes_per_step": int(frame_bytes_per_step + STREAMS * C * A * 4), "d2h_bytes_per_step": d2h,
