@@ -440,14 +440,10 @@ class Handle:
                 _int_array([h for h, _ in dst_hw_list]), _int_array([w for _, w in dst_hw_list]), self._stream()))
         return outs
 
-    def draw_rects(self, images, ops_per_image) -> None:
-        """Draw, in place and in list order, ``(kind, x1, y1, x2, y2, (b, g, r))`` rectangles into CUDA uint8 [H, W, 3]
-        images: kind 0 = ``cv2.rectangle(.., color, 2)``, kind 1 = ``cv2.rectangle(.., color, -1)`` (kafka_sink.py:240, 249-255)."""
-        fb = self._batch(images)
-        if not fb.n:
-            return
-        if len(ops_per_image) != fb.n:
-            raise ValueError("draw_rects: one operation list per image")
+    @staticmethod
+    def pack_rects(ops_per_image):
+        """``[(kind, x1, y1, x2, y2, (b, g, r)), ...]`` per image -> the ``b200va_rect_op`` array and offsets
+        ``draw_rects`` passes down (pack once when the same overlay is drawn repeatedly)."""
         offs, flat = [0], []
         for ops in ops_per_image:
             flat.extend(ops)
@@ -455,7 +451,19 @@ class Handle:
         arr = (RectOp * max(len(flat), 1))()
         for i, (kind, x1, y1, x2, y2, col) in enumerate(flat):
             arr[i] = RectOp(int(kind), int(x1), int(y1), int(x2), int(y2), int(col[0]), int(col[1]), int(col[2]), 0)
-        self._check(self.lib.b200va_draw_rects(self._h, fb.ptrs, fb.hs, fb.ws, fb.pitch, fb.n, arr, _int_array(offs), self._stream()))
+        return arr, _int_array(offs), len(ops_per_image)
+
+    def draw_rects(self, images, ops_per_image) -> None:
+        """Draw, in place and in list order, ``(kind, x1, y1, x2, y2, (b, g, r))`` rectangles into CUDA uint8 [H, W, 3]
+        images: kind 0 = ``cv2.rectangle(.., color, 2)``, kind 1 = ``cv2.rectangle(.., color, -1)`` (kafka_sink.py:240,
+        249-255).  ``ops_per_image``: one list per image, or the result of ``pack_rects``."""
+        fb = self._batch(images)
+        if not fb.n:
+            return
+        arr, offs, n = ops_per_image if isinstance(ops_per_image, tuple) else self.pack_rects(ops_per_image)
+        if n != fb.n:
+            raise ValueError("draw_rects: one operation list per image")
+        self._check(self.lib.b200va_draw_rects(self._h, fb.ptrs, fb.hs, fb.ws, fb.pitch, fb.n, arr, offs, self._stream()))
 
     # -- a9 ---------------------------------------------------------------------------------
     def roi_rasterize(self, polygons, height: int, width: int):

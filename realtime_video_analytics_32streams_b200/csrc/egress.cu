@@ -68,6 +68,41 @@ __global__ void __launch_bounds__(256) k_area_fast(const __grid_constant__ AreaP
   }
 }
 
+// The 2 x 2 case on aligned frames (what a 4K camera sends): a thread owns four destination pixels -- two source rows
+// of 24 bytes each as three 8-byte loads, twelve result bytes as three 4-byte stores, both fully coalesced.
+__device__ __forceinline__ uint32_t byte_of(const uint32_t (&w)[6], int i) { return (w[i >> 2] >> ((i & 3) * 8)) & 0xffu; }
+
+__global__ void __launch_bounds__(256) k_area_2x2_vec(const __grid_constant__ AreaParams p) {
+  const AreaFrame& f = p.f[blockIdx.z];
+  const int q = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;  // q: group of four destination pixels
+  if (q * 4 >= p.dst_w) return;
+  const uint8_t* s0 = f.src + (long long)(2 * dy) * f.pitch + (size_t)q * 24;
+  const uint8_t* s1 = s0 + f.pitch;
+  uint32_t a[6], b[6];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const uint2 va = __ldcs(reinterpret_cast<const uint2*>(s0) + k), vb = __ldcs(reinterpret_cast<const uint2*>(s1) + k);
+    a[2 * k] = va.x;
+    a[2 * k + 1] = va.y;
+    b[2 * k] = vb.x;
+    b[2 * k + 1] = vb.y;
+  }
+  uint32_t o[3] = {0u, 0u, 0u};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const uint32_t v = (byte_of(a, 6 * j + c) + byte_of(a, 6 * j + 3 + c) + byte_of(b, 6 * j + c) + byte_of(b, 6 * j + 3 + c) + 2u) >> 2;
+      const int ob = 3 * j + c;
+      o[ob >> 2] |= v << ((ob & 3) * 8);
+    }
+  }
+  uint32_t* d = reinterpret_cast<uint32_t*>(f.dst + ((size_t)dy * p.dst_w + (size_t)q * 4) * 3);
+  __stcs(d, o[0]);
+  __stcs(d + 1, o[1]);
+  __stcs(d + 2, o[2]);
+}
+
 // ResizeArea_<uchar, float>: for every source row of the destination row (y table order) a horizontal float sum in
 // x table order starting from 0, then sum = beta * buf for the first row and sum += beta * buf for the others; no
 // contraction (the file is compiled with -fmad=false and the operations are spelled out).
@@ -148,31 +183,63 @@ __device__ __forceinline__ bool in_box(int x, int y, int x1, int y1, int x2, int
 }
 
 // The reference draws its rectangles one after another, so a pixel ends up with the colour of the LAST operation that
-// covers it: every thread owns one pixel and walks the list backwards until the first hit.
+// covers it.  A CTA owns a 64 x 4 pixel tile: its threads first collect the operations whose bounding box (grown by the
+// outline's stroke) touches the tile -- most tiles of a frame collect none and leave -- then every thread takes the
+// highest-numbered collected operation that covers its pixel.
 //   kind 1  cv2.rectangle(.., -1): the inclusive box
 //   kind 0  cv2.rectangle(.., 2):  four 3-pixel bands between the corner points (ThickLine's polygon at half-thickness
 //           1) whose round caps (Circle radius 1: a plus shape) add nothing the neighbouring band does not cover
-__global__ void __launch_bounds__(256) k_draw_rects(const __grid_constant__ RectParams p) {
+constexpr int kTileW = 64, kTileH = 4, kTileOps = 256;
+
+__device__ __forceinline__ bool op_hits(const b200va_rect_op& o, int x, int y) {
+  const int x1 = min(o.x1, o.x2), x2 = max(o.x1, o.x2), y1 = min(o.y1, o.y2), y2 = max(o.y1, o.y2);
+  if (o.kind) return in_box(x, y, x1, y1, x2, y2);
+  return in_box(x, y, x1, y1 - 1, x2, y1 + 1) || in_box(x, y, x1, y2 - 1, x2, y2 + 1) || in_box(x, y, x1 - 1, y1, x1 + 1, y2) ||
+         in_box(x, y, x2 - 1, y1, x2 + 1, y2);
+}
+
+__global__ void __launch_bounds__(kTileW * kTileH) k_draw_rects(const __grid_constant__ RectParams p) {
   const RectImage& im = p.im[blockIdx.z];
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= im.w || y >= im.h) return;
-  for (int k = im.op1 - 1; k >= im.op0; --k) {
+  const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
+  if (tx0 >= im.w || ty0 >= im.h) return;
+  __shared__ int s_n;
+  __shared__ int s_ops[kTileOps];
+  const int tid = threadIdx.y * kTileW + threadIdx.x;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  const int tx1 = tx0 + kTileW - 1, ty1 = ty0 + kTileH - 1;
+  for (int k = im.op0 + tid; k < im.op1; k += kTileW * kTileH) {
     const b200va_rect_op o = p.ops[k];
-    const int x1 = min(o.x1, o.x2), x2 = max(o.x1, o.x2), y1 = min(o.y1, o.y2), y2 = max(o.y1, o.y2);
-    bool hit;
-    if (o.kind) {
-      hit = in_box(x, y, x1, y1, x2, y2);
-    } else {
-      hit = in_box(x, y, x1, y1 - 1, x2, y1 + 1) || in_box(x, y, x1, y2 - 1, x2, y2 + 1) ||
-            in_box(x, y, x1 - 1, y1, x1 + 1, y2) || in_box(x, y, x2 - 1, y1, x2 + 1, y2);
+    const int x1 = min(o.x1, o.x2) - 1, x2 = max(o.x1, o.x2) + 1, y1 = min(o.y1, o.y2) - 1, y2 = max(o.y1, o.y2) + 1;
+    if (x1 <= tx1 && x2 >= tx0 && y1 <= ty1 && y2 >= ty0) {
+      const int slot = atomicAdd(&s_n, 1);
+      if (slot < kTileOps) s_ops[slot] = k;
     }
-    if (hit) {
-      uint8_t* d = im.img + (long long)y * im.pitch + (size_t)x * 3;
-      d[0] = o.b;
-      d[1] = o.g;
-      d[2] = o.r;
-      return;
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n == 0) return;
+  const int x = tx0 + threadIdx.x, y = ty0 + threadIdx.y;
+  if (x >= im.w || y >= im.h) return;
+  int best = -1;
+  if (n <= kTileOps) {
+    for (int i = 0; i < n; ++i) {
+      const int k = s_ops[i];
+      if (k > best && op_hits(p.ops[k], x, y)) best = k;
     }
+  } else {  // a tile under more operations than the list holds: walk the whole list backwards
+    for (int k = im.op1 - 1; k >= im.op0; --k)
+      if (op_hits(p.ops[k], x, y)) {
+        best = k;
+        break;
+      }
+  }
+  if (best >= 0) {
+    const b200va_rect_op o = p.ops[best];
+    uint8_t* d = im.img + (long long)y * im.pitch + (size_t)x * 3;
+    d[0] = o.b;
+    d[1] = o.g;
+    d[2] = o.r;
   }
 }
 
@@ -268,7 +335,11 @@ extern "C" int b200va_resize_area_u8(b200va_handle h, const uint8_t* const* fram
         p.f[i] = AreaFrame{frames[b], dst[b], src_pitch ? (long long)src_pitch[b] : 3ll * sw, sh, sw};
       }
       const dim3 grid((dw + 255) / 256, dh, n);
-      if (fast) k_area_fast<<<grid, 256, 0, st>>>(p);
+      bool vec = fast && iscale_x == 2 && iscale_y == 2 && dw % 4 == 0;
+      for (int i = 0; i < n && vec; ++i)
+        vec = ((uintptr_t)p.f[i].src % 8 == 0) && (p.f[i].pitch % 8 == 0) && ((uintptr_t)p.f[i].dst % 4 == 0);
+      if (vec) k_area_2x2_vec<<<dim3((dw / 4 + 255) / 256, dh, n), 256, 0, st>>>(p);
+      else if (fast) k_area_fast<<<grid, 256, 0, st>>>(p);
       else k_area_general<<<grid, 256, 0, st>>>(p);
       LAUNCH_CHECK(h);
     }
@@ -319,7 +390,7 @@ extern "C" int b200va_draw_rects(b200va_handle h, uint8_t* const* images, const 
       mh = std::max(mh, img_h[b]);
       mw = std::max(mw, img_w[b]);
     }
-    k_draw_rects<<<dim3((mw + 255) / 256, mh, n), 256, 0, st>>>(p);
+    k_draw_rects<<<dim3((mw + kTileW - 1) / kTileW, (mh + kTileH - 1) / kTileH, n), dim3(kTileW, kTileH), 0, st>>>(p);
     LAUNCH_CHECK(h);
   }
   return B200VA_OK;

