@@ -322,6 +322,46 @@ B200VA_API int b200va_tracker_reset(b200va_handle h, int stream_slot, void* stre
 /* Set the next id of the shared counter (default 1, like itertools.count(1)). */
 B200VA_API int b200va_tracker_set_next_id(b200va_handle h, int64_t next_id, void* stream);
 
+/* ---- a12 on the device: the per-stream gates and the adaptive-FPS state -----------------------
+ * Replaces, for a batch of streams and without a host round trip, the gate logic of StreamWorker._process_packet:
+ * `self._frame_index += 1` (pipeline.py:144), the motion decision `count / size >= threshold`
+ * (frame_filter.py:38-40, pipeline.py:156-163; a stream's first frame always passes), the adaptive-FPS test
+ * `(self._frame_index - 1) % self._process_every != 0` (pipeline.py:165-170) and _adjust_adaptive_state
+ * (pipeline.py:242-262).  frame_index, idle_frames and process_every live in the handle per slot.
+ *
+ * b200va_gates_decide   after b200va_motion: writes skip_out[i] (DEVICE uint8 [batch]) = B200VA_GATE_PROCESS,
+ *                       _SKIP_MOTION or _SKIP_ADAPTIVE.  `changed` = b200va_motion's changed_out (DEVICE; may be NULL
+ *                       when no gate uses the motion filter); gates[i].changed_index picks the entry.
+ * b200va_set_skip_mask  makes every later b200va_preprocess / b200va_preprocess_geom / b200va_postprocess* /
+ *                       b200va_tracker_update* / b200va_tick call on this handle read `skip` (DEVICE uint8, one flag
+ *                       per batch position, same order in all of them) ON THE DEVICE: a flagged frame is not
+ *                       letterboxed (its rows of the output tensor are left as they are) and not decoded, its
+ *                       detection count is 0, and its stream's tracker update is `update(stream, [])`
+ *                       (_skip_frame, pipeline.py:214-222).  NULL switches the mask off.  The pointer is read by
+ *                       the kernels, not by the call: it must stay valid while they run.
+ * b200va_gates_commit   after the tracker update: _adjust_adaptive_state(len(filtered), len(tracks)) from the
+ *                       device-side counts (det_count: b200va_dets.count, trk_count: b200va_tracks.count), and
+ *                       state_out (DEVICE int32 [batch, 4], may be NULL) = {skip flag, process_every, idle_frames,
+ *                       frame_index} after this frame -- what the caller copies back with its result tables. */
+enum b200va_gate_decision { B200VA_GATE_PROCESS = 0, B200VA_GATE_SKIP_MOTION = 1, B200VA_GATE_SKIP_ADAPTIVE = 2 };
+typedef struct b200va_gate {
+  int32_t slot;              /* gate-state slot in [0, max_streams) (the stream's tracker slot)               */
+  int32_t motion;            /* stream.motion_filter (config.py:67-73)                                        */
+  int32_t changed_index;     /* index of this stream in `changed`; -1 = no motion result for it this tick      */
+  int32_t adaptive;          /* stream.adaptive_fps                                                           */
+  int32_t max_process_every; /* max(1, int(round(target_fps / max(min_target_fps, 1)))) (pipeline.py:107-111) */
+  int32_t idle_tolerance;    /* max(int(idle_frame_tolerance), 1) (pipeline.py:112)                           */
+  double motion_threshold;   /* MotionFilterConfig.threshold                                                  */
+  int64_t pixels;            /* thresh.size: height * width of the frame the motion gate saw                  */
+} b200va_gate;
+B200VA_API int b200va_gates_decide(b200va_handle h, const b200va_gate* gates /* HOST [batch] */, int batch,
+                                   const int32_t* changed, uint8_t* skip_out, void* stream);
+B200VA_API int b200va_gates_commit(b200va_handle h, const b200va_gate* gates /* HOST [batch] */, int batch,
+                                   const int32_t* det_count, const int32_t* trk_count, const uint8_t* skip,
+                                   int32_t* state_out, void* stream);
+B200VA_API int b200va_gates_reset(b200va_handle h, int slot, void* stream);
+B200VA_API int b200va_set_skip_mask(b200va_handle h, const uint8_t* skip /* DEVICE or NULL */);
+
 /* ---- Ultralytics semantics (additive) ---------------------------------
  * What `YOLO(...).predict(frame, conf, iou, classes, half)` -- the call UltralyticsDetector.predict makes
  * (detector.py:147-155) -- does around the model forward.  ultralytics==8.3.209 (pylock.toml:1432-1433) is not

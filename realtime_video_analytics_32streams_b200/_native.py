@@ -60,6 +60,17 @@ class Tracks(C.Structure):
                 ("age", C.c_void_p), ("hits", C.c_void_p), ("count", C.c_void_p), ("rows", C.c_int32)]
 
 
+class Gate(C.Structure):
+    """``b200va_gate`` (include/b200va.h): one stream's gates for the device-side decisions (pipeline.py:104-116, 156-170)."""
+
+    _fields_ = [("slot", C.c_int32), ("motion", C.c_int32), ("changed_index", C.c_int32), ("adaptive", C.c_int32),
+                ("max_process_every", C.c_int32), ("idle_tolerance", C.c_int32), ("motion_threshold", C.c_double),
+                ("pixels", C.c_int64)]
+
+
+GATE_PROCESS, GATE_SKIP_MOTION, GATE_SKIP_ADAPTIVE = 0, 1, 2
+
+
 class RectOp(C.Structure):
     """``b200va_rect_op`` (include/b200va.h): kind 0 = thickness-2 outline, 1 = filled."""
 
@@ -114,6 +125,7 @@ EXPORTS = (
     "b200va_letterbox_meta_ultralytics", "b200va_preprocess_geom", "b200va_postprocess_ultralytics",
     "b200va_motion_preprocess", "b200va_set_profiling", "b200va_get_phase_times",
     "b200va_read_status_async", "b200va_resize_area_u8", "b200va_draw_rects", "b200va_tracks_json",
+    "b200va_gates_decide", "b200va_gates_commit", "b200va_gates_reset", "b200va_set_skip_mask",
 )
 PHASES = ("upload", "roi", "resize", "motion", "preprocess", "decode", "nms", "tracker", "dfl", "tick", "egress")  # enum b200va_phase
 
@@ -177,6 +189,10 @@ def load_library() -> C.CDLL:
     lib.b200va_tracker_set_next_id.argtypes = [vp, C.c_int64, vp]
     lib.b200va_resize_area_u8.argtypes = [vp, C.POINTER(vp), ip, ip, i64p, C.c_int, C.POINTER(vp), ip, ip, vp]
     lib.b200va_draw_rects.argtypes = [vp, C.POINTER(vp), ip, ip, i64p, C.c_int, C.POINTER(RectOp), ip, vp]
+    lib.b200va_gates_decide.argtypes = [vp, C.POINTER(Gate), C.c_int, vp, vp, vp]
+    lib.b200va_gates_commit.argtypes = [vp, C.POINTER(Gate), C.c_int, vp, vp, vp, vp, vp]
+    lib.b200va_gates_reset.argtypes = [vp, C.c_int, vp]
+    lib.b200va_set_skip_mask.argtypes = [vp, vp]
     lib.b200va_tracks_json.restype = C.c_int64
     lib.b200va_tracks_json.argtypes = [C.c_char_p, C.c_int64, vp, vp, vp, vp, C.c_int, C.c_char_p, vp, C.c_int64]
     for name in EXPORTS:
@@ -759,6 +775,32 @@ class Handle:
     def tick(self, plan: TickPlan) -> None:
         """Run a prepared tick on the current stream (results land in the plan's buffers)."""
         self._check(self.lib.b200va_tick(self._h, C.byref(plan.args), self._stream()))
+
+    # -- a12 on the device: gates --------------------------------------------------------------
+    def gates_decide(self, gates, changed, skip_out) -> None:
+        """``gates``: a ctypes array of ``Gate``; ``changed``: the int32 device tensor ``motion`` returned (or None);
+        ``skip_out``: uint8 device tensor [len(gates)] receiving GATE_PROCESS / GATE_SKIP_MOTION / GATE_SKIP_ADAPTIVE."""
+        self._check(self.lib.b200va_gates_decide(self._h, gates, len(gates),
+                                                 C.c_void_p(changed.data_ptr()) if changed is not None else None,
+                                                 C.c_void_p(skip_out.data_ptr()), self._stream()))
+
+    def gates_commit(self, gates, det_count, trk_count, skip, state_out) -> None:
+        """``_adjust_adaptive_state`` on the device; ``state_out``: int32 device tensor [len(gates), 4] =
+        (skip flag, process_every, idle_frames, frame_index)."""
+        self._check(self.lib.b200va_gates_commit(self._h, gates, len(gates), C.c_void_p(det_count.data_ptr()),
+                                                 C.c_void_p(trk_count.data_ptr()),
+                                                 C.c_void_p(skip.data_ptr()) if skip is not None else None,
+                                                 C.c_void_p(state_out.data_ptr()) if state_out is not None else None,
+                                                 self._stream()))
+
+    def gates_reset(self, slot: int) -> None:
+        self._check(self.lib.b200va_gates_reset(self._h, int(slot), self._stream()))
+
+    def set_skip_mask(self, skip) -> None:
+        """Device uint8 tensor (one flag per batch position) read by the kernels of every later preprocess /
+        postprocess / tracker_update / tick call, or None to switch the mask off.  The caller keeps the tensor alive."""
+        self._skip_mask = skip
+        self._check(self.lib.b200va_set_skip_mask(self._h, C.c_void_p(skip.data_ptr()) if skip is not None else None))
 
     def tracker_reset(self, slot: int) -> None:
         self._check(self.lib.b200va_tracker_reset(self._h, int(slot), self._stream()))

@@ -11,6 +11,8 @@ void postprocess_release(b200va_ctx* h);   // postprocess.cu
 void egress_destroy(b200va_ctx* h);        // egress.cu
 int preprocess_configure(b200va_ctx* h);   // preprocess.cu
 int filters_configure(b200va_ctx* h);      // filters.cu
+int gates_create(b200va_ctx* h);           // gates.cu
+void gates_destroy(b200va_ctx* h);         // gates.cu
 
 extern "C" int b200va_version(void) { return B200VA_VERSION; }
 
@@ -129,6 +131,8 @@ static int create_impl(b200va_ctx* h) {
   if (rc) return rc;
   rc = tracker_state_create(h);
   if (rc) return rc;
+  rc = gates_create(h);
+  if (rc) return rc;
   if (cudaHostAlloc((void**)&h->nms_stats_host, 64, cudaHostAllocMapped) == cudaSuccess) {
     memset(h->nms_stats_host, 0, 64);
     if (cudaHostGetDevicePointer((void**)&h->nms_stats_dev, h->nms_stats_host, 0) != cudaSuccess) h->nms_stats_dev = nullptr;
@@ -174,6 +178,7 @@ extern "C" int b200va_destroy(b200va_handle h) {
     postprocess_release(h);
     egress_destroy(h);
     tracker_state_destroy(h);
+    gates_destroy(h);
     tap_cache_destroy(h);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);

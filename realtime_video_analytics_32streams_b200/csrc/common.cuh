@@ -58,6 +58,9 @@ struct b200va_ctx {
   void* roi_scratch = nullptr;  // device, ROI_SCRATCH_BYTES
   // ---- tracker ----
   TrackerState* tracker = nullptr;
+  // ---- device-side gates (gates.cu): skip mask read by the letterbox, decode, NMS and tracker kernels ----
+  const uint8_t* skip_dev = nullptr;  // DEVICE uint8 [batch] or NULL (b200va_set_skip_mask)
+  void* gates = nullptr;              // gates.cu: per-slot gate state
   void* egress = nullptr;  // egress.cu: INTER_AREA tables per geometry, device copy of the rectangle list
   // ---- b200va_tick: second stream for the post-process + tracker branch ----
   cudaStream_t side_stream = nullptr;    // non-blocking, highest priority (its 32-CTA kernels slot in first)

@@ -40,6 +40,7 @@ struct PostParams {
   int use_obj;  // multiply class scores by column 4
   float conf_thr;
   long long* dbg;  // timing builds: timeline stamps
+  const uint8_t* skip;  // device-side gates: frames with a non-zero flag are not decoded (indexed by frame0 + frame)
   int ultra;    // Ultralytics semantics: strict `>` threshold, boxes stay in network-input pixels, equal scores keep
                 // the lower anchor first (torchvision's stable descending sort)
 };
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(64) k_decode_cm(const __grid_constant__ PostPa
   griddep_launch_dependents();  // the NMS kernel may start its prologue now; its griddep_wait() still waits for this grid
   TIMELINE_BEGIN(p.dbg, 40);
   const int frame = blockIdx.y;
+  if (p.skip && p.skip[frame0 + frame]) return;
   const int lane = threadIdx.x & 31;
   const int a0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   const float* __restrict__ hd = p.head + (size_t)(frame0 + frame) * p.C * p.A;
@@ -246,6 +248,7 @@ __global__ void __launch_bounds__(32 * kSplitParts) k_decode_cm_split(const __gr
   __shared__ int s_cls[kSplitParts - 1][4][32];
   __shared__ unsigned s_nan[kSplitParts - 1][32];
   const int frame = blockIdx.y;
+  if (p.skip && p.skip[frame0 + frame]) return;
   const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
   const int a0 = (blockIdx.x * 32 + lane) * 4;
   const int A = p.A, C = p.C, cls0 = p.cls0;
@@ -557,6 +560,7 @@ __global__ void __launch_bounds__(32 * (kRingWarps + 1)) k_decode_ring(const __g
 __global__ void __launch_bounds__(256) k_decode_am(const __grid_constant__ PostParams p, int frame0) {
   griddep_launch_dependents();  // the NMS kernel may start its prologue now; its griddep_wait() still waits for this grid
   const int frame = blockIdx.y;
+  if (p.skip && p.skip[frame0 + frame]) return;
   const int lane = threadIdx.x & 31;
   const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (a >= p.A) return;
@@ -623,6 +627,7 @@ struct NmsParams {
   int grid_off;  // byte offset of the NmsGrid in dynamic shared memory; 0 = no grid (survivors-vs-tail scan instead)
   int* stats;    // host-mapped word: set by frames with more than 256 candidates (the host picks the next variant from it)
   double iou_thr64;
+  const uint8_t* skip;  // device-side gates (already offset to this launch's first frame): flagged frames emit nothing
   PostFrame f[B200VA_LAUNCH_FRAMES];
 };
 static_assert(sizeof(NmsParams) <= 4000, "kernel parameter block too large");
@@ -688,7 +693,7 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
   static_assert(NT >= 128 && NT % 32 == 0, "bad CTA width");
   const int tid = threadIdx.x;
   PHASE_STAMP(p.dbg, 16);
-  const int n_raw = p.cand_count[frame];
+  const int n_raw = (p.skip && p.skip[frame]) ? 0 : p.cand_count[frame];  // a gated frame was not decoded either
   const int n = min(n_raw, p.max_cand);
   int np2 = 64;
   while (np2 < n) np2 <<= 1;
@@ -1365,6 +1370,7 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
     p.cls0 = p.use_obj ? 5 : 4;
     p.conf_thr = (float)conf_thr;  // NEP-50 weak scalar: compared in float32 (detector.py:312)
     p.ultra = ultra ? 1 : 0;
+    p.skip = h->skip_dev;
     {
     PhaseScope phase(h, B200VA_PHASE_DECODE, st);
     if (layout == B200VA_HEAD_CHANNEL_MAJOR) {
@@ -1381,7 +1387,7 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
       // kernel, and neither can be -- a pure 90 MB read of this tensor takes 19.4 us on a B200 whatever fetches it
       // (linear LDG, 1-D bulk copies with enough issuing warps, tensor-map boxes: tools/readbw.cu,
       // profiles/r2_readbw.log), and k_decode_cm<4> needs 20.1 us.
-      bool ring_ok = vec4 && anchors >= 128 && impl == 2;
+      bool ring_ok = vec4 && anchors >= 128 && impl == 2 && !h->skip_dev;
       RingCfg rc;
       int ring_ctas = 0;
       size_t ring_smem = 0;
@@ -1447,6 +1453,7 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
     q.ultra_agnostic = ultra ? ultra->agnostic : 0;
     q.max_det_cap = ultra ? ultra->max_det : 0;
     q.grid_off = (int)nms_grid_offset(h->cfg.max_candidates);
+    q.skip = h->skip_dev ? h->skip_dev + base : nullptr;
     q.iou_thr64 = iou_thr;  // torchvision's CPU kernel compares the float32 IoU with the double threshold
     memcpy(q.f, p.f, sizeof(q.f));
     // dense scenes (more than 256 candidates in some frame of the previous launch) take the grid variant; the

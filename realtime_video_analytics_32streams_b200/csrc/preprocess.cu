@@ -42,6 +42,7 @@ struct PreParams {
   int rows_per_stage;  // 1 when no frame of the launch ever needs the second source row
   int keep_pad_rows;   // B200VA_OUT_FLAG_PADS_VALID: full-width pad rows of `out` already hold the pad value
   long long* dbg;      // timing builds: timeline stamps
+  const uint8_t* skip; // device-side gates: frames whose flag is non-zero are not letterboxed (indexed by out_idx)
   int pdl_wait;        // launched as a programmatic dependent that must not touch HBM before its primary is done (tick schedule 5)
 };
 static_assert(sizeof(PreParams) <= 4000, "kernel parameter block too large");
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(kThreads) k_letterbox(const __grid_constant__ 
   TIMELINE_BEGIN(p.dbg, 42);
   const int frame = blockIdx.y;
   const PreFrame& f = p.f[frame];
+  if (p.skip && p.skip[f.out_idx]) return;  // gated off on the device (pipeline.py:156-170): nobody reads this frame's tensor
   const TapX* __restrict__ xt = reinterpret_cast<const TapX*>(p.tabs + f.xtab);
   const TapY* __restrict__ yt = reinterpret_cast<const TapY*>(p.tabs + f.ytab);
   const int S = p.stages;
@@ -644,6 +646,7 @@ static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* 
       }
       p.tabs = h->taps->arena;
       p.dbg = h->dbg;
+      p.skip = outs ? nullptr : h->skip_dev;  // the downsample runs before the gates (pipeline.py:152-154)
       p.pdl_wait = (h->pdl_preprocess && h->pdl_preprocess_wait) ? 1 : 0;
       p.out = out;
       p.dst_h = dst_h;

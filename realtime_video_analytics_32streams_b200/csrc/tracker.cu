@@ -134,6 +134,7 @@ int tracker_fill_params(b200va_ctx* h, TrkParams& p, const int* stream_slots, in
   p.flags = h->status_flags;
   p.dbg = h->dbg;
   p.stats = h->nms_stats_dev;
+  p.skip_dev = h->skip_dev;
   return B200VA_OK;
 }
 

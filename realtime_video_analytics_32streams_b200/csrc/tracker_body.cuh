@@ -29,6 +29,7 @@ struct TrkParams {
   double det_scale[B200VA_MAX_BATCH];
   long long id_base[B200VA_MAX_BATCH];
   uint8_t skip[B200VA_MAX_BATCH];
+  const uint8_t* skip_dev;  // device-side gates: [batch] flags decided on the device (b200va_set_skip_mask), OR-ed with skip[]
   // detections (one of the two sources)
   const float* f_box;
   const float* f_conf;
@@ -208,7 +209,7 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
   int32_t* age_c = S.age[cur] + sb;
   int32_t* hits_c = S.hits[cur] + sb;
   const int T0 = S.count[slot];
-  const int D = p.skip[bi] ? 0 : min(p.d_count[bi], p.max_dets);
+  const int D = (p.skip[bi] || (p.skip_dev && p.skip_dev[bi])) ? 0 : min(p.d_count[bi], p.max_dets);
   // phase A is bound by dependent shared-memory latency on one SM and scales with the warp count (dense config,
   // 313 detections x 365 tracks: 131 us with 256 threads, 84 us with 512, 63 us with 1024), while a small stream
   // (25 x 25) only pays for the wider barriers (19 us with 256, 22 us with 1024): the surplus warps of a small
@@ -600,7 +601,7 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
 // decides (uniformly for the CTA) whether the working table fits the shared memory this launch was given.
 __device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi, uint8_t* const smem_raw) {
   const int slot = p.slots[bi];
-  const int need = p.st.count[slot] + (p.skip[bi] ? 0 : min(p.d_count[bi], p.max_dets));
+  const int need = p.st.count[slot] + ((p.skip[bi] || (p.skip_dev && p.skip_dev[bi])) ? 0 : min(p.d_count[bi], p.max_dets));
   if (threadIdx.x == 0 && need > 256) atomicMax(p.st.need_max, need);
   __shared__ TrkShared sh;
   if (need <= p.smem_tracks) tracker_stream_impl<false>(p, bi, smem_raw, p.smem_tracks, sh);

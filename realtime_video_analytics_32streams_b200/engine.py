@@ -147,6 +147,11 @@ class _TickCtx:
         self.host_dets = {k: v.numpy() for k, v in self.host_dets_t.items() if not k.startswith("_")}
         self.host_tracks = {k: v.numpy() for k, v in self.host_tracks_t.items() if not k.startswith("_")}
         self.status = t.zeros(h.STATUS_WORDS, dtype=t.int32).pin_memory()  # capacity flags, copied back with the tables
+        # device-side gates: skip flags decided on the device and (skip, process_every, idle_frames, frame_index) per row
+        self.skip = t.zeros((n,), dtype=t.uint8, device=h.device)
+        self.gate_state = t.zeros((n, 4), dtype=t.int32, device=h.device)
+        self.host_gate_state = t.zeros((n, 4), dtype=t.int32).pin_memory()
+        self.device_gates = False
         self.done = t.cuda.Event()
         self.busy = False
         self.gen = 0       # bumped by every submit that takes these buffers (FrameResult lifetime check)
@@ -168,8 +173,13 @@ class HotPathEngine:
 
     def __init__(self, streams: Sequence, detector_config, tracker_config, infer: Callable,
                  handle: Optional[_native.Handle] = None, input_hw=None, depth: int = 2, static_pads: bool = True,
-                 on_overflow: str = "raise", profile: bool = False):
-        """``on_overflow``: what ``collect`` does when a frame exceeded ``max_candidates`` / ``max_dets`` /
+                 on_overflow: str = "raise", profile: bool = False, device_gates: bool = False):
+        """``device_gates``: take the motion and adaptive-FPS decisions on the device (``b200va_gates_decide`` /
+        ``b200va_gates_commit``): no host round trip inside a tick, every live frame keeps its batch position (``infer``
+        sees all of them; rows of gated-off frames hold stale pixels and their heads are ignored), and ticks may be
+        pipelined (``submit`` before ``collect``) even for streams with motion_filter / adaptive_fps.  Results are
+        identical to the host-side gates.
+        ``on_overflow``: what ``collect`` does when a frame exceeded ``max_candidates`` / ``max_dets`` /
         ``max_tracks`` (rows were dropped; the reference has no such limits): "raise" (default) or "warn".
         ``profile``: record per-phase device times (``FrameResult.device_ms``); costs one event pair per phase."""
         if on_overflow not in ("raise", "warn"):
@@ -197,8 +207,12 @@ class HotPathEngine:
         # Needs an `infer` that does not write into its input; pass static_pads=False otherwise.
         self.static_pads = bool(static_pads)
         # a tick's gates depend on the previous tick's results for these features
-        self.sequential = any(getattr(s, "motion_filter", False) or getattr(s, "adaptive_fps", False)
-                              for s in self.streams)
+        self.device_gates = bool(device_gates)
+        self.sequential = (not self.device_gates) and any(getattr(s, "motion_filter", False) or getattr(s, "adaptive_fps", False)
+                                                          for s in self.streams)
+        if self.device_gates:
+            for s in self.streams:
+                self.h.gates_reset(self.tracker.slot_of(s.name))
 
     def reset_tracks(self) -> None:
         """Drop every stream's tracks (the id counter keeps running, like a reference tracker that lost its streams)."""
@@ -294,9 +308,12 @@ class HotPathEngine:
                 work[k] = s
                 work_masks[k] = None  # the ROI is already baked into the downsampled frame
 
+        mot = [k for k, st in enumerate(states) if getattr(st.cfg, "motion_filter", False)]
+        if self.device_gates:
+            return self._submit_device_gates(ctx, live, names, states, ids, work, work_masks, ratios, mot, infer_ctx)
+
         # 3. motion gate (one launch for every stream that has it enabled, one count read-back)
         skip_reason: List[Optional[str]] = [None] * len(live)
-        mot = [k for k, st in enumerate(states) if getattr(st.cfg, "motion_filter", False)]
         if mot:
             prevs, nexts = [], []
             for k in mot:
@@ -351,8 +368,73 @@ class HotPathEngine:
         self.h.read_status_async(ctx.status)
         ctx.done.record()
         ctx.busy = True
+        ctx.device_gates = False
         ctx.order, ctx.n_act, ctx.names, ctx.ids, ctx.states = order, n_act, names, ids, states
         ctx.skip_reason, ctx.scale, ctx.live = skip_reason, scale, live
+        return ctx
+
+    def _submit_device_gates(self, ctx, live, names, states, ids, work, work_masks, ratios, mot, infer_ctx):
+        """Steps 3-9 of ``submit`` with the gates on the device: nothing here waits for the GPU."""
+        h = self.h
+        nb = len(live)
+        changed = None
+        if mot:
+            prevs, nexts = [], []
+            for k in mot:
+                st = states[k]
+                if st.motion is None:
+                    st.motion = MotionFilter(MotionFilterConfig(enable=True, threshold=st.cfg.motion_threshold),
+                                             tuple(work[k].shape), handle=h)
+                p, n = st.motion.buffers(work[k].shape[0], work[k].shape[1])
+                prevs.append(p)
+                nexts.append(n)
+            changed = h.motion([work[k] for k in mot], prevs, nexts, [work_masks[k] for k in mot], self._changed[:len(mot)])
+            for k in mot:
+                states[k].motion.advance()
+        gates = (_native.Gate * nb)()
+        where = {k: j for j, k in enumerate(mot)}
+        for k, st in enumerate(states):
+            g = gates[k]
+            g.slot = self.tracker.slot_of(names[k])
+            g.motion = 1 if k in where else 0
+            g.changed_index = where.get(k, -1)
+            g.adaptive = 1 if st.adaptive else 0
+            g.max_process_every = max(st.max_process_every, 1)
+            g.idle_tolerance = max(st.idle_tolerance, 1)
+            g.motion_threshold = float(st.cfg.motion_threshold) if k in where else 0.0
+            g.pixels = int(work[k].shape[0]) * int(work[k].shape[1])
+        skip = ctx.skip[:nb]
+        h.gates_decide(gates, changed, skip)
+        dets = {k_: v[:nb] for k_, v in ctx.dets.items() if not k_.startswith("_")}
+        out = {k_: v[:nb] for k_, v in ctx.tracks.items() if not k_.startswith("_")}
+        try:
+            net = self._net_in(nb)
+            pads = self._pads_flag(work)
+            # a batch position whose pad rows were never written must be letterboxed whatever its gate says
+            h.set_skip_mask(skip if pads else None)
+            tensor, metas = h.preprocess(self._frame_batch(work, work_masks), self.detector.input_hw,
+                                         self.detector._fmt | pads, out=net)
+            h.set_skip_mask(skip)
+            self.active_streams = list(live)
+            head = self.detector._infer(tensor) if infer_ctx is None else self.detector._infer_fn(tensor, infer_ctx)
+            head = self.detector._as_head(head)
+            if head.dim() != 3 or head.shape[0] != nb:
+                raise ValueError(f"infer returned {tuple(head.shape)} for a batch of {nb}")
+            self.detector._run_post(head, metas, dets)
+            scale = [1.0 / max(r, 1e-6) if r < 0.999 else 1.0 for r in ratios]
+            self.tracker.update_batch(names, dets, det_scale=scale if any(s != 1.0 for s in scale) else None, out=out)
+            h.gates_commit(gates, dets["count"], out["count"], skip, ctx.gate_state[:nb])
+        finally:
+            h.set_skip_mask(None)
+        ctx.host_dets_t["_flat"].copy_(ctx.dets["_flat"], non_blocking=True)
+        ctx.host_tracks_t["_flat"].copy_(ctx.tracks["_flat"], non_blocking=True)
+        ctx.host_gate_state.copy_(ctx.gate_state, non_blocking=True)
+        h.read_status_async(ctx.status)
+        ctx.done.record()
+        ctx.busy = True
+        ctx.device_gates = True
+        ctx.order, ctx.n_act, ctx.names, ctx.ids, ctx.states = list(range(nb)), nb, names, ids, states
+        ctx.skip_reason, ctx.scale, ctx.live = [None] * nb, scale, live
         return ctx
 
     def collect(self, ctx: _TickCtx) -> List[FrameResult]:
@@ -370,7 +452,19 @@ class HotPathEngine:
         det_counts = ctx.host_dets["count"]
         trk_counts = ctx.host_tracks["count"]
         results: List[Optional[FrameResult]] = [None] * len(ctx.order)
+        gate = ctx.host_gate_state.tolist() if ctx.device_gates else None
         for pos, k in enumerate(ctx.order):
+            if gate is not None:  # decided and committed on the device: mirror the state, do not recompute it
+                flag, pe, idle, _ = gate[pos]
+                processed = flag == _native.GATE_PROCESS
+                ctx.skip_reason[k] = None if processed else ("motion" if flag == _native.GATE_SKIP_MOTION else "adaptive")
+                n_det = int(det_counts[pos]) if processed else 0
+                n_trk = int(trk_counts[pos])
+                if ctx.states[k].adaptive:
+                    ctx.states[k].process_every, ctx.states[k].idle_frames = pe, idle
+                results[k] = FrameResult(ctx.names[k], ctx.ids[k], processed, ctx.skip_reason[k], n_det, n_trk, ctx, pos, phase_ms)
+                results[k].adaptive_state = (ctx.states[k].process_every, ctx.states[k].idle_frames)
+                continue
             processed = pos < ctx.n_act
             n_det = int(det_counts[pos]) if processed else 0
             n_trk = int(trk_counts[pos])

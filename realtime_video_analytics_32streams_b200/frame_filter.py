@@ -108,6 +108,12 @@ class MotionFilter:
         motion_ratio = float(count) / float(hgt * wid)
         return motion_ratio >= self.config.threshold
 
+    def advance(self) -> None:
+        """Device-side gates: the kernel wrote ``next``; the decision itself is taken on the device
+        (``b200va_gates_decide``), so only the ping-pong index moves here."""
+        self._cur = 0 if self._cur < 0 else 1 - self._cur
+        self.last_count = None
+
     def should_process(self, frame, roi_mask=None) -> bool:
         if not self.config.enable:
             return True

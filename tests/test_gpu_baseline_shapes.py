@@ -54,7 +54,10 @@ def _config4_head(s: int, t: int):
 
 
 @pytest.mark.timeout(900)
-def test_config4_engine_32x4k_roi_motion_adaptive_vs_oracle_stream_worker():
+@pytest.mark.parametrize("device_gates", [False, True])
+def test_config4_engine_32x4k_roi_motion_adaptive_vs_oracle_stream_worker(device_gates):
+    """``device_gates=True``: gates decided on the device (b200va_gates_decide / _commit) and ticks PIPELINED -- tick
+    t + 1 is submitted before tick t is collected, which the host-side gates cannot allow for these streams."""
     import torch
     from realtime_video_analytics_32streams_b200 import (DetectorConfig, HotPathEngine, StreamConfig, TrackerConfig,
                                                          _native)
@@ -83,24 +86,37 @@ def test_config4_engine_32x4k_roi_motion_adaptive_vs_oracle_stream_worker():
         eng = HotPathEngine(streams, DetectorConfig(confidence_threshold=conf, iou_threshold=iou), TrackerConfig(**trk_cfg),
                             infer=lambda tensor: torch.from_numpy(
                                 np.stack([_config4_head(s, tick["t"]) for s in eng.active_streams])).to(h.device),
-                            handle=h, input_hw=(640, 640))
+                            handle=h, input_hw=(640, 640), device_gates=device_gates)
         seen = {"motion": 0, "adaptive": 0, "processed": 0, "raised": 0}
-        for t in range(T):
-            tick["t"] = t
-            frames = [sc.frame(t) for sc in scenes]
-            got = eng.tick(frames)
+        pending = None
+        for t in range(T + 1):
+            if t < T:
+                tick["t"] = t
+                frames = [sc.frame(t) for sc in scenes]
+                if device_gates:
+                    ctx, ctx_frames = eng.submit(frames), frames
+                else:
+                    got, got_t, got_frames = eng.tick(frames), t, frames
+            if device_gates:
+                if pending is None:
+                    pending = (ctx, t, ctx_frames)
+                    continue
+                got, got_t, got_frames = eng.collect(pending[0]), pending[1], pending[2]
+                pending = (ctx, t, ctx_frames) if t < T else None
+            elif t == T:
+                break
+            tick["t"] = got_t  # the oracle's infer callback reads it
             for s in range(S):
-                want = workers[s].process(frames[s])
+                want = workers[s].process(got_frames[s])
                 r = got[s]
-                st = eng.state[r.stream_name]
-                assert (r.processed, r.skip_reason) == (want.processed, want.skip_reason), (t, s)
-                assert (st.process_every, st.idle_frames) == (workers[s].process_every, workers[s].idle_frames), (t, s)
+                assert (r.processed, r.skip_reason) == (want.processed, want.skip_reason), (got_t, s)
+                assert r.adaptive_state == (workers[s].process_every, workers[s].idle_frames), (got_t, s)
                 wc, wf, wb = G.dets_arrays(want.detections)
                 gc, gf, gb = G.dets_arrays(r.detections)
-                assert np.array_equal(gc, wc) and np.array_equal(gf, wf) and np.array_equal(gb, wb), (t, s, "detections")
+                assert np.array_equal(gc, wc) and np.array_equal(gf, wf) and np.array_equal(gb, wb), (got_t, s, "detections")
                 wt, gt = G.tracks_arrays(want.tracks), G.tracks_arrays(r.tracks)
                 for k in wt:
-                    assert np.array_equal(gt[k], wt[k]), (t, s, k)
+                    assert np.array_equal(gt[k], wt[k]), (got_t, s, k)
                 seen["processed"] += int(want.processed)
                 if want.skip_reason:
                     seen[want.skip_reason] += 1

@@ -587,7 +587,9 @@ def test_tracker_dense_long_lived(H):
 # ------------------------------------------------------------------------------------------------
 # a12: the per-stream driver, against the reference StreamWorker's recorded behaviour
 # ------------------------------------------------------------------------------------------------
-def test_engine_replays_reference_stream_worker(H):
+@pytest.mark.parametrize("device_gates", [False, True])
+def test_engine_replays_reference_stream_worker(H, device_gates):
+    """``device_gates``: the motion / adaptive-FPS decisions are taken on the device (b200va_gates_decide / _commit)."""
     from test_oracle_golden import replay_pipeline
     from realtime_video_analytics_32streams_b200 import DetectorConfig, HotPathEngine, StreamConfig, TrackerConfig
 
@@ -610,7 +612,7 @@ def test_engine_replays_reference_stream_worker(H):
                 box["eng"] = HotPathEngine(
                     box["streams"], DetectorConfig(confidence_threshold=cfg["conf"], iou_threshold=cfg["iou"]),
                     TrackerConfig(max_age=cfg["max_age"], max_iou_distance=cfg["thr"], min_hits=cfg["min_hits"]),
-                    infer=lambda tensor: box["head"], handle=H, input_hw=cfg["input_hw"])
+                    infer=lambda tensor: box["head"], handle=H, input_hw=cfg["input_hw"], device_gates=device_gates)
             eng = box["eng"]
             box["head"] = cu(head)
             frames = [None, None]
