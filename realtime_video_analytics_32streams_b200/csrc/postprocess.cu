@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(32 * kSplitParts) k_decode_cm_split(const __gr
   __shared__ unsigned s_nan[kSplitParts - 1][32];
   const int frame = blockIdx.y;
   if (p.skip && p.skip[frame0 + frame]) return;
+  TIMELINE_BEGIN(p.dbg, 40);
   const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
   const int a0 = (blockIdx.x * 32 + lane) * 4;
   const int A = p.A, C = p.C, cls0 = p.cls0;
@@ -321,6 +322,7 @@ __global__ void __launch_bounds__(32 * kSplitParts) k_decode_cm_split(const __gr
     if (lane >= o) incl += t;
   }
   const int total = __shfl_sync(0xffffffffu, incl, 31);
+  TIMELINE_END(p.dbg, 40);  // (warps with survivors run a little longer)
   if (total == 0) return;
   int base = 0;
   if (lane == 31) base = atomicAdd(p.cand_count + frame, total);
@@ -628,6 +630,7 @@ struct NmsParams {
   int* stats;    // host-mapped word: set by frames with more than 256 candidates (the host picks the next variant from it)
   double iou_thr64;
   const uint8_t* skip;  // device-side gates (already offset to this launch's first frame): flagged frames emit nothing
+  int dbg_reps;         // timing builds only
   PostFrame f[B200VA_LAUNCH_FRAMES];
 };
 static_assert(sizeof(NmsParams) <= 4000, "kernel parameter block too large");
@@ -687,17 +690,51 @@ constexpr int kNmsThreadsSmall = 256;  // k_post_track: sparse scenes, NMS and t
 // GRID: carries the kept-box grid code.  Two instantiations because the grid path's registers and stack slots slow
 // the common small-n launch (which never runs it) from 9.5 to 14 us when it is compiled in; the host picks per launch
 // from the candidate counts the previous launch reported (NmsParams::stats).
+// Small frames (n <= kSmallN candidates) use their own compact shared-memory layout and a barrier-light schedule:
+// ONE round of global loads (count, keys, boxes and classes of the first kSmallN slots are fetched together,
+// before the count is known), rank sort, gather from shared memory, the whole symmetric n x n suppression bit matrix
+// at once with all threads, then ONE warp resolves the greedy recursion chunk by chunk from the matrix alone (the
+// ballot fixed point per 64 boxes, kept rows OR-ed into the suppression bitmap of the later chunks).  Six block
+// barriers in total instead of four per 64-box chunk; measured on 72 candidates: 15.4 k -> ~7 k SM cycles.
+constexpr int kSmallN = 256;
+constexpr int kSmallPairs = 1536;
+struct SmallNms {
+  unsigned long long keys[kSmallN];
+  unsigned long long sorted[kSmallN];
+  float4 box[kSmallN];   // sorted order (class-shifted in Ultralytics mode)
+  float4 ubox[kSmallN];  // by candidate slot, as decoded
+  int ucls[kSmallN];     // by candidate slot
+  uint16_t scl[kSmallN]; // sorted order
+  uint32_t M[kSmallN][kSmallN / 32];  // M[i] bit j: boxes i and j suppress each other (symmetric predicate)
+  uint32_t supp[kSmallN / 32], keep_w[kSmallN / 32];
+  int keep_off[kSmallN / 64 + 1];
+  int n_pairs;
+  uint32_t pairs[kSmallPairs];  // pairs that are not disjoint: lo | hi << 16
+};
+
+// What the fused kernel's NMS half leaves in shared memory for its tracker half (k_post_track): the first chunk of
+// detections already converted the way the tracker stages them, and the detection count.
+struct DetHandover {
+  TrkShared* sh;
+  double scale;
+  int has_scale;
+};
+
+// Sort + NMS + emit of one frame by one CTA of NT threads.
+// GRID: carries the kept-box grid code.  Two instantiations because the grid path's registers and stack slots slow
+// the common small-n launch (which never runs it) from 9.5 to 14 us when it is compiled in; the host picks per launch
+// from the candidate counts the previous launch reported (NmsParams::stats).
+// The general path of nms_frame (more than kSmallN candidates): bitonic sort, greedy NMS in 64-box chunks, emit.
+// Deliberately NOT inlined: the latency-bound CTAs of a sparse tick stall on instruction fetch more than on anything
+// else (ncu: stall_no_inst 29-33 % of all samples in k_post_track), so the code a small frame never runs must not
+// sit between the lines it does run.
 template <bool GRID, int NT>
-__device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, uint8_t* const smem_raw) {
-  static_assert(!GRID || NT == 1024, "the kept-box grid code assumes 1024 threads");
-  static_assert(NT >= 128 && NT % 32 == 0, "bad CTA width");
+__device__ __noinline__ void nms_general(const NmsParams& p, const int frame, uint8_t* const smem_raw, const int n) {
   const int tid = threadIdx.x;
-  PHASE_STAMP(p.dbg, 16);
-  const int n_raw = (p.skip && p.skip[frame]) ? 0 : p.cand_count[frame];  // a gated frame was not decoded either
-  const int n = min(n_raw, p.max_cand);
+  const size_t cbase = (size_t)frame * p.max_cand;
   int np2 = 64;
   while (np2 < n) np2 <<= 1;
-
+  constexpr bool small = false;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);              // [cap_pow2]
   float4* box = reinterpret_cast<float4*>(smem_raw + (size_t)p.cap_pow2 * 8);               // [cap_pow2]
   uint32_t* supp = reinterpret_cast<uint32_t*>(smem_raw + (size_t)p.cap_pow2 * 24);         // [cap_pow2/32]
@@ -710,45 +747,20 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
   __shared__ uint32_t rows[64][2];
   __shared__ float4 kbox[64];
   __shared__ int kcl[64];
+  SmallNms& sm = *reinterpret_cast<SmallNms*>(smem_raw);  // (never touched here: `small` is false)
+  const DetHandover* const hand = nullptr;
+  const bool aware = p.class_aware != 0;
+  const bool ultra = p.ultra != 0;
+  const float thr = p.iou_thr;
+  const bool thr_nonneg = ultra ? p.iou_thr64 >= 0.0 : thr >= 0.f;
+  const int nchunks = (n + 63) >> 6;
 
-  __syncthreads();
-  if (tid == 0) {
-    if (p.stats && n > 256) *(volatile int*)p.stats = n;  // posted write, dense frames only (an atomic to host memory cost 25 us)
-    p.cand_count[frame] = 0;
-    if (n_raw > p.max_cand) atomicOr(p.flags + FLAG_CAND_OVERFLOW, 1);
-  }
-  if (n == 0) {
-    if (tid == 0) p.out_count[frame] = 0;
-    return;
-  }
-  const size_t cbase = (size_t)frame * p.max_cand;
   for (int i = tid; i < np2; i += NT) keys[i] = i < n ? p.cand_key[cbase + i] : 0ull;
   for (int i = tid; i < np2 / 32; i += NT) supp[i] = 0u;
   __syncthreads();
 
   PHASE_STAMP(p.dbg, 17);
-  if (n <= 256) {
-    // rank sort (small n): keys are unique, so rank_i = #{j : key_j > key_i} is a permutation.  Every thread
-    // streams the whole key array from shared memory (broadcast reads) -- two barriers in total
-    // where a bitonic network needs one per round.  O(n^2) compares: only worth it for small n.
-    unsigned long long* sorted = reinterpret_cast<unsigned long long*>(box);  // box[] is not live yet
-    for (int i = tid; i < n; i += NT) {
-      const unsigned long long ki = keys[i];
-      int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-      int j = 0;
-      for (; j + 4 <= n; j += 4) {
-        r0 += keys[j] > ki;
-        r1 += keys[j + 1] > ki;
-        r2 += keys[j + 2] > ki;
-        r3 += keys[j + 3] > ki;
-      }
-      for (; j < n; ++j) r0 += keys[j] > ki;
-      sorted[r0 + r1 + r2 + r3] = ki;
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += NT) keys[i] = sorted[i];
-    __syncthreads();
-  } else {
+  {
     // bitonic sort, descending.  Only the warps that own a compare-exchange take part (named barrier 1).
     // Thread q owns the q-th pair of a step; for j <= 32 the 32 pairs of a warp lie inside one aligned block of 64
     // keys, so consecutive steps with j <= 32 depend on nothing another warp writes and a __syncwarp separates
@@ -792,11 +804,6 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
   __syncthreads();
 
   PHASE_STAMP(p.dbg, 19);
-  const bool aware = p.class_aware != 0;
-  const bool ultra = p.ultra != 0;
-  const float thr = p.iou_thr;
-  const bool thr_nonneg = ultra ? p.iou_thr64 >= 0.0 : thr >= 0.f;
-  const int nchunks = (n + 63) >> 6;
   // few candidates: the survivors-vs-tail scan is cheaper than keeping the grid
   const bool use_grid = GRID && grid != nullptr && !ultra && thr_nonneg && n > 256;
   const float inv_cw = (float)kGX / (p.f[frame].xmax + 1.0f), inv_ch = (float)kGY / (p.f[frame].ymax + 1.0f);
@@ -1032,7 +1039,6 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
     }
   }
 #endif
-
   PHASE_STAMP(p.dbg, 20);
   // ultralytics: `i = i[:max_det]` on the NMS survivors, before anything else looks at them
   if (ultra) {
@@ -1070,6 +1076,7 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
     }
     __syncthreads();
   }
+  PHASE_STAMP(p.dbg, 54);
   if (tid == 0) {
     int acc = 0;
     for (int ch = 0; ch < nchunks; ++ch) {
@@ -1080,7 +1087,9 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
     p.out_count[frame] = min(acc, p.max_dets);
     if (acc > p.max_dets) atomicOr(p.flags + FLAG_DET_OVERFLOW, 1);
   }
+  PHASE_STAMP(p.dbg, 55);
   __syncthreads();
+  PHASE_STAMP(p.dbg, 56);
   for (int i = tid; i < n; i += NT) {
     const unsigned long long w = ((unsigned long long)keep_w[2 * (i >> 6) + 1] << 32) | keep_w[2 * (i >> 6)];
     if ((w >> (i & 63)) & 1ull) {
@@ -1088,10 +1097,267 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
       if (pos < p.max_dets) {
         const size_t o = (size_t)frame * p.max_dets + pos;
         float4 b = box[i];
-        if (ultra) b = ultra_scale_box(p.cand_box[cbase + (keys[i] & 0x3fffull)], p.f[frame]);  // the un-shifted box
+        const int slot = (int)(keys[i] & 0x3fffull);
+        if (ultra) b = ultra_scale_box(small ? sm.ubox[slot] : p.cand_box[cbase + slot], p.f[frame]);  // the un-shifted box
+        const float cf = unorder_bits((uint32_t)(keys[i] >> 32));
+        const int cl = small ? sm.ucls[slot] : p.cand_cls[cbase + slot];  // the full int32 class id (scl[] holds 16 bits)
         reinterpret_cast<float4*>(p.out_box)[o] = b;
-        p.out_conf[o] = unorder_bits((uint32_t)(keys[i] >> 32));
-        p.out_cls[o] = p.cand_cls[cbase + (keys[i] & 0x3fffull)];  // the full int32 class id (scl[] holds 16 bits)
+        p.out_conf[o] = cf;
+        p.out_cls[o] = cl;
+        if (hand && small && pos < kDetChunk) stage_detection(hand->sh->sd, pos, b, cf, cl, hand->scale, hand->has_scale != 0);
+      }
+    }
+  }
+  PHASE_STAMP(p.dbg, 21);
+}
+
+template <bool GRID, int NT>
+__device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, uint8_t* const smem_raw,
+                                          const DetHandover* hand = nullptr) {
+  static_assert(!GRID || NT == 1024, "the kept-box grid code assumes 1024 threads");
+  static_assert(NT >= kSmallN && NT % 32 == 0, "bad CTA width");
+  const int tid = threadIdx.x;
+  PHASE_STAMP(p.dbg, 16);
+  const size_t cbase = (size_t)frame * p.max_cand;
+  // speculative: the first kSmallN candidate slots, fetched in the same round trip as the count (slots past the count
+  // hold stale rows of earlier frames; they are masked below)
+  unsigned long long k_spec = 0ull;
+  float4 b_spec = make_float4(0.f, 0.f, 0.f, 0.f);
+  int c_spec = 0;
+  if (tid < kSmallN && tid < p.max_cand) {
+    k_spec = p.cand_key[cbase + tid];
+    b_spec = p.cand_box[cbase + tid];
+    c_spec = p.cand_cls[cbase + tid];
+  }
+  const int n_raw = (p.skip && p.skip[frame]) ? 0 : p.cand_count[frame];  // a gated frame was not decoded either
+  const int n = min(n_raw, p.max_cand);
+  const bool small = n <= kSmallN;
+  SmallNms& sm = *reinterpret_cast<SmallNms*>(smem_raw);
+
+
+  __syncthreads();
+  if (tid == 0) {
+    if (p.stats && n > 256) *(volatile int*)p.stats = n;  // posted write, dense frames only (an atomic to host memory cost 25 us)
+    p.cand_count[frame] = 0;
+    if (n_raw > p.max_cand) atomicOr(p.flags + FLAG_CAND_OVERFLOW, 1);
+    if (hand) hand->sh->s_prestaged = n == 0 ? 0 : -1;
+  }
+  PHASE_STAMP(p.dbg, 50);
+  if (n == 0) {
+    if (tid == 0) p.out_count[frame] = 0;
+    return;
+  }
+  const bool aware = p.class_aware != 0;
+  const bool ultra = p.ultra != 0;
+  const float thr = p.iou_thr;
+  const bool thr_nonneg = ultra ? p.iou_thr64 >= 0.0 : thr >= 0.f;
+  const int nchunks = (n + 63) >> 6;
+  if (!small) {
+    nms_general<GRID, NT>(p, frame, smem_raw, n);
+    return;
+  }
+  unsigned long long* const keys = sm.keys;
+  float4* const box = sm.box;
+  uint32_t* const keep_w = sm.keep_w;
+  int* const keep_off = sm.keep_off;
+  {
+    // ---- small frame: one load round, rank sort, full bit matrix, one-warp resolution ----
+    const int words = (n + 31) >> 5;
+    if (tid < kSmallN) {
+      sm.keys[tid] = tid < n ? k_spec : 0ull;
+      sm.ubox[tid] = b_spec;
+      sm.ucls[tid] = c_spec;
+    }
+    for (int w = tid; w < n * (kSmallN / 32); w += NT) (&sm.M[0][0])[w] = 0u;
+    if (tid < kSmallN / 32) sm.supp[tid] = 0u;
+    if (tid == 0) sm.n_pairs = 0;
+    __syncthreads();
+    PHASE_STAMP(p.dbg, 17);
+    if (tid < n) {  // rank sort: keys are unique, rank = number of larger keys
+      const unsigned long long ki = sm.keys[tid];
+      int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+      int j = 0;
+      for (; j + 4 <= n; j += 4) {
+        r0 += sm.keys[j] > ki;
+        r1 += sm.keys[j + 1] > ki;
+        r2 += sm.keys[j + 2] > ki;
+        r3 += sm.keys[j + 3] > ki;
+      }
+      for (; j < n; ++j) r0 += sm.keys[j] > ki;
+      sm.sorted[r0 + r1 + r2 + r3] = ki;
+    }
+    __syncthreads();
+    PHASE_STAMP(p.dbg, 18);
+    if (tid < n) {
+      const unsigned long long k = sm.sorted[tid];
+      const int slot = (int)(k & 0x3fffull);
+      float4 b = sm.ubox[slot];
+      const int cl = sm.ucls[slot];
+      if (p.ultra && !p.ultra_agnostic) {  // boxes = x[:, :4] + x[:, 5:6] * max_wh, float32 (the rounding is part of the semantics)
+        const float c = __fmul_rn((float)cl, 7680.f);
+        b = make_float4(__fadd_rn(b.x, c), __fadd_rn(b.y, c), __fadd_rn(b.z, c), __fadd_rn(b.w, c));
+      }
+      sm.keys[tid] = k;
+      sm.box[tid] = b;
+      sm.scl[tid] = (uint16_t)cl;
+    }
+    __syncthreads();
+    PHASE_STAMP(p.dbg, 19);
+    // The CTA is latency-bound: what a phase costs is the instruction count of its longest warp times ~4.5 cycles, and
+    // a warp in which ONE lane meets an overlapping pair walks all 32 lanes through the IoU formula.  So: pass 1 only
+    // sorts the pairs i < j into "disjoint" (nothing to do: IoU 0 <= thr) and "candidate" (appended to a list), with
+    // every pair visited once and the rows spread evenly -- thread (part, i) takes the pairs {i, i + k mod n} for
+    // k = 1 + part, 1 + part + parts, .. <= n / 2 -- and pass 2 runs the formula on one listed pair per thread, all
+    // lanes converged.  (72 candidates: 7.0 k -> ~1.2 k SM cycles for this phase.)
+    {
+      const int part = (int)(((float)tid + 0.5f) * (1.0f / (float)n));  // tid / n for these small integers
+      const int i = tid - part * n;
+      const int parts = NT / n, half = n >> 1;
+      const float4 bi = sm.box[i];
+      const int ci = sm.scl[i];
+      // which of this thread's pairs are candidates: bit `it` of (c_lo, c_hi) <-> k = 1 + part + it * parts
+      // (at most 128 iterations: n <= 256, parts >= 1)
+      unsigned long long c_lo = 0ull, c_hi = 0ull;
+      if (part < parts) {
+        int it = 0;
+#pragma unroll 1
+        for (int k = 1 + part; k <= half; k += parts, ++it) {
+          int j = i + k;
+          if (j >= n) j -= n;
+          if (!(n & 1) && k == half && i >= half) continue;  // even n: the antipodal pairs come up twice
+          const float4 bj = sm.box[j];
+          if (thr_nonneg && (bj.z <= bi.x || bi.z <= bj.x || bj.w <= bi.y || bi.w <= bj.y)) continue;  // disjoint: IoU 0
+          if (aware && ci != sm.scl[j]) continue;
+          if (it < 64) c_lo |= 1ull << it;
+          else c_hi |= 1ull << (it - 64);
+        }
+      }
+      // one list reservation per warp: exclusive prefix of the lanes' counts, lane 31 draws the block
+      const int mine = __popcll(c_lo) + __popcll(c_hi);
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += v;
+      }
+      int base = 0;
+      if ((tid & 31) == 31 && incl > 0) base = atomicAdd(&sm.n_pairs, incl);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      int slot = base + incl - mine;
+#pragma unroll 1
+      for (int half_w = 0; half_w < 2; ++half_w) {
+        unsigned long long bits = half_w ? c_hi : c_lo;
+        while (bits) {
+          const int it = __ffsll((long long)bits) - 1 + 64 * half_w;
+          bits &= bits - 1ull;
+          int j = i + 1 + part + it * parts;
+          if (j >= n) j -= n;
+          const int lo = min(i, j), hi = max(i, j);
+          if (slot < kSmallPairs) {
+            sm.pairs[slot] = (uint32_t)lo | ((uint32_t)hi << 16);
+          } else if (ultra ? suppresses_tv(sm.box[lo], sm.box[hi], p.iou_thr64) : suppresses(sm.box[lo], sm.box[hi], thr)) {
+            atomicOr(&sm.M[lo][hi >> 5], 1u << (hi & 31));  // list full (a dense cluster): evaluate on the spot
+            atomicOr(&sm.M[hi][lo >> 5], 1u << (lo & 31));
+          }
+          ++slot;
+        }
+      }
+    }
+    PHASE_STAMP(p.dbg, 51);
+    __syncthreads();
+    PHASE_STAMP(p.dbg, 52);
+    {
+      const int listed = min(sm.n_pairs, kSmallPairs);
+#pragma unroll 1
+      for (int q = tid; q < listed; q += NT) {
+        const uint32_t pr = sm.pairs[q];
+        const int lo = (int)(pr & 0xffffu), hi = (int)(pr >> 16);
+        if (ultra ? suppresses_tv(sm.box[lo], sm.box[hi], p.iou_thr64) : suppresses(sm.box[lo], sm.box[hi], thr)) {
+          atomicOr(&sm.M[lo][hi >> 5], 1u << (hi & 31));
+          atomicOr(&sm.M[hi][lo >> 5], 1u << (lo & 31));
+        }
+      }
+    }
+    __syncthreads();
+    PHASE_STAMP(p.dbg, 57);
+    if (tid < 32) {
+      // greedy resolution, chunk by chunk: kept_i = alive_i and no kept j < i of the chunk suppresses i (fixed point
+      // of ballots, see the general path); a chunk's kept rows then mark the later chunks' boxes.  The same warp
+      // then derives what is EMITTED from what is kept -- Ultralytics' `i[:max_det]`, then filter_detections
+      // (detector.py:99-103, float64 compare) -- and the output offsets, so no further block-wide phase is needed.
+      int acc_kept = 0, acc_emit = 0;
+#pragma unroll 1
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int c0 = ch << 6, m = min(64, n - c0);
+        const unsigned long long lo_mask = (1ull << tid) - 1ull, hi_mask = (1ull << (tid + 32)) - 1ull;
+        const int r0 = min(c0 + tid, kSmallN - 1), r1 = min(c0 + tid + 32, kSmallN - 1);
+        const unsigned long long e0 = (((unsigned long long)sm.M[r0][2 * ch + 1] << 32) | sm.M[r0][2 * ch]) & lo_mask;
+        const unsigned long long e1 = (((unsigned long long)sm.M[r1][2 * ch + 1] << 32) | sm.M[r1][2 * ch]) & hi_mask;
+        const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
+        const unsigned long long alive = ~(((unsigned long long)sm.supp[2 * ch + 1] << 32) | sm.supp[2 * ch]) & valid;
+        const bool a0 = (alive >> tid) & 1ull, a1 = (alive >> (tid + 32)) & 1ull;
+        bool k0 = a0, k1 = a1;
+        unsigned long long kept;
+        while (true) {
+          kept = ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32) | __ballot_sync(0xffffffffu, k0);
+          const bool n0 = a0 && !(e0 & kept), n1 = a1 && !(e1 & kept);
+          const unsigned changed = __ballot_sync(0xffffffffu, n0 != k0 || n1 != k1);
+          k0 = n0;
+          k1 = n1;
+          if (!changed) break;
+        }
+#pragma unroll 1
+        for (int w = 2 * ch + 2; w < words; ++w) {
+          uint32_t v = (k0 ? sm.M[r0][w] : 0u) | (k1 ? sm.M[r1][w] : 0u);
+          v = __reduce_or_sync(0xffffffffu, v);
+          if (tid == 0) sm.supp[w] |= v;
+        }
+        bool m0 = k0, m1 = k1;
+        if (ultra) {  // `i = i[:max_det]`: the first max_det_cap survivors, in score order
+          m0 = m0 && acc_kept + __popcll(kept & lo_mask) < p.max_det_cap;
+          m1 = m1 && acc_kept + __popcll(kept & hi_mask) < p.max_det_cap;
+          acc_kept += __popcll(kept);
+        }
+        if (p.use_filter) {
+          m0 = m0 && (double)unorder_bits((uint32_t)(sm.keys[r0] >> 32)) >= p.filter_thr;
+          m1 = m1 && (double)unorder_bits((uint32_t)(sm.keys[r1] >> 32)) >= p.filter_thr;
+        }
+        const uint32_t w0 = __ballot_sync(0xffffffffu, m0), w1 = __ballot_sync(0xffffffffu, m1);
+        if (tid == 0) {
+          sm.keep_w[2 * ch] = w0;
+          sm.keep_w[2 * ch + 1] = w1;
+          sm.keep_off[ch] = acc_emit;
+        }
+        acc_emit += __popc(w0) + __popc(w1);
+        __syncwarp();
+      }
+      if (tid == 0) {
+        sm.keep_off[nchunks] = acc_emit;
+        p.out_count[frame] = min(acc_emit, p.max_dets);
+        if (acc_emit > p.max_dets) atomicOr(p.flags + FLAG_DET_OVERFLOW, 1);
+        if (hand) hand->sh->s_prestaged = min(acc_emit, p.max_dets);  // the emit loop stages the first chunk
+      }
+    }
+    PHASE_STAMP(p.dbg, 53);  // (the barrier before the emit loop below closes this phase)
+  }
+  PHASE_STAMP(p.dbg, 55);
+  __syncthreads();
+  PHASE_STAMP(p.dbg, 56);
+  for (int i = tid; i < n; i += NT) {
+    const unsigned long long w = ((unsigned long long)keep_w[2 * (i >> 6) + 1] << 32) | keep_w[2 * (i >> 6)];
+    if ((w >> (i & 63)) & 1ull) {
+      const int pos = keep_off[i >> 6] + __popcll(w & ((1ull << (i & 63)) - 1ull));
+      if (pos < p.max_dets) {
+        const size_t o = (size_t)frame * p.max_dets + pos;
+        float4 b = box[i];
+        const int slot = (int)(keys[i] & 0x3fffull);
+        if (ultra) b = ultra_scale_box(small ? sm.ubox[slot] : p.cand_box[cbase + slot], p.f[frame]);  // the un-shifted box
+        const float cf = unorder_bits((uint32_t)(keys[i] >> 32));
+        const int cl = small ? sm.ucls[slot] : p.cand_cls[cbase + slot];  // the full int32 class id (scl[] holds 16 bits)
+        reinterpret_cast<float4*>(p.out_box)[o] = b;
+        p.out_conf[o] = cf;
+        p.out_cls[o] = cl;
+        if (hand && small && pos < kDetChunk) stage_detection(hand->sh->sd, pos, b, cf, cl, hand->scale, hand->has_scale != 0);
       }
     }
   }
@@ -1103,6 +1369,18 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
   extern __shared__ __align__(16) uint8_t smem_raw[];
   griddep_launch_dependents();  // a tracker kernel behind this one may be scheduled; its griddep_wait() waits for this grid
   griddep_wait();
+#ifdef B200VA_PHASE_TIMING
+  // developer experiment (B200VA_DBG_REPS=n): run the frame n times in one launch; the stamps of the LAST pass show what
+  // the same code costs once its instructions and data are warm in the SM
+  for (int r = 1; r < p.dbg_reps; ++r) {
+    const int saved = p.cand_count[blockIdx.x];
+    __syncthreads();
+    nms_frame<GRID, kNmsThreads>(p, blockIdx.x, smem_raw);
+    __syncthreads();
+    if (threadIdx.x == 0) p.cand_count[blockIdx.x] = saved;
+    __syncthreads();
+  }
+#endif
   nms_frame<GRID, kNmsThreads>(p, blockIdx.x, smem_raw);
 }
 
@@ -1116,11 +1394,17 @@ __global__ void __launch_bounds__(kNmsThreadsSmall) k_post_track(const __grid_co
   extern __shared__ __align__(16) uint8_t smem_raw[];
   griddep_wait();
   TIMELINE_BEGIN(q.dbg, 44);
-  nms_frame<false, kNmsThreadsSmall>(q, blockIdx.x, smem_raw);
+  __shared__ TrkShared sh;
+  const DetHandover hand{&sh, t.det_scale[blockIdx.x], t.has_scale};
+  // the stream's table header, fetched before the NMS half instead of between the halves (nobody else writes this slot)
+  const int trk_slot = t.slots[blockIdx.x];
+  const int pre_cur = t.st.cur[trk_slot], pre_T0 = t.st.count[trk_slot];
+  // the handover stages float32 detections; a skipped stream (host flag or device mask) takes none
+  nms_frame<false, kNmsThreadsSmall>(q, blockIdx.x, smem_raw, t.f_box ? &hand : nullptr);
   __syncthreads();  // this frame's detections were written by this CTA: visible to all of its threads from here on
   TIMELINE_END(q.dbg, 44);
   TIMELINE_BEGIN(q.dbg, 46);
-  tracker_stream(t, blockIdx.x, smem_raw);
+  tracker_stream(t, blockIdx.x, smem_raw, sh, t.f_box ? sh.s_prestaged : -1, pre_cur, pre_T0);
   TIMELINE_END(q.dbg, 46);  // (threads the tracker retires early never get here; thread 0 always does)
 }
 
@@ -1134,7 +1418,8 @@ static int next_pow2(int v) {
 
 static size_t nms_base_bytes(int max_cand) {
   const size_t cap = (size_t)next_pow2(max_cand);
-  return (cap * 24 + cap / 8 + cap / 8 + (cap / 64 + 1) * 4 + cap * 2 + 64 + 15) & ~(size_t)15;  // keys, boxes, supp, keep_w, keep_off, classes
+  const size_t general = (cap * 24 + cap / 8 + cap / 8 + (cap / 64 + 1) * 4 + cap * 2 + 64 + 15) & ~(size_t)15;  // keys, boxes, supp, keep_w, keep_off, classes
+  return std::max(general, (sizeof(SmallNms) + 15) & ~(size_t)15);  // frames of at most kSmallN candidates use their own layout
 }
 // the kept-box grid is carried when the candidate capacity leaves room for it (cap <= 4096: 106 KB + 21 KB)
 static size_t nms_grid_offset(int max_cand) { return next_pow2(max_cand) <= 4096 ? nms_base_bytes(max_cand) : 0; }
@@ -1449,6 +1734,7 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
     q.use_filter = use_filter;
     q.class_aware = nms_mode == B200VA_NMS_CLASS_AWARE;
     q.dbg = h->dbg;
+    q.dbg_reps = getenv("B200VA_DBG_REPS") ? atoi(getenv("B200VA_DBG_REPS")) : 1;
     q.ultra = ultra ? 1 : 0;
     q.ultra_agnostic = ultra ? ultra->agnostic : 0;
     q.max_det_cap = ultra ? ultra->max_det : 0;

@@ -85,6 +85,7 @@ constexpr int kTrkThreadsMax = 1024;   // widest launch (dense scenes, see track
 constexpr int kTrkThreadsWide = 512;   // default launch width
 constexpr int kTrkThreadsMin = 256;
 constexpr int kDetChunk = 64;  // detections staged in shared memory at a time (two warps cover a chunk)
+constexpr int kTrkPairs = 1024;  // phase A, few pairs: capacity of the overlapping-pair list
 constexpr int kCand = 6;        // candidate slots per detection and kind; more -> exact brute-force scan
 
 struct DetStage {
@@ -98,7 +99,37 @@ struct Cand {
   int pad_;
 };
 
+// One detection into the chunk staging area, converted the way the tracker consumes it (float32 rows of the
+// post-process: exact widening, then StreamWorker._rescale_detections' float64 multiply, pipeline.py:224-240).
+__device__ __forceinline__ void stage_detection(DetStage& sd, int i, float4 f4, float conf, int cls, double scale, bool has_scale) {
+  double4 b = make_double4(f4.x, f4.y, f4.z, f4.w);
+  if (has_scale) {
+    b.x = __dmul_rn(b.x, scale);
+    b.y = __dmul_rn(b.y, scale);
+    b.z = __dmul_rn(b.z, scale);
+    b.w = __dmul_rn(b.w, scale);
+  }
+  sd.box[i] = b;
+  sd.conf[i] = (double)conf;
+  sd.cls[i] = cls;
+}
+
 // Boxes whose intersection is empty have IoU 0, which can never beat best_iou = 0.0 (tracker.py:100-106).
+// A cheap superset of overlaps(): the same eight comparisons on order-preserving integer keys of the doubles' HIGH
+// words (x > y implies key(x) >= key(y), whatever the signs), as `>=`.  It may pass pairs that do not overlap (their
+// IoU then comes out as 0 and is discarded like before) but never rejects one that does; NaN coordinates pass or fail
+// arbitrarily, which is harmless for the same reason.  Integer compares instead of a chain of eight dependent float64
+// compares: the pre-filter runs once per (detection, track) pair on the latency-bound path.
+__device__ __forceinline__ uint32_t hi_key(double v) {
+  const int hi = __double2hiint(v);
+  return (uint32_t)hi ^ ((uint32_t)(hi >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ bool may_overlap(const double4 a, const double4 b) {
+  const uint32_t ax = hi_key(a.x), ay = hi_key(a.y), az = hi_key(a.z), aw = hi_key(a.w);
+  const uint32_t bx = hi_key(b.x), by = hi_key(b.y), bz = hi_key(b.z), bw = hi_key(b.w);
+  return (az >= bx) & (bz >= ax) & (az >= ax) & (bz >= bx) & (aw >= by) & (bw >= ay) & (aw >= ay) & (bw >= by);
+}
+
 __device__ __forceinline__ bool overlaps(const double4 a, const double4 b) {
   return (a.z > b.x) & (b.z > a.x) & (a.z > a.x) & (b.z > b.x) & (a.w > b.y) & (b.w > a.y) & (a.w > a.y) & (b.w > b.y);
 }
@@ -158,6 +189,9 @@ struct TrkShared {
   Cand c_trk[kDetChunk][kCand], c_det[kDetChunk][kCand];
   int n_trk[kDetChunk], n_det[kDetChunk], key[kDetChunk], conflicted[kDetChunk], clist[kDetChunk];
   int s_T, s_new, s_is_last, s_fallback, s_nconf;
+  int n_plist;      // phase A, few pairs: number of listed (overlapping, same class) pairs
+  uint32_t plist[kTrkPairs];  // idx | detection << 16 | (vs track) << 31
+  int s_prestaged;  // fused kernel: detections of this frame (count) whose first chunk the NMS half left in `sd`; -1 = none
   int wsum[kTrkThreadsMax / 32];
   int warp_cnt[kTrkThreadsMax / 32];
   int s_base;
@@ -165,182 +199,16 @@ struct TrkShared {
   long long f_next;
 };
 
-template <bool TAB_GLOBAL>
-__device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const int bi, uint8_t* const tab, const int cap,
-                                                    TrkShared& sh) {
-  double* sbox = reinterpret_cast<double*>(tab);                           // [cap][4]
-  int32_t* scls = reinterpret_cast<int32_t*>(sbox + (size_t)cap * 4);      // [cap]
-  int32_t* shits = scls + cap;                                             // [cap]
-  int32_t* aux = shits + cap;                                              // [cap + kDetChunk] claims, then phase-B state
-  int16_t* last_det = reinterpret_cast<int16_t*>(aux + cap + kDetChunk);   // [cap] detection holding the track's box now, -1 untouched
-  // one set of statically allocated shared variables for both instantiations (declared by tracker_stream)
+// A crowded chunk (some detection with more than kCand candidates): the plain sequential scan of the live table by
+// one warp, exact (tracker.py:50-109).  Not inlined: rare, and its code would otherwise sit in the middle of the
+// instruction stream every ordinary chunk runs through.
+__device__ __noinline__ void chunk_fallback_scan(const TrkParams& p, TrkShared& sh, double* sbox, int32_t* scls, int32_t* shits,
+                                                 int16_t* last_det, const int d0, const int nd) {
   DetStage& sd = sh.sd;
-  auto& c_trk = sh.c_trk;
-  auto& c_det = sh.c_det;
-  auto& n_trk = sh.n_trk;
-  auto& n_det = sh.n_det;
-  auto& key = sh.key;
-  auto& conflicted = sh.conflicted;
-  auto& clist = sh.clist;
   int& s_T = sh.s_T;
   int& s_new = sh.s_new;
-  int& s_is_last = sh.s_is_last;
-  int& s_fallback = sh.s_fallback;
-  int& s_nconf = sh.s_nconf;
-  auto& wsum = sh.wsum;
-  auto& warp_cnt = sh.warp_cnt;
-  int& s_base = sh.s_base;
-  auto& f_new = sh.f_new;
-  auto& f_cur = sh.f_cur;
-  auto& f_cnt = sh.f_cnt;
-  auto& f_pre = sh.f_pre;
-  long long& f_next = sh.f_next;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  PHASE_STAMP(p.dbg, 0);
-  const int slot = p.slots[bi];
-  const TrackerState& S = p.st;
-  const int cur = S.cur[slot];
-  const size_t sb = (size_t)slot * p.max_tracks;
-  long long* id_c = S.id[cur] + sb;
-  int32_t* cls_c = S.cls[cur] + sb;
-  double* conf_c = S.conf[cur] + sb;
-  double* box_c = S.box[cur] + sb * 4;
-  int32_t* age_c = S.age[cur] + sb;
-  int32_t* hits_c = S.hits[cur] + sb;
-  const int T0 = S.count[slot];
-  const int D = (p.skip[bi] || (p.skip_dev && p.skip_dev[bi])) ? 0 : min(p.d_count[bi], p.max_dets);
-  // phase A is bound by dependent shared-memory latency on one SM and scales with the warp count (dense config,
-  // 313 detections x 365 tracks: 131 us with 256 threads, 84 us with 512, 63 us with 1024), while a small stream
-  // (25 x 25) only pays for the wider barriers (19 us with 256, 22 us with 1024): the surplus warps of a small
-  // stream leave at once (a barrier counts the warps that are still alive); see kTrkThreadsMax for the width launched
-  const int kTrkThreads = (T0 > 96 || D > 64) ? (int)blockDim.x : kTrkThreadsMin;
-  if (tid >= kTrkThreads) return;
-
-  for (int t = tid; t < T0; t += kTrkThreads) {
-    const double4 b0 = reinterpret_cast<const double4*>(box_c)[t];
-    reinterpret_cast<double4*>(sbox)[t] = b0;
-    scls[t] = cls_c[t];
-    shits[t] = hits_c[t];
-    last_det[t] = -1;
-  }
-  if (tid == 0) {
-    s_T = T0;
-    s_new = 0;
-  }
-
-  const size_t db = (size_t)bi * p.max_dets;
-  const double scale = p.det_scale[bi];
-
-  PHASE_STAMP(p.dbg, 1);
-  for (int d0 = 0; d0 < D; d0 += kDetChunk) {
-    const int nd = min(kDetChunk, D - d0);
-    if (d0) __syncthreads();  // previous chunk fully consumed
-    for (int i = tid; i < nd; i += kTrkThreads) {
-      const int d = d0 + i;
-      double4 b;
-      double cf;
-      if (p.f_box) {
-        const float4 f4 = reinterpret_cast<const float4*>(p.f_box)[db + d];
-        b = make_double4(f4.x, f4.y, f4.z, f4.w);
-        cf = (double)p.f_conf[db + d];
-        if (p.has_scale) {  // StreamWorker._rescale_detections, pipeline.py:224-240: float64 multiply
-          b.x = __dmul_rn(b.x, scale);
-          b.y = __dmul_rn(b.y, scale);
-          b.z = __dmul_rn(b.z, scale);
-          b.w = __dmul_rn(b.w, scale);
-        }
-      } else {
-        b = reinterpret_cast<const double4*>(p.d_box)[db + d];
-        cf = p.d_conf[db + d];
-      }
-      sd.box[i] = b;
-      sd.conf[i] = cf;
-      sd.cls[i] = p.d_cls[db + d];
-      n_trk[i] = 0;
-      n_det[i] = 0;
-    }
-    if (tid == 0) {
-      s_fallback = 0;
-      s_nconf = 0;
-    }
-    __syncthreads();
-    PHASE_STAMP(p.dbg, 2);
-
-    // ---- phase A: every IoU the chunk can need.  Warp w takes detections w, w+8, ..; lanes take tracks ----
-    const int Tc = s_T;
-    for (int t = tid; t < Tc + kDetChunk; t += kTrkThreads) aux[t] = 0;  // claims per track
-    __syncthreads();
-    for (int i = warp; i < nd; i += kTrkThreads / 32) {
-      const double4 bx = sd.box[i];
-      const int dcls = sd.cls[i];
-      for (int t = lane; t < Tc; t += 32) {
-        if (scls[t] != dcls) continue;
-        const double4 tb = reinterpret_cast<const double4*>(sbox)[t];
-        if (!overlaps(tb, bx)) continue;
-        const double v = iou64(tb.x, tb.y, tb.z, tb.w, bx.x, bx.y, bx.z, bx.w);
-        if (v >= p.thr && v > 0.0) {
-          const int k = atomicAdd(&n_trk[i], 1);
-          if (k < kCand) {
-            c_trk[i][k].iou = v;
-            c_trk[i][k].idx = t;
-          }
-          atomicAdd(&aux[t], 1);
-        }
-      }
-      for (int e = lane; e < i; e += 32) {
-        if (sd.cls[e] != dcls) continue;
-        const double4 eb = sd.box[e];
-        if (!overlaps(eb, bx)) continue;
-        const double v = iou64(eb.x, eb.y, eb.z, eb.w, bx.x, bx.y, bx.z, bx.w);
-        if (v >= p.thr && v > 0.0) {
-          const int k = atomicAdd(&n_det[i], 1);
-          if (k < kCand) {
-            c_det[i][k].iou = v;
-            c_det[i][k].idx = e;
-          }
-        }
-      }
-    }
-    __syncthreads();
-
-    // ---- phase A2: classify; simple detections are resolved here ----
-    {
-      bool conf = false;
-      if (tid < nd) {
-        const int i = tid;
-        const int nt = n_trk[i], ne = n_det[i];
-        if (nt > kCand || ne > kCand) atomicOr(&s_fallback, 1);
-        conf = ne > 0;
-        double best = 0.0;
-        int best_t = 0x7fffffff;
-        for (int k = 0; k < min(nt, kCand); ++k) {
-          const Cand c = c_trk[i][k];
-          conf |= aux[c.idx] > 1;
-          if (c.iou > best || (c.iou == best && c.idx < best_t)) {
-            best = c.iou;
-            best_t = c.idx;
-          }
-        }
-        conflicted[i] = conf;
-        key[i] = conf ? -1 : (best_t == 0x7fffffff ? Tc + i : best_t);
-      }
-      // ordered list of the conflicted detections (kDetChunk <= 64: two warps cover the chunk)
-      const unsigned bal = __ballot_sync(0xffffffffu, conf);
-      if (warp < 2 && lane == 0) wsum[warp] = __popc(bal);
-      __syncthreads();
-      if (tid < nd && conf) clist[(warp ? wsum[0] : 0) + __popc(bal & ((1u << lane) - 1u))] = tid;
-      if (tid == 0) s_nconf = wsum[0] + (nd > 32 ? wsum[1] : 0);
-      // phase-B state: aux[key] = last conflicted detection that took `key` (-1: none)
-      __syncthreads();
-      for (int t = tid; t < Tc + kDetChunk; t += kTrkThreads) aux[t] = -1;
-      __syncthreads();
-    }
-    PHASE_STAMP(p.dbg, 7);
-
-    if (s_fallback) {
-      // ---- crowded chunk: plain sequential scan of the live table, exact (tracker.py:50-109) ----
-      if (warp == 0) {
+  const int lane = threadIdx.x & 31;
+  {
         for (int i = 0; i < nd; ++i) {
           const int T = s_T;
           const int dcls = sd.cls[i];
@@ -377,6 +245,248 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
           __syncwarp();
         }
       }
+}
+
+template <bool TAB_GLOBAL, bool SMALL>
+__device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const int bi, uint8_t* const tab, const int cap,
+                                                    TrkShared& sh, const int D, const bool prestaged, const int cur,
+                                                    const int T0) {
+  double* sbox = reinterpret_cast<double*>(tab);                           // [cap][4]
+  int32_t* scls = reinterpret_cast<int32_t*>(sbox + (size_t)cap * 4);      // [cap]
+  int32_t* shits = scls + cap;                                             // [cap]
+  int32_t* aux = shits + cap;                                              // [cap + kDetChunk] claims, then phase-B state
+  int16_t* last_det = reinterpret_cast<int16_t*>(aux + cap + kDetChunk);   // [cap] detection holding the track's box now, -1 untouched
+  // one set of statically allocated shared variables for both instantiations (declared by tracker_stream)
+  DetStage& sd = sh.sd;
+  auto& c_trk = sh.c_trk;
+  auto& c_det = sh.c_det;
+  auto& n_trk = sh.n_trk;
+  auto& n_det = sh.n_det;
+  auto& key = sh.key;
+  auto& conflicted = sh.conflicted;
+  auto& clist = sh.clist;
+  int& s_T = sh.s_T;
+  int& s_new = sh.s_new;
+  int& s_is_last = sh.s_is_last;
+  int& s_fallback = sh.s_fallback;
+  int& s_nconf = sh.s_nconf;
+  auto& wsum = sh.wsum;
+  auto& warp_cnt = sh.warp_cnt;
+  int& s_base = sh.s_base;
+  auto& f_new = sh.f_new;
+  auto& f_cur = sh.f_cur;
+  auto& f_cnt = sh.f_cnt;
+  auto& f_pre = sh.f_pre;
+  long long& f_next = sh.f_next;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  PHASE_STAMP(p.dbg, 0);
+  const int slot = p.slots[bi];
+  const TrackerState& S = p.st;
+  const size_t sb = (size_t)slot * p.max_tracks;
+  long long* id_c = S.id[cur] + sb;
+  int32_t* cls_c = S.cls[cur] + sb;
+  double* conf_c = S.conf[cur] + sb;
+  double* box_c = S.box[cur] + sb * 4;
+  int32_t* age_c = S.age[cur] + sb;
+  int32_t* hits_c = S.hits[cur] + sb;
+  // phase A is bound by dependent shared-memory latency on one SM and scales with the warp count (dense config,
+  // 313 detections x 365 tracks: 131 us with 256 threads, 84 us with 512, 63 us with 1024), while a small stream
+  // (25 x 25) only pays for the wider barriers (19 us with 256, 22 us with 1024): the surplus warps of a small
+  // stream leave at once (a barrier counts the warps that are still alive); see kTrkThreadsMax for the width launched
+  // SMALL (one chunk, few pairs: what tracker_stream checks before it picks this instantiation) always runs 256 wide
+  const int kTrkThreads = SMALL ? kTrkThreadsMin : ((T0 > 96 || D > 64) ? (int)blockDim.x : kTrkThreadsMin);
+  if (tid >= kTrkThreads) return;
+
+  // what the prune step needs of the first kTrkThreads rows, fetched now: its loads would otherwise start a global
+  // round trip at the very end of the critical path
+  int pf_age = 0;
+  long long pf_id = 0;
+  double pf_conf = 0.0;
+  if (tid < T0) {
+    pf_age = age_c[tid];
+    pf_id = id_c[tid];
+    pf_conf = conf_c[tid];
+  }
+  for (int t = tid; t < T0; t += kTrkThreads) {
+    const double4 b0 = reinterpret_cast<const double4*>(box_c)[t];
+    reinterpret_cast<double4*>(sbox)[t] = b0;
+    scls[t] = cls_c[t];
+    shits[t] = hits_c[t];
+    last_det[t] = -1;
+  }
+  if (tid == 0) {
+    s_T = T0;
+    s_new = 0;
+  }
+
+  const size_t db = (size_t)bi * p.max_dets;
+  const double scale = p.det_scale[bi];
+
+  PHASE_STAMP(p.dbg, 1);
+  for (int d0 = 0; d0 < D; d0 += kDetChunk) {
+    const int nd = min(kDetChunk, D - d0);
+    if (d0) __syncthreads();  // previous chunk fully consumed
+    const bool staged = prestaged && d0 == 0;  // fused kernel: the NMS half left the first chunk in `sd`
+    for (int i = tid; i < nd; i += kTrkThreads) {
+      const int d = d0 + i;
+      if (staged) {
+      } else if (p.f_box) {
+        stage_detection(sd, i, reinterpret_cast<const float4*>(p.f_box)[db + d], p.f_conf[db + d], p.d_cls[db + d], scale,
+                        p.has_scale != 0);
+      } else {
+        sd.box[i] = reinterpret_cast<const double4*>(p.d_box)[db + d];
+        sd.conf[i] = p.d_conf[db + d];
+        sd.cls[i] = p.d_cls[db + d];
+      }
+      n_trk[i] = 0;
+      n_det[i] = 0;
+    }
+    if (tid == 0) {
+      s_fallback = 0;
+      s_nconf = 0;
+      sh.n_plist = 0;
+    }
+    __syncthreads();
+    PHASE_STAMP(p.dbg, 2);
+
+    // ---- phase A: every IoU the chunk can need.  Warp w takes detections w, w+8, ..; lanes take tracks ----
+    const int Tc = s_T;
+    for (int t = tid; t < Tc + kDetChunk; t += kTrkThreads) aux[t] = 0;  // claims per track
+    __syncthreads();
+    const int pairs_t = nd * Tc, pairs = pairs_t + nd * nd;
+    if (SMALL || pairs <= 8 * kTrkThreads) {
+      // Few pairs.  The CTA is latency-bound: a warp in which ONE lane meets an overlapping pair walks all 32 lanes
+      // through the float64 IoU (a dependent chain of ~170 instructions), and the warp that owns a detection does
+      // that once per 32 tracks and again for the earlier detections.  So pass 1 spreads ALL (detection, track) and
+      // (detection, earlier detection) pairs over the threads and only lists those of equal class whose boxes overlap;
+      // pass 2 evaluates one listed pair per thread, lanes converged (25 x 25: 5.6 k -> ~1.6 k SM cycles).  The
+      // candidate lists come out in a different order, which nothing downstream depends on (arg-max with index ties).
+      auto score = [&](int i, int idx, bool vs_track) {
+        const double4 bx = sd.box[i];
+        const double4 ob = vs_track ? reinterpret_cast<const double4*>(sbox)[idx] : sd.box[idx];
+        const double v = iou64(ob.x, ob.y, ob.z, ob.w, bx.x, bx.y, bx.z, bx.w);
+        if (v >= p.thr && v > 0.0) {
+          if (vs_track) {
+            const int k = atomicAdd(&n_trk[i], 1);
+            if (k < kCand) {
+              c_trk[i][k].iou = v;
+              c_trk[i][k].idx = idx;
+            }
+            atomicAdd(&aux[idx], 1);
+          } else {
+            const int k = atomicAdd(&n_det[i], 1);
+            if (k < kCand) {
+              c_det[i][k].iou = v;
+              c_det[i][k].idx = idx;
+            }
+          }
+        }
+      };
+      PHASE_STAMP(p.dbg, 58);
+      const float inv_T = 1.0f / (float)max(Tc, 1), inv_n = 1.0f / (float)nd;
+#pragma unroll 1
+      for (int q = tid; q < pairs; q += kTrkThreads) {
+        int i, idx;
+        const bool vs_track = q < pairs_t;
+        if (vs_track) {
+          i = (int)(((float)q + 0.5f) * inv_T);  // q / Tc for these small integers
+          idx = q - i * Tc;
+          if (scls[idx] != sd.cls[i]) continue;
+          if (!may_overlap(reinterpret_cast<const double4*>(sbox)[idx], sd.box[i])) continue;
+        } else {
+          const int r = q - pairs_t;
+          i = (int)(((float)r + 0.5f) * inv_n);
+          idx = r - i * nd;
+          if (idx >= i || sd.cls[idx] != sd.cls[i]) continue;
+          if (!may_overlap(sd.box[idx], sd.box[i])) continue;
+        }
+        const int slot = atomicAdd(&sh.n_plist, 1);
+        if (slot < kTrkPairs) sh.plist[slot] = (uint32_t)idx | ((uint32_t)i << 16) | (vs_track ? 0x80000000u : 0u);
+        else score(i, idx, vs_track);  // list full: evaluate on the spot
+      }
+      PHASE_STAMP(p.dbg, 59);
+      __syncthreads();
+      PHASE_STAMP(p.dbg, 60);
+      const int listed = min(sh.n_plist, kTrkPairs);
+#pragma unroll 1
+      for (int q = tid; q < listed; q += kTrkThreads) {
+        const uint32_t e = sh.plist[q];
+        score((int)((e >> 16) & 0x7fffu), (int)(e & 0xffffu), (e >> 31) != 0u);
+      }
+      PHASE_STAMP(p.dbg, 61);
+    } else
+    for (int i = warp; i < nd; i += kTrkThreads / 32) {
+      const double4 bx = sd.box[i];
+      const int dcls = sd.cls[i];
+      for (int t = lane; t < Tc; t += 32) {
+        if (scls[t] != dcls) continue;
+        const double4 tb = reinterpret_cast<const double4*>(sbox)[t];
+        if (!overlaps(tb, bx)) continue;
+        const double v = iou64(tb.x, tb.y, tb.z, tb.w, bx.x, bx.y, bx.z, bx.w);
+        if (v >= p.thr && v > 0.0) {
+          const int k = atomicAdd(&n_trk[i], 1);
+          if (k < kCand) {
+            c_trk[i][k].iou = v;
+            c_trk[i][k].idx = t;
+          }
+          atomicAdd(&aux[t], 1);
+        }
+      }
+      for (int e = lane; e < i; e += 32) {
+        if (sd.cls[e] != dcls) continue;
+        const double4 eb = sd.box[e];
+        if (!overlaps(eb, bx)) continue;
+        const double v = iou64(eb.x, eb.y, eb.z, eb.w, bx.x, bx.y, bx.z, bx.w);
+        if (v >= p.thr && v > 0.0) {
+          const int k = atomicAdd(&n_det[i], 1);
+          if (k < kCand) {
+            c_det[i][k].iou = v;
+            c_det[i][k].idx = e;
+          }
+        }
+      }
+    }
+    __syncthreads();
+
+    PHASE_STAMP(p.dbg, 62);
+    // ---- phase A2: classify; simple detections are resolved here ----
+    {
+      bool conf = false;
+      if (tid < nd) {
+        const int i = tid;
+        const int nt = n_trk[i], ne = n_det[i];
+        if (nt > kCand || ne > kCand) atomicOr(&s_fallback, 1);
+        conf = ne > 0;
+        double best = 0.0;
+        int best_t = 0x7fffffff;
+        for (int k = 0; k < min(nt, kCand); ++k) {
+          const Cand c = c_trk[i][k];
+          conf |= aux[c.idx] > 1;
+          if (c.iou > best || (c.iou == best && c.idx < best_t)) {
+            best = c.iou;
+            best_t = c.idx;
+          }
+        }
+        conflicted[i] = conf;
+        key[i] = conf ? -1 : (best_t == 0x7fffffff ? Tc + i : best_t);
+      }
+      // ordered list of the conflicted detections (kDetChunk <= 64: two warps cover the chunk)
+      const unsigned bal = __ballot_sync(0xffffffffu, conf);
+      if (warp < 2 && lane == 0) wsum[warp] = __popc(bal);
+      __syncthreads();
+      if (tid < nd && conf) clist[(warp ? wsum[0] : 0) + __popc(bal & ((1u << lane) - 1u))] = tid;
+      if (tid == 0) s_nconf = wsum[0] + (nd > 32 ? wsum[1] : 0);
+      // phase-B state: aux[key] = last conflicted detection that took `key` (-1: none)
+      __syncthreads();
+      for (int t = tid; t < Tc + kDetChunk; t += kTrkThreads) aux[t] = -1;
+      __syncthreads();
+    }
+    PHASE_STAMP(p.dbg, 7);
+
+    if (s_fallback) {
+      // ---- crowded chunk: plain sequential scan of the live table, exact (tracker.py:50-109) ----
+      if (warp == 0) chunk_fallback_scan(p, sh, sbox, scls, shits, last_det, d0, nd);
     } else {
       // ---- phase B: conflicted detections, in order, look-ups only ----
       if (warp == 0) {
@@ -487,7 +597,7 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
       if (ld >= 0) {  // matched or created this frame: age = 0 (tracker.py:85)
         keep = true;
       } else {
-        age = age_c[t] + 1;
+        age = (t0 == 0 ? pf_age : age_c[t]) + 1;
         keep = !(age > p.max_age || hits < p.min_hits);
       }
     }
@@ -499,10 +609,10 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
     if (keep) {
       const int dst = off + __popc(bal & ((1u << lane) - 1u));
       // tracks appended this frame sit at t >= T0 in creation order: provisional id = -(ordinal + 1)
-      const long long idv = t < T0 ? id_c[t]
+      const long long idv = t < T0 ? (t0 == 0 ? pf_id : id_c[t])
                                    : (p.has_id_base ? p.id_base[bi] + (t - T0) : -(long long)(t - T0 + 1));
       double cf;
-      if (ld < 0) cf = conf_c[t];
+      if (ld < 0) cf = t0 == 0 ? pf_conf : conf_c[t];
       else if (p.f_box) cf = (double)p.f_conf[db + ld];
       else cf = p.d_conf[db + ld];
       const double4 b = reinterpret_cast<const double4*>(sbox)[t];
@@ -597,15 +707,33 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
 }
 
 
+__device__ __noinline__ void tracker_stream_general(const TrkParams& p, const int bi, uint8_t* const smem_raw, TrkShared& sh,
+                                                    const int D, const bool prestaged, const int cur, const int T0,
+                                                    const int need) {
+  if (need <= p.smem_tracks) tracker_stream_impl<false, false>(p, bi, smem_raw, p.smem_tracks, sh, D, prestaged, cur, T0);
+  else tracker_stream_impl<true, false>(p, bi, p.st.scratch + (size_t)bi * p.st.scratch_stride, p.max_tracks, sh, D, prestaged, cur, T0);
+}
+
 // One stream's tracker update.  The table never grows past `live tracks + detections` within the call, so that sum
 // decides (uniformly for the CTA) whether the working table fits the shared memory this launch was given.
-__device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi, uint8_t* const smem_raw) {
+// `prestaged` >= 0 (fused kernel only): the detection count of this frame, whose first chunk already sits in sh.sd.
+// `pre_cur` / `pre_T0` >= 0: the slot's buffer index and track count, read by the caller ahead of time.
+__device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi, uint8_t* const smem_raw, TrkShared& sh,
+                                               const int prestaged, const int pre_cur = -1, const int pre_T0 = -1) {
   const int slot = p.slots[bi];
-  const int need = p.st.count[slot] + ((p.skip[bi] || (p.skip_dev && p.skip_dev[bi])) ? 0 : min(p.d_count[bi], p.max_dets));
+  const int cur = pre_cur >= 0 ? pre_cur : p.st.cur[slot];
+  const int T0 = pre_T0 >= 0 ? pre_T0 : p.st.count[slot];
+  const bool skipped = p.skip[bi] || (p.skip_dev && p.skip_dev[bi]);
+  const int D = skipped ? 0 : (prestaged >= 0 ? prestaged : min(p.d_count[bi], p.max_dets));
+  const int need = T0 + D;
   if (threadIdx.x == 0 && need > 256) atomicMax(p.st.need_max, need);
-  __shared__ TrkShared sh;
-  if (need <= p.smem_tracks) tracker_stream_impl<false>(p, bi, smem_raw, p.smem_tracks, sh);
-  else tracker_stream_impl<true>(p, bi, p.st.scratch + (size_t)bi * p.st.scratch_stride, p.max_tracks, sh);
+  // the common case -- the table fits shared memory, one chunk of detections, few pairs -- runs a compact
+  // instantiation inline; everything else goes through one call to the general code, kept out of the hot
+  // instruction stream (these CTAs stall on instruction fetch more than on anything else)
+  if (need <= p.smem_tracks && D <= kDetChunk && D * (T0 + D) <= 8 * kTrkThreadsMin)
+    tracker_stream_impl<false, true>(p, bi, smem_raw, p.smem_tracks, sh, D, prestaged >= 0, cur, T0);
+  else
+    tracker_stream_general(p, bi, smem_raw, sh, D, prestaged >= 0, cur, T0, need);
 }
 
 }  // namespace
