@@ -729,7 +729,7 @@ struct DetHandover {
 // else (ncu: stall_no_inst 29-33 % of all samples in k_post_track), so the code a small frame never runs must not
 // sit between the lines it does run.
 template <bool GRID, int NT>
-__device__ __noinline__ void nms_general(const NmsParams& p, const int frame, uint8_t* const smem_raw, const int n) {
+__device__ __forceinline__ void nms_general_body(const NmsParams& p, const int frame, uint8_t* const smem_raw, const int n) {
   const int tid = threadIdx.x;
   const size_t cbase = (size_t)frame * p.max_cand;
   int np2 = 64;
@@ -1111,9 +1111,25 @@ __device__ __noinline__ void nms_general(const NmsParams& p, const int frame, ui
   PHASE_STAMP(p.dbg, 21);
 }
 
+// The part of the small-frame set-up that does not depend on the frame: cleared matrix, bitmap and pair counter.
+template <int NT>
+__device__ __forceinline__ void nms_small_init(uint8_t* const smem_raw) {
+  SmallNms& sm = *reinterpret_cast<SmallNms*>(smem_raw);
+  for (int w = threadIdx.x; w < kSmallN * (kSmallN / 32); w += NT) (&sm.M[0][0])[w] = 0u;
+  if (threadIdx.x < kSmallN / 32) sm.supp[threadIdx.x] = 0u;
+  if (threadIdx.x == 0) sm.n_pairs = 0;
+}
+
 template <bool GRID, int NT>
+__device__ __noinline__ void nms_general(const NmsParams& p, const int frame, uint8_t* const smem_raw, const int n) {
+  nms_general_body<GRID, NT>(p, frame, smem_raw, n);
+}
+
+// COLD_GENERAL: the general path sits behind a call (the fused sparse-scene kernel); otherwise it is inlined (the
+// kernels the host picks for dense scenes, where that path is the one that runs).
+template <bool GRID, int NT, bool COLD_GENERAL>
 __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, uint8_t* const smem_raw,
-                                          const DetHandover* hand = nullptr) {
+                                          const DetHandover* hand = nullptr, const bool pre_init = false) {
   static_assert(!GRID || NT == 1024, "the kept-box grid code assumes 1024 threads");
   static_assert(NT >= kSmallN && NT % 32 == 0, "bad CTA width");
   const int tid = threadIdx.x;
@@ -1153,7 +1169,8 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
   const bool thr_nonneg = ultra ? p.iou_thr64 >= 0.0 : thr >= 0.f;
   const int nchunks = (n + 63) >> 6;
   if (!small) {
-    nms_general<GRID, NT>(p, frame, smem_raw, n);
+    if (COLD_GENERAL) nms_general<GRID, NT>(p, frame, smem_raw, n);
+    else nms_general_body<GRID, NT>(p, frame, smem_raw, n);
     return;
   }
   unsigned long long* const keys = sm.keys;
@@ -1168,9 +1185,11 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
       sm.ubox[tid] = b_spec;
       sm.ucls[tid] = c_spec;
     }
-    for (int w = tid; w < n * (kSmallN / 32); w += NT) (&sm.M[0][0])[w] = 0u;
-    if (tid < kSmallN / 32) sm.supp[tid] = 0u;
-    if (tid == 0) sm.n_pairs = 0;
+    if (!pre_init) {  // (the fused kernel did this while it waited for the decode kernel)
+      for (int w = tid; w < n * (kSmallN / 32); w += NT) (&sm.M[0][0])[w] = 0u;
+      if (tid < kSmallN / 32) sm.supp[tid] = 0u;
+      if (tid == 0) sm.n_pairs = 0;
+    }
     __syncthreads();
     PHASE_STAMP(p.dbg, 17);
     if (tid < n) {  // rank sort: keys are unique, rank = number of larger keys
@@ -1375,13 +1394,13 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
   for (int r = 1; r < p.dbg_reps; ++r) {
     const int saved = p.cand_count[blockIdx.x];
     __syncthreads();
-    nms_frame<GRID, kNmsThreads>(p, blockIdx.x, smem_raw);
+    nms_frame<GRID, kNmsThreads, false>(p, blockIdx.x, smem_raw);
     __syncthreads();
     if (threadIdx.x == 0) p.cand_count[blockIdx.x] = saved;
     __syncthreads();
   }
 #endif
-  nms_frame<GRID, kNmsThreads>(p, blockIdx.x, smem_raw);
+  nms_frame<GRID, kNmsThreads, false>(p, blockIdx.x, smem_raw);
 }
 
 // Sparse scenes: sort + NMS + emit of frame i followed by the tracker update of stream i in ONE CTA of 256 threads.
@@ -1392,19 +1411,33 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
 __global__ void __launch_bounds__(kNmsThreadsSmall) k_post_track(const __grid_constant__ NmsParams q,
                                                                   const __grid_constant__ TrkParams t) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  griddep_wait();
-  TIMELINE_BEGIN(q.dbg, 44);
   __shared__ TrkShared sh;
-  const DetHandover hand{&sh, t.det_scale[blockIdx.x], t.has_scale};
-  // the stream's table header, fetched before the NMS half instead of between the halves (nobody else writes this slot)
+  // ---- before the decode kernel is done (this grid is its programmatic dependent): everything that does not read
+  // its candidates.  The stream's live tracks go into a working table BEHIND the small-frame NMS layout, so the
+  // tracker half finds them in shared memory (the general NMS path uses the whole buffer and voids that copy).
   const int trk_slot = t.slots[blockIdx.x];
   const int pre_cur = t.st.cur[trk_slot], pre_T0 = t.st.count[trk_slot];
+  constexpr int kTabOff = (int)((sizeof(SmallNms) + 127) & ~(size_t)127);
+  unsigned dyn_bytes;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+  const int staged_cap = ((int)dyn_bytes - kTabOff - kDetChunk * 4 - 16) / 46;  // rows (see tracker_smem_bytes)
+  const bool stage_early = pre_T0 <= staged_cap - kDetChunk && pre_T0 <= kNmsThreadsSmall;
+  TablePrefetch pf{0, 0, 0.0};
+  if (stage_early) pf = stage_table(t, trk_slot, pre_cur, pre_T0, smem_raw + kTabOff, staged_cap, kNmsThreadsSmall);
+  nms_small_init<kNmsThreadsSmall>(smem_raw);
+  griddep_wait();
+  TIMELINE_BEGIN(q.dbg, 44);
+  const DetHandover hand{&sh, t.det_scale[blockIdx.x], t.has_scale};
   // the handover stages float32 detections; a skipped stream (host flag or device mask) takes none
-  nms_frame<false, kNmsThreadsSmall>(q, blockIdx.x, smem_raw, t.f_box ? &hand : nullptr);
+  nms_frame<false, kNmsThreadsSmall, true>(q, blockIdx.x, smem_raw, t.f_box ? &hand : nullptr, true);
   __syncthreads();  // this frame's detections were written by this CTA: visible to all of its threads from here on
   TIMELINE_END(q.dbg, 44);
   TIMELINE_BEGIN(q.dbg, 46);
-  tracker_stream(t, blockIdx.x, smem_raw, sh, t.f_box ? sh.s_prestaged : -1, pre_cur, pre_T0);
+  const int prestaged = t.f_box ? sh.s_prestaged : -1;
+  // (s_prestaged >= 0 also says that the small-frame NMS ran, i.e. the early copy of the table is intact)
+  const bool table_ok = stage_early && prestaged >= 0;
+  tracker_stream<true>(t, blockIdx.x, smem_raw, sh, prestaged, pre_cur, pre_T0, table_ok ? &pf : nullptr, smem_raw + kTabOff,
+                       staged_cap);
   TIMELINE_END(q.dbg, 46);  // (threads the tracker retires early never get here; thread 0 always does)
 }
 

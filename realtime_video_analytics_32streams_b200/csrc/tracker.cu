@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(kTrkThreadsMax) k_tracker(const __grid_constan
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ TrkShared sh;
   griddep_wait();  // launched as a programmatic dependent of the NMS kernel: everything above overlapped its tail
-  tracker_stream(p, blockIdx.x, smem_raw, sh, -1);
+  tracker_stream<false>(p, blockIdx.x, smem_raw, sh, -1);
 }
 
 __global__ void k_tracker_reset(TrackerState S, int slot) {

@@ -202,8 +202,8 @@ struct TrkShared {
 // A crowded chunk (some detection with more than kCand candidates): the plain sequential scan of the live table by
 // one warp, exact (tracker.py:50-109).  Not inlined: rare, and its code would otherwise sit in the middle of the
 // instruction stream every ordinary chunk runs through.
-__device__ __noinline__ void chunk_fallback_scan(const TrkParams& p, TrkShared& sh, double* sbox, int32_t* scls, int32_t* shits,
-                                                 int16_t* last_det, const int d0, const int nd) {
+__device__ __forceinline__ void chunk_fallback_scan_body(const TrkParams& p, TrkShared& sh, double* sbox, int32_t* scls, int32_t* shits,
+                                                         int16_t* last_det, const int d0, const int nd) {
   DetStage& sd = sh.sd;
   int& s_T = sh.s_T;
   int& s_new = sh.s_new;
@@ -247,10 +247,48 @@ __device__ __noinline__ void chunk_fallback_scan(const TrkParams& p, TrkShared& 
       }
 }
 
+__device__ __noinline__ void chunk_fallback_scan(const TrkParams& p, TrkShared& sh, double* sbox, int32_t* scls, int32_t* shits,
+                                                 int16_t* last_det, const int d0, const int nd) {
+  chunk_fallback_scan_body(p, sh, sbox, scls, shits, last_det, d0, nd);
+}
+
+// What the prune step needs of a stream's first rows (row = threadIdx.x), fetched while the table is staged: its
+// loads would otherwise start a global round trip at the very end of the critical path.
+struct TablePrefetch {
+  int age;
+  long long id;
+  double conf;
+};
+
+// Copy the live rows of a stream's table (buffer `cur`, T0 rows) into the working table at `tab` (capacity `cap` rows).
+__device__ __forceinline__ TablePrefetch stage_table(const TrkParams& p, const int slot, const int cur, const int T0,
+                                                     uint8_t* const tab, const int cap, const int nthreads) {
+  double* sbox = reinterpret_cast<double*>(tab);
+  int32_t* scls = reinterpret_cast<int32_t*>(sbox + (size_t)cap * 4);
+  int32_t* shits = scls + cap;
+  int16_t* last_det = reinterpret_cast<int16_t*>(shits + cap + cap + kDetChunk);
+  const TrackerState& S = p.st;
+  const size_t sb = (size_t)slot * p.max_tracks;
+  const int tid = threadIdx.x;
+  TablePrefetch pf{0, 0, 0.0};
+  if (tid < T0) {
+    pf.age = S.age[cur][sb + tid];
+    pf.id = S.id[cur][sb + tid];
+    pf.conf = S.conf[cur][sb + tid];
+  }
+  for (int t = tid; t < T0; t += nthreads) {
+    reinterpret_cast<double4*>(sbox)[t] = reinterpret_cast<const double4*>(S.box[cur] + sb * 4)[t];
+    scls[t] = S.cls[cur][sb + t];
+    shits[t] = S.hits[cur][sb + t];
+    last_det[t] = -1;
+  }
+  return pf;
+}
+
 template <bool TAB_GLOBAL, bool SMALL>
 __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const int bi, uint8_t* const tab, const int cap,
                                                     TrkShared& sh, const int D, const bool prestaged, const int cur,
-                                                    const int T0) {
+                                                    const int T0, const TablePrefetch* const staged_table = nullptr) {
   double* sbox = reinterpret_cast<double*>(tab);                           // [cap][4]
   int32_t* scls = reinterpret_cast<int32_t*>(sbox + (size_t)cap * 4);      // [cap]
   int32_t* shits = scls + cap;                                             // [cap]
@@ -298,23 +336,11 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
   const int kTrkThreads = SMALL ? kTrkThreadsMin : ((T0 > 96 || D > 64) ? (int)blockDim.x : kTrkThreadsMin);
   if (tid >= kTrkThreads) return;
 
-  // what the prune step needs of the first kTrkThreads rows, fetched now: its loads would otherwise start a global
-  // round trip at the very end of the critical path
-  int pf_age = 0;
-  long long pf_id = 0;
-  double pf_conf = 0.0;
-  if (tid < T0) {
-    pf_age = age_c[tid];
-    pf_id = id_c[tid];
-    pf_conf = conf_c[tid];
-  }
-  for (int t = tid; t < T0; t += kTrkThreads) {
-    const double4 b0 = reinterpret_cast<const double4*>(box_c)[t];
-    reinterpret_cast<double4*>(sbox)[t] = b0;
-    scls[t] = cls_c[t];
-    shits[t] = hits_c[t];
-    last_det[t] = -1;
-  }
+  // (`staged_table`: the fused kernel copied the table into `tab` before it even waited for the decode kernel)
+  const TablePrefetch pf = staged_table ? *staged_table : stage_table(p, slot, cur, T0, tab, cap, kTrkThreads);
+  const int pf_age = pf.age;
+  const long long pf_id = pf.id;
+  const double pf_conf = pf.conf;
   if (tid == 0) {
     s_T = T0;
     s_new = 0;
@@ -486,7 +512,10 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
 
     if (s_fallback) {
       // ---- crowded chunk: plain sequential scan of the live table, exact (tracker.py:50-109) ----
-      if (warp == 0) chunk_fallback_scan(p, sh, sbox, scls, shits, last_det, d0, nd);
+      if (warp == 0) {
+        if (SMALL) chunk_fallback_scan(p, sh, sbox, scls, shits, last_det, d0, nd);
+        else chunk_fallback_scan_body(p, sh, sbox, scls, shits, last_det, d0, nd);
+      }
     } else {
       // ---- phase B: conflicted detections, in order, look-ups only ----
       if (warp == 0) {
@@ -718,8 +747,14 @@ __device__ __noinline__ void tracker_stream_general(const TrkParams& p, const in
 // decides (uniformly for the CTA) whether the working table fits the shared memory this launch was given.
 // `prestaged` >= 0 (fused kernel only): the detection count of this frame, whose first chunk already sits in sh.sd.
 // `pre_cur` / `pre_T0` >= 0: the slot's buffer index and track count, read by the caller ahead of time.
+// HOT_SMALL (the fused sparse-scene kernel): the common small case runs a compact instantiation inline and everything
+// else sits behind one call; otherwise (k_tracker, which the host launches on its own for dense scenes and for plain
+// b200va_tracker_update calls) the general code is inlined as it always was.
+template <bool HOT_SMALL>
 __device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi, uint8_t* const smem_raw, TrkShared& sh,
-                                               const int prestaged, const int pre_cur = -1, const int pre_T0 = -1) {
+                                               const int prestaged, const int pre_cur = -1, const int pre_T0 = -1,
+                                               const TablePrefetch* const staged_table = nullptr,
+                                               uint8_t* const staged_tab = nullptr, const int staged_cap = 0) {
   const int slot = p.slots[bi];
   const int cur = pre_cur >= 0 ? pre_cur : p.st.cur[slot];
   const int T0 = pre_T0 >= 0 ? pre_T0 : p.st.count[slot];
@@ -730,10 +765,16 @@ __device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi,
   // the common case -- the table fits shared memory, one chunk of detections, few pairs -- runs a compact
   // instantiation inline; everything else goes through one call to the general code, kept out of the hot
   // instruction stream (these CTAs stall on instruction fetch more than on anything else)
-  if (need <= p.smem_tracks && D <= kDetChunk && D * (T0 + D) <= 8 * kTrkThreadsMin)
+  if (!HOT_SMALL) {
+    if (need <= p.smem_tracks) tracker_stream_impl<false, false>(p, bi, smem_raw, p.smem_tracks, sh, D, prestaged >= 0, cur, T0);
+    else tracker_stream_impl<true, false>(p, bi, p.st.scratch + (size_t)bi * p.st.scratch_stride, p.max_tracks, sh, D, prestaged >= 0, cur, T0);
+  } else if (staged_table && need <= staged_cap && D <= kDetChunk && D * (T0 + D) <= 8 * kTrkThreadsMin) {
+    tracker_stream_impl<false, true>(p, bi, staged_tab, staged_cap, sh, D, prestaged >= 0, cur, T0, staged_table);
+  } else if (need <= p.smem_tracks && D <= kDetChunk && D * (T0 + D) <= 8 * kTrkThreadsMin) {
     tracker_stream_impl<false, true>(p, bi, smem_raw, p.smem_tracks, sh, D, prestaged >= 0, cur, T0);
-  else
+  } else {
     tracker_stream_general(p, bi, smem_raw, sh, D, prestaged >= 0, cur, T0, need);
+  }
 }
 
 }  // namespace
