@@ -261,6 +261,15 @@ __global__ void __launch_bounds__(32 * kSplitParts) k_decode_cm_split(const __gr
   int cls[4] = {0, 0, 0, 0};
   unsigned nan_seen = 0;
   bool any = false;
+  // the warp that emits (part 0) fetches the four box rows together with its class rows: one round of loads per launch
+  // instead of a second, dependent one for the anchors that pass (a launch of a few frames is latency-bound)
+  float4 cx = make_float4(0.f, 0.f, 0.f, 0.f), cy = cx, w = cx, hh = cx;
+  if (part == 0 && in_range) {
+    cx = __ldg(reinterpret_cast<const float4*>(hd + a0));
+    cy = __ldg(reinterpret_cast<const float4*>(hd + (size_t)A + a0));
+    w = __ldg(reinterpret_cast<const float4*>(hd + (size_t)2 * A + a0));
+    hh = __ldg(reinterpret_cast<const float4*>(hd + (size_t)3 * A + a0));
+  }
   if (in_range && c_lo < c_hi) {
     any = true;
     float4 obj = make_float4(1.f, 1.f, 1.f, 1.f);  // x * 1.0f is exact: scores = pred[:, 4:]
@@ -329,10 +338,6 @@ __global__ void __launch_bounds__(32 * kSplitParts) k_decode_cm_split(const __gr
   base = __shfl_sync(0xffffffffu, base, 31);
   int pos = base + incl - mine;
   if (pass) {
-    const float4 cx = __ldg(reinterpret_cast<const float4*>(hd + a0));
-    const float4 cy = __ldg(reinterpret_cast<const float4*>(hd + (size_t)A + a0));
-    const float4 w = __ldg(reinterpret_cast<const float4*>(hd + (size_t)2 * A + a0));
-    const float4 hh = __ldg(reinterpret_cast<const float4*>(hd + (size_t)3 * A + a0));
     const float cxa[4] = {cx.x, cx.y, cx.z, cx.w}, cya[4] = {cy.x, cy.y, cy.z, cy.w};
     const float wa[4] = {w.x, w.y, w.z, w.w}, ha[4] = {hh.x, hh.y, hh.z, hh.w};
 #pragma unroll
