@@ -1132,7 +1132,9 @@ __device__ __noinline__ void nms_general(const NmsParams& p, const int frame, ui
 
 // COLD_GENERAL: the general path sits behind a call (the fused sparse-scene kernel); otherwise it is inlined (the
 // kernels the host picks for dense scenes, where that path is the one that runs).
-template <bool GRID, int NT, bool COLD_GENERAL>
+// ULTRA_OK = false: the caller guarantees reference semantics (p.ultra == 0) and the Ultralytics variants of the
+// predicate, the class shift and the un-letterbox step are compiled out of the small-frame path.
+template <bool GRID, int NT, bool COLD_GENERAL, bool ULTRA_OK>
 __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, uint8_t* const smem_raw,
                                           const DetHandover* hand = nullptr, const bool pre_init = false) {
   static_assert(!GRID || NT == 1024, "the kept-box grid code assumes 1024 threads");
@@ -1169,7 +1171,7 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
     return;
   }
   const bool aware = p.class_aware != 0;
-  const bool ultra = p.ultra != 0;
+  const bool ultra = ULTRA_OK && p.ultra != 0;
   const float thr = p.iou_thr;
   const bool thr_nonneg = ultra ? p.iou_thr64 >= 0.0 : thr >= 0.f;
   const int nchunks = (n + 63) >> 6;
@@ -1217,7 +1219,7 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
       const int slot = (int)(k & 0x3fffull);
       float4 b = sm.ubox[slot];
       const int cl = sm.ucls[slot];
-      if (p.ultra && !p.ultra_agnostic) {  // boxes = x[:, :4] + x[:, 5:6] * max_wh, float32 (the rounding is part of the semantics)
+      if (ultra && !p.ultra_agnostic) {  // boxes = x[:, :4] + x[:, 5:6] * max_wh, float32 (the rounding is part of the semantics)
         const float c = __fmul_rn((float)cl, 7680.f);
         b = make_float4(__fadd_rn(b.x, c), __fadd_rn(b.y, c), __fadd_rn(b.z, c), __fadd_rn(b.w, c));
       }
@@ -1243,17 +1245,27 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
       // (at most 128 iterations: n <= 256, parts >= 1)
       unsigned long long c_lo = 0ull, c_hi = 0ull;
       if (part < parts) {
-        int it = 0;
+        const bool even = !(n & 1);
 #pragma unroll 1
-        for (int k = 1 + part; k <= half; k += parts, ++it) {
-          int j = i + k;
-          if (j >= n) j -= n;
-          if (!(n & 1) && k == half && i >= half) continue;  // even n: the antipodal pairs come up twice
-          const float4 bj = sm.box[j];
-          if (thr_nonneg && (bj.z <= bi.x || bi.z <= bj.x || bj.w <= bi.y || bi.w <= bj.y)) continue;  // disjoint: IoU 0
-          if (aware && ci != sm.scl[j]) continue;
-          if (it < 64) c_lo |= 1ull << it;
-          else c_hi |= 1ull << (it - 64);
+        for (int hw = 0; hw < 2; ++hw) {
+          unsigned long long mm = 0ull;
+          const int kb = 1 + part + hw * 64 * parts;
+          // branch-free body, unrolled once: two iterations' loads in flight (code size matters more than latency here)
+#pragma unroll 2
+          for (int b = 0; b < 64; ++b) {
+            const int k = kb + b * parts;
+            if (k > half) break;
+            int j = i + k;
+            j -= j >= n ? n : 0;
+            const float4 bj = sm.box[j];
+            bool c = !(thr_nonneg && (bj.z <= bi.x || bi.z <= bj.x || bj.w <= bi.y || bi.w <= bj.y));  // disjoint: IoU 0
+            if (aware) c = c && ci == sm.scl[j];
+            c = c && !(even && k == half && i >= half);  // even n: the antipodal pairs come up twice
+            mm |= (unsigned long long)c << b;
+          }
+          if (hw == 0) c_lo = mm;
+          else c_hi = mm;
+          if (kb + 64 * parts > half) break;
         }
       }
       // one list reservation per warp: exclusive prefix of the lanes' counts, lane 31 draws the block
@@ -1277,12 +1289,7 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
           int j = i + 1 + part + it * parts;
           if (j >= n) j -= n;
           const int lo = min(i, j), hi = max(i, j);
-          if (slot < kSmallPairs) {
-            sm.pairs[slot] = (uint32_t)lo | ((uint32_t)hi << 16);
-          } else if (ultra ? suppresses_tv(sm.box[lo], sm.box[hi], p.iou_thr64) : suppresses(sm.box[lo], sm.box[hi], thr)) {
-            atomicOr(&sm.M[lo][hi >> 5], 1u << (hi & 31));  // list full (a dense cluster): evaluate on the spot
-            atomicOr(&sm.M[hi][lo >> 5], 1u << (lo & 31));
-          }
+          if (slot < kSmallPairs) sm.pairs[slot] = (uint32_t)lo | ((uint32_t)hi << 16);
           ++slot;
         }
       }
@@ -1291,7 +1298,14 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
     __syncthreads();
     PHASE_STAMP(p.dbg, 52);
     {
-      const int listed = min(sm.n_pairs, kSmallPairs);
+      const int listed = sm.n_pairs;
+      if (listed > kSmallPairs) {
+        // more overlapping pairs than the list holds (one dense cluster): the chunked general path takes the frame
+        // from its candidate arrays, which are untouched
+        if (COLD_GENERAL) nms_general<GRID, NT>(p, frame, smem_raw, n);
+        else nms_general_body<GRID, NT>(p, frame, smem_raw, n);
+        return;
+      }
 #pragma unroll 1
       for (int q = tid; q < listed; q += NT) {
         const uint32_t pr = sm.pairs[q];
@@ -1399,13 +1413,13 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
   for (int r = 1; r < p.dbg_reps; ++r) {
     const int saved = p.cand_count[blockIdx.x];
     __syncthreads();
-    nms_frame<GRID, kNmsThreads, false>(p, blockIdx.x, smem_raw);
+    nms_frame<GRID, kNmsThreads, false, true>(p, blockIdx.x, smem_raw);
     __syncthreads();
     if (threadIdx.x == 0) p.cand_count[blockIdx.x] = saved;
     __syncthreads();
   }
 #endif
-  nms_frame<GRID, kNmsThreads, false>(p, blockIdx.x, smem_raw);
+  nms_frame<GRID, kNmsThreads, false, true>(p, blockIdx.x, smem_raw);
 }
 
 // Sparse scenes: sort + NMS + emit of frame i followed by the tracker update of stream i in ONE CTA of 256 threads.
@@ -1413,6 +1427,7 @@ __global__ void __launch_bounds__(kNmsThreads) k_sort_nms(const __grid_constant_
 // disappear from the critical chain decode -> NMS -> tracker (what a tick of a few streams per GPU is made of), and
 // 256-thread barriers replace 1024-thread ones.  Any candidate count is handled correctly (just more slowly than by
 // the 1024-thread grid variant), so the host's choice between the two never changes a result.
+template <bool ULTRA>
 __global__ void __launch_bounds__(kNmsThreadsSmall) k_post_track(const __grid_constant__ NmsParams q,
                                                                   const __grid_constant__ TrkParams t) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -1434,7 +1449,7 @@ __global__ void __launch_bounds__(kNmsThreadsSmall) k_post_track(const __grid_co
   TIMELINE_BEGIN(q.dbg, 44);
   const DetHandover hand{&sh, t.det_scale[blockIdx.x], t.has_scale};
   // the handover stages float32 detections; a skipped stream (host flag or device mask) takes none
-  nms_frame<false, kNmsThreadsSmall, true>(q, blockIdx.x, smem_raw, t.f_box ? &hand : nullptr, true);
+  nms_frame<false, kNmsThreadsSmall, true, ULTRA>(q, blockIdx.x, smem_raw, t.f_box ? &hand : nullptr, true);
   __syncthreads();  // this frame's detections were written by this CTA: visible to all of its threads from here on
   TIMELINE_END(q.dbg, 44);
   TIMELINE_BEGIN(q.dbg, 46);
@@ -1567,18 +1582,23 @@ int postprocess_configure(b200va_ctx* h) {
     CUDA_TRY(h, prefer_max_shared(k_decode_ring));
     CUDA_TRY(h, prefer_max_shared(k_sort_nms<false>));
     CUDA_TRY(h, prefer_max_shared(k_sort_nms<true>));
-    CUDA_TRY(h, prefer_max_shared(k_post_track));
+    CUDA_TRY(h, prefer_max_shared(k_post_track<false>));
+    CUDA_TRY(h, prefer_max_shared(k_post_track<true>));
   }
   const size_t smem = nms_smem_bytes(h->cfg.max_candidates);
   if (smem > 220 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_candidates %d needs %zu bytes of shared memory", h->cfg.max_candidates, smem);
   {
     const size_t fused = std::min<size_t>(200 * 1024, std::max(smem, tracker_smem_bytes(h->cfg.max_tracks)));
-    CUDA_TRY(h, raise_dyn_smem(k_post_track, fused));
+    CUDA_TRY(h, raise_dyn_smem(k_post_track<false>, fused));
+    CUDA_TRY(h, raise_dyn_smem(k_post_track<true>, fused));
     // k_post_track runs beside the letterbox in b200va_tick, and an SM only hosts kernels that agree on its L1 /
     // shared-memory split (see prefer_max_shared): ask for the split the 1080p letterbox launch gets (164 KB, six
     // 24.5 KB CTAs) instead of the one the driver would derive from this kernel's own occupancy
     const int pct = h->tune.post_carveout >= 0 ? h->tune.post_carveout : 71;
-    if (pct > 0) CUDA_TRY(h, cudaFuncSetAttribute(k_post_track, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    if (pct > 0) {
+      CUDA_TRY(h, cudaFuncSetAttribute(k_post_track<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+      CUDA_TRY(h, cudaFuncSetAttribute(k_post_track<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
   }
   CUDA_TRY(h, raise_dyn_smem(k_sort_nms<false>, smem));
   CUDA_TRY(h, raise_dyn_smem(k_sort_nms<true>, smem));
@@ -1842,7 +1862,8 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
                                          fuse->id_base, fuse->out, fuse->new_counts);
       if (rc != B200VA_OK) return rc;
       t.smem_tracks = trk_rows;
-      CUDA_TRY(h, launch_pdl(k_post_track, dim3(n), dim3(kNmsThreadsSmall), fused_smem, st, pdl, q, t));
+      if (q.ultra) CUDA_TRY(h, launch_pdl(k_post_track<true>, dim3(n), dim3(kNmsThreadsSmall), fused_smem, st, pdl, q, t));
+      else CUDA_TRY(h, launch_pdl(k_post_track<false>, dim3(n), dim3(kNmsThreadsSmall), fused_smem, st, pdl, q, t));
       fuse->done = true;
     } else if (dense && q.grid_off) {
       CUDA_TRY(h, launch_pdl(k_sort_nms<true>, dim3(n), dim3(kNmsThreads), nms_smem, st, pdl, q));
@@ -1900,7 +1921,8 @@ int postprocess_run_pending(b200va_handle h, void* stream) {
     PhaseScope phase(h, B200VA_PHASE_NMS, st);
     if (fusable && fused_smem <= 200 * 1024) {
       pc->t.smem_tracks = trk_rows;
-      CUDA_TRY(h, launch_pdl(k_post_track, dim3(n), dim3(kNmsThreadsSmall), fused_smem, st, false, pc->q, pc->t));
+      if (pc->q.ultra) CUDA_TRY(h, launch_pdl(k_post_track<true>, dim3(n), dim3(kNmsThreadsSmall), fused_smem, st, false, pc->q, pc->t));
+      else CUDA_TRY(h, launch_pdl(k_post_track<false>, dim3(n), dim3(kNmsThreadsSmall), fused_smem, st, false, pc->q, pc->t));
       LAUNCH_CHECK(h);
       return B200VA_OK;
     }

@@ -85,7 +85,7 @@ constexpr int kTrkThreadsMax = 1024;   // widest launch (dense scenes, see track
 constexpr int kTrkThreadsWide = 512;   // default launch width
 constexpr int kTrkThreadsMin = 256;
 constexpr int kDetChunk = 64;  // detections staged in shared memory at a time (two warps cover a chunk)
-constexpr int kTrkPairs = 1024;  // phase A, few pairs: capacity of the overlapping-pair list
+constexpr int kTrkPairs = 2048;  // phase A, few pairs: capacity of the overlapping-pair list (= the most pairs that path takes)
 constexpr int kCand = 6;        // candidate slots per detection and kind; more -> exact brute-force scan
 
 struct DetStage {
@@ -381,7 +381,8 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
     for (int t = tid; t < Tc + kDetChunk; t += kTrkThreads) aux[t] = 0;  // claims per track
     __syncthreads();
     const int pairs_t = nd * Tc, pairs = pairs_t + nd * nd;
-    if (SMALL || pairs <= 8 * kTrkThreads) {
+    static_assert(kTrkPairs >= 8 * kTrkThreadsMin, "the pair list must hold every pair of the small path");
+    if (SMALL || pairs <= min(kTrkPairs, 8 * kTrkThreads)) {
       // Few pairs.  The CTA is latency-bound: a warp in which ONE lane meets an overlapping pair walks all 32 lanes
       // through the float64 IoU (a dependent chain of ~170 instructions), and the warp that owns a detection does
       // that once per 32 tracks and again for the earlier detections.  So pass 1 spreads ALL (detection, track) and
@@ -411,30 +412,56 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
       };
       PHASE_STAMP(p.dbg, 58);
       const float inv_T = 1.0f / (float)max(Tc, 1), inv_n = 1.0f / (float)nd;
-#pragma unroll 1
-      for (int q = tid; q < pairs; q += kTrkThreads) {
-        int i, idx;
+      // which of this thread's pairs q = tid + it * kTrkThreads are listed (at most 8 rounds: pairs <= 8 * kTrkThreads)
+      auto unpack = [&](int q, int& i, int& idx) -> bool {
         const bool vs_track = q < pairs_t;
-        if (vs_track) {
-          i = (int)(((float)q + 0.5f) * inv_T);  // q / Tc for these small integers
-          idx = q - i * Tc;
-          if (scls[idx] != sd.cls[i]) continue;
-          if (!may_overlap(reinterpret_cast<const double4*>(sbox)[idx], sd.box[i])) continue;
-        } else {
-          const int r = q - pairs_t;
-          i = (int)(((float)r + 0.5f) * inv_n);
-          idx = r - i * nd;
-          if (idx >= i || sd.cls[idx] != sd.cls[i]) continue;
-          if (!may_overlap(sd.box[idx], sd.box[i])) continue;
+        const int r = vs_track ? q : q - pairs_t;
+        i = (int)(((float)r + 0.5f) * (vs_track ? inv_T : inv_n));  // r / Tc, r / nd for these small integers
+        idx = r - i * (vs_track ? Tc : nd);
+        return vs_track;
+      };
+      unsigned cmask = 0u;
+      {
+        int it = 0;
+#pragma unroll 1
+        for (int q = tid; q < pairs; q += kTrkThreads, ++it) {
+          int i, idx;
+          if (unpack(q, i, idx)) {
+            if (scls[idx] != sd.cls[i]) continue;
+            if (!may_overlap(reinterpret_cast<const double4*>(sbox)[idx], sd.box[i])) continue;
+          } else {
+            if (idx >= i || sd.cls[idx] != sd.cls[i]) continue;
+            if (!may_overlap(sd.box[idx], sd.box[i])) continue;
+          }
+          cmask |= 1u << it;
         }
-        const int slot = atomicAdd(&sh.n_plist, 1);
-        if (slot < kTrkPairs) sh.plist[slot] = (uint32_t)idx | ((uint32_t)i << 16) | (vs_track ? 0x80000000u : 0u);
-        else score(i, idx, vs_track);  // list full: evaluate on the spot
+      }
+      // one list reservation per warp (exclusive prefix of the lanes' counts; lane 31 draws the block)
+      {
+        const int mine = __popc(cmask);
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        int base = 0;
+        if (lane == 31 && incl > 0) base = atomicAdd(&sh.n_plist, incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int slot = base + incl - mine;
+        while (cmask) {
+          const int it = __ffs((int)cmask) - 1;
+          cmask &= cmask - 1u;
+          int i, idx;
+          const bool vs_track = unpack(tid + it * kTrkThreads, i, idx);
+          sh.plist[slot] = (uint32_t)idx | ((uint32_t)i << 16) | (vs_track ? 0x80000000u : 0u);  // (slot < pairs <= kTrkPairs)
+          ++slot;
+        }
       }
       PHASE_STAMP(p.dbg, 59);
       __syncthreads();
       PHASE_STAMP(p.dbg, 60);
-      const int listed = min(sh.n_plist, kTrkPairs);
+      const int listed = sh.n_plist;
 #pragma unroll 1
       for (int q = tid; q < listed; q += kTrkThreads) {
         const uint32_t e = sh.plist[q];
@@ -615,6 +642,7 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
   const size_t ob = (size_t)bi * p.o_rows;
   if (tid == 0) s_base = 0;
   __syncthreads();
+  int kept_total = 0;  // (thread 0) rows that survive; stays 0 for an empty table
   for (int t0 = 0; t0 < T; t0 += kTrkThreads) {
     const int t = t0 + tid;
     bool keep = false;
@@ -660,6 +688,14 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
         p.o_hits[ob + dst] = hits;
       }
     }
+    if (t0 + kTrkThreads >= T) {  // last round (the only one of a small table): no further barrier needed
+      if (tid == 0) {
+        int tot = s_base;
+        for (int w = 0; w < kTrkThreads / 32; ++w) tot += warp_cnt[w];
+        kept_total = tot;
+      }
+      break;
+    }
     __syncthreads();
     if (tid == 0) {
       int tot = 0;
@@ -669,11 +705,11 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
     __syncthreads();
   }
   if (tid == 0) {
-    S.count[slot] = s_base;
+    S.count[slot] = kept_total;
     S.cur[slot] = nxt;
     S.new_count[bi] = s_new;
-    if (p.o_count) p.o_count[bi] = s_base;
-    if (p.o_id && s_base > p.o_rows) atomicOr(p.flags + FLAG_TRACK_ROWS, 1);
+    if (p.o_count) p.o_count[bi] = kept_total;
+    if (p.o_id && kept_total > p.o_rows) atomicOr(p.flags + FLAG_TRACK_ROWS, 1);
     if (p.o_new) p.o_new[bi] = s_new;
   }
 
