@@ -729,6 +729,38 @@ struct DetHandover {
 // GRID: carries the kept-box grid code.  Two instantiations because the grid path's registers and stack slots slow
 // the common small-n launch (which never runs it) from 9.5 to 14 us when it is compiled in; the host picks per launch
 // from the candidate counts the previous launch reported (NmsParams::stats).
+// Bitonic sort of np2 (a power of two >= 64) 64-bit keys in shared memory, descending, by a CTA of NT threads; ends with
+// a block barrier.  Only the warps that own a compare-exchange take part (named barrier 1).  Thread q owns the q-th
+// pair of a step; for j <= 32 the 32 pairs of a warp lie inside one aligned block of 64 keys, so consecutive steps
+// with j <= 32 depend on nothing another warp writes and a __syncwarp separates them; the block-wide barrier is paid
+// only around the steps with j > 32 (20 of the 66 steps at 2048 keys).
+template <int NT>
+__device__ __forceinline__ void block_bitonic_sort_desc(unsigned long long* keys, const int np2) {
+  const int tid = threadIdx.x;
+  const int sort_threads = min(NT, max(32, np2 >> 1));
+  if (tid < sort_threads) {
+    for (int k = 2; k <= np2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int q = tid; q < (np2 >> 1); q += sort_threads) {
+          // q-th pair of this round: i has bit j clear
+          const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+          const int ixj = i | j;
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) {
+            keys[i] = b;
+            keys[ixj] = a;
+          }
+        }
+        const int j_next = j > 1 ? (j >> 1) : k;  // first step of the next stage has j = (2k) / 2 = k
+        if (sort_threads == 32 || (j <= 32 && j_next <= 32)) __syncwarp();
+        else asm volatile("bar.sync 1, %0;" ::"r"(sort_threads) : "memory");
+      }
+    }
+  }
+  __syncthreads();
+}
+
 // The general path of nms_frame (more than kSmallN candidates): bitonic sort, greedy NMS in 64-box chunks, emit.
 // Deliberately NOT inlined: the latency-bound CTAs of a sparse tick stall on instruction fetch more than on anything
 // else (ncu: stall_no_inst 29-33 % of all samples in k_post_track), so the code a small frame never runs must not
@@ -765,34 +797,7 @@ __device__ __forceinline__ void nms_general_body(const NmsParams& p, const int f
   __syncthreads();
 
   PHASE_STAMP(p.dbg, 17);
-  {
-    // bitonic sort, descending.  Only the warps that own a compare-exchange take part (named barrier 1).
-    // Thread q owns the q-th pair of a step; for j <= 32 the 32 pairs of a warp lie inside one aligned block of 64
-    // keys, so consecutive steps with j <= 32 depend on nothing another warp writes and a __syncwarp separates
-    // them; the block-wide barrier is paid only around the steps with j > 32 (20 of the 66 steps at 2048 keys).
-    const int sort_threads = min(NT, max(32, np2 >> 1));
-    if (tid < sort_threads) {
-      for (int k = 2; k <= np2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int q = tid; q < (np2 >> 1); q += sort_threads) {
-            // q-th pair of this round: i has bit j clear
-            const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1));
-            const int ixj = i | j;
-            const unsigned long long a = keys[i], b = keys[ixj];
-            const bool desc = (i & k) == 0;
-            if (desc ? (a < b) : (a > b)) {
-              keys[i] = b;
-              keys[ixj] = a;
-            }
-          }
-          const int j_next = j > 1 ? (j >> 1) : k;  // first step of the next stage has j = (2k) / 2 = k
-          if (sort_threads == 32 || (j <= 32 && j_next <= 32)) __syncwarp();
-          else asm volatile("bar.sync 1, %0;" ::"r"(sort_threads) : "memory");
-        }
-      }
-    }
-    __syncthreads();
-  }
+  block_bitonic_sort_desc<NT>(keys, np2);
   PHASE_STAMP(p.dbg, 18);
   // gather boxes and class ids of the sorted candidates into shared memory in one round of global loads
   for (int i = tid; i < n; i += NT) {
@@ -1461,6 +1466,291 @@ __global__ void __launch_bounds__(kNmsThreadsSmall) k_post_track(const __grid_co
   TIMELINE_END(q.dbg, 46);  // (threads the tracker retires early never get here; thread 0 always does)
 }
 
+
+// ---- dense scenes: NMS off "one CTA on one SM" -------------------------------------------------------------------
+// k_sort_nms keeps a whole frame in one CTA; with ~1800 candidates it is issue-bound on ONE SM per frame (32 of 148 SMs
+// busy, 113-130 us).  The dense path splits the work by what is parallel and what is not:
+//   k_dense_sort   one CTA per frame: sort the keys, leave keys / boxes / classes in score order in HBM scratch.
+//   k_dense_mask   every SM: the suppression predicate of ALL pairs (i, j >= chunk start of i) as a bit matrix,
+//                  stored transposed (word w of row i at [w][i]) so that a warp's 32 rows write one 128-byte line.
+//                  A thread owns a row and walks the columns; the column box is a warp-uniform load.
+//   k_dense_sweep  one CTA per frame: the greedy recursion itself, chunk by chunk from the matrix alone -- the ballot
+//                  fixed point inside a 64-box chunk, then the kept rows OR-ed into the suppressed bitmap of the later
+//                  chunks -- followed by the emit step.  No IoU arithmetic on the sequential path.
+// Results are those of the single-kernel path bit for bit (same predicate, same greedy order).
+struct DenseNms {
+  unsigned long long* keys;  // [frames][cap] sorted, descending
+  float4* box;               // [frames][cap] score order (class-shifted in Ultralytics mode)
+  uint16_t* cls;             // [frames][cap]
+  int32_t* n;                // [frames] candidates of the frame (after the max_candidates clamp)
+  uint32_t* mask;            // [frames][cap / 32][cap]: bit b of [w][i] = boxes i and 32 w + b suppress each other
+  int cap;                   // rows per frame (a power of two, <= kDenseCapMax)
+};
+constexpr int kDenseCapMax = 4096;
+constexpr int kDenseRows = 128;    // rows (threads) per k_dense_mask CTA
+constexpr int kDenseCols = 256;    // columns per k_dense_mask CTA (eight words of the bit matrix)
+constexpr int kSweepThreads = 512;
+
+__global__ void __launch_bounds__(kNmsThreads) k_dense_sort(const __grid_constant__ NmsParams p, const DenseNms D) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);  // [np2]
+  griddep_launch_dependents();
+  griddep_wait();
+  const int tid = threadIdx.x, frame = blockIdx.x;
+  const int n_raw = (p.skip && p.skip[frame]) ? 0 : p.cand_count[frame];
+  const int n = min(n_raw, p.max_cand);
+  __syncthreads();
+  if (tid == 0) {
+    if (p.stats && n > 256) *(volatile int*)p.stats = n;
+    p.cand_count[frame] = 0;
+    if (n_raw > p.max_cand) atomicOr(p.flags + FLAG_CAND_OVERFLOW, 1);
+    D.n[frame] = n;
+  }
+  if (n == 0) return;
+  int np2 = 64;
+  while (np2 < n) np2 <<= 1;
+  const size_t cbase = (size_t)frame * p.max_cand, dbase = (size_t)frame * D.cap;
+  for (int i = tid; i < np2; i += kNmsThreads) keys[i] = i < n ? p.cand_key[cbase + i] : 0ull;
+  __syncthreads();
+  block_bitonic_sort_desc<kNmsThreads>(keys, np2);
+  for (int i = tid; i < n; i += kNmsThreads) {
+    const unsigned long long k = keys[i];
+    const size_t o = cbase + (k & 0x3fffull);
+    float4 b = p.cand_box[o];
+    const int cl = p.cand_cls[o];
+    if (p.ultra && !p.ultra_agnostic) {  // boxes = x[:, :4] + x[:, 5:6] * max_wh, float32 (the rounding is part of the semantics)
+      const float c = __fmul_rn((float)cl, 7680.f);
+      b = make_float4(__fadd_rn(b.x, c), __fadd_rn(b.y, c), __fadd_rn(b.z, c), __fadd_rn(b.w, c));
+    }
+    D.keys[dbase + i] = k;
+    D.box[dbase + i] = b;
+    D.cls[dbase + i] = (uint16_t)cl;
+  }
+}
+
+__global__ void __launch_bounds__(kDenseRows) k_dense_mask(const __grid_constant__ NmsParams p, const DenseNms D) {
+  __shared__ float2 sx[kDenseCols], sy[kDenseCols];  // this CTA's slice of columns: (x1, x2) and (y1, y2)
+  __shared__ uint16_t scls[kDenseCols];
+  const int frame = blockIdx.z;
+  const int n = D.n[frame];
+  const int r0 = blockIdx.y * kDenseRows;  // a thread owns row r0 + tid
+  const int j_begin = blockIdx.x * kDenseCols, j_end = min(n, j_begin + kDenseCols);
+  // a row needs every column from the start of its own 64-box chunk on (the columns before the row inside its chunk
+  // feed the in-chunk resolution; the predicate is symmetric): this CTA has work when its column slice reaches past
+  // the first chunk of its rows
+  if (r0 >= n || j_end <= r0) return;
+  const int tid = threadIdx.x, i = r0 + tid;
+  const size_t dbase = (size_t)frame * D.cap;
+  const float4* __restrict__ box = D.box + dbase;
+  const uint16_t* __restrict__ cls = D.cls + dbase;
+  uint32_t* __restrict__ mask = D.mask + (size_t)frame * (D.cap / 32) * D.cap;
+  const bool aware = p.class_aware != 0, ultra = p.ultra != 0;
+  const float thr = p.iou_thr;
+  const bool thr_nonneg = ultra ? p.iou_thr64 >= 0.0 : thr >= 0.f;
+  for (int j = j_begin + tid; j < j_end; j += kDenseRows) {
+    const float4 bj = box[j];
+    sx[j - j_begin] = make_float2(bj.x, bj.z);
+    sy[j - j_begin] = make_float2(bj.y, bj.w);
+    scls[j - j_begin] = cls[j];
+  }
+  const bool valid = i < n;
+  const float4 bi = box[valid ? i : n - 1];
+  const int ci = cls[valid ? i : n - 1];
+  __syncthreads();
+  // Per word of 32 columns: a branch-free, fully unrolled pass marks the columns whose x-interval meets the row's (two
+  // compares on a broadcast 8-byte shared-memory load, the bit position an immediate); y-interval, class and the IoU
+  // formula are looked at for the marked columns only -- about one in ten.  (The first word of a row is that of its
+  // chunk start: warp-uniform.)
+  const int w_lo = max(j_begin, r0 + (tid & 64)) >> 5, w_hi = (j_end + 31) >> 5;
+  for (int w = w_lo; w < w_hi; ++w) {
+    const int j0 = w << 5, jn = min(32, n - j0);
+    const float2* __restrict__ px = sx + (j0 - j_begin);
+    const float2* __restrict__ py = sy + (j0 - j_begin);
+    uint32_t cand = 0u;
+    if (!thr_nonneg) {
+      cand = jn == 32 ? 0xffffffffu : ((1u << jn) - 1u);
+    } else if (jn == 32) {
+#pragma unroll
+      for (int b = 0; b < 32; ++b) {
+        const float2 xj = px[b];
+        cand |= (xj.y <= bi.x || bi.z <= xj.x) ? 0u : (1u << b);
+      }
+    } else {
+      for (int b = 0; b < jn; ++b) {
+        const float2 xj = px[b];
+        cand |= (xj.y <= bi.x || bi.z <= xj.x) ? 0u : (1u << b);
+      }
+    }
+    if (!valid) continue;
+    uint32_t bits = 0u;
+    while (cand) {
+      const int b = __ffs((int)cand) - 1;
+      cand &= cand - 1u;
+      const int j = j0 + b;
+      const float2 xj = px[b], yj = py[b];
+      if (thr_nonneg && (yj.y <= bi.y || bi.w <= yj.x)) continue;  // disjoint: IoU 0
+      if (j == i || (aware && ci != (int)scls[j - j_begin])) continue;
+      const float4 bj = make_float4(xj.x, yj.x, xj.y, yj.y);
+      // (i, j) in the order the greedy loop meets them: the earlier box first
+      const bool hit = ultra ? (j > i ? suppresses_tv(bi, bj, p.iou_thr64) : suppresses_tv(bj, bi, p.iou_thr64))
+                             : (j > i ? suppresses(bi, bj, thr) : suppresses(bj, bi, thr));
+      bits |= (uint32_t)hit << b;
+    }
+    mask[(size_t)w * D.cap + i] = bits;
+  }
+}
+
+// Rows c0 .. c0 + 63 of the bit matrix, words 2 ch .. words - 1, into a shared-memory stage: 256 bytes per word.
+__device__ __forceinline__ void sweep_stage_rows(uint32_t* stage, const uint32_t* __restrict__ mask, int cap, int ch, int words) {
+  const int c0 = ch << 6, nw = words - 2 * ch;
+  for (int t = threadIdx.x; t < nw * 16; t += kSweepThreads) {
+    const int w = t >> 4, part = t & 15;
+    cp_async16(stage + w * 64 + part * 4, mask + (size_t)(2 * ch + w) * cap + c0 + part * 4);
+  }
+  cp_async_commit();
+}
+
+__global__ void __launch_bounds__(kSweepThreads) k_dense_sweep(const __grid_constant__ NmsParams p, const DenseNms D) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  griddep_launch_dependents();  // a tracker kernel behind this one may be scheduled; its griddep_wait() waits for this grid
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, frame = blockIdx.x;
+  const int n = D.n[frame];
+  if (n == 0) {
+    if (tid == 0) p.out_count[frame] = 0;
+    return;
+  }
+  const int cap = D.cap;
+  uint32_t* stage0 = reinterpret_cast<uint32_t*>(smem_raw);  // two stages of [cap / 32][64] words
+  uint32_t* stage1 = stage0 + (cap / 32) * 64;
+  uint32_t* supp = stage1 + (cap / 32) * 64;                // [cap / 32]
+  uint32_t* keep_w = supp + cap / 32;                       // [cap / 32] what is emitted
+  int* keep_off = reinterpret_cast<int*>(keep_w + cap / 32);  // [cap / 64 + 1]
+  __shared__ unsigned long long s_kept;
+  __shared__ uint8_t s_klist[64];
+  const size_t dbase = (size_t)frame * cap;
+  const uint32_t* __restrict__ mask = D.mask + (size_t)frame * (cap / 32) * cap;
+  const int words = (n + 31) >> 5, nchunks = (n + 63) >> 6;
+  for (int w = tid; w < words; w += kSweepThreads) supp[w] = 0u;
+  // The rows of a chunk are staged one chunk ahead with cp.async (the whole upper triangle passes through shared memory
+  // once, 256 contiguous bytes per word), so neither the resolution nor the spreading of the kept rows waits for L2.
+  sweep_stage_rows(stage0, mask, cap, 0, words);
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const int c0 = ch << 6, m = min(64, n - c0);
+    uint32_t* const st = (ch & 1) ? stage1 : stage0;
+    if (ch + 1 < nchunks) {
+      sweep_stage_rows((ch & 1) ? stage0 : stage1, mask, cap, ch + 1, words);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const bool two = 2 * ch + 1 < words;
+    if (warp == 0) {
+      const unsigned long long e0 = (((unsigned long long)(two ? st[64 + lane] : 0u) << 32) | st[lane]) & ((1ull << lane) - 1ull);
+      const unsigned long long e1 =
+          (((unsigned long long)(two ? st[64 + lane + 32] : 0u) << 32) | st[lane + 32]) & ((1ull << (lane + 32)) - 1ull);
+      const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
+      const unsigned long long alive = ~(((unsigned long long)(two ? supp[2 * ch + 1] : 0u) << 32) | supp[2 * ch]) & valid;
+      const bool a0 = (alive >> lane) & 1ull, a1 = (alive >> (lane + 32)) & 1ull;
+      bool k0 = a0, k1 = a1;
+      unsigned long long kept;
+      while (true) {
+        kept = ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32) | __ballot_sync(0xffffffffu, k0);
+        const bool n0 = a0 && !(e0 & kept), n1 = a1 && !(e1 & kept);
+        const unsigned changed = __ballot_sync(0xffffffffu, n0 != k0 || n1 != k1);
+        k0 = n0;
+        k1 = n1;
+        if (!changed) break;
+      }
+      if (k0) s_klist[__popcll(kept & ((1ull << lane) - 1ull))] = (uint8_t)lane;
+      if (k1) s_klist[__popcll(kept & ((1ull << (lane + 32)) - 1ull))] = (uint8_t)(lane + 32);
+      if (lane == 0) {
+        s_kept = kept;
+        keep_w[2 * ch] = (uint32_t)kept;
+        if (two) keep_w[2 * ch + 1] = (uint32_t)(kept >> 32);
+      }
+    }
+    __syncthreads();
+    {
+      // the kept rows of this chunk mark the boxes of the later chunks: (word, eighth of the kept rows) per thread
+      const int nk = __popcll(s_kept);
+      const int later = words - (2 * ch + 2);
+      const int t = tid >> 3, part = tid & 7;
+      for (int wl = t; wl < later; wl += kSweepThreads / 8) {
+        const uint32_t* __restrict__ row = st + (2 + wl) * 64;
+        uint32_t acc = 0u;
+        for (int q = part; q < nk; q += 8) acc |= row[s_klist[q]];
+        if (acc) atomicOr(&supp[2 * ch + 2 + wl], acc);
+      }
+    }
+    __syncthreads();
+  }
+  const bool ultra = p.ultra != 0;
+  // ultralytics: `i = i[:max_det]` on the NMS survivors, before anything else looks at them
+  if (ultra) {
+    if (tid == 0) {
+      int acc = 0;
+      for (int w = 0; w < words; ++w) {
+        uint32_t bits = keep_w[w];
+        const int room = p.max_det_cap - acc;
+        if (room <= 0) {
+          bits = 0u;
+        } else if (__popc(bits) > room) {
+          uint32_t kept_bits = 0u;
+          for (int r = 0; r < room; ++r) {  // keep the `room` lowest set bits
+            const uint32_t low = bits & (0u - bits);
+            kept_bits |= low;
+            bits ^= low;
+          }
+          bits = kept_bits;
+        }
+        keep_w[w] = bits;
+        acc += __popc(bits);
+      }
+    }
+    __syncthreads();
+  }
+  // filter_detections (detector.py:99-103): float64 compare on the kept boxes only
+  if (p.use_filter) {
+    for (int i = tid; i < n; i += kSweepThreads) {
+      if ((keep_w[i >> 5] >> (i & 31)) & 1u) {
+        const float conf = unorder_bits((uint32_t)(D.keys[dbase + i] >> 32));
+        if (!((double)conf >= p.filter_thr)) atomicAnd(&keep_w[i >> 5], ~(1u << (i & 31)));
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int acc = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+      keep_off[ch] = acc;
+      acc += __popc(keep_w[2 * ch]) + (2 * ch + 1 < words ? __popc(keep_w[2 * ch + 1]) : 0);
+    }
+    p.out_count[frame] = min(acc, p.max_dets);
+    if (acc > p.max_dets) atomicOr(p.flags + FLAG_DET_OVERFLOW, 1);
+  }
+  __syncthreads();
+  const size_t cbase = (size_t)frame * p.max_cand;
+  for (int i = tid; i < n; i += kSweepThreads) {
+    const int wi = i >> 5;
+    if (!((keep_w[wi] >> (i & 31)) & 1u)) continue;
+    const uint32_t lo = keep_w[wi & ~1], hi = (wi | 1) < words ? keep_w[wi | 1] : 0u;
+    const unsigned long long w = ((unsigned long long)hi << 32) | lo;
+    const int pos = keep_off[i >> 6] + __popcll(w & ((1ull << (i & 63)) - 1ull));
+    if (pos >= p.max_dets) continue;
+    const size_t o = (size_t)frame * p.max_dets + pos;
+    const unsigned long long k = D.keys[dbase + i];
+    const int slot = (int)(k & 0x3fffull);
+    float4 b = D.box[dbase + i];
+    if (ultra) b = ultra_scale_box(p.cand_box[cbase + slot], p.f[frame]);  // the un-shifted box
+    reinterpret_cast<float4*>(p.out_box)[o] = b;
+    p.out_conf[o] = unorder_bits((uint32_t)(k >> 32));
+    p.out_cls[o] = p.cand_cls[cbase + slot];  // the full int32 class id
+  }
+}
+
+static size_t dense_sweep_smem(int cap) { return (size_t)cap * 16 + (size_t)(cap / 32) * 8 + (cap / 64 + 1) * 4; }
+
 static int next_pow2(int v) {
   int p = 64;
   while (p < v) p <<= 1;
@@ -1602,6 +1892,23 @@ int postprocess_configure(b200va_ctx* h) {
   }
   CUDA_TRY(h, raise_dyn_smem(k_sort_nms<false>, smem));
   CUDA_TRY(h, raise_dyn_smem(k_sort_nms<true>, smem));
+  // dense-scene path (k_dense_sort / _mask / _sweep): scratch for the sorted candidates and the bit matrix
+  const int cap = next_pow2(h->cfg.max_candidates);
+  if (cap <= kDenseCapMax && h->tune.dense_impl != 1) {
+    DenseNms* D = new DenseNms();
+    memset(D, 0, sizeof(*D));
+    h->dense_nms = D;
+    D->cap = cap;
+    const size_t frames = (size_t)h->cand_set_frames;
+    CUDA_TRY(h, cudaMalloc(&D->keys, frames * cap * sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaMalloc(&D->box, frames * cap * sizeof(float4)));
+    CUDA_TRY(h, cudaMalloc(&D->cls, frames * cap * sizeof(uint16_t)));
+    CUDA_TRY(h, cudaMalloc(&D->n, frames * sizeof(int32_t)));
+    CUDA_TRY(h, cudaMalloc(&D->mask, frames * (size_t)(cap / 32) * cap * sizeof(uint32_t)));
+    CUDA_TRY(h, cudaMemset(D->n, 0, frames * sizeof(int32_t)));
+    CUDA_TRY(h, raise_dyn_smem(k_dense_sort, (size_t)cap * 8));
+    CUDA_TRY(h, raise_dyn_smem(k_dense_sweep, dense_sweep_smem(cap)));
+  }
   return B200VA_OK;
 }
 
@@ -1865,6 +2172,12 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
       if (q.ultra) CUDA_TRY(h, launch_pdl(k_post_track<true>, dim3(n), dim3(kNmsThreadsSmall), fused_smem, st, pdl, q, t));
       else CUDA_TRY(h, launch_pdl(k_post_track<false>, dim3(n), dim3(kNmsThreadsSmall), fused_smem, st, pdl, q, t));
       fuse->done = true;
+    } else if (dense && h->dense_nms) {
+      const DenseNms& D = *(const DenseNms*)h->dense_nms;
+      CUDA_TRY(h, launch_pdl(k_dense_sort, dim3(n), dim3(kNmsThreads), (size_t)D.cap * 8, st, pdl, q, D));
+      k_dense_mask<<<dim3(D.cap / kDenseCols, D.cap / kDenseRows, n), kDenseRows, 0, st>>>(q, D);
+      k_dense_sweep<<<n, kSweepThreads, dense_sweep_smem(D.cap), st>>>(q, D);
+      h->launches.fetch_add(2, std::memory_order_relaxed);
     } else if (dense && q.grid_off) {
       CUDA_TRY(h, launch_pdl(k_sort_nms<true>, dim3(n), dim3(kNmsThreads), nms_smem, st, pdl, q));
     } else {
@@ -1926,7 +2239,13 @@ int postprocess_run_pending(b200va_handle h, void* stream) {
       LAUNCH_CHECK(h);
       return B200VA_OK;
     }
-    if (dense && pc->q.grid_off) CUDA_TRY(h, launch_pdl(k_sort_nms<true>, dim3(n), dim3(kNmsThreads), nms_smem, st, false, pc->q));
+    if (dense && h->dense_nms) {
+      const DenseNms& D = *(const DenseNms*)h->dense_nms;
+      CUDA_TRY(h, launch_pdl(k_dense_sort, dim3(n), dim3(kNmsThreads), (size_t)D.cap * 8, st, false, pc->q, D));
+      k_dense_mask<<<dim3(D.cap / kDenseCols, D.cap / kDenseRows, n), kDenseRows, 0, st>>>(pc->q, D);
+      k_dense_sweep<<<n, kSweepThreads, dense_sweep_smem(D.cap), st>>>(pc->q, D);
+      h->launches.fetch_add(2, std::memory_order_relaxed);
+    } else if (dense && pc->q.grid_off) CUDA_TRY(h, launch_pdl(k_sort_nms<true>, dim3(n), dim3(kNmsThreads), nms_smem, st, false, pc->q));
     else CUDA_TRY(h, launch_pdl(k_sort_nms<false>, dim3(n), dim3(kNmsThreads), nms_plain, st, false, pc->q));
     LAUNCH_CHECK(h);
   }
@@ -1942,6 +2261,15 @@ bool postprocess_has_pending(b200va_handle h) {
 void postprocess_release(b200va_ctx* h) {
   delete (PendingChain*)h->pending_chain;
   h->pending_chain = nullptr;
+  if (DenseNms* D = (DenseNms*)h->dense_nms) {
+    if (D->keys) cudaFree(D->keys);
+    if (D->box) cudaFree(D->box);
+    if (D->cls) cudaFree(D->cls);
+    if (D->n) cudaFree(D->n);
+    if (D->mask) cudaFree(D->mask);
+    delete D;
+    h->dense_nms = nullptr;
+  }
 }
 
 // b200va_tick: post-process followed by the tracker update of the same rows; *fused tells the caller whether the
