@@ -61,7 +61,7 @@ struct b200va_ctx {
   // ---- device-side gates (gates.cu): skip mask read by the letterbox, decode, NMS and tracker kernels ----
   const uint8_t* skip_dev = nullptr;  // DEVICE uint8 [batch] or NULL (b200va_set_skip_mask)
   void* gates = nullptr;              // gates.cu: per-slot gate state
-  void* dense_nms = nullptr;          // postprocess.cu: scratch of the dense-scene NMS (sorted candidates, bit matrix)
+  void* dense_nms = nullptr;          // postprocess.cu: scratch of the dense-scene NMS (suppressor lists)
   void* egress = nullptr;  // egress.cu: INTER_AREA tables per geometry, device copy of the rectangle list
   // ---- b200va_tick: second stream for the post-process + tracker branch ----
   cudaStream_t side_stream = nullptr;    // non-blocking, highest priority (its 32-CTA kernels slot in first)
@@ -91,7 +91,8 @@ struct b200va_ctx {
     int pdl = 1;              // B200VA_PDL=0: no programmatic dependent launches
     int uniform_carveout = 0; // B200VA_UNIFORM_CARVEOUT=1: every tick kernel prefers the all-shared-memory split
     int post_carveout = -1;   // B200VA_POST_CARVEOUT=pct: preferred shared-memory carve-out of k_post_track (0: driver default)
-    int dense_impl = 0;       // B200VA_DENSE_IMPL=1: dense scenes stay on the single-kernel NMS (k_sort_nms<true>)
+    int dense_impl = 0;       // B200VA_DENSE_IMPL=1: dense scenes stay on the single-kernel NMS (k_sort_nms<true>); 2: every launch is 'dense'
+    int dense_ctas_per_sm = 0; // B200VA_DENSE_CTAS=n: CTAs per SM of k_dense_pairs (default 8)
     int trk_smem_tracks = 0;  // B200VA_TRK_SMEM_TRACKS=n: fix the tracker's shared-memory table at n rows (tests)
   } tune;
   // ---- developer phase timing (only written by builds with -DB200VA_PHASE_TIMING) ----

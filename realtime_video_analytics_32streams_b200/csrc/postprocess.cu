@@ -58,11 +58,30 @@ __device__ __forceinline__ float unorder_bits(uint32_t u) {
 
 // ultralytics scale_boxes + clip_boxes (utils/ops.py): un-pad, true division by float32(gain), clamp to [0, w] x [0, h]
 // (torch CPU semantics; torch CUDA multiplies by the float32 reciprocal instead).
+// NaN-propagating maximum / minimum (FMNMX.NAN / FMNMX3.NAN): the result is NaN as soon as one input is -- what
+// np.maximum, np.minimum and np.clip do; fmaxf / fminf return the other operand instead
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float min_nan(float a, float b) {
+  float d;
+  asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ float max3_nan(float a, float b, float c) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+__device__ __forceinline__ float clip_nan(float x, float lo, float hi) { return min_nan(max_nan(x, lo), hi); }  // np.clip
+
 __device__ __forceinline__ float4 ultra_scale_box(float4 b, const PostFrame& f) {
-  b.x = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.x, f.left), f.scale), 0.f), f.xmax);
-  b.y = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.y, f.top), f.scale), 0.f), f.ymax);
-  b.z = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.z, f.left), f.scale), 0.f), f.xmax);
-  b.w = fminf(fmaxf(__fdiv_rn(__fsub_rn(b.w, f.top), f.scale), 0.f), f.ymax);
+  b.x = clip_nan(__fdiv_rn(__fsub_rn(b.x, f.left), f.scale), 0.f, f.xmax);  // (clamp_ keeps a NaN)
+  b.y = clip_nan(__fdiv_rn(__fsub_rn(b.y, f.top), f.scale), 0.f, f.ymax);
+  b.z = clip_nan(__fdiv_rn(__fsub_rn(b.z, f.left), f.scale), 0.f, f.xmax);
+  b.w = clip_nan(__fdiv_rn(__fsub_rn(b.w, f.top), f.scale), 0.f, f.ymax);
   return b;
 }
 
@@ -76,10 +95,10 @@ __device__ __forceinline__ float4 decode_box(float cx, float cy, float w, float 
   x2 = __fdiv_rn(__fsub_rn(x2, f.left), f.scale);
   y1 = __fdiv_rn(__fsub_rn(y1, f.top), f.scale);
   y2 = __fdiv_rn(__fsub_rn(y2, f.top), f.scale);
-  x1 = fminf(fmaxf(x1, 0.f), f.xmax);
-  x2 = fminf(fmaxf(x2, 0.f), f.xmax);
-  y1 = fminf(fmaxf(y1, 0.f), f.ymax);
-  y2 = fminf(fmaxf(y2, 0.f), f.ymax);
+  x1 = clip_nan(x1, 0.f, f.xmax);  // np.clip keeps a NaN (fminf / fmaxf would turn it into a frame edge)
+  x2 = clip_nan(x2, 0.f, f.xmax);
+  y1 = clip_nan(y1, 0.f, f.ymax);
+  y2 = clip_nan(y2, 0.f, f.ymax);
   return make_float4(x1, y1, x2, y2);
 }
 
@@ -409,18 +428,6 @@ __device__ __forceinline__ void emit_quad(const PostParams& p, int frame, int la
   }
 }
 
-// NaN-propagating maximum (FMNMX.NAN / FMNMX3.NAN): the result is NaN as soon as one input is
-__device__ __forceinline__ float max_nan(float a, float b) {
-  float d;
-  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-  return d;
-}
-__device__ __forceinline__ float max3_nan(float a, float b, float c) {
-  float d;
-  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
-
 // One stage = `rows` consecutive channel rows of a tile, fetched by ONE tensor-map copy per 256-anchor box
 // (cp.async.bulk.tensor.3d -> UTMALDG): coordinates (anchor, channel, frame) of a [B, C, A] float32 tensor; rows past C
 // and anchors past A are out of bounds for the map and arrive as zeros without touching memory.  Row-by-row 1-D bulk
@@ -642,16 +649,27 @@ static_assert(sizeof(NmsParams) <= 4000, "kernel parameter block too large");
 
 // _iou of detector.py:469-481 in float32; returns true when box j must be suppressed by box i.
 __device__ __forceinline__ bool suppresses(const float4 a, const float4 b, float thr) {
-  const float x1 = fmaxf(a.x, b.x), y1 = fmaxf(a.y, b.y), x2 = fminf(a.z, b.z), y2 = fminf(a.w, b.w);
-  const float iw = fmaxf(0.f, __fsub_rn(x2, x1)), ih = fmaxf(0.f, __fsub_rn(y2, y1));
+  // np.maximum / np.minimum / np.clip propagate NaN: a box with a NaN coordinate has IoU NaN with every box, and
+  // `iou <= thr` is False for NaN -- it suppresses, and is suppressed by, everything
+  const float x1 = max_nan(a.x, b.x), y1 = max_nan(a.y, b.y), x2 = min_nan(a.z, b.z), y2 = min_nan(a.w, b.w);
+  const float iw = max_nan(0.f, __fsub_rn(x2, x1)), ih = max_nan(0.f, __fsub_rn(y2, y1));
   const float inter = __fmul_rn(iw, ih);
   const float area_a = __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y));
   const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
   const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
   // disjoint boxes (the common case): 0 / max(union, 1e-6) is exactly +-0 for any finite union
   if (inter == 0.f && fabsf(uni) <= 3.0e38f) return !(0.f <= thr);
-  const float iou = __fdiv_rn(inter, fmaxf(uni, 1e-6f));
+  const float iou = __fdiv_rn(inter, max_nan(uni, 1e-6f));
   return !(iou <= thr);
+}
+
+// A box with a NaN coordinate has IoU NaN with every box whatever its other coordinates say (NaN * 0 is NaN), so the
+// "these two are apart on one axis: IoU 0" short-cuts must not see the finite coordinates of such a box: the NMS
+// kernels work on this view of it (every coordinate NaN; the predicate is the same) and emit the box as decoded.
+__device__ __forceinline__ float4 nan_box_view(float4 b) {
+  const bool ok = b.x == b.x && b.y == b.y && b.z == b.z && b.w == b.w;
+  const float q = __int_as_float(0x7fffffff);
+  return ok ? b : make_float4(q, q, q, q);
 }
 
 // torchvision.ops.nms (csrc/ops/cpu/nms_kernel.cpp): inter / (area_i + area_j - inter) > thr, no epsilon.
@@ -808,14 +826,24 @@ __device__ __forceinline__ void nms_general_body(const NmsParams& p, const int f
       const float c = __fmul_rn((float)cl, 7680.f);
       b = make_float4(__fadd_rn(b.x, c), __fadd_rn(b.y, c), __fadd_rn(b.z, c), __fadd_rn(b.w, c));
     }
-    box[i] = b;
+    box[i] = p.ultra ? b : nan_box_view(b);
     scl[i] = (uint16_t)cl;
   }
   __syncthreads();
 
   PHASE_STAMP(p.dbg, 19);
   // few candidates: the survivors-vs-tail scan is cheaper than keeping the grid
-  const bool use_grid = GRID && grid != nullptr && !ultra && thr_nonneg && n > 256;
+  // (the grid assumes finite coordinates: a NaN box suppresses, and is suppressed by, boxes anywhere in the frame)
+  bool finite = true;
+  if (GRID && grid != nullptr && !ultra && thr_nonneg && n > 256) {
+    int bad = 0;
+    for (int i = tid; i < n; i += NT) {
+      const float4 b = box[i];
+      bad |= !(fabsf(b.x) <= 3.0e38f && fabsf(b.y) <= 3.0e38f && fabsf(b.z) <= 3.0e38f && fabsf(b.w) <= 3.0e38f);
+    }
+    finite = !__syncthreads_or(bad);
+  }
+  const bool use_grid = GRID && grid != nullptr && !ultra && thr_nonneg && n > 256 && finite;
   const float inv_cw = (float)kGX / (p.f[frame].xmax + 1.0f), inv_ch = (float)kGY / (p.f[frame].ymax + 1.0f);
   if (GRID && use_grid) {
     for (int c = tid; c < kCells; c += NT) grid->cnt[c] = 0;
@@ -1109,6 +1137,7 @@ __device__ __forceinline__ void nms_general_body(const NmsParams& p, const int f
         float4 b = box[i];
         const int slot = (int)(keys[i] & 0x3fffull);
         if (ultra) b = ultra_scale_box(small ? sm.ubox[slot] : p.cand_box[cbase + slot], p.f[frame]);  // the un-shifted box
+        else if (b.x != b.x) b = small ? sm.ubox[slot] : p.cand_box[cbase + slot];  // (nan_box_view: emit the box as decoded)
         const float cf = unorder_bits((uint32_t)(keys[i] >> 32));
         const int cl = small ? sm.ucls[slot] : p.cand_cls[cbase + slot];  // the full int32 class id (scl[] holds 16 bits)
         reinterpret_cast<float4*>(p.out_box)[o] = b;
@@ -1229,7 +1258,7 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
         b = make_float4(__fadd_rn(b.x, c), __fadd_rn(b.y, c), __fadd_rn(b.z, c), __fadd_rn(b.w, c));
       }
       sm.keys[tid] = k;
-      sm.box[tid] = b;
+      sm.box[tid] = ultra ? b : nan_box_view(b);
       sm.scl[tid] = (uint16_t)cl;
     }
     __syncthreads();
@@ -1395,6 +1424,7 @@ __device__ __forceinline__ void nms_frame(const NmsParams& p, const int frame, u
         float4 b = box[i];
         const int slot = (int)(keys[i] & 0x3fffull);
         if (ultra) b = ultra_scale_box(small ? sm.ubox[slot] : p.cand_box[cbase + slot], p.f[frame]);  // the un-shifted box
+        else if (b.x != b.x) b = small ? sm.ubox[slot] : p.cand_box[cbase + slot];  // (nan_box_view: emit the box as decoded)
         const float cf = unorder_bits((uint32_t)(keys[i] >> 32));
         const int cl = small ? sm.ucls[slot] : p.cand_cls[cbase + slot];  // the full int32 class id (scl[] holds 16 bits)
         reinterpret_cast<float4*>(p.out_box)[o] = b;
@@ -1469,287 +1499,425 @@ __global__ void __launch_bounds__(kNmsThreadsSmall) k_post_track(const __grid_co
 
 // ---- dense scenes: NMS off "one CTA on one SM" -------------------------------------------------------------------
 // k_sort_nms keeps a whole frame in one CTA; with ~1800 candidates it is issue-bound on ONE SM per frame (32 of 148 SMs
-// busy, 113-130 us).  The dense path splits the work by what is parallel and what is not:
-//   k_dense_sort   one CTA per frame: sort the keys, leave keys / boxes / classes in score order in HBM scratch.
-//   k_dense_mask   every SM: the suppression predicate of ALL pairs (i, j >= chunk start of i) as a bit matrix,
-//                  stored transposed (word w of row i at [w][i]) so that a warp's 32 rows write one 128-byte line.
-//                  A thread owns a row and walks the columns; the column box is a warp-uniform load.
-//   k_dense_sweep  one CTA per frame: the greedy recursion itself, chunk by chunk from the matrix alone -- the ballot
-//                  fixed point inside a 64-box chunk, then the kept rows OR-ed into the suppressed bitmap of the later
-//                  chunks -- followed by the emit step.  No IoU arithmetic on the sequential path.
-// Results are those of the single-kernel path bit for bit (same predicate, same greedy order).
+// busy, 113-130 us).  Greedy NMS is the unique solution of  kept_i = no kept j ahead of i (in score order) suppresses i,
+// and that recurrence needs neither a sorted array nor a sequential sweep:
+//   k_dense_pairs    every SM: the suppression predicate of ALL unordered pairs of a frame's candidates, in the order
+//                    decode left them (slot order, no sort).  A work item is 128 rows x 64 columns of the upper
+//                    triangle, handed out to single warps through an atomic counter; a thread owns four rows (a 16-byte column broadcast
+//                    from shared memory costs four cycles of its pipe however many lanes want the same address, so it
+//                    has to feed four tests), four compares decide "the boxes overlap at all" branch-free, the
+//                    overlapping pairs of a warp (2 % of all) are queued in shared memory and the IoU formula then runs
+//                    over the queue with every lane busy.  A hit appends the box with the larger key (the one greedy
+//                    NMS meets first) to the suppressor list of the other one; the hits of an item are recorded together
+//                    (their key loads and atomics are dependent round trips to L2).
+//   k_dense_resolve  one CTA per frame: Jacobi iteration of the recurrence over the suppressor lists (a box of
+//                    dependency depth d is final after d + 1 rounds; clusters of near-duplicates have depth 1-2), then
+//                    only the KEPT boxes (~300 of 1800) are ordered by key -- rank among the kept = output position.
+// A frame with a full suppressor list (more than kNbrCap boxes ahead of one candidate suppress it) or a dependency chain
+// longer than kResolveRounds falls back to the single-CTA path inside k_dense_resolve (same results, slower).
+// Results are those of the single-kernel path bit for bit: same predicate (IEEE add / mul / min / max commute, so the
+// predicate is symmetric in its two boxes), same greedy recurrence, same tie rule (the keys are unique).
 struct DenseNms {
-  unsigned long long* keys;  // [frames][cap] sorted, descending
-  float4* box;               // [frames][cap] score order (class-shifted in Ultralytics mode)
-  uint16_t* cls;             // [frames][cap]
-  int32_t* n;                // [frames] candidates of the frame (after the max_candidates clamp)
-  uint32_t* mask;            // [frames][cap / 32][cap]: bit b of [w][i] = boxes i and 32 w + b suppress each other
-  int cap;                   // rows per frame (a power of two, <= kDenseCapMax)
+  int32_t* nbr_cnt;  // [frames][max_cand] suppressors found for a candidate; all zero between launches
+  uint16_t* nbr;     // [frames][max_cand][kNbrCap] slots of the suppressors, in no particular order
+  int32_t* work;     // next work item of k_dense_pairs; zero between launches (k_dense_resolve clears it)
+  int max_cand;
+  int ctas;          // grid of k_dense_pairs
 };
-constexpr int kDenseCapMax = 4096;
-constexpr int kDenseRows = 128;    // rows (threads) per k_dense_mask CTA
-constexpr int kDenseCols = 256;    // columns per k_dense_mask CTA (eight words of the bit matrix)
-constexpr int kSweepThreads = 512;
+constexpr int kDenseCandMax = 4096;   // candidates per frame the dense path is built for (k_dense_resolve: 4 rows per thread)
+constexpr int kNbrCap = 32;
+constexpr int kPairWarps = 4, kPairThreads = 32 * kPairWarps;  // the warps of a CTA work on their own items
+constexpr int kPairGroups = 4;                               // a thread owns kPairGroups rows (32 apart)
+constexpr int kPairRows = 32 * kPairGroups;                  // rows of a work item (one warp)
+#ifndef B200VA_PAIR_COLS
+#define B200VA_PAIR_COLS 64
+#endif
+constexpr int kPairCols = B200VA_PAIR_COLS;                  // columns of a work item (64 or 128)
+constexpr int kPairRC = kPairRows / kPairCols;               // column tiles per row tile
+constexpr int kPairColBits = kPairCols == 64 ? 6 : 7;
+constexpr int kPairQueue = 256;                              // overlapping pairs a warp queues per 32 columns
+constexpr int kPairHits = 128;                               // suppressing pairs a warp collects before it records them
+constexpr int kResolveThreads = 1024, kResolveRows = kDenseCandMax / kResolveThreads;
+constexpr int kResolveRounds = 64;
+constexpr int kRankMax = 512;         // more kept boxes than this are ordered by the bitonic sort instead of by rank
 
-__global__ void __launch_bounds__(kNmsThreads) k_dense_sort(const __grid_constant__ NmsParams p, const DenseNms D) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);  // [np2]
+// Ultralytics' class-aware trick: boxes = x[:, :4] + x[:, 5:6] * max_wh in float32 (the rounding is part of the semantics)
+__device__ __forceinline__ float4 nms_view_of_box(const NmsParams& p, float4 b, int cl) {
+  if (!p.ultra) return nan_box_view(b);
+  if (!p.ultra_agnostic) {
+    const float c = __fmul_rn((float)cl, 7680.f);
+    b = make_float4(__fadd_rn(b.x, c), __fadd_rn(b.y, c), __fadd_rn(b.z, c), __fadd_rn(b.w, c));
+  }
+  return b;
+}
+
+// Work items of a frame with n candidates: row tile r (kPairRows rows) x column tile c (kPairCols columns) with
+// c >= kPairRC r (the upper triangle, diagonal tiles included).
+__device__ __forceinline__ int dense_items_of(int n) {
+  const int R = (n + kPairRows - 1) / kPairRows, Cn = (n + kPairCols - 1) / kPairCols;
+  return n > 1 ? R * Cn - kPairRC * (R * (R - 1) / 2) : 0;
+}
+static_assert(kPairRows == kPairRC * kPairCols && (kPairCols == 64 || kPairCols == 128), "bad work item shape");
+
+struct PairWarp {  // a warp's staging area
+  float4 row[kPairRows];
+  float4 col[kPairCols];
+  int rcl[kPairRows];
+  int ccl[kPairCols];
+  uint16_t queue[kPairQueue];
+  uint16_t hits[kPairHits];
+};
+
+__global__ void __launch_bounds__(kPairThreads, 8) k_dense_pairs(const __grid_constant__ NmsParams p, const DenseNms D, const int frames) {
+  __shared__ PairWarp s_warp[kPairWarps];
+  __shared__ int s_first[B200VA_LAUNCH_FRAMES + 1];  // first work item of each frame
+  __shared__ int s_n[B200VA_LAUNCH_FRAMES];
   griddep_launch_dependents();
   griddep_wait();
-  const int tid = threadIdx.x, frame = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int next = 0;
+  if (lane == 0) next = atomicAdd(D.work, 1);  // items are handed out dynamically: diagonal tiles are cheaper than the rest
+  if (tid < 32) {
+    int v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int f = lane + 32 * h;
+      int n = 0;
+      if (f < frames && !(p.skip && p.skip[f])) n = min(p.cand_count[f], p.max_cand);
+      s_n[f] = n;
+      v[h] = dense_items_of(n);
+    }
+    int base = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int incl = v[h];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      s_first[1 + lane + 32 * h] = base + incl;
+      base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_first[0] = 0;
+  }
+  __syncthreads();  // (the only block-wide barrier: from here on every warp is on its own)
+  static_assert(B200VA_LAUNCH_FRAMES == 64, "the item scan covers two frames per lane");
+  const int total = s_first[B200VA_LAUNCH_FRAMES];
+  const bool aware = p.class_aware != 0, ultra = p.ultra != 0;
+  const float thr = p.iou_thr;
+  const bool thr_nonneg = ultra ? p.iou_thr64 >= 0.0 : thr >= 0.f;
+  PairWarp& S = s_warp[warp];
+  for (;;) {
+    const int item = __shfl_sync(0xffffffffu, next, 0);
+    if (item >= total) break;
+    if (lane == 0) next = atomicAdd(D.work, 1);  // (in flight while this item is worked on)
+    // frame of the item: how many frames start at or before it
+    const int frame = __popc(__ballot_sync(0xffffffffu, s_first[1 + lane] <= item)) +
+                      __popc(__ballot_sync(0xffffffffu, s_first[33 + lane] <= item));
+    const int n = s_n[frame];
+    const int Cn = (n + kPairCols - 1) / kPairCols;
+    int local = item - s_first[frame], r = 0;
+    while (local >= Cn - kPairRC * r) {
+      local -= Cn - kPairRC * r;
+      ++r;
+    }
+    const int c = kPairRC * r + local;
+    const size_t cbase = (size_t)frame * p.max_cand;
+    const int jb = c * kPairCols, jn = min(kPairCols, n - jb);
+    const int row0 = r * kPairRows;
+    float4 bi[kPairGroups];
+#pragma unroll
+    for (int q = 0; q < kPairGroups; ++q) {
+      const int rl = q * 32 + lane, i = row0 + rl;
+      bi[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int ci = 0;
+      if (i < n) {
+        ci = p.cand_cls[cbase + i];
+        bi[q] = nms_view_of_box(p, p.cand_box[cbase + i], ci);
+      }
+      S.row[rl] = bi[q];
+      S.rcl[rl] = ci;
+    }
+#pragma unroll
+    for (int h = 0; h < kPairCols / 32; ++h) {
+      const int cl = 32 * h + lane;
+      if (cl < jn) {
+        const int cj = p.cand_cls[cbase + jb + cl];
+        S.col[cl] = nms_view_of_box(p, p.cand_box[cbase + jb + cl], cj);
+        S.ccl[cl] = cj;
+      }
+    }
+    __syncwarp();
+    // one overlapping pair, rows and columns by their position in the item: does either box suppress the other?
+    auto test_pair = [&](const int rl, const int col) -> bool {
+      if (aware && S.rcl[rl] != S.ccl[col]) return false;
+      const float4 a = S.row[rl], b = S.col[col];
+      return ultra ? suppresses_tv(a, b, p.iou_thr64) : suppresses(a, b, thr);
+    };
+    // a suppressing pair: the box greedy NMS meets first (the larger key) goes on the suppressor list of the other one
+    auto record = [&](const int rl, const int col) {
+      const int i = row0 + rl, j = jb + col;
+      const bool i_first = p.cand_key[cbase + i] > p.cand_key[cbase + j];
+      const int loser = i_first ? j : i, winner = i_first ? i : j;
+      const size_t row = (size_t)frame * D.max_cand + loser;
+      const int slot = atomicAdd(D.nbr_cnt + row, 1);
+      if (slot < kNbrCap) D.nbr[row * kNbrCap + slot] = (uint16_t)winner;
+    };
+    // The hits of an item are recorded together at its end: the two key loads and the atomic of a hit are dependent
+    // round trips to L2, paid once per item this way instead of once per 32 queued pairs.
+    int n_hits = 0;
+    auto flush_hits = [&]() {
+      __syncwarp();
+      for (int e = lane; e < n_hits; e += 32) {
+        const int code = S.hits[e];
+        record(code >> kPairColBits, code & (kPairCols - 1));
+      }
+      n_hits = 0;
+      __syncwarp();
+    };
+#pragma unroll 1
+    for (int w = 0; w < kPairCols / 32; ++w) {
+      const int j0 = jb + 32 * w, cnt = min(32, n - j0);
+      if (cnt <= 0 || j0 + 31 <= row0) continue;  // (warp-uniform) no column of the word lies behind a row of the warp
+      const float4* __restrict__ pc = S.col + 32 * w;
+      uint32_t cand[kPairGroups];
+#pragma unroll
+      for (int q = 0; q < kPairGroups; ++q) cand[q] = thr_nonneg ? 0u : 0xffffffffu;  // a negative threshold: disjoint boxes suppress each other too
+      if (thr_nonneg) {
+        // Two boxes are apart when one ends before the other begins, on either axis: the sign of one of four
+        // differences (subtractions on the FMA pipe; two LOP3 and a funnel shift -- sign bit into the accumulator --
+        // on the ALU pipe).  Touching boxes (difference +0) and NaN coordinates (the canonical NaN is positive, and
+        // nan_box_view made every coordinate of such a box NaN) stay in: the formula then decides.
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+          const float4 cb = pc[b];
+#pragma unroll
+          for (int q = 0; q < kPairGroups; ++q) {
+            const int t = __float_as_int(__fsub_rn(cb.z, bi[q].x)) | __float_as_int(__fsub_rn(bi[q].z, cb.x)) |
+                          __float_as_int(__fsub_rn(cb.w, bi[q].y)) | __float_as_int(__fsub_rn(bi[q].w, cb.y));
+            cand[q] = __funnelshift_l((uint32_t)t, cand[q], 1);  // bit 31 - b: column b is apart from the row
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kPairGroups; ++q) cand[q] = ~__brev(cand[q]);
+      }
+      // columns of this frame that come after row i; queue what is left
+      const uint32_t in_frame = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+      int mine = 0;
+#pragma unroll
+      for (int q = 0; q < kPairGroups; ++q) {
+        const int i = row0 + q * 32 + lane;
+        uint32_t live = in_frame;
+        if (i >= j0) live = (i - j0 >= 31) ? 0u : (live & ~((2u << (i - j0)) - 1u));
+        cand[q] = i < n ? (cand[q] & live) : 0u;
+        mine += __popc(cand[q]);
+      }
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int queued = min(__shfl_sync(0xffffffffu, incl, 31), kPairQueue);
+      int pos = incl - mine;
+#pragma unroll
+      for (int q = 0; q < kPairGroups; ++q) {
+        uint32_t cq = cand[q];
+        while (cq) {
+          const int b = __ffs((int)cq) - 1;
+          cq &= cq - 1u;
+          if (pos < kPairQueue) S.queue[pos] = (uint16_t)(((q * 32 + lane) << kPairColBits) | (32 * w + b));
+          else if (test_pair(q * 32 + lane, 32 * w + b)) record(q * 32 + lane, 32 * w + b);  // (queue full: on the spot)
+          ++pos;
+        }
+      }
+      __syncwarp();
+      for (int e0 = 0; e0 < queued; e0 += 32) {
+        if (n_hits > kPairHits - 32) flush_hits();
+        const int e = e0 + lane;
+        const int code = e < queued ? S.queue[e] : 0;
+        const bool hit = e < queued && test_pair(code >> kPairColBits, code & (kPairCols - 1));
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (hit) S.hits[n_hits + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)code;
+        n_hits += __popc(bal);
+      }
+      __syncwarp();
+    }
+    flush_hits();
+  }
+}
+
+__global__ void __launch_bounds__(kResolveThreads) k_dense_resolve(const __grid_constant__ NmsParams p, const DenseNms D) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ int s_m, s_out;
+  griddep_launch_dependents();  // a tracker kernel behind this one may be scheduled; its griddep_wait() waits for this grid
+  griddep_wait();
+  const int tid = threadIdx.x, lane = tid & 31, frame = blockIdx.x;
+  PHASE_STAMP(p.dbg, 36);
   const int n_raw = (p.skip && p.skip[frame]) ? 0 : p.cand_count[frame];
   const int n = min(n_raw, p.max_cand);
-  __syncthreads();
+  const size_t cbase = (size_t)frame * p.max_cand, fbase = (size_t)frame * D.max_cand;
+  // suppressor lists of this thread's rows: count, first eight entries (registers), the key
+  int cnt[kResolveRows];
+  uint4 nb[kResolveRows];
+  unsigned long long key[kResolveRows];
+  bool over = false;
+#pragma unroll
+  for (int q = 0; q < kResolveRows; ++q) {
+    const int r = tid + q * kResolveThreads;
+    cnt[q] = r < n ? D.nbr_cnt[fbase + r] : 0;
+    key[q] = r < n ? p.cand_key[cbase + r] : 0ull;
+    // (fetched in the same round trip as the count; entries past the count are stale and never looked at)
+    nb[q] = r < n ? *reinterpret_cast<const uint4*>(D.nbr + (fbase + r) * kNbrCap) : make_uint4(0u, 0u, 0u, 0u);
+  }
+#pragma unroll
+  for (int q = 0; q < kResolveRows; ++q) {
+    const int r = tid + q * kResolveThreads;
+    if (cnt[q] > 0) {
+      D.nbr_cnt[fbase + r] = 0;  // left clean for the next launch
+      over |= cnt[q] > kNbrCap;
+    }
+  }
+  const int kstride = (D.max_cand + 15) & ~15;
+  uint8_t* kept_a = smem_raw;           // [max_cand]
+  uint8_t* kept_b = kept_a + kstride;   // [max_cand]
+  unsigned long long* kkeys = reinterpret_cast<unsigned long long*>(smem_raw + 2 * (size_t)kstride);  // [pow2 >= max_cand]
+#pragma unroll
+  for (int q = 0; q < kResolveRows; ++q) {
+    const int r = tid + q * kResolveThreads;
+    if (r < n) kept_a[r] = kept_b[r] = cnt[q] == 0;  // nothing ahead suppresses it: kept, for good
+  }
+  if (tid == 0) {
+    s_m = 0;
+    s_out = 0;
+  }
+  const int fall_back = __syncthreads_or(over);  // (also: every thread has read the count)
   if (tid == 0) {
     if (p.stats && n > 256) *(volatile int*)p.stats = n;
     p.cand_count[frame] = 0;
     if (n_raw > p.max_cand) atomicOr(p.flags + FLAG_CAND_OVERFLOW, 1);
-    D.n[frame] = n;
+    if (frame == 0) *D.work = 0;  // (every CTA of k_dense_pairs has finished: griddep_wait / stream order)
   }
-  if (n == 0) return;
-  int np2 = 64;
-  while (np2 < n) np2 <<= 1;
-  const size_t cbase = (size_t)frame * p.max_cand, dbase = (size_t)frame * D.cap;
-  for (int i = tid; i < np2; i += kNmsThreads) keys[i] = i < n ? p.cand_key[cbase + i] : 0ull;
-  __syncthreads();
-  block_bitonic_sort_desc<kNmsThreads>(keys, np2);
-  for (int i = tid; i < n; i += kNmsThreads) {
-    const unsigned long long k = keys[i];
-    const size_t o = cbase + (k & 0x3fffull);
-    float4 b = p.cand_box[o];
-    const int cl = p.cand_cls[o];
-    if (p.ultra && !p.ultra_agnostic) {  // boxes = x[:, :4] + x[:, 5:6] * max_wh, float32 (the rounding is part of the semantics)
-      const float c = __fmul_rn((float)cl, 7680.f);
-      b = make_float4(__fadd_rn(b.x, c), __fadd_rn(b.y, c), __fadd_rn(b.z, c), __fadd_rn(b.w, c));
-    }
-    D.keys[dbase + i] = k;
-    D.box[dbase + i] = b;
-    D.cls[dbase + i] = (uint16_t)cl;
-  }
-}
-
-__global__ void __launch_bounds__(kDenseRows) k_dense_mask(const __grid_constant__ NmsParams p, const DenseNms D) {
-  __shared__ float2 sx[kDenseCols], sy[kDenseCols];  // this CTA's slice of columns: (x1, x2) and (y1, y2)
-  __shared__ uint16_t scls[kDenseCols];
-  const int frame = blockIdx.z;
-  const int n = D.n[frame];
-  const int r0 = blockIdx.y * kDenseRows;  // a thread owns row r0 + tid
-  const int j_begin = blockIdx.x * kDenseCols, j_end = min(n, j_begin + kDenseCols);
-  // a row needs every column from the start of its own 64-box chunk on (the columns before the row inside its chunk
-  // feed the in-chunk resolution; the predicate is symmetric): this CTA has work when its column slice reaches past
-  // the first chunk of its rows
-  if (r0 >= n || j_end <= r0) return;
-  const int tid = threadIdx.x, i = r0 + tid;
-  const size_t dbase = (size_t)frame * D.cap;
-  const float4* __restrict__ box = D.box + dbase;
-  const uint16_t* __restrict__ cls = D.cls + dbase;
-  uint32_t* __restrict__ mask = D.mask + (size_t)frame * (D.cap / 32) * D.cap;
-  const bool aware = p.class_aware != 0, ultra = p.ultra != 0;
-  const float thr = p.iou_thr;
-  const bool thr_nonneg = ultra ? p.iou_thr64 >= 0.0 : thr >= 0.f;
-  for (int j = j_begin + tid; j < j_end; j += kDenseRows) {
-    const float4 bj = box[j];
-    sx[j - j_begin] = make_float2(bj.x, bj.z);
-    sy[j - j_begin] = make_float2(bj.y, bj.w);
-    scls[j - j_begin] = cls[j];
-  }
-  const bool valid = i < n;
-  const float4 bi = box[valid ? i : n - 1];
-  const int ci = cls[valid ? i : n - 1];
-  __syncthreads();
-  // Per word of 32 columns: a branch-free, fully unrolled pass marks the columns whose x-interval meets the row's (two
-  // compares on a broadcast 8-byte shared-memory load, the bit position an immediate); y-interval, class and the IoU
-  // formula are looked at for the marked columns only -- about one in ten.  (The first word of a row is that of its
-  // chunk start: warp-uniform.)
-  const int w_lo = max(j_begin, r0 + (tid & 64)) >> 5, w_hi = (j_end + 31) >> 5;
-  for (int w = w_lo; w < w_hi; ++w) {
-    const int j0 = w << 5, jn = min(32, n - j0);
-    const float2* __restrict__ px = sx + (j0 - j_begin);
-    const float2* __restrict__ py = sy + (j0 - j_begin);
-    uint32_t cand = 0u;
-    if (!thr_nonneg) {
-      cand = jn == 32 ? 0xffffffffu : ((1u << jn) - 1u);
-    } else if (jn == 32) {
-#pragma unroll
-      for (int b = 0; b < 32; ++b) {
-        const float2 xj = px[b];
-        cand |= (xj.y <= bi.x || bi.z <= xj.x) ? 0u : (1u << b);
-      }
-    } else {
-      for (int b = 0; b < jn; ++b) {
-        const float2 xj = px[b];
-        cand |= (xj.y <= bi.x || bi.z <= xj.x) ? 0u : (1u << b);
-      }
-    }
-    if (!valid) continue;
-    uint32_t bits = 0u;
-    while (cand) {
-      const int b = __ffs((int)cand) - 1;
-      cand &= cand - 1u;
-      const int j = j0 + b;
-      const float2 xj = px[b], yj = py[b];
-      if (thr_nonneg && (yj.y <= bi.y || bi.w <= yj.x)) continue;  // disjoint: IoU 0
-      if (j == i || (aware && ci != (int)scls[j - j_begin])) continue;
-      const float4 bj = make_float4(xj.x, yj.x, xj.y, yj.y);
-      // (i, j) in the order the greedy loop meets them: the earlier box first
-      const bool hit = ultra ? (j > i ? suppresses_tv(bi, bj, p.iou_thr64) : suppresses_tv(bj, bi, p.iou_thr64))
-                             : (j > i ? suppresses(bi, bj, thr) : suppresses(bj, bi, thr));
-      bits |= (uint32_t)hit << b;
-    }
-    mask[(size_t)w * D.cap + i] = bits;
-  }
-}
-
-// Rows c0 .. c0 + 63 of the bit matrix, words 2 ch .. words - 1, into a shared-memory stage: 256 bytes per word.
-__device__ __forceinline__ void sweep_stage_rows(uint32_t* stage, const uint32_t* __restrict__ mask, int cap, int ch, int words) {
-  const int c0 = ch << 6, nw = words - 2 * ch;
-  for (int t = threadIdx.x; t < nw * 16; t += kSweepThreads) {
-    const int w = t >> 4, part = t & 15;
-    cp_async16(stage + w * 64 + part * 4, mask + (size_t)(2 * ch + w) * cap + c0 + part * 4);
-  }
-  cp_async_commit();
-}
-
-__global__ void __launch_bounds__(kSweepThreads) k_dense_sweep(const __grid_constant__ NmsParams p, const DenseNms D) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  griddep_launch_dependents();  // a tracker kernel behind this one may be scheduled; its griddep_wait() waits for this grid
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, frame = blockIdx.x;
-  const int n = D.n[frame];
   if (n == 0) {
     if (tid == 0) p.out_count[frame] = 0;
     return;
   }
-  const int cap = D.cap;
-  uint32_t* stage0 = reinterpret_cast<uint32_t*>(smem_raw);  // two stages of [cap / 32][64] words
-  uint32_t* stage1 = stage0 + (cap / 32) * 64;
-  uint32_t* supp = stage1 + (cap / 32) * 64;                // [cap / 32]
-  uint32_t* keep_w = supp + cap / 32;                       // [cap / 32] what is emitted
-  int* keep_off = reinterpret_cast<int*>(keep_w + cap / 32);  // [cap / 64 + 1]
-  __shared__ unsigned long long s_kept;
-  __shared__ uint8_t s_klist[64];
-  const size_t dbase = (size_t)frame * cap;
-  const uint32_t* __restrict__ mask = D.mask + (size_t)frame * (cap / 32) * cap;
-  const int words = (n + 31) >> 5, nchunks = (n + 63) >> 6;
-  for (int w = tid; w < words; w += kSweepThreads) supp[w] = 0u;
-  // The rows of a chunk are staged one chunk ahead with cp.async (the whole upper triangle passes through shared memory
-  // once, 256 contiguous bytes per word), so neither the resolution nor the spreading of the kept rows waits for L2.
-  sweep_stage_rows(stage0, mask, cap, 0, words);
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const int c0 = ch << 6, m = min(64, n - c0);
-    uint32_t* const st = (ch & 1) ? stage1 : stage0;
-    if (ch + 1 < nchunks) {
-      sweep_stage_rows((ch & 1) ? stage0 : stage1, mask, cap, ch + 1, words);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();
-    const bool two = 2 * ch + 1 < words;
-    if (warp == 0) {
-      const unsigned long long e0 = (((unsigned long long)(two ? st[64 + lane] : 0u) << 32) | st[lane]) & ((1ull << lane) - 1ull);
-      const unsigned long long e1 =
-          (((unsigned long long)(two ? st[64 + lane + 32] : 0u) << 32) | st[lane + 32]) & ((1ull << (lane + 32)) - 1ull);
-      const unsigned long long valid = m == 64 ? ~0ull : ((1ull << m) - 1ull);
-      const unsigned long long alive = ~(((unsigned long long)(two ? supp[2 * ch + 1] : 0u) << 32) | supp[2 * ch]) & valid;
-      const bool a0 = (alive >> lane) & 1ull, a1 = (alive >> (lane + 32)) & 1ull;
-      bool k0 = a0, k1 = a1;
-      unsigned long long kept;
-      while (true) {
-        kept = ((unsigned long long)__ballot_sync(0xffffffffu, k1) << 32) | __ballot_sync(0xffffffffu, k0);
-        const bool n0 = a0 && !(e0 & kept), n1 = a1 && !(e1 & kept);
-        const unsigned changed = __ballot_sync(0xffffffffu, n0 != k0 || n1 != k1);
-        k0 = n0;
-        k1 = n1;
-        if (!changed) break;
-      }
-      if (k0) s_klist[__popcll(kept & ((1ull << lane) - 1ull))] = (uint8_t)lane;
-      if (k1) s_klist[__popcll(kept & ((1ull << (lane + 32)) - 1ull))] = (uint8_t)(lane + 32);
-      if (lane == 0) {
-        s_kept = kept;
-        keep_w[2 * ch] = (uint32_t)kept;
-        if (two) keep_w[2 * ch + 1] = (uint32_t)(kept >> 32);
-      }
-    }
-    __syncthreads();
-    {
-      // the kept rows of this chunk mark the boxes of the later chunks: (word, eighth of the kept rows) per thread
-      const int nk = __popcll(s_kept);
-      const int later = words - (2 * ch + 2);
-      const int t = tid >> 3, part = tid & 7;
-      for (int wl = t; wl < later; wl += kSweepThreads / 8) {
-        const uint32_t* __restrict__ row = st + (2 + wl) * 64;
-        uint32_t acc = 0u;
-        for (int q = part; q < nk; q += 8) acc |= row[s_klist[q]];
-        if (acc) atomicOr(&supp[2 * ch + 2 + wl], acc);
-      }
-    }
-    __syncthreads();
+  PHASE_STAMP(p.dbg, 37);
+  if (fall_back) {
+    nms_general<true, kResolveThreads>(p, frame, smem_raw, n);
+    return;
   }
-  const bool ultra = p.ultra != 0;
-  // ultralytics: `i = i[:max_det]` on the NMS survivors, before anything else looks at them
-  if (ultra) {
-    if (tid == 0) {
-      int acc = 0;
-      for (int w = 0; w < words; ++w) {
-        uint32_t bits = keep_w[w];
-        const int room = p.max_det_cap - acc;
-        if (room <= 0) {
-          bits = 0u;
-        } else if (__popc(bits) > room) {
-          uint32_t kept_bits = 0u;
-          for (int r = 0; r < room; ++r) {  // keep the `room` lowest set bits
-            const uint32_t low = bits & (0u - bits);
-            kept_bits |= low;
-            bits ^= low;
-          }
-          bits = kept_bits;
+  // kept_i = no kept suppressor, iterated from "only the unsuppressible boxes are kept" until nothing changes
+  uint8_t *old = kept_a, *nw = kept_b;
+  bool converged = false;
+  for (int round = 0; round < kResolveRounds; ++round) {
+    int changed = 0;
+#pragma unroll
+    for (int q = 0; q < kResolveRows; ++q) {
+      if (cnt[q] > 0) {
+        const int r = tid + q * kResolveThreads;
+        const uint32_t w[4] = {nb[q].x, nb[q].y, nb[q].z, nb[q].w};
+        bool k = true;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (s < cnt[q]) k = k && !old[(w[s >> 1] >> (16 * (s & 1))) & 0xffffu];
+        if (k && cnt[q] > 8) {
+          const uint16_t* __restrict__ more = D.nbr + (fbase + r) * kNbrCap;
+          for (int s = 8; s < cnt[q]; ++s)
+            if (old[more[s]]) {
+              k = false;
+              break;
+            }
         }
-        keep_w[w] = bits;
-        acc += __popc(bits);
+        changed |= (int)(k != (old[r] != 0));
+        nw[r] = k;
       }
     }
-    __syncthreads();
-  }
-  // filter_detections (detector.py:99-103): float64 compare on the kept boxes only
-  if (p.use_filter) {
-    for (int i = tid; i < n; i += kSweepThreads) {
-      if ((keep_w[i >> 5] >> (i & 31)) & 1u) {
-        const float conf = unorder_bits((uint32_t)(D.keys[dbase + i] >> 32));
-        if (!((double)conf >= p.filter_thr)) atomicAnd(&keep_w[i >> 5], ~(1u << (i & 31)));
-      }
+    uint8_t* t = old;
+    old = nw;
+    nw = t;
+    if (!__syncthreads_or(changed)) {
+      converged = true;
+      break;
     }
-    __syncthreads();
   }
-  if (tid == 0) {
-    int acc = 0;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      keep_off[ch] = acc;
-      acc += __popc(keep_w[2 * ch]) + (2 * ch + 1 < words ? __popc(keep_w[2 * ch + 1]) : 0);
-    }
-    p.out_count[frame] = min(acc, p.max_dets);
-    if (acc > p.max_dets) atomicOr(p.flags + FLAG_DET_OVERFLOW, 1);
+  if (!converged) {  // a suppression chain deeper than kResolveRounds: let the sequential path walk it
+    nms_general<true, kResolveThreads>(p, frame, smem_raw, n);
+    return;
+  }
+  PHASE_STAMP(p.dbg, 38);
+  // the kept keys, in no particular order
+#pragma unroll
+  for (int q = 0; q < kResolveRows; ++q) {
+    const int r = tid + q * kResolveThreads;
+    const bool k = r < n && old[r];
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    int base = 0;
+    if (lane == 0 && bal) base = atomicAdd(&s_m, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (k) kkeys[base + __popc(bal & ((1u << lane) - 1u))] = key[q];
   }
   __syncthreads();
-  const size_t cbase = (size_t)frame * p.max_cand;
-  for (int i = tid; i < n; i += kSweepThreads) {
-    const int wi = i >> 5;
-    if (!((keep_w[wi] >> (i & 31)) & 1u)) continue;
-    const uint32_t lo = keep_w[wi & ~1], hi = (wi | 1) < words ? keep_w[wi | 1] : 0u;
-    const unsigned long long w = ((unsigned long long)hi << 32) | lo;
-    const int pos = keep_off[i >> 6] + __popcll(w & ((1ull << (i & 63)) - 1ull));
-    if (pos >= p.max_dets) continue;
-    const size_t o = (size_t)frame * p.max_dets + pos;
-    const unsigned long long k = D.keys[dbase + i];
+  PHASE_STAMP(p.dbg, 39);
+  const int m = s_m;
+  const bool ultra = p.ultra != 0;
+  // output position = rank among the kept keys.  ultralytics: `i = i[:max_det]` on the NMS survivors, before anything
+  // else looks at them; filter_detections (detector.py:99-103): float64 compare on the kept boxes only (a threshold on
+  // the score the keys are ordered by, so the boxes that pass are a prefix and their ranks do not move)
+  auto emit = [&](const unsigned long long k, const int pos) {
+    if (ultra && pos >= p.max_det_cap) return;
+    const float conf = unorder_bits((uint32_t)(k >> 32));
+    if (p.use_filter && !((double)conf >= p.filter_thr)) return;
+    atomicAdd(&s_out, 1);
+    if (pos >= p.max_dets) return;
     const int slot = (int)(k & 0x3fffull);
-    float4 b = D.box[dbase + i];
-    if (ultra) b = ultra_scale_box(p.cand_box[cbase + slot], p.f[frame]);  // the un-shifted box
+    const size_t o = (size_t)frame * p.max_dets + pos;
+    float4 b = p.cand_box[cbase + slot];
+    if (ultra) b = ultra_scale_box(b, p.f[frame]);
     reinterpret_cast<float4*>(p.out_box)[o] = b;
-    p.out_conf[o] = unorder_bits((uint32_t)(k >> 32));
-    p.out_cls[o] = p.cand_cls[cbase + slot];  // the full int32 class id
+    p.out_conf[o] = conf;
+    p.out_cls[o] = p.cand_cls[cbase + slot];
+  };
+  if (m <= kRankMax) {
+    // eight lanes share four kept keys (registers) and split the scan of all kept keys between them: a 64-bit
+    // shared-memory load feeds four compares (one compare per load is bound by the shared-memory pipe)
+    static_assert(kRankMax == 4 * (kResolveThreads / 8), "four keys per group of eight lanes cover kRankMax");
+    const int g = tid >> 3, part = tid & 7;
+    unsigned long long ke[4];
+    int ahead[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ke[k] = g + k * (kResolveThreads / 8) < m ? kkeys[g + k * (kResolveThreads / 8)] : ~0ull;
+    for (int t = part; t < m; t += 8) {
+      const unsigned long long kt = kkeys[t];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ahead[k] += kt > ke[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      ahead[k] += __shfl_xor_sync(0xffffffffu, ahead[k], 1);
+      ahead[k] += __shfl_xor_sync(0xffffffffu, ahead[k], 2);
+      ahead[k] += __shfl_xor_sync(0xffffffffu, ahead[k], 4);
+    }
+    // (lane k of a group emits key k: the stores of a warp spread over its lanes)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (part == k && g + k * (kResolveThreads / 8) < m) emit(ke[k], ahead[k]);
+  } else {
+    int np2 = 64;
+    while (np2 < m) np2 <<= 1;
+    for (int t = m + tid; t < np2; t += kResolveThreads) kkeys[t] = 0ull;
+    __syncthreads();
+    block_bitonic_sort_desc<kResolveThreads>(kkeys, np2);
+    for (int t = tid; t < m; t += kResolveThreads) emit(kkeys[t], t);
+  }
+  __syncthreads();
+  PHASE_STAMP(p.dbg, 48);
+  if (tid == 0) {
+    p.out_count[frame] = min(s_out, p.max_dets);
+    if (s_out > p.max_dets) atomicOr(p.flags + FLAG_DET_OVERFLOW, 1);
   }
 }
-
-static size_t dense_sweep_smem(int cap) { return (size_t)cap * 16 + (size_t)(cap / 32) * 8 + (cap / 64 + 1) * 4; }
 
 static int next_pow2(int v) {
   int p = 64;
@@ -1770,6 +1938,14 @@ size_t nms_smem_bytes(int max_cand) {
   const size_t cap = (size_t)next_pow2(max_cand);
   return nms_base_bytes(max_cand) + (nms_grid_offset(max_cand) ? sizeof(NmsGrid) + cap / 8 + cap * 2 : 0);
 }
+static size_t dense_resolve_smem(int max_cand) {
+  int np2 = 64;
+  while (np2 < max_cand) np2 <<= 1;
+  const size_t own = 2 * (((size_t)max_cand + 15) & ~(size_t)15) + (size_t)np2 * 8;
+  return std::max(own, nms_smem_bytes(max_cand));
+}
+
+
 
 static const int kRingSmemMax = 96 * 1024;
 
@@ -1892,22 +2068,20 @@ int postprocess_configure(b200va_ctx* h) {
   }
   CUDA_TRY(h, raise_dyn_smem(k_sort_nms<false>, smem));
   CUDA_TRY(h, raise_dyn_smem(k_sort_nms<true>, smem));
-  // dense-scene path (k_dense_sort / _mask / _sweep): scratch for the sorted candidates and the bit matrix
-  const int cap = next_pow2(h->cfg.max_candidates);
-  if (cap <= kDenseCapMax && h->tune.dense_impl != 1) {
+  // dense-scene path (k_dense_pairs / k_dense_resolve): suppressor lists of every candidate
+  if (h->cfg.max_candidates <= kDenseCandMax && h->tune.dense_impl != 1) {
     DenseNms* D = new DenseNms();
     memset(D, 0, sizeof(*D));
     h->dense_nms = D;
-    D->cap = cap;
-    const size_t frames = (size_t)h->cand_set_frames;
-    CUDA_TRY(h, cudaMalloc(&D->keys, frames * cap * sizeof(unsigned long long)));
-    CUDA_TRY(h, cudaMalloc(&D->box, frames * cap * sizeof(float4)));
-    CUDA_TRY(h, cudaMalloc(&D->cls, frames * cap * sizeof(uint16_t)));
-    CUDA_TRY(h, cudaMalloc(&D->n, frames * sizeof(int32_t)));
-    CUDA_TRY(h, cudaMalloc(&D->mask, frames * (size_t)(cap / 32) * cap * sizeof(uint32_t)));
-    CUDA_TRY(h, cudaMemset(D->n, 0, frames * sizeof(int32_t)));
-    CUDA_TRY(h, raise_dyn_smem(k_dense_sort, (size_t)cap * 8));
-    CUDA_TRY(h, raise_dyn_smem(k_dense_sweep, dense_sweep_smem(cap)));
+    D->max_cand = h->cfg.max_candidates;
+    D->ctas = h->num_sms * (h->tune.dense_ctas_per_sm > 0 ? h->tune.dense_ctas_per_sm : 8);
+    const size_t rows = (size_t)h->cand_set_frames * D->max_cand;
+    CUDA_TRY(h, cudaMalloc(&D->nbr_cnt, rows * sizeof(int32_t)));
+    CUDA_TRY(h, cudaMalloc(&D->nbr, rows * kNbrCap * sizeof(uint16_t)));
+    CUDA_TRY(h, cudaMemset(D->nbr_cnt, 0, rows * sizeof(int32_t)));
+    CUDA_TRY(h, cudaMalloc(&D->work, sizeof(int32_t)));
+    CUDA_TRY(h, cudaMemset(D->work, 0, sizeof(int32_t)));
+    CUDA_TRY(h, raise_dyn_smem(k_dense_resolve, dense_resolve_smem(D->max_cand)));
   }
   return B200VA_OK;
 }
@@ -2123,6 +2297,7 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
       dense = h->nms_dense_ttl > 0;
       if (dense && cap == cudaStreamCaptureStatusNone) --h->nms_dense_ttl;
     }
+    if (h->tune.dense_impl == 2 && h->dense_nms) dense = true;  // tests: every launch takes the dense-scene kernels
     if (defer) {
       // stash the chain: the next b200va_tick launches it beside its own decode and letterbox
       PendingChain* pc = (PendingChain*)h->pending_chain;
@@ -2174,10 +2349,9 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
       fuse->done = true;
     } else if (dense && h->dense_nms) {
       const DenseNms& D = *(const DenseNms*)h->dense_nms;
-      CUDA_TRY(h, launch_pdl(k_dense_sort, dim3(n), dim3(kNmsThreads), (size_t)D.cap * 8, st, pdl, q, D));
-      k_dense_mask<<<dim3(D.cap / kDenseCols, D.cap / kDenseRows, n), kDenseRows, 0, st>>>(q, D);
-      k_dense_sweep<<<n, kSweepThreads, dense_sweep_smem(D.cap), st>>>(q, D);
-      h->launches.fetch_add(2, std::memory_order_relaxed);
+      CUDA_TRY(h, launch_pdl(k_dense_pairs, dim3(D.ctas), dim3(kPairThreads), 0, st, pdl, q, D, n));
+      CUDA_TRY(h, launch_pdl(k_dense_resolve, dim3(n), dim3(kResolveThreads), dense_resolve_smem(D.max_cand), st, h->tune.pdl != 0, q, D));
+      h->launches.fetch_add(1, std::memory_order_relaxed);
     } else if (dense && q.grid_off) {
       CUDA_TRY(h, launch_pdl(k_sort_nms<true>, dim3(n), dim3(kNmsThreads), nms_smem, st, pdl, q));
     } else {
@@ -2225,6 +2399,7 @@ int postprocess_run_pending(b200va_handle h, void* stream) {
     dense = h->nms_dense_ttl > 0;
     if (dense && cap == cudaStreamCaptureStatusNone) --h->nms_dense_ttl;
   }
+  if (h->tune.dense_impl == 2 && h->dense_nms) dense = true;
   const size_t nms_smem = nms_smem_bytes(h->cfg.max_candidates);
   const bool fusable = pc->has_trk && !dense && h->tune.fuse_post_track != 0 && pc->t.max_dets == h->cfg.max_dets;
   const int trk_rows = fusable ? tracker_pick_smem_tracks(h, st) : 0;
@@ -2241,10 +2416,9 @@ int postprocess_run_pending(b200va_handle h, void* stream) {
     }
     if (dense && h->dense_nms) {
       const DenseNms& D = *(const DenseNms*)h->dense_nms;
-      CUDA_TRY(h, launch_pdl(k_dense_sort, dim3(n), dim3(kNmsThreads), (size_t)D.cap * 8, st, false, pc->q, D));
-      k_dense_mask<<<dim3(D.cap / kDenseCols, D.cap / kDenseRows, n), kDenseRows, 0, st>>>(pc->q, D);
-      k_dense_sweep<<<n, kSweepThreads, dense_sweep_smem(D.cap), st>>>(pc->q, D);
-      h->launches.fetch_add(2, std::memory_order_relaxed);
+      CUDA_TRY(h, launch_pdl(k_dense_pairs, dim3(D.ctas), dim3(kPairThreads), 0, st, false, pc->q, D, n));
+      CUDA_TRY(h, launch_pdl(k_dense_resolve, dim3(n), dim3(kResolveThreads), dense_resolve_smem(D.max_cand), st, h->tune.pdl != 0, pc->q, D));
+      h->launches.fetch_add(1, std::memory_order_relaxed);
     } else if (dense && pc->q.grid_off) CUDA_TRY(h, launch_pdl(k_sort_nms<true>, dim3(n), dim3(kNmsThreads), nms_smem, st, false, pc->q));
     else CUDA_TRY(h, launch_pdl(k_sort_nms<false>, dim3(n), dim3(kNmsThreads), nms_plain, st, false, pc->q));
     LAUNCH_CHECK(h);
@@ -2262,11 +2436,9 @@ void postprocess_release(b200va_ctx* h) {
   delete (PendingChain*)h->pending_chain;
   h->pending_chain = nullptr;
   if (DenseNms* D = (DenseNms*)h->dense_nms) {
-    if (D->keys) cudaFree(D->keys);
-    if (D->box) cudaFree(D->box);
-    if (D->cls) cudaFree(D->cls);
-    if (D->n) cudaFree(D->n);
-    if (D->mask) cudaFree(D->mask);
+    if (D->nbr_cnt) cudaFree(D->nbr_cnt);
+    if (D->nbr) cudaFree(D->nbr);
+    if (D->work) cudaFree(D->work);
     delete D;
     h->dense_nms = nullptr;
   }

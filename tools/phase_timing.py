@@ -29,6 +29,7 @@ print("nms phases: count+keys %d, sort %d, gather %d, chunks %d, filter+emit %d"
 print("nms chunk loop split: (q) grid query (warp 0) %d, (a) pair matrix %d, (b) resolve %d, (c) tail / insert %d" % (v[27], v[24], v[25], v[26]))
 print("grid query split (accumulated over launches, thread 0): setup %d, cells %d, overflow %d, pass2 %d" % (v[32], v[33], v[34], v[35]))
 print("grid: max entries per cell %d, overflow list %d, total entries %d" % (v[28], v[29], v[30]))
+print("dense resolve (SM cycles, frame 0): loads+lists %d, Jacobi rounds %d, compaction %d, rank+emit %d" % (v[37] - v[36], v[38] - v[37], v[39] - v[38], v[48] - v[39]))
 print("dets per frame", dets["count"].cpu().tolist()[:8], "tracks", tracks["count"].cpu().tolist()[:8])
 
 # hypothesis check: does a low-occupancy grid (32 CTAs) run slower per instruction than when the rest of the chip is busy?

@@ -1,4 +1,6 @@
-python -m pytest tests -m gpu -x -q -k "not config4" > gpurun_out/post_test.log 2>&1; tail -2 gpurun_out/post_test.log
-echo new; python tools/bench_configs.py --only 5 2>&1 | tail -1 | cut -c1-200
-echo old; B200VA_DENSE_IMPL=1 python tools/bench_configs.py --only 5 2>&1 | tail -1 | cut -c1-200
-ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:k_dense -c 3 --csv python tools/bench_configs.py --only 5 --steps 3 2>/dev/null | grep -E "k_dense" | cut -d, -f5,15-
+python -m pytest tests/test_gpu_dense_nms.py -x -q > gpurun_out/dense_test.log 2>&1; tail -3 gpurun_out/dense_test.log
+python -m pytest tests -m gpu -x -q -k "not config4 and not dense_nms" > gpurun_out/post_test.log 2>&1; tail -2 gpurun_out/post_test.log
+echo cols64; python tools/bench_configs.py --only 5 2>&1 | tail -1 | cut -c1-130
+echo cols128; B200VA_LIB=$PWD/realtime_video_analytics_32streams_b200/lib/libb200va_A.so python tools/bench_configs.py --only 5 2>&1 | tail -1 | cut -c1-130
+echo cols128 ctas6; B200VA_DENSE_CTAS=6 B200VA_LIB=$PWD/realtime_video_analytics_32streams_b200/lib/libb200va_A.so python tools/bench_configs.py --only 5 2>&1 | tail -1 | cut -c1-130
+B200VA_LIB=$PWD/realtime_video_analytics_32streams_b200/lib/libb200va_A.so python -m pytest tests/test_gpu_dense_nms.py -x -q 2>&1 | tail -1
