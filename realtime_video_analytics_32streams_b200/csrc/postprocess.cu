@@ -1475,7 +1475,7 @@ __global__ void __launch_bounds__(kNmsThreadsSmall) k_post_track(const __grid_co
   constexpr int kTabOff = (int)((sizeof(SmallNms) + 127) & ~(size_t)127);
   unsigned dyn_bytes;
   asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
-  const int staged_cap = ((int)dyn_bytes - kTabOff - kDetChunk * 4 - 16) / 46;  // rows (see tracker_smem_bytes)
+  const int staged_cap = (((int)dyn_bytes - kTabOff - kDetChunk * 4 - 32) / kTrkRowBytes) & ~7;  // rows (see tracker_smem_bytes)
   const bool stage_early = pre_T0 <= staged_cap - kDetChunk && pre_T0 <= kNmsThreadsSmall;
   TablePrefetch pf{0, 0, 0.0};
   if (stage_early) pf = stage_table(t, trk_slot, pre_cur, pre_T0, smem_raw + kTabOff, staged_cap, kNmsThreadsSmall);
@@ -2054,7 +2054,7 @@ int postprocess_configure(b200va_ctx* h) {
   const size_t smem = nms_smem_bytes(h->cfg.max_candidates);
   if (smem > 220 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_candidates %d needs %zu bytes of shared memory", h->cfg.max_candidates, smem);
   {
-    const size_t fused = std::min<size_t>(200 * 1024, std::max(smem, tracker_smem_bytes(h->cfg.max_tracks)));
+    const size_t fused = std::min<size_t>(200 * 1024, std::max(smem, tracker_smem_bytes(std::min(h->cfg.max_tracks, kTrkSmemRowsMax))));
     CUDA_TRY(h, raise_dyn_smem(k_post_track<false>, fused));
     CUDA_TRY(h, raise_dyn_smem(k_post_track<true>, fused));
     // k_post_track runs beside the letterbox in b200va_tick, and an SM only hosts kernels that agree on its L1 /

@@ -79,8 +79,8 @@ int tracker_state_create(b200va_ctx* h) {
   S->scratch_stride = scratch_stride;
   const long long one = 1;  // itertools.count(1), tracker.py:47
   CUDA_TRY(h, cudaMemcpy(S->next_id, &one, 8, cudaMemcpyHostToDevice));
-  const size_t smem = tracker_smem_bytes(h->cfg.max_tracks);
-  if (smem > 190 * 1024) return set_error(h, B200VA_ERR_INVALID, "max_tracks %d too large (<= 4096)", h->cfg.max_tracks);
+  if (h->cfg.max_tracks > 4096) return set_error(h, B200VA_ERR_INVALID, "max_tracks %d too large (<= 4096)", h->cfg.max_tracks);
+  const size_t smem = tracker_smem_bytes(std::min(h->cfg.max_tracks, kTrkSmemRowsMax));
   CUDA_TRY(h, raise_dyn_smem(k_tracker, smem));
   if (h->tune.uniform_carveout) CUDA_TRY(h, prefer_max_shared(k_tracker));
   return B200VA_OK;
@@ -144,7 +144,7 @@ int tracker_fill_params(b200va_ctx* h, TrkParams& p, const int* stream_slots, in
 // up to 1024 / 2048 / max_tracks, for the next 64 launches.  A stream that still does not fit runs from its global
 // scratch -- the choice only moves time, never results.  Under stream capture the size is frozen into the graph.
 int tracker_pick_smem_tracks(b200va_ctx* h, cudaStream_t st) {
-  const int cap = h->cfg.max_tracks;
+  const int cap = std::min(h->cfg.max_tracks, kTrkSmemRowsMax);  // (a stream that needs more rows works in the global scratch)
   if (h->tune.trk_smem_tracks > 0) return std::min(cap, h->tune.trk_smem_tracks);  // B200VA_TRK_SMEM_TRACKS (tests)
   if (h->nms_stats_host) {
     cudaStreamCaptureStatus capt = cudaStreamCaptureStatusNone;

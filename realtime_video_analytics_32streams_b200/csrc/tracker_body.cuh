@@ -1,6 +1,7 @@
 // The per-stream body of the IoU tracker (tracker.py:50-126 restated for one CTA), shared by k_tracker (tracker.cu)
 // and the fused post-process + tracker kernel (postprocess.cu).  See tracker.cu for the algorithm notes.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 struct TrackerState {
@@ -53,7 +54,7 @@ struct TrkParams {
   int o_rows;  // rows per stream of the output arrays
   int32_t* flags;
   long long* dbg;
-  // The working table (boxes, classes, hits, claims, last detection: 46 bytes per track) of a stream lives in shared
+  // The working table (boxes, classes, hits, claims, last detection, overlap keys: 62 bytes per track) of a stream lives in shared
   // memory when `live tracks + detections <= smem_tracks`, in the stream's global scratch otherwise (same code, exact,
   // slower).  The launch sizes its dynamic shared memory for smem_tracks, not for max_tracks: a CTA that asks for
   // 188 KB closes its SM to the letterbox CTAs it runs beside in b200va_tick (measured: 32 x 1080p letterbox 36 us
@@ -130,6 +131,17 @@ __device__ __forceinline__ bool may_overlap(const double4 a, const double4 b) {
   return (az >= bx) & (bz >= ax) & (az >= ax) & (bz >= bx) & (aw >= by) & (bw >= ay) & (aw >= ay) & (bw >= by);
 }
 
+// Row bytes of a stream's working table: box 32, class 4, hits 4, claims 4, last detection 2, overlap keys 16.
+constexpr int kTrkRowBytes = 62;
+// The overlap keys of a row: hi_key of (x1, y1, x2, y2), 16 bytes.  Phase A of a dense stream tests every (detection,
+// track) pair; reading the track's four doubles for that costs 8 shared-memory wavefronts per warp step (32-byte lane
+// stride) and eight float64 compares, the keys cost 4 wavefronts and four integer compares -- and only a pair that
+// passes them (a superset of the overlapping ones, see may_overlap) looks at the doubles.
+__device__ __forceinline__ uint4 box_keys(const double4 b) { return make_uint4(hi_key(b.x), hi_key(b.y), hi_key(b.z), hi_key(b.w)); }
+__device__ __forceinline__ uint4* trk_key_table(uint8_t* tab, int cap) {
+  return reinterpret_cast<uint4*>(tab + (((size_t)cap * 46 + kDetChunk * 4 + 15) & ~(size_t)15));
+}
+
 __device__ __forceinline__ bool overlaps(const double4 a, const double4 b) {
   return (a.z > b.x) & (b.z > a.x) & (a.z > a.x) & (b.z > b.x) & (a.w > b.y) & (b.w > a.y) & (a.w > a.y) & (b.w > b.y);
 }
@@ -191,6 +203,7 @@ struct TrkShared {
   int s_T, s_new, s_is_last, s_fallback, s_nconf;
   int n_plist;      // phase A, few pairs: number of listed (overlapping, same class) pairs
   uint32_t plist[kTrkPairs];  // idx | detection << 16 | (vs track) << 31
+  uint4 dkey[kDetChunk];      // phase A, many pairs: overlap keys of the chunk's detections (box_keys)
   int s_prestaged;  // fused kernel: detections of this frame (count) whose first chunk the NMS half left in `sd`; -1 = none
   int wsum[kTrkThreadsMax / 32];
   int warp_cnt[kTrkThreadsMax / 32];
@@ -202,7 +215,7 @@ struct TrkShared {
 // A crowded chunk (some detection with more than kCand candidates): the plain sequential scan of the live table by
 // one warp, exact (tracker.py:50-109).  Not inlined: rare, and its code would otherwise sit in the middle of the
 // instruction stream every ordinary chunk runs through.
-__device__ __forceinline__ void chunk_fallback_scan_body(const TrkParams& p, TrkShared& sh, double* sbox, int32_t* scls, int32_t* shits,
+__device__ __forceinline__ void chunk_fallback_scan_body(const TrkParams& p, TrkShared& sh, double* sbox, uint4* skey, int32_t* scls, int32_t* shits,
                                                          int16_t* last_det, const int d0, const int nd) {
   DetStage& sd = sh.sd;
   int& s_T = sh.s_T;
@@ -240,6 +253,7 @@ __device__ __forceinline__ void chunk_fallback_scan_body(const TrkParams& p, Trk
             if (t >= 0) {
               last_det[t] = (int16_t)(d0 + i);
               reinterpret_cast<double4*>(sbox)[t] = sd.box[i];
+              skey[t] = box_keys(sd.box[i]);
             }
           }
           __syncwarp();
@@ -247,9 +261,9 @@ __device__ __forceinline__ void chunk_fallback_scan_body(const TrkParams& p, Trk
       }
 }
 
-__device__ __noinline__ void chunk_fallback_scan(const TrkParams& p, TrkShared& sh, double* sbox, int32_t* scls, int32_t* shits,
+__device__ __noinline__ void chunk_fallback_scan(const TrkParams& p, TrkShared& sh, double* sbox, uint4* skey, int32_t* scls, int32_t* shits,
                                                  int16_t* last_det, const int d0, const int nd) {
-  chunk_fallback_scan_body(p, sh, sbox, scls, shits, last_det, d0, nd);
+  chunk_fallback_scan_body(p, sh, sbox, skey, scls, shits, last_det, d0, nd);
 }
 
 // What the prune step needs of a stream's first rows (row = threadIdx.x), fetched while the table is staged: its
@@ -267,6 +281,7 @@ __device__ __forceinline__ TablePrefetch stage_table(const TrkParams& p, const i
   int32_t* scls = reinterpret_cast<int32_t*>(sbox + (size_t)cap * 4);
   int32_t* shits = scls + cap;
   int16_t* last_det = reinterpret_cast<int16_t*>(shits + cap + cap + kDetChunk);
+  uint4* skey = trk_key_table(tab, cap);
   const TrackerState& S = p.st;
   const size_t sb = (size_t)slot * p.max_tracks;
   const int tid = threadIdx.x;
@@ -277,7 +292,9 @@ __device__ __forceinline__ TablePrefetch stage_table(const TrkParams& p, const i
     pf.conf = S.conf[cur][sb + tid];
   }
   for (int t = tid; t < T0; t += nthreads) {
-    reinterpret_cast<double4*>(sbox)[t] = reinterpret_cast<const double4*>(S.box[cur] + sb * 4)[t];
+    const double4 b = reinterpret_cast<const double4*>(S.box[cur] + sb * 4)[t];
+    reinterpret_cast<double4*>(sbox)[t] = b;
+    skey[t] = box_keys(b);
     scls[t] = S.cls[cur][sb + t];
     shits[t] = S.hits[cur][sb + t];
     last_det[t] = -1;
@@ -294,6 +311,7 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
   int32_t* shits = scls + cap;                                             // [cap]
   int32_t* aux = shits + cap;                                              // [cap + kDetChunk] claims, then phase-B state
   int16_t* last_det = reinterpret_cast<int16_t*>(aux + cap + kDetChunk);   // [cap] detection holding the track's box now, -1 untouched
+  uint4* skey = trk_key_table(tab, cap);                                   // [cap] overlap keys of sbox (kept in step with it)
   // one set of statically allocated shared variables for both instantiations (declared by tracker_stream)
   DetStage& sd = sh.sd;
   auto& c_trk = sh.c_trk;
@@ -379,9 +397,32 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
     // ---- phase A: every IoU the chunk can need.  Warp w takes detections w, w+8, ..; lanes take tracks ----
     const int Tc = s_T;
     for (int t = tid; t < Tc + kDetChunk; t += kTrkThreads) aux[t] = 0;  // claims per track
+    if (!SMALL && tid < nd) sh.dkey[tid] = box_keys(sd.box[tid]);
     __syncthreads();
     const int pairs_t = nd * Tc, pairs = pairs_t + nd * nd;
     static_assert(kTrkPairs >= 8 * kTrkThreadsMin, "the pair list must hold every pair of the small path");
+    // one listed pair: the float64 IoU, and the candidate lists / claim counts it feeds
+    auto score = [&](int i, int idx, bool vs_track) {
+      const double4 bx = sd.box[i];
+      const double4 ob = vs_track ? reinterpret_cast<const double4*>(sbox)[idx] : sd.box[idx];
+      const double v = iou64(ob.x, ob.y, ob.z, ob.w, bx.x, bx.y, bx.z, bx.w);
+      if (v >= p.thr && v > 0.0) {
+        if (vs_track) {
+          const int k = atomicAdd(&n_trk[i], 1);
+          if (k < kCand) {
+            c_trk[i][k].iou = v;
+            c_trk[i][k].idx = idx;
+          }
+          atomicAdd(&aux[idx], 1);
+        } else {
+          const int k = atomicAdd(&n_det[i], 1);
+          if (k < kCand) {
+            c_det[i][k].iou = v;
+            c_det[i][k].idx = idx;
+          }
+        }
+      }
+    };
     if (SMALL || pairs <= min(kTrkPairs, 8 * kTrkThreads)) {
       // Few pairs.  The CTA is latency-bound: a warp in which ONE lane meets an overlapping pair walks all 32 lanes
       // through the float64 IoU (a dependent chain of ~170 instructions), and the warp that owns a detection does
@@ -389,27 +430,6 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
       // (detection, earlier detection) pairs over the threads and only lists those of equal class whose boxes overlap;
       // pass 2 evaluates one listed pair per thread, lanes converged (25 x 25: 5.6 k -> ~1.6 k SM cycles).  The
       // candidate lists come out in a different order, which nothing downstream depends on (arg-max with index ties).
-      auto score = [&](int i, int idx, bool vs_track) {
-        const double4 bx = sd.box[i];
-        const double4 ob = vs_track ? reinterpret_cast<const double4*>(sbox)[idx] : sd.box[idx];
-        const double v = iou64(ob.x, ob.y, ob.z, ob.w, bx.x, bx.y, bx.z, bx.w);
-        if (v >= p.thr && v > 0.0) {
-          if (vs_track) {
-            const int k = atomicAdd(&n_trk[i], 1);
-            if (k < kCand) {
-              c_trk[i][k].iou = v;
-              c_trk[i][k].idx = idx;
-            }
-            atomicAdd(&aux[idx], 1);
-          } else {
-            const int k = atomicAdd(&n_det[i], 1);
-            if (k < kCand) {
-              c_det[i][k].iou = v;
-              c_det[i][k].idx = idx;
-            }
-          }
-        }
-      };
       PHASE_STAMP(p.dbg, 58);
       const float inv_T = 1.0f / (float)max(Tc, 1), inv_n = 1.0f / (float)nd;
       // which of this thread's pairs q = tid + it * kTrkThreads are listed (at most 8 rounds: pairs <= 8 * kTrkThreads)
@@ -468,37 +488,108 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
         score((int)((e >> 16) & 0x7fffu), (int)(e & 0xffffu), (e >> 31) != 0u);
       }
       PHASE_STAMP(p.dbg, 61);
-    } else
-    for (int i = warp; i < nd; i += kTrkThreads / 32) {
-      const double4 bx = sd.box[i];
-      const int dcls = sd.cls[i];
-      for (int t = lane; t < Tc; t += 32) {
-        if (scls[t] != dcls) continue;
-        const double4 tb = reinterpret_cast<const double4*>(sbox)[t];
-        if (!overlaps(tb, bx)) continue;
-        const double v = iou64(tb.x, tb.y, tb.z, tb.w, bx.x, bx.y, bx.z, bx.w);
-        if (v >= p.thr && v > 0.0) {
-          const int k = atomicAdd(&n_trk[i], 1);
-          if (k < kCand) {
-            c_trk[i][k].iou = v;
-            c_trk[i][k].idx = t;
-          }
-          atomicAdd(&aux[t], 1);
+    } else {
+      // Many pairs (a dense stream).  Pass 1: warp w scans detections w, w + warps, ..: lanes over the tracks (integer
+      // overlap keys first, see box_keys) and over the earlier detections of the chunk; a pair of equal class whose
+      // boxes overlap is LISTED, not evaluated -- the float64 IoU is a dependent chain of ~170 instructions, and a warp
+      // that meets such pairs in different steps of its scan would walk through it once per step.  Pass 2: one listed
+      // pair per thread, all of them in flight together.  (Pairs past the end of the list are evaluated on the spot.)
+      auto list_pair = [&](int i, int idx, bool vs_track) {
+        const int slot = atomicAdd(&sh.n_plist, 1);
+        if (slot < kTrkPairs) sh.plist[slot] = (uint32_t)idx | ((uint32_t)i << 16) | (vs_track ? 0x80000000u : 0u);
+        else score(i, idx, vs_track);
+      };
+      PHASE_STAMP(p.dbg, 58);
+      // A unit of pass 1 = 64 rows (lane l owns rows l and l + 32 of the block: keys and class in registers) x one
+      // group of the chunk's detections, whose keys are broadcast from shared memory one by one (a 16-byte broadcast
+      // occupies the shared-memory pipe for four cycles whatever the lanes do with it, hence two rows per lane).  The
+      // rows are the live tracks followed by the chunk's own detections (row e of that block pairs with the later
+      // detections i > e only).  The CTA is issue-bound on its one SM: a (row, detection) visit costs ~8 instructions
+      // this way (ALU pipe, two cycles each), ~25 as a scan of the tracks per detection.
+      const int nblk_t = (Tc + 63) >> 6, nblk = nblk_t + 1;
+      const int G = nblk >= 16 ? 2 : (nblk >= 8 ? 4 : 8);  // detection groups: enough units for every warp
+      // (the group size is a compile-time constant of the unit: the loop over its detections is unrolled, the bit a
+      // visit sets is an immediate, and the five compares of a visit chain into one predicate)
+      auto unit = [&](auto gs_c, const int u) {
+        constexpr int GS = decltype(gs_c)::value;
+        constexpr int kGroups = kDetChunk / GS;
+        const int blk = u / kGroups, i0 = (u - blk * kGroups) * GS, i1 = min(nd, i0 + GS);
+        if (i0 >= i1) return;
+        const bool vs_track = blk < nblk_t;
+        const int r0 = (vs_track ? blk * 64 : 0) + lane, r1 = r0 + 32;
+        const int rows = vs_track ? Tc : nd;
+        // (a row past the end gets keys no box can meet)
+        uint4 k0 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u), k1 = k0;
+        int c0 = 0, c1 = 0;
+        if (r0 < rows) {
+          k0 = vs_track ? skey[r0] : sh.dkey[r0];
+          c0 = vs_track ? scls[r0] : sd.cls[r0];
         }
-      }
-      for (int e = lane; e < i; e += 32) {
-        if (sd.cls[e] != dcls) continue;
-        const double4 eb = sd.box[e];
-        if (!overlaps(eb, bx)) continue;
-        const double v = iou64(eb.x, eb.y, eb.z, eb.w, bx.x, bx.y, bx.z, bx.w);
-        if (v >= p.thr && v > 0.0) {
-          const int k = atomicAdd(&n_det[i], 1);
-          if (k < kCand) {
-            c_det[i][k].iou = v;
-            c_det[i][k].idx = e;
+        if (r1 < rows) {
+          k1 = vs_track ? skey[r1] : sh.dkey[r1];
+          c1 = vs_track ? scls[r1] : sd.cls[r1];
+        }
+        uint32_t pass0 = 0u, pass1 = 0u;
+#pragma unroll
+        for (int b = 0; b < GS; ++b) {  // (entries past nd are stale; their bits are masked below)
+          const uint4 dk = sh.dkey[i0 + b];
+          const int dc = sd.cls[i0 + b];
+          // same class, and the key intervals meet on both axes (cf. may_overlap)
+          asm("{\n\t.reg .pred t;\n\t"
+              "setp.eq.s32 t, %1, %2;\n\t"
+              "setp.ge.and.u32 t, %3, %4, t;\n\t"
+              "setp.ge.and.u32 t, %5, %6, t;\n\t"
+              "setp.ge.and.u32 t, %7, %8, t;\n\t"
+              "setp.ge.and.u32 t, %9, %10, t;\n\t"
+              "@t or.b32 %0, %0, %11;\n\t}"
+              : "+r"(pass0)
+              : "r"(c0), "r"(dc), "r"(k0.z), "r"(dk.x), "r"(dk.z), "r"(k0.x), "r"(k0.w), "r"(dk.y), "r"(dk.w), "r"(k0.y), "r"(1u << b));
+          asm("{\n\t.reg .pred t;\n\t"
+              "setp.eq.s32 t, %1, %2;\n\t"
+              "setp.ge.and.u32 t, %3, %4, t;\n\t"
+              "setp.ge.and.u32 t, %5, %6, t;\n\t"
+              "setp.ge.and.u32 t, %7, %8, t;\n\t"
+              "setp.ge.and.u32 t, %9, %10, t;\n\t"
+              "@t or.b32 %0, %0, %11;\n\t}"
+              : "+r"(pass1)
+              : "r"(c1), "r"(dc), "r"(k1.z), "r"(dk.x), "r"(dk.z), "r"(k1.x), "r"(k1.w), "r"(dk.y), "r"(dk.w), "r"(k1.y), "r"(1u << b));
+        }
+        const uint32_t in_chunk = i1 - i0 >= 32 ? 0xffffffffu : ((1u << (i1 - i0)) - 1u);
+        pass0 &= in_chunk;
+        pass1 &= in_chunk;
+        if (!vs_track) {  // detection rows: only the detections after the row
+          pass0 = r0 < i0 ? pass0 : (r0 - i0 >= 31 ? 0u : (pass0 & ~((2u << (r0 - i0)) - 1u)));
+          pass1 = r1 < i0 ? pass1 : (r1 - i0 >= 31 ? 0u : (pass1 & ~((2u << (r1 - i0)) - 1u)));
+        }
+        if (r0 >= rows) pass0 = 0u;
+        if (r1 >= rows) pass1 = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t pass = h ? pass1 : pass0;
+          const int r = h ? r1 : r0;
+          while (pass) {
+            const int i = i0 + __ffs((int)pass) - 1;
+            pass &= pass - 1u;
+            const double4 rb = vs_track ? reinterpret_cast<const double4*>(sbox)[r] : sd.box[r];
+            if (overlaps(rb, sd.box[i])) list_pair(i, r, vs_track);
           }
         }
+      };
+      for (int u = warp; u < nblk * G; u += kTrkThreads / 32) {
+        if (G == 2) unit(std::integral_constant<int, 32>{}, u);
+        else if (G == 4) unit(std::integral_constant<int, 16>{}, u);
+        else unit(std::integral_constant<int, 8>{}, u);
       }
+      PHASE_STAMP(p.dbg, 59);
+      __syncthreads();
+      PHASE_STAMP(p.dbg, 60);
+      const int listed = min(sh.n_plist, kTrkPairs);
+#pragma unroll 1
+      for (int q = tid; q < listed; q += kTrkThreads) {
+        const uint32_t e = sh.plist[q];
+        score((int)((e >> 16) & 0x7fffu), (int)(e & 0xffffu), (e >> 31) != 0u);
+      }
+      PHASE_STAMP(p.dbg, 61);
     }
     __syncthreads();
 
@@ -540,8 +631,8 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
     if (s_fallback) {
       // ---- crowded chunk: plain sequential scan of the live table, exact (tracker.py:50-109) ----
       if (warp == 0) {
-        if (SMALL) chunk_fallback_scan(p, sh, sbox, scls, shits, last_det, d0, nd);
-        else chunk_fallback_scan_body(p, sh, sbox, scls, shits, last_det, d0, nd);
+        if (SMALL) chunk_fallback_scan(p, sh, sbox, skey, scls, shits, last_det, d0, nd);
+        else chunk_fallback_scan_body(p, sh, sbox, skey, scls, shits, last_det, d0, nd);
       }
     } else {
       // ---- phase B: conflicted detections, in order, look-ups only ----
@@ -615,6 +706,7 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
             if (last) {
               last_det[r] = (int16_t)(d0 + i);
               reinterpret_cast<double4*>(sbox)[r] = sd.box[i];
+              skey[r] = box_keys(sd.box[i]);
             }
           }
         }
@@ -816,7 +908,9 @@ __device__ __forceinline__ void tracker_stream(const TrkParams& p, const int bi,
 }  // namespace
 
 // shared-memory bytes tracker_stream needs for a working table of `tracks` rows
-inline size_t tracker_smem_bytes(int tracks) { return (size_t)tracks * 46 + kDetChunk * 4 + 16; }
+inline size_t tracker_smem_bytes(int tracks) { return (size_t)tracks * kTrkRowBytes + kDetChunk * 4 + 32; }
+// rows a shared-memory working table can have at most (190 KB of dynamic shared memory); bigger streams use the global scratch
+constexpr int kTrkSmemRowsMax = 3072;
 // rows of the shared-memory working table the next launch gets (host side, tracker.cu)
 int tracker_pick_smem_tracks(b200va_ctx* h, cudaStream_t st);
 // validates the host arguments of a tracker update and fills the launch parameters (tracker.cu)

@@ -25,6 +25,7 @@ v = list(buf)
 print("tracker phases (SM cycles, block 0): start->staged-issue %d, ->dets staged %d, ->match loop done %d, ->prune done %d, ->fence+sync %d, ->ticket %d" %
       tuple(v[i + 1] - v[i] for i in range(6)))
 print("tracker: phase A %d, phase B %d; first iterations of B: %s" % (v[7] - v[2], v[3] - v[7], [v[9 + i] - v[8 + i] for i in range(7)]))
+print("tracker phase A split (last chunk): clear %d, scan %d, barrier %d, iou %d, barrier %d, classify %d; n_plist?" % (v[58] - v[2], v[59] - v[58], v[60] - v[59], v[61] - v[60], v[62] - v[61], v[7] - v[62]))
 print("nms phases: count+keys %d, sort %d, gather %d, chunks %d, filter+emit %d" % tuple(v[16 + i + 1] - v[16 + i] for i in range(5)))
 print("nms chunk loop split: (q) grid query (warp 0) %d, (a) pair matrix %d, (b) resolve %d, (c) tail / insert %d" % (v[27], v[24], v[25], v[26]))
 print("grid query split (accumulated over launches, thread 0): setup %d, cells %d, overflow %d, pass2 %d" % (v[32], v[33], v[34], v[35]))
