@@ -132,6 +132,22 @@ __device__ __forceinline__ void store_px4(void* o, size_t plane, bool vec_ok, in
 }
 
 // Four output pixels of one row from the staged source rows (general two-tap, two-row case).
+// The two taps of a pixel are six consecutive bytes of the row (off1 = off0 + 3; where the x axis clamps, off1 = off0
+// and a1 = 0, so whatever sits behind off0 + 3 is multiplied by zero).  They are fetched as the three aligned words
+// that cover them and lined up with two funnel shifts; per channel one PRMT pairs the tap bytes and one IDP.2A does
+// byte * a0 + byte * a1 (the coefficients are at most 2048: two 16-bit halves of one register).  Three word loads
+// instead of six byte loads per pixel and row: the byte loads, at a 24- or 48-byte lane stride, kept the shared-memory
+// pipe 60-72 % busy with 2- and 4-way bank conflicts.
+__device__ __forceinline__ void taps_row(const uint8_t* __restrict__ r, int off0, uint32_t coef, int (&s)[3]) {
+  const uint32_t* __restrict__ w = reinterpret_cast<const uint32_t*>(r + (off0 & ~3));
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+  const uint32_t sh = (uint32_t)(off0 & 3) * 8u;
+  const uint32_t x = __funnelshift_r(w0, w1, sh), y = __funnelshift_r(w1, w2, sh);  // bytes off0 .. off0 + 7
+  s[0] = (int)__dp2a_lo(coef, __byte_perm(x, y, 0x0030), 0u);  // (B0, B1)
+  s[1] = (int)__dp2a_lo(coef, __byte_perm(x, y, 0x0041), 0u);  // (G0, G1)
+  s[2] = (int)__dp2a_lo(coef, __byte_perm(x, y, 0x0052), 0u);  // (R0, R1)
+}
+
 template <bool MASK>
 __device__ __forceinline__ void px4_general(const TapX (&t)[4], const uint8_t* __restrict__ r0,
                                             const uint8_t* __restrict__ r1, const uint8_t* __restrict__ m0,
@@ -149,8 +165,7 @@ __device__ __forceinline__ void px4_general(const TapX (&t)[4], const uint8_t* _
         c0 = m0[t[j].mx0 & 0xffff] ? c0 : 0;
         c1 = m0[(unsigned)t[j].mx0 >> 16] ? c1 : 0;
       }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) s0[c] = (int)r0[t[j].off0 + c] * c0 + (int)r0[t[j].off1 + c] * c1;
+      taps_row(r0, t[j].off0, (uint32_t)c0 | ((uint32_t)c1 << 16), s0);
     }
     if (b1) {
       int c0 = t[j].a0, c1 = t[j].a1;
@@ -158,8 +173,7 @@ __device__ __forceinline__ void px4_general(const TapX (&t)[4], const uint8_t* _
         c0 = m1[t[j].mx0 & 0xffff] ? c0 : 0;
         c1 = m1[(unsigned)t[j].mx0 >> 16] ? c1 : 0;
       }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) s1[c] = (int)r1[t[j].off0 + c] * c0 + (int)r1[t[j].off1 + c] * c1;
+      taps_row(r1, t[j].off0, (uint32_t)c0 | ((uint32_t)c1 << 16), s1);
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) v[j][c] = (((b0 * (s0[c] >> 4)) >> 16) + ((b1 * (s1[c] >> 4)) >> 16) + 2) >> 2;
@@ -579,9 +593,9 @@ static const int kLetterboxSmemMax = 200 * 1024;
 
 template <int FMT>
 static cudaError_t configure_fmt(bool uniform_carveout) {
-  cudaError_t e = cudaFuncSetAttribute(k_letterbox<FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax);
+  cudaError_t e = cudaFuncSetAttribute(k_letterbox<FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax + 128);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(k_letterbox<FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax);
+  e = cudaFuncSetAttribute(k_letterbox<FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLetterboxSmemMax + 128);
   if (e != cudaSuccess) return e;
   if (!uniform_carveout) return e;
   e = prefer_max_shared(k_letterbox<FMT, false>);
@@ -684,7 +698,7 @@ static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* 
         for (int i = 0; i < n; ++i)
           if ((uintptr_t)outs[idx[base + i]] % 16 != 0) p.vec_ok = 0;
       dim3 grid((dst_h + rpc - 1) / rpc, n);
-      const size_t smem = (size_t)stages * per_stage;
+      const size_t smem = (size_t)stages * per_stage + 16;  // (taps_row reads up to 8 bytes past the end of a row)
       cudaError_t e;
       const bool pdl = h->pdl_preprocess && h->tune.pdl != 0;
       h->pdl_preprocess = false;  // only the first launch of the call directly follows the decode kernel

@@ -1,2 +1,2 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/gputest.log 2>&1; tail -3 gpurun_out/gputest.log
-python tools/bench_configs.py --only 1,2,5 2>&1 | tail -3 | cut -c1-150
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_fuzz.py tests/test_gpu_ultralytics.py -x -q -k "letterbox or preprocess or resize or geom or fused or motion" > gpurun_out/lb_test.log 2>&1; tail -3 gpurun_out/lb_test.log
+python tools/bench_configs.py --only L 2>&1 | tail -12 | cut -c1-200
