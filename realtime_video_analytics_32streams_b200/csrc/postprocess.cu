@@ -1748,11 +1748,8 @@ __global__ void __launch_bounds__(kPairThreads, 8) k_dense_pairs(const __grid_co
   }
 }
 
-__global__ void __launch_bounds__(kResolveThreads) k_dense_resolve(const __grid_constant__ NmsParams p, const DenseNms D) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+__device__ __forceinline__ void dense_resolve_frame(const NmsParams& p, const DenseNms& D, uint8_t* const smem_raw) {
   __shared__ int s_m, s_out;
-  griddep_launch_dependents();  // a tracker kernel behind this one may be scheduled; its griddep_wait() waits for this grid
-  griddep_wait();
   const int tid = threadIdx.x, lane = tid & 31, frame = blockIdx.x;
   PHASE_STAMP(p.dbg, 36);
   const int n_raw = (p.skip && p.skip[frame]) ? 0 : p.cand_count[frame];
@@ -1938,6 +1935,32 @@ size_t nms_smem_bytes(int max_cand) {
   const size_t cap = (size_t)next_pow2(max_cand);
   return nms_base_bytes(max_cand) + (nms_grid_offset(max_cand) ? sizeof(NmsGrid) + cap / 8 + cap * 2 : 0);
 }
+__global__ void __launch_bounds__(kResolveThreads) k_dense_resolve(const __grid_constant__ NmsParams p, const DenseNms D) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  griddep_launch_dependents();  // a tracker kernel behind this one may be scheduled; its griddep_wait() waits for this grid
+  griddep_wait();
+  dense_resolve_frame(p, D, smem_raw);
+}
+
+// Dense scenes with the tracker update in the same call: the resolution of frame i and the tracker update of stream i in
+// ONE CTA (as k_post_track does for sparse scenes) -- one launch and one grid-to-grid dependency fewer on the chain
+// decode -> pairs -> resolve -> tracker, which is what a dense tick waits for.
+static_assert(kResolveThreads == kTrkThreadsMax, "the fused dense kernel runs both halves at the tracker's widest launch");
+__global__ void __launch_bounds__(kResolveThreads) k_dense_resolve_track(const __grid_constant__ NmsParams q, const DenseNms D,
+                                                                          const __grid_constant__ TrkParams t) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __shared__ TrkShared sh;
+  griddep_launch_dependents();
+  griddep_wait();
+  TIMELINE_BEGIN(q.dbg, 44);
+  dense_resolve_frame(q, D, smem_raw);
+  __syncthreads();  // this frame's detections were written by this CTA: visible to all of its threads from here on
+  TIMELINE_END(q.dbg, 44);
+  TIMELINE_BEGIN(q.dbg, 46);
+  tracker_stream<false>(t, blockIdx.x, smem_raw, sh, -1);
+  TIMELINE_END(q.dbg, 46);
+}
+
 static size_t dense_resolve_smem(int max_cand) {
   int np2 = 64;
   while (np2 < max_cand) np2 <<= 1;
@@ -2082,6 +2105,9 @@ int postprocess_configure(b200va_ctx* h) {
     CUDA_TRY(h, cudaMalloc(&D->work, sizeof(int32_t)));
     CUDA_TRY(h, cudaMemset(D->work, 0, sizeof(int32_t)));
     CUDA_TRY(h, raise_dyn_smem(k_dense_resolve, dense_resolve_smem(D->max_cand)));
+    CUDA_TRY(h, raise_dyn_smem(k_dense_resolve_track,
+                               std::min<size_t>(200 * 1024, std::max(dense_resolve_smem(D->max_cand),
+                                                                     tracker_smem_bytes(std::min(h->cfg.max_tracks, kTrkSmemRowsMax))))));
   }
   return B200VA_OK;
 }
@@ -2350,8 +2376,29 @@ static int postprocess_impl(b200va_handle h, const float* head, int layout, int 
     } else if (dense && h->dense_nms) {
       const DenseNms& D = *(const DenseNms*)h->dense_nms;
       CUDA_TRY(h, launch_pdl(k_dense_pairs, dim3(D.ctas), dim3(kPairThreads), 0, st, pdl, q, D, n));
-      CUDA_TRY(h, launch_pdl(k_dense_resolve, dim3(n), dim3(kResolveThreads), dense_resolve_smem(D.max_cand), st, h->tune.pdl != 0, q, D));
       h->launches.fetch_add(1, std::memory_order_relaxed);
+      // the tracker update of the same rows rides in the resolving CTA when the call carries one
+      const bool fuse_trk = fuse && fuse->stream_slots && fuse->cfg && h->tune.fuse_post_track != 0 && base == 0 && n == batch &&
+                            fuse->batch == batch && fuse->max_dets == h->cfg.max_dets;
+      const int rows = fuse_trk ? tracker_pick_smem_tracks(h, st) : 0;
+      const size_t both = std::max(dense_resolve_smem(D.max_cand), tracker_smem_bytes(rows));
+      if (fuse_trk && both <= 200 * 1024) {
+        TrkParams t;
+        memset(&t, 0, sizeof(t));
+        t.f_box = out->bbox_xyxy;
+        t.f_conf = out->conf;
+        t.d_cls = out->cls;
+        t.d_count = out->count;
+        t.max_dets = fuse->max_dets;
+        const int rc = tracker_fill_params(h, t, fuse->stream_slots, fuse->batch, fuse->det_scale, fuse->skip, fuse->cfg,
+                                           fuse->id_base, fuse->out, fuse->new_counts);
+        if (rc != B200VA_OK) return rc;
+        t.smem_tracks = rows;
+        CUDA_TRY(h, launch_pdl(k_dense_resolve_track, dim3(n), dim3(kResolveThreads), both, st, h->tune.pdl != 0, q, D, t));
+        fuse->done = true;
+      } else {
+        CUDA_TRY(h, launch_pdl(k_dense_resolve, dim3(n), dim3(kResolveThreads), dense_resolve_smem(D.max_cand), st, h->tune.pdl != 0, q, D));
+      }
     } else if (dense && q.grid_off) {
       CUDA_TRY(h, launch_pdl(k_sort_nms<true>, dim3(n), dim3(kNmsThreads), nms_smem, st, pdl, q));
     } else {
@@ -2417,8 +2464,17 @@ int postprocess_run_pending(b200va_handle h, void* stream) {
     if (dense && h->dense_nms) {
       const DenseNms& D = *(const DenseNms*)h->dense_nms;
       CUDA_TRY(h, launch_pdl(k_dense_pairs, dim3(D.ctas), dim3(kPairThreads), 0, st, false, pc->q, D, n));
-      CUDA_TRY(h, launch_pdl(k_dense_resolve, dim3(n), dim3(kResolveThreads), dense_resolve_smem(D.max_cand), st, h->tune.pdl != 0, pc->q, D));
       h->launches.fetch_add(1, std::memory_order_relaxed);
+      const bool fuse_trk = pc->has_trk && h->tune.fuse_post_track != 0 && pc->t.max_dets == h->cfg.max_dets;
+      const int rows = fuse_trk ? tracker_pick_smem_tracks(h, st) : 0;
+      const size_t both = std::max(dense_resolve_smem(D.max_cand), tracker_smem_bytes(rows));
+      if (fuse_trk && both <= 200 * 1024) {
+        pc->t.smem_tracks = rows;
+        CUDA_TRY(h, launch_pdl(k_dense_resolve_track, dim3(n), dim3(kResolveThreads), both, st, h->tune.pdl != 0, pc->q, D, pc->t));
+        LAUNCH_CHECK(h);
+        return B200VA_OK;
+      }
+      CUDA_TRY(h, launch_pdl(k_dense_resolve, dim3(n), dim3(kResolveThreads), dense_resolve_smem(D.max_cand), st, h->tune.pdl != 0, pc->q, D));
     } else if (dense && pc->q.grid_off) CUDA_TRY(h, launch_pdl(k_sort_nms<true>, dim3(n), dim3(kNmsThreads), nms_smem, st, false, pc->q));
     else CUDA_TRY(h, launch_pdl(k_sort_nms<false>, dim3(n), dim3(kNmsThreads), nms_plain, st, false, pc->q));
     LAUNCH_CHECK(h);
