@@ -1508,8 +1508,10 @@ __global__ void __launch_bounds__(kNmsThreadsSmall) k_post_track(const __grid_co
 //                    has to feed four tests), four compares decide "the boxes overlap at all" branch-free, the
 //                    overlapping pairs of a warp (2 % of all) are queued in shared memory and the IoU formula then runs
 //                    over the queue with every lane busy.  A hit appends the box with the larger key (the one greedy
-//                    NMS meets first) to the suppressor list of the other one; the hits of an item are recorded together
-//                    (their key loads and atomics are dependent round trips to L2).
+//                    NMS meets first) to the suppressor list of the other one; hits are collected across items and
+//                    recorded 128 at a time (their key loads and atomics are dependent round trips to L2).  Measured and
+//                    dropped: 64- and 128-column items, two rows per thread, 10 / 12 CTAs per SM at 48 / 40 registers,
+//                    rows and columns of the next item prefetched with cp.async into a second buffer (7 CTAs per SM).
 //   k_dense_resolve  one CTA per frame: Jacobi iteration of the recurrence over the suppressor lists (a box of
 //                    dependency depth d is final after d + 1 rounds; clusters of near-duplicates have depth 1-2), then
 //                    only the KEPT boxes (~300 of 1800) are ordered by key -- rank among the kept = output position.
@@ -1530,11 +1532,12 @@ constexpr int kPairWarps = 4, kPairThreads = 32 * kPairWarps;  // the warps of a
 constexpr int kPairGroups = 4;                               // a thread owns kPairGroups rows (32 apart)
 constexpr int kPairRows = 32 * kPairGroups;                  // rows of a work item (one warp)
 #ifndef B200VA_PAIR_COLS
-#define B200VA_PAIR_COLS 64
+#define B200VA_PAIR_COLS 32
 #endif
-constexpr int kPairCols = B200VA_PAIR_COLS;                  // columns of a work item (64 or 128)
+constexpr int kPairCols = B200VA_PAIR_COLS;                  // columns of a work item (32, 64 or 128; 32 measured best: the
+                                                             // kernel ends when the last item does, so items are kept short)
 constexpr int kPairRC = kPairRows / kPairCols;               // column tiles per row tile
-constexpr int kPairColBits = kPairCols == 64 ? 6 : 7;
+constexpr int kPairColBits = kPairCols == 32 ? 5 : (kPairCols == 64 ? 6 : 7);
 constexpr int kPairQueue = 256;                              // overlapping pairs a warp queues per 32 columns
 constexpr int kPairHits = 128;                               // suppressing pairs a warp collects before it records them
 constexpr int kResolveThreads = 1024, kResolveRows = kDenseCandMax / kResolveThreads;
@@ -1557,7 +1560,8 @@ __device__ __forceinline__ int dense_items_of(int n) {
   const int R = (n + kPairRows - 1) / kPairRows, Cn = (n + kPairCols - 1) / kPairCols;
   return n > 1 ? R * Cn - kPairRC * (R * (R - 1) / 2) : 0;
 }
-static_assert(kPairRows == kPairRC * kPairCols && (kPairCols == 64 || kPairCols == 128), "bad work item shape");
+static_assert(kDenseCandMax <= 4096 && B200VA_LAUNCH_FRAMES <= 256, "a hit is packed into 32 bits");
+static_assert(kPairRows == kPairRC * kPairCols && (kPairCols == 32 || kPairCols == 64 || kPairCols == 128), "bad work item shape");
 
 struct PairWarp {  // a warp's staging area
   float4 row[kPairRows];
@@ -1565,7 +1569,7 @@ struct PairWarp {  // a warp's staging area
   int rcl[kPairRows];
   int ccl[kPairCols];
   uint16_t queue[kPairQueue];
-  uint16_t hits[kPairHits];
+  uint32_t hits[kPairHits];  // frame << 24 | row << 12 | column (candidate slots)
 };
 
 __global__ void __launch_bounds__(kPairThreads, 8) k_dense_pairs(const __grid_constant__ NmsParams p, const DenseNms D, const int frames) {
@@ -1575,8 +1579,10 @@ __global__ void __launch_bounds__(kPairThreads, 8) k_dense_pairs(const __grid_co
   griddep_launch_dependents();
   griddep_wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int next = 0;
-  if (lane == 0) next = atomicAdd(D.work, 1);  // items are handed out dynamically: diagonal tiles are cheaper than the rest
+  // Every warp starts on the item of its own number; the rest are handed out through an atomic counter (diagonal tiles
+  // are cheaper than the others), fetched one item ahead.
+  const int n_warps = (int)gridDim.x * kPairWarps;
+  int item = (int)blockIdx.x * kPairWarps + warp, next = 0;
   if (tid < 32) {
     int v[2];
 #pragma unroll
@@ -1608,8 +1614,26 @@ __global__ void __launch_bounds__(kPairThreads, 8) k_dense_pairs(const __grid_co
   const float thr = p.iou_thr;
   const bool thr_nonneg = ultra ? p.iou_thr64 >= 0.0 : thr >= 0.f;
   PairWarp& S = s_warp[warp];
-  for (;;) {
-    const int item = __shfl_sync(0xffffffffu, next, 0);
+  // a suppressing pair: the box greedy NMS meets first (the larger key) goes on the suppressor list of the other one
+  auto record = [&](const uint32_t hit) {
+    const int frame = (int)(hit >> 24), i = (int)((hit >> 12) & 0xfffu), j = (int)(hit & 0xfffu);
+    const size_t cbase = (size_t)frame * p.max_cand;
+    const bool i_first = p.cand_key[cbase + i] > p.cand_key[cbase + j];
+    const int loser = i_first ? j : i, winner = i_first ? i : j;
+    const size_t row = (size_t)frame * D.max_cand + loser;
+    const int slot = atomicAdd(D.nbr_cnt + row, 1);
+    if (slot < kNbrCap) D.nbr[row * kNbrCap + slot] = (uint16_t)winner;
+  };
+  // Hits are collected across items and recorded kPairHits at a time: the two key loads and the atomic of a hit are
+  // dependent round trips to L2, paid once per batch this way instead of once per 32 queued pairs.
+  int n_hits = 0;
+  auto flush_hits = [&]() {
+    __syncwarp();
+    for (int e = lane; e < n_hits; e += 32) record(S.hits[e]);
+    n_hits = 0;
+    __syncwarp();
+  };
+  for (;; item = n_warps + __shfl_sync(0xffffffffu, next, 0)) {
     if (item >= total) break;
     if (lane == 0) next = atomicAdd(D.work, 1);  // (in flight while this item is worked on)
     // frame of the item: how many frames start at or before it
@@ -1655,27 +1679,7 @@ __global__ void __launch_bounds__(kPairThreads, 8) k_dense_pairs(const __grid_co
       const float4 a = S.row[rl], b = S.col[col];
       return ultra ? suppresses_tv(a, b, p.iou_thr64) : suppresses(a, b, thr);
     };
-    // a suppressing pair: the box greedy NMS meets first (the larger key) goes on the suppressor list of the other one
-    auto record = [&](const int rl, const int col) {
-      const int i = row0 + rl, j = jb + col;
-      const bool i_first = p.cand_key[cbase + i] > p.cand_key[cbase + j];
-      const int loser = i_first ? j : i, winner = i_first ? i : j;
-      const size_t row = (size_t)frame * D.max_cand + loser;
-      const int slot = atomicAdd(D.nbr_cnt + row, 1);
-      if (slot < kNbrCap) D.nbr[row * kNbrCap + slot] = (uint16_t)winner;
-    };
-    // The hits of an item are recorded together at its end: the two key loads and the atomic of a hit are dependent
-    // round trips to L2, paid once per item this way instead of once per 32 queued pairs.
-    int n_hits = 0;
-    auto flush_hits = [&]() {
-      __syncwarp();
-      for (int e = lane; e < n_hits; e += 32) {
-        const int code = S.hits[e];
-        record(code >> kPairColBits, code & (kPairCols - 1));
-      }
-      n_hits = 0;
-      __syncwarp();
-    };
+    const uint32_t hit_base = ((uint32_t)frame << 24) | ((uint32_t)row0 << 12) | (uint32_t)jb;  // + (row << 12 | column) in the item
 #pragma unroll 1
     for (int w = 0; w < kPairCols / 32; ++w) {
       const int j0 = jb + 32 * w, cnt = min(32, n - j0);
@@ -1728,7 +1732,7 @@ __global__ void __launch_bounds__(kPairThreads, 8) k_dense_pairs(const __grid_co
           const int b = __ffs((int)cq) - 1;
           cq &= cq - 1u;
           if (pos < kPairQueue) S.queue[pos] = (uint16_t)(((q * 32 + lane) << kPairColBits) | (32 * w + b));
-          else if (test_pair(q * 32 + lane, 32 * w + b)) record(q * 32 + lane, 32 * w + b);  // (queue full: on the spot)
+          else if (test_pair(q * 32 + lane, 32 * w + b)) record(hit_base + ((uint32_t)(q * 32 + lane) << 12) + (uint32_t)(32 * w + b));  // (queue full: on the spot)
           ++pos;
         }
       }
@@ -1739,13 +1743,13 @@ __global__ void __launch_bounds__(kPairThreads, 8) k_dense_pairs(const __grid_co
         const int code = e < queued ? S.queue[e] : 0;
         const bool hit = e < queued && test_pair(code >> kPairColBits, code & (kPairCols - 1));
         const unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (hit) S.hits[n_hits + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)code;
+        if (hit) S.hits[n_hits + __popc(bal & ((1u << lane) - 1u))] = hit_base + ((uint32_t)(code >> kPairColBits) << 12) + (uint32_t)(code & (kPairCols - 1));
         n_hits += __popc(bal);
       }
       __syncwarp();
     }
-    flush_hits();
   }
+  flush_hits();
 }
 
 __device__ __forceinline__ void dense_resolve_frame(const NmsParams& p, const DenseNms& D, uint8_t* const smem_raw) {

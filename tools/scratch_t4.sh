@@ -1,4 +1,3 @@
-python -m pytest tests -m gpu -x -q -k "not config4" > gpurun_out/post_test.log 2>&1; tail -3 gpurun_out/post_test.log
-python tools/bench_configs.py --only 5 2>&1 | tail -1 | cut -c1-150
-B200VA_BENCH_SCHEDULE=4 python tools/bench_configs.py --only 5 2>&1 | tail -1 | cut -c1-150
-B200VA_BENCH_SCHEDULE=3 python tools/bench_configs.py --only 5 2>&1 | tail -1 | cut -c1-150
+python -m pytest tests/test_gpu_dense_nms.py tests/test_gpu_fuzz.py tests/test_gpu_ultralytics.py tests/test_gpu_properties.py -x -q 2>&1 | tail -2
+python tools/bench_configs.py --only 5 2>&1 | tail -1 | cut -c1-130
+ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,sm__cycles_active.avg --clock-control none -k regex:k_dense_pairs -c 2 --csv python tools/bench_configs.py --only 5 --steps 3 2>/dev/null | grep -E "k_dense" | cut -d, -f5,15-
