@@ -90,6 +90,7 @@ struct b200va_ctx {
     int fuse_post_track = 1;  // B200VA_FUSE_POST_TRACK=0: always launch NMS and tracker as two kernels
     int pdl = 1;              // B200VA_PDL=0: no programmatic dependent launches
     int uniform_carveout = 0; // B200VA_UNIFORM_CARVEOUT=1: every tick kernel prefers the all-shared-memory split
+    int lb_smem_floor = 33 * 1024;  // B200VA_LB_SMEM_FLOOR=bytes: least dynamic shared memory of a letterbox CTA (caps CTAs per SM, see preprocess.cu)
     int post_carveout = -1;   // B200VA_POST_CARVEOUT=pct: preferred shared-memory carve-out of k_post_track (0: driver default)
     int dense_impl = 0;       // B200VA_DENSE_IMPL=1: dense scenes stay on the single-kernel NMS (k_sort_nms<true>); 2: every launch is 'dense'
     int dense_ctas_per_sm = 0; // B200VA_DENSE_CTAS=n: CTAs per SM of k_dense_pairs (default 8)

@@ -698,7 +698,11 @@ static int run_resample(b200va_ctx* h, const uint8_t* const* frames, const int* 
         for (int i = 0; i < n; ++i)
           if ((uintptr_t)outs[idx[base + i]] % 16 != 0) p.vec_ok = 0;
       dim3 grid((dst_h + rpc - 1) / rpc, n);
-      const size_t smem = (size_t)stages * per_stage + 16;  // (taps_row reads up to 8 bytes past the end of a row)
+      // (taps_row reads up to 8 bytes past the end of a row.)  The floor keeps at most six CTAs on an SM: with the 48
+      // registers the kernel needs since the word-load taps, eight would fit, and the 32 x 1080p launch is 5 % slower
+      // that way (43.2 against 41.4 us: more rows in flight than the memory system wants; the same was measured in
+      // round 1 by forcing 7 / 8 CTAs per SM with __launch_bounds__).
+      const size_t smem = std::max((size_t)stages * per_stage + 16, (size_t)std::max(h->tune.lb_smem_floor, 0));
       cudaError_t e;
       const bool pdl = h->pdl_preprocess && h->tune.pdl != 0;
       h->pdl_preprocess = false;  // only the first launch of the call directly follows the decode kernel

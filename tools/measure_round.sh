@@ -23,4 +23,15 @@ python tools/bench_configs.py --only 4 --steps 3 > $O/plain3.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:'k_motion|k_letterbox' -c 4 -f \
     -o $O/prof_${R}_cfg4 python tools/bench_configs.py --only 4 --steps 3 > $O/ncu3.log 2>&1
 ncu -i $O/prof_${R}_cfg4.ncu-rep --page raw --csv > $O/raw_${R}_cfg4.csv 2>/dev/null
+# the dense config (5): decode, k_dense_pairs, k_dense_resolve(_track), k_tracker
+python tools/bench_configs.py --only 5 --steps 3 > $O/plain4.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:'k_dense|k_tracker$|k_decode' -s 8 -c 8 -f \
+    -o $O/prof_${R}_dense python tools/bench_configs.py --only 5 --steps 3 > $O/ncu4.log 2>&1
+ncu -i $O/prof_${R}_dense.ncu-rep --page raw --csv > $O/raw_${R}_dense.csv 2>/dev/null
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_dense|k_tracker$|k_decode|k_letterbox' -c 400 --csv --log-file $O/${R}_launches_dense.csv \
+    python tools/bench_configs.py --only 5 --steps 10 > $O/ncu5.log 2>&1
+python tools/bench_configs.py --only 1,2,5,4,D,E --out $O/${R}_configs.json > $O/${R}_configs.log 2>&1
+python tools/ncu_summary.py $O/raw_${R}.csv $O/${R}_launches.csv $O/${R}_ncu_summary.md "Round ${R#r} -- bench.py tick kernels (32 x 1080p + [32,84,8400]): ncu --set full and the launch list of the bench command" all
+python tools/ncu_summary.py $O/raw_${R}_cfg4.csv $O/${R}_launches.csv $O/${R}_ncu_cfg4.md "Round ${R#r} -- config 4 (32 x 4K + ROI + motion): ncu --set full" all
+python tools/ncu_summary.py $O/raw_${R}_dense.csv $O/${R}_launches_dense.csv $O/${R}_ncu_dense.md "Round ${R#r} -- config 5 (dense stress, 32 x ~1800 candidates): ncu --set full and the launch list" all
 tail -c 600 $O/${R}_bench.json

@@ -1,3 +1,2 @@
-python -m pytest tests/test_gpu_dense_nms.py tests/test_gpu_fuzz.py tests/test_gpu_ultralytics.py tests/test_gpu_properties.py -x -q 2>&1 | tail -2
-python tools/bench_configs.py --only 5 2>&1 | tail -1 | cut -c1-130
-ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,sm__cycles_active.avg --clock-control none -k regex:k_dense_pairs -c 2 --csv python tools/bench_configs.py --only 5 --steps 3 2>/dev/null | grep -E "k_dense" | cut -d, -f5,15-
+for f in 0 33792 40960 49152; do echo floor $f; B200VA_LB_SMEM_FLOOR=$f python tools/bench_configs.py --only L --lshape 0 2>&1 | tail -1 | cut -c1-140; done
+echo; for f in 0 33792; do echo floor $f all shapes; B200VA_LB_SMEM_FLOOR=$f python tools/bench_configs.py --only L 2>&1 | tail -6 | cut -c1-60,100-180; done
