@@ -1,2 +1,2 @@
-for f in 0 33792 40960 49152; do echo floor $f; B200VA_LB_SMEM_FLOOR=$f python tools/bench_configs.py --only L --lshape 0 2>&1 | tail -1 | cut -c1-140; done
-echo; for f in 0 33792; do echo floor $f all shapes; B200VA_LB_SMEM_FLOOR=$f python tools/bench_configs.py --only L 2>&1 | tail -6 | cut -c1-60,100-180; done
+bash tools/measure_round.sh r2 2>&1 | tail -3
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2_bench_2gpu.json 2> gpurun_out/r2_bench_2gpu.err; tail -c 400 gpurun_out/r2_bench_2gpu.json
