@@ -92,6 +92,7 @@ static int create_impl(b200va_ctx* h) {
   if (getenv("B200VA_PDL")) h->tune.pdl = env_int("B200VA_PDL");
   h->tune.uniform_carveout = env_int("B200VA_UNIFORM_CARVEOUT");
   h->tune.trk_smem_tracks = env_int("B200VA_TRK_SMEM_TRACKS");
+  h->tune.trk_max_threads = env_int("B200VA_TRK_THREADS");
   h->tune.dense_impl = env_int("B200VA_DENSE_IMPL");
   h->tune.dense_ctas_per_sm = env_int("B200VA_DENSE_CTAS");
   if (getenv("B200VA_LB_SMEM_FLOOR")) h->tune.lb_smem_floor = env_int("B200VA_LB_SMEM_FLOOR");

@@ -94,6 +94,7 @@ struct b200va_ctx {
     int post_carveout = -1;   // B200VA_POST_CARVEOUT=pct: preferred shared-memory carve-out of k_post_track (0: driver default)
     int dense_impl = 0;       // B200VA_DENSE_IMPL=1: dense scenes stay on the single-kernel NMS (k_sort_nms<true>); 2: every launch is 'dense'
     int dense_ctas_per_sm = 0; // B200VA_DENSE_CTAS=n: CTAs per SM of k_dense_pairs (default 8)
+    int trk_max_threads = 0;  // B200VA_TRK_THREADS=n: widest tracker update of a stream (0: the CTA's width)
     int trk_smem_tracks = 0;  // B200VA_TRK_SMEM_TRACKS=n: fix the tracker's shared-memory table at n rows (tests)
   } tune;
   // ---- developer phase timing (only written by builds with -DB200VA_PHASE_TIMING) ----

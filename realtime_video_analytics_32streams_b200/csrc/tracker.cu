@@ -112,6 +112,7 @@ int tracker_fill_params(b200va_ctx* h, TrkParams& p, const int* stream_slots, in
     p.skip[i] = skip ? skip[i] : 0;
   }
   p.st = *h->tracker;
+  p.max_threads = h->tune.trk_max_threads;
   p.max_tracks = h->cfg.max_tracks;
   p.batch = batch;
   p.max_age = cfg->max_age;

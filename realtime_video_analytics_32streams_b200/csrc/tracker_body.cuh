@@ -31,6 +31,7 @@ struct TrkParams {
   long long id_base[B200VA_MAX_BATCH];
   uint8_t skip[B200VA_MAX_BATCH];
   const uint8_t* skip_dev;  // device-side gates: [batch] flags decided on the device (b200va_set_skip_mask), OR-ed with skip[]
+  int max_threads;          // 0: the whole CTA; else the widest a stream's update runs (the surplus warps leave at once)
   // detections (one of the two sources)
   const float* f_box;
   const float* f_conf;
@@ -351,7 +352,8 @@ __device__ __forceinline__ void tracker_stream_impl(const TrkParams& p, const in
   // (25 x 25) only pays for the wider barriers (19 us with 256, 22 us with 1024): the surplus warps of a small
   // stream leave at once (a barrier counts the warps that are still alive); see kTrkThreadsMax for the width launched
   // SMALL (one chunk, few pairs: what tracker_stream checks before it picks this instantiation) always runs 256 wide
-  const int kTrkThreads = SMALL ? kTrkThreadsMin : ((T0 > 96 || D > 64) ? (int)blockDim.x : kTrkThreadsMin);
+  const int wide = p.max_threads > 0 ? min((int)blockDim.x, p.max_threads) : (int)blockDim.x;
+  const int kTrkThreads = SMALL ? kTrkThreadsMin : ((T0 > 96 || D > 64) ? wide : kTrkThreadsMin);
   if (tid >= kTrkThreads) return;
 
   // (`staged_table`: the fused kernel copied the table into `tab` before it even waited for the decode kernel)

@@ -1,2 +1,1 @@
-bash tools/measure_round.sh r2 2>&1 | tail -3
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2_bench_2gpu.json 2> gpurun_out/r2_bench_2gpu.err; tail -c 400 gpurun_out/r2_bench_2gpu.json
+DENSE=1 python tools/phase_timing.py 2>&1 | head -3
