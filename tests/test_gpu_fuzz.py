@@ -208,13 +208,18 @@ def test_nms_clusters_near_threshold(H):
             assert np.array_equal(out["bbox_xyxy"][0, :m].cpu().numpy().astype(np.float64), rb)
 
 
-def test_nms_grid_paths(H):
-    """More than 256 candidates take the kept-box grid: mixes of tiny boxes crowding one cell (cell lists overflow),
-    frame-sized boxes (too many cells: overflow list), ordinary clusters, zero-area boxes and boxes on the frame
-    border, class-agnostic and class-aware, several thresholds and frame shapes."""
+@pytest.mark.parametrize("dense_impl", ["1", "0"])
+def test_nms_grid_paths(H, dense_impl, monkeypatch):
+    """Frames with more than 256 candidates: mixes of tiny boxes crowding one cell (the grid's cell lists overflow; the
+    suppressor lists of the pair kernel overflow), frame-sized boxes (too many cells: overflow list), ordinary clusters,
+    zero-area boxes and boxes on the frame border, class-agnostic and class-aware, several thresholds and frame shapes.
+    dense_impl "1": the single-CTA kernel with the kept-box grid (k_sort_nms<true>, also the fall-back of the dense
+    kernels); "0": k_dense_pairs + k_dense_resolve from the second launch on (the default)."""
     from realtime_video_analytics_32streams_b200 import _native as N
 
+    monkeypatch.setenv("B200VA_DENSE_IMPL", dense_impl)
     H = N.Handle(device=0, max_batch=2, max_anchors=4096, max_candidates=2048, max_dets=2048, max_streams=2, max_tracks=64)
+    monkeypatch.delenv("B200VA_DENSE_IMPL")
     rng = np.random.default_rng(29)
     for it, (fh, fw) in enumerate([(1080, 1920), (1000, 1000), (2160, 3840), (360, 640), (1920, 1080), (90, 4000)]):
         lb = N.Letterbox(fh, fw, fh, fw, 0, 0, 1.0)

@@ -561,12 +561,16 @@ def test_tracker_batched_f32_streams_share_id_counter(H):
     H.poll_status()
 
 
-def test_tracker_dense_long_lived(H):
-    """Config-5 shape: ~300 detections per frame against ~300+ live tracks."""
+@pytest.mark.parametrize("threads", [0, 512])
+def test_tracker_dense_long_lived(threads, monkeypatch):
+    """Config-5 shape: ~300 detections per frame against ~300+ live tracks (the dense-stream phase A: overlap keys, listed
+    pairs); also with the update capped at 512 threads (B200VA_TRK_THREADS: other unit-to-warp assignment, same result)."""
     from realtime_video_analytics_32streams_b200 import B200IouTracker, TrackerConfig, _native as N
 
-    H.tracker_set_next_id(1)
-    H.tracker_reset(0)
+    if threads:
+        monkeypatch.setenv("B200VA_TRK_THREADS", str(threads))
+    H = N.Handle(device=0, max_batch=1, max_anchors=8400, max_candidates=4096, max_dets=1024, max_streams=1, max_tracks=1024)
+    monkeypatch.delenv("B200VA_TRK_THREADS", raising=False)
     trk = B200IouTracker(TrackerConfig(max_age=30, max_iou_distance=0.5, min_hits=1), handle=H)
     ora = O.IouTracker(30, 0.5, 1)
     scene = synth.DenseScene(5)
@@ -582,6 +586,8 @@ def test_tracker_dense_long_lived(H):
         for k, v in got.items():
             assert np.array_equal(v, want[k]), (t, k)
         assert len(want["id"]) > 250
+    H.poll_status()
+    H.close()
 
 
 # ------------------------------------------------------------------------------------------------
