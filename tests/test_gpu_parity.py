@@ -437,6 +437,7 @@ def test_dfl_decode_matches_float32_reference_within_tolerance(H):
 
     rng = np.random.default_rng(71)
     for nc, levels, strides in ((80, ((80, 80), (40, 40), (20, 20)), (8.0, 16.0, 32.0)),
+                                (21, ((5, 7), (3, 5)), (8.0, 16.0)),  # 50 anchors: rows not 16-byte aligned (one anchor per thread)
                                 (3, ((12, 20), (6, 10)), (8.0, 16.0))):
         a = sum(h * w for h, w in levels)
         raw = rng.normal(0, 2.5, size=(3, 64 + nc, a)).astype(np.float32)
