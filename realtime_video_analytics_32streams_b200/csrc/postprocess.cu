@@ -2085,9 +2085,12 @@ int postprocess_configure(b200va_ctx* h) {
     CUDA_TRY(h, raise_dyn_smem(k_post_track<false>, fused));
     CUDA_TRY(h, raise_dyn_smem(k_post_track<true>, fused));
     // k_post_track runs beside the letterbox in b200va_tick, and an SM only hosts kernels that agree on its L1 /
-    // shared-memory split (see prefer_max_shared): ask for the split the 1080p letterbox launch gets (164 KB, six
-    // 24.5 KB CTAs) instead of the one the driver would derive from this kernel's own occupancy
-    const int pct = h->tune.post_carveout >= 0 ? h->tune.post_carveout : 71;
+    // shared-memory split (see prefer_max_shared): ask for the split the letterbox launches get -- all of it: six
+    // 34 KB CTAs at 1080p (preprocess.cu: the shared-memory floor that keeps it at six), two or three 50-100 KB CTAs at
+    // 4K -- instead of the one the driver would derive from this kernel's own occupancy.  Measured on the 32 x 1080p
+    // tick: 63.5 us with 100 %, 64.3 us with 86 %, 65.5 us with the 71 % that matched the letterbox of round 1 (six
+    // 24.5 KB CTAs): with a split that differs, the 32 SMs that host this kernel are closed to letterbox CTAs.
+    const int pct = h->tune.post_carveout >= 0 ? h->tune.post_carveout : 100;
     if (pct > 0) {
       CUDA_TRY(h, cudaFuncSetAttribute(k_post_track<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
       CUDA_TRY(h, cudaFuncSetAttribute(k_post_track<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
