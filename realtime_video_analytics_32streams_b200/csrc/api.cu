@@ -96,6 +96,7 @@ static int create_impl(b200va_ctx* h) {
   h->tune.dense_impl = env_int("B200VA_DENSE_IMPL");
   h->tune.dense_ctas_per_sm = env_int("B200VA_DENSE_CTAS");
   if (getenv("B200VA_LB_SMEM_FLOOR")) h->tune.lb_smem_floor = env_int("B200VA_LB_SMEM_FLOOR");
+  if (getenv("B200VA_DENSE_CARVEOUT")) h->tune.dense_carveout = env_int("B200VA_DENSE_CARVEOUT");
   if (getenv("B200VA_POST_CARVEOUT")) h->tune.post_carveout = env_int("B200VA_POST_CARVEOUT");
   REQUIRE(h, c.max_batch >= 1 && c.max_batch <= B200VA_MAX_BATCH, "max_batch must be in [1, %d]", B200VA_MAX_BATCH);
   REQUIRE(h, c.max_anchors >= 1 && c.max_anchors <= 262144, "max_anchors must be in [1, 262144]");

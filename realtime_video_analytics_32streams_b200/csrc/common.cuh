@@ -91,6 +91,7 @@ struct b200va_ctx {
     int pdl = 1;              // B200VA_PDL=0: no programmatic dependent launches
     int uniform_carveout = 0; // B200VA_UNIFORM_CARVEOUT=1: every tick kernel prefers the all-shared-memory split
     int lb_smem_floor = 33 * 1024;  // B200VA_LB_SMEM_FLOOR=bytes: least dynamic shared memory of a letterbox CTA (caps CTAs per SM, see preprocess.cu)
+    int dense_carveout = -1;  // B200VA_DENSE_CARVEOUT=pct: preferred carve-out of the dense-scene NMS kernels (-1: driver default)
     int post_carveout = -1;   // B200VA_POST_CARVEOUT=pct: preferred shared-memory carve-out of k_post_track (0: driver default)
     int dense_impl = 0;       // B200VA_DENSE_IMPL=1: dense scenes stay on the single-kernel NMS (k_sort_nms<true>); 2: every launch is 'dense'
     int dense_ctas_per_sm = 0; // B200VA_DENSE_CTAS=n: CTAs per SM of k_dense_pairs (default 8)

@@ -2112,6 +2112,11 @@ int postprocess_configure(b200va_ctx* h) {
     CUDA_TRY(h, cudaMalloc(&D->work, sizeof(int32_t)));
     CUDA_TRY(h, cudaMemset(D->work, 0, sizeof(int32_t)));
     CUDA_TRY(h, raise_dyn_smem(k_dense_resolve, dense_resolve_smem(D->max_cand)));
+    if (h->tune.dense_carveout >= 0) {  // B200VA_DENSE_CARVEOUT=pct (see the note on k_post_track's carve-out above)
+      CUDA_TRY(h, cudaFuncSetAttribute(k_dense_pairs, cudaFuncAttributePreferredSharedMemoryCarveout, h->tune.dense_carveout));
+      CUDA_TRY(h, cudaFuncSetAttribute(k_dense_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, h->tune.dense_carveout));
+      CUDA_TRY(h, cudaFuncSetAttribute(k_dense_resolve_track, cudaFuncAttributePreferredSharedMemoryCarveout, h->tune.dense_carveout));
+    }
     CUDA_TRY(h, raise_dyn_smem(k_dense_resolve_track,
                                std::min<size_t>(200 * 1024, std::max(dense_resolve_smem(D->max_cand),
                                                                      tracker_smem_bytes(std::min(h->cfg.max_tracks, kTrkSmemRowsMax))))));
