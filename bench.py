@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the pre + post + track hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--schedule 0|1|2] [--no-graph] [--no-cpu]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--schedule 0..6] [--no-graph] [--no-cpu]
 
 Workload at every N: each GPU serves 32 streams of 1080p BGR frames with a synthetic decoded
 YOLOv8 head [32, 84, 8400] (config 3 of BASELINE.json, the one the metric is quoted on); with
@@ -358,7 +358,7 @@ def run_gpu(args) -> None:
                             tracks=p_tracks, schedule=args.schedule) for k in range(N_SETS)]
 
     # one prepared b200va_tick per input set: decode -> NMS -> tracker on the library's second stream, letterbox on the
-    # caller's (schedule 1: it starts when the decode kernel is done and overlaps NMS + tracker); fork and join inside
+    # caller's (schedule 6 = 3 for this sparse workload: launched beside the decode kernel, overlapping NMS + tracker)
     plans = make_plans()
 
     # ---- parity of the timed computation (before anything is timed) -------------------------
@@ -678,7 +678,9 @@ def run_gpu(args) -> None:
                     "on the second stream (b200va_tick)",
                  5: "letterbox launched as a programmatic dependent of the decode kernel and waiting for it to drain "
                     "(griddepcontrol.wait), NMS + tracker on the second stream (b200va_tick)",
-                 4: "software-pipelined b200va_tick: decode + letterbox of step k beside NMS + tracker of step k-1"}
+                 4: "software-pipelined b200va_tick: decode + letterbox of step k beside NMS + tracker of step k-1",
+                 6: "automatic (b200va_tick schedule 6): sparse scenes -> letterbox launched beside the decode kernel as its "
+                    "programmatic dependent, NMS + tracker on the second stream; dense scenes -> letterbox after decode"}
         line = {"metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": K,
                 "warmup": warm, "ms_per_step": round(ms / K, 5), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",
@@ -735,8 +737,9 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--schedule", type=int, default=1, choices=[0, 1, 2, 3, 4, 5],
-                    help="b200va_tick schedule: 0 serial, 1 letterbox after decode (default), 2 fully parallel")
+    ap.add_argument("--schedule", type=int, default=6, choices=[0, 1, 2, 3, 4, 5, 6],
+                    help="b200va_tick schedule: 0 serial, 1 letterbox after decode, 2 fully parallel, 3 / 5 letterbox as the "
+                         "decode kernel's programmatic dependent, 4 software-pipelined, 6 automatic (default; see include/b200va.h)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-bind", action="store_true", help="N > 1: do not pin each rank to its GPU's NUMA-local cores")
     ap.add_argument("--no-cpu", action="store_true", help="skip the single-core CPU sample")

@@ -99,6 +99,7 @@ class TickArgs(C.Structure):
 
 SCHEDULE_SERIAL, SCHEDULE_PRE_AFTER_DECODE, SCHEDULE_PRE_PARALLEL, SCHEDULE_PRE_BESIDE_DECODE = 0, 1, 2, 3
 SCHEDULE_PRE_BEHIND_DECODE = 5  # like 3, the letterbox waits for the decode grid to drain (griddepcontrol.wait)
+SCHEDULE_AUTO = 6  # 3 while the scenes are sparse, 1 while the post-process reports dense frames (the default)
 SCHEDULE_SOFTWARE_PIPELINED = 4  # decode + letterbox of this call beside NMS + tracker of the previous call's head
 
 
@@ -710,7 +711,7 @@ class Handle:
                   head=None, metas=None, conf_thr: float = 0.25, iou_thr: float = 0.45, classes=None, layout=None,
                   filter_conf: Optional[float] = None, dets=None, score_mode: int = SCORE_REF_COMPAT,
                   nms_mode: int = NMS_AGNOSTIC, slots=None, tracker_cfg=None, det_scale=None, skip=None,
-                  tracks=None, schedule: int = SCHEDULE_PRE_AFTER_DECODE) -> TickPlan:
+                  tracks=None, schedule: int = SCHEDULE_AUTO) -> TickPlan:
         """Prepare a ``b200va_tick``: the letterbox of ``frames`` into ``net_out`` and the post-process
         of ``head`` into ``dets`` followed by the tracker update of ``slots`` into ``tracks``.  Either
         half may be omitted.  ``tracker_cfg`` = (max_age, min_hits, max_iou_distance)."""

@@ -11,7 +11,12 @@ extern "C" int b200va_tick(b200va_handle h, const b200va_tick_args* a, void* str
   if (!h || !a) return B200VA_ERR_INVALID;
   std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
-  REQUIRE(h, a->schedule >= 0 && a->schedule <= 5, "unknown schedule %d", a->schedule);
+  REQUIRE(h, a->schedule >= 0 && a->schedule <= 6, "unknown schedule %d", a->schedule);
+  // schedule 6 (auto): 3 while the scenes are sparse -- the letterbox is launched as a programmatic dependent of the
+  // decode kernel and fills the SMs as that drains (60.6 against 63.5 us on the 32 x 1080p tick) -- and 1 while the
+  // post-process reports dense frames: there the chain decode -> pairs -> resolve + tracker is the tick, and letterbox
+  // CTAs launched early take SMs from k_dense_pairs (0.142 against 0.129 ms)
+  const int schedule = a->schedule == 6 ? (h->nms_dense_ttl > 0 ? 1 : 3) : a->schedule;
   cudaStream_t main_st = (cudaStream_t)stream;
   const bool has_pre = a->frames != nullptr && a->batch > 0;
   const bool has_post = a->head != nullptr && a->head_batch > 0;
@@ -21,7 +26,7 @@ extern "C" int b200va_tick(b200va_handle h, const b200va_tick_args* a, void* str
   // latency-bound chain decode -> NMS -> tracker, which is what bounds schedules 1-3 (tools/timeline.py: 23 us of
   // decode, then 38 us of NMS + tracker slowed down by the letterbox CTAs they share SMs with), leaves the critical path.
   // Results lag one call: the tables of tick k are complete after call k + 1 (or a final call without a head).
-  const bool sched4 = a->schedule == 4 && (!has_post || (a->head_batch <= B200VA_LAUNCH_FRAMES && a->channels >= 5 && a->anchors > 0));
+  const bool sched4 = schedule == 4 && (!has_post || (a->head_batch <= B200VA_LAUNCH_FRAMES && a->channels >= 5 && a->anchors > 0));
   const bool pending = postprocess_has_pending(h);
   PhaseScope phase(h, B200VA_PHASE_TICK, main_st);
   int rc = B200VA_OK;
@@ -61,7 +66,7 @@ extern "C" int b200va_tick(b200va_handle h, const b200va_tick_args* a, void* str
     return rc;
   }
 
-  const bool fork = a->schedule != 0 && has_pre && (has_post || has_trk);
+  const bool fork = schedule != 0 && has_pre && (has_post || has_trk);
   // schedule 3: the decode kernel stays on the caller's stream and the letterbox follows it there as a programmatic
   // dependent that never waits: its CTAs start as soon as SM resources allow (see prefer_max_shared in common.cuh for
   // why that is only the decode's tail today); NMS + tracker move to the side stream behind an event recorded right
@@ -69,7 +74,7 @@ extern "C" int b200va_tick(b200va_handle h, const b200va_tick_args* a, void* str
   // schedule 5: the same launch, but the letterbox executes griddepcontrol.wait before its first load: the two HBM
   // kernels never share the bus (their mix is slower than their sequence, tools/membw.cu) and no launch latency
   // separates them.
-  const bool sched3 = (a->schedule == 3 || a->schedule == 5) && fork && has_post && a->head_batch <= B200VA_LAUNCH_FRAMES;
+  const bool sched3 = (schedule == 3 || schedule == 5) && fork && has_post && a->head_batch <= B200VA_LAUNCH_FRAMES;
   cudaStream_t post_st = (fork && !sched3) ? h->side_stream : main_st;
   if (fork && !sched3) {
     CUDA_TRY(h, cudaEventRecord(h->ev_fork, main_st));
@@ -79,7 +84,7 @@ extern "C" int b200va_tick(b200va_handle h, const b200va_tick_args* a, void* str
   // stream invalidates a CUDA-graph capture), so failures are collected in `rc` instead of returning early.
   bool tracked = false, tail_on_side = false;
   if (has_post) {
-    h->hook_after_decode = (fork && (a->schedule == 1 || sched3)) ? h->ev_decoded : nullptr;
+    h->hook_after_decode = (fork && (schedule == 1 || sched3)) ? h->ev_decoded : nullptr;
     h->hook_recorded = false;
     h->post_tail_stream = sched3 ? h->side_stream : nullptr;
     // sparse scenes: NMS and the tracker update of the same rows run as ONE kernel (k_post_track)
@@ -96,7 +101,7 @@ extern "C" int b200va_tick(b200va_handle h, const b200va_tick_args* a, void* str
   const bool joined = fork && post_st == h->side_stream;
   if (joined) note(cudaEventRecord(h->ev_join, post_st), "cudaEventRecord(join)");
   h->pdl_preprocess = sched3 && tail_on_side;
-  h->pdl_preprocess_wait = a->schedule == 5;
+  h->pdl_preprocess_wait = schedule == 5;
   if (rc == B200VA_OK && has_pre) {
     if (a->ev_pre_begin) note(cudaEventRecord((cudaEvent_t)a->ev_pre_begin, main_st), "cudaEventRecord(pre_begin)");
     if (rc == B200VA_OK)

@@ -56,7 +56,7 @@ def _check(h, want, net, tracks, t):
 
 
 @pytest.mark.parametrize("fused", [1, 0])
-@pytest.mark.parametrize("schedule", [0, 1, 2, 3, 5])
+@pytest.mark.parametrize("schedule", [0, 1, 2, 3, 5, 6])
 def test_tick_matches_oracle(schedule, fused, monkeypatch):
     """fused=1: NMS + tracker as one kernel (k_post_track, the default for sparse scenes); fused=0: two kernels
     chained by programmatic dependent launch.  Schedule 3 also launches the letterbox as a programmatic dependent
@@ -187,7 +187,7 @@ def test_tick_software_pipelined_graph_replay():
 
 
 @pytest.mark.parametrize("pdl", [1, 0])
-@pytest.mark.parametrize("schedule", [1, 3, 5])
+@pytest.mark.parametrize("schedule", [1, 3, 5, 6])
 def test_tick_graph_replay_matches_oracle(schedule, pdl, monkeypatch):
     import torch
     from realtime_video_analytics_32streams_b200 import _native as N

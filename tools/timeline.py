@@ -25,7 +25,7 @@ heads_np = np.stack([B.make_heads(s, SETS) for s in range(S)], axis=1)
 heads = [torch.from_numpy(heads_np[k]).to(dev) for k in range(SETS)]
 metas = (_native.Letterbox * S)(*[_native.letterbox_meta(B.H, B.W, *B.IN_HW) for _ in range(S)])
 out = {}
-for schedule in (1, 3, 4):
+for schedule in tuple(int(x) for x in os.environ.get("SCHEDULES", "1,3,4").split(",")):
     h = _native.Handle(device=0, max_batch=S, max_anchors=B.A, max_candidates=2048, max_dets=512, max_streams=S,
                        max_tracks=int(os.environ.get("MAX_TRACKS", 1024)))
     h.lib.b200va_debug_read.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.c_int]
