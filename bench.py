@@ -679,8 +679,9 @@ def run_gpu(args) -> None:
                  5: "letterbox launched as a programmatic dependent of the decode kernel and waiting for it to drain "
                     "(griddepcontrol.wait), NMS + tracker on the second stream (b200va_tick)",
                  4: "software-pipelined b200va_tick: decode + letterbox of step k beside NMS + tracker of step k-1",
-                 6: "automatic (b200va_tick schedule 6): sparse scenes -> letterbox launched beside the decode kernel as its "
-                    "programmatic dependent, NMS + tracker on the second stream; dense scenes -> letterbox after decode"}
+                 6: "automatic (b200va_tick schedule 6): >= 24 sparse frames -> letterbox launched beside the decode kernel as "
+                    "its programmatic dependent, NMS + tracker on the second stream; small batches and dense scenes -> "
+                    "letterbox after decode"}
         line = {"metric": METRIC, "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": K,
                 "warmup": warm, "ms_per_step": round(ms / K, 5), "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32", "data": "synthetic",

@@ -419,8 +419,10 @@ B200VA_API int b200va_postprocess_ultralytics(b200va_handle h, const float* head
  *           The result tables of call k are complete after call k + 1 has run (or after a final call with neither
  *           frames nor head, which only drains the pipeline); `dets`, `tracks`, `new_counts` and the buffers they
  *           point to must stay valid and untouched until then.  A call with another schedule first runs what is owed.
- *           6 = automatic: 3 while the scenes are sparse, 1 while the post-process reports dense frames (more than 256
- *           candidates in a frame lately), where letterbox CTAs launched early would take SMs from the NMS chain.
+ *           6 = automatic: 3 for batches of 24 frames or more while the scenes are sparse (the letterbox is the long
+ *           pole), otherwise 1: small batches (the chain decode -> NMS -> tracker is, and 3 starts it later) and while
+ *           the post-process reports dense frames (more than 256 candidates in a frame lately), where letterbox CTAs
+ *           launched early would take SMs from the NMS chain.
  * Sparse scenes run NMS and the tracker update of the same rows as ONE kernel (a 256-thread CTA per stream);
  * otherwise the two kernels are chained by programmatic dependent launch.
  * ev_pre_begin / ev_pre_end: optional cudaEvent_t recorded on `stream` around the letterbox launch. */

@@ -99,7 +99,7 @@ class TickArgs(C.Structure):
 
 SCHEDULE_SERIAL, SCHEDULE_PRE_AFTER_DECODE, SCHEDULE_PRE_PARALLEL, SCHEDULE_PRE_BESIDE_DECODE = 0, 1, 2, 3
 SCHEDULE_PRE_BEHIND_DECODE = 5  # like 3, the letterbox waits for the decode grid to drain (griddepcontrol.wait)
-SCHEDULE_AUTO = 6  # 3 while the scenes are sparse, 1 while the post-process reports dense frames (the default)
+SCHEDULE_AUTO = 6  # 3 for large sparse batches, 1 for small batches and dense scenes (the default; include/b200va.h)
 SCHEDULE_SOFTWARE_PIPELINED = 4  # decode + letterbox of this call beside NMS + tracker of the previous call's head
 
 

@@ -12,11 +12,14 @@ extern "C" int b200va_tick(b200va_handle h, const b200va_tick_args* a, void* str
   std::lock_guard<std::recursive_mutex> lock(h->mu);
   DeviceGuard guard(h->cfg.device);
   REQUIRE(h, a->schedule >= 0 && a->schedule <= 6, "unknown schedule %d", a->schedule);
-  // schedule 6 (auto): 3 while the scenes are sparse -- the letterbox is launched as a programmatic dependent of the
-  // decode kernel and fills the SMs as that drains (60.6 against 63.5 us on the 32 x 1080p tick) -- and 1 while the
-  // post-process reports dense frames: there the chain decode -> pairs -> resolve + tracker is the tick, and letterbox
-  // CTAs launched early take SMs from k_dense_pairs (0.142 against 0.129 ms)
-  const int schedule = a->schedule == 6 ? (h->nms_dense_ttl > 0 ? 1 : 3) : a->schedule;
+  // schedule 6 (auto).  Large sparse batches take 3: the letterbox is the long pole, and launched as a programmatic
+  // dependent of the decode kernel it fills the SMs as that drains (60.6 against 63.5 us on the 32 x 1080p tick).  Up to
+  // ~16 streams the chain decode -> NMS + tracker is as long as the letterbox, and schedule 3 starts it 2-4 us later (it
+  // moves to the second stream behind an event): 1 there (4 streams: 20.2 against 21.3 us, 1 stream: 15.3 against
+  // 16.5).  Dense frames (the post-process saw more than 256 candidates lately) take 1 as well: the chain decode ->
+  // pairs -> resolve + tracker is the tick, and letterbox CTAs launched early take SMs from k_dense_pairs (0.142
+  // against 0.129 ms).
+  const int schedule = a->schedule == 6 ? ((h->nms_dense_ttl > 0 || a->batch < 24) ? 1 : 3) : a->schedule;
   cudaStream_t main_st = (cudaStream_t)stream;
   const bool has_pre = a->frames != nullptr && a->batch > 0;
   const bool has_post = a->head != nullptr && a->head_batch > 0;

@@ -73,7 +73,7 @@ def _graph_tick_ms(h, plans, reps):
     return e0.elapsed_time(e1) / reps
 
 
-def simple(name, B, hw, n_obj, dup, steps=30, conf=0.35, iou=0.5, trk=(30, 1, 0.5), max_tracks=4096, schedule=3):
+def simple(name, B, hw, n_obj, dup, steps=30, conf=0.35, iou=0.5, trk=(30, 1, 0.5), max_tracks=4096, schedule=6):
     H, W = hw
     dev = _dev()
     h = _native.Handle(device=dev.index, max_batch=max(B, 1), max_anchors=8400, max_candidates=4096, max_dets=1024,
