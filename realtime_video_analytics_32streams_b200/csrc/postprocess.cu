@@ -1502,13 +1502,14 @@ __global__ void __launch_bounds__(kNmsThreadsSmall) k_post_track(const __grid_co
 // busy, 113-130 us).  Greedy NMS is the unique solution of  kept_i = no kept j ahead of i (in score order) suppresses i,
 // and that recurrence needs neither a sorted array nor a sequential sweep:
 //   k_dense_pairs    every SM: the suppression predicate of ALL unordered pairs of a frame's candidates, in the order
-//                    decode left them (slot order, no sort).  A work item is 128 rows x 64 columns of the upper
-//                    triangle, handed out to single warps through an atomic counter; a thread owns four rows (a 16-byte column broadcast
-//                    from shared memory costs four cycles of its pipe however many lanes want the same address, so it
-//                    has to feed four tests), four compares decide "the boxes overlap at all" branch-free, the
-//                    overlapping pairs of a warp (2 % of all) are queued in shared memory and the IoU formula then runs
-//                    over the queue with every lane busy.  A hit appends the box with the larger key (the one greedy
-//                    NMS meets first) to the suppressor list of the other one; hits are collected across items and
+//                    decode left them (slot order, no sort).  A work item is 128 rows x 32 columns of the upper
+//                    triangle, handed to single warps (the first by warp number, the rest through an atomic counter
+//                    fetched one item ahead); a thread owns four rows (a 16-byte column broadcast from shared memory
+//                    costs four cycles of its pipe however many lanes want the same address, so it has to feed four
+//                    tests); "the boxes overlap at all" is the sign of four differences, branch-free; the overlapping
+//                    pairs of a warp (0.4 % of all in config 5) are queued in shared memory and the IoU formula then
+//                    runs over the queue with every lane busy.  A hit appends the box with the larger key (the one
+//                    greedy NMS meets first) to the suppressor list of the other one; hits are collected across items and
 //                    recorded 128 at a time (their key loads and atomics are dependent round trips to L2).  Measured and
 //                    dropped: 64- and 128-column items, two rows per thread, 10 / 12 CTAs per SM at 48 / 40 registers,
 //                    rows and columns of the next item prefetched with cp.async into a second buffer (7 CTAs per SM).
@@ -1517,6 +1518,7 @@ __global__ void __launch_bounds__(kNmsThreadsSmall) k_post_track(const __grid_co
 //                    only the KEPT boxes (~300 of 1800) are ordered by key -- rank among the kept = output position.
 // A frame with a full suppressor list (more than kNbrCap boxes ahead of one candidate suppress it) or a dependency chain
 // longer than kResolveRounds falls back to the single-CTA path inside k_dense_resolve (same results, slower).
+// k_dense_resolve_track: the same resolution followed by the stream's tracker update in the same CTA (b200va_tick).
 // Results are those of the single-kernel path bit for bit: same predicate (IEEE add / mul / min / max commute, so the
 // predicate is symmetric in its two boxes), same greedy recurrence, same tie rule (the keys are unique).
 struct DenseNms {
